@@ -1,0 +1,370 @@
+"""NumPy restatement of the reference hot path (TEST INFRASTRUCTURE -- see oracle/__init__.py).
+
+Every function follows the reference file:line it cites (paths relative to
+/root/reference/algorithm).  Arithmetic runs in the dtype of the inputs: float32 mirrors
+the reference's TF1 CPU graph, float64 is the high-precision anchor the fp32 results are
+themselves checked against.  Forward functions mirror the reference op-for-op (including
+its quirks); backward functions are the analytic gradients of those forwards and are
+cross-checked against torch.autograd(float64) in tests/test_oracle.py.
+
+Weights are always explicit arguments: the reference never seeds its initialisers, so
+parity is defined on injected weights.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Row L -- embedding lookup  (fc.input_layer over embedding columns)
+# --------------------------------------------------------------------------------------
+
+
+def vocab_ids(keys: Sequence[bytes], vocab: Sequence[bytes]) -> np.ndarray:
+    """String key -> vocabulary line index, OOV (and b'') -> -1.
+
+    ``fc.categorical_column_with_vocabulary_file(key, file)`` with the defaults the
+    reference uses (DeepFM/deepfm.py:56-64): ``num_oov_buckets=0, default_value=None`` =>
+    id = 0-based line number, out-of-vocabulary => -1  [TF-internal, SURVEY A.4].
+    Vocabulary files hold one token per line (dataset/wechat_algo_data1/DataGenerator.py:206-210).
+    """
+    table = {}
+    for i, tok in enumerate(vocab):
+        table.setdefault(tok, i)  # first occurrence wins, like a hash-table init from file
+    return np.asarray([table.get(k, -1) for k in keys], dtype=np.int64)
+
+
+def embedding_lookup(table: np.ndarray, ids: np.ndarray, field_row_offset: np.ndarray) -> np.ndarray:
+    """Single-valued per-field lookup -> (B, F, D).
+
+    ``fc.input_layer(features, [embedding_column(col, D)])`` for one id per row
+    (DeepFM/deepfm.py:187-190, xDeepFM/xdeepfm.py:158,167):
+    ``safe_embedding_lookup_sparse(combiner='mean')`` on a one-element bag is the row itself
+    (bit-exact copy); id < 0 is pruned => empty bag => **zero vector**  [TF-internal, SURVEY A.5].
+
+    ``table`` is the concatenation of the F per-field tables, field f owning rows
+    ``field_row_offset[f] : field_row_offset[f+1]``; ``ids`` are per-field local ids (B, F).
+    """
+    B, F = ids.shape
+    D = table.shape[1]
+    out = np.zeros((B, F, D), dtype=table.dtype)
+    for f in range(F):
+        valid = ids[:, f] >= 0
+        out[valid, f, :] = table[field_row_offset[f] + ids[valid, f]]
+    return out
+
+
+def bag_lookup_mean(table: np.ndarray, ids: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """Multi-valued lookup with combiner='mean' -> (B, D).
+
+    ``embedding_column(col, D, combiner='mean')`` over a VarLen feature, e.g.
+    ``manual_tag_list`` (DCN/dcn.py:98,103; xDeepFM/xdeepfm.py:103,108).
+    [TF-internal, SURVEY A.5]: (1) drop ids < 0; (2) sum the remaining rows in bag order and
+    divide by their count; (3) a bag with no valid id yields zeros.
+    ``ids`` is the flat CSR value array, bag b = ids[offsets[b]:offsets[b+1]].
+    """
+    B = offsets.shape[0] - 1
+    D = table.shape[1]
+    out = np.zeros((B, D), dtype=table.dtype)
+    for b in range(B):
+        acc = np.zeros((D,), dtype=table.dtype)
+        n = 0
+        for i in ids[offsets[b]:offsets[b + 1]]:
+            if i >= 0:
+                acc = acc + table[i]
+                n += 1
+        if n:
+            out[b] = acc / table.dtype.type(n)
+    return out
+
+
+def embedding_lookup_bwd_dense(V: int, ids: np.ndarray, field_row_offset: np.ndarray,
+                               row_grads: np.ndarray) -> np.ndarray:
+    """Densify the IndexedSlices gradient of ``embedding_lookup`` (duplicates summed, ids<0 dropped).
+
+    TF's gradient of the gather is ``IndexedSlices(values=(B*F, D), indices)``; the optimizer
+    sums duplicate indices before applying [TF-internal, SURVEY A.8].  float64 accumulate.
+    """
+    B, F = ids.shape
+    D = row_grads.shape[-1]
+    g = np.zeros((V, D), dtype=np.float64)
+    for f in range(F):
+        valid = ids[:, f] >= 0
+        np.add.at(g, field_row_offset[f] + ids[valid, f], row_grads[valid, f, :].astype(np.float64))
+    return g
+
+
+# --------------------------------------------------------------------------------------
+# Row FM2 -- DeepFM second-order term (inline in deepfm_model_fn)
+# --------------------------------------------------------------------------------------
+
+
+def fm2_fwd(e: np.ndarray) -> np.ndarray:
+    """FM second-order logit (B, 1) from the F field embeddings e: (B, F, K).
+
+    DeepFM/deepfm.py:184-200: ``square(add_n(e_f))``, ``add_n(square(e_f))``,
+    ``reduce_sum(0.5 * (a - b), axis=1, keepdims=True)``; add_n accumulates in list order.
+    """
+    F = e.shape[1]
+    s = e[:, 0, :].copy()
+    q = np.square(e[:, 0, :])
+    for f in range(1, F):
+        s = s + e[:, f, :]
+        q = q + np.square(e[:, f, :])
+    half = e.dtype.type(0.5)
+    return np.sum(half * (np.square(s) - q), axis=1, keepdims=True)
+
+
+def fm2_bwd(e: np.ndarray, g: np.ndarray) -> np.ndarray:
+    """d(fm2)/d(e) * g : ``de[b,f,:] = g[b] * (S[b,:] - e[b,f,:])`` with S = sum_f e."""
+    s = e.sum(axis=1, keepdims=True)
+    return g.reshape(-1, 1, 1) * (s - e)
+
+
+def fm2_pairwise(e: np.ndarray) -> np.ndarray:
+    """Identity check: FM2 == sum_{i<j} <e_i, e_j> (float64)."""
+    e = e.astype(np.float64)
+    F = e.shape[1]
+    out = np.zeros((e.shape[0], 1))
+    for i, j in itertools.combinations(range(F), 2):
+        out[:, 0] += np.sum(e[:, i, :] * e[:, j, :], axis=1)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Row CROSS -- DCN cross layer
+# --------------------------------------------------------------------------------------
+
+
+def cross_layer_fwd(x0: np.ndarray, xl: np.ndarray, wl: np.ndarray, bl: np.ndarray) -> np.ndarray:
+    """One cross layer.  DCN/cross_layer.py:21-24; wl, bl have shape (d, 1) (:18-19)."""
+    xl_wl = xl @ wl                      # (B, 1)
+    x0_xl_wl = x0 * xl_wl                # (B, d)
+    out = x0_xl_wl + bl.T                # + (1, d)
+    return out + xl
+
+
+def cross_stack_fwd(x0: np.ndarray, ws: np.ndarray, bs: np.ndarray) -> List[np.ndarray]:
+    """The stack loop of DCN/dcn.py:157-160.  ws, bs: (L, d).  Returns [x_0, x_1, ..., x_L]."""
+    xs = [x0]
+    for l in range(ws.shape[0]):
+        xs.append(cross_layer_fwd(x0, xs[-1], ws[l][:, None], bs[l][:, None]))
+    return xs
+
+
+def cross_stack_bwd(x0: np.ndarray, ws: np.ndarray, bs: np.ndarray, g_out: np.ndarray
+                    ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Gradient of the stack w.r.t. (x0, ws, bs) given dL/dx_L.  Returns (dx0, dws, dbs)."""
+    xs = cross_stack_fwd(x0, ws, bs)
+    L = ws.shape[0]
+    g = g_out.copy()
+    dx0 = np.zeros_like(x0)
+    dws = np.zeros_like(ws)
+    dbs = np.zeros_like(bs)
+    for l in range(L - 1, -1, -1):
+        xl = xs[l]
+        s = xl @ ws[l]                                   # (B,)
+        t = np.sum(g * x0, axis=1)                       # (B,)
+        dx0 += g * s[:, None]
+        dws[l] = xl.T @ t
+        dbs[l] = g.sum(axis=0)
+        g = g + t[:, None] * ws[l][None, :]
+    return dx0 + g, dws, dbs
+
+
+# --------------------------------------------------------------------------------------
+# Row CIN -- xDeepFM compressed interaction network layer
+# --------------------------------------------------------------------------------------
+
+
+def cin_layer_fwd(x0: np.ndarray, xk: np.ndarray, filt: np.ndarray) -> np.ndarray:
+    """One CIN layer.  xDeepFM/cin_layer.py:17-28.
+
+    x0 (B, m, D), xk (B, hk, D), filt (hk*m, hk_1) == the conv1d filter (1, hk*m, hk_1)[0].
+    outer[b,d,i,j] = xk[b,i,d] * x0[b,j,d] (:21), flattened with index i*m+j (:22),
+    conv1d(width 1, VALID) == matmul over the last axis (:25-27), transposed to (B, hk_1, D) (:28).
+    The outer tensor is materialised exactly like the reference does.
+    """
+    B, m, D = x0.shape
+    hk = xk.shape[1]
+    outer = np.einsum('bik,bjk->bkij', xk, x0).reshape(B, D, hk * m)
+    xk_1 = outer @ filt                                   # (B, D, hk_1)
+    return np.transpose(xk_1, (0, 2, 1))
+
+
+def cin_layer_bwd(x0: np.ndarray, xk: np.ndarray, filt: np.ndarray, g: np.ndarray
+                  ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Gradients (dx0, dxk, dfilt) of ``cin_layer_fwd`` given g = dL/d(out) (B, hk_1, D)."""
+    B, m, D = x0.shape
+    hk = xk.shape[1]
+    gt = np.transpose(g, (0, 2, 1))                       # (B, D, hk_1)
+    outer = np.einsum('bik,bjk->bkij', xk, x0).reshape(B, D, hk * m)
+    dfilt = np.einsum('bdz,bdn->zn', outer, gt)
+    dz = (gt @ filt.T).reshape(B, D, hk, m)               # (B, D, hk, m)
+    dxk = np.einsum('bdij,bjd->bid', dz, x0)
+    dx0 = np.einsum('bdij,bid->bjd', dz, xk)
+    return dx0, dxk, dfilt
+
+
+def cin_stack_fwd(x0: np.ndarray, filters: Sequence[np.ndarray]) -> Tuple[List[np.ndarray], np.ndarray]:
+    """xDeepFM/xdeepfm.py:166-174: every layer's full output feeds the next layer and the pooled sum.
+
+    Returns ([X^1, X^2, ...], p_plus (B, sum_k h_k)).
+    """
+    xs, xk = [], x0
+    for filt in filters:
+        xk = cin_layer_fwd(x0, xk, filt)
+        xs.append(xk)
+    p_plus = np.concatenate([x.sum(axis=-1) for x in xs], axis=-1)
+    return xs, p_plus
+
+
+# --------------------------------------------------------------------------------------
+# Row DIN-ATT -- DIN attention unit
+# --------------------------------------------------------------------------------------
+
+DIN_PAD = -2 ** 32 + 1   # DIN/din_attention.py:31 -- Python precedence: -(2**32) + 1
+
+
+def din_attention_fwd(query: np.ndarray, keys: np.ndarray, keys_length: np.ndarray,
+                      w1, b1, w2, b2, w3, b3, is_softmax: bool = False, return_cache: bool = False):
+    """DIN/din_attention.py:17-43.
+
+    query (B,H); keys (B,T,H); keys_length (B,); dense f1_att (4H->64, relu), f2_att (64->32, relu),
+    f3_att (32->1).  Non-softmax (default): weights * mask (:37-38).  Softmax: masked scores are
+    filled with -2**32+1, THEN divided by sqrt(H), then softmax over T (:31-35).
+    """
+    dt = query.dtype
+    B, T, H = keys.shape
+    q = np.broadcast_to(query[:, None, :], (B, T, H))                    # tile + reshape (:18-19)
+    cross = np.concatenate([q, keys, q - keys, q * keys], axis=-1)       # (:20)
+    h1 = np.maximum(cross @ w1 + b1, 0)                                  # (:21)
+    h2 = np.maximum(h1 @ w2 + b2, 0)                                     # (:22)
+    s = h2 @ w3 + b3                                                     # (B,T,1) (:23)
+    mask = (np.arange(T)[None, :] < keys_length[:, None])[..., None]     # (:27-28)
+    if is_softmax:
+        pad = np.ones_like(s) * dt.type(DIN_PAD)
+        s2 = np.where(mask, s, pad)
+        s2 = s2 / dt.type(H ** 0.5)
+        s2 = s2 - s2.max(axis=1, keepdims=True)
+        ex = np.exp(s2)
+        w = ex / ex.sum(axis=1, keepdims=True)
+    else:
+        w = s * mask.astype(dt)
+    out = np.matmul(np.transpose(w, (0, 2, 1)), keys)[:, 0, :]           # (:40-41)
+    if return_cache:
+        return out, dict(cross=cross, h1=h1, h2=h2, w=w, mask=mask)
+    return out
+
+
+def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, is_softmax=False):
+    """Gradients of ``din_attention_fwd`` given g_out (B,H).
+
+    Returns dict(query, keys, w1, b1, w2, b2, w3, b3).
+    """
+    dt = query.dtype
+    B, T, H = keys.shape
+    _, c = din_attention_fwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, is_softmax, True)
+    cross, h1, h2, w, mask = c['cross'], c['h1'], c['h2'], c['w'], c['mask']
+    dw = np.einsum('bh,bth->bt', g_out, keys)[..., None]                  # (B,T,1)
+    dkeys = w * g_out[:, None, :]
+    if is_softmax:
+        ds2 = w * (dw - np.sum(w * dw, axis=1, keepdims=True))
+        ds = np.where(mask, ds2 / dt.type(H ** 0.5), 0).astype(dt)
+    else:
+        ds = dw * mask.astype(dt)
+    dw3 = np.einsum('btk,bto->ko', h2, ds)
+    db3 = ds.sum(axis=(0, 1))
+    dh2 = (ds @ w3.T) * (h2 > 0)
+    dw2 = np.einsum('btk,bto->ko', h1, dh2)
+    db2 = dh2.sum(axis=(0, 1))
+    dh1 = (dh2 @ w2.T) * (h1 > 0)
+    dw1 = np.einsum('btk,bto->ko', cross, dh1)
+    db1 = dh1.sum(axis=(0, 1))
+    dcross = dh1 @ w1.T                                                   # (B,T,4H)
+    dq_a, dk_a, dqmk, dqk = np.split(dcross, 4, axis=-1)
+    q = query[:, None, :]
+    dquery = (dq_a + dqmk + dqk * keys).sum(axis=1)
+    dkeys = dkeys + dk_a - dqmk + dqk * q
+    return dict(query=dquery, keys=dkeys, w1=dw1, b1=db1, w2=dw2, b2=db2, w3=dw3, b3=db3)
+
+
+# --------------------------------------------------------------------------------------
+# Row SENET / BILINEAR -- FiBiNET
+# --------------------------------------------------------------------------------------
+
+
+def senet_fwd(x: np.ndarray, w1: np.ndarray, w2: np.ndarray) -> np.ndarray:
+    """FiBiNET/senet.py:26-34.  x (B,F,K); w1 (F,r); w2 (r,F); no bias.
+
+    NB ``r = embedding_dim // reduction_ratio`` (:18) -- reduced from K, not F (reference quirk).
+    """
+    z = x.mean(axis=-1)
+    a = np.maximum(z @ w1, 0)
+    a = np.maximum(a @ w2, 0)
+    return x * a[..., None]
+
+
+def senet_bwd(x, w1, w2, g):
+    """Gradients (dx, dw1, dw2) of ``senet_fwd``."""
+    K = x.shape[-1]
+    z = x.mean(axis=-1)
+    a1 = np.maximum(z @ w1, 0)
+    a2 = np.maximum(a1 @ w2, 0)
+    da2 = np.sum(g * x, axis=-1) * (a2 > 0)
+    dw2 = a1.T @ da2
+    da1 = (da2 @ w2.T) * (a1 > 0)
+    dw1 = z.T @ da1
+    dz = da1 @ w1.T
+    dx = g * a2[..., None] + dz[..., None] / x.dtype.type(K)
+    return dx, dw1, dw2
+
+
+def bilinear_pairs(F: int) -> List[Tuple[int, int]]:
+    """``itertools.combinations(range(F-1), 2)`` -- the reference pairs only fields 0..F-2
+    (FiBiNET/bilinear_interaction_layer.py:24,29,33), giving (F-1)(F-2)/2 outputs."""
+    return list(itertools.combinations(range(F - 1), 2))
+
+
+def bilinear_fwd(x: np.ndarray, w: np.ndarray, type: str) -> np.ndarray:
+    """FiBiNET/bilinear_interaction_layer.py:21-40.  x (B,F,K) -> (B,P,K).
+
+    all: w (K,K); each: w (F-1,K,K); interaction: w (F(F-1)/2,K,K) of which the first P are used.
+    """
+    B, F, K = x.shape
+    pairs = bilinear_pairs(F)
+    if type == 'all':
+        vw = x @ w
+        p = [vw[:, i, :] * x[:, j, :] for i, j in pairs]
+    elif type == 'each':
+        vw = [x[:, i, :] @ w[i] for i in range(F - 1)]
+        p = [vw[i] * x[:, j, :] for i, j in pairs]
+    elif type == 'interaction':
+        p = [(x[:, i, :] @ w[k]) * x[:, j, :] for k, (i, j) in enumerate(pairs)]
+    else:
+        raise ValueError(f"Bilinear Interaction type must be in ['all','each','interaction'], got '{type}'")
+    return np.stack(p, axis=1)
+
+
+def bilinear_bwd(x, w, type, g):
+    """Gradients (dx, dw) of ``bilinear_fwd`` given g (B,P,K)."""
+    B, F, K = x.shape
+    pairs = bilinear_pairs(F)
+    dx = np.zeros_like(x)
+    dw = np.zeros_like(w)
+    for k, (i, j) in enumerate(pairs):
+        wi = w if type == 'all' else (w[i] if type == 'each' else w[k])
+        vw = x[:, i, :] @ wi
+        dvw = g[:, k, :] * x[:, j, :]
+        dx[:, j, :] += g[:, k, :] * vw
+        dx[:, i, :] += dvw @ wi.T
+        gw = x[:, i, :].T @ dvw
+        if type == 'all':
+            dw += gw
+        elif type == 'each':
+            dw[i] += gw
+        else:
+            dw[k] += gw
+    return dx, dw

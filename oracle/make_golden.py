@@ -1,0 +1,243 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN LAYER FILES (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The five interaction-layer files are imported verbatim from /root/reference/algorithm with
+``oracle/tf1_shim`` standing in for TensorFlow 1.14 (see that package's docstring for what
+this does and does not pin).  Each fixture stores the seeded inputs, the injected weights
+(under the TF variable names the reference created), and the reference outputs computed in
+float32 (like the reference) and float64 (anchor).  FM2 and the lookup have no importable
+reference function (inline code / TF-internal); their fixtures come from
+``oracle/layers_np.py`` and are marked ``source='restated'``.
+
+The GPU box has no /root/reference: tests read only the committed .npz files.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference/algorithm"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
+sys.path.insert(0, ROOT)
+import tensorflow as tf  # noqa: E402  (the shim)
+
+assert "tf1_shim" in tf.__file__, "the TF shim must shadow any real tensorflow"
+
+
+def _load(relpath, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+ref_cross = _load("DCN/cross_layer.py", "ref_cross_layer")
+ref_cin = _load("xDeepFM/cin_layer.py", "ref_cin_layer")
+ref_din = _load("DIN/din_attention.py", "ref_din_attention")
+ref_senet = _load("FiBiNET/senet.py", "ref_senet")
+ref_bilinear = _load("FiBiNET/bilinear_interaction_layer.py", "ref_bilinear")
+
+
+def trunc_normal(rng, shape, std):
+    x = rng.standard_normal(shape)
+    bad = np.abs(x) > 2
+    while bad.any():
+        x[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(x) > 2
+    return (x * std).astype(np.float32)
+
+
+def glorot(rng, shape, fan_in=None, fan_out=None):
+    fan_in = fan_in or shape[-2]
+    fan_out = fan_out or shape[-1]
+    lim = (6.0 / (fan_in + fan_out)) ** 0.5
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def run_both(fn, variables):
+    """Run ``fn`` (which builds the reference layer) in float32 and float64."""
+    outs = {}
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        tf.reset(dtype=dt, variables=variables)
+        outs[tag] = fn(dt)
+    created = tf.created_variables()
+    return outs, created
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def gen_cross():
+    rng = np.random.default_rng(1234)
+    for d, L, B in ((82, 1, 8), (82, 3, 8), (480, 3, 6)):
+        x0 = trunc_normal(rng, (B, d), 0.25)
+        variables = {}
+        for i in range(L):
+            variables[f"cross_part/wl_{i}"] = glorot(rng, (d, 1))
+            variables[f"cross_part/bl_{i}"] = glorot(rng, (d, 1))    # glorot, NOT zeros (cross_layer.py:18-19)
+
+        def fn(dt):
+            x0_t = tf.Tensor(x0.astype(dt))
+            with tf.variable_scope("cross_part"):              # DCN/dcn.py:156-160
+                vec = x0_t
+                for i in range(L):
+                    vec = ref_cross.cross_layer(x0=x0_t, xl=vec, index=i)
+            return vec.a
+
+        outs, created = run_both(fn, variables)
+        assert all(created[k] == (d, 1) for k in created)
+        ws = np.stack([variables[f"cross_part/wl_{i}"][:, 0] for i in range(L)])
+        bs = np.stack([variables[f"cross_part/bl_{i}"][:, 0] for i in range(L)])
+        save(f"cross_d{d}_L{L}", x0=x0, ws=ws, bs=bs, out_f32=outs["f32"], out_f64=outs["f64"],
+             source="reference:DCN/cross_layer.py via tf1_shim")
+
+
+def gen_cin():
+    rng = np.random.default_rng(2345)
+    for m, D, maps, B in ((8, 8, ("50", "50", "50"), 4), (30, 16, ("128", "128"), 3), (8, 16, ("17",), 5)):
+        x0 = trunc_normal(rng, (B, m, D), 1.0 / np.sqrt(D))
+        variables, hk = {}, m
+        for i, h in enumerate(maps):
+            h = int(h)
+            variables[f"cin_part/cin_layer_{i + 1}_filter"] = glorot(rng, (1, hk * m, h), fan_in=hk * m, fan_out=h)
+            hk = h
+
+        def fn(dt):
+            x0_t = tf.Tensor(x0.astype(dt))
+            outs = []
+            with tf.variable_scope("cin_part"):                # xDeepFM/xdeepfm.py:166-174
+                xk = x0_t
+                for i, h in enumerate(maps):
+                    # layer widths reach model_fn as *strings* (xdeepfm.py:253); the reference's
+                    # tf.get_variable accepts that because TF int()s shape entries.
+                    xk = ref_cin.cin_layer(x0_t, xk, int(h), i + 1)
+                    outs.append(xk)
+                p_plus = tf.concat([tf.reduce_sum(x, axis=-1) for x in outs], axis=-1)
+            return [o.a for o in outs] + [p_plus.a]
+
+        outs, created = run_both(fn, variables)
+        arrays = dict(x0=x0, n_layers=len(maps), source="reference:xDeepFM/cin_layer.py via tf1_shim")
+        for i in range(len(maps)):
+            arrays[f"filter_{i + 1}"] = variables[f"cin_part/cin_layer_{i + 1}_filter"][0]
+            arrays[f"x{i + 1}_f32"] = outs["f32"][i]
+            arrays[f"x{i + 1}_f64"] = outs["f64"][i]
+        arrays["p_plus_f32"] = outs["f32"][-1]
+        arrays["p_plus_f64"] = outs["f64"][-1]
+        save(f"cin_m{m}_D{D}_" + "x".join(maps), **arrays)
+
+
+def gen_din():
+    rng = np.random.default_rng(3456)
+    cases = (("T3_smoke", 2, 3, 4, np.array([0, 1])),          # the reference's own __main__ case (din_attention.py:46-54)
+             ("T1", 3, 1, 16, np.array([0, 1, 1])),
+             ("T50", 6, 50, 16, np.array([0, 1, 17, 49, 50, 50])))
+    for tag, B, T, H, lens in cases:
+        q = trunc_normal(rng, (B, H), 0.25)
+        keys = trunc_normal(rng, (B, T, H), 0.25)
+        variables = {
+            "attention_part/f1_att/kernel": glorot(rng, (4 * H, 64)),
+            "attention_part/f1_att/bias": (rng.standard_normal(64) * 0.1).astype(np.float32),
+            "attention_part/f2_att/kernel": glorot(rng, (64, 32)),
+            "attention_part/f2_att/bias": (rng.standard_normal(32) * 0.1).astype(np.float32),
+            "attention_part/f3_att/kernel": glorot(rng, (32, 1)),
+            "attention_part/f3_att/bias": (rng.standard_normal(1) * 0.1).astype(np.float32),
+        }
+        arrays = dict(query=q, keys=keys, keys_length=lens.astype(np.int64),
+                      source="reference:DIN/din_attention.py via tf1_shim")
+        for k, v in variables.items():
+            arrays[k.split("/", 1)[1].replace("/", "_")] = v
+        for soft in (False, True):
+            def fn(dt):
+                with tf.variable_scope("attention_part"):      # DIN/din.py:216-218
+                    return ref_din.din_attention(tf.Tensor(q.astype(dt)), tf.Tensor(keys.astype(dt)),
+                                                 tf.Tensor(lens), is_softmax=soft).a
+            outs, _ = run_both(fn, variables)
+            arrays[f"out_softmax{int(soft)}_f32"] = outs["f32"]
+            arrays[f"out_softmax{int(soft)}_f64"] = outs["f64"]
+        save(f"din_{tag}", **arrays)
+
+
+def gen_fibinet():
+    rng = np.random.default_rng(4567)
+    for F, K, ratio, B in ((8, 8, 2, 5), (30, 16, 2, 3)):
+        x = trunc_normal(rng, (B, F, K), 1.0 / np.sqrt(K))
+        r = K // ratio
+        variables = {"senet_part/senet_w1": glorot(rng, (F, r)), "senet_part/senet_w2": glorot(rng, (r, F))}
+
+        def fn(dt):
+            with tf.variable_scope("senet_part"):              # FiBiNET/fibinet.py:171-174
+                return ref_senet.senet(tf.Tensor(x.astype(dt)), embedding_dim=K, reduction_ratio=ratio).a
+        outs, created = run_both(fn, variables)
+        assert created["senet_part/senet_w1"] == (F, r)        # reduced from K, not F (senet.py:18)
+        arrays = dict(x=x, senet_w1=variables["senet_part/senet_w1"], senet_w2=variables["senet_part/senet_w2"],
+                      senet_f32=outs["f32"], senet_f64=outs["f64"],
+                      source="reference:FiBiNET/{senet,bilinear_interaction_layer}.py via tf1_shim")
+        P = (F - 1) * (F - 2) // 2
+        for typ, wshape in (("all", (K, K)), ("each", (F - 1, K, K)), ("interaction", (F * (F - 1) // 2, K, K))):
+            w = glorot(rng, wshape)
+            vs = {f"bilinear_interaction_part/orginal_w_{typ}": w}
+
+            def fn2(dt):
+                with tf.variable_scope("bilinear_interaction_part"):   # FiBiNET/fibinet.py:177-181
+                    return ref_bilinear.bilinear_interaction_layer(tf.Tensor(x.astype(dt)), embedding_dim=K,
+                                                                   type=typ, name="orginal").a
+            outs2, created2 = run_both(fn2, vs)
+            assert outs2["f32"].shape == (B, P, K), outs2["f32"].shape   # (F-1)(F-2)/2 pairs, not F(F-1)/2
+            arrays[f"w_{typ}"] = w
+            arrays[f"bilinear_{typ}_f32"] = outs2["f32"]
+            arrays[f"bilinear_{typ}_f64"] = outs2["f64"]
+        save(f"fibinet_F{F}_K{K}", **arrays)
+    # error behaviour: bad type -> ValueError (bilinear_interaction_layer.py:36-38)
+    tf.reset()
+    try:
+        ref_bilinear.bilinear_interaction_layer(tf.Tensor(np.zeros((1, 4, 2), np.float32)), 2, "nope", "x")
+        raise AssertionError("reference accepted a bad bilinear type")
+    except ValueError:
+        pass
+
+
+def gen_restated():
+    from oracle import layers_np as O
+    rng = np.random.default_rng(5678)
+    for F, D, B in ((6, 8, 16), (40, 32, 8)):
+        e = trunc_normal(rng, (B, F, D), 1.0 / np.sqrt(D))
+        save(f"fm2_F{F}_D{D}", e=e, out_f32=O.fm2_fwd(e), out_f64=O.fm2_fwd(e.astype(np.float64)),
+             pairwise_f64=O.fm2_pairwise(e), source="restated:DeepFM/deepfm.py:184-200")
+    # lookup edge cases: OOV, empty string, duplicate ids, empty bag, multi-valued mean
+    vocab = [b"userid_8", b"userid_3", b"userid_11", b"userid_5"]
+    keys = [b"userid_3", b"", b"userid_999", b"userid_8", b"userid_3", b"userid_5"]
+    ids = O.vocab_ids(keys, vocab)
+    assert ids.tolist() == [1, -1, -1, 0, 1, 3]
+    rows = [4, 3, 5]
+    off = np.array([0, 4, 7], dtype=np.int64)
+    table = trunc_normal(rng, (sum(rows), 8), 1 / np.sqrt(8))
+    ids2 = np.array([[1, 0, 4], [-1, 2, -1], [3, -1, 0], [1, 2, 4], [0, 0, 0], [-1, -1, -1]], dtype=np.int64)
+    out = O.embedding_lookup(table, ids2, off)
+    bag_ids = np.array([2, 0, -1, 5, 5, -1, -1, 11, 3], dtype=np.int64)
+    bag_off = np.array([0, 3, 3, 5, 7, 9], dtype=np.int64)      # bags: [2,0,-1] [] [5,5] [-1,-1] [11,3]
+    bag = O.bag_lookup_mean(table, bag_ids, bag_off)
+    save("lookup_edge", vocab=np.array(vocab), keys=np.array(keys), key_ids=ids, table=table, field_row_offset=off,
+         ids=ids2, out=out, bag_ids=bag_ids, bag_offsets=bag_off, bag_out=bag,
+         source="restated:TF1.14 feature_column semantics (SURVEY A.4-A.6) -- parity unpinned")
+
+
+if __name__ == "__main__":
+    gen_cross()
+    gen_cin()
+    gen_din()
+    gen_fibinet()
+    gen_restated()

@@ -1,0 +1,211 @@
+"""CPU tests: the restated oracle (oracle/layers_np.py) against the golden vectors produced by
+executing the reference's own layer files (oracle/make_golden.py), and the oracle's analytic
+backward against torch.autograd in float64."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_np as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"), allow_pickle=False)
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def test_all_fixtures_present():
+    names = {os.path.basename(p) for p in glob.glob(os.path.join(G, "*.npz"))}
+    assert len(names) == 14, names
+
+
+# ---------------------------------------------------------------- forward vs reference-executed golden
+@pytest.mark.parametrize("name", ["cross_d82_L1", "cross_d82_L3", "cross_d480_L3"])
+def test_cross_matches_reference(name):
+    g = load(name)
+    assert "reference:" in str(g["source"])
+    for dt, key, tol in ((np.float32, "out_f32", 1e-6), (np.float64, "out_f64", 1e-13)):
+        xs = O.cross_stack_fwd(g["x0"].astype(dt), g["ws"].astype(dt), g["bs"].astype(dt))
+        assert rel(xs[-1], g[key]) <= tol
+    assert rel(g["out_f32"], g["out_f64"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["cin_m8_D8_50x50x50", "cin_m30_D16_128x128", "cin_m8_D16_17"])
+def test_cin_matches_reference(name):
+    g = load(name)
+    n = int(g["n_layers"])
+    for dt, sfx, tol in ((np.float32, "f32", 2e-6), (np.float64, "f64", 1e-13)):
+        filters = [g[f"filter_{i + 1}"].astype(dt) for i in range(n)]
+        xs, pp = O.cin_stack_fwd(g["x0"].astype(dt), filters)
+        for i in range(n):
+            assert xs[i].shape == g[f"x{i + 1}_{sfx}"].shape
+            assert rel(xs[i], g[f"x{i + 1}_{sfx}"]) <= tol
+        assert rel(pp, g[f"p_plus_{sfx}"]) <= tol
+    # identity from SURVEY 8c: CIN == einsum('bid,bjd,ijn->bnd')
+    x0 = g["x0"].astype(np.float64)
+    m = x0.shape[1]
+    w = g["filter_1"].astype(np.float64).reshape(m, m, -1)
+    assert rel(np.einsum("bid,bjd,ijn->bnd", x0, x0, w), g["x1_f64"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["din_T3_smoke", "din_T1", "din_T50"])
+@pytest.mark.parametrize("soft", [False, True])
+def test_din_matches_reference(name, soft):
+    g = load(name)
+    for dt, sfx, tol in ((np.float32, "f32", 2e-6), (np.float64, "f64", 1e-13)):
+        args = [g[k].astype(dt) for k in ("f1_att_kernel", "f1_att_bias", "f2_att_kernel", "f2_att_bias",
+                                          "f3_att_kernel", "f3_att_bias")]
+        out = O.din_attention_fwd(g["query"].astype(dt), g["keys"].astype(dt), g["keys_length"], *args, is_softmax=soft)
+        ref = g[f"out_softmax{int(soft)}_{sfx}"]
+        assert np.isfinite(ref).all()
+        assert np.abs(out - ref).max() <= tol * max(np.abs(ref).max(), 1e-3)
+    # keys_length == 0: non-softmax output is exactly zero (din_attention.py:37-38)
+    if not soft:
+        zero_rows = g["keys_length"] == 0
+        assert np.all(g["out_softmax0_f32"][zero_rows] == 0)
+
+
+@pytest.mark.parametrize("name", ["fibinet_F8_K8", "fibinet_F30_K16"])
+def test_fibinet_matches_reference(name):
+    g = load(name)
+    F = g["x"].shape[1]
+    for dt, sfx, tol in ((np.float32, "f32", 2e-6), (np.float64, "f64", 1e-13)):
+        x = g["x"].astype(dt)
+        assert rel(O.senet_fwd(x, g["senet_w1"].astype(dt), g["senet_w2"].astype(dt)), g[f"senet_{sfx}"]) <= tol
+        for typ in ("all", "each", "interaction"):
+            out = O.bilinear_fwd(x, g[f"w_{typ}"].astype(dt), typ)
+            assert out.shape[1] == (F - 1) * (F - 2) // 2
+            assert rel(out, g[f"bilinear_{typ}_{sfx}"]) <= tol
+    with pytest.raises(ValueError):
+        O.bilinear_fwd(g["x"], g["w_all"], "nope")
+
+
+@pytest.mark.parametrize("name", ["fm2_F6_D8", "fm2_F40_D32"])
+def test_fm2(name):
+    g = load(name)
+    e = g["e"]
+    assert np.array_equal(O.fm2_fwd(e), g["out_f32"])
+    assert rel(O.fm2_fwd(e.astype(np.float64)), g["pairwise_f64"]) < 1e-12
+    assert rel(g["out_f32"], g["pairwise_f64"]) < 2e-6
+
+
+def test_lookup_edges():
+    g = load("lookup_edge")
+    ids = O.vocab_ids(list(g["keys"]), list(g["vocab"]))
+    assert np.array_equal(ids, g["key_ids"]) and ids.dtype == np.int64
+    out = O.embedding_lookup(g["table"], g["ids"], g["field_row_offset"])
+    assert np.array_equal(out, g["out"])
+    assert np.all(out[5] == 0) and np.all(out[1, 0] == 0)            # id -1 -> zero vector
+    assert np.array_equal(out[4, 0], g["table"][0])                    # single id -> exact row copy
+    bag = O.bag_lookup_mean(g["table"], g["bag_ids"], g["bag_offsets"])
+    assert np.array_equal(bag, g["bag_out"])
+    assert np.all(bag[1] == 0) and np.all(bag[3] == 0)                 # empty bag / all-OOV bag -> zeros
+    assert np.allclose(bag[0], (g["table"][2] + g["table"][0]) / 2)
+
+
+# ---------------------------------------------------------------- analytic backward vs autograd (float64)
+def T(x, grad=True):
+    return torch.tensor(np.asarray(x, dtype=np.float64), requires_grad=grad)
+
+
+def test_fm2_bwd():
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal((5, 7, 8))
+    g = rng.standard_normal((5,))
+    et = T(e)
+    s = et.sum(1)
+    out = 0.5 * (s * s - (et * et).sum(1)).sum(1)
+    out.backward(torch.tensor(g))
+    assert rel(O.fm2_bwd(e, g), et.grad.numpy()) < 1e-12
+
+
+def test_cross_bwd():
+    rng = np.random.default_rng(1)
+    B, d, L = 6, 11, 3
+    x0, ws, bs, g = (rng.standard_normal(s) for s in ((B, d), (L, d), (L, d), (B, d)))
+    x0t, wt, bt = T(x0), T(ws), T(bs)
+    x = x0t
+    for l in range(L):
+        x = x0t * (x @ wt[l])[:, None] + bt[l][None, :] + x
+    x.backward(torch.tensor(g))
+    dx0, dws, dbs = O.cross_stack_bwd(x0, ws, bs, g)
+    assert rel(dx0, x0t.grad.numpy()) < 1e-12
+    assert rel(dws, wt.grad.numpy()) < 1e-12
+    assert rel(dbs, bt.grad.numpy()) < 1e-12
+
+
+def test_cin_bwd():
+    rng = np.random.default_rng(2)
+    B, m, hk, D, H = 3, 5, 4, 6, 7
+    x0, xk, w, g = (rng.standard_normal(s) for s in ((B, m, D), (B, hk, D), (hk * m, H), (B, H, D)))
+    x0t, xkt, wt = T(x0), T(xk), T(w)
+    out = torch.einsum("bid,bjd,ijn->bnd", xkt, x0t, wt.reshape(hk, m, H))
+    out.backward(torch.tensor(g))
+    dx0, dxk, dw = O.cin_layer_bwd(x0, xk, w, g)
+    assert rel(dx0, x0t.grad.numpy()) < 1e-12
+    assert rel(dxk, xkt.grad.numpy()) < 1e-12
+    assert rel(dw, wt.grad.numpy()) < 1e-12
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_din_bwd(soft):
+    rng = np.random.default_rng(3)
+    B, Tn, H = 4, 5, 6
+    q, k = rng.standard_normal((B, H)), rng.standard_normal((B, Tn, H))
+    lens = np.array([0, 2, 5, 1])
+    ws = [rng.standard_normal(s) * 0.3 for s in ((4 * H, 64), (64,), (64, 32), (32,), (32, 1), (1,))]
+    g = rng.standard_normal((B, H))
+    qt, kt = T(q), T(k)
+    wt = [T(w) for w in ws]
+    qq = qt[:, None, :].expand(B, Tn, H)
+    cross = torch.cat([qq, kt, qq - kt, qq * kt], -1)
+    h1 = torch.relu(cross @ wt[0] + wt[1])
+    h2 = torch.relu(h1 @ wt[2] + wt[3])
+    s = h2 @ wt[4] + wt[5]
+    mask = (torch.arange(Tn)[None, :] < torch.tensor(lens)[:, None])[..., None]
+    if soft:
+        s2 = torch.where(mask, s, torch.full_like(s, float(O.DIN_PAD))) / (H ** 0.5)
+        w = torch.softmax(s2, dim=1)
+    else:
+        w = s * mask.double()
+    out = (w.transpose(1, 2) @ kt)[:, 0, :]
+    assert rel(O.din_attention_fwd(q, k, lens, *ws, is_softmax=soft), out.detach().numpy()) < 1e-12
+    out.backward(torch.tensor(g))
+    gr = O.din_attention_bwd(q, k, lens, *ws, g, is_softmax=soft)
+    assert rel(gr["query"], qt.grad.numpy()) < 1e-11
+    assert rel(gr["keys"], kt.grad.numpy()) < 1e-11
+    for name, t in zip(("w1", "b1", "w2", "b2", "w3", "b3"), wt):
+        ref = t.grad.numpy()      # d/db3 is analytically 0 under softmax (shift invariance): absolute floor
+        assert np.abs(gr[name] - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1.0), name
+
+
+def test_senet_bilinear_bwd():
+    rng = np.random.default_rng(4)
+    B, F, K, r = 4, 6, 8, 4
+    x, w1, w2, g = (rng.standard_normal(s) for s in ((B, F, K), (F, r), (r, F), (B, F, K)))
+    xt, w1t, w2t = T(x), T(w1), T(w2)
+    a = torch.relu(torch.relu(xt.mean(-1) @ w1t) @ w2t)
+    (xt * a[..., None]).backward(torch.tensor(g))
+    dx, dw1, dw2 = O.senet_bwd(x, w1, w2, g)
+    assert rel(dx, xt.grad.numpy()) < 1e-12 and rel(dw1, w1t.grad.numpy()) < 1e-12 and rel(dw2, w2t.grad.numpy()) < 1e-12
+    pairs = O.bilinear_pairs(F)
+    P = len(pairs)
+    gp = rng.standard_normal((B, P, K))
+    for typ, shape in (("all", (K, K)), ("each", (F - 1, K, K)), ("interaction", (F * (F - 1) // 2, K, K))):
+        w = rng.standard_normal(shape)
+        xt, wt = T(x), T(w)
+        ps = []
+        for k, (i, j) in enumerate(pairs):
+            wi = wt if typ == "all" else (wt[i] if typ == "each" else wt[k])
+            ps.append((xt[:, i, :] @ wi) * xt[:, j, :])
+        torch.stack(ps, 1).backward(torch.tensor(gp))
+        dx, dw = O.bilinear_bwd(x, w, typ, gp)
+        assert rel(dx, xt.grad.numpy()) < 1e-12, typ
+        assert rel(dw, wt.grad.numpy()) < 1e-12, typ
