@@ -1,0 +1,143 @@
+/* ctr_b200.h -- C ABI of the Blackwell-native CTR feature-interaction engine (libctr_b200.so).
+ *
+ * Drop-in boundary for the hot path of tangxyw/RecAlgorithm (reference paths below are relative to
+ * /root/reference/algorithm).  The reference has no FFI of its own -- its boundary is Python
+ * callables invoked while a TF1 graph is built -- so each entry point here
+ * names the reference callable whose forward / autodiff-backward it replaces.  The Python side
+ * (recalgorithm_b200/layers.py) re-exposes them under the reference's own signatures.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, int64_t sizes, `void* stream` is a cudaStream_t (NULL = default stream);
+ *   - every function returns 0 on success or a negative CTR_ERR_* code; ctr_last_error() gives the text
+ *     (thread-local).  Argument errors are detected before any launch;
+ *   - the CALLER owns every buffer; kernels never allocate, never synchronise, and are re-entrant
+ *     across streams.  Where a workspace is needed there is a *_workspace_bytes() query;
+ *   - all tensors are dense row-major fp32 unless stated; ids / offsets / lengths are int64;
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute entry point fails
+ *     with CTR_ERR_CUDA.
+ */
+#ifndef CTR_B200_H_
+#define CTR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTR_OK 0
+#define CTR_ERR_INVALID_ARG (-1)
+#define CTR_ERR_UNSUPPORTED (-2)
+#define CTR_ERR_CUDA (-3)
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* ctr_last_error(void);
+int ctr_version(void);                          /* ABI version, currently 1 */
+int ctr_device_info(int* sm_count, int* cc_major, int* cc_minor);   /* current device */
+int64_t ctr_kernel_launches(void);              /* kernels launched by this library so far (process-wide) */
+
+/* ---- Row L + FM2: fused embedding lookup + DeepFM second-order term ------------------------------
+ * Replaces   fc.input_layer(features, [embedding_column])   x F   (DeepFM/deepfm.py:187-190;
+ *            xDeepFM/xdeepfm.py:158,167; DCN/dcn.py:153; FiBiNET/fibinet.py:162-163)
+ *   and the inline FM second-order block (DeepFM/deepfm.py:192-200).
+ *
+ * table            (V_total, D): the F per-field tables stored back to back; field f owns rows
+ *                  [field_row_offset[f], field_row_offset[f+1]).
+ * field_row_offset device int64[F+1].
+ * ids              device int64 (B, F), per-field local ids.  id < 0 (the vocabulary's OOV / '' value, -1)
+ *                  or id >= the field's row count gives the ZERO vector (TF: pruned id -> empty bag -> zeros).
+ * tile             out (B, F, D) contiguous, or NULL (lookup+FM2 only).
+ * fm2              out (B), 0.5 * sum_d[(sum_f e)^2 - sum_f e^2], or NULL (lookup only).
+ * D must be a multiple of 4 and <= 128 (128-bit row chunks); other widths go through ctr_bag_lookup_*.
+ */
+int ctr_embed_fm2_fwd(const float* table, const int64_t* field_row_offset, const int64_t* ids,
+                      int64_t B, int64_t F, int64_t D, float* tile, float* fm2, void* stream);
+
+/* Backward of the pair above = the `values` of TF's IndexedSlices gradient of the gather
+ * (indices are the caller's ids):   row_grads[b,f,:] = d_tile[b,f,:] + d_fm2[b] * (S[b,:] - e[b,f,:]),
+ * S = sum_f e[b,f,:].   tile = the forward output; d_tile (B,F,D) and d_fm2 (B) may each be NULL (= 0).
+ * Rows whose id was invalid receive a gradient too (it is simply never applied; see ctr_embed_scatter_add). */
+int ctr_embed_fm2_bwd(const float* tile, const float* d_tile, const float* d_fm2,
+                      int64_t B, int64_t F, int64_t D, float* row_grads, void* stream);
+
+/* Densify: grad_table[field_row_offset[f] + ids[b,f], :] += row_grads[b,f,:] for valid ids (duplicates
+ * summed, like the optimizer's IndexedSlices de-duplication; TF-internal).  grad_table is
+ * NOT zeroed here.  fp32 red.global.add -> summation order is not deterministic. */
+int ctr_embed_scatter_add(float* grad_table, const int64_t* field_row_offset, const int64_t* ids,
+                          const float* row_grads, int64_t B, int64_t F, int64_t D, void* stream);
+
+/* ---- Row L (general): multi-valued bag lookup, combiner='mean' ----------------------------------
+ * Replaces fc.input_layer over embedding_column(col, D, combiner='mean') on a VarLen feature
+ * (DCN/dcn.py:98,103; xDeepFM/xdeepfm.py:103,108) and any single-valued column whose D is not a
+ * multiple of 4 (DCN/dcn.py:99-102 use D = 2 and 4).
+ * ids (nnz) flat values, offsets (B+1) CSR; ids < 0 or >= V are dropped; empty bag -> zeros.
+ * out[b*out_stride + 0..D) is written (lets the caller place the field inside a (B, sum_d) row). */
+int ctr_bag_lookup_fwd(const float* table, int64_t V, int64_t D, const int64_t* ids, const int64_t* offsets,
+                       int64_t B, float* out, int64_t out_stride, void* stream);
+/* row_grads (nnz, D): d_out[b]/count_b for valid ids, 0 for dropped ids. */
+int ctr_bag_lookup_bwd(const float* d_out, int64_t out_stride, int64_t V, int64_t D, const int64_t* ids,
+                       const int64_t* offsets, int64_t B, float* row_grads, void* stream);
+
+/* ---- Row CROSS: DCN cross-layer stack --------------------------------------------------------------
+ * Replaces the loop `for i: cross_vec = cross_layer(x0, cross_vec, i)` (DCN/dcn.py:157-160) over
+ * cross_layer (DCN/cross_layer.py:21-24):  x_{l+1} = x0 * (x_l . w_l) + b_l + x_l,  x_0 = x0.
+ * x0 (B,d); w, b (L,d) = the L (d,1) variables wl_i / bl_i stacked; out (B,d) = x_L.
+ * xl_in: optional (B,d) start vector (NULL = x0); lets a single layer be called as cross_layer(x0, xl, i). */
+int ctr_cross_fwd(const float* x0, const float* xl_in, const float* w, const float* b,
+                  int64_t B, int64_t d, int64_t L, float* out, void* stream);
+/* Gradients given g_out = dL/dx_L.  dx0 (B,d) receives the gradient through every use of x0
+ * (and through x_0 when xl_in == NULL); dxl_in (B,d) is written only when xl_in != NULL.
+ * dw, db (L,d) are overwritten (batch-reduced with fp32 atomics across CTAs). */
+int ctr_cross_bwd(const float* x0, const float* xl_in, const float* w, const float* b, const float* g_out,
+                  int64_t B, int64_t d, int64_t L, float* dx0, float* dxl_in, float* dw, float* db, void* stream);
+
+/* ---- Row CIN: xDeepFM compressed-interaction layer -------------------------------------------------
+ * Replaces cin_layer(x0, xk, hk_1, index) (xDeepFM/cin_layer.py:17-30):
+ *   out[b,n,d] = sum_{i,j} xk[b,i,d] * x0[b,j,d] * filter[i*m + j, n]
+ * x0 (B,m,D); xk (B,hk,D); filter (hk*m, H) = the conv1d filter (1, hk*m, hk_1)[0]; out (B,H,D);
+ * pooled (B,H) = sum_d out (the reduce_sum of xDeepFM/xdeepfm.py:173) or NULL.
+ * precision: 0 = fp32-class (3xTF32 split on the tensor cores; default, meets 1e-5),
+ *            1 = single-pass TF32 (about 1e-3; for speed comparisons only). */
+int ctr_cin_fwd(const float* x0, const float* xk, const float* filter, int64_t B, int64_t m, int64_t hk,
+                int64_t D, int64_t H, float* out, float* pooled, int precision, void* stream);
+int ctr_cin_bwd(const float* x0, const float* xk, const float* filter, const float* g_out,
+                int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H,
+                float* dx0 /* accumulated into (+=) */, float* dxk /* overwritten */, float* dfilter /* overwritten */,
+                void* workspace, int64_t workspace_bytes, void* stream);
+int64_t ctr_cin_bwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H);
+
+/* ---- Row DIN-ATT: DIN attention unit -----------------------------------------------------------------
+ * Replaces din_attention(query, keys, keys_length, is_softmax) (DIN/din_attention.py:17-43).
+ * query (B,H); keys (B,T,H); keys_length int64 (B); dense layers f1_att (4H->64, relu), f2_att (64->32,
+ * relu), f3_att (32->1): w1 (4H,64) b1 (64) w2 (64,32) b2 (32) w3 (32) b3 (1); out (B,H).
+ * att_w (B,T): the final per-position weights (saved for backward), or NULL. */
+int ctr_din_attention_fwd(const float* query, const float* keys, const int64_t* keys_length,
+                          const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* w3, const float* b3, int64_t B, int64_t T, int64_t H, int is_softmax,
+                          float* out, float* att_w, void* stream);
+/* d_params: one flat fp32 buffer laid out [w1 | b1 | w2 | b2 | w3 | b3] (4H*64+64+64*32+32+32+1), overwritten. */
+int ctr_din_attention_bwd(const float* query, const float* keys, const int64_t* keys_length,
+                          const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* w3, const float* b3, const float* g_out,
+                          int64_t B, int64_t T, int64_t H, int is_softmax,
+                          float* d_query, float* d_keys, float* d_params, void* stream);
+
+/* ---- Rows SENET / BILINEAR: FiBiNET ---------------------------------------------------------------------
+ * senet(input, embedding_dim, reduction_ratio) (FiBiNET/senet.py:26-34): x (B,F,K); w1 (F,r); w2 (r,F). */
+int ctr_senet_fwd(const float* x, const float* w1, const float* w2, int64_t B, int64_t F, int64_t K, int64_t r,
+                  float* out, void* stream);
+int ctr_senet_bwd(const float* x, const float* w1, const float* w2, const float* g_out,
+                  int64_t B, int64_t F, int64_t K, int64_t r, float* dx, float* dw1, float* dw2, void* stream);
+/* bilinear_interaction_layer(input, embedding_dim, type, name) (FiBiNET/bilinear_interaction_layer.py:21-40).
+ * type: 0 'all' w (K,K); 1 'each' w (F-1,K,K); 2 'interaction' w (F(F-1)/2,K,K).
+ * Pairs are itertools.combinations(range(F-1), 2) -- fields 0..F-2 only -- so out is (B, P, K) with
+ * P = (F-1)(F-2)/2, exactly like the reference. */
+int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64_t F, int64_t K, int type,
+                     float* out, void* stream);
+int ctr_bilinear_bwd(const float* x, const float* w, const float* g_out, int64_t B, int64_t F, int64_t K, int type,
+                     float* dx, float* dw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTR_B200_H_ */

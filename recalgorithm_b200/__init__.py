@@ -1,0 +1,10 @@
+"""recalgorithm_b200 -- Blackwell-native (sm_100a) hot path of tangxyw/RecAlgorithm.
+
+Only the path named in BASELINE.json lives here: the per-field embedding lookup and the
+feature-interaction layers (FM2, cross, CIN, DIN attention, SENET/bilinear), as hand-written CUDA
+behind a C ABI (include/ctr_b200.h) with a Python host side that mirrors the reference's own
+layer signatures (recalgorithm_b200.layers).
+"""
+from . import _lib  # noqa: F401
+
+__all__ = ["_lib", "ops", "layers"]

@@ -1,0 +1,47 @@
+// Library-level entry points of libctr_b200.so: error text, version, device info, launch counter.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "ctr_common.cuh"
+
+namespace ctr {
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+}  // namespace ctr
+
+extern "C" {
+const char* ctr_last_error(void) { return ctr::g_err; }
+int ctr_version(void) { return 1; }
+int64_t ctr_kernel_launches(void) { return ctr::g_launches.load(); }
+
+int ctr_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  CTR_CUDA(cudaGetDevice(&dev));
+  int v = 0;
+  if (sm_count) { CTR_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm_count = v; }
+  if (cc_major) { CTR_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *cc_major = v; }
+  if (cc_minor) { CTR_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
+  return CTR_OK;
+}
+}

@@ -1,0 +1,354 @@
+// Row CROSS: the DCN cross-layer stack, all L layers in one launch.
+//
+// Reference: cross_layer(x0, xl, index) -- DCN/cross_layer.py:21-24 -- stacked by the loop at
+// DCN/dcn.py:157-160:   x_{l+1} = x0 * (x_l . w_l) + b_l + x_l   (w_l, b_l are (d,1) variables).
+//
+// B200 mapping (HBM/L2-bound, 20*d bytes per sample fwd+bwd; no tensor cores):
+//   forward : one warp per sample, x0 and x_l live in registers (d/32 values per lane), w/b of all layers
+//             staged once per CTA in shared memory, the (B,d)x(d,1) product is a warp-shuffle dot.
+//   backward: phase 1 (warp per sample) re-runs the forward recurrence to get s_l = x_l.w_l, then walks
+//             the layers backwards keeping g in registers (t_l = g.x0, dx0 += g*s_l, g += t_l*w_l);
+//             phase 2 (thread per column) forms the batch reductions dw_l = sum_b x_l*t_l and
+//             db_l = sum_b g_{l+1} from the tile staged in shared memory, using
+//                 x_l     = xs + x0 * sum_{k<l} s_k + sum_{k<l} b_k        (xs = start vector)
+//                 g_{l+1} = g_out + sum_{k>l} t_k * w_k
+//             so no per-layer activations are ever written to HBM; per-CTA partials are merged with
+//             fp32 atomics.
+#include "ctr_common.cuh"
+
+namespace ctr {
+
+constexpr int CROSS_WARPS = 8;          // samples per CTA iteration
+constexpr int CROSS_LMAX = 8;           // layers supported by the fused backward
+
+// N = ceil(d / (32*VEC)) element groups per lane; element index of (k, lane, v) = (k*32 + lane)*VEC + v
+template <int VEC, int N>
+struct LaneVec {
+  float v[N * VEC];
+  __device__ __forceinline__ void load(const float* __restrict__ p, int d, int lane) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int i = (k * 32 + lane) * VEC;
+      if constexpr (VEC == 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < d) t = __ldg(reinterpret_cast<const float4*>(p + i));
+        v[k * 4 + 0] = t.x; v[k * 4 + 1] = t.y; v[k * 4 + 2] = t.z; v[k * 4 + 3] = t.w;
+      } else {
+        v[k] = i < d ? __ldg(p + i) : 0.f;
+      }
+    }
+  }
+  // plain (generic-address) store: used for both global outputs and the shared-memory tile
+  __device__ __forceinline__ void store(float* __restrict__ p, int d, int lane) const {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int i = (k * 32 + lane) * VEC;
+      if (i < d) {
+        if constexpr (VEC == 4)
+          *reinterpret_cast<float4*>(p + i) = make_float4(v[k * 4 + 0], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
+        else
+          p[i] = v[k];
+      }
+    }
+  }
+};
+
+template <int VEC, int N>
+__device__ __forceinline__ void lane_load_smem(float (&r)[N * VEC], const float* s, int d, int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int i = (k * 32 + lane) * VEC;
+    if constexpr (VEC == 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < d) t = *reinterpret_cast<const float4*>(s + i);
+      r[k * 4 + 0] = t.x; r[k * 4 + 1] = t.y; r[k * 4 + 2] = t.z; r[k * 4 + 3] = t.w;
+    } else {
+      r[k] = i < d ? s[i] : 0.f;
+    }
+  }
+}
+
+template <int VEC, int N>
+__global__ void __launch_bounds__(CROSS_WARPS * 32)
+cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, const float* __restrict__ w,
+                 const float* __restrict__ b, int B, int d, int L, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sw = smem;                  // (L, d)
+  float* sb = smem + (size_t)L * d;  // (L, d)
+  for (int i = threadIdx.x; i < L * d; i += blockDim.x) { sw[i] = __ldg(w + i); sb[i] = __ldg(b + i); }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = warp0; s < B; s += nwarps) {
+    LaneVec<VEC, N> a0, x;
+    a0.load(x0 + (size_t)s * d, d, lane);
+    if (xl_in) x.load(xl_in + (size_t)s * d, d, lane);
+    else {
+#pragma unroll
+      for (int k = 0; k < N * VEC; ++k) x.v[k] = a0.v[k];
+    }
+    for (int l = 0; l < L; ++l) {
+      float wv[N * VEC], bv[N * VEC];
+      lane_load_smem<VEC, N>(wv, sw + (size_t)l * d, d, lane);
+      lane_load_smem<VEC, N>(bv, sb + (size_t)l * d, d, lane);
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < N * VEC; ++k) dot += x.v[k] * wv[k];
+      dot = warp_sum(dot);                                            // xl_wl  (B,1)
+#pragma unroll
+      for (int k = 0; k < N * VEC; ++k) x.v[k] = (a0.v[k] * dot + bv[k]) + x.v[k];   // (x0*xl_wl + bl^T) + xl
+    }
+    x.store(out + (size_t)s * d, d, lane);
+  }
+}
+
+// CPT = ceil(d / blockDim) columns per thread in phase 2.
+template <int VEC, int N, int CPT>
+__global__ void __launch_bounds__(CROSS_WARPS * 32)
+cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, const float* __restrict__ w,
+                 const float* __restrict__ b, const float* __restrict__ g_out, int B, int d, int L,
+                 float* __restrict__ dx0, float* __restrict__ dxl_in, float* __restrict__ dw,
+                 float* __restrict__ db) {
+  extern __shared__ __align__(16) float smem[];
+  float* sw = smem;                                  // (L, d)  weights
+  float* sb = sw + (size_t)L * d;                    // (L, d)  biases
+  float* scb = sb + (size_t)L * d;                   // (L, d)  prefix biases  cb_l = sum_{k<l} b_k
+  float* tx0 = scb + (size_t)L * d;                  // (W, d)  x0 tile
+  float* txs = tx0 + (size_t)CROSS_WARPS * d;        // (W, d)  start-vector tile (aliases tx0 when xl_in == NULL)
+  float* tg = xl_in ? txs + (size_t)CROSS_WARPS * d : txs;   // (W, d) g_out tile
+  if (!xl_in) txs = tx0;
+  float* scs = tg + (size_t)CROSS_WARPS * d;         // (W, LMAX)  cs_l = sum_{k<l} s_k
+  float* st = scs + CROSS_WARPS * CROSS_LMAX;        // (W, LMAX)  t_l
+  __shared__ int s_valid[CROSS_WARPS];
+
+  for (int i = threadIdx.x; i < L * d; i += blockDim.x) { sw[i] = __ldg(w + i); sb[i] = __ldg(b + i); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) { scb[(size_t)l * d + i] = acc; acc += sb[(size_t)l * d + i]; }
+  }
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  float acc_dw[CROSS_LMAX][CPT], acc_db[CROSS_LMAX][CPT];
+#pragma unroll
+  for (int l = 0; l < CROSS_LMAX; ++l)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) { acc_dw[l][c] = 0.f; acc_db[l][c] = 0.f; }
+  __syncthreads();
+
+  const int ntiles = (B + CROSS_WARPS - 1) / CROSS_WARPS;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int s = tile * CROSS_WARPS + wid;
+    // ---------------- phase 1: warp per sample ----------------
+    if (lane == 0) s_valid[wid] = s < B;
+    if (s < B) {
+      LaneVec<VEC, N> a0, x, g;
+      a0.load(x0 + (size_t)s * d, d, lane);
+      if (xl_in) x.load(xl_in + (size_t)s * d, d, lane);
+      else {
+#pragma unroll
+        for (int k = 0; k < N * VEC; ++k) x.v[k] = a0.v[k];
+      }
+      g.load(g_out + (size_t)s * d, d, lane);
+      a0.store(tx0 + (size_t)wid * d, d, lane);
+      if (xl_in) x.store(txs + (size_t)wid * d, d, lane);
+      g.store(tg + (size_t)wid * d, d, lane);
+      // forward recurrence -> s_l (kept in registers of every lane), prefix sums to smem
+      float sl[CROSS_LMAX];
+      float cs = 0.f;
+#pragma unroll
+      for (int l = 0; l < CROSS_LMAX; ++l) {
+        sl[l] = 0.f;
+        if (l < L) {
+          float wv[N * VEC], bv[N * VEC];
+          lane_load_smem<VEC, N>(wv, sw + (size_t)l * d, d, lane);
+          lane_load_smem<VEC, N>(bv, sb + (size_t)l * d, d, lane);
+          float dot = 0.f;
+#pragma unroll
+          for (int k = 0; k < N * VEC; ++k) dot += x.v[k] * wv[k];
+          dot = warp_sum(dot);
+          sl[l] = dot;
+          if (lane == 0) scs[wid * CROSS_LMAX + l] = cs;
+          cs += dot;
+#pragma unroll
+          for (int k = 0; k < N * VEC; ++k) x.v[k] = (a0.v[k] * dot + bv[k]) + x.v[k];
+        }
+      }
+      // backward walk; x now reused as the dx0 accumulator
+#pragma unroll
+      for (int k = 0; k < N * VEC; ++k) x.v[k] = 0.f;
+#pragma unroll
+      for (int l = CROSS_LMAX - 1; l >= 0; --l) {
+        if (l < L) {
+          float wv[N * VEC];
+          lane_load_smem<VEC, N>(wv, sw + (size_t)l * d, d, lane);
+          float t = 0.f;
+#pragma unroll
+          for (int k = 0; k < N * VEC; ++k) t += g.v[k] * a0.v[k];
+          t = warp_sum(t);
+          if (lane == 0) st[wid * CROSS_LMAX + l] = t;
+#pragma unroll
+          for (int k = 0; k < N * VEC; ++k) {
+            x.v[k] += g.v[k] * sl[l];
+            g.v[k] += t * wv[k];
+          }
+        }
+      }
+      if (xl_in) {
+        g.store(dxl_in + (size_t)s * d, d, lane);
+      } else {
+#pragma unroll
+        for (int k = 0; k < N * VEC; ++k) x.v[k] += g.v[k];
+      }
+      x.store(dx0 + (size_t)s * d, d, lane);
+    }
+    __syncthreads();
+    // ---------------- phase 2: thread per column ----------------
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int i = c * (CROSS_WARPS * 32) + threadIdx.x;
+      if (i < d) {
+        for (int q = 0; q < CROSS_WARPS; ++q) {
+          if (!s_valid[q]) continue;
+          const float vx0 = tx0[(size_t)q * d + i], vxs = txs[(size_t)q * d + i];
+          float gl = tg[(size_t)q * d + i];
+#pragma unroll
+          for (int l = CROSS_LMAX - 1; l >= 0; --l) {
+            if (l < L) {
+              const float t = st[q * CROSS_LMAX + l];
+              const float xl = (vx0 * scs[q * CROSS_LMAX + l] + scb[(size_t)l * d + i]) + vxs;
+              acc_dw[l][c] += xl * t;
+              acc_db[l][c] += gl;
+              gl += t * sw[(size_t)l * d + i];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int i = c * (CROSS_WARPS * 32) + threadIdx.x;
+    if (i < d) {
+#pragma unroll
+      for (int l = 0; l < CROSS_LMAX; ++l) {
+        if (l < L) {
+          atomicAdd(dw + (size_t)l * d + i, acc_dw[l][c]);
+          atomicAdd(db + (size_t)l * d + i, acc_db[l][c]);
+        }
+      }
+    }
+  }
+}
+
+static size_t cross_bwd_smem(int64_t d, int64_t L, bool has_xl) {
+  return sizeof(float) * ((size_t)3 * L * d + (size_t)(has_xl ? 3 : 2) * CROSS_WARPS * d +
+                          2 * CROSS_WARPS * CROSS_LMAX);
+}
+
+template <int VEC, int N>
+static int launch_cross_fwd(const float* x0, const float* xl_in, const float* w, const float* b, int64_t B, int64_t d,
+                            int64_t L, float* out, cudaStream_t st) {
+  auto k = cross_fwd_kernel<VEC, N>;
+  const size_t smem = sizeof(float) * 2 * (size_t)L * d;
+  if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, CROSS_WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)per_sm * sm_count();
+  const long long need = (B + CROSS_WARPS - 1) / CROSS_WARPS;
+  if (grid > need) grid = need;
+  k<<<(int)grid, CROSS_WARPS * 32, smem, st>>>(x0, xl_in, w, b, (int)B, (int)d, (int)L, out);
+  CTR_CHECK_LAUNCH("ctr_cross_fwd");
+  return CTR_OK;
+}
+
+template <int VEC, int N, int CPT>
+static int launch_cross_bwd(const float* x0, const float* xl_in, const float* w, const float* b, const float* g,
+                            int64_t B, int64_t d, int64_t L, float* dx0, float* dxl, float* dw, float* db,
+                            cudaStream_t st) {
+  auto k = cross_bwd_kernel<VEC, N, CPT>;
+  const size_t smem = cross_bwd_smem(d, L, xl_in != nullptr);
+  if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, CROSS_WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;                         // fewer CTAs -> fewer atomic merges of dw/db
+  long long grid = (long long)per_sm * sm_count();
+  const long long need = (B + CROSS_WARPS - 1) / CROSS_WARPS;
+  if (grid > need) grid = need;
+  CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * L * d, st));
+  CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * L * d, st));
+  k<<<(int)grid, CROSS_WARPS * 32, smem, st>>>(x0, xl_in, w, b, g, (int)B, (int)d, (int)L, dx0, dxl, dw, db);
+  CTR_CHECK_LAUNCH("ctr_cross_bwd");
+  return CTR_OK;
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+// d is served by N element groups per lane: vector path (VEC=4) when d % 4 == 0, scalar path otherwise.
+#define CTR_CROSS_DISPATCH(FN, ...)                                                          \
+  if (d % 4 == 0) {                                                                          \
+    const int64_t n = (d / 4 + 31) / 32;                                                     \
+    if (n <= 1) return FN(4, 1, __VA_ARGS__);                                                \
+    if (n <= 2) return FN(4, 2, __VA_ARGS__);                                                \
+    if (n <= 4) return FN(4, 4, __VA_ARGS__);                                                \
+    return FN(4, 8, __VA_ARGS__);                                                            \
+  } else {                                                                                   \
+    const int64_t n = (d + 31) / 32;                                                         \
+    if (n <= 1) return FN(1, 1, __VA_ARGS__);                                                \
+    if (n <= 2) return FN(1, 2, __VA_ARGS__);                                                \
+    if (n <= 4) return FN(1, 4, __VA_ARGS__);                                                \
+    if (n <= 8) return FN(1, 8, __VA_ARGS__);                                                \
+    if (n <= 16) return FN(1, 16, __VA_ARGS__);                                              \
+    return FN(1, 32, __VA_ARGS__);                                                           \
+  }
+
+static int check_cross(const char* fn, int64_t B, int64_t d, int64_t L) {
+  CTR_REQUIRE(B >= 0 && d >= 1 && L >= 1, "%s: bad sizes B=%lld d=%lld L=%lld", fn, (long long)B, (long long)d,
+              (long long)L);
+  CTR_UNSUPPORTED(d > 1024, "%s: d=%lld > 1024 unsupported", fn, (long long)d);
+  CTR_UNSUPPORTED(L > CROSS_LMAX, "%s: L=%lld > %d unsupported", fn, (long long)L, CROSS_LMAX);
+  return CTR_OK;
+}
+
+extern "C" int ctr_cross_fwd(const float* x0, const float* xl_in, const float* w, const float* b, int64_t B, int64_t d,
+                             int64_t L, float* out, void* stream) {
+  int rc = check_cross("ctr_cross_fwd", B, d, L);
+  if (rc) return rc;
+  CTR_REQUIRE(x0 && w && b && out, "ctr_cross_fwd: null argument");
+  if (d % 4 == 0)
+    CTR_REQUIRE(aligned16(x0) && aligned16(xl_in) && aligned16(out), "ctr_cross_fwd: buffers must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+#define FWD(V, NN, ...) launch_cross_fwd<V, NN>(__VA_ARGS__)
+  CTR_CROSS_DISPATCH(FWD, x0, xl_in, w, b, B, d, L, out, st)
+#undef FWD
+}
+
+extern "C" int ctr_cross_bwd(const float* x0, const float* xl_in, const float* w, const float* b, const float* g_out,
+                             int64_t B, int64_t d, int64_t L, float* dx0, float* dxl_in, float* dw, float* db,
+                             void* stream) {
+  int rc = check_cross("ctr_cross_bwd", B, d, L);
+  if (rc) return rc;
+  CTR_REQUIRE(x0 && w && b && g_out && dx0 && dw && db, "ctr_cross_bwd: null argument");
+  CTR_REQUIRE((xl_in == nullptr) == (dxl_in == nullptr), "ctr_cross_bwd: xl_in and dxl_in must both be given or both NULL");
+  if (d % 4 == 0)
+    CTR_REQUIRE(aligned16(x0) && aligned16(xl_in) && aligned16(g_out) && aligned16(dx0) && aligned16(dxl_in),
+                "ctr_cross_bwd: buffers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  if (B == 0) {
+    CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * L * d, st));
+    CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * L * d, st));
+    return CTR_OK;
+  }
+#define BWD(V, NN, ...)                                                        \
+  (d <= 256 ? launch_cross_bwd<V, NN, 1>(__VA_ARGS__)                          \
+            : d <= 512 ? launch_cross_bwd<V, NN, 2>(__VA_ARGS__) : launch_cross_bwd<V, NN, 4>(__VA_ARGS__))
+  CTR_CROSS_DISPATCH(BWD, x0, xl_in, w, b, g_out, B, d, L, dx0, dxl_in, dw, db, st)
+#undef BWD
+}

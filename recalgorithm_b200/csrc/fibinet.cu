@@ -1,0 +1,405 @@
+// Rows SENET and BILINEAR: FiBiNET's two interaction layers.
+//
+// Reference:
+//   senet(input, embedding_dim, reduction_ratio)                   -- FiBiNET/senet.py:26-34
+//       z = mean_K(x); a = relu(relu(z @ w1) @ w2); out = x * a[..., None]      (w1 (F,r), w2 (r,F), no bias)
+//   bilinear_interaction_layer(input, embedding_dim, type, name)    -- FiBiNET/bilinear_interaction_layer.py:21-40
+//       p_(i,j) = (x_i @ W) * x_j  for (i,j) in combinations(range(F-1), 2)  -> (B, (F-1)(F-2)/2, K)
+//       W = w (K,K) ['all'] | w[i] ['each'] | w[pair index] ['interaction']
+//
+// B200 mapping: both layers are small, HBM/L2-bound CUDA-core kernels (K x K = 16 x 16 weights); SENET runs one
+// warp per sample with the squeeze/excite vectors in shared memory, bilinear runs one CTA per sample with the
+// sample's (F,K) block and the projected vectors in shared memory and writes the (P,K) output coalesced.
+// Weight gradients are reduced per CTA in shared memory (or registers) and merged with fp32 atomics.
+#include "ctr_common.cuh"
+
+namespace ctr {
+
+constexpr int SENET_WARPS = 4;
+
+// smem layout per CTA: w1 (F*r) | w2 (r*F) | [bwd: dw1 (F*r) | dw2 (r*F)] | per warp: z (F), a1 (r), a2 (F), t1 (r), t2 (F)
+template <bool BWD>
+__global__ void __launch_bounds__(SENET_WARPS * 32)
+senet_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ w2,
+             const float* __restrict__ g, int B, int F, int K, int r, float* __restrict__ out /* fwd: out; bwd: dx */,
+             float* __restrict__ dw1, float* __restrict__ dw2) {
+  extern __shared__ __align__(16) float smem[];
+  float* sw1 = smem;
+  float* sw2 = sw1 + F * r;
+  float* sdw1 = sw2 + r * F;
+  float* sdw2 = BWD ? sdw1 + F * r : sdw1;
+  float* per_warp = BWD ? sdw2 + r * F : sdw1;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stride = 3 * F + 2 * r;
+  float* z = per_warp + wid * stride;
+  float* a1 = z + F;
+  float* a2 = a1 + r;
+  float* t1 = a2 + F;      // bwd: da1
+  float* t2 = t1 + r;      // bwd: da2, then dz
+  for (int i = threadIdx.x; i < F * r; i += blockDim.x) {
+    sw1[i] = __ldg(w1 + i); sw2[i] = __ldg(w2 + i);
+    if (BWD) { sdw1[i] = 0.f; sdw2[i] = 0.f; }
+  }
+  __syncthreads();
+  const float fK = (float)K;
+  const int nwarps = gridDim.x * SENET_WARPS;
+  for (int b = blockIdx.x * SENET_WARPS + wid; b < B; b += nwarps) {
+    const float* xb = x + (size_t)b * F * K;
+    const float* gb = BWD ? g + (size_t)b * F * K : nullptr;
+    // squeeze: z[f] = mean_k x[f,k]   (+ bwd: t2[f] = sum_k g[f,k]*x[f,k])
+    for (int f = lane; f < F; f += 32) {
+      float s = 0.f, gx = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float v = __ldg(xb + f * K + k);
+        s += v;
+        if (BWD) gx += __ldg(gb + f * K + k) * v;
+      }
+      z[f] = s / fK;
+      if (BWD) t2[f] = gx;
+    }
+    __syncwarp();
+    for (int j = lane; j < r; j += 32) {
+      float s = 0.f;
+      for (int f = 0; f < F; ++f) s += z[f] * sw1[f * r + j];
+      a1[j] = fmaxf(s, 0.f);
+    }
+    __syncwarp();
+    for (int f = lane; f < F; f += 32) {
+      float s = 0.f;
+      for (int j = 0; j < r; ++j) s += a1[j] * sw2[j * F + f];
+      a2[f] = fmaxf(s, 0.f);
+    }
+    __syncwarp();
+    if (!BWD) {
+      for (int i = lane; i < F * K; i += 32) out[(size_t)b * F * K + i] = __ldg(xb + i) * a2[i / K];
+    } else {
+      for (int f = lane; f < F; f += 32) t2[f] = a2[f] > 0.f ? t2[f] : 0.f;            // da2 (relu gate)
+      __syncwarp();
+      for (int j = lane; j < r; j += 32) {
+        float s = 0.f;
+        for (int f = 0; f < F; ++f) s += t2[f] * sw2[j * F + f];
+        t1[j] = a1[j] > 0.f ? s : 0.f;                                                  // da1
+      }
+      __syncwarp();
+      for (int i = lane; i < F * r; i += 32) {
+        const int f1 = i / r, j1 = i % r;      // dw1[f,j] += z[f]*da1[j]
+        atomicAdd(sdw1 + i, z[f1] * t1[j1]);
+        const int j2 = i / F, f2 = i % F;      // dw2[j,f] += a1[j]*da2[f]
+        atomicAdd(sdw2 + i, a1[j2] * t2[f2]);
+      }
+      __syncwarp();
+      for (int f = lane; f < F; f += 32) {      // dz[f] = sum_j da1[j]*w1[f,j]  (overwrites t2 after its last use)
+        float s = 0.f;
+        for (int j = 0; j < r; ++j) s += t1[j] * sw1[f * r + j];
+        z[f] = s / fK;                           // reuse z as dz/K
+      }
+      __syncwarp();
+      for (int i = lane; i < F * K; i += 32)
+        out[(size_t)b * F * K + i] = __ldg(gb + i) * a2[i / K] + z[i / K];
+    }
+    __syncwarp();
+  }
+  if (BWD) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * r; i += blockDim.x) {
+      atomicAdd(dw1 + i, sdw1[i]);
+      atomicAdd(dw2 + i, sdw2[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bilinear
+// ---------------------------------------------------------------------------------------------------
+constexpr int BIL_THREADS = 256;
+
+__device__ __forceinline__ int pair_base(int i, int n) {   // index of pair (i, i+1) among combinations(range(n), 2)
+  return i * (2 * n - i - 1) / 2;
+}
+
+// smem: xs (F*K) | vw ((F-1)*K)  [all/each]  | pair table (P x int2 packed as int)
+template <int TYPE>
+__global__ void __launch_bounds__(BIL_THREADS)
+bilinear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int B, int F, int K,
+                    float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = F - 1;                        // fields that take part (reference quirk: range(F-1))
+  const int P = n * (n - 1) / 2;
+  float* xs = smem;
+  float* vw = xs + F * K;
+  int* pairs = reinterpret_cast<int*>(vw + n * K);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int j = i + 1; j < n; ++j) pairs[pair_base(i, n) + (j - i - 1)] = (i << 16) | j;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * K; i += blockDim.x) xs[i] = __ldg(x + (size_t)b * F * K + i);
+    __syncthreads();
+    if (TYPE != 2) {
+      for (int t = threadIdx.x; t < n * K; t += blockDim.x) {
+        const int i = t / K, k = t % K;
+        const float* wi = TYPE == 0 ? w : w + (size_t)i * K * K;
+        float s = 0.f;
+        for (int c = 0; c < K; ++c) s += xs[i * K + c] * __ldg(wi + c * K + k);
+        vw[t] = s;
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < P * K; t += blockDim.x) {
+        const int p = t / K, k = t % K;
+        const int ij = pairs[p];
+        out[(size_t)b * P * K + t] = vw[(ij >> 16) * K + k] * xs[(ij & 0xffff) * K + k];
+      }
+    } else {
+      for (int t = threadIdx.x; t < P * K; t += blockDim.x) {
+        const int p = t / K, k = t % K;
+        const int ij = pairs[p];
+        const float* wp = w + (size_t)p * K * K;
+        const float* xi = xs + (ij >> 16) * K;
+        float s = 0.f;
+        for (int c = 0; c < K; ++c) s += xi[c] * __ldg(wp + c * K + k);
+        out[(size_t)b * P * K + t] = s * xs[(ij & 0xffff) * K + k];
+      }
+    }
+  }
+}
+
+// Backward for 'all' / 'each'.  smem: xs (F*K) | vw (n*K) | dvw (n*K) | dwacc (TYPE0: K*K, TYPE1: n*K*K)
+template <int TYPE>
+__global__ void __launch_bounds__(BIL_THREADS)
+bilinear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g, int B,
+                    int F, int K, float* __restrict__ dx, float* __restrict__ dw) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = F - 1;
+  const int P = n * (n - 1) / 2;
+  float* xs = smem;
+  float* vw = xs + F * K;
+  float* dvw = vw + n * K;
+  float* dwacc = dvw + n * K;
+  const int ndw = (TYPE == 0 ? 1 : n) * K * K;
+  for (int i = threadIdx.x; i < ndw; i += blockDim.x) dwacc[i] = 0.f;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * K; i += blockDim.x) xs[i] = __ldg(x + (size_t)b * F * K + i);
+    __syncthreads();
+    const float* gb = g + (size_t)b * P * K;
+    for (int t = threadIdx.x; t < n * K; t += blockDim.x) {
+      const int i = t / K, k = t % K;
+      const float* wi = TYPE == 0 ? w : w + (size_t)i * K * K;
+      float s = 0.f;
+      for (int c = 0; c < K; ++c) s += xs[i * K + c] * __ldg(wi + c * K + k);
+      vw[t] = s;
+      // dvw_i[k] = sum_{j>i} g[(i,j),k] * x_j[k]
+      float d = 0.f;
+      const int p0 = pair_base(i, n);
+      for (int j = i + 1; j < n; ++j) d += __ldg(gb + (size_t)(p0 + j - i - 1) * K + k) * xs[j * K + k];
+      dvw[t] = d;
+    }
+    __syncthreads();
+    // dx_j[k] = sum_{i<j} g[(i,j),k]*vw_i[k]  +  sum_c dvw_j[c] * W_j[k][c]   (second term only for j < n)
+    for (int t = threadIdx.x; t < F * K; t += blockDim.x) {
+      const int j = t / K, k = t % K;
+      float s = 0.f;
+      if (j < n) {
+        for (int i = 0; i < j; ++i) s += __ldg(gb + (size_t)(pair_base(i, n) + j - i - 1) * K + k) * vw[i * K + k];
+        const float* wj = TYPE == 0 ? w : w + (size_t)j * K * K;
+        for (int c = 0; c < K; ++c) s += dvw[j * K + c] * __ldg(wj + k * K + c);
+      }
+      dx[(size_t)b * F * K + t] = s;           // field F-1 never takes part -> zero gradient
+    }
+    // dW_i[c][k] += x_i[c] * dvw_i[k]   (thread-owned accumulators: element e belongs to thread e % blockDim)
+    for (int e = threadIdx.x; e < ndw; e += blockDim.x) {
+      const int k = e % K, c = (e / K) % K;
+      if (TYPE == 0) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += xs[i * K + c] * dvw[i * K + k];
+        dwacc[e] += s;
+      } else {
+        const int i = e / (K * K);
+        dwacc[e] += xs[i * K + c] * dvw[i * K + k];
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ndw; e += blockDim.x) atomicAdd(dw + e, dwacc[e]);
+}
+
+// 'interaction' backward, data gradient: one CTA per sample.  smem: xs (F*K) | pairs (P)
+__global__ void __launch_bounds__(BIL_THREADS)
+bilinear_bwd_interaction_dx_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ g, int B, int F, int K, float* __restrict__ dx) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = F - 1;
+  const int P = n * (n - 1) / 2;
+  float* xs = smem;
+  float* dxs = xs + F * K;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * K; i += blockDim.x) { xs[i] = __ldg(x + (size_t)b * F * K + i); dxs[i] = 0.f; }
+    __syncthreads();
+    const float* gb = g + (size_t)b * P * K;
+    // thread per (p, k): contributes to dx_j[k] (vw_p[k]*g) and to dx_i[c] for all c (g*x_j[k]*W_p[c][k])
+    for (int i = 0; i < n; ++i) {
+      for (int t = threadIdx.x; t < (n - i - 1) * K; t += blockDim.x) {
+        const int j = i + 1 + t / K, k = t % K;
+        const int p = pair_base(i, n) + (j - i - 1);
+        const float* wp = w + (size_t)p * K * K;
+        const float gv = __ldg(gb + (size_t)p * K + k);
+        float vwk = 0.f;
+        for (int c = 0; c < K; ++c) vwk += xs[i * K + c] * __ldg(wp + c * K + k);
+        atomicAdd(dxs + j * K + k, gv * vwk);
+        const float dv = gv * xs[j * K + k];                   // dvw_p[k]
+        for (int c = 0; c < K; ++c) atomicAdd(dxs + i * K + c, dv * __ldg(wp + c * K + k));
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * K; i += blockDim.x) dx[(size_t)b * F * K + i] = dxs[i];
+  }
+}
+
+// 'interaction' backward, weight gradient: dW_p[c][k] = sum_b x[b,i,c] * g[b,p,k] * x[b,j,k].
+// grid (P, nsplit); thread e = c*K + k loops over the samples of its split.
+__global__ void __launch_bounds__(1024)
+bilinear_bwd_interaction_dw_kernel(const float* __restrict__ x, const float* __restrict__ g, int B, int F, int K,
+                                   float* __restrict__ dw) {
+  const int n = F - 1;
+  const int P = n * (n - 1) / 2;
+  const int p = blockIdx.x;
+  int i = 0;
+  while (pair_base(i + 1, n) <= p && i + 1 < n - 1) ++i;
+  const int j = i + 1 + (p - pair_base(i, n));
+  for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
+    const int c = e / K, k = e % K;
+    float s = 0.f;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+      const float* xb = x + (size_t)b * F * K;
+      s += __ldg(xb + i * K + c) * __ldg(g + ((size_t)b * P + p) * K + k) * __ldg(xb + j * K + k);
+    }
+    atomicAdd(dw + (size_t)p * K * K + e, s);
+  }
+}
+
+static int grid_for(long long need, int per_sm) {
+  long long g = (long long)sm_count() * per_sm;
+  if (g > need) g = need;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+static int check_senet(const char* fn, int64_t B, int64_t F, int64_t K, int64_t r) {
+  CTR_REQUIRE(B >= 0 && F >= 1 && K >= 1 && r >= 1, "%s: bad sizes", fn);
+  // reference: assert reduction_dim < embedding_dim (FiBiNET/senet.py:19)
+  CTR_REQUIRE(r < K, "%s: reduction_dim must be less than embedding_dim (r=%lld, K=%lld)", fn, (long long)r, (long long)K);
+  CTR_UNSUPPORTED(F > 1024 || K > 1024 || F * r > 8192, "%s: F=%lld K=%lld r=%lld too large", fn, (long long)F,
+                  (long long)K, (long long)r);
+  return CTR_OK;
+}
+
+extern "C" int ctr_senet_fwd(const float* x, const float* w1, const float* w2, int64_t B, int64_t F, int64_t K, int64_t r,
+                             float* out, void* stream) {
+  int rc = check_senet("ctr_senet_fwd", B, F, K, r);
+  if (rc) return rc;
+  CTR_REQUIRE(x && w1 && w2 && out, "ctr_senet_fwd: null argument");
+  if (B == 0) return CTR_OK;
+  const size_t smem = sizeof(float) * (2 * F * r + SENET_WARPS * (3 * F + 2 * r));
+  auto k = senet_kernel<false>;
+  if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid_for((B + SENET_WARPS - 1) / SENET_WARPS, 8), SENET_WARPS * 32, smem, as_stream(stream)>>>(
+      x, w1, w2, nullptr, (int)B, (int)F, (int)K, (int)r, out, nullptr, nullptr);
+  CTR_CHECK_LAUNCH("ctr_senet_fwd");
+  return CTR_OK;
+}
+
+extern "C" int ctr_senet_bwd(const float* x, const float* w1, const float* w2, const float* g_out, int64_t B, int64_t F,
+                             int64_t K, int64_t r, float* dx, float* dw1, float* dw2, void* stream) {
+  int rc = check_senet("ctr_senet_bwd", B, F, K, r);
+  if (rc) return rc;
+  CTR_REQUIRE(x && w1 && w2 && g_out && dx && dw1 && dw2, "ctr_senet_bwd: null argument");
+  cudaStream_t st = as_stream(stream);
+  CTR_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * F * r, st));
+  CTR_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * F * r, st));
+  if (B == 0) return CTR_OK;
+  const size_t smem = sizeof(float) * (4 * F * r + SENET_WARPS * (3 * F + 2 * r));
+  auto k = senet_kernel<true>;
+  if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid_for((B + SENET_WARPS - 1) / SENET_WARPS, 4), SENET_WARPS * 32, smem, st>>>(
+      x, w1, w2, g_out, (int)B, (int)F, (int)K, (int)r, dx, dw1, dw2);
+  CTR_CHECK_LAUNCH("ctr_senet_bwd");
+  return CTR_OK;
+}
+
+static int check_bilinear(const char* fn, int64_t B, int64_t F, int64_t K, int type) {
+  CTR_REQUIRE(B >= 0 && F >= 1 && K >= 1, "%s: bad sizes", fn);
+  // reference: ValueError for an unknown type (FiBiNET/bilinear_interaction_layer.py:36-38)
+  CTR_REQUIRE(type >= 0 && type <= 2, "%s: Bilinear Interaction type must be in ['all','each','interaction'] (0..2), got %d",
+              fn, type);
+  CTR_UNSUPPORTED(F > 256 || K > 128, "%s: F=%lld K=%lld too large", fn, (long long)F, (long long)K);
+  return CTR_OK;
+}
+
+extern "C" int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64_t F, int64_t K, int type, float* out,
+                                void* stream) {
+  int rc = check_bilinear("ctr_bilinear_fwd", B, F, K, type);
+  if (rc) return rc;
+  CTR_REQUIRE(x && w && out, "ctr_bilinear_fwd: null argument");
+  const int64_t n = F - 1, P = n * (n - 1) / 2;
+  if (B == 0 || P == 0) return CTR_OK;
+  const size_t smem = sizeof(float) * (F * K + n * K) + sizeof(int) * P;
+  cudaStream_t st = as_stream(stream);
+  const int grid = grid_for(B, 8);
+#define LAUNCH(T)                                                                                            \
+  {                                                                                                          \
+    auto k = bilinear_fwd_kernel<T>;                                                                         \
+    if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<grid, BIL_THREADS, smem, st>>>(x, w, (int)B, (int)F, (int)K, out);                                   \
+  }
+  if (type == 0) LAUNCH(0) else if (type == 1) LAUNCH(1) else LAUNCH(2)
+#undef LAUNCH
+  CTR_CHECK_LAUNCH("ctr_bilinear_fwd");
+  return CTR_OK;
+}
+
+extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_out, int64_t B, int64_t F, int64_t K,
+                                int type, float* dx, float* dw, void* stream) {
+  int rc = check_bilinear("ctr_bilinear_bwd", B, F, K, type);
+  if (rc) return rc;
+  CTR_REQUIRE(x && w && g_out && dx && dw, "ctr_bilinear_bwd: null argument");
+  const int64_t n = F - 1, P = n * (n - 1) / 2;
+  const int64_t nw = (type == 0 ? 1 : type == 1 ? n : F * (F - 1) / 2) * K * K;
+  cudaStream_t st = as_stream(stream);
+  CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * nw, st));
+  if (B == 0) return CTR_OK;
+  if (P == 0) {
+    CTR_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * B * F * K, st));
+    return CTR_OK;
+  }
+  if (type == 2) {
+    const size_t smem = sizeof(float) * 2 * F * K;
+    auto k = bilinear_bwd_interaction_dx_kernel;
+    if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid_for(B, 8), BIL_THREADS, smem, st>>>(x, w, g_out, (int)B, (int)F, (int)K, dx);
+    CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dx)");
+    int nsplit = (int)((B + 255) / 256);
+    if (nsplit > 16) nsplit = 16;
+    const int threads = (int)(K * K < 1024 ? ((K * K + 31) / 32) * 32 : 1024);
+    bilinear_bwd_interaction_dw_kernel<<<dim3((unsigned)P, (unsigned)nsplit), threads, 0, st>>>(x, g_out, (int)B, (int)F,
+                                                                                               (int)K, dw);
+    CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dw)");
+    return CTR_OK;
+  }
+  const size_t smem = sizeof(float) * (F * K + 2 * n * K + (type == 0 ? 1 : n) * K * K);
+  CTR_UNSUPPORTED(smem > 200 * 1024, "ctr_bilinear_bwd: F=%lld K=%lld needs %zu B of shared memory", (long long)F,
+                  (long long)K, smem);
+  const int grid = grid_for(B, 2);
+#define LAUNCH(T)                                                                                            \
+  {                                                                                                          \
+    auto k = bilinear_bwd_kernel<T>;                                                                         \
+    if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<grid, BIL_THREADS, smem, st>>>(x, w, g_out, (int)B, (int)F, (int)K, dx, dw);                         \
+  }
+  if (type == 0) LAUNCH(0) else LAUNCH(1)
+#undef LAUNCH
+  CTR_CHECK_LAUNCH("ctr_bilinear_bwd");
+  return CTR_OK;
+}

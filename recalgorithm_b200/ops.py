@@ -1,0 +1,235 @@
+"""Thin tensor-level wrappers over the C ABI (device pointers + sizes + the current CUDA stream).
+
+torch is plumbing here: it owns device memory and streams; every computation below is one call
+into libctr_b200.so.  Functions validate devices/dtypes and raise instead of falling back.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+F32, I64 = torch.float32, torch.int64
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str, shape=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+# ------------------------------------------------------------------ Row L + FM2
+def embed_fm2_fwd(table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor,
+                  want_tile: bool = True, want_fm2: bool = True,
+                  tile: Optional[torch.Tensor] = None, fm2: Optional[torch.Tensor] = None
+                  ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Fused lookup (+ FM second-order logit).  table (V,D); field_row_offset (F+1,) i64; ids (B,F) i64.
+    Returns (tile (B,F,D) | None, fm2 (B,1) | None)."""
+    B, F = ids.shape
+    D = table.shape[1]
+    _chk(table, F32, "table"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,)); _chk(ids, I64, "ids")
+    if want_tile and tile is None:
+        tile = torch.empty((B, F, D), dtype=F32, device=table.device)
+    if want_fm2 and fm2 is None:
+        fm2 = torch.empty((B, 1), dtype=F32, device=table.device)
+    _chk(tile, F32, "tile", (B, F, D)); _chk(fm2, F32, "fm2", (B, 1))
+    _lib.check(_lib.lib().ctr_embed_fm2_fwd(_ptr(table), _ptr(field_row_offset), _ptr(ids), B, F, D,
+                                            _ptr(tile), _ptr(fm2), _stream()))
+    return tile, fm2
+
+
+def embed_fm2_bwd(tile: torch.Tensor, d_tile: Optional[torch.Tensor], d_fm2: Optional[torch.Tensor],
+                  row_grads: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """IndexedSlices values (B,F,D) of the lookup gradient: d_tile + d_fm2 * (S - e)."""
+    B, F, D = tile.shape
+    _chk(tile, F32, "tile"); _chk(d_tile, F32, "d_tile", (B, F, D))
+    if d_fm2 is not None:
+        d_fm2 = d_fm2.reshape(B)
+    _chk(d_fm2, F32, "d_fm2", (B,))
+    if row_grads is None:
+        row_grads = torch.empty_like(tile)
+    _chk(row_grads, F32, "row_grads", (B, F, D))
+    _lib.check(_lib.lib().ctr_embed_fm2_bwd(_ptr(tile), _ptr(d_tile), _ptr(d_fm2), B, F, D, _ptr(row_grads), _stream()))
+    return row_grads
+
+
+def embed_scatter_add(grad_table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor,
+                      row_grads: torch.Tensor) -> torch.Tensor:
+    B, F, D = row_grads.shape
+    _chk(grad_table, F32, "grad_table"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,))
+    _chk(ids, I64, "ids", (B, F)); _chk(row_grads, F32, "row_grads")
+    _lib.check(_lib.lib().ctr_embed_scatter_add(_ptr(grad_table), _ptr(field_row_offset), _ptr(ids), _ptr(row_grads),
+                                                B, F, D, _stream()))
+    return grad_table
+
+
+def bag_lookup_fwd(table: torch.Tensor, ids: torch.Tensor, offsets: torch.Tensor,
+                   out: Optional[torch.Tensor] = None, out_col: int = 0) -> torch.Tensor:
+    """Multi-valued lookup, combiner='mean'.  Writes out[:, out_col:out_col+D] of a (B, stride) buffer."""
+    V, D = table.shape
+    B = offsets.numel() - 1
+    _chk(table, F32, "table"); _chk(ids, I64, "ids"); _chk(offsets, I64, "offsets")
+    if out is None:
+        out = torch.empty((B, D), dtype=F32, device=table.device)
+    _chk(out, F32, "out")
+    stride = out.shape[1]
+    if out_col + D > stride:
+        raise ValueError("bag_lookup_fwd: field does not fit in the output row")
+    _lib.check(_lib.lib().ctr_bag_lookup_fwd(_ptr(table), V, D, _ptr(ids), _ptr(offsets), B,
+                                             out.data_ptr() + 4 * out_col, stride, _stream()))
+    return out
+
+
+def bag_lookup_bwd(d_out: torch.Tensor, out_col: int, V: int, D: int, ids: torch.Tensor,
+                   offsets: torch.Tensor) -> torch.Tensor:
+    B = offsets.numel() - 1
+    _chk(d_out, F32, "d_out"); _chk(ids, I64, "ids"); _chk(offsets, I64, "offsets")
+    row_grads = torch.empty((ids.numel(), D), dtype=F32, device=d_out.device)
+    _lib.check(_lib.lib().ctr_bag_lookup_bwd(d_out.data_ptr() + 4 * out_col, d_out.shape[1], V, D, _ptr(ids),
+                                             _ptr(offsets), B, _ptr(row_grads), _stream()))
+    return row_grads
+
+
+# ------------------------------------------------------------------ Row CROSS
+def cross_fwd(x0: torch.Tensor, w: torch.Tensor, b: torch.Tensor, xl_in: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x_L of the cross stack.  x0 (B,d); w, b (L,d); xl_in optional start vector (default x0)."""
+    B, d = x0.shape
+    L = w.shape[0]
+    _chk(x0, F32, "x0"); _chk(w, F32, "w", (L, d)); _chk(b, F32, "b", (L, d)); _chk(xl_in, F32, "xl_in", (B, d))
+    if out is None:
+        out = torch.empty_like(x0)
+    _chk(out, F32, "out", (B, d))
+    _lib.check(_lib.lib().ctr_cross_fwd(_ptr(x0), _ptr(xl_in), _ptr(w), _ptr(b), B, d, L, _ptr(out), _stream()))
+    return out
+
+
+def cross_bwd(x0, w, b, g_out, xl_in=None):
+    """Returns (dx0, dxl_in | None, dw, db)."""
+    B, d = x0.shape
+    L = w.shape[0]
+    _chk(x0, F32, "x0"); _chk(w, F32, "w", (L, d)); _chk(b, F32, "b", (L, d))
+    _chk(g_out, F32, "g_out", (B, d)); _chk(xl_in, F32, "xl_in", (B, d))
+    dx0 = torch.empty_like(x0)
+    dxl = torch.empty_like(x0) if xl_in is not None else None
+    dw = torch.empty_like(w)
+    db = torch.empty_like(b)
+    _lib.check(_lib.lib().ctr_cross_bwd(_ptr(x0), _ptr(xl_in), _ptr(w), _ptr(b), _ptr(g_out), B, d, L,
+                                        _ptr(dx0), _ptr(dxl), _ptr(dw), _ptr(db), _stream()))
+    return dx0, dxl, dw, db
+
+
+# ------------------------------------------------------------------ Row DIN-ATT
+DIN_PARAM_SHAPES = lambda H: [(4 * H, 64), (64,), (64, 32), (32,), (32, 1), (1,)]   # f1_att / f2_att / f3_att kernel+bias
+
+
+def _din_params(H, w1, b1, w2, b2, w3, b3):
+    w3 = w3.reshape(32)
+    b3 = b3.reshape(1)
+    for t, n, s in ((w1, "w1", (4 * H, 64)), (b1, "b1", (64,)), (w2, "w2", (64, 32)), (b2, "b2", (32,)),
+                    (w3, "w3", (32,)), (b3, "b3", (1,))):
+        _chk(t, F32, n, s)
+    return w1, b1, w2, b2, w3, b3
+
+
+def din_attention_fwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, is_softmax=False, want_weights=False):
+    """DIN attention unit.  query (B,H); keys (B,T,H); keys_length (B,) int64.  Returns out (B,H) [, att_w (B,T)]."""
+    B, T, H = keys.shape
+    _chk(query, F32, "query", (B, H)); _chk(keys, F32, "keys"); _chk(keys_length, I64, "keys_length", (B,))
+    w1, b1, w2, b2, w3, b3 = _din_params(H, w1, b1, w2, b2, w3, b3)
+    out = torch.empty((B, H), dtype=F32, device=query.device)
+    att = torch.empty((B, T), dtype=F32, device=query.device) if want_weights else None
+    _lib.check(_lib.lib().ctr_din_attention_fwd(_ptr(query), _ptr(keys) if T > 0 else None, _ptr(keys_length), _ptr(w1),
+                                                _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), B, T, H,
+                                                int(bool(is_softmax)), _ptr(out), _ptr(att), _stream()))
+    return (out, att) if want_weights else out
+
+
+def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, is_softmax=False):
+    """Returns (d_query, d_keys, [dw1, db1, dw2, db2, dw3, db3])."""
+    B, T, H = keys.shape
+    _chk(query, F32, "query", (B, H)); _chk(keys, F32, "keys"); _chk(keys_length, I64, "keys_length", (B,))
+    _chk(g_out, F32, "g_out", (B, H))
+    w3_shape, b3_shape = w3.shape, b3.shape
+    w1, b1, w2, b2, w3, b3 = _din_params(H, w1, b1, w2, b2, w3, b3)
+    dq = torch.empty_like(query)
+    dk = torch.empty_like(keys)
+    sizes = [4 * H * 64, 64, 64 * 32, 32, 32, 1]
+    flat = torch.empty((sum(sizes),), dtype=F32, device=query.device)
+    _lib.check(_lib.lib().ctr_din_attention_bwd(_ptr(query), _ptr(keys) if T > 0 else None, _ptr(keys_length), _ptr(w1),
+                                                _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), _ptr(g_out), B, T, H,
+                                                int(bool(is_softmax)), _ptr(dq), _ptr(dk) if T > 0 else None, _ptr(flat),
+                                                _stream()))
+    parts = list(torch.split(flat, sizes))
+    shapes = [(4 * H, 64), (64,), (64, 32), (32,), tuple(w3_shape), tuple(b3_shape)]
+    return dq, dk, [p.reshape(s) for p, s in zip(parts, shapes)]
+
+
+# ------------------------------------------------------------------ Rows SENET / BILINEAR
+def senet_fwd(x, w1, w2):
+    B, F, K = x.shape
+    r = w1.shape[1]
+    _chk(x, F32, "x"); _chk(w1, F32, "w1", (F, r)); _chk(w2, F32, "w2", (r, F))
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().ctr_senet_fwd(_ptr(x), _ptr(w1), _ptr(w2), B, F, K, r, _ptr(out), _stream()))
+    return out
+
+
+def senet_bwd(x, w1, w2, g_out):
+    B, F, K = x.shape
+    r = w1.shape[1]
+    _chk(x, F32, "x"); _chk(w1, F32, "w1", (F, r)); _chk(w2, F32, "w2", (r, F)); _chk(g_out, F32, "g_out", (B, F, K))
+    dx, dw1, dw2 = torch.empty_like(x), torch.empty_like(w1), torch.empty_like(w2)
+    _lib.check(_lib.lib().ctr_senet_bwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(g_out), B, F, K, r, _ptr(dx), _ptr(dw1),
+                                        _ptr(dw2), _stream()))
+    return dx, dw1, dw2
+
+
+BILINEAR_TYPES = {"all": 0, "each": 1, "interaction": 2}
+
+
+def _bilinear_type(type_):
+    if type_ not in BILINEAR_TYPES:      # same message as FiBiNET/bilinear_interaction_layer.py:36-38
+        raise ValueError(f"Bilinear Interaction type must be in ['all','each','interaction'], got '{type_}'")
+    return BILINEAR_TYPES[type_]
+
+
+def bilinear_w_shape(F, K, type_):
+    return {"all": (K, K), "each": (F - 1, K, K), "interaction": (F * (F - 1) // 2, K, K)}[type_]
+
+
+def bilinear_fwd(x, w, type_):
+    t = _bilinear_type(type_)
+    B, F, K = x.shape
+    _chk(x, F32, "x"); _chk(w, F32, "w", bilinear_w_shape(F, K, type_))
+    P = (F - 1) * (F - 2) // 2
+    out = torch.empty((B, P, K), dtype=F32, device=x.device)
+    _lib.check(_lib.lib().ctr_bilinear_fwd(_ptr(x), _ptr(w), B, F, K, t, _ptr(out), _stream()))
+    return out
+
+
+def bilinear_bwd(x, w, type_, g_out):
+    t = _bilinear_type(type_)
+    B, F, K = x.shape
+    P = (F - 1) * (F - 2) // 2
+    _chk(x, F32, "x"); _chk(w, F32, "w", bilinear_w_shape(F, K, type_)); _chk(g_out, F32, "g_out", (B, P, K))
+    dx, dw = torch.empty_like(x), torch.empty_like(w)
+    _lib.check(_lib.lib().ctr_bilinear_bwd(_ptr(x), _ptr(w), _ptr(g_out), B, F, K, t, _ptr(dx), _ptr(dw), _stream()))
+    return dx, dw

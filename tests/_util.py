@@ -1,0 +1,39 @@
+"""Shared helpers for the GPU parity tests."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-5   # BASELINE.json north_star: interaction-layer fp32 outputs within 1e-5 relative
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def relerr(a, b):
+    """max-norm relative error: max|a-b| / max|b| (b = reference, float64 preferred)."""
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def assert_close(a, b, tol=TOL, what=""):
+    e = relerr(a, b)
+    assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e}"
+
+
+def trunc_normal(rng, shape, std):
+    x = np.clip(rng.standard_normal(shape), -2, 2)
+    return (x * std).astype(np.float32)

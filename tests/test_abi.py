@@ -1,0 +1,55 @@
+"""CPU tests: the C-ABI library loads and exports exactly what include/ctr_b200.h declares."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    hdr = open(os.path.join(ROOT, "include", "ctr_b200.h")).read()
+    return set(re.findall(r"\b(ctr_[a-z0-9_]+)\s*\(", hdr))
+
+
+def test_library_exports_every_declared_symbol():
+    from recalgorithm_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    handle = _lib.lib()                         # raises AttributeError if a declared symbol is missing
+    declared = header_symbols()
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (ctr_[a-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    assert handle.ctr_version() == 1
+
+
+def test_argument_validation_happens_before_any_launch():
+    """Bad arguments are rejected on the host with an error string (no GPU needed, no compute call)."""
+    from recalgorithm_b200 import _lib
+    h = _lib.lib()
+    assert h.ctr_embed_fm2_fwd(None, None, None, 1, 1, 3, None, None, None) == _lib.CTR_ERR_UNSUPPORTED
+    assert b"D=3" in h.ctr_last_error()
+    assert h.ctr_cross_fwd(None, None, None, None, 4, 0, 1, None, None) == _lib.CTR_ERR_INVALID_ARG
+    with pytest.raises(_lib.CtrInvalidArgument):
+        _lib.check(h.ctr_cross_fwd(None, None, None, None, 4, 8, 99, None, None))
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing on the host."""
+    import torch
+    from recalgorithm_b200 import ops
+    t = torch.zeros((4, 8))
+    with pytest.raises(RuntimeError):
+        ops.embed_fm2_fwd(t, torch.tensor([0, 4]), torch.zeros((2, 1), dtype=torch.int64))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "recalgorithm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
