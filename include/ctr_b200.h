@@ -97,12 +97,17 @@ int ctr_cross_bwd(const float* x0, const float* xl_in, const float* w, const flo
  * x0 (B,m,D); xk (B,hk,D); filter (hk*m, H) = the conv1d filter (1, hk*m, hk_1)[0]; out (B,H,D);
  * pooled (B,H) = sum_d out (the reduce_sum of xDeepFM/xdeepfm.py:173) or NULL.
  * precision: 0 = fp32-class (3xTF32 split on the tensor cores; default, meets 1e-5),
- *            1 = single-pass TF32 (about 1e-3; for speed comparisons only). */
+ *            1 = single-pass TF32 (about 1e-3; for speed comparisons only).
+ * workspace: ctr_cin_fwd_workspace_bytes() bytes, 128-byte aligned (holds the filter re-ordered / tf32-split for
+ *            TMA); may be NULL when that query returns 0 (shapes served by the CUDA-core path). */
+int64_t ctr_cin_fwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H);
 int ctr_cin_fwd(const float* x0, const float* xk, const float* filter, int64_t B, int64_t m, int64_t hk,
-                int64_t D, int64_t H, float* out, float* pooled, int precision, void* stream);
+                int64_t D, int64_t H, float* out, float* pooled, int precision,
+                void* workspace, int64_t workspace_bytes, void* stream);
+/* Gradients of ctr_cin_fwd given g_out (B,H,D); dx0 (B,m,D), dxk (B,hk,D), dfilter (hk*m,H) are overwritten. */
 int ctr_cin_bwd(const float* x0, const float* xk, const float* filter, const float* g_out,
                 int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H,
-                float* dx0 /* accumulated into (+=) */, float* dxk /* overwritten */, float* dfilter /* overwritten */,
+                float* dx0, float* dxk, float* dfilter,
                 void* workspace, int64_t workspace_bytes, void* stream);
 int64_t ctr_cin_bwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H);
 

@@ -107,3 +107,85 @@ class _CrossStack(torch.autograd.Function):
 def cross_stack(x0: torch.Tensor, w: torch.Tensor, b: torch.Tensor, xl: Optional[torch.Tensor] = None) -> torch.Tensor:
     """All L cross layers (DCN/dcn.py:157-160) in one launch.  w, b: (L, d)."""
     return _CrossStack.apply(x0, xl, w, b)
+
+
+class _CIN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, xk, filt, want_pooled):
+        x0c, xkc, fc_ = x0.contiguous(), xk.contiguous(), filt.contiguous()
+        ctx.save_for_backward(x0c, xkc, fc_)
+        ctx.want_pooled = want_pooled
+        if want_pooled:
+            out, pooled = ops.cin_fwd(x0c, xkc, fc_, want_pooled=True)
+            return out, pooled
+        return ops.cin_fwd(x0c, xkc, fc_)
+
+    @staticmethod
+    def backward(ctx, g_out, g_pooled=None):
+        x0, xk, filt = ctx.saved_tensors
+        if g_out is None:
+            g_out = torch.zeros((x0.shape[0], filt.shape[1], x0.shape[2]), dtype=x0.dtype, device=x0.device)
+        if g_pooled is not None:
+            g_out = g_out + g_pooled.unsqueeze(-1)          # pooled = sum_d out
+        dx0, dxk, dw = ops.cin_bwd(x0, xk, filt, g_out.contiguous())
+        return dx0, dxk, dw, None
+
+
+def cin(x0, xk, filt, want_pooled=False):
+    """One CIN layer on the tensor cores: (B,m,D),(B,hk,D),(hk*m,H) -> (B,H,D) [, sum over D (B,H)]."""
+    return _CIN.apply(x0, xk, filt, want_pooled)
+
+
+class _DinAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query, keys, keys_length, is_softmax, w1, b1, w2, b2, w3, b3):
+        args = [t.contiguous() for t in (query, keys)] + [keys_length.contiguous()] + \
+               [t.contiguous() for t in (w1, b1, w2, b2, w3, b3)]
+        ctx.save_for_backward(*args)
+        ctx.is_softmax = bool(is_softmax)
+        return ops.din_attention_fwd(*args, is_softmax=ctx.is_softmax)
+
+    @staticmethod
+    def backward(ctx, g):
+        args = ctx.saved_tensors
+        dq, dk, dws = ops.din_attention_bwd(*args, g.contiguous(), is_softmax=ctx.is_softmax)
+        return (dq, dk, None, None, *dws)
+
+
+def din_attention(query, keys, keys_length, w1, b1, w2, b2, w3, b3, is_softmax=False):
+    return _DinAttention.apply(query, keys, keys_length, is_softmax, w1, b1, w2, b2, w3, b3)
+
+
+class _Senet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, w2):
+        xc, w1c, w2c = x.contiguous(), w1.contiguous(), w2.contiguous()
+        ctx.save_for_backward(xc, w1c, w2c)
+        return ops.senet_fwd(xc, w1c, w2c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.senet_bwd(*ctx.saved_tensors, g.contiguous())
+
+
+def senet(x, w1, w2):
+    return _Senet.apply(x, w1, w2)
+
+
+class _Bilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, type_):
+        xc, wc = x.contiguous(), w.contiguous()
+        ctx.save_for_backward(xc, wc)
+        ctx.type_ = type_
+        return ops.bilinear_fwd(xc, wc, type_)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        dx, dw = ops.bilinear_bwd(x, w, ctx.type_, g.contiguous())
+        return dx, dw, None
+
+
+def bilinear(x, w, type_):
+    return _Bilinear.apply(x, w, type_)

@@ -1,0 +1,576 @@
+// Row CIN: the xDeepFM compressed-interaction layer.
+//
+// Reference: cin_layer(x0, xk, hk_1, index) -- xDeepFM/cin_layer.py:17-30
+//   outer[b,d,i,j] = xk[b,i,d] * x0[b,j,d]; reshape (B, D, hk*m) with flat index i*m+j; conv1d with a
+//   (1, hk*m, hk_1) filter == matmul over the last axis; transpose -> (B, hk_1, D).  The reference
+//   materialises the (B, D, hk*m) outer tensor (2 GB at BASELINE config 3, layer 2).
+//
+// B200 mapping -- the one genuinely dense contraction of the hot path, so it runs on the 5th-gen tensor cores:
+//   GEMM view  C[M x N] = A[M x K] . B[K x N],  M = B*D rows r = (b,d),  K = hk*m,  N = hk_1.
+//   * A (the outer product) is never written to HBM: 256 producer threads each own one row r, keep the row's
+//     x0[b,:,d] (m <= 32 values) in registers and, for every K-block i, form the 32 products xk[b,i,d]*x0[b,j,d],
+//     and store them straight into shared memory in the UMMA canonical K-major SWIZZLE_128B layout
+//     (K is re-ordered as i*32 + j, zero padded from m to 32, so one K-block == one i == one 128-byte swizzle row);
+//   * B (the filter) is pre-transposed/padded once per call into that K order (workspace) and streamed by TMA
+//     (cp.async.bulk.tensor, SWIZZLE_128B) through an mbarrier pipeline;
+//   * one elected thread issues tcgen05.mma (kind::tf32, M=128, N=hk_1 padded to 16, K=8); accumulators live in
+//     TMEM (2 M-tiles x N columns per CTA so that every B stage is used twice); tcgen05.commit releases stages;
+//   * fp32-class accuracy (north_star: 1e-5) comes from the 3xTF32 split  A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo
+//     with fp32 accumulation in TMEM (error ~2^-22 per product); precision=1 runs a single TF32 pass (~1e-3);
+//   * epilogue: tcgen05.ld -> registers -> (B, hk_1, D) stores + the pooled sum over D by warp shuffles.
+//   Shapes outside the tensor path's limits (m > 32, hk_1 > 128, D not a power of two <= 32) use a plain
+//   CUDA-core kernel.  The backward pass is CUDA-core in this revision (next step).
+#include <cuda.h>
+
+#include "ctr_common.cuh"
+
+namespace ctr {
+namespace cin {
+
+constexpr int BM = 128;                  // rows per UMMA tile
+constexpr int TILES = 2;                 // M tiles per CTA
+constexpr int KB = 32;                   // tf32 per K-block (128 B == swizzle span)
+constexpr int A_TILE_BYTES = BM * 128;   // 16 KB
+constexpr int NTHREADS = 320;            // 8 producer/epilogue warps + TMA warp + MMA warp
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem], kind::tf32
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address           bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset      bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
+__host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct FwdSmem {
+  int stage_bytes, a_bytes_per_tile, b_tile_bytes, bar_off, total;
+};
+__host__ __device__ inline FwdSmem fwd_smem(int NP, int passes, int stages) {
+  FwdSmem s;
+  const int na = passes == 3 ? 2 : 1;
+  s.a_bytes_per_tile = na * A_TILE_BYTES;
+  s.b_tile_bytes = NP * 128;
+  s.stage_bytes = TILES * s.a_bytes_per_tile + na * s.b_tile_bytes;
+  s.bar_off = stages * s.stage_bytes;
+  s.total = s.bar_off + 8 * (3 * stages + 2) + 16;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+// filter (hk*m, H) -> Wt[2][NP][KP]: [0] = tf32-rounded value, [1] = residual; K order i*32 + j, zero padded.
+__global__ void cin_split_filter_kernel(const float* __restrict__ w, float* __restrict__ wt, int m, int hk, int H, int NP) {
+  const int KP = hk * KB;
+  const size_t total = (size_t)NP * KP;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / KP), kk = (int)(idx % KP);
+    const int i = kk / KB, j = kk % KB;
+    float v = 0.f;
+    if (n < H && j < m) v = __ldg(w + ((size_t)i * m + j) * H + n);
+    const float hi = tf32_rna(v);
+    wt[idx] = hi;
+    wt[total + idx] = v - hi;
+  }
+}
+
+template <int PASSES, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ x0,
+                  const float* __restrict__ xk, float* __restrict__ out, float* __restrict__ pooled, int B, int m,
+                  int hk, int logD, int H, int NP, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles: align explicitly (the launch adds 1 KB of slack)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const FwdSmem L = fwd_smem(NP, PASSES, STAGES);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + L.bar_off;
+  auto full_a = [&](int s) { return bar0 + 8 * s; };
+  auto full_b = [&](int s) { return bar0 + 8 * (STAGES + s); };
+  auto empty = [&](int s) { return bar0 + 8 * (2 * STAGES + s); };
+  const uint32_t tmem_full = bar0 + 8 * (3 * STAGES), tmem_empty = tmem_full + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (3 * STAGES + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = 1 << logD;
+  const long long rows_total = (long long)B * D;
+  const int num_tiles = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
+  constexpr int NA = PASSES == 3 ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), 8); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(smem_u32(tmem_ptr), (uint32_t)tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 8) {
+    // ============================ A producers (one row each) + epilogue ============================
+    const int t = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    const int sw = row & 7;
+    int s = 0, ph = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const long long r = (long long)tile * (TILES * BM) + t * BM + row;
+      const bool valid = r < rows_total;
+      const int b = valid ? (int)(r >> logD) : 0;
+      const int d = (int)(r & (D - 1));
+      float x0v[KB];
+#pragma unroll
+      for (int j = 0; j < KB; ++j) x0v[j] = (valid && j < m) ? __ldg(x0 + ((size_t)b * m + j) * D + d) : 0.f;
+      const float* xkp = xk + (size_t)b * hk * D + d;
+      float xnext = valid ? __ldg(xkp) : 0.f;
+      for (int i = 0; i < hk; ++i) {
+        const float xi = xnext;
+        if (i + 1 < hk) xnext = valid ? __ldg(xkp + (size_t)(i + 1) * D) : 0.f;
+        mbar_wait(empty(s), ph ^ 1);
+        const uint32_t a_hi = sbase + s * L.stage_bytes + t * L.a_bytes_per_tile + row_off;
+#pragma unroll
+        for (int c = 0; c < KB / 4; ++c) {
+          const float p0 = xi * x0v[4 * c + 0], p1 = xi * x0v[4 * c + 1], p2 = xi * x0v[4 * c + 2],
+                      p3 = xi * x0v[4 * c + 3];
+          const uint32_t off = (uint32_t)((c ^ sw) << 4);
+          if (PASSES == 3) {
+            const float h0 = tf32_rna(p0), h1 = tf32_rna(p1), h2 = tf32_rna(p2), h3 = tf32_rna(p3);
+            sts_f4(a_hi + off, h0, h1, h2, h3);
+            sts_f4(a_hi + A_TILE_BYTES + off, p0 - h0, p1 - h1, p2 - h2, p3 - h3);
+          } else {
+            sts_f4(a_hi + off, p0, p1, p2, p3);
+          }
+        }
+        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_a(s));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      // ---------------- epilogue: TMEM -> registers -> out (B,H,D) and pooled (B,H) ----------------
+      mbar_wait(tmem_full, lt & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * NP);
+      for (int c0 = 0; c0 < NP; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int n = c0 + q;
+          if (n < H) {
+            if (valid) out[((size_t)b * H + n) * D + d] = v[q];
+            if (pooled != nullptr) {
+              float sred = valid ? v[q] : 0.f;
+              for (int o = D >> 1; o > 0; o >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, o);
+              if (valid && d == 0) pooled[(size_t)b * H + n] = sred;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  } else if (warp == 8) {
+    // ============================ TMA producer for the filter tiles ============================
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int i = 0; i < hk; ++i) {
+          mbar_wait(empty(s), ph ^ 1);
+          const uint32_t b_dst = sbase + s * L.stage_bytes + TILES * L.a_bytes_per_tile;
+          mbar_expect_tx(full_b(s), (uint32_t)(NA * L.b_tile_bytes));
+          tma_load_2d(b_dst, &tmap_w, i * KB, 0, full_b(s));
+          if (PASSES == 3) tma_load_2d(b_dst + L.b_tile_bytes, &tmap_w, i * KB, NP, full_b(s));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(NP);
+      int s = 0, ph = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        mbar_wait(tmem_empty, (lt & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
+        tc_fence_after();
+        for (int i = 0; i < hk; ++i) {
+          mbar_wait(full_a(s), ph);
+          mbar_wait(full_b(s), ph);
+          tc_fence_after();
+          const uint32_t st_base = sbase + s * L.stage_bytes;
+          const uint64_t b_hi = umma_desc_sw128(st_base + TILES * L.a_bytes_per_tile);
+          const uint64_t b_lo = umma_desc_sw128(st_base + TILES * L.a_bytes_per_tile + L.b_tile_bytes);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+            const uint64_t a_hi = umma_desc_sw128(st_base + t * L.a_bytes_per_tile);
+            const uint64_t a_lo = umma_desc_sw128(st_base + t * L.a_bytes_per_tile + A_TILE_BYTES);
+            const uint32_t dcol = tmem_base + (uint32_t)(t * NP);
+#pragma unroll
+            for (int k = 0; k < KB / 8; ++k)          // 32 B per K=8 step inside the 128 B swizzle row
+              umma_tf32(dcol, a_hi + 2 * k, b_hi + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (PASSES == 3) {
+#pragma unroll
+              for (int k = 0; k < KB / 8; ++k) umma_tf32(dcol, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < KB / 8; ++k) umma_tf32(dcol, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            }
+          }
+          umma_commit(empty(s));                       // frees the stage when these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tmem_full);                        // accumulators complete -> epilogue
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
+// ---- CUDA-core forward for shapes outside the tensor path.  One CTA per sample.
+__global__ void __launch_bounds__(256)
+cin_fwd_simple_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ w,
+                      float* __restrict__ out, float* __restrict__ pooled, int B, int m, int hk, int D, int H) {
+  extern __shared__ __align__(16) float sm[];
+  float* x0s = sm;
+  float* xks = sm + m * D;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * D; i += blockDim.x) x0s[i] = __ldg(x0 + (size_t)b * m * D + i);
+    for (int i = threadIdx.x; i < hk * D; i += blockDim.x) xks[i] = __ldg(xk + (size_t)b * hk * D + i);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < H * D; idx += blockDim.x) {
+      const int n = idx / D, d = idx % D;
+      float acc = 0.f;
+      for (int i = 0; i < hk; ++i) {
+        const float a = xks[i * D + d];
+        const float* wr = w + (size_t)i * m * H + n;
+        for (int j = 0; j < m; ++j) acc += (a * x0s[j * D + d]) * __ldg(wr + (size_t)j * H);
+      }
+      out[(size_t)b * H * D + idx] = acc;
+    }
+    if (pooled != nullptr) {
+      __syncthreads();
+      for (int n = threadIdx.x; n < H; n += blockDim.x) {
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s += out[((size_t)b * H + n) * D + d];
+        pooled[(size_t)b * H + n] = s;
+      }
+    }
+  }
+}
+
+// ---- CUDA-core backward, data gradients.  One CTA per sample.
+//   dz[p,d] = sum_n g[n,d]*W[p,n];  dxk[i,d] += dz*x0[j,d];  dx0[j,d] += dz*xk[i,d]      (p = i*m + j)
+__global__ void __launch_bounds__(256)
+cin_bwd_dx_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ w,
+                  const float* __restrict__ g, int B, int m, int hk, int D, int H, float* __restrict__ dx0,
+                  float* __restrict__ dxk) {
+  extern __shared__ __align__(16) float sm[];
+  float* x0s = sm;
+  float* xks = x0s + m * D;
+  float* gs = xks + hk * D;
+  float* dx0s = gs + H * D;
+  float* dxks = dx0s + m * D;
+  const int d = threadIdx.x % D, pl = threadIdx.x / D, pstep = blockDim.x / D;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * D; i += blockDim.x) { x0s[i] = __ldg(x0 + (size_t)b * m * D + i); dx0s[i] = 0.f; }
+    for (int i = threadIdx.x; i < hk * D; i += blockDim.x) { xks[i] = __ldg(xk + (size_t)b * hk * D + i); dxks[i] = 0.f; }
+    for (int i = threadIdx.x; i < H * D; i += blockDim.x) gs[i] = __ldg(g + (size_t)b * H * D + i);
+    __syncthreads();
+    if (pl < pstep) {
+      for (int p = pl; p < hk * m; p += pstep) {
+        const float* wr = w + (size_t)p * H;
+        float dz = 0.f;
+        for (int n = 0; n < H; ++n) dz += gs[n * D + d] * __ldg(wr + n);
+        const int i = p / m, j = p % m;
+        atomicAdd(dxks + i * D + d, dz * x0s[j * D + d]);
+        atomicAdd(dx0s + j * D + d, dz * xks[i * D + d]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * D; i += blockDim.x) dx0[(size_t)b * m * D + i] = dx0s[i];
+    for (int i = threadIdx.x; i < hk * D; i += blockDim.x) dxk[(size_t)b * hk * D + i] = dxks[i];
+  }
+}
+
+// ---- CUDA-core backward, filter gradient: dW[p,n] = sum_{b,d} xk[b,i,d]*x0[b,j,d]*g[b,n,d].
+// grid (ceil(hk*m / PC), nsplit); block = threads over n; each CTA streams its share of the batch.
+constexpr int CIN_PC = 16;
+__global__ void __launch_bounds__(256)
+cin_bwd_dw_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ g, int B, int m,
+                  int hk, int D, int H, float* __restrict__ dw) {
+  extern __shared__ __align__(16) float sm[];
+  float* gs = sm;                         // (H, D+1) padded against bank conflicts
+  float* zs = gs + H * (D + 1);           // (PC, D)
+  const int p0 = blockIdx.x * CIN_PC;
+  const int K = hk * m;
+  float acc[CIN_PC];
+#pragma unroll
+  for (int q = 0; q < CIN_PC; ++q) acc[q] = 0.f;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * D; i += blockDim.x) gs[(i / D) * (D + 1) + i % D] = __ldg(g + (size_t)b * H * D + i);
+    for (int i = threadIdx.x; i < CIN_PC * D; i += blockDim.x) {
+      const int q = i / D, d = i % D, p = p0 + q;
+      float z = 0.f;
+      if (p < K) z = __ldg(xk + ((size_t)b * hk + p / m) * D + d) * __ldg(x0 + ((size_t)b * m + p % m) * D + d);
+      zs[i] = z;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < H; n += blockDim.x) {     // H <= blockDim in practice: one n per thread
+      for (int d = 0; d < D; ++d) {
+        const float gv = gs[n * (D + 1) + d];
+#pragma unroll
+        for (int q = 0; q < CIN_PC; ++q) acc[q] += zs[q * D + d] * gv;
+      }
+    }
+  }
+  const int n = threadIdx.x;
+  if (n < H) {
+#pragma unroll
+    for (int q = 0; q < CIN_PC; ++q)
+      if (p0 + q < K) atomicAdd(dw + (size_t)(p0 + q) * H + n, acc[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool tensor_path_ok(int64_t m, int64_t hk, int64_t D, int64_t H) {
+  return m >= 1 && m <= KB && hk >= 1 && H >= 1 && H <= 128 && D >= 1 && D <= 32 && (D & (D - 1)) == 0;
+}
+static int64_t pad16(int64_t h) { return (h + 15) / 16 * 16; }
+
+}  // namespace cin
+}  // namespace ctr
+
+using namespace ctr;
+using namespace ctr::cin;
+
+extern "C" int64_t ctr_cin_fwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H) {
+  (void)B;
+  if (!tensor_path_ok(m, hk, D, H)) return 0;
+  return 2 * pad16(H) * hk * KB * (int64_t)sizeof(float);
+}
+
+static int check_cin(const char* fn, int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H) {
+  CTR_REQUIRE(B >= 0 && m >= 1 && hk >= 1 && D >= 1 && H >= 1, "%s: bad sizes B=%lld m=%lld hk=%lld D=%lld H=%lld", fn,
+              (long long)B, (long long)m, (long long)hk, (long long)D, (long long)H);
+  CTR_UNSUPPORTED(B * D > 0x7fffffffLL || hk * m > (1 << 24), "%s: problem too large", fn);
+  return CTR_OK;
+}
+
+extern "C" int ctr_cin_fwd(const float* x0, const float* xk, const float* filter, int64_t B, int64_t m, int64_t hk,
+                           int64_t D, int64_t H, float* out, float* pooled, int precision, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  int rc = check_cin("ctr_cin_fwd", B, m, hk, D, H);
+  if (rc) return rc;
+  CTR_REQUIRE(x0 && xk && filter && out, "ctr_cin_fwd: null argument");
+  CTR_REQUIRE(precision == 0 || precision == 1, "ctr_cin_fwd: precision must be 0 (3xTF32) or 1 (TF32)");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  if (!tensor_path_ok(m, hk, D, H)) {
+    const size_t smem = sizeof(float) * (size_t)(m + hk) * D;
+    CTR_UNSUPPORTED(smem > 200 * 1024, "ctr_cin_fwd: (m+hk)*D too large for the CUDA-core path");
+    if (smem > 48 * 1024)
+      CTR_CUDA(cudaFuncSetAttribute(cin_fwd_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)(B < (int64_t)sm_count() * 4 ? B : (int64_t)sm_count() * 4);
+    cin_fwd_simple_kernel<<<grid, 256, smem, st>>>(x0, xk, filter, out, pooled, (int)B, (int)m, (int)hk, (int)D, (int)H);
+    CTR_CHECK_LAUNCH("ctr_cin_fwd(simple)");
+    return CTR_OK;
+  }
+  const int NP = (int)pad16(H);
+  const int64_t need = ctr_cin_fwd_workspace_bytes(B, m, hk, D, H);
+  CTR_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+              "ctr_cin_fwd: workspace of %lld bytes required (ctr_cin_fwd_workspace_bytes), got %lld", (long long)need,
+              (long long)workspace_bytes);
+  CTR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, "ctr_cin_fwd: workspace must be 128-byte aligned");
+  float* wt = static_cast<float*>(workspace);
+  const int KP = (int)hk * KB;
+  {
+    const long long total = (long long)NP * KP;
+    const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    cin_split_filter_kernel<<<grid, 256, 0, st>>>(filter, wt, (int)m, (int)hk, (int)H, NP);
+    CTR_CHECK_LAUNCH("ctr_cin_fwd(split filter)");
+  }
+  EncodeTiledFn enc = encode_tiled();
+  if (enc == nullptr) {
+    set_error("ctr_cin_fwd: cuTensorMapEncodeTiled is not available from the driver");
+    return CTR_ERR_CUDA;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)KP, (cuuint64_t)(2 * NP)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)KP * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)NP};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, wt, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("ctr_cin_fwd: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    return CTR_ERR_CUDA;
+  }
+  int logD = 0;
+  while ((1 << logD) < D) ++logD;
+  const long long rows_total = (long long)B * D;
+  const int num_tiles = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  int tmem_cols = 32;
+  while (tmem_cols < TILES * NP) tmem_cols <<= 1;
+  if (precision == 0) {
+    constexpr int STAGES = 2;
+    const FwdSmem L = fwd_smem(NP, 3, STAGES);
+    auto k = cin_fwd_tc_kernel<3, STAGES>;
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total + 1024));
+    k<<<grid, NTHREADS, L.total + 1024, st>>>(tmap, x0, xk, out, pooled, (int)B, (int)m, (int)hk, logD, (int)H, NP, tmem_cols);
+  } else {
+    constexpr int STAGES = 4;
+    const FwdSmem L = fwd_smem(NP, 1, STAGES);
+    auto k = cin_fwd_tc_kernel<1, STAGES>;
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total + 1024));
+    k<<<grid, NTHREADS, L.total + 1024, st>>>(tmap, x0, xk, out, pooled, (int)B, (int)m, (int)hk, logD, (int)H, NP, tmem_cols);
+  }
+  CTR_CHECK_LAUNCH("ctr_cin_fwd(tcgen05)");
+  return CTR_OK;
+}
+
+extern "C" int64_t ctr_cin_bwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H) {
+  (void)B; (void)m; (void)hk; (void)D; (void)H;
+  return 0;
+}
+
+extern "C" int ctr_cin_bwd(const float* x0, const float* xk, const float* filter, const float* g_out, int64_t B,
+                           int64_t m, int64_t hk, int64_t D, int64_t H, float* dx0, float* dxk, float* dfilter,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  int rc = check_cin("ctr_cin_bwd", B, m, hk, D, H);
+  if (rc) return rc;
+  CTR_REQUIRE(x0 && xk && filter && g_out && dx0 && dxk && dfilter, "ctr_cin_bwd: null argument");
+  CTR_UNSUPPORTED(D > 256 || H > 256, "ctr_cin_bwd: D=%lld H=%lld too large", (long long)D, (long long)H);
+  cudaStream_t st = as_stream(stream);
+  CTR_CUDA(cudaMemsetAsync(dfilter, 0, sizeof(float) * hk * m * H, st));
+  if (B == 0) return CTR_OK;
+  {
+    const size_t smem = sizeof(float) * (size_t)(2 * (m + hk) + H) * D;
+    CTR_UNSUPPORTED(smem > 200 * 1024, "ctr_cin_bwd: shared memory need %zu B too large", smem);
+    if (smem > 48 * 1024)
+      CTR_CUDA(cudaFuncSetAttribute(cin_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)(B < (int64_t)sm_count() * 4 ? B : (int64_t)sm_count() * 4);
+    cin_bwd_dx_kernel<<<grid, 256, smem, st>>>(x0, xk, filter, g_out, (int)B, (int)m, (int)hk, (int)D, (int)H, dx0, dxk);
+    CTR_CHECK_LAUNCH("ctr_cin_bwd(dx)");
+  }
+  {
+    const size_t smem = sizeof(float) * (size_t)(H * (D + 1) + CIN_PC * D);
+    CTR_UNSUPPORTED(smem > 200 * 1024, "ctr_cin_bwd: shared memory need %zu B too large", smem);
+    if (smem > 48 * 1024)
+      CTR_CUDA(cudaFuncSetAttribute(cin_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int gx = (int)((hk * m + CIN_PC - 1) / CIN_PC);
+    int gy = (int)((int64_t)sm_count() * 4 / gx);
+    if (gy < 1) gy = 1;
+    if (gy > B) gy = (int)B;
+    cin_bwd_dw_kernel<<<dim3(gx, gy), 256, smem, st>>>(x0, xk, g_out, (int)B, (int)m, (int)hk, (int)D, (int)H, dfilter);
+    CTR_CHECK_LAUNCH("ctr_cin_bwd(dw)");
+  }
+  return CTR_OK;
+}

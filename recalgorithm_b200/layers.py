@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's layer interface (the drop-in boundary).
+
+The reference has no package API: each ``model_fn`` calls plain Python functions that create their
+parameters by side effect with ``tf.get_variable`` inside ``tf.variable_scope`` blocks.  The functions
+below keep those names, argument meanings, variable names/shapes and error behaviour, so that a
+``model_fn`` body ported to this engine reads like the reference's own:
+
+    with variable_scope("cross_part"):                 # DCN/dcn.py:156-160
+        cross_vec = concat_all
+        for i in range(params["num_cross_layer"]):
+            cross_vec = cross_layer(x0=concat_all, xl=cross_vec, index=i)
+
+Each call is one launch of the matching sm_100a kernel (through recalgorithm_b200.autograd); there
+is no other implementation behind these names.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import autograd
+
+AUTO_REUSE = "AUTO_REUSE"
+
+
+class VariableStore:
+    """Name-keyed parameter registry mirroring TF1 variable scopes (``tf.get_variable`` semantics:
+    create on first use with the default glorot-uniform initializer, reuse afterwards)."""
+
+    def __init__(self, device="cuda", seed: Optional[int] = None):
+        self.device = torch.device(device)
+        self.vars: Dict[str, torch.nn.Parameter] = {}
+        self.scope: List[str] = []
+        self.gen = torch.Generator(device="cpu")
+        if seed is not None:
+            self.gen.manual_seed(seed)
+
+    def full_name(self, name: str) -> str:
+        return "/".join(self.scope + [name])
+
+    def get_variable(self, name: str, shape, initializer=None) -> torch.nn.Parameter:
+        full = self.full_name(name)
+        shape = tuple(int(s) for s in shape)
+        if full in self.vars:
+            v = self.vars[full]
+            if tuple(v.shape) != shape:
+                raise ValueError(f"Trying to share variable {full}, but specified shape {shape} and found shape {tuple(v.shape)}.")
+            return v
+        if initializer is None:                         # tf.get_variable default: glorot_uniform_initializer
+            if len(shape) >= 2:
+                rf = 1
+                for s in shape[:-2]:
+                    rf *= s
+                fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+            else:
+                fan_in = fan_out = shape[0] if shape else 1
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            data = (torch.rand(shape, generator=self.gen) * 2 - 1) * lim
+        elif callable(initializer):
+            data = initializer(shape)
+        else:
+            data = torch.as_tensor(initializer, dtype=torch.float32).reshape(shape)
+        v = torch.nn.Parameter(data.to(torch.float32).to(self.device).contiguous())
+        self.vars[full] = v
+        return v
+
+    def assign(self, values: Dict[str, "torch.Tensor"]):
+        """Inject weights by their TF variable names (parity is defined on injected weights)."""
+        for k, val in values.items():
+            t = torch.as_tensor(val, dtype=torch.float32).to(self.device).contiguous()
+            if k in self.vars:
+                if tuple(self.vars[k].shape) != tuple(t.shape):
+                    raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(self.vars[k].shape)}")
+                self.vars[k].data.copy_(t)
+            else:
+                self.vars[k] = torch.nn.Parameter(t)
+
+    def parameters(self):
+        return list(self.vars.values())
+
+
+_default_store: Optional[VariableStore] = None
+
+
+def default_store() -> VariableStore:
+    global _default_store
+    if _default_store is None:
+        _default_store = VariableStore()
+    return _default_store
+
+
+def set_default_store(store: VariableStore) -> VariableStore:
+    global _default_store
+    _default_store = store
+    return store
+
+
+@contextlib.contextmanager
+def variable_scope(name: str, reuse=None):
+    st = default_store()
+    st.scope.append(name)
+    try:
+        yield
+    finally:
+        st.scope.pop()
+
+
+def get_variable(name, shape, dtype=None, initializer=None):
+    return default_store().get_variable(name, shape, initializer)
+
+
+# --------------------------------------------------------------------------------------------------- DCN
+def cross_layer(x0: torch.Tensor, xl: torch.Tensor, index: int) -> torch.Tensor:
+    """dcn cross layer -- same signature as DCN/cross_layer.py:4.  Variables ``wl_{index}``, ``bl_{index}`` of shape
+    (d, 1), default (glorot-uniform) initialised -- the bias is NOT zero-initialised in the reference (:18-19)."""
+    dimension = int(x0.shape[-1])
+    wl = get_variable(name=f"wl_{index}", shape=(dimension, 1))
+    bl = get_variable(name=f"bl_{index}", shape=(dimension, 1))
+    return autograd.cross_stack(x0, wl.reshape(1, dimension), bl.reshape(1, dimension), xl=None if xl is x0 else xl)
+
+
+def cross_network(x0: torch.Tensor, num_cross_layer: int) -> torch.Tensor:
+    """The whole loop of DCN/dcn.py:157-160 (``for i: cross_vec = cross_layer(x0, cross_vec, i)``) in ONE launch;
+    creates exactly the variables the loop would create."""
+    dimension = int(x0.shape[-1])
+    if num_cross_layer == 0:
+        return x0
+    ws = [get_variable(name=f"wl_{i}", shape=(dimension, 1)) for i in range(num_cross_layer)]
+    bs = [get_variable(name=f"bl_{i}", shape=(dimension, 1)) for i in range(num_cross_layer)]
+    w = torch.cat([t.reshape(1, dimension) for t in ws], 0)
+    b = torch.cat([t.reshape(1, dimension) for t in bs], 0)
+    return autograd.cross_stack(x0, w, b)
+
+
+# --------------------------------------------------------------------------------------------------- xDeepFM
+def cin_layer(x0: torch.Tensor, xk: torch.Tensor, hk_1, index: int, return_pooled: bool = False):
+    """xdeepfm CIN layer -- same signature as xDeepFM/cin_layer.py:4.  x0 (B,m,D), xk (B,hk,D) -> (B,hk_1,D).
+    ``hk_1`` may arrive as a *string* (the reference splits a comma flag, xdeepfm.py:253).  Variable
+    ``cin_layer_{index}_filter`` of shape (1, hk*m, hk_1).  ``return_pooled`` additionally returns sum over D
+    (the ``tf.reduce_sum(x, axis=-1)`` of xdeepfm.py:173) from the same kernel."""
+    hk_1 = int(hk_1)
+    m = int(x0.shape[1])
+    hk = int(xk.shape[1])
+    filters = get_variable(name=f"cin_layer_{index}_filter", shape=(1, hk * m, hk_1))
+    return autograd.cin(x0, xk, filters[0], want_pooled=return_pooled)
+
+
+# --------------------------------------------------------------------------------------------------- DIN
+def din_attention(query: torch.Tensor, keys: torch.Tensor, keys_length: torch.Tensor, is_softmax: bool = False):
+    """DIN attention unit -- same signature as DIN/din_attention.py:4.  Dense layers ``f1_att`` (4H->64, relu),
+    ``f2_att`` (64->32, relu), ``f3_att`` (32->1) with AUTO_REUSE: variables <name>/kernel, <name>/bias (zeros)."""
+    H = int(query.shape[-1])
+    params = []
+    for name, (fi, fo) in (("f1_att", (4 * H, 64)), ("f2_att", (64, 32)), ("f3_att", (32, 1))):
+        with variable_scope(name, reuse=AUTO_REUSE):
+            params.append(get_variable("kernel", (fi, fo)))
+            params.append(get_variable("bias", (fo,), initializer=lambda s: torch.zeros(s)))
+    return autograd.din_attention(query, keys, keys_length.to(torch.int64), *params, is_softmax=is_softmax)
+
+
+# --------------------------------------------------------------------------------------------------- FiBiNET
+def senet(input: torch.Tensor, embedding_dim: int, reduction_ratio: int) -> torch.Tensor:
+    """SENET -- same signature as FiBiNET/senet.py:4.  NB the reference reduces from ``embedding_dim``
+    (``reduction_dim = embedding_dim // reduction_ratio``, :18), not from the field count."""
+    F = int(input.shape[1])
+    reduction_dim = embedding_dim // reduction_ratio
+    assert reduction_dim < embedding_dim, "reduction_dim must be less than embedding_dim"
+    w1 = get_variable(name="senet_w1", shape=(F, reduction_dim))
+    w2 = get_variable(name="senet_w2", shape=(reduction_dim, F))
+    return autograd.senet(input, w1, w2)
+
+
+def bilinear_interaction_layer(input: torch.Tensor, embedding_dim: int, type: str, name: str) -> torch.Tensor:
+    """Bilinear interaction -- same signature as FiBiNET/bilinear_interaction_layer.py:5.  Output is
+    (B, (F-1)(F-2)/2, K): the reference enumerates ``combinations(range(F-1), 2)`` (:24,29,33)."""
+    F = int(input.shape[1])
+    if type == "all":
+        w = get_variable(name=f"{name}_w_all", shape=(embedding_dim, embedding_dim))
+    elif type == "each":
+        w = get_variable(name=f"{name}_w_each", shape=(F - 1, embedding_dim, embedding_dim))
+    elif type == "interaction":
+        w = get_variable(name=f"{name}_w_interaction", shape=(F * (F - 1) // 2, embedding_dim, embedding_dim))
+    else:
+        raise ValueError(f"Bilinear Interaction type must be in ['all','each','interaction'], got '{type}'")
+    return autograd.bilinear(input, w, type)
+
+
+# --------------------------------------------------------------------------------------------------- DeepFM
+def fm_second_order(tables: autograd.EmbeddingTables, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The lookup + FM second-order block of DeepFM/deepfm.py:184-200 in one kernel: per-field ids (B,F) ->
+    (fields_embeddings as a (B,F,K) tile, fm_second_order_logit (B,1))."""
+    return autograd.lookup_fm2(tables, ids)

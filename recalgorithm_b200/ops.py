@@ -221,6 +221,8 @@ def bilinear_fwd(x, w, type_):
     _chk(x, F32, "x"); _chk(w, F32, "w", bilinear_w_shape(F, K, type_))
     P = (F - 1) * (F - 2) // 2
     out = torch.empty((B, P, K), dtype=F32, device=x.device)
+    if B == 0 or P == 0:
+        return out
     _lib.check(_lib.lib().ctr_bilinear_fwd(_ptr(x), _ptr(w), B, F, K, t, _ptr(out), _stream()))
     return out
 
@@ -231,5 +233,55 @@ def bilinear_bwd(x, w, type_, g_out):
     P = (F - 1) * (F - 2) // 2
     _chk(x, F32, "x"); _chk(w, F32, "w", bilinear_w_shape(F, K, type_)); _chk(g_out, F32, "g_out", (B, P, K))
     dx, dw = torch.empty_like(x), torch.empty_like(w)
+    if B == 0 or P == 0:
+        return dx.zero_(), dw.zero_()
     _lib.check(_lib.lib().ctr_bilinear_bwd(_ptr(x), _ptr(w), _ptr(g_out), B, F, K, t, _ptr(dx), _ptr(dw), _stream()))
     return dx, dw
+
+
+# ------------------------------------------------------------------ Row CIN
+_cin_ws = {}
+
+
+def _cin_workspace(nbytes: int, device) -> Optional[torch.Tensor]:
+    """Per-(device, stream) cached scratch for the re-ordered / tf32-split filter (caller-owned, as the ABI requires)."""
+    if nbytes == 0:
+        return None
+    key = (device.index, _stream())
+    buf = _cin_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        _cin_ws[key] = buf
+    return buf
+
+
+def cin_fwd(x0: torch.Tensor, xk: torch.Tensor, filt: torch.Tensor, want_pooled: bool = False, precision: int = 0):
+    """One CIN layer.  x0 (B,m,D); xk (B,hk,D); filt (hk*m, H).  Returns out (B,H,D) [, pooled (B,H)]."""
+    B, m, D = x0.shape
+    hk = xk.shape[1]
+    H = filt.shape[1]
+    _chk(x0, F32, "x0"); _chk(xk, F32, "xk", (B, hk, D)); _chk(filt, F32, "filter", (hk * m, H))
+    out = torch.empty((B, H, D), dtype=F32, device=x0.device)
+    pooled = torch.empty((B, H), dtype=F32, device=x0.device) if want_pooled else None
+    L = _lib.lib()
+    nbytes = int(L.ctr_cin_fwd_workspace_bytes(B, m, hk, D, H))
+    ws = _cin_workspace(nbytes, x0.device)
+    _lib.check(L.ctr_cin_fwd(_ptr(x0), _ptr(xk), _ptr(filt), B, m, hk, D, H, _ptr(out), _ptr(pooled), int(precision),
+                             _ptr(ws), nbytes, _stream()))
+    return (out, pooled) if want_pooled else out
+
+
+def cin_bwd(x0, xk, filt, g_out):
+    """Returns (dx0, dxk, dfilter)."""
+    B, m, D = x0.shape
+    hk = xk.shape[1]
+    H = filt.shape[1]
+    _chk(x0, F32, "x0"); _chk(xk, F32, "xk", (B, hk, D)); _chk(filt, F32, "filter", (hk * m, H))
+    _chk(g_out, F32, "g_out", (B, H, D))
+    dx0, dxk, dw = torch.empty_like(x0), torch.empty_like(xk), torch.empty_like(filt)
+    L = _lib.lib()
+    nbytes = int(L.ctr_cin_bwd_workspace_bytes(B, m, hk, D, H))
+    ws = _cin_workspace(nbytes, x0.device)
+    _lib.check(L.ctr_cin_bwd(_ptr(x0), _ptr(xk), _ptr(filt), _ptr(g_out), B, m, hk, D, H, _ptr(dx0), _ptr(dxk), _ptr(dw),
+                             _ptr(ws), nbytes, _stream()))
+    return dx0, dxk, dw

@@ -78,7 +78,8 @@ def test_lookup_golden_edges():
     from recalgorithm_b200 import ops
     g = golden("lookup_edge")
     table = np.ascontiguousarray(g["table"])
-    tile, _ = ops.embed_fm2_fwd(dev(table), dev(g["field_row_offset"]), dev(g["ids"]), want_fm2=False)
+    off = np.concatenate([g["field_row_offset"], [table.shape[0]]]).astype(np.int64)     # fixture stores the F starts
+    tile, _ = ops.embed_fm2_fwd(dev(table), dev(off), dev(g["ids"]), want_fm2=False)
     assert np.array_equal(tile.cpu().numpy(), g["out"])
     out = ops.bag_lookup_fwd(dev(table), dev(g["bag_ids"]), dev(g["bag_offsets"]))
     assert np.array_equal(out.cpu().numpy(), g["bag_out"]), "mean combiner must match bit for bit (same op order)"
