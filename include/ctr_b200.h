@@ -66,6 +66,13 @@ int ctr_embed_fm2_bwd(const float* tile, const float* d_tile, const float* d_fm2
 int ctr_embed_scatter_add(float* grad_table, const int64_t* field_row_offset, const int64_t* ids,
                           const float* row_grads, int64_t B, int64_t F, int64_t D, void* stream);
 
+/* DeepFM first-order ("wide") term as a D=1 lookup.  Replaces indicator_column multi-hot (B, sum V) @
+ * dense(1) (DeepFM/deepfm.py:72-80,180-181): out[b] = bias + sum_f w[field_row_offset[f] + ids[b,f]]; invalid ids add 0.
+ * w (V_total) is the dense(1) kernel; its gradient is the IndexedSlices (ids, d_out[b] broadcast over F) -- no kernel
+ * needed -- and d_bias = sum_b d_out[b]. */
+int ctr_first_order_fwd(const float* w, const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F,
+                        float bias, float* out, void* stream);
+
 /* ---- Row L (general): multi-valued bag lookup, combiner='mean' ----------------------------------
  * Replaces fc.input_layer over embedding_column(col, D, combiner='mean') on a VarLen feature
  * (DCN/dcn.py:98,103; xDeepFM/xdeepfm.py:103,108) and any single-valued column whose D is not a

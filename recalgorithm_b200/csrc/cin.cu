@@ -30,8 +30,7 @@ namespace cin {
 constexpr int BM = 128;                  // rows per UMMA tile
 constexpr int TILES = 2;                 // M tiles per CTA
 constexpr int KB = 32;                   // tf32 per K-block (128 B == swizzle span)
-constexpr int A_TILE_BYTES = BM * 128;   // 16 KB
-constexpr int NTHREADS = 320;            // 8 producer/epilogue warps + TMA warp + MMA warp
+constexpr int NTHREADS = 384;            // 3 warpgroups: 8 producer/drain warps, then TMA warp + MMA warp (+2 idle)
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,6 +99,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem], kind::tf32 (TS mode)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -130,11 +157,11 @@ struct FwdSmem {
 __host__ __device__ inline FwdSmem fwd_smem(int NP, int passes, int stages) {
   FwdSmem s;
   const int na = passes == 3 ? 2 : 1;
-  s.a_bytes_per_tile = na * A_TILE_BYTES;
+  s.a_bytes_per_tile = 0;                         // A lives in TMEM (TS-mode MMA)
   s.b_tile_bytes = NP * 128;
-  s.stage_bytes = TILES * s.a_bytes_per_tile + na * s.b_tile_bytes;
+  s.stage_bytes = na * s.b_tile_bytes;
   s.bar_off = stages * s.stage_bytes;
-  s.total = s.bar_off + 8 * (3 * stages + 2) + 16;
+  s.total = s.bar_off + 8 * (2 * stages + 2 * 8 + 2) + 16;
   return s;
 }
 
@@ -154,104 +181,165 @@ __global__ void cin_split_filter_kernel(const float* __restrict__ w, float* __re
   }
 }
 
-template <int PASSES, int STAGES>
+// One halving-butterfly step of the sum over the D lanes of a sample: lanes whose bit `o` is clear keep the lower
+// HALF columns, the others the upper HALF; returns the column offset this lane now owns.
+template <int N, int HALF>
+__device__ __forceinline__ int bfly_step(float (&acc)[N], int lane, int o) {
+  const bool up = (lane & o) != 0;
+#pragma unroll
+  for (int q = 0; q < HALF; ++q) {
+    const float keep = up ? acc[q + HALF] : acc[q];
+    const float send = up ? acc[q] : acc[q + HALF];
+    acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+  }
+  return up ? HALF : 0;
+}
+
+// Accumulation note: the tensor core adds each K=8 product group into the fp32 TMEM accumulator with truncation,
+// so a long accumulation chain drifts by ~0.5 ulp per MMA (measured 3.8e-5 after 1440 MMAs at K = 3840 x 3 passes).
+// The K loop is therefore cut into chunks of `chunk` K-blocks: each chunk accumulates from zero in TMEM and the
+// row-owning threads add the finished chunk into fp32 registers (round-to-nearest).
+//
+// Operand placement (second revision): the first version staged A in shared memory; ncu showed it bound by shared
+// memory bandwidth (producer stores + tensor-core operand reads + TMA writes > 128 B/clk) with the proxy fence as the
+// top producer stall.  A now goes registers -> TMEM (tcgen05.st; the row-owning thread IS the TMEM lane) and the MMA
+// runs in TS mode (A from TMEM, B from shared memory), so shared memory only carries the filter tiles.
+//   TMEM columns: [0, TILES*NP) accumulators | [256, 512) A staging: stage sa, tile t at 256 + (sa*TILES + t)*32*NA (+32 = lo)
+template <int PASSES, int SB, int NPT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ x0,
                   const float* __restrict__ xk, float* __restrict__ out, float* __restrict__ pooled, int B, int m,
-                  int hk, int logD, int H, int NP, int tmem_cols) {
+                  int hk, int logD, int H, int NP, int chunk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align explicitly (the launch adds 1 KB of slack)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const FwdSmem L = fwd_smem(NP, PASSES, STAGES);
+  constexpr int NA = PASSES == 3 ? 2 : 1;                 // hi (+ lo) operand copies
+  constexpr int SA = 256 / (TILES * KB * NA);             // A stages that fit TMEM columns [256, 512)
+  const FwdSmem L = fwd_smem(NP, PASSES, SB);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + L.bar_off;
-  auto full_a = [&](int s) { return bar0 + 8 * s; };
-  auto full_b = [&](int s) { return bar0 + 8 * (STAGES + s); };
-  auto empty = [&](int s) { return bar0 + 8 * (2 * STAGES + s); };
-  const uint32_t tmem_full = bar0 + 8 * (3 * STAGES), tmem_empty = tmem_full + 8;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (3 * STAGES + 2));
+  auto full_b = [&](int s) { return bar0 + 8 * s; };
+  auto empty_b = [&](int s) { return bar0 + 8 * (SB + s); };
+  auto full_a = [&](int s) { return bar0 + 8 * (2 * SB + s); };
+  auto empty_a = [&](int s) { return bar0 + 8 * (2 * SB + SA + s); };
+  const uint32_t acc_full = bar0 + 8 * (2 * SB + 2 * SA), acc_empty = acc_full + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (2 * SB + 2 * SA + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = 1 << logD;
   const long long rows_total = (long long)B * D;
   const int num_tiles = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
-  constexpr int NA = PASSES == 3 ? 2 : 1;
+  const int nch = (hk + chunk - 1) / chunk;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), 8); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 8);
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), 8); mbar_init(empty_a(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(tmem_ptr), (uint32_t)tmem_cols);
+  if (warp == 9) tmem_alloc(smem_u32(tmem_ptr), 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t a_stage0 = tmem_base + 256u;
 
+  // Register re-distribution between warpgroups (registers are per SM sub-partition: 3 warps x 168 at launch):
+  // the two row-owning warpgroups hold x0 (32) + the running output row (up to 128) in registers.
   if (warp < 8) {
-    // ============================ A producers (one row each) + epilogue ============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  }
+  if (warp < 8) {
+    // ============================ A producers (one row each) + chunk drain + epilogue ============================
     const int t = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-    const int sw = row & 7;
-    int s = 0, ph = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const long long r = (long long)tile * (TILES * BM) + t * BM + row;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    int sa = 0, pha = 0;
+    uint32_t g = 0;                                   // chunk counter (same sequence as the MMA warp)
+    float acc[NPT];
+    auto drain = [&](uint32_t gi) {                   // add finished chunk gi into acc, then hand TMEM back
+      mbar_wait(acc_full, gi & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_sel + (uint32_t)(t * NP);
+#pragma unroll
+      for (int c0 = 0; c0 < NPT; c0 += 16) {
+        if (c0 < NP) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[c0 + q] += v[q];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long r = (long long)tile * (TILES * BM) + t * BM + (warp & 3) * 32 + lane;
       const bool valid = r < rows_total;
       const int b = valid ? (int)(r >> logD) : 0;
       const int d = (int)(r & (D - 1));
       float x0v[KB];
 #pragma unroll
       for (int j = 0; j < KB; ++j) x0v[j] = (valid && j < m) ? __ldg(x0 + ((size_t)b * m + j) * D + d) : 0.f;
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) acc[n] = 0.f;
       const float* xkp = xk + (size_t)b * hk * D + d;
       float xnext = valid ? __ldg(xkp) : 0.f;
-      for (int i = 0; i < hk; ++i) {
-        const float xi = xnext;
-        if (i + 1 < hk) xnext = valid ? __ldg(xkp + (size_t)(i + 1) * D) : 0.f;
-        mbar_wait(empty(s), ph ^ 1);
-        const uint32_t a_hi = sbase + s * L.stage_bytes + t * L.a_bytes_per_tile + row_off;
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int i_beg = c * chunk, i_end = min(hk, (c + 1) * chunk);
+        const int drain_at = min(SA, i_end - i_beg);  // previous chunk is drained once SA blocks of this one are staged
+        for (int i = i_beg; i < i_end; ++i) {
+          const float xi = xnext;
+          if (i + 1 < hk) xnext = valid ? __ldg(xkp + (size_t)(i + 1) * D) : 0.f;
+          mbar_wait(empty_a(sa), pha ^ 1);
+          tc_fence_after();
+          const uint32_t a_hi = a_stage0 + lane_sel + (uint32_t)((sa * TILES + t) * KB * NA);
 #pragma unroll
-        for (int c = 0; c < KB / 4; ++c) {
-          const float p0 = xi * x0v[4 * c + 0], p1 = xi * x0v[4 * c + 1], p2 = xi * x0v[4 * c + 2],
-                      p3 = xi * x0v[4 * c + 3];
-          const uint32_t off = (uint32_t)((c ^ sw) << 4);
-          if (PASSES == 3) {
-            const float h0 = tf32_rna(p0), h1 = tf32_rna(p1), h2 = tf32_rna(p2), h3 = tf32_rna(p3);
-            sts_f4(a_hi + off, h0, h1, h2, h3);
-            sts_f4(a_hi + A_TILE_BYTES + off, p0 - h0, p1 - h1, p2 - h2, p3 - h3);
-          } else {
-            sts_f4(a_hi + off, p0, p1, p2, p3);
-          }
-        }
-        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_a(s));
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
-      // ---------------- epilogue: TMEM -> registers -> out (B,H,D) and pooled (B,H) ----------------
-      mbar_wait(tmem_full, lt & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * NP);
-      for (int c0 = 0; c0 < NP; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
+          for (int part = 0; part < KB / 8; ++part) {
+            float p[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int n = c0 + q;
-          if (n < H) {
-            if (valid) out[((size_t)b * H + n) * D + d] = v[q];
-            if (pooled != nullptr) {
-              float sred = valid ? v[q] : 0.f;
-              for (int o = D >> 1; o > 0; o >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, o);
-              if (valid && d == 0) pooled[(size_t)b * H + n] = sred;
+            for (int q = 0; q < 8; ++q) p[q] = xi * x0v[part * 8 + q];
+            if (PASSES == 3) {
+              float h[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) h[q] = tf32_rna(p[q]);
+              tmem_st8(a_hi + part * 8, h);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) p[q] -= h[q];
+              tmem_st8(a_hi + KB + part * 8, p);
+            } else {
+              tmem_st8(a_hi + part * 8, p);
             }
           }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_a(sa));
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+          if (c > 0 && i - i_beg + 1 == drain_at) drain(g - 1);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
+      drain(g - 1);
+      // ---------------- epilogue: registers -> out (B,H,D) and pooled (B,H) ----------------
+#pragma unroll
+      for (int n = 0; n < NPT; ++n)
+        if (n < H && valid) out[((size_t)b * H + n) * D + d] = acc[n];
+      if (pooled != nullptr) {
+        // sum over the D lanes of each sample: halving butterfly (after step s a lane keeps NPT >> (s+1) partial columns)
+        int col0 = 0;
+        if (logD > 0) col0 += bfly_step<NPT, NPT / 2>(acc, lane, D >> 1);
+        if (logD > 1) col0 += bfly_step<NPT, NPT / 4>(acc, lane, D >> 2);
+        if (logD > 2) col0 += bfly_step<NPT, NPT / 8>(acc, lane, D >> 3);
+        if (logD > 3) col0 += bfly_step<NPT, NPT / 16>(acc, lane, D >> 4);
+        if (logD > 4) col0 += bfly_step<NPT, NPT / 32>(acc, lane, D >> 5);
+        const int cnt = NPT >> logD;
+#pragma unroll
+        for (int q = 0; q < NPT; ++q)
+          if (q < cnt && valid && col0 + q < H) pooled[(size_t)b * H + col0 + q] = acc[q];
+      }
     }
   } else if (warp == 8) {
     // ============================ TMA producer for the filter tiles ============================
@@ -259,49 +347,59 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
       int s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int i = 0; i < hk; ++i) {
-          mbar_wait(empty(s), ph ^ 1);
-          const uint32_t b_dst = sbase + s * L.stage_bytes + TILES * L.a_bytes_per_tile;
+          mbar_wait(empty_b(s), ph ^ 1);
+          const uint32_t b_dst = sbase + s * L.stage_bytes;
           mbar_expect_tx(full_b(s), (uint32_t)(NA * L.b_tile_bytes));
           tma_load_2d(b_dst, &tmap_w, i * KB, 0, full_b(s));
           if (PASSES == 3) tma_load_2d(b_dst + L.b_tile_bytes, &tmap_w, i * KB, NP, full_b(s));
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == SB) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else {
-    // ============================ MMA issuer ============================
+  } else if (warp == 9) {
+    // ============================ MMA issuer (TS mode: A from TMEM, B from shared memory) ============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(NP);
-      int s = 0, ph = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        mbar_wait(tmem_empty, (lt & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
-        tc_fence_after();
-        for (int i = 0; i < hk; ++i) {
-          mbar_wait(full_a(s), ph);
-          mbar_wait(full_b(s), ph);
+      int sb = 0, phb = 0, sa = 0, pha = 0;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nch; ++c, ++g) {
+          mbar_wait(acc_empty, (g & 1u) ^ 1u);                 // previous chunk has been drained out of TMEM
           tc_fence_after();
-          const uint32_t st_base = sbase + s * L.stage_bytes;
-          const uint64_t b_hi = umma_desc_sw128(st_base + TILES * L.a_bytes_per_tile);
-          const uint64_t b_lo = umma_desc_sw128(st_base + TILES * L.a_bytes_per_tile + L.b_tile_bytes);
+          const int i_beg = c * chunk, i_end = min(hk, (c + 1) * chunk);
+          for (int i = i_beg; i < i_end; ++i) {
+            mbar_wait(full_a(sa), pha);
+            mbar_wait(full_b(sb), phb);
+            tc_fence_after();
+            const uint32_t first = (i == i_beg) ? 0u : 1u;
+            const uint32_t st_base = sbase + sb * L.stage_bytes;
+            const uint64_t b_hi = umma_desc_sw128(st_base);
+            const uint64_t b_lo = umma_desc_sw128(st_base + L.b_tile_bytes);
 #pragma unroll
-          for (int t = 0; t < TILES; ++t) {
-            const uint64_t a_hi = umma_desc_sw128(st_base + t * L.a_bytes_per_tile);
-            const uint64_t a_lo = umma_desc_sw128(st_base + t * L.a_bytes_per_tile + A_TILE_BYTES);
-            const uint32_t dcol = tmem_base + (uint32_t)(t * NP);
+            for (int tt = 0; tt < TILES; ++tt) {
+              const uint32_t a_hi = a_stage0 + (uint32_t)((sa * TILES + tt) * KB * NA);
+              const uint32_t a_lo = a_hi + KB;
+              const uint32_t dcol = tmem_base + (uint32_t)(tt * NP);
+              if (PASSES == 3) {
+                // small terms first, the dominant hi*hi term last
 #pragma unroll
-            for (int k = 0; k < KB / 8; ++k)          // 32 B per K=8 step inside the 128 B swizzle row
-              umma_tf32(dcol, a_hi + 2 * k, b_hi + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            if (PASSES == 3) {
+                for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(dcol, a_lo + 8 * k, b_hi + 2 * k, idesc, k > 0 ? 1u : first);
 #pragma unroll
-              for (int k = 0; k < KB / 8; ++k) umma_tf32(dcol, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(dcol, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-              for (int k = 0; k < KB / 8; ++k) umma_tf32(dcol, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(dcol, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(dcol, a_hi + 8 * k, b_hi + 2 * k, idesc, k > 0 ? 1u : first);
+              }
             }
+            umma_commit(empty_a(sa));                  // A staging columns free once these MMAs have read them
+            umma_commit(empty_b(sb));                  // and the filter stage
+            if (++sa == SA) { sa = 0; pha ^= 1; }
+            if (++sb == SB) { sb = 0; phb ^= 1; }
           }
-          umma_commit(empty(s));                       // frees the stage when these MMAs have read it
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          umma_commit(acc_full);                       // chunk complete -> drain
         }
-        umma_commit(tmem_full);                        // accumulators complete -> epilogue
       }
     }
   }
@@ -309,7 +407,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -516,21 +614,20 @@ extern "C" int ctr_cin_fwd(const float* x0, const float* xk, const float* filter
   const long long rows_total = (long long)B * D;
   const int num_tiles = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  int tmem_cols = 32;
-  while (tmem_cols < TILES * NP) tmem_cols <<= 1;
-  if (precision == 0) {
-    constexpr int STAGES = 2;
-    const FwdSmem L = fwd_smem(NP, 3, STAGES);
-    auto k = cin_fwd_tc_kernel<3, STAGES>;
-    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total + 1024));
-    k<<<grid, NTHREADS, L.total + 1024, st>>>(tmap, x0, xk, out, pooled, (int)B, (int)m, (int)hk, logD, (int)H, NP, tmem_cols);
-  } else {
-    constexpr int STAGES = 4;
-    const FwdSmem L = fwd_smem(NP, 1, STAGES);
-    auto k = cin_fwd_tc_kernel<1, STAGES>;
-    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total + 1024));
-    k<<<grid, NTHREADS, L.total + 1024, st>>>(tmap, x0, xk, out, pooled, (int)B, (int)m, (int)hk, logD, (int)H, NP, tmem_cols);
+#define CIN_LAUNCH(PASSES_, SB_, NPT_, CHUNK_)                                                                        \
+  {                                                                                                                   \
+    const FwdSmem L = fwd_smem(NP, PASSES_, SB_);                                                                     \
+    auto k = cin_fwd_tc_kernel<PASSES_, SB_, NPT_>;                                                                   \
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total + 1024));                   \
+    k<<<grid, NTHREADS, L.total + 1024, st>>>(tmap, x0, xk, out, pooled, (int)B, (int)m, (int)hk, logD, (int)H, NP,   \
+                                              CHUNK_);                                                                \
   }
+  if (precision == 0) {
+    if (NP <= 32) CIN_LAUNCH(3, 4, 32, 8) else if (NP <= 64) CIN_LAUNCH(3, 4, 64, 8) else CIN_LAUNCH(3, 4, 128, 8)
+  } else {
+    if (NP <= 32) CIN_LAUNCH(1, 6, 32, 32) else if (NP <= 64) CIN_LAUNCH(1, 6, 64, 32) else CIN_LAUNCH(1, 6, 128, 32)
+  }
+#undef CIN_LAUNCH
   CTR_CHECK_LAUNCH("ctr_cin_fwd(tcgen05)");
   return CTR_OK;
 }

@@ -240,6 +240,27 @@ bag_lookup_bwd_kernel(const float* __restrict__ d_out, long long out_stride, lon
   }
 }
 
+// ---- DeepFM first-order ("wide") term as a D=1 lookup --------------------------------------
+// Reference: indicator_column multi-hot (B, sum V) @ dense(1) kernel (sum V, 1) + bias  (DeepFM/deepfm.py:72-80,180-181).
+// A multi-hot times a one-column kernel is a per-id scalar gather-sum; id -1 contributes 0 (all-zero indicator row).
+__global__ void __launch_bounds__(256)
+first_order_fwd_kernel(const float* __restrict__ w, const long long* __restrict__ row_off,
+                       const long long* __restrict__ ids, int B, int F, float bias, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp0; b < B; b += nwarps) {
+    float acc = 0.f;
+    for (int f = lane; f < F; f += 32) {
+      const long long id = ldg_stream_i64(ids + (size_t)b * F + f);
+      const long long lo = __ldg(row_off + f), hi = __ldg(row_off + f + 1);
+      if (id >= 0 && id < hi - lo) acc += __ldg(w + lo + id);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[b] = acc + bias;
+  }
+}
+
 template <typename K>
 static int resident_grid(K kernel, int block, size_t smem, long long blocks_needed) {
   int per_sm = 0;
@@ -398,5 +419,19 @@ extern "C" int ctr_bag_lookup_bwd(const float* d_out, int64_t out_stride, int64_
                                                              reinterpret_cast<const long long*>(offsets), (int)B,
                                                              row_grads, G);
   CTR_CHECK_LAUNCH("ctr_bag_lookup_bwd");
+  return CTR_OK;
+}
+
+extern "C" int ctr_first_order_fwd(const float* w, const int64_t* field_row_offset, const int64_t* ids, int64_t B,
+                                   int64_t F, float bias, float* out, void* stream) {
+  CTR_REQUIRE(w && field_row_offset && ids && out, "ctr_first_order_fwd: null argument");
+  CTR_REQUIRE(B >= 0 && F >= 1 && B <= 0x7fffffffLL / 8 && F <= 65536, "ctr_first_order_fwd: bad sizes");
+  if (B == 0) return CTR_OK;
+  const long long blocks = (B + 7) / 8;
+  const int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : (long long)sm_count() * 8);
+  first_order_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<const long long*>(field_row_offset),
+                                                              reinterpret_cast<const long long*>(ids), (int)B, (int)F,
+                                                              bias, out);
+  CTR_CHECK_LAUNCH("ctr_first_order_fwd");
   return CTR_OK;
 }

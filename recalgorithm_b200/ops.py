@@ -80,6 +80,16 @@ def embed_scatter_add(grad_table: torch.Tensor, field_row_offset: torch.Tensor, 
     return grad_table
 
 
+def first_order_fwd(w: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor, bias: float = 0.0) -> torch.Tensor:
+    """DeepFM first-order logit (B,1): bias + sum_f w[row(b,f)].  w (V_total,) = the dense(1) kernel over the indicators."""
+    B, F = ids.shape
+    _chk(w, F32, "w"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,)); _chk(ids, I64, "ids")
+    out = torch.empty((B, 1), dtype=F32, device=w.device)
+    _lib.check(_lib.lib().ctr_first_order_fwd(_ptr(w), _ptr(field_row_offset), _ptr(ids), B, F, float(bias), _ptr(out),
+                                              _stream()))
+    return out
+
+
 def bag_lookup_fwd(table: torch.Tensor, ids: torch.Tensor, offsets: torch.Tensor,
                    out: Optional[torch.Tensor] = None, out_col: int = 0) -> torch.Tensor:
     """Multi-valued lookup, combiner='mean'.  Writes out[:, out_col:out_col+D] of a (B, stride) buffer."""

@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Per-layer timings of the non-headline BASELINE configs (2: DCN cross, 3: xDeepFM CIN, 4: DIN attention) and FiBiNET.
+
+Each kernel is timed alone with CUDA events; an L2 flush (a 256 MB write) runs between timed iterations because these
+working sets fit the 126 MB L2.  Prints one JSON line per measurement; meant to be redirected into profiles/.
+
+    python tools/bench_layers.py [--iters 20] [--only cin,dcn,din,fibinet]
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from recalgorithm_b200 import ops  # noqa: E402
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        flush.zero_()                                   # 256 MB write: evicts the 126 MB L2
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    return statistics.median(times), min(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="dcn,cin,din,fibinet")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    torch.cuda.set_device(0)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    rn = lambda *s, std=1.0: torch.randn(s, device="cuda", generator=gen) * std
+    flush = torch.empty(64 * 1024 * 1024, device="cuda")
+    hbm, tf, src = peaks()
+
+    def emit(name, cfg, med, best, bytes_=None, flops=None, note=""):
+        line = {"kernel": name, "config": cfg, "ms_median": med, "ms_best": best, "l2": "flushed between iterations", "note": note}
+        if bytes_ is not None:
+            line["algorithmic_GBps"] = bytes_ / (med * 1e-3) / 1e9
+            line["frac_of_hbm_peak"] = line["algorithmic_GBps"] / hbm
+        if flops is not None:
+            line["TFLOPs"] = flops / (med * 1e-3) / 1e12
+            line["frac_of_bf16_peak"] = line["TFLOPs"] / tf
+        line["peak_source"] = src
+        print(json.dumps(line), flush=True)
+
+    if "dcn" in only:   # BASELINE config 2: DCN 3 cross layers, 30 fields x 16 = 480, batch 4096
+        B, d, L = 4096, 480, 3
+        x0, w, b, g = rn(B, d), rn(L, d, std=0.05), rn(L, d, std=0.05), rn(B, d)
+        cfg = {"B": B, "d": d, "L": L}
+        m, bst = timeit(lambda: ops.cross_fwd(x0, w, b), args.iters, flush)
+        emit("cross_fwd", cfg, m, bst, bytes_=B * 2 * d * 4, note="2*d*4 B/sample")
+        m, bst = timeit(lambda: ops.cross_bwd(x0, w, b, g), args.iters, flush)
+        emit("cross_bwd", cfg, m, bst, bytes_=B * 3 * d * 4, note="3*d*4 B/sample")
+        for B2 in (65536,):
+            x0b, gb = rn(B2, d), rn(B2, d)
+            m, bst = timeit(lambda: ops.cross_fwd(x0b, w, b), args.iters, flush)
+            emit("cross_fwd", {"B": B2, "d": d, "L": L}, m, bst, bytes_=B2 * 2 * d * 4)
+            m, bst = timeit(lambda: ops.cross_bwd(x0b, w, b, gb), args.iters, flush)
+            emit("cross_bwd", {"B": B2, "d": d, "L": L}, m, bst, bytes_=B2 * 3 * d * 4)
+
+    if "cin" in only:   # BASELINE config 3: xDeepFM CIN [128,128], 30 fields, D=16, batch 8192
+        B, mm, D, H = 8192, 30, 16, 128
+        x0 = rn(B, mm, D, std=0.25)
+        w1, w2 = rn(mm * mm, H, std=0.05), rn(H * mm, H, std=0.05)
+        x1 = ops.cin_fwd(x0, x0, w1)
+        g = rn(B, H, D)
+        for prec in (0, 1):
+            tag = "3xTF32" if prec == 0 else "1xTF32"
+            m, bst = timeit(lambda: ops.cin_fwd(x0, x0, w1, want_pooled=True, precision=prec), args.iters, flush)
+            emit(f"cin_fwd_layer1_{tag}", {"B": B, "m": mm, "hk": mm, "D": D, "H": H}, m, bst, flops=2.0 * B * D * mm * mm * H)
+            m, bst = timeit(lambda: ops.cin_fwd(x0, x1, w2, want_pooled=True, precision=prec), args.iters, flush)
+            emit(f"cin_fwd_layer2_{tag}", {"B": B, "m": mm, "hk": H, "D": D, "H": H}, m, bst, flops=2.0 * B * D * H * mm * H)
+        m, bst = timeit(lambda: ops.cin_bwd(x0, x0, w1, g), max(3, args.iters // 4), flush)
+        emit("cin_bwd_layer1", {"B": B, "m": mm, "hk": mm, "D": D, "H": H}, m, bst, flops=4.0 * B * D * mm * mm * H)
+        m, bst = timeit(lambda: ops.cin_bwd(x0, x1, w2, g), max(3, args.iters // 4), flush)
+        emit("cin_bwd_layer2", {"B": B, "m": mm, "hk": H, "D": D, "H": H}, m, bst, flops=4.0 * B * D * H * mm * H)
+
+    if "din" in only:   # BASELINE config 4: DIN attention, seq_len 50, H=16, batch 4096
+        B, T, H = 4096, 50, 16
+        q, k = rn(B, H, std=0.25), rn(B, T, H, std=0.25)
+        lens = torch.randint(0, T + 1, (B,), device="cuda", generator=gen)
+        ws = [rn(4 * H, 64, std=0.2), rn(64, std=0.1), rn(64, 32, std=0.2), rn(32, std=0.1), rn(32, 1, std=0.3), rn(1, std=0.1)]
+        g = rn(B, H)
+        flops_full = B * T * 2.0 * (4 * H * 64 + 64 * 32 + 32)
+        for soft in (False, True):
+            m, bst = timeit(lambda: ops.din_attention_fwd(q, k, lens, *ws, is_softmax=soft), args.iters, flush)
+            emit(f"din_fwd_softmax{int(soft)}", {"B": B, "T": T, "H": H, "lengths": "uniform{0..50}"}, m, bst,
+                 bytes_=B * (T * H * 4 + 8 + 2 * H * 4), flops=flops_full,
+                 note="FLOPs counted as the reference does them (all T positions, unfolded layer 1)")
+            m, bst = timeit(lambda: ops.din_attention_bwd(q, k, lens, *ws, g, is_softmax=soft), args.iters, flush)
+            emit(f"din_bwd_softmax{int(soft)}", {"B": B, "T": T, "H": H}, m, bst, flops=2 * flops_full)
+
+    if "fibinet" in only:   # FiBiNET F=30, K=16, r=8 (no BASELINE config; reference defaults)
+        B, F, K, r = 4096, 30, 16, 8
+        x, w1, w2 = rn(B, F, K, std=0.25), rn(F, r, std=0.3), rn(r, F, std=0.3)
+        g = rn(B, F, K)
+        m, bst = timeit(lambda: ops.senet_fwd(x, w1, w2), args.iters, flush)
+        emit("senet_fwd", {"B": B, "F": F, "K": K, "r": r}, m, bst, bytes_=B * 2 * F * K * 4)
+        m, bst = timeit(lambda: ops.senet_bwd(x, w1, w2, g), args.iters, flush)
+        emit("senet_bwd", {"B": B, "F": F, "K": K, "r": r}, m, bst, bytes_=B * 3 * F * K * 4)
+        P = (F - 1) * (F - 2) // 2
+        gp = rn(B, P, K)
+        for typ in ("all", "each", "interaction"):
+            w = rn(*ops.bilinear_w_shape(F, K, typ), std=0.2)
+            m, bst = timeit(lambda: ops.bilinear_fwd(x, w, typ), args.iters, flush)
+            emit(f"bilinear_fwd_{typ}", {"B": B, "F": F, "K": K}, m, bst, bytes_=B * (F * K + P * K) * 4)
+            m, bst = timeit(lambda: ops.bilinear_bwd(x, w, typ, gp), max(3, args.iters // 4), flush)
+            emit(f"bilinear_bwd_{typ}", {"B": B, "F": F, "K": K}, m, bst, bytes_=B * (2 * F * K + P * K) * 4)
+
+
+if __name__ == "__main__":
+    main()
