@@ -1,0 +1,508 @@
+// Row CIN, backward on the tensor cores (tcgen05, TS mode) -- gradients of xDeepFM/cin_layer.py:17-30.
+//
+//   out[b,n,d] = sum_{i,j} xk[b,i,d] x0[b,j,d] W[(i,j),n]            g = dL/dout  (B,H,D)
+//   dZ[r,(i,j)] = sum_n g[b,n,d] W[(i,j),n]      (r = (b,d))
+//   dxk[b,i,d]  = sum_j dZ[r,(i,j)] x0[b,j,d]        dx0[b,j,d] = sum_i dZ[r,(i,j)] xk[b,i,d]
+//   dW[(i,j),n] = sum_r xk[b,i,d] x0[b,j,d] g[b,n,d]
+//
+// Two kernels, both with the operand the threads generate placed in TMEM (the generating thread is the TMEM lane) and
+// the streamed operand delivered by TMA, 3xTF32 split for fp32-class accuracy (see cin.cu for the accuracy notes):
+//
+//  dX kernel   GEMM dZ_i[128 rows x 32 j] = Gt[128 x H] . W_i^T[H x 32]   for every i
+//     A = Gt (hi, lo) written ONCE per 128-row tile into TMEM by the row-owning threads;
+//     B = W rows (i*m .. i*m+31) x H, K-major in the filter's native layout, TMA-streamed (3-D box = 4 swizzled sub-tiles);
+//     D = dZ_i in one of 8 TMEM buffers; the row-owning thread reads its 32 values and does both contractions
+//     (dxk: dot with its x0 registers; dx0: axpy into 32 register accumulators) -- no cross-thread traffic at all.
+//
+//  dW kernel   GEMM dW_blk[128 (i,j) x H] += Z^T[128 (i,j) x D] . G_b^T[D x H]   for every sample b
+//     A = Z^T: thread (i,j) forms xk[b,i,:] * x0[b,j,:] (two contiguous D-vectors) -> TMEM;
+//     B = g[b] as [H rows x D] K-major tiles (TMA 3-D box, swizzle width = D*4 bytes);
+//     each CTA owns 2 blocks of 128 (i,j) rows (8 consecutive i) and a slice of the batch; accumulation chains are cut every
+//     CHUNK samples and added into fp32 registers (round-to-nearest); one vector red.global.add per element at the end.
+#include "tc_ptx.cuh"
+
+namespace ctr {
+namespace cinb {
+using namespace ctr::tc;
+
+constexpr int KB = 32;
+
+// ================================================================================================= prep kernels
+// filter (hk*m, H) -> ws[2][KRP][HP]  (tf32-rounded value | residual), zero padded rows/cols.
+__global__ void split_filter_native_kernel(const float* __restrict__ w, float* __restrict__ ws, int K, int H, int KRP, int HP) {
+  const size_t total = (size_t)KRP * HP;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / HP), n = (int)(idx % HP);
+    float v = 0.f;
+    if (row < K && n < H) v = __ldg(w + (size_t)row * H + n);
+    const float hi = tf32_rna(v);
+    ws[idx] = hi;
+    ws[total + idx] = v - hi;
+  }
+}
+// g (B,H,D) -> gs[2][B][H][D]
+__global__ void split_grad_kernel(const float* __restrict__ g, float* __restrict__ gs, size_t total) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(g + idx);
+    const float hi = tf32_rna(v);
+    gs[idx] = hi;
+    gs[total + idx] = v - hi;
+  }
+}
+
+// ================================================================================================= dX kernel
+constexpr int DX_THREADS = 192;     // 4 row-owner warps + TMA warp + MMA warp
+constexpr int DX_DBUF = 8;          // dZ_i buffers of 32 TMEM columns at columns [256, 512)
+
+template <int SB>
+__global__ void __launch_bounds__(DX_THREADS, 1)
+cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ x0,
+                     const float* __restrict__ xk, const float* __restrict__ g, float* __restrict__ dx0,
+                     float* __restrict__ dxk, int B, int m, int hk, int logD, int H, int HP, int KRP) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int nkb = HP / KB;                                 // K-blocks of 32 n per MMA group
+  const int b_copy_bytes = nkb * 32 * 128;                 // one (hi or lo) copy: nkb sub-tiles of [32 rows x 128 B]
+  const int stage_bytes = 2 * b_copy_bytes;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SB * stage_bytes;
+  auto full_b = [&](int s) { return bar0 + 8 * s; };
+  auto empty_b = [&](int s) { return bar0 + 8 * (SB + s); };
+  auto d_full = [&](int q) { return bar0 + 8 * (2 * SB + q); };
+  auto d_empty = [&](int q) { return bar0 + 8 * (2 * SB + DX_DBUF + q); };
+  const uint32_t a_full = bar0 + 8 * (2 * SB + 2 * DX_DBUF), a_empty = a_full + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SB * stage_bytes + 8 * (2 * SB + 2 * DX_DBUF + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = 1 << logD;
+  const long long rows_total = (long long)B * D;
+  const int num_tiles = (int)((rows_total + BM - 1) / BM);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int q = 0; q < DX_DBUF; ++q) { mbar_init(d_full(q), 1); mbar_init(d_empty(q), 4); }
+    mbar_init(a_full, 4);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_ptr), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t d_col0 = tmem_base + 256u;
+
+  if (warp < 4) {
+    // ============================ row owners: stage Gt once per tile, then consume dZ_i ============================
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    uint32_t di = 0;                                   // dZ buffer use counter (same sequence as the MMA warp)
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const long long r = (long long)tile * BM + warp * 32 + lane;
+      const bool valid = r < rows_total;
+      const int b = valid ? (int)(r >> logD) : 0;
+      const int d = (int)(r & (D - 1));
+      float x0v[KB], dx0acc[KB];
+#pragma unroll
+      for (int j = 0; j < KB; ++j) {
+        x0v[j] = (valid && j < m) ? __ldg(x0 + ((size_t)b * m + j) * D + d) : 0.f;
+        dx0acc[j] = 0.f;
+      }
+      mbar_wait(a_empty, (lt & 1) ^ 1);                // MMAs of the previous tile no longer read the A columns
+      tc_fence_after();
+      const float* gp = g + (size_t)b * H * D + d;
+      for (int n0 = 0; n0 < HP; n0 += 8) {
+        float v[8], h[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = (valid && n0 + q < H) ? __ldg(gp + (size_t)(n0 + q) * D) : 0.f;
+          h[q] = tf32_rna(v[q]);
+          v[q] -= h[q];
+        }
+        tmem_st8(tmem_base + lane_sel + (uint32_t)n0, h);
+        tmem_st8(tmem_base + lane_sel + (uint32_t)(HP + n0), v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+      const float* xkp = xk + (size_t)b * hk * D + d;
+      float xnext = valid ? __ldg(xkp) : 0.f;
+      for (int i = 0; i < hk; ++i, ++di) {
+        const float xi = xnext;
+        if (i + 1 < hk) xnext = valid ? __ldg(xkp + (size_t)(i + 1) * D) : 0.f;
+        const uint32_t q = di % DX_DBUF;
+        mbar_wait(d_full(q), (di / DX_DBUF) & 1u);
+        tc_fence_after();
+        float dz[KB];
+        {
+          float v0[16], v1[16];
+          tmem_ld16(d_col0 + lane_sel + q * KB, v0);
+          tmem_ld16(d_col0 + lane_sel + q * KB + 16, v1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { dz[j] = v0[j]; dz[16 + j] = v1[j]; }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty(q));         // buffer can be overwritten by dZ_{i+8}
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+          s += dz[j] * x0v[j];                           // x0v[j >= m] == 0 masks the columns that belong to row i+1
+          dx0acc[j] += dz[j] * xi;
+        }
+        if (valid) dxk[((size_t)b * hk + i) * D + d] = s;
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < KB; ++j)
+          if (j < m) dx0[((size_t)b * m + j) * D + d] = dx0acc[j];
+      }
+    }
+  } else if (warp == 4) {
+    // ============================ TMA: filter rows of K-block i (hi and lo copies) ============================
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int i = 0; i < hk; ++i) {
+          mbar_wait(empty_b(s), ph ^ 1);
+          const uint32_t dst = sbase + s * stage_bytes;
+          mbar_expect_tx(full_b(s), (uint32_t)stage_bytes);
+          tma_load_3d(dst, &tmap_w, 0, i * m, 0, full_b(s));
+          tma_load_3d(dst + b_copy_bytes, &tmap_w, 0, KRP + i * m, 0, full_b(s));
+          if (++s == SB) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(KB);        // N = 32
+      int s = 0, ph = 0, lt = 0;
+      uint32_t di = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        mbar_wait(a_full, lt & 1);
+        tc_fence_after();
+        for (int i = 0; i < hk; ++i, ++di) {
+          const uint32_t q = di % DX_DBUF;
+          mbar_wait(d_empty(q), ((di / DX_DBUF) & 1u) ^ 1u);
+          mbar_wait(full_b(s), ph);
+          tc_fence_after();
+          const uint32_t dcol = d_col0 + q * KB;
+          const uint32_t st = sbase + s * stage_bytes;
+          // small terms first: Glo.Whi, Ghi.Wlo, then Ghi.Whi
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_col = tmem_base + (pass == 0 ? (uint32_t)HP : 0u);
+            const uint32_t b_base = st + (pass == 1 ? (uint32_t)b_copy_bytes : 0u);
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint64_t bdesc = umma_desc_sw128(b_base + kb * 4096);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_ts(dcol, a_col + (uint32_t)(kb * KB + 8 * k), bdesc + 2 * k, idesc,
+                             (pass | kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_b(s));
+          umma_commit(d_full(q));
+          if (++s == SB) { s = 0; ph ^= 1; }
+        }
+        umma_commit(a_empty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// ================================================================================================= dW kernel
+constexpr int DW_THREADS = 384;     // 8 (i,j)-row warps + TMA warp + MMA warp (+2 idle, completes the third warpgroup)
+constexpr int DW_BLOCKS = 2;        // (i,j) blocks of 128 rows per CTA  (= 8 consecutive i)
+
+template <int SB, int NPT>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __restrict__ x0,
+                     const float* __restrict__ xk, float* __restrict__ dw, int B, int m, int hk, int D, int H, int NP,
+                     int ngroups, int nslices, int chunk) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int row_bytes = D * 4;                             // one sample's D values of one n-row (= swizzle width)
+  const int b_copy_bytes = NP * row_bytes;
+  const int stage_bytes = 2 * b_copy_bytes;
+  const int SA = 256 / (DW_BLOCKS * 2 * D);                // A stages in TMEM columns [256, 512)
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SB * stage_bytes;
+  auto full_b = [&](int s) { return bar0 + 8 * s; };
+  auto empty_b = [&](int s) { return bar0 + 8 * (SB + s); };
+  auto full_a = [&](int s) { return bar0 + 8 * (2 * SB + s); };
+  auto empty_a = [&](int s) { return bar0 + 8 * (2 * SB + 16 + s); };
+  const uint32_t acc_full = bar0 + 8 * (2 * SB + 32), acc_empty = acc_full + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SB * stage_bytes + 8 * (2 * SB + 34));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.x % ngroups, slice = blockIdx.x / ngroups;
+  const int per_slice = (B + nslices - 1) / nslices;
+  const int b_beg = min(B, slice * per_slice), b_end = min(B, b_beg + per_slice);
+  const int nsamp = (slice < nslices) ? b_end - b_beg : 0;
+  const int nch = (nsamp + chunk - 1) / chunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < 16; ++s) { mbar_init(full_a(s), 8); mbar_init(empty_a(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(smem_u32(tmem_ptr), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t a_stage0 = tmem_base + 256u;
+
+  if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  }
+  if (warp < 8) {
+    // ============================ (i,j)-row owners: produce Z^T, drain chunks, final reduction ============================
+    const int t = warp >> 2;                               // block inside the CTA
+    const int row = (warp & 3) * 32 + lane;                // row inside the block = i_local * 32 + j
+    const int i = group * (DW_BLOCKS * 4) + t * 4 + (row >> 5);
+    const int j = row & 31;
+    const bool live = i < hk && j < m;                     // padding rows produce zeros and are never stored
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    float acc[NPT];
+#pragma unroll
+    for (int n = 0; n < NPT; ++n) acc[n] = 0.f;
+    auto drain = [&](uint32_t gi) {
+      mbar_wait(acc_full, gi & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_sel + (uint32_t)(t * NP);
+#pragma unroll
+      for (int c0 = 0; c0 < NPT; c0 += 16) {
+        if (c0 < NP) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[c0 + q] += v[q];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    };
+    int sa = 0, pha = 0;
+    uint32_t gch = 0;
+    for (int c = 0; c < nch; ++c, ++gch) {
+      const int s_beg = b_beg + c * chunk, s_end = min(b_end, s_beg + chunk);
+      const int drain_at = min(SA, s_end - s_beg);
+      for (int b = s_beg; b < s_end; ++b) {
+        const float4* xkv = reinterpret_cast<const float4*>(xk + ((size_t)b * hk + (live ? i : 0)) * D);
+        const float4* x0v = reinterpret_cast<const float4*>(x0 + ((size_t)b * m + (live ? j : 0)) * D);
+        mbar_wait(empty_a(sa), pha ^ 1);
+        tc_fence_after();
+        const uint32_t a_hi = a_stage0 + lane_sel + (uint32_t)((sa * DW_BLOCKS + t) * 2 * D);
+        for (int c8 = 0; c8 < D; c8 += 8) {
+          float p[8], h[8];
+          if (live) {
+            const float4 a0 = __ldg(xkv + c8 / 4), a1 = __ldg(xkv + c8 / 4 + 1);
+            const float4 b0 = __ldg(x0v + c8 / 4), b1 = __ldg(x0v + c8 / 4 + 1);
+            p[0] = a0.x * b0.x; p[1] = a0.y * b0.y; p[2] = a0.z * b0.z; p[3] = a0.w * b0.w;
+            p[4] = a1.x * b1.x; p[5] = a1.y * b1.y; p[6] = a1.z * b1.z; p[7] = a1.w * b1.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) p[q] = 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { h[q] = tf32_rna(p[q]); p[q] -= h[q]; }
+          tmem_st8(a_hi + c8, h);
+          tmem_st8(a_hi + D + c8, p);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_a(sa));
+        if (++sa == SA) { sa = 0; pha ^= 1; }
+        if (c > 0 && b - s_beg + 1 == drain_at) drain(gch - 1);
+      }
+    }
+    if (nch > 0) drain(gch - 1);
+    if (live && nch > 0) {
+      float* dst = dw + ((size_t)i * m + j) * H;
+      if ((H & 3) == 0) {
+#pragma unroll
+        for (int n = 0; n < NPT; n += 4)
+          if (n < H) atomicAdd(reinterpret_cast<float4*>(dst + n), make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]));
+      } else {
+#pragma unroll
+        for (int n = 0; n < NPT; ++n)
+          if (n < H) atomicAdd(dst + n, acc[n]);
+      }
+    }
+  } else if (warp == 8) {
+    // ============================ TMA: g[b] as [NP rows x D] tiles (hi and lo) ============================
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int b = b_beg; b < b_beg + nsamp; ++b) {
+        mbar_wait(empty_b(s), ph ^ 1);
+        const uint32_t dst = sbase + s * stage_bytes;
+        mbar_expect_tx(full_b(s), (uint32_t)stage_bytes);
+        tma_load_3d(dst, &tmap_g, 0, 0, b, full_b(s));
+        tma_load_3d(dst + b_copy_bytes, &tmap_g, 0, 0, B + b, full_b(s));
+        if (++s == SB) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(NP);
+      int sb = 0, phb = 0, sa = 0, pha = 0;
+      uint32_t gch = 0;
+      for (int c = 0; c < nch; ++c, ++gch) {
+        mbar_wait(acc_empty, (gch & 1u) ^ 1u);
+        tc_fence_after();
+        const int s_beg = b_beg + c * chunk, s_end = min(b_end, s_beg + chunk);
+        for (int b = s_beg; b < s_end; ++b) {
+          mbar_wait(full_a(sa), pha);
+          mbar_wait(full_b(sb), phb);
+          tc_fence_after();
+          const uint32_t first = (b == s_beg) ? 0u : 1u;
+          const uint32_t st = sbase + sb * stage_bytes;
+          const uint64_t b_hi = umma_desc_kmajor(st, row_bytes);
+          const uint64_t b_lo = umma_desc_kmajor(st + b_copy_bytes, row_bytes);
+#pragma unroll
+          for (int tt = 0; tt < DW_BLOCKS; ++tt) {
+            const uint32_t a_hi = a_stage0 + (uint32_t)((sa * DW_BLOCKS + tt) * 2 * D);
+            const uint32_t a_lo = a_hi + (uint32_t)D;
+            const uint32_t dcol = tmem_base + (uint32_t)(tt * NP);
+            for (int k = 0; k < D / 8; ++k) umma_tf32_ts(dcol, a_lo + 8 * k, b_hi + 2 * k, idesc, k > 0 ? 1u : first);
+            for (int k = 0; k < D / 8; ++k) umma_tf32_ts(dcol, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+            for (int k = 0; k < D / 8; ++k) umma_tf32_ts(dcol, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
+          }
+          umma_commit(empty_a(sa));
+          umma_commit(empty_b(sb));
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+          if (++sb == SB) { sb = 0; phb ^= 1; }
+        }
+        umma_commit(acc_full);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+static int64_t pad_to(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+}  // namespace cinb
+}  // namespace ctr
+
+using namespace ctr;
+using namespace ctr::cinb;
+
+// Shapes the tensor-core backward serves; everything else goes to the CUDA-core kernels in cin.cu.
+// (internal, not part of the public ABI)
+extern "C" __attribute__((visibility("hidden"))) int ctr_cin_bwd_tc_supported(int64_t m, int64_t hk, int64_t D, int64_t H) {
+  return m >= 1 && m <= 32 && hk >= 1 && H >= 1 && H <= 128 && (D == 8 || D == 16 || D == 32);
+}
+
+extern "C" int64_t ctr_cin_bwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H) {
+  if (!ctr_cin_bwd_tc_supported(m, hk, D, H)) return 0;
+  const int64_t HP = pad_to(H, 32), KRP = hk * m + 32;
+  return (2 * KRP * HP + 2 * B * H * D) * (int64_t)sizeof(float);
+}
+
+// Returns CTR_OK after enqueueing both tensor-core kernels; the caller has already validated the arguments.
+int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const float* g_out, int64_t B, int64_t m,
+                   int64_t hk, int64_t D, int64_t H, float* dx0, float* dxk, float* dfilter, void* workspace,
+                   cudaStream_t st) {
+  const int HP = (int)pad_to(H, 32), NP = (int)pad_to(H, 16), KRP = (int)(hk * m + 32);
+  float* ws_w = static_cast<float*>(workspace);
+  float* ws_g = ws_w + (size_t)2 * KRP * HP;
+  {
+    const long long total = (long long)KRP * HP;
+    split_filter_native_kernel<<<(int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048), 256, 0, st>>>(
+        filter, ws_w, (int)(hk * m), (int)H, KRP, HP);
+    CTR_CHECK_LAUNCH("ctr_cin_bwd(split filter)");
+    const size_t tg = (size_t)B * H * D;
+    split_grad_kernel<<<(int)((tg + 255) / 256 < 4096 ? (tg + 255) / 256 : 4096), 256, 0, st>>>(g_out, ws_g, tg);
+    CTR_CHECK_LAUNCH("ctr_cin_bwd(split grad)");
+  }
+  EncodeTiledFn enc = encode_tiled();
+  if (enc == nullptr) {
+    set_error("ctr_cin_bwd: cuTensorMapEncodeTiled is not available from the driver");
+    return CTR_ERR_CUDA;
+  }
+  int logD = 0;
+  while ((1 << logD) < D) ++logD;
+  // ---- dX: filter as a 3-D tensor (n_inner 32 | row | n_outer) so one box lands as HP/32 swizzled [32 x 128 B] sub-tiles
+  {
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {32, (cuuint64_t)(2 * KRP), (cuuint64_t)(HP / 32)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)HP * sizeof(float), 32 * sizeof(float)};
+    const cuuint32_t box[3] = {32, 32, (cuuint32_t)(HP / 32)};
+    const cuuint32_t es[3] = {1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws_w, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("ctr_cin_bwd: cuTensorMapEncodeTiled(filter) failed with CUresult %d", (int)cr);
+      return CTR_ERR_CUDA;
+    }
+    constexpr int SB = 6;
+    const int stage_bytes = 2 * (HP / 32) * 4096;
+    const int smem = SB * stage_bytes + 8 * (2 * SB + 2 * DX_DBUF + 2) + 16 + 1024;
+    auto k = cin_bwd_dx_tc_kernel<SB>;
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long rows = (long long)B * D;
+    const int tiles = (int)((rows + BM - 1) / BM);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    k<<<grid, DX_THREADS, smem, st>>>(tmap, x0, xk, g_out, dx0, dxk, (int)B, (int)m, (int)hk, logD, (int)H, HP, KRP);
+    CTR_CHECK_LAUNCH("ctr_cin_bwd(dx, tcgen05)");
+  }
+  // ---- dW: g (hi | lo stacked along the batch axis) as a 3-D tensor (d | n | b); box = one sample's [NP x D] tile
+  {
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)H, (cuuint64_t)(2 * B)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)D * sizeof(float), (cuuint64_t)H * D * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)D, (cuuint32_t)NP, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = D == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : D == 16 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws_g, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("ctr_cin_bwd: cuTensorMapEncodeTiled(grad) failed with CUresult %d", (int)cr);
+      return CTR_ERR_CUDA;
+    }
+    constexpr int SB = 8;
+    const int stage_bytes = 2 * NP * (int)D * 4;
+    const int smem = SB * stage_bytes + 8 * (2 * SB + 34) + 16 + 1024;
+    const int ngroups = (int)((hk + DW_BLOCKS * 4 - 1) / (DW_BLOCKS * 4));
+    int nslices = sm_count() / ngroups;
+    if (nslices < 1) nslices = 1;
+    if (nslices > B) nslices = (int)B;
+    const int grid = ngroups * nslices;
+    const int chunk = (int)(256 / D);                        // 96 chained MMAs per accumulator before a drain
+#define DW_LAUNCH(NPT_)                                                                                              \
+  {                                                                                                                  \
+    auto k = cin_bwd_dw_tc_kernel<SB, NPT_>;                                                                         \
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                            \
+    k<<<grid, DW_THREADS, smem, st>>>(tmap, x0, xk, dfilter, (int)B, (int)m, (int)hk, (int)D, (int)H, NP, ngroups,   \
+                                      nslices, chunk);                                                               \
+  }
+    if (NP <= 32) DW_LAUNCH(32) else if (NP <= 64) DW_LAUNCH(64) else DW_LAUNCH(128)
+#undef DW_LAUNCH
+    CTR_CHECK_LAUNCH("ctr_cin_bwd(dw, tcgen05)");
+  }
+  return CTR_OK;
+}

@@ -20,9 +20,17 @@ namespace ctr {
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-template <int LPR>
+// Row-sharded tables: global row gr lives on rank gr % G at local row gr / G (G a power of two <= 8).
+// `base[r]` is rank r's shard as seen from THIS GPU (peer-mapped over NVLink for r != my rank), so the gather pulls
+// remote rows with the same 128-bit loads and the return all-to-all disappears into the kernel.
+struct PeerTables {
+  const float4* base[8];
+  int G, logG;
+};
+
+template <int LPR, bool SH>
 __global__ void __launch_bounds__(256)
-embed_fm2_fwd_kernel(const float4* __restrict__ table, const long long* __restrict__ row_off,
+embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, const long long* __restrict__ row_off,
                      const long long* __restrict__ ids, int B, int F, float4* __restrict__ tile,
                      float* __restrict__ fm2) {
   constexpr int RPW = 32 / LPR;             // rows fetched per warp-level load
@@ -55,7 +63,11 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const long long* __restri
           const long long r = __shfl_sync(full, row, fs);
           in[u] = fs < nf;
           v[u] = f4_zero();
-          if (in[u] && r >= 0) v[u] = ldg_stream_f4(table + (size_t)r * LPR + c);
+          if (in[u] && r >= 0) {
+            const float4* src = SH ? peers.base[r & (peers.G - 1)] + (size_t)(r >> peers.logG) * LPR + c
+                                   : table + (size_t)r * LPR + c;
+            v[u] = ldg_stream_f4(src);
+          }
         }
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
@@ -273,13 +285,20 @@ static int resident_grid(K kernel, int block, size_t smem, long long blocks_need
 }
 
 template <int LPR>
-static int launch_fwd(const float* table, const int64_t* off, const int64_t* ids, int64_t B, int64_t F,
-                      float* tile, float* fm2, cudaStream_t st) {
-  auto k = embed_fm2_fwd_kernel<LPR>;
-  const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
-  k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), reinterpret_cast<const long long*>(off),
-                          reinterpret_cast<const long long*>(ids), (int)B, (int)F,
-                          reinterpret_cast<float4*>(tile), fm2);
+static int launch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const int64_t* ids, int64_t B,
+                      int64_t F, float* tile, float* fm2, cudaStream_t st) {
+  PeerTables none = {};
+  if (peers == nullptr) {
+    auto k = embed_fm2_fwd_kernel<LPR, false>;
+    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
+    k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), none, reinterpret_cast<const long long*>(off),
+                            reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), fm2);
+  } else {
+    auto k = embed_fm2_fwd_kernel<LPR, true>;
+    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
+    k<<<grid, 256, 0, st>>>(nullptr, *peers, reinterpret_cast<const long long*>(off),
+                            reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), fm2);
+  }
   CTR_CHECK_LAUNCH("ctr_embed_fm2_fwd");
   return CTR_OK;
 }
@@ -305,6 +324,9 @@ static int dispatch_bwd(const float* tile, const float* d_tile, const float* d_f
   return launch_bwd<LPR, 0>(tile, d_tile, d_fm2, B, F, row_grads, st);
 }
 
+static int dispatch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const int64_t* ids, int64_t B,
+                        int64_t F, int64_t D, float* tile, float* fm2, cudaStream_t st);
+
 static int check_bfd(const char* fn, int64_t B, int64_t F, int64_t D) {
   CTR_REQUIRE(B >= 0 && F >= 1 && D >= 1, "%s: bad sizes B=%lld F=%lld D=%lld", fn, (long long)B, (long long)F,
               (long long)D);
@@ -313,6 +335,18 @@ static int check_bfd(const char* fn, int64_t B, int64_t F, int64_t D) {
                   "%s: D=%lld unsupported by the fused 128-bit path (need a power of two in 4..128); "
                   "use ctr_bag_lookup_* for other widths", fn, (long long)D);
   return CTR_OK;
+}
+
+static int dispatch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const int64_t* ids, int64_t B,
+                        int64_t F, int64_t D, float* tile, float* fm2, cudaStream_t st) {
+  switch (D / 4) {
+    case 1: return launch_fwd<1>(table, peers, off, ids, B, F, tile, fm2, st);
+    case 2: return launch_fwd<2>(table, peers, off, ids, B, F, tile, fm2, st);
+    case 4: return launch_fwd<4>(table, peers, off, ids, B, F, tile, fm2, st);
+    case 8: return launch_fwd<8>(table, peers, off, ids, B, F, tile, fm2, st);
+    case 16: return launch_fwd<16>(table, peers, off, ids, B, F, tile, fm2, st);
+    default: return launch_fwd<32>(table, peers, off, ids, B, F, tile, fm2, st);
+  }
 }
 
 }  // namespace ctr
@@ -328,14 +362,28 @@ extern "C" int ctr_embed_fm2_fwd(const float* table, const int64_t* field_row_of
   CTR_REQUIRE(aligned16(table) && aligned16(tile), "ctr_embed_fm2_fwd: table and tile must be 16-byte aligned");
   if (B == 0) return CTR_OK;
   cudaStream_t st = as_stream(stream);
-  switch (D / 4) {
-    case 1: return launch_fwd<1>(table, field_row_offset, ids, B, F, tile, fm2, st);
-    case 2: return launch_fwd<2>(table, field_row_offset, ids, B, F, tile, fm2, st);
-    case 4: return launch_fwd<4>(table, field_row_offset, ids, B, F, tile, fm2, st);
-    case 8: return launch_fwd<8>(table, field_row_offset, ids, B, F, tile, fm2, st);
-    case 16: return launch_fwd<16>(table, field_row_offset, ids, B, F, tile, fm2, st);
-    default: return launch_fwd<32>(table, field_row_offset, ids, B, F, tile, fm2, st);
+  return dispatch_fwd(table, nullptr, field_row_offset, ids, B, F, D, tile, fm2, st);
+}
+
+extern "C" int ctr_embed_fm2_fwd_sharded(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
+                                         const int64_t* ids, int64_t B, int64_t F, int64_t D, float* tile, float* fm2,
+                                         void* stream) {
+  int rc = check_bfd("ctr_embed_fm2_fwd_sharded", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(shard_ptrs && field_row_offset && ids, "ctr_embed_fm2_fwd_sharded: null shard_ptrs/field_row_offset/ids");
+  CTR_REQUIRE(G >= 1 && G <= 8 && (G & (G - 1)) == 0, "ctr_embed_fm2_fwd_sharded: G=%lld must be a power of two <= 8",
+              (long long)G);
+  CTR_REQUIRE(tile || fm2, "ctr_embed_fm2_fwd_sharded: both outputs are NULL");
+  PeerTables peers = {};
+  peers.G = (int)G;
+  while ((1 << peers.logG) < G) ++peers.logG;
+  for (int r = 0; r < G; ++r) {
+    CTR_REQUIRE(shard_ptrs[r] != nullptr && aligned16(shard_ptrs[r]), "ctr_embed_fm2_fwd_sharded: shard %d null/unaligned", r);
+    peers.base[r] = reinterpret_cast<const float4*>(shard_ptrs[r]);
   }
+  CTR_REQUIRE(aligned16(tile), "ctr_embed_fm2_fwd_sharded: tile must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  return dispatch_fwd(nullptr, &peers, field_row_offset, ids, B, F, D, tile, fm2, as_stream(stream));
 }
 
 extern "C" int ctr_embed_fm2_bwd(const float* tile, const float* d_tile, const float* d_fm2, int64_t B, int64_t F,

@@ -56,7 +56,9 @@ def test_cin_fwd_cuda_core_path(B, m, hk, D, H):
     assert_close(out, ref, TOL, "fwd"); assert_close(pooled, ref.sum(-1), TOL, "pooled")
 
 
-@pytest.mark.parametrize("B,m,hk,D,H", [(3, 5, 4, 8, 7), (8, 30, 30, 16, 128), (4, 30, 128, 16, 128), (33, 8, 50, 8, 50)])
+@pytest.mark.parametrize("B,m,hk,D,H", [(3, 5, 4, 8, 7), (8, 30, 30, 16, 128), (4, 30, 128, 16, 128), (33, 8, 50, 8, 50),
+                                        (70, 30, 100, 16, 100), (9, 32, 13, 32, 48), (1, 1, 1, 16, 1), (300, 6, 9, 16, 20),
+                                        (5, 7, 6, 4, 9), (3, 40, 5, 8, 9)])
 def test_cin_bwd(B, m, hk, D, H):
     from recalgorithm_b200 import ops
     rng = np.random.default_rng(B + m + hk + D + H + 1)
