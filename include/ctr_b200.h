@@ -34,6 +34,7 @@ extern "C" {
 const char* ctr_last_error(void);
 int ctr_version(void);                          /* ABI version, currently 1 */
 int ctr_device_info(int* sm_count, int* cc_major, int* cc_minor);   /* current device */
+int ctr_enable_peer_access(int peer_device);     /* map `peer_device`'s memory into the current device (NVLink P2P); idempotent */
 int64_t ctr_kernel_launches(void);              /* kernels launched by this library so far (process-wide) */
 
 /* ---- Row L + FM2: fused embedding lookup + DeepFM second-order term ------------------------------
@@ -65,6 +66,33 @@ int ctr_embed_fm2_bwd(const float* tile, const float* d_tile, const float* d_fm2
  * NOT zeroed here.  fp32 red.global.add -> summation order is not deterministic. */
 int ctr_embed_scatter_add(float* grad_table, const int64_t* field_row_offset, const int64_t* ids,
                           const float* row_grads, int64_t B, int64_t F, int64_t D, void* stream);
+
+/* ---- Row (e): row-sharded tables across the GPUs of one NVSwitch box -----------------------------------------
+ * Global row gr = field_row_offset[f] + id is owned by rank gr % G and stored at local row gr / G (G a power of two <= 8).
+ * The reference has no multi-device path; the semantics kept are the lookup's and the IndexedSlices gradient's.
+ *
+ * Forward: same contract as ctr_embed_fm2_fwd, but rows are PULLED from the owners' shards inside the gather kernel.
+ * shard_ptrs: HOST array of G device pointers, entry r = rank r's shard (ceil(V_total/G), D) as mapped into THIS process
+ * (CUDA IPC / peer mapping for r != own rank).  No collective is involved. */
+int ctr_embed_fm2_fwd_sharded(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
+                              const int64_t* ids, int64_t B, int64_t F, int64_t D, float* tile, float* fm2, void* stream);
+/* Backward exchange fused into one kernel: every valid (b,f) writes (local_row, row_grads[b,f,:]) into its OWNER's receive
+ * buffer with peer stores.  recv_vals / recv_rows: HOST arrays of G device pointers; entry d = owner d's buffers
+ * (G_src, capacity, D) fp32 / (G_src, capacity) int64 as mapped into this process; this rank writes slice [my_rank].
+ * counters: device int64[G], zeroed here, ends as the number of entries sent to each owner; *overflow is OR-ed with 1 if
+ * an owner's slice would exceed `capacity` (those entries are dropped).  Follow with ctr_sharded_publish_counts, a
+ * stream sync and a cross-rank barrier before any owner reads its buffers. */
+int ctr_sharded_grad_push(const float* row_grads, const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F,
+                          int64_t D, int64_t G, int64_t my_rank, float* const* recv_vals, int64_t* const* recv_rows,
+                          int64_t capacity, int64_t* counters, int* overflow, void* stream);
+/* peer_counts_dev: DEVICE array of G device pointers; entry d = owner d's int64[G] count vector (peer mapped);
+ * writes peer_counts[d][my_rank] = counters[d]. */
+int ctr_sharded_publish_counts(const int64_t* counters, int64_t* const* peer_counts_dev, int64_t G, int64_t my_rank,
+                               void* stream);
+/* Owner side / generic IndexedSlices consumer: dst[rows[i], :] += vals[i, :] for i < min(*count, max_n) (count may be
+ * NULL = max_n); rows outside [0, V) are ignored.  fp32 vector red.global.add. */
+int ctr_rows_scatter_add(float* dst, int64_t V, int64_t D, const int64_t* rows, const float* vals, const int64_t* count,
+                         int64_t max_n, void* stream);
 
 /* DeepFM first-order ("wide") term as a D=1 lookup.  Replaces indicator_column multi-hot (B, sum V) @
  * dense(1) (DeepFM/deepfm.py:72-80,180-181): out[b] = bias + sum_f w[field_row_offset[f] + ids[b,f]]; invalid ids add 0.

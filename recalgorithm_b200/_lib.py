@@ -23,10 +23,15 @@ SIGNATURES = {
     "ctr_last_error": (c_char_p, []),
     "ctr_version": (c_int, []),
     "ctr_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "ctr_enable_peer_access": (c_int, [c_int]),
     "ctr_kernel_launches": (c_int64, []),
     "ctr_embed_fm2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ctr_embed_fm2_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "ctr_embed_scatter_add": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "ctr_embed_fm2_fwd_sharded": (c_int, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "ctr_sharded_grad_push": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
+    "ctr_sharded_publish_counts": (c_int, [_P, _P, _I, _I, _P]),
+    "ctr_rows_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, _I, _P]),
     "ctr_first_order_fwd": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, _P, _P]),
     "ctr_bag_lookup_fwd": (c_int, [_P, _I, _I, _P, _P, _I, _P, _I, _P]),
     "ctr_bag_lookup_bwd": (c_int, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),

@@ -35,6 +35,25 @@ const char* ctr_last_error(void) { return ctr::g_err; }
 int ctr_version(void) { return 1; }
 int64_t ctr_kernel_launches(void) { return ctr::g_launches.load(); }
 
+int ctr_enable_peer_access(int peer_device) {
+  int dev = 0;
+  CTR_CUDA(cudaGetDevice(&dev));
+  if (peer_device == dev) return CTR_OK;
+  int can = 0;
+  CTR_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  if (!can) {
+    ctr::set_error("ctr_enable_peer_access: device %d cannot access device %d over P2P", dev, peer_device);
+    return CTR_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return CTR_OK; }
+  if (e != cudaSuccess) {
+    ctr::set_error("cudaDeviceEnablePeerAccess(%d) failed: %s", peer_device, cudaGetErrorString(e));
+    return CTR_ERR_CUDA;
+  }
+  return CTR_OK;
+}
+
 int ctr_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   CTR_CUDA(cudaGetDevice(&dev));

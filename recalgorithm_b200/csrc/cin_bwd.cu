@@ -52,18 +52,29 @@ __global__ void split_grad_kernel(const float* __restrict__ g, float* __restrict
 
 // ================================================================================================= dX kernel
 constexpr int DX_THREADS = 192;     // 4 row-owner warps + TMA warp + MMA warp
-constexpr int DX_DBUF = 8;          // dZ_i buffers of 32 TMEM columns at columns [256, 512)
+constexpr int DX_IPS = 2;           // i's per MMA step: N = 64 keeps the single issuing thread ahead of the tensor pipe
+constexpr int DX_N = DX_IPS * KB;   // 64 columns of dZ per step
+constexpr int DX_DBUF = 4;          // dZ buffers of 64 TMEM columns at columns [256, 512)
 
-template <int SB>
+// 4-D TMA view of the split filter (n_inner 32 | row | i-in-step | n_outer): one box lands as
+//   [n_outer kb][i_t][32 rows][128 B]  = per kb one K-major [64 rows x 128 B] SWIZZLE_128B operand tile.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+template <int SB, int NKB>
 __global__ void __launch_bounds__(DX_THREADS, 1)
 cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ x0,
                      const float* __restrict__ xk, const float* __restrict__ g, float* __restrict__ dx0,
-                     float* __restrict__ dxk, int B, int m, int hk, int logD, int H, int HP, int KRP) {
+                     float* __restrict__ dxk, int B, int m, int hk, int logD, int H, int KRP) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int nkb = HP / KB;                                 // K-blocks of 32 n per MMA group
-  const int b_copy_bytes = nkb * 32 * 128;                 // one (hi or lo) copy: nkb sub-tiles of [32 rows x 128 B]
-  const int stage_bytes = 2 * b_copy_bytes;
+  constexpr int HP = NKB * KB;
+  constexpr int b_copy_bytes = NKB * DX_N * 128;           // one (hi or lo) copy: NKB sub-tiles of [64 rows x 128 B]
+  constexpr int stage_bytes = 2 * b_copy_bytes;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SB * stage_bytes;
   auto full_b = [&](int s) { return bar0 + 8 * s; };
@@ -77,6 +88,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
   const int D = 1 << logD;
   const long long rows_total = (long long)B * D;
   const int num_tiles = (int)((rows_total + BM - 1) / BM);
+  const int nsteps = (hk + DX_IPS - 1) / DX_IPS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
@@ -93,7 +105,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
   const uint32_t d_col0 = tmem_base + 256u;
 
   if (warp < 4) {
-    // ============================ row owners: stage Gt once per tile, then consume dZ_i ============================
+    // ============================ row owners: stage Gt once per tile, then consume dZ of two i per step ============================
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     uint32_t di = 0;                                   // dZ buffer use counter (same sequence as the MMA warp)
     int lt = 0;
@@ -111,6 +123,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
       mbar_wait(a_empty, (lt & 1) ^ 1);                // MMAs of the previous tile no longer read the A columns
       tc_fence_after();
       const float* gp = g + (size_t)b * H * D + d;
+#pragma unroll 1
       for (int n0 = 0; n0 < HP; n0 += 8) {
         float v[8], h[8];
 #pragma unroll
@@ -127,31 +140,36 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
       const float* xkp = xk + (size_t)b * hk * D + d;
-      float xnext = valid ? __ldg(xkp) : 0.f;
-      for (int i = 0; i < hk; ++i, ++di) {
-        const float xi = xnext;
-        if (i + 1 < hk) xnext = valid ? __ldg(xkp + (size_t)(i + 1) * D) : 0.f;
+      for (int st = 0; st < nsteps; ++st, ++di) {
+        const int i0 = st * DX_IPS;
+        float xi[DX_IPS];
+#pragma unroll
+        for (int t = 0; t < DX_IPS; ++t) xi[t] = (valid && i0 + t < hk) ? __ldg(xkp + (size_t)(i0 + t) * D) : 0.f;
         const uint32_t q = di % DX_DBUF;
         mbar_wait(d_full(q), (di / DX_DBUF) & 1u);
         tc_fence_after();
-        float dz[KB];
-        {
-          float v0[16], v1[16];
-          tmem_ld16(d_col0 + lane_sel + q * KB, v0);
-          tmem_ld16(d_col0 + lane_sel + q * KB + 16, v1);
+        float dz[DX_IPS][KB];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { dz[j] = v0[j]; dz[16 + j] = v1[j]; }
+        for (int t = 0; t < DX_IPS; ++t) {
+          float v0[16], v1[16];
+          tmem_ld16(d_col0 + lane_sel + q * DX_N + t * KB, v0);
+          tmem_ld16(d_col0 + lane_sel + q * DX_N + t * KB + 16, v1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { dz[t][j] = v0[j]; dz[t][16 + j] = v1[j]; }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d_empty(q));         // buffer can be overwritten by dZ_{i+8}
-        float s = 0.f;
+        if (lane == 0) mbar_arrive(d_empty(q));         // buffer may be overwritten by a later step
 #pragma unroll
-        for (int j = 0; j < KB; ++j) {
-          s += dz[j] * x0v[j];                           // x0v[j >= m] == 0 masks the columns that belong to row i+1
-          dx0acc[j] += dz[j] * xi;
+        for (int t = 0; t < DX_IPS; ++t) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+            s += dz[t][j] * x0v[j];                      // x0v[j >= m] == 0 masks the rows that belong to the next i
+            dx0acc[j] += dz[t][j] * xi[t];               // xi == 0 for i >= hk
+          }
+          if (valid && i0 + t < hk) dxk[((size_t)b * hk + i0 + t) * D + d] = s;
         }
-        if (valid) dxk[((size_t)b * hk + i) * D + d] = s;
       }
       if (valid) {
 #pragma unroll
@@ -160,49 +178,55 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
       }
     }
   } else if (warp == 4) {
-    // ============================ TMA: filter rows of K-block i (hi and lo copies) ============================
+    // ============================ TMA: filter rows of i0 and i0+1 (hi and lo copies) ============================
     if (lane == 0) {
       int s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int i = 0; i < hk; ++i) {
+        for (int st = 0; st < nsteps; ++st) {
           mbar_wait(empty_b(s), ph ^ 1);
           const uint32_t dst = sbase + s * stage_bytes;
           mbar_expect_tx(full_b(s), (uint32_t)stage_bytes);
-          tma_load_3d(dst, &tmap_w, 0, i * m, 0, full_b(s));
-          tma_load_3d(dst + b_copy_bytes, &tmap_w, 0, KRP + i * m, 0, full_b(s));
+          tma_load_4d(dst, &tmap_w, 0, st * DX_IPS * m, 0, 0, full_b(s));
+          tma_load_4d(dst + b_copy_bytes, &tmap_w, 0, KRP + st * DX_IPS * m, 0, 0, full_b(s));
           if (++s == SB) { s = 0; ph ^= 1; }
         }
       }
     }
   } else {
-    // ============================ MMA issuer ============================
+    // ============================ MMA issuer (fully unrolled: 3 passes x NKB x 4 MMAs of 128x64x8) ============================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(KB);        // N = 32
+      const uint32_t idesc = umma_idesc_tf32(DX_N);
       int s = 0, ph = 0, lt = 0;
       uint32_t di = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         mbar_wait(a_full, lt & 1);
         tc_fence_after();
-        for (int i = 0; i < hk; ++i, ++di) {
+        for (int st = 0; st < nsteps; ++st, ++di) {
           const uint32_t q = di % DX_DBUF;
           mbar_wait(d_empty(q), ((di / DX_DBUF) & 1u) ^ 1u);
           mbar_wait(full_b(s), ph);
           tc_fence_after();
-          const uint32_t dcol = d_col0 + q * KB;
-          const uint32_t st = sbase + s * stage_bytes;
-          // small terms first: Glo.Whi, Ghi.Wlo, then Ghi.Whi
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a_col = tmem_base + (pass == 0 ? (uint32_t)HP : 0u);
-            const uint32_t b_base = st + (pass == 1 ? (uint32_t)b_copy_bytes : 0u);
-            for (int kb = 0; kb < nkb; ++kb) {
-              const uint64_t bdesc = umma_desc_sw128(b_base + kb * 4096);
+          const uint32_t dcol = d_col0 + q * DX_N;
+          const uint64_t b_hi = umma_desc_sw128(sbase + s * stage_bytes);
+          const uint64_t b_lo = umma_desc_sw128(sbase + s * stage_bytes + b_copy_bytes);
+          const uint32_t a_hi = tmem_base, a_lo = tmem_base + (uint32_t)HP;
+          // small terms first: Glo.Whi, Ghi.Wlo, then Ghi.Whi ; sub-tile kb starts DX_N*128 bytes (>>4 = 512) further
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_tf32_ts(dcol, a_col + (uint32_t)(kb * KB + 8 * k), bdesc + 2 * k, idesc,
-                             (pass | kb | k) != 0 ? 1u : 0u);
-            }
-          }
+          for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts(dcol, a_lo + (uint32_t)(kb * KB + 8 * k), b_hi + (uint64_t)(kb * (DX_N * 128 / 16) + 2 * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts(dcol, a_hi + (uint32_t)(kb * KB + 8 * k), b_lo + (uint64_t)(kb * (DX_N * 128 / 16) + 2 * k), idesc, 1u);
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts(dcol, a_hi + (uint32_t)(kb * KB + 8 * k), b_hi + (uint64_t)(kb * (DX_N * 128 / 16) + 2 * k), idesc, 1u);
           umma_commit(empty_b(s));
           umma_commit(d_full(q));
           if (++s == SB) { s = 0; ph ^= 1; }
@@ -223,17 +247,17 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
 constexpr int DW_THREADS = 384;     // 8 (i,j)-row warps + TMA warp + MMA warp (+2 idle, completes the third warpgroup)
 constexpr int DW_BLOCKS = 2;        // (i,j) blocks of 128 rows per CTA  (= 8 consecutive i)
 
-template <int SB, int NPT>
+template <int SB, int NPT, int D>
 __global__ void __launch_bounds__(DW_THREADS, 1)
 cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __restrict__ x0,
-                     const float* __restrict__ xk, float* __restrict__ dw, int B, int m, int hk, int D, int H, int NP,
+                     const float* __restrict__ xk, float* __restrict__ dw, int B, int m, int hk, int H, int NP,
                      int ngroups, int nslices, int chunk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int row_bytes = D * 4;                             // one sample's D values of one n-row (= swizzle width)
+  constexpr int row_bytes = D * 4;                         // one sample's D values of one n-row (= swizzle width)
   const int b_copy_bytes = NP * row_bytes;
   const int stage_bytes = 2 * b_copy_bytes;
-  const int SA = 256 / (DW_BLOCKS * 2 * D);                // A stages in TMEM columns [256, 512)
+  constexpr int SA = 256 / (DW_BLOCKS * 2 * D);            // A stages in TMEM columns [256, 512)
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SB * stage_bytes;
   auto full_b = [&](int s) { return bar0 + 8 * s; };
@@ -308,6 +332,7 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __
         mbar_wait(empty_a(sa), pha ^ 1);
         tc_fence_after();
         const uint32_t a_hi = a_stage0 + lane_sel + (uint32_t)((sa * DW_BLOCKS + t) * 2 * D);
+#pragma unroll
         for (int c8 = 0; c8 < D; c8 += 8) {
           float p[8], h[8];
           if (live) {
@@ -381,8 +406,11 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __
             const uint32_t a_hi = a_stage0 + (uint32_t)((sa * DW_BLOCKS + tt) * 2 * D);
             const uint32_t a_lo = a_hi + (uint32_t)D;
             const uint32_t dcol = tmem_base + (uint32_t)(tt * NP);
+#pragma unroll
             for (int k = 0; k < D / 8; ++k) umma_tf32_ts(dcol, a_lo + 8 * k, b_hi + 2 * k, idesc, k > 0 ? 1u : first);
+#pragma unroll
             for (int k = 0; k < D / 8; ++k) umma_tf32_ts(dcol, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
             for (int k = 0; k < D / 8; ++k) umma_tf32_ts(dcol, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
           }
           umma_commit(empty_a(sa));
@@ -418,17 +446,17 @@ extern "C" __attribute__((visibility("hidden"))) int ctr_cin_bwd_tc_supported(in
 
 extern "C" int64_t ctr_cin_bwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H) {
   if (!ctr_cin_bwd_tc_supported(m, hk, D, H)) return 0;
-  const int64_t HP = pad_to(H, 32), KRP = hk * m + 32;
-  return (2 * KRP * HP + 2 * B * H * D) * (int64_t)sizeof(float);
+  const int64_t HP = pad_to(H, 32), KRP = (hk + 2) * m + 32;
+  return ((2 * KRP + m) * HP + 2 * B * H * D) * (int64_t)sizeof(float);
 }
 
 // Returns CTR_OK after enqueueing both tensor-core kernels; the caller has already validated the arguments.
 int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const float* g_out, int64_t B, int64_t m,
                    int64_t hk, int64_t D, int64_t H, float* dx0, float* dxk, float* dfilter, void* workspace,
                    cudaStream_t st) {
-  const int HP = (int)pad_to(H, 32), NP = (int)pad_to(H, 16), KRP = (int)(hk * m + 32);
+  const int HP = (int)pad_to(H, 32), NP = (int)pad_to(H, 16), KRP = (int)((hk + 2) * m + 32);
   float* ws_w = static_cast<float*>(workspace);
-  float* ws_g = ws_w + (size_t)2 * KRP * HP;
+  float* ws_g = ws_w + (size_t)(2 * KRP + m) * HP;          // + m rows so the i-in-step window of the lo copy stays inside
   {
     const long long total = (long long)KRP * HP;
     split_filter_native_kernel<<<(int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048), 256, 0, st>>>(
@@ -445,28 +473,35 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
   }
   int logD = 0;
   while ((1 << logD) < D) ++logD;
-  // ---- dX: filter as a 3-D tensor (n_inner 32 | row | n_outer) so one box lands as HP/32 swizzled [32 x 128 B] sub-tiles
+  // ---- dX: filter as a 4-D tensor (n_inner 32 | row | i-in-step (stride m rows) | n_outer) so one box lands as
+  //      HP/32 K-major [64 rows x 128 B] swizzled sub-tiles holding the rows of i0 and i0+1
   {
     CUtensorMap tmap;
-    const cuuint64_t gdim[3] = {32, (cuuint64_t)(2 * KRP), (cuuint64_t)(HP / 32)};
-    const cuuint64_t gstr[2] = {(cuuint64_t)HP * sizeof(float), 32 * sizeof(float)};
-    const cuuint32_t box[3] = {32, 32, (cuuint32_t)(HP / 32)};
-    const cuuint32_t es[3] = {1, 1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws_w, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t gdim[4] = {32, (cuuint64_t)(2 * KRP), (cuuint64_t)DX_IPS, (cuuint64_t)(HP / 32)};
+    const cuuint64_t gstr[3] = {(cuuint64_t)HP * sizeof(float), (cuuint64_t)m * HP * sizeof(float), 32 * sizeof(float)};
+    const cuuint32_t box[4] = {32, 32, (cuuint32_t)DX_IPS, (cuuint32_t)(HP / 32)};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ws_w, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
       set_error("ctr_cin_bwd: cuTensorMapEncodeTiled(filter) failed with CUresult %d", (int)cr);
       return CTR_ERR_CUDA;
     }
-    constexpr int SB = 6;
-    const int stage_bytes = 2 * (HP / 32) * 4096;
+    constexpr int SB = 3;
+    const int nkb = HP / 32;
+    const int stage_bytes = 2 * nkb * DX_N * 128;
     const int smem = SB * stage_bytes + 8 * (2 * SB + 2 * DX_DBUF + 2) + 16 + 1024;
-    auto k = cin_bwd_dx_tc_kernel<SB>;
-    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long rows = (long long)B * D;
     const int tiles = (int)((rows + BM - 1) / BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    k<<<grid, DX_THREADS, smem, st>>>(tmap, x0, xk, g_out, dx0, dxk, (int)B, (int)m, (int)hk, logD, (int)H, HP, KRP);
+#define DX_LAUNCH(NKB_)                                                                                              \
+  {                                                                                                                  \
+    auto k = cin_bwd_dx_tc_kernel<SB, NKB_>;                                                                         \
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                            \
+    k<<<grid, DX_THREADS, smem, st>>>(tmap, x0, xk, g_out, dx0, dxk, (int)B, (int)m, (int)hk, logD, (int)H, KRP);    \
+  }
+    if (nkb == 1) DX_LAUNCH(1) else if (nkb == 2) DX_LAUNCH(2) else if (nkb == 3) DX_LAUNCH(3) else DX_LAUNCH(4)
+#undef DX_LAUNCH
     CTR_CHECK_LAUNCH("ctr_cin_bwd(dx, tcgen05)");
   }
   // ---- dW: g (hi | lo stacked along the batch axis) as a 3-D tensor (d | n | b); box = one sample's [NP x D] tile
@@ -493,14 +528,17 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
     if (nslices > B) nslices = (int)B;
     const int grid = ngroups * nslices;
     const int chunk = (int)(256 / D);                        // 96 chained MMAs per accumulator before a drain
-#define DW_LAUNCH(NPT_)                                                                                              \
+#define DW_LAUNCH(NPT_, D_)                                                                                          \
   {                                                                                                                  \
-    auto k = cin_bwd_dw_tc_kernel<SB, NPT_>;                                                                         \
+    auto k = cin_bwd_dw_tc_kernel<SB, NPT_, D_>;                                                                     \
     CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                            \
-    k<<<grid, DW_THREADS, smem, st>>>(tmap, x0, xk, dfilter, (int)B, (int)m, (int)hk, (int)D, (int)H, NP, ngroups,   \
-                                      nslices, chunk);                                                               \
+    k<<<grid, DW_THREADS, smem, st>>>(tmap, x0, xk, dfilter, (int)B, (int)m, (int)hk, (int)H, NP, ngroups, nslices,  \
+                                      chunk);                                                                        \
   }
-    if (NP <= 32) DW_LAUNCH(32) else if (NP <= 64) DW_LAUNCH(64) else DW_LAUNCH(128)
+#define DW_LAUNCH_D(NPT_)                                                                                            \
+  if (D == 8) DW_LAUNCH(NPT_, 8) else if (D == 16) DW_LAUNCH(NPT_, 16) else DW_LAUNCH(NPT_, 32)
+    if (NP <= 32) { DW_LAUNCH_D(32) } else if (NP <= 64) { DW_LAUNCH_D(64) } else { DW_LAUNCH_D(128) }
+#undef DW_LAUNCH_D
 #undef DW_LAUNCH
     CTR_CHECK_LAUNCH("ctr_cin_bwd(dw, tcgen05)");
   }
