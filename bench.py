@@ -227,6 +227,8 @@ def run_ours(args, cfg):
     sharded_mode = bool(cfg.get("sharded"))
     B, F, D, NB = cfg["B"], cfg["F"], cfg["D"], cfg["id_batches"]
     rows = cfg["rows_per_field_per_rank"] * world if sharded_mode else cfg["rows_per_field"]
+    if os.environ.get("CTR_BENCH_ROWS"):                       # experiment knob (table-size sweeps); not used by default
+        rows = int(os.environ["CTR_BENCH_ROWS"])
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 
     if sharded_mode:

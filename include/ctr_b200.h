@@ -35,6 +35,13 @@ const char* ctr_last_error(void);
 int ctr_version(void);                          /* ABI version, currently 1 */
 int ctr_device_info(int* sm_count, int* cc_major, int* cc_minor);   /* current device */
 int ctr_enable_peer_access(int peer_device);     /* map `peer_device`'s memory into the current device (NVLink P2P); idempotent */
+/* Peer-mappable device buffers for the row-sharded path: a plain device allocation, its 64-byte CUDA-IPC handle, and the
+ * import of a peer's handle into the current device's address space (peer access over NVLink is enabled on import). */
+int ctr_peer_alloc(int64_t bytes, void** ptr);
+int ctr_peer_free(void* ptr);
+int ctr_ipc_export(void* ptr, unsigned char* handle64);
+int ctr_ipc_import(const unsigned char* handle64, void** ptr);
+int ctr_ipc_close(void* ptr);
 int64_t ctr_kernel_launches(void);              /* kernels launched by this library so far (process-wide) */
 
 /* ---- Row L + FM2: fused embedding lookup + DeepFM second-order term ------------------------------

@@ -24,6 +24,11 @@ SIGNATURES = {
     "ctr_version": (c_int, []),
     "ctr_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "ctr_enable_peer_access": (c_int, [c_int]),
+    "ctr_peer_alloc": (c_int, [_I, POINTER(c_void_p)]),
+    "ctr_peer_free": (c_int, [_P]),
+    "ctr_ipc_export": (c_int, [_P, ctypes.c_char_p]),
+    "ctr_ipc_import": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),
+    "ctr_ipc_close": (c_int, [_P]),
     "ctr_kernel_launches": (c_int64, []),
     "ctr_embed_fm2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ctr_embed_fm2_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),

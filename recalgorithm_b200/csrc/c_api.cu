@@ -1,5 +1,6 @@
 // Library-level entry points of libctr_b200.so: error text, version, device info, launch counter.
 #include <stdarg.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -51,6 +52,37 @@ int ctr_enable_peer_access(int peer_device) {
     ctr::set_error("cudaDeviceEnablePeerAccess(%d) failed: %s", peer_device, cudaGetErrorString(e));
     return CTR_ERR_CUDA;
   }
+  return CTR_OK;
+}
+
+// ---- peer-mappable buffers (row-sharded tables): plain cudaMalloc allocations exported / imported with CUDA IPC.
+int ctr_peer_alloc(int64_t bytes, void** ptr) {
+  CTR_REQUIRE(ptr != nullptr && bytes > 0, "ctr_peer_alloc: bad arguments");
+  CTR_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  return CTR_OK;
+}
+int ctr_peer_free(void* ptr) {
+  if (ptr) CTR_CUDA(cudaFree(ptr));
+  return CTR_OK;
+}
+int ctr_ipc_export(void* ptr, unsigned char* handle64) {
+  CTR_REQUIRE(ptr && handle64, "ctr_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CTR_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return CTR_OK;
+}
+// Opens in the CURRENT device's context with lazy peer access: the mapping is usable by kernels of this device.
+int ctr_ipc_import(const unsigned char* handle64, void** ptr) {
+  CTR_REQUIRE(ptr && handle64, "ctr_ipc_import: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CTR_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return CTR_OK;
+}
+int ctr_ipc_close(void* ptr) {
+  if (ptr) CTR_CUDA(cudaIpcCloseMemHandle(ptr));
   return CTR_OK;
 }
 

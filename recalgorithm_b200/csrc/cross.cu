@@ -103,8 +103,14 @@ cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
   }
 }
 
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
 // CPT = ceil(d / blockDim) columns per thread in phase 2.
-template <int VEC, int N, int CPT>
+// PF: the (x0, xs, g) tiles of the NEXT iteration are fetched with cp.async into a second shared-memory buffer while
+// this iteration computes (the kernel is otherwise bound by exposed global-load latency: 8 warps/SM, one sample each).
+template <int VEC, int N, int CPT, bool PF, int LM>
 __global__ void __launch_bounds__(CROSS_WARPS * 32)
 cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, const float* __restrict__ w,
                  const float* __restrict__ b, const float* __restrict__ g_out, int B, int d, int L,
@@ -114,12 +120,11 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
   float* sw = smem;                                  // (L, d)  weights
   float* sb = sw + (size_t)L * d;                    // (L, d)  biases
   float* scb = sb + (size_t)L * d;                   // (L, d)  prefix biases  cb_l = sum_{k<l} b_k
-  float* tx0 = scb + (size_t)L * d;                  // (W, d)  x0 tile
-  float* txs = tx0 + (size_t)CROSS_WARPS * d;        // (W, d)  start-vector tile (aliases tx0 when xl_in == NULL)
-  float* tg = xl_in ? txs + (size_t)CROSS_WARPS * d : txs;   // (W, d) g_out tile
-  if (!xl_in) txs = tx0;
-  float* scs = tg + (size_t)CROSS_WARPS * d;         // (W, LMAX)  cs_l = sum_{k<l} s_k
-  float* st = scs + CROSS_WARPS * CROSS_LMAX;        // (W, LMAX)  t_l
+  const int narr = xl_in ? 3 : 2;                    // tiles per buffer: x0, [xs], g
+  const size_t buf_floats = (size_t)narr * CROSS_WARPS * d;
+  float* tiles0 = scb + (size_t)L * d;               // buffer 0 (and buffer 1 right behind it when PF)
+  float* scs = tiles0 + (PF ? 2 : 1) * buf_floats;   // (W, LMAX)  cs_l = sum_{k<l} s_k
+  float* st = scs + CROSS_WARPS * LM;        // (W, LMAX)  t_l
   __shared__ int s_valid[CROSS_WARPS];
 
   for (int i = threadIdx.x; i < L * d; i += blockDim.x) { sw[i] = __ldg(w + i); sb[i] = __ldg(b + i); }
@@ -130,35 +135,68 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
   }
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
-  float acc_dw[CROSS_LMAX][CPT], acc_db[CROSS_LMAX][CPT];
+  float acc_dw[LM][CPT], acc_db[LM][CPT];
 #pragma unroll
-  for (int l = 0; l < CROSS_LMAX; ++l)
+  for (int l = 0; l < LM; ++l)
 #pragma unroll
     for (int c = 0; c < CPT; ++c) { acc_dw[l][c] = 0.f; acc_db[l][c] = 0.f; }
   __syncthreads();
 
   const int ntiles = (B + CROSS_WARPS - 1) / CROSS_WARPS;
+  const unsigned tiles_u32 = (unsigned)__cvta_generic_to_shared(tiles0);
+  auto issue_tile = [&](int tile, int buf) {          // cp.async the tile's contiguous 8*d floats of each array
+    const unsigned base = tiles_u32 + (unsigned)(buf * buf_floats * sizeof(float));
+    const long long first = (long long)tile * CROSS_WARPS;
+    const int nfl = (int)min((long long)CROSS_WARPS, (long long)B - first) * d;
+    const unsigned arr_bytes = (unsigned)(CROSS_WARPS * d * sizeof(float));
+    for (int i = threadIdx.x * 4; i < nfl; i += blockDim.x * 4) {
+      cp_async16(base + 4u * i, x0 + first * d + i);
+      if (xl_in) cp_async16(base + arr_bytes + 4u * i, xl_in + first * d + i);
+      cp_async16(base + (narr - 1) * arr_bytes + 4u * i, g_out + first * d + i);
+    }
+  };
+  int buf = 0;
+  if (PF) {
+    if ((int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int s = tile * CROSS_WARPS + wid;
+    float* tx0 = tiles0 + (size_t)(PF ? buf : 0) * buf_floats;
+    float* txs = xl_in ? tx0 + (size_t)CROSS_WARPS * d : tx0;
+    float* tg = tx0 + (size_t)(narr - 1) * CROSS_WARPS * d;
+    if (PF) {
+      const int next = tile + gridDim.x;
+      if (next < ntiles) issue_tile(next, buf ^ 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");     // this iteration's tile has landed
+      __syncthreads();
+    }
     // ---------------- phase 1: warp per sample ----------------
     if (lane == 0) s_valid[wid] = s < B;
     if (s < B) {
       LaneVec<VEC, N> a0, x, g;
-      a0.load(x0 + (size_t)s * d, d, lane);
-      if (xl_in) x.load(xl_in + (size_t)s * d, d, lane);
-      else {
+      if (PF) {
+        lane_load_smem<VEC, N>(a0.v, tx0 + (size_t)wid * d, d, lane);
+        lane_load_smem<VEC, N>(x.v, txs + (size_t)wid * d, d, lane);
+        lane_load_smem<VEC, N>(g.v, tg + (size_t)wid * d, d, lane);
+      } else {
+        a0.load(x0 + (size_t)s * d, d, lane);
+        if (xl_in) x.load(xl_in + (size_t)s * d, d, lane);
+        else {
 #pragma unroll
-        for (int k = 0; k < N * VEC; ++k) x.v[k] = a0.v[k];
+          for (int k = 0; k < N * VEC; ++k) x.v[k] = a0.v[k];
+        }
+        g.load(g_out + (size_t)s * d, d, lane);
+        a0.store(tx0 + (size_t)wid * d, d, lane);
+        if (xl_in) x.store(txs + (size_t)wid * d, d, lane);
+        g.store(tg + (size_t)wid * d, d, lane);
       }
-      g.load(g_out + (size_t)s * d, d, lane);
-      a0.store(tx0 + (size_t)wid * d, d, lane);
-      if (xl_in) x.store(txs + (size_t)wid * d, d, lane);
-      g.store(tg + (size_t)wid * d, d, lane);
       // forward recurrence -> s_l (kept in registers of every lane), prefix sums to smem
-      float sl[CROSS_LMAX];
+      float sl[LM];
       float cs = 0.f;
 #pragma unroll
-      for (int l = 0; l < CROSS_LMAX; ++l) {
+      for (int l = 0; l < LM; ++l) {
         sl[l] = 0.f;
         if (l < L) {
           float wv[N * VEC], bv[N * VEC];
@@ -169,7 +207,7 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
           for (int k = 0; k < N * VEC; ++k) dot += x.v[k] * wv[k];
           dot = warp_sum(dot);
           sl[l] = dot;
-          if (lane == 0) scs[wid * CROSS_LMAX + l] = cs;
+          if (lane == 0) scs[wid * LM + l] = cs;
           cs += dot;
 #pragma unroll
           for (int k = 0; k < N * VEC; ++k) x.v[k] = (a0.v[k] * dot + bv[k]) + x.v[k];
@@ -179,7 +217,7 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
 #pragma unroll
       for (int k = 0; k < N * VEC; ++k) x.v[k] = 0.f;
 #pragma unroll
-      for (int l = CROSS_LMAX - 1; l >= 0; --l) {
+      for (int l = LM - 1; l >= 0; --l) {
         if (l < L) {
           float wv[N * VEC];
           lane_load_smem<VEC, N>(wv, sw + (size_t)l * d, d, lane);
@@ -187,7 +225,7 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
 #pragma unroll
           for (int k = 0; k < N * VEC; ++k) t += g.v[k] * a0.v[k];
           t = warp_sum(t);
-          if (lane == 0) st[wid * CROSS_LMAX + l] = t;
+          if (lane == 0) st[wid * LM + l] = t;
 #pragma unroll
           for (int k = 0; k < N * VEC; ++k) {
             x.v[k] += g.v[k] * sl[l];
@@ -214,10 +252,10 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
           const float vx0 = tx0[(size_t)q * d + i], vxs = txs[(size_t)q * d + i];
           float gl = tg[(size_t)q * d + i];
 #pragma unroll
-          for (int l = CROSS_LMAX - 1; l >= 0; --l) {
+          for (int l = LM - 1; l >= 0; --l) {
             if (l < L) {
-              const float t = st[q * CROSS_LMAX + l];
-              const float xl = (vx0 * scs[q * CROSS_LMAX + l] + scb[(size_t)l * d + i]) + vxs;
+              const float t = st[q * LM + l];
+              const float xl = (vx0 * scs[q * LM + l] + scb[(size_t)l * d + i]) + vxs;
               acc_dw[l][c] += xl * t;
               acc_db[l][c] += gl;
               gl += t * sw[(size_t)l * d + i];
@@ -227,13 +265,14 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
       }
     }
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
   for (int c = 0; c < CPT; ++c) {
     const int i = c * (CROSS_WARPS * 32) + threadIdx.x;
     if (i < d) {
 #pragma unroll
-      for (int l = 0; l < CROSS_LMAX; ++l) {
+      for (int l = 0; l < LM; ++l) {
         if (l < L) {
           atomicAdd(dw + (size_t)l * d + i, acc_dw[l][c]);
           atomicAdd(db + (size_t)l * d + i, acc_db[l][c]);
@@ -243,9 +282,9 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
   }
 }
 
-static size_t cross_bwd_smem(int64_t d, int64_t L, bool has_xl) {
-  return sizeof(float) * ((size_t)3 * L * d + (size_t)(has_xl ? 3 : 2) * CROSS_WARPS * d +
-                          2 * CROSS_WARPS * CROSS_LMAX);
+static size_t cross_bwd_smem(int64_t d, int64_t L, bool has_xl, bool prefetch) {
+  return sizeof(float) * ((size_t)3 * L * d + (size_t)(prefetch ? 2 : 1) * (has_xl ? 3 : 2) * CROSS_WARPS * d +
+                          2 * CROSS_WARPS * CROSS_LMAX);     // sized for the larger layer bound
 }
 
 template <int VEC, int N>
@@ -269,8 +308,12 @@ template <int VEC, int N, int CPT>
 static int launch_cross_bwd(const float* x0, const float* xl_in, const float* w, const float* b, const float* g,
                             int64_t B, int64_t d, int64_t L, float* dx0, float* dxl, float* dw, float* db,
                             cudaStream_t st) {
-  auto k = cross_bwd_kernel<VEC, N, CPT>;
-  const size_t smem = cross_bwd_smem(d, L, xl_in != nullptr);
+  // double-buffered cp.async staging needs 16-byte rows (VEC == 4) and has to fit next to the parameter tables
+  const bool pf = VEC == 4 && cross_bwd_smem(d, L, xl_in != nullptr, true) <= 160 * 1024;
+  // LM = compile-time bound of the unrolled layer loops (predicated-off iterations still issue): 4 covers the reference's sweeps
+  auto k = L <= 4 ? (pf ? cross_bwd_kernel<VEC, N, CPT, VEC == 4, 4> : cross_bwd_kernel<VEC, N, CPT, false, 4>)
+                  : (pf ? cross_bwd_kernel<VEC, N, CPT, VEC == 4, 8> : cross_bwd_kernel<VEC, N, CPT, false, 8>);
+  const size_t smem = cross_bwd_smem(d, L, xl_in != nullptr, pf);
   if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, CROSS_WARPS * 32, smem);

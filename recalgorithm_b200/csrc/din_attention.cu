@@ -271,9 +271,11 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
   float* tile = sm + L.tile + wid * DIN_TT * L.tile_stride;
 
   // thread-owned weight-gradient accumulators (rank-k updates in phase B)
-  //   dW1 (4H x 64): thread owns column c1 = tid % 64 and rows r = (tid / 64) + (NT/64) * i
-  //   dW2 (64 x 32): thread owns column c2 = tid % 32 and rows c = (tid / 32) + (NT/32) * i
-  constexpr int R1 = (4 * HP * DIN_H1 + NT - 1) / NT;     // rows of dW1 per thread
+  //   dW1 (4H x 64): thread owns column c1 = tid % 64 and the R1 CONSECUTIVE rows starting at (tid / 64) * R1
+  //   dW2 (64 x 32): thread owns column c2 = tid % 32 and the R2 consecutive rows starting at (tid / 32) * R2
+  //   (consecutive rows -> the per-position row vectors are read with 128-bit shared loads)
+  constexpr int R1 = (4 * HP * DIN_H1) / NT;              // rows of dW1 per thread (= HP at 256 threads; multiple of 4)
+  static_assert(R1 % 4 == 0 && (4 * HP * DIN_H1) % NT == 0, "row blocks must be float4-sized");
   constexpr int R2 = (DIN_H1 * DIN_H2) / NT;               // rows of dW2 per thread
   float acc_w1[R1], acc_w2[R2], acc_b1 = 0.f, acc_b2 = 0.f, acc_w3 = 0.f, acc_b3 = 0.f;
 #pragma unroll
@@ -433,17 +435,24 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
         const float* dpre2 = tp + din_off_dpre2(H);
         {
           const float dv = dpre1[tid % DIN_H1];
+          const int r0 = (tid / DIN_H1) * R1;
 #pragma unroll
-          for (int i = 0; i < R1; ++i) {
-            const int r = tid / DIN_H1 + (NT / DIN_H1) * i;
-            if (r < H4) acc_w1[i] += cross[r] * dv;
+          for (int i4 = 0; i4 < R1; i4 += 4) {
+            if (r0 + i4 < H4) {                               // H4 is a multiple of 4: whole float4 in range
+              const float4 cv = *reinterpret_cast<const float4*>(cross + r0 + i4);
+              acc_w1[i4 + 0] += cv.x * dv; acc_w1[i4 + 1] += cv.y * dv; acc_w1[i4 + 2] += cv.z * dv; acc_w1[i4 + 3] += cv.w * dv;
+            }
           }
           if (tid < DIN_H1) acc_b1 += dpre1[tid];
         }
         {
           const float dv = dpre2[tid % DIN_H2];
+          const int c0 = (tid / DIN_H2) * R2;
 #pragma unroll
-          for (int i = 0; i < R2; ++i) acc_w2[i] += h1[tid / DIN_H2 + (NT / DIN_H2) * i] * dv;
+          for (int i4 = 0; i4 < R2; i4 += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(h1 + c0 + i4);
+            acc_w2[i4 + 0] += hv.x * dv; acc_w2[i4 + 1] += hv.y * dv; acc_w2[i4 + 2] += hv.z * dv; acc_w2[i4 + 3] += hv.w * dv;
+          }
           if (tid < DIN_H2) acc_b2 += dpre2[tid];
         }
         const float dsv = tp[din_off_ds(H)];
@@ -464,11 +473,11 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
   float* dB3 = dW3 + DIN_H2;
 #pragma unroll
   for (int i = 0; i < R1; ++i) {
-    const int r = tid / DIN_H1 + (NT / DIN_H1) * i;
+    const int r = (tid / DIN_H1) * R1 + i;
     if (r < H4) atomicAdd(dW1 + r * DIN_H1 + tid % DIN_H1, acc_w1[i]);
   }
 #pragma unroll
-  for (int i = 0; i < R2; ++i) atomicAdd(dW2 + (tid / DIN_H2 + (NT / DIN_H2) * i) * DIN_H2 + tid % DIN_H2, acc_w2[i]);
+  for (int i = 0; i < R2; ++i) atomicAdd(dW2 + ((tid / DIN_H2) * R2 + i) * DIN_H2 + tid % DIN_H2, acc_w2[i]);
   if (tid < DIN_H1) atomicAdd(dB1 + tid, acc_b1);
   if (tid < DIN_H2) { atomicAdd(dB2 + tid, acc_b2); atomicAdd(dW3 + tid, acc_w3); }
   if (tid == DIN_H2) atomicAdd(dB3, acc_b3);

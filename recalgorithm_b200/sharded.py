@@ -10,6 +10,7 @@ Sharding rule: global row ``gr = field_row_offset[f] + id`` lives on rank ``gr %
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -54,19 +55,52 @@ def receive_capacity(batch: int, fields: int, G: int, slack: float = 1.25) -> in
     return int((batch * fields / G) * slack) + 1024
 
 
-# ------------------------------------------------------------------ peer mapping
-def _share(t: torch.Tensor):
-    from torch.multiprocessing.reductions import reduce_tensor
-    return reduce_tensor(t)
+# ------------------------------------------------------------------ peer-mappable buffers (CUDA IPC through the C ABI)
+class _Raw:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
 
 
-def _open(handle) -> torch.Tensor:
-    fn, args = handle
-    return fn(*args)
+def _view(ptr: int, shape, dtype, device) -> torch.Tensor:
+    ts = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_Raw(ptr, shape, ts), device=device)
+
+
+class PeerBuffer:
+    """A cudaMalloc'ed buffer (ctr_peer_alloc) viewed as a torch tensor, with its 64-byte CUDA-IPC handle."""
+
+    def __init__(self, shape, dtype, device):
+        self.shape, self.dtype, self.device = tuple(shape), dtype, device
+        nbytes = max(1, int(torch.empty((), dtype=dtype).element_size())) * max(1, int(torch.Size(shape).numel()))
+        p = ctypes.c_void_p()
+        _lib.check(_lib.lib().ctr_peer_alloc(nbytes, ctypes.byref(p)))
+        self.ptr = int(p.value)
+        self.tensor = _view(self.ptr, shape, dtype, device)
+        h = ctypes.create_string_buffer(64)
+        _lib.check(_lib.lib().ctr_ipc_export(ctypes.c_void_p(self.ptr), h))
+        self.handle = bytes(h.raw)
+
+    def open_peer(self, handle: bytes) -> torch.Tensor:
+        q = ctypes.c_void_p()
+        _lib.check(_lib.lib().ctr_ipc_import(handle, ctypes.byref(q)))
+        return _view(int(q.value), self.shape, self.dtype, self.device)
 
 
 def _ptr_array(ptrs: List[int]):
     return (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+
+class SymmBuffer:
+    """Same role as PeerBuffer, backed by torch's symmetric memory (CUDA VMM allocations with 2 MB pages, handles passed
+    as file descriptors): measured necessary for the table shard -- a legacy-IPC mapping of a 32 GB shard collapsed to
+    7 GB/s under random 128-byte reads, while <= 5 GB shards reached 553 GB/s (peer TLB reach)."""
+
+    def __init__(self, shape, dtype, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.shape, self.dtype, self.device = tuple(shape), dtype, device
+        self.tensor = symm_mem.empty(*shape, dtype=dtype, device=device)
+        self._hdl = symm_mem.rendezvous(self.tensor, group)
+        self.peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
 
 
 class ShardedEmbeddingTables:
@@ -89,40 +123,48 @@ class ShardedEmbeddingTables:
         self.num_rows = int(off[-1])
         self.field_row_offset = off.to(self.device)
         self.local_rows = shard_rows(self.num_rows, self.G)
-        self.weight = torch.empty((self.local_rows, self.dim), dtype=torch.float32, device=self.device)
+        self._bufs = {}
+        self._symm_w = None
+        if os.environ.get("CTR_PEER_BACKEND", "symm") == "symm":
+            grp = group if group is not None else dist.group.WORLD
+            self._symm_w = SymmBuffer((self.local_rows, self.dim), torch.float32, self.device, grp)
+            self.weight = self._symm_w.tensor
+        else:
+            self._bufs["w"] = PeerBuffer((self.local_rows, self.dim), torch.float32, self.device)
+            self.weight = self._bufs["w"].tensor
         if init == "normal":
             g = torch.Generator(device=self.device).manual_seed(seed + self.rank)
             self.weight.normal_(0, self.dim ** -0.5, generator=g)
         self.capacity = receive_capacity(batch_per_rank, self.num_fields, self.G, slack)
-        self.recv_vals = torch.empty((self.G, self.capacity, self.dim), dtype=torch.float32, device=self.device)
-        self.recv_rows = torch.empty((self.G, self.capacity), dtype=torch.int64, device=self.device)
-        self.recv_counts = torch.zeros((self.G,), dtype=torch.int64, device=self.device)
+        self._bufs["v"] = PeerBuffer((self.G, self.capacity, self.dim), torch.float32, self.device)
+        self._bufs["r"] = PeerBuffer((self.G, self.capacity), torch.int64, self.device)
+        self._bufs["c"] = PeerBuffer((self.G,), torch.int64, self.device)
+        self.recv_vals, self.recv_rows, self.recv_counts = (self._bufs[k].tensor for k in ("v", "r", "c"))
+        self.recv_counts.zero_()
         self.counters = torch.zeros((self.G,), dtype=torch.int64, device=self.device)
         self.overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self._rendezvous()
 
     def _rendezvous(self):
-        """Exchange CUDA-IPC handles of the shard and the receive buffers; keep the peers' mappings alive."""
-        # kernels on this GPU dereference the peers' buffers directly: peer access must be enabled from THIS device
-        # (the IPC open below happens under the exporting device's guard and does not do it)
-        devs = [None] * self.G
-        self.dist.all_gather_object(devs, int(self.device.index), group=self.group)
-        for r, peer_dev in enumerate(devs):
-            if r != self.rank:
-                _lib.check(_lib.lib().ctr_enable_peer_access(int(peer_dev)))
-        mine = {"w": _share(self.weight), "v": _share(self.recv_vals), "r": _share(self.recv_rows), "c": _share(self.recv_counts)}
+        """Exchange the CUDA-IPC handles of the shard and the receive buffers and map every peer's buffers into this
+        device (the import enables NVLink peer access); the mappings live as long as the object."""
+        mine = {k: buf.handle for k, buf in self._bufs.items()}
         gathered = [None] * self.G
         self.dist.all_gather_object(gathered, mine, group=self.group)
         self._peer = []
         for r in range(self.G):
             if r == self.rank:
-                self._peer.append({"w": self.weight, "v": self.recv_vals, "r": self.recv_rows, "c": self.recv_counts})
+                self._peer.append({k: buf.tensor for k, buf in self._bufs.items()})
             else:
-                self._peer.append({k: _open(h) for k, h in gathered[r].items()})
-        self._w_ptrs = _ptr_array([p["w"].data_ptr() for p in self._peer])
+                self._peer.append({k: self._bufs[k].open_peer(gathered[r][k]) for k in self._bufs})
+        if self._symm_w is not None:
+            self._w_ptrs = _ptr_array(self._symm_w.peer_ptrs)
+        else:
+            self._w_ptrs = _ptr_array([p["w"].data_ptr() for p in self._peer])
         self._v_ptrs = _ptr_array([p["v"].data_ptr() for p in self._peer])
         self._r_ptrs = _ptr_array([p["r"].data_ptr() for p in self._peer])
         self._c_ptrs_dev = torch.tensor([p["c"].data_ptr() for p in self._peer], dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize()
         self.dist.barrier(group=self.group)
 
     # ---- forward: pull
