@@ -162,10 +162,11 @@ int ctr_din_attention_fwd(const float* query, const float* keys, const int64_t* 
                           const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* w3, const float* b3, int64_t B, int64_t T, int64_t H, int is_softmax,
                           float* out, float* att_w, void* stream);
-/* d_params: one flat fp32 buffer laid out [w1 | b1 | w2 | b2 | w3 | b3] (4H*64+64+64*32+32+32+1), overwritten. */
+/* d_params: one flat fp32 buffer laid out [w1 | b1 | w2 | b2 | w3 | b3] (4H*64+64+64*32+32+32+1), overwritten.
+ * att_w: the (B,T) weights saved by the forward, or NULL (they are then recomputed). */
 int ctr_din_attention_bwd(const float* query, const float* keys, const int64_t* keys_length,
                           const float* w1, const float* b1, const float* w2, const float* b2,
-                          const float* w3, const float* b3, const float* g_out,
+                          const float* w3, const float* b3, const float* g_out, const float* att_w,
                           int64_t B, int64_t T, int64_t H, int is_softmax,
                           float* d_query, float* d_keys, float* d_params, void* stream);
 

@@ -141,14 +141,15 @@ class _DinAttention(torch.autograd.Function):
     def forward(ctx, query, keys, keys_length, is_softmax, w1, b1, w2, b2, w3, b3):
         args = [t.contiguous() for t in (query, keys)] + [keys_length.contiguous()] + \
                [t.contiguous() for t in (w1, b1, w2, b2, w3, b3)]
-        ctx.save_for_backward(*args)
         ctx.is_softmax = bool(is_softmax)
-        return ops.din_attention_fwd(*args, is_softmax=ctx.is_softmax)
+        out, att = ops.din_attention_fwd(*args, is_softmax=ctx.is_softmax, want_weights=True)
+        ctx.save_for_backward(*args, att)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        args = ctx.saved_tensors
-        dq, dk, dws = ops.din_attention_bwd(*args, g.contiguous(), is_softmax=ctx.is_softmax)
+        *args, att = ctx.saved_tensors
+        dq, dk, dws = ops.din_attention_bwd(*args, g.contiguous(), is_softmax=ctx.is_softmax, att_w=att)
         return (dq, dk, None, None, *dws)
 
 

@@ -145,12 +145,18 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_sel + (uint32_t)(t * NP);
 #pragma unroll
-      for (int c0 = 0; c0 < NPT; c0 += 16) {
+      for (int c0 = 0; c0 < NPT; c0 += 32) {            // two 16-column loads in flight per wait
         if (c0 < NP) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
+          uint32_t v0[16], v1[16];
+          tmem_ld16_nowait(taddr + c0, v0);
+          if (c0 + 16 < NP) tmem_ld16_nowait(taddr + c0 + 16, v1);
+          tmem_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) acc[c0 + q] += v[q];
+          for (int q = 0; q < 16; ++q) acc[c0 + q] += __uint_as_float(v0[q]);
+          if (c0 + 16 < NP) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[c0 + 16 + q] += __uint_as_float(v1[q]);
+          }
         }
       }
       tc_fence_before();

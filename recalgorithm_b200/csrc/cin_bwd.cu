@@ -19,6 +19,8 @@
 //     B = g[b] as [H rows x D] K-major tiles (TMA 3-D box, swizzle width = D*4 bytes);
 //     each CTA owns 2 blocks of 128 (i,j) rows (8 consecutive i) and a slice of the batch; accumulation chains are cut every
 //     CHUNK samples and added into fp32 registers (round-to-nearest); one vector red.global.add per element at the end.
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 
 namespace ctr {
@@ -65,7 +67,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-template <int SB, int NKB>
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                               uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// MC: launched as 2-CTA clusters; the two CTAs work on different row tiles in lockstep and share every filter stage --
+// rank 0 TMA-multicasts the hi copy, rank 1 the lo copy, into BOTH CTAs' shared memory (halves the L2->SM traffic the
+// kernel is bound by); a stage is released when both CTAs' MMAs have consumed it (multicast commit, count 2).
+template <int SB, int NKB, bool MC>
 __global__ void __launch_bounds__(DX_THREADS, 1)
 cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ x0,
                      const float* __restrict__ xk, const float* __restrict__ g, float* __restrict__ dx0,
@@ -88,10 +115,12 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
   const int D = 1 << logD;
   const long long rows_total = (long long)B * D;
   const int num_tiles = (int)((rows_total + BM - 1) / BM);
+  const int tile_iters = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // identical for every CTA (lockstep in a cluster)
   const int nsteps = (hk + DX_IPS - 1) / DX_IPS;
+  const uint32_t cta_rank = MC ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), MC ? 2 : 1); }
     for (int q = 0; q < DX_DBUF; ++q) { mbar_init(d_full(q), 1); mbar_init(d_empty(q), 4); }
     mbar_init(a_full, 4);
     mbar_init(a_empty, 1);
@@ -100,6 +129,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
   if (warp == 5) tmem_alloc(smem_u32(tmem_ptr), 512u);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();                          // the peer's barriers are initialised before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t d_col0 = tmem_base + 256u;
@@ -109,9 +139,10 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     uint32_t di = 0;                                   // dZ buffer use counter (same sequence as the MMA warp)
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int ti = 0; ti < tile_iters; ++ti, ++lt) {
+      const int tile = blockIdx.x + ti * gridDim.x;          // may be past the end: an all-invalid tile keeps the pipeline in step
       const long long r = (long long)tile * BM + warp * 32 + lane;
-      const bool valid = r < rows_total;
+      const bool valid = tile < num_tiles && r < rows_total;
       const int b = valid ? (int)(r >> logD) : 0;
       const int d = (int)(r & (D - 1));
       float x0v[KB], dx0acc[KB];
@@ -148,27 +179,23 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
         const uint32_t q = di % DX_DBUF;
         mbar_wait(d_full(q), (di / DX_DBUF) & 1u);
         tc_fence_after();
-        float dz[DX_IPS][KB];
+        uint32_t raw[DX_IPS * 2][16];                   // all four 16-column loads in flight, one wait
 #pragma unroll
-        for (int t = 0; t < DX_IPS; ++t) {
-          float v0[16], v1[16];
-          tmem_ld16(d_col0 + lane_sel + q * DX_N + t * KB, v0);
-          tmem_ld16(d_col0 + lane_sel + q * DX_N + t * KB + 16, v1);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { dz[t][j] = v0[j]; dz[t][16 + j] = v1[j]; }
-        }
+        for (int t = 0; t < DX_IPS * 2; ++t) tmem_ld16_nowait(d_col0 + lane_sel + q * DX_N + t * 16, raw[t]);
+        tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d_empty(q));         // buffer may be overwritten by a later step
 #pragma unroll
         for (int t = 0; t < DX_IPS; ++t) {
-          float s = 0.f;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};            // four independent partial sums (ILP) for the dxk dot product
 #pragma unroll
           for (int j = 0; j < KB; ++j) {
-            s += dz[t][j] * x0v[j];                      // x0v[j >= m] == 0 masks the rows that belong to the next i
-            dx0acc[j] += dz[t][j] * xi[t];               // xi == 0 for i >= hk
+            const float dzv = __uint_as_float(raw[t * 2 + (j >> 4)][j & 15]);
+            s4[j & 3] += dzv * x0v[j];                   // x0v[j >= m] == 0 masks the rows that belong to the next i
+            dx0acc[j] += dzv * xi[t];                    // xi == 0 for i >= hk
           }
-          if (valid && i0 + t < hk) dxk[((size_t)b * hk + i0 + t) * D + d] = s;
+          if (valid && i0 + t < hk) dxk[((size_t)b * hk + i0 + t) * D + d] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         }
       }
       if (valid) {
@@ -181,13 +208,18 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
     // ============================ TMA: filter rows of i0 and i0+1 (hi and lo copies) ============================
     if (lane == 0) {
       int s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int ti = 0; ti < tile_iters; ++ti) {
         for (int st = 0; st < nsteps; ++st) {
           mbar_wait(empty_b(s), ph ^ 1);
           const uint32_t dst = sbase + s * stage_bytes;
           mbar_expect_tx(full_b(s), (uint32_t)stage_bytes);
-          tma_load_4d(dst, &tmap_w, 0, st * DX_IPS * m, 0, 0, full_b(s));
-          tma_load_4d(dst + b_copy_bytes, &tmap_w, 0, KRP + st * DX_IPS * m, 0, 0, full_b(s));
+          if (MC) {
+            if (cta_rank == 0) tma_load_4d_mc(dst, &tmap_w, 0, st * DX_IPS * m, 0, 0, full_b(s), (uint16_t)3);
+            else tma_load_4d_mc(dst + b_copy_bytes, &tmap_w, 0, KRP + st * DX_IPS * m, 0, 0, full_b(s), (uint16_t)3);
+          } else {
+            tma_load_4d(dst, &tmap_w, 0, st * DX_IPS * m, 0, 0, full_b(s));
+            tma_load_4d(dst + b_copy_bytes, &tmap_w, 0, KRP + st * DX_IPS * m, 0, 0, full_b(s));
+          }
           if (++s == SB) { s = 0; ph ^= 1; }
         }
       }
@@ -198,7 +230,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
       const uint32_t idesc = umma_idesc_tf32(DX_N);
       int s = 0, ph = 0, lt = 0;
       uint32_t di = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int ti = 0; ti < tile_iters; ++ti, ++lt) {
         mbar_wait(a_full, lt & 1);
         tc_fence_after();
         for (int st = 0; st < nsteps; ++st, ++di) {
@@ -227,7 +259,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_tf32_ts(dcol, a_hi + (uint32_t)(kb * KB + 8 * k), b_hi + (uint64_t)(kb * (DX_N * 128 / 16) + 2 * k), idesc, 1u);
-          umma_commit(empty_b(s));
+          if (MC) umma_commit_mc(empty_b(s), (uint16_t)3); else umma_commit(empty_b(s));
           umma_commit(d_full(q));
           if (++s == SB) { s = 0; ph ^= 1; }
         }
@@ -237,6 +269,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();                          // nobody leaves while the peer may still multicast into it
   if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
@@ -309,12 +342,18 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_sel + (uint32_t)(t * NP);
 #pragma unroll
-      for (int c0 = 0; c0 < NPT; c0 += 16) {
+      for (int c0 = 0; c0 < NPT; c0 += 32) {            // two 16-column loads in flight per wait
         if (c0 < NP) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
+          uint32_t v0[16], v1[16];
+          tmem_ld16_nowait(taddr + c0, v0);
+          if (c0 + 16 < NP) tmem_ld16_nowait(taddr + c0 + 16, v1);
+          tmem_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) acc[c0 + q] += v[q];
+          for (int q = 0; q < 16; ++q) acc[c0 + q] += __uint_as_float(v0[q]);
+          if (c0 + 16 < NP) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[c0 + 16 + q] += __uint_as_float(v1[q]);
+          }
         }
       }
       tc_fence_before();
@@ -323,31 +362,39 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __
     };
     int sa = 0, pha = 0;
     uint32_t gch = 0;
+    float4 pa[D / 4], pb[D / 4];                              // prefetched xk[b,i,:] and x0[b,j,:] (zeros for padding rows)
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q) { pa[q] = make_float4(0.f, 0.f, 0.f, 0.f); pb[q] = pa[q]; }
+    if (live && nsamp > 0) {
+      const float4* xkv = reinterpret_cast<const float4*>(xk + ((size_t)b_beg * hk + i) * D);
+      const float4* x0v = reinterpret_cast<const float4*>(x0 + ((size_t)b_beg * m + j) * D);
+#pragma unroll
+      for (int q = 0; q < D / 4; ++q) { pa[q] = __ldg(xkv + q); pb[q] = __ldg(x0v + q); }
+    }
     for (int c = 0; c < nch; ++c, ++gch) {
       const int s_beg = b_beg + c * chunk, s_end = min(b_end, s_beg + chunk);
       const int drain_at = min(SA, s_end - s_beg);
       for (int b = s_beg; b < s_end; ++b) {
-        const float4* xkv = reinterpret_cast<const float4*>(xk + ((size_t)b * hk + (live ? i : 0)) * D);
-        const float4* x0v = reinterpret_cast<const float4*>(x0 + ((size_t)b * m + (live ? j : 0)) * D);
+        // operands of this sample were requested one sample ago (pa/pb)
         mbar_wait(empty_a(sa), pha ^ 1);
         tc_fence_after();
         const uint32_t a_hi = a_stage0 + lane_sel + (uint32_t)((sa * DW_BLOCKS + t) * 2 * D);
 #pragma unroll
         for (int c8 = 0; c8 < D; c8 += 8) {
           float p[8], h[8];
-          if (live) {
-            const float4 a0 = __ldg(xkv + c8 / 4), a1 = __ldg(xkv + c8 / 4 + 1);
-            const float4 b0 = __ldg(x0v + c8 / 4), b1 = __ldg(x0v + c8 / 4 + 1);
-            p[0] = a0.x * b0.x; p[1] = a0.y * b0.y; p[2] = a0.z * b0.z; p[3] = a0.w * b0.w;
-            p[4] = a1.x * b1.x; p[5] = a1.y * b1.y; p[6] = a1.z * b1.z; p[7] = a1.w * b1.w;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) p[q] = 0.f;
-          }
+          const float4 a0 = pa[c8 / 4], a1 = pa[c8 / 4 + 1], b0 = pb[c8 / 4], b1 = pb[c8 / 4 + 1];
+          p[0] = a0.x * b0.x; p[1] = a0.y * b0.y; p[2] = a0.z * b0.z; p[3] = a0.w * b0.w;
+          p[4] = a1.x * b1.x; p[5] = a1.y * b1.y; p[6] = a1.z * b1.z; p[7] = a1.w * b1.w;
 #pragma unroll
           for (int q = 0; q < 8; ++q) { h[q] = tf32_rna(p[q]); p[q] -= h[q]; }
           tmem_st8(a_hi + c8, h);
           tmem_st8(a_hi + D + c8, p);
+        }
+        if (live && b + 1 < b_end) {                       // request the next sample's operands (a whole step ahead of use)
+          const float4* xkv = reinterpret_cast<const float4*>(xk + ((size_t)(b + 1) * hk + i) * D);
+          const float4* x0v = reinterpret_cast<const float4*>(x0 + ((size_t)(b + 1) * m + j) * D);
+#pragma unroll
+          for (int q = 0; q < D / 4; ++q) { pa[q] = __ldg(xkv + q); pb[q] = __ldg(x0v + q); }
         }
         tmem_wait_st();
         tc_fence_before();
@@ -494,9 +541,26 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
     const long long rows = (long long)B * D;
     const int tiles = (int)((rows + BM - 1) / BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
+    static const bool no_mc = getenv("CTR_CIN_NO_MULTICAST") != nullptr;
+    const bool mc = !no_mc && tiles >= 2;
+    int grid_mc = grid & ~1;                               // whole 2-CTA clusters
+    if (grid_mc < 2) grid_mc = 2;
 #define DX_LAUNCH(NKB_)                                                                                              \
-  {                                                                                                                  \
-    auto k = cin_bwd_dx_tc_kernel<SB, NKB_>;                                                                         \
+  if (mc) {                                                                                                          \
+    auto k = cin_bwd_dx_tc_kernel<SB, NKB_, true>;                                                                   \
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                            \
+    cudaLaunchConfig_t cfg = {};                                                                                     \
+    cfg.gridDim = dim3((unsigned)grid_mc);                                                                           \
+    cfg.blockDim = dim3(DX_THREADS);                                                                                 \
+    cfg.dynamicSmemBytes = (size_t)smem;                                                                             \
+    cfg.stream = st;                                                                                                 \
+    cudaLaunchAttribute at[1];                                                                                       \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                                  \
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                              \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                                \
+    CTR_CUDA(cudaLaunchKernelEx(&cfg, k, tmap, x0, xk, g_out, dx0, dxk, (int)B, (int)m, (int)hk, logD, (int)H, KRP)); \
+  } else {                                                                                                           \
+    auto k = cin_bwd_dx_tc_kernel<SB, NKB_, false>;                                                                  \
     CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                            \
     k<<<grid, DX_THREADS, smem, st>>>(tmap, x0, xk, g_out, dx0, dxk, (int)B, (int)m, (int)hk, logD, (int)H, KRP);    \
   }

@@ -237,250 +237,303 @@ din_attention_fwd_kernel(const float* __restrict__ query, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
-// backward
+// backward (second revision: every warp is independent -- no block-level phases)
 // ---------------------------------------------------------------------------------------------------
+// The first version staged per-position vectors for a CTA-cooperative rank-k update and needed two block syncs per
+// 32 positions at one CTA (8 warps, 255 registers) per SM: 0.92 ms at config 4, issue slots 25 % used.  The weight
+// gradient of layer 1 is restructured algebraically so that nothing per-position has to leave the warp:
+//     D_b  = sum_t dpre1[t]            (64)         KD_b = sum_t k[t] (x) dpre1[t]      (H x 64, same shape as Weff)
+//     dW1a = sum_b q_b (x) D_b         dW1b = sum_b KD_b       dW1c = dW1a - dW1b       dW1d = sum_b diag(q_b) KD_b
+//     dq_b = (W1a+W1c) D_b + rowsum(W1d * KD_b)            dk[t] = Weff_b dpre1[t]
+// so per position the warp only adds into 32 (KD) + 64 (dW2 column) + a few register accumulators; per SAMPLE it flushes
+// 3*H*64 values into shared-memory accumulators; per CTA one set of global atomics at the end.
 // d_params layout: [w1 (4H*64) | b1 (64) | w2 (64*32) | b2 (32) | w3 (32) | b3 (1)]
+struct DinBwdSmem {
+  int wq, wk, wd, b1, w2, b2, w3, aw1a, aw1b, aw1d, ab1, aw2, ab2, aw3, per_warp, warp_stride, total;
+  int o_sc, o_q, o_go, o_ds, o_dk, o_wt, o_h1, o_dp1, o_dp2;      // offsets inside a warp's region
+};
+
+__host__ __device__ inline DinBwdSmem din_bwd_layout(int H, int HP, int T, int warps) {
+  DinBwdSmem L;
+  int o = 0;
+  L.wq = o; o += H * DIN_H1;
+  L.wk = o; o += H * DIN_H1;
+  L.wd = o; o += H * DIN_H1;
+  L.b1 = o; o += DIN_H1;
+  L.w2 = o; o += DIN_H1 * DIN_H2;
+  L.b2 = o; o += DIN_H2;
+  L.w3 = o; o += DIN_H2 + 4;
+  L.aw1a = o; o += H * DIN_H1;
+  L.aw1b = o; o += H * DIN_H1;
+  L.aw1d = o; o += H * DIN_H1;
+  L.ab1 = o; o += DIN_H1;
+  L.aw2 = o; o += DIN_H1 * DIN_H2;
+  L.ab2 = o; o += DIN_H2;
+  L.aw3 = o; o += DIN_H2 + 4;                       // dw3 (32) + db3 (1)
+  L.per_warp = o;
+  int w = 0;
+  w += T * H;                                       // keys
+  L.o_sc = w; w += T;
+  L.o_q = w; w += H;
+  L.o_go = w; w += H;
+  L.o_ds = w; w += T;
+  L.o_dk = w; w += T * H;
+  w = (w + 3) & ~3;
+  L.o_wt = w; w += DIN_H1 * (HP + 1);               // Weff^T[c][h], padded rows
+  w = (w + 3) & ~3;
+  L.o_h1 = w; w += DIN_H1;
+  L.o_dp1 = w; w += DIN_H1;
+  L.o_dp2 = w; w += DIN_H2;
+  w = (w + 3) & ~3;
+  L.warp_stride = w;
+  L.total = o + warps * w;
+  return L;
+}
+
 template <int HP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 din_attention_bwd_kernel(const float* __restrict__ query, const float* __restrict__ keys,
                          const long long* __restrict__ keys_length, const float* __restrict__ w1,
                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                          const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ g_out,
-                         int B, int T, int H, int is_softmax, float* __restrict__ d_query,
-                         float* __restrict__ d_keys, float* __restrict__ d_params) {
+                         const float* __restrict__ att_w, int B, int T, int H, int is_softmax,
+                         float* __restrict__ d_query, float* __restrict__ d_keys, float* __restrict__ d_params) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int NT = WARPS * 32;
-  const DinSmem L = din_layout(H, T, WARPS, true);
-  din_stage_weights(sm, L, w1, b1, w2, b2, w3, b3, H, true);
-  __shared__ int s_npos[WARPS];                 // positions staged by each warp this round
-  __shared__ int s_more[2];                     // any warp still has work (double-buffered by round parity)
-  __syncthreads();
+  const DinBwdSmem L = din_bwd_layout(H, HP, T, WARPS);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
   const int H4 = 4 * H;
-  float w2col[DIN_H1];
-#pragma unroll
-  for (int c = 0; c < DIN_H1; ++c) w2col[c] = sm[L.w2 + c * DIN_H2 + lane];
+  // ---- stage weights (folded like the forward) and zero the CTA accumulators
+  for (int i = tid; i < H * DIN_H1; i += blockDim.x) {
+    const float a = __ldg(w1 + i), b = __ldg(w1 + H * DIN_H1 + i), c = __ldg(w1 + 2 * H * DIN_H1 + i),
+                d = __ldg(w1 + 3 * H * DIN_H1 + i);
+    sm[L.wq + i] = a + c;
+    sm[L.wk + i] = b - c;
+    sm[L.wd + i] = d;
+    sm[L.aw1a + i] = 0.f; sm[L.aw1b + i] = 0.f; sm[L.aw1d + i] = 0.f;
+  }
+  for (int i = tid; i < DIN_H1; i += blockDim.x) { sm[L.b1 + i] = __ldg(b1 + i); sm[L.ab1 + i] = 0.f; }
+  for (int i = tid; i < DIN_H1 * DIN_H2; i += blockDim.x) { sm[L.w2 + i] = __ldg(w2 + i); sm[L.aw2 + i] = 0.f; }
+  for (int i = tid; i < DIN_H2; i += blockDim.x) {
+    sm[L.b2 + i] = __ldg(b2 + i); sm[L.w3 + i] = __ldg(w3 + i); sm[L.ab2 + i] = 0.f; sm[L.aw3 + i] = 0.f;
+  }
+  if (tid == 0) { sm[L.w3 + DIN_H2] = __ldg(b3); sm[L.aw3 + DIN_H2] = 0.f; }
+  __syncthreads();
+
   float* wsm = sm + L.per_warp + wid * L.warp_stride;
   float* skeys = wsm;
-  float* sc = wsm + T * H;                      // attention weights w[t]
-  float* sq = sc + T;
-  float* sgo = sq + H;
-  float* sdq = sgo + H;
-  float* sdk = sdq + H;                         // (T,H) dkeys accumulator
-  float* sds = sdk + T * H;                     // (T) ds
-  float* tile = sm + L.tile + wid * DIN_TT * L.tile_stride;
+  float* sc = wsm + L.o_sc;
+  float* sq = wsm + L.o_q;
+  float* sgo = wsm + L.o_go;
+  float* sds = wsm + L.o_ds;
+  float* sdk = wsm + L.o_dk;
+  float* swt = wsm + L.o_wt;
+  float* sh1 = wsm + L.o_h1;
+  float* sdp1 = wsm + L.o_dp1;
+  float* sdp2 = wsm + L.o_dp2;
+  const float b2v = sm[L.b2 + lane], w3v = sm[L.w3 + lane], b3v = sm[L.w3 + DIN_H2];
+  const float* W2s = sm + L.w2;
 
-  // thread-owned weight-gradient accumulators (rank-k updates in phase B)
-  //   dW1 (4H x 64): thread owns column c1 = tid % 64 and the R1 CONSECUTIVE rows starting at (tid / 64) * R1
-  //   dW2 (64 x 32): thread owns column c2 = tid % 32 and the R2 consecutive rows starting at (tid / 32) * R2
-  //   (consecutive rows -> the per-position row vectors are read with 128-bit shared loads)
-  constexpr int R1 = (4 * HP * DIN_H1) / NT;              // rows of dW1 per thread (= HP at 256 threads; multiple of 4)
-  static_assert(R1 % 4 == 0 && (4 * HP * DIN_H1) % NT == 0, "row blocks must be float4-sized");
-  constexpr int R2 = (DIN_H1 * DIN_H2) / NT;               // rows of dW2 per thread
-  float acc_w1[R1], acc_w2[R2], acc_b1 = 0.f, acc_b2 = 0.f, acc_w3 = 0.f, acc_b3 = 0.f;
+  // register accumulators that live for the whole kernel
+  float acc_w2[DIN_H1];                         // column `lane` of dW2
 #pragma unroll
-  for (int i = 0; i < R1; ++i) acc_w1[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < R2; ++i) acc_w2[i] = 0.f;
+  for (int c = 0; c < DIN_H1; ++c) acc_w2[c] = 0.f;
+  float acc_b2 = 0.f, acc_w3 = 0.f, acc_b3 = 0.f;
 
-  int b = blockIdx.x * WARPS + wid;             // current sample of this warp
-  int t_next = 0, len = 0, round = 0;
-  bool loaded = false;
-  float weff[HP][2], qpart[2];
-
-  while (true) {
-    // ------------------------------------------------ phase A: each warp stages up to DIN_TT positions
-    int n = 0;
-    while (b < B && n == 0) {
-      if (!loaded) {
-        __syncwarp();
-        din_prepare<HP>(sm, L, wsm, query, keys, b, T, H, lane, weff, qpart);
-        for (int i = lane; i < H; i += 32) { sgo[i] = __ldg(g_out + (size_t)b * H + i); sdq[i] = 0.f; }
-        long long len64 = __ldg(keys_length + b);
-        len = (int)(len64 < 0 ? 0 : (len64 > T ? T : len64));
-        // recompute the forward scores -> attention weights (nothing but inputs is read from HBM)
-        for (int t0 = 0; t0 < len; t0 += DIN_TT) {
-          float h2[DIN_TT], score[DIN_TT];
-          const int nn = min(DIN_TT, len - t0);
-          din_mlp_tile<HP>(sm, L, skeys, tile, t0, nn, H, lane, weff, qpart, w2col, h2, score);
-          if (lane == 0) {
+  // layer-1 + layer-2 forward of one position from the folded per-sample weights; h1 goes to smem, returns h2 and score
+  auto mlp_fwd = [&](const float* k, const float (&weff)[HP][2], const float (&qpart)[2], float& h1a, float& h1b,
+                     float& h2, float& score) {
+    float p0 = qpart[0], p1 = qpart[1];
 #pragma unroll
-            for (int tt = 0; tt < DIN_TT; ++tt)
-              if (tt < nn) sc[t0 + tt] = score[tt];
-          }
-          __syncwarp();
-        }
-        din_weights(sc, T, len, H, is_softmax, lane);
-        // dw[t] = go . k[t];  dkeys[t,:] = w[t]*go;  ds from the mask / softmax backward
-        float dot = 0.f;
-        for (int t = lane; t < T; t += 32) {
-          float dwv = 0.f;
-          for (int h = 0; h < H; ++h) dwv += sgo[h] * skeys[t * H + h];
-          sds[t] = dwv;
-          dot += sc[t] * dwv;
-        }
-        dot = warp_sum(dot);
-        const float scale = sqrtf((float)H);
-        for (int t = lane; t < T; t += 32) {
-          const float dwv = sds[t];
-          float dsv;
-          if (is_softmax) dsv = t < len ? sc[t] * (dwv - dot) / scale : 0.f;
-          else dsv = t < len ? dwv : 0.f;
-          sds[t] = dsv;
-        }
-        for (int i = lane; i < T * H; i += 32) sdk[i] = sc[i / H] * sgo[i % H];
-        __syncwarp();
-        loaded = true;
-        t_next = 0;
-      }
-      if (t_next < len) {
-        n = min(DIN_TT, len - t_next);
-      } else {
-        // sample finished: flush its input gradients
-        for (int i = lane; i < T * H; i += 32) d_keys[(size_t)b * T * H + i] = sdk[i];
-        for (int i = lane; i < H; i += 32) d_query[(size_t)b * H + i] = sdq[i];
-        __syncwarp();
-        b += gridDim.x * WARPS;
-        loaded = false;
+    for (int h = 0; h < HP; ++h) {
+      if (h < H) {
+        const float kv = k[h];
+        p0 += kv * weff[h][0];
+        p1 += kv * weff[h][1];
       }
     }
-    if (n > 0) {
-      const int t0 = t_next;
-      float h2[DIN_TT], score[DIN_TT];
-      din_mlp_tile<HP>(sm, L, skeys, tile, t0, n, H, lane, weff, qpart, w2col, h2, score);
-      // stage cross, h2, dpre2, ds
+    h1a = fmaxf(p0, 0.f); h1b = fmaxf(p1, 0.f);
+    sh1[lane] = h1a; sh1[lane + 32] = h1b;
+    __syncwarp();
+    float acc = b2v;
+    const float4* h1v = reinterpret_cast<const float4*>(sh1);
 #pragma unroll
-      for (int tt = 0; tt < DIN_TT; ++tt) {
-        if (tt < n) {
-          float* tp = tile + tt * L.tile_stride;
-          float* cross = tp + din_off_cross();
-          const float* k = skeys + (t0 + tt) * H;
-          for (int h = lane; h < H; h += 32) {
-            const float qv = sq[h], kv = k[h];
-            cross[h] = qv; cross[H + h] = kv; cross[2 * H + h] = qv - kv; cross[3 * H + h] = qv * kv;
-          }
-          const float dsv = sds[t0 + tt];
-          tp[din_off_h2(H) + lane] = h2[tt];
-          tp[din_off_dpre2(H) + lane] = h2[tt] > 0.f ? dsv * sm[L.w3 + lane] : 0.f;
-          if (lane == 0) tp[din_off_ds(H)] = dsv;
+    for (int c4 = 0; c4 < DIN_H1 / 4; ++c4) {
+      const float4 v = h1v[c4];
+      acc += v.x * W2s[(4 * c4 + 0) * DIN_H2 + lane];
+      acc += v.y * W2s[(4 * c4 + 1) * DIN_H2 + lane];
+      acc += v.z * W2s[(4 * c4 + 2) * DIN_H2 + lane];
+      acc += v.w * W2s[(4 * c4 + 3) * DIN_H2 + lane];
+    }
+    h2 = fmaxf(acc, 0.f);
+    score = warp_sum(h2 * w3v) + b3v;
+  };
+
+  for (int b = blockIdx.x * WARPS + wid; b < B; b += gridDim.x * WARPS) {
+    // ---------------- per-sample preparation
+    __syncwarp();
+    for (int i = lane; i < T * H; i += 32) skeys[i] = __ldg(keys + (size_t)b * T * H + i);
+    for (int i = lane; i < H; i += 32) { sq[i] = __ldg(query + (size_t)b * H + i); sgo[i] = __ldg(g_out + (size_t)b * H + i); }
+    __syncwarp();
+    float weff[HP][2], kd[HP][2], qpart[2], dsum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = lane + 32 * u;
+      float acc = sm[L.b1 + c];
+#pragma unroll
+      for (int h = 0; h < HP; ++h) {
+        kd[h][u] = 0.f;
+        if (h < H) {
+          const float qh = sq[h];
+          acc += qh * sm[L.wq + h * DIN_H1 + c];
+          weff[h][u] = sm[L.wk + h * DIN_H1 + c] + qh * sm[L.wd + h * DIN_H1 + c];
+        } else {
+          weff[h][u] = 0.f;
+        }
+        swt[c * (HP + 1) + h] = weff[h][u];
+      }
+      qpart[u] = acc;
+    }
+    long long len64 = __ldg(keys_length + b);
+    const int len = (int)(len64 < 0 ? 0 : (len64 > T ? T : len64));
+    // ---------------- attention weights: saved by the forward, or recomputed
+    if (att_w != nullptr) {
+      for (int t = lane; t < T; t += 32) sc[t] = __ldg(att_w + (size_t)b * T + t);
+      __syncwarp();
+    } else {
+      for (int t = 0; t < len; ++t) {
+        float h1a, h1b, h2, score;
+        mlp_fwd(skeys + t * H, weff, qpart, h1a, h1b, h2, score);
+        if (lane == 0) sc[t] = score;
+        __syncwarp();
+      }
+      din_weights(sc, T, len, H, is_softmax, lane);
+    }
+    // dw[t] = go . k[t];  dkeys[t,:] = w[t]*go;  ds from the mask / softmax backward
+    float dot = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      float dwv = 0.f;
+      for (int h = 0; h < H; ++h) dwv += sgo[h] * skeys[t * H + h];
+      sds[t] = dwv;
+      dot += sc[t] * dwv;
+    }
+    dot = warp_sum(dot);
+    const float scale = sqrtf((float)H);
+    for (int t = lane; t < T; t += 32) {
+      const float dwv = sds[t];
+      sds[t] = t < len ? (is_softmax ? sc[t] * (dwv - dot) / scale : dwv) : 0.f;
+    }
+    for (int i = lane; i < T * H; i += 32) sdk[i] = sc[i / H] * sgo[i % H];
+    __syncwarp();
+    // ---------------- positions
+    for (int t = 0; t < len; ++t) {
+      const float* k = skeys + t * H;
+      float h1a, h1b, h2, score;
+      mlp_fwd(k, weff, qpart, h1a, h1b, h2, score);
+      const float dsv = sds[t];
+      const float dp2 = h2 > 0.f ? dsv * w3v : 0.f;
+      sdp2[lane] = dp2;
+      acc_w3 += h2 * dsv;
+      acc_b2 += dp2;
+      acc_b3 += dsv;
+      {
+        const float4* h1v = reinterpret_cast<const float4*>(sh1);
+#pragma unroll
+        for (int c4 = 0; c4 < DIN_H1 / 4; ++c4) {
+          const float4 v = h1v[c4];
+          acc_w2[4 * c4 + 0] += v.x * dp2; acc_w2[4 * c4 + 1] += v.y * dp2;
+          acc_w2[4 * c4 + 2] += v.z * dp2; acc_w2[4 * c4 + 3] += v.w * dp2;
         }
       }
       __syncwarp();
-      // dh1[c] = sum_c2 dpre2[c2] * W2[c][c2] for c = lane, lane+32 -> dpre1 = dh1 * (h1 > 0).
-      // W2 rows sit 128 B apart in smem; every lane walks the eight 16-byte chunks of its rows in a rotated order
-      // so that a quarter-warp always touches eight different chunks (conflict-free LDS.128).
+      // dh1[c] = sum_c2 dpre2[c2] * W2[c][c2] for c = lane, lane+32 (rotated 16-byte chunks: conflict-free)
+      float a0 = 0.f, a1 = 0.f;
+      {
+        const float4* dp2v = reinterpret_cast<const float4*>(sdp2);
+        const float4* r0 = reinterpret_cast<const float4*>(W2s + lane * DIN_H2);
+        const float4* r1 = reinterpret_cast<const float4*>(W2s + (lane + 32) * DIN_H2);
 #pragma unroll
-      for (int tt = 0; tt < DIN_TT; ++tt) {
-        if (tt < n) {
-          float* tp = tile + tt * L.tile_stride;
-          const float4* dp2 = reinterpret_cast<const float4*>(tp + din_off_dpre2(H));
-          const float4* r0 = reinterpret_cast<const float4*>(sm + L.w2 + lane * DIN_H2);
-          const float4* r1 = reinterpret_cast<const float4*>(sm + L.w2 + (lane + 32) * DIN_H2);
-          float a0 = 0.f, a1 = 0.f;
+        for (int c4 = 0; c4 < DIN_H2 / 4; ++c4) {
+          const int ch = (c4 + lane) & (DIN_H2 / 4 - 1);
+          const float4 dd = dp2v[ch], x0 = r0[ch], x1 = r1[ch];
+          a0 += dd.x * x0.x + dd.y * x0.y + dd.z * x0.z + dd.w * x0.w;
+          a1 += dd.x * x1.x + dd.y * x1.y + dd.z * x1.z + dd.w * x1.w;
+        }
+      }
+      const float d0 = h1a > 0.f ? a0 : 0.f, d1 = h1b > 0.f ? a1 : 0.f;
+      dsum[0] += d0; dsum[1] += d1;
+      sdp1[lane] = d0; sdp1[lane + 32] = d1;
 #pragma unroll
-          for (int c4 = 0; c4 < DIN_H2 / 4; ++c4) {
-            const int ch = (c4 + lane) & (DIN_H2 / 4 - 1);
-            const float4 dd = dp2[ch], x0 = r0[ch], x1 = r1[ch];
-            a0 += dd.x * x0.x + dd.y * x0.y + dd.z * x0.z + dd.w * x0.w;
-            a1 += dd.x * x1.x + dd.y * x1.y + dd.z * x1.z + dd.w * x1.w;
-          }
-          tp[din_off_dpre1(H) + lane] = tp[lane] > 0.f ? a0 : 0.f;
-          tp[din_off_dpre1(H) + lane + 32] = tp[lane + 32] > 0.f ? a1 : 0.f;
+      for (int h = 0; h < HP; ++h) {
+        if (h < H) {
+          const float kv = k[h];
+          kd[h][0] += kv * d0;
+          kd[h][1] += kv * d1;
         }
       }
       __syncwarp();
-      // dcross[r] = sum_c dpre1[c] * W1[r][c]  (W1^T[c][r] in smem: lanes read consecutive r)
-#pragma unroll
-      for (int tt = 0; tt < DIN_TT; ++tt) {
-        if (tt < n) {
-          float* tp = tile + tt * L.tile_stride;
-          const float* dpre1 = tp + din_off_dpre1(H);
-          for (int r = lane; r < H4; r += 32) {
-            float a = 0.f;
+      // dk[t][h] += sum_c Weff[h][c] * dpre1[c] : lane = (group, h); every group covers 64/ngroups columns
+      {
+        constexpr int NG = 32 / HP;                 // groups of HP lanes
+        constexpr int CPG = DIN_H1 / NG;            // columns per group
+        const int hh = lane % HP, grp = lane / HP;
+        float sdk_part = 0.f;
 #pragma unroll 8
-            for (int c = 0; c < DIN_H1; ++c) a += dpre1[c] * sm[L.w1t + c * H4 + r];
-            tp[din_off_dcross(H) + r] = a;
-          }
+        for (int cc = 0; cc < CPG; ++cc) {
+          const int c = grp * CPG + cc;
+          sdk_part += sdp1[c] * swt[c * (HP + 1) + hh];
         }
+#pragma unroll
+        for (int o = HP; o < 32; o <<= 1) sdk_part += __shfl_xor_sync(0xffffffffu, sdk_part, o);
+        if (grp == 0 && hh < H) sdk[t * H + hh] += sdk_part;
       }
       __syncwarp();
-#pragma unroll
-      for (int tt = 0; tt < DIN_TT; ++tt) {
-        if (tt < n) {
-          const float* dcross = tile + tt * L.tile_stride + din_off_dcross(H);
-          const float* k = skeys + (t0 + tt) * H;
-          for (int h = lane; h < H; h += 32) {
-            const float da = dcross[h], db_ = dcross[H + h], dc = dcross[2 * H + h], dd = dcross[3 * H + h];
-            sdq[h] += da + dc + dd * k[h];
-            sdk[(t0 + tt) * H + h] += db_ - dc + dd * sq[h];
-          }
-        }
-      }
-      t_next += n;
     }
-    const int par = round & 1;
-    if (lane == 0) s_npos[wid] = n;
-    if (tid == 0) s_more[par] = 0;
-    __syncthreads();
-    if (lane == 0 && (n > 0 || b < B)) s_more[par] = 1;      // every writer stores the same value
-    // ------------------------------------------------ phase B: cooperative rank-k update of the weight grads
-    for (int wv = 0; wv < WARPS; ++wv) {
-      const int np = s_npos[wv];
-      for (int tt = 0; tt < np; ++tt) {
-        const float* tp = sm + L.tile + (wv * DIN_TT + tt) * L.tile_stride;
-        const float* h1 = tp;
-        const float* cross = tp + din_off_cross();
-        const float* dpre1 = tp + din_off_dpre1(H);
-        const float* sh2 = tp + din_off_h2(H);
-        const float* dpre2 = tp + din_off_dpre2(H);
-        {
-          const float dv = dpre1[tid % DIN_H1];
-          const int r0 = (tid / DIN_H1) * R1;
+    // ---------------- sample epilogue: d_query, d_keys, flush the layer-1 weight-gradient pieces
+    const int c0 = lane, c1 = lane + 32;
 #pragma unroll
-          for (int i4 = 0; i4 < R1; i4 += 4) {
-            if (r0 + i4 < H4) {                               // H4 is a multiple of 4: whole float4 in range
-              const float4 cv = *reinterpret_cast<const float4*>(cross + r0 + i4);
-              acc_w1[i4 + 0] += cv.x * dv; acc_w1[i4 + 1] += cv.y * dv; acc_w1[i4 + 2] += cv.z * dv; acc_w1[i4 + 3] += cv.w * dv;
-            }
-          }
-          if (tid < DIN_H1) acc_b1 += dpre1[tid];
-        }
-        {
-          const float dv = dpre2[tid % DIN_H2];
-          const int c0 = (tid / DIN_H2) * R2;
-#pragma unroll
-          for (int i4 = 0; i4 < R2; i4 += 4) {
-            const float4 hv = *reinterpret_cast<const float4*>(h1 + c0 + i4);
-            acc_w2[i4 + 0] += hv.x * dv; acc_w2[i4 + 1] += hv.y * dv; acc_w2[i4 + 2] += hv.z * dv; acc_w2[i4 + 3] += hv.w * dv;
-          }
-          if (tid < DIN_H2) acc_b2 += dpre2[tid];
-        }
-        const float dsv = tp[din_off_ds(H)];
-        if (tid < DIN_H2) acc_w3 += sh2[tid] * dsv;
-        else if (tid == DIN_H2) acc_b3 += dsv;
+    for (int h = 0; h < HP; ++h) {
+      if (h < H) {
+        float v = sm[L.wq + h * DIN_H1 + c0] * dsum[0] + sm[L.wq + h * DIN_H1 + c1] * dsum[1] +
+                  sm[L.wd + h * DIN_H1 + c0] * kd[h][0] + sm[L.wd + h * DIN_H1 + c1] * kd[h][1];
+        v = warp_sum(v);
+        if (lane == 0) d_query[(size_t)b * H + h] = v;
+        const float qh = sq[h];
+        atomicAdd(sm + L.aw1b + h * DIN_H1 + c0, kd[h][0]);
+        atomicAdd(sm + L.aw1b + h * DIN_H1 + c1, kd[h][1]);
+        atomicAdd(sm + L.aw1d + h * DIN_H1 + c0, qh * kd[h][0]);
+        atomicAdd(sm + L.aw1d + h * DIN_H1 + c1, qh * kd[h][1]);
+        atomicAdd(sm + L.aw1a + h * DIN_H1 + c0, qh * dsum[0]);
+        atomicAdd(sm + L.aw1a + h * DIN_H1 + c1, qh * dsum[1]);
       }
     }
-    __syncthreads();
-    if (!s_more[par]) break;
-    ++round;
+    atomicAdd(sm + L.ab1 + c0, dsum[0]);
+    atomicAdd(sm + L.ab1 + c1, dsum[1]);
+    for (int i = lane; i < T * H; i += 32) d_keys[(size_t)b * T * H + i] = sdk[i];
   }
-  // merge this CTA's partial weight gradients
+  // ---------------- merge: warp registers -> CTA shared accumulators -> global
+#pragma unroll
+  for (int c = 0; c < DIN_H1; ++c) atomicAdd(sm + L.aw2 + c * DIN_H2 + lane, acc_w2[c]);
+  atomicAdd(sm + L.ab2 + lane, acc_b2);
+  atomicAdd(sm + L.aw3 + lane, acc_w3);
+  if (lane == 0) atomicAdd(sm + L.aw3 + DIN_H2, acc_b3);
+  __syncthreads();
   float* dW1 = d_params;
   float* dB1 = dW1 + H4 * DIN_H1;
   float* dW2 = dB1 + DIN_H1;
   float* dB2 = dW2 + DIN_H1 * DIN_H2;
   float* dW3 = dB2 + DIN_H2;
   float* dB3 = dW3 + DIN_H2;
-#pragma unroll
-  for (int i = 0; i < R1; ++i) {
-    const int r = (tid / DIN_H1) * R1 + i;
-    if (r < H4) atomicAdd(dW1 + r * DIN_H1 + tid % DIN_H1, acc_w1[i]);
+  for (int i = tid; i < H * DIN_H1; i += blockDim.x) {
+    const float a = sm[L.aw1a + i], bb = sm[L.aw1b + i], d = sm[L.aw1d + i];
+    atomicAdd(dW1 + i, a);
+    atomicAdd(dW1 + H * DIN_H1 + i, bb);
+    atomicAdd(dW1 + 2 * H * DIN_H1 + i, a - bb);
+    atomicAdd(dW1 + 3 * H * DIN_H1 + i, d);
   }
-#pragma unroll
-  for (int i = 0; i < R2; ++i) atomicAdd(dW2 + ((tid / DIN_H2) * R2 + i) * DIN_H2 + tid % DIN_H2, acc_w2[i]);
-  if (tid < DIN_H1) atomicAdd(dB1 + tid, acc_b1);
-  if (tid < DIN_H2) { atomicAdd(dB2 + tid, acc_b2); atomicAdd(dW3 + tid, acc_w3); }
-  if (tid == DIN_H2) atomicAdd(dB3, acc_b3);
+  for (int i = tid; i < DIN_H1; i += blockDim.x) atomicAdd(dB1 + i, sm[L.ab1 + i]);
+  for (int i = tid; i < DIN_H1 * DIN_H2; i += blockDim.x) atomicAdd(dW2 + i, sm[L.aw2 + i]);
+  for (int i = tid; i < DIN_H2; i += blockDim.x) { atomicAdd(dB2 + i, sm[L.ab2 + i]); atomicAdd(dW3 + i, sm[L.aw3 + i]); }
+  if (tid == 0) atomicAdd(dB3, sm[L.aw3 + DIN_H2]);
 }
 
 }  // namespace ctr
@@ -539,8 +592,9 @@ extern "C" int ctr_din_attention_fwd(const float* query, const float* keys, cons
 
 extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, const int64_t* keys_length, const float* w1,
                                      const float* b1, const float* w2, const float* b2, const float* w3,
-                                     const float* b3, const float* g_out, int64_t B, int64_t T, int64_t H,
-                                     int is_softmax, float* d_query, float* d_keys, float* d_params, void* stream) {
+                                     const float* b3, const float* g_out, const float* att_w, int64_t B, int64_t T,
+                                     int64_t H, int is_softmax, float* d_query, float* d_keys, float* d_params,
+                                     void* stream) {
   int rc = check_din("ctr_din_attention_bwd", B, T, H);
   if (rc) return rc;
   CTR_REQUIRE(query && keys_length && w1 && b1 && w2 && b2 && w3 && b3 && g_out && d_query && d_params &&
@@ -554,7 +608,8 @@ extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, cons
     return CTR_OK;
   }
   constexpr int WARPS = 8;
-  const DinSmem L = din_layout((int)H, (int)T, WARPS, true);
+  const int HPv = H <= 4 ? 4 : H <= 8 ? 8 : H <= 16 ? 16 : 32;
+  const DinBwdSmem L = din_bwd_layout((int)H, HPv, (int)T, WARPS);
   const size_t smem = sizeof(float) * (size_t)L.total;
   CTR_UNSUPPORTED(smem > 220 * 1024, "ctr_din_attention_bwd: T=%lld H=%lld needs %zu B of shared memory", (long long)T,
                   (long long)H, smem);
@@ -568,8 +623,8 @@ extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, cons
     long long grid = (long long)(per_sm < 1 ? 1 : per_sm) * sm_count();                                           \
     if (grid > need) grid = need;                                                                                 \
     k<<<(int)grid, WARPS * 32, smem, st>>>(query, keys, reinterpret_cast<const long long*>(keys_length), w1, b1,  \
-                                           w2, b2, w3, b3, g_out, (int)B, (int)T, (int)H, is_softmax, d_query,    \
-                                           d_keys, d_params);                                                     \
+                                           w2, b2, w3, b3, g_out, att_w, (int)B, (int)T, (int)H, is_softmax,      \
+                                           d_query, d_keys, d_params);                                            \
   }
   if (H <= 4) GO(4) else if (H <= 8) GO(8) else if (H <= 16) GO(16) else GO(32)
 #undef GO

@@ -30,7 +30,9 @@ struct PeerTables {
   int G, logG;
 };
 
-template <int LPR, bool SH, int MINB>
+// NCH > 0: F <= 32*NCH; the lane's row-offset window is cached and the ids of the NEXT sample are requested before the
+// current sample's rows (one DRAM latency taken off the per-sample critical path).  NCH == 0: any F, ids loaded per chunk.
+template <int LPR, bool SH, int MINB, int NCH>
 __global__ void __launch_bounds__(256, MINB)
 embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, const long long* __restrict__ row_off,
                      const long long* __restrict__ ids, int B, int F, float4* __restrict__ tile,
@@ -44,12 +46,40 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, c
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
 
+  constexpr int NC = NCH > 0 ? NCH : 1;
+  long long lo_c[NC], n_c[NC], id_next[NC];
+  if (NCH > 0) {
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) {
+      const int f = ch * 32 + lane;
+      lo_c[ch] = 0; n_c[ch] = 0; id_next[ch] = -1;
+      if (f < F) {
+        lo_c[ch] = __ldg(row_off + f);
+        n_c[ch] = __ldg(row_off + f + 1) - lo_c[ch];
+        if (warp0 < B) id_next[ch] = ldg_stream_i64(ids + (size_t)warp0 * F + f);
+      }
+    }
+  }
   for (int b = warp0; b < B; b += nwarps) {
     float4 S = f4_zero(), Q = f4_zero();
+    long long row_c[NC];
+    if (NCH > 0) {
+#pragma unroll
+      for (int ch = 0; ch < NC; ++ch) {
+        const long long id = id_next[ch];
+        row_c[ch] = (id >= 0 && id < n_c[ch]) ? lo_c[ch] + id : -1;      // OOV(-1)/out-of-range -> zero vector
+        const int f = ch * 32 + lane;
+        if (f < F && b + nwarps < B) id_next[ch] = ldg_stream_i64(ids + (size_t)(b + nwarps) * F + f);
+      }
+    }
     for (int f0 = 0; f0 < F; f0 += 32) {
       const int nf = min(32, F - f0);
       long long row = -1;
-      if (lane < nf) {
+      if (NCH > 0) {
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch)
+          if (f0 == ch * 32) row = row_c[ch];
+      } else if (lane < nf) {
         const long long id = ldg_stream_i64(ids + (size_t)b * F + f0 + lane);
         const long long lo = __ldg(row_off + f0 + lane), hi = __ldg(row_off + f0 + lane + 1);
         row = (id >= 0 && id < hi - lo) ? lo + id : -1;      // OOV(-1)/out-of-range -> zero vector
@@ -292,22 +322,26 @@ static int launch_fwd(const float* table, const PeerTables* peers, const int64_t
   PeerTables none = {};
   // 4 CTAs/SM (64 registers) measured 0.80 of HBM peak vs 0.71-0.80 uncapped; CTR_EMBED_OCC1 keeps the A/B switch
   static const bool occ4 = getenv("CTR_EMBED_OCC1") == nullptr;
-  if (peers == nullptr && occ4) {
-    auto k = embed_fm2_fwd_kernel<LPR, false, 4>;
-    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
-    k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), none, reinterpret_cast<const long long*>(off),
-                            reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), fm2);
-  } else if (peers == nullptr) {
-    auto k = embed_fm2_fwd_kernel<LPR, false, 1>;
-    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
-    k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), none, reinterpret_cast<const long long*>(off),
-                            reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), fm2);
-  } else {
-    auto k = embed_fm2_fwd_kernel<LPR, true, 1>;
-    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
-    k<<<grid, 256, 0, st>>>(nullptr, *peers, reinterpret_cast<const long long*>(off),
-                            reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), fm2);
+  // next-sample id prefetch measured neutral-to-negative at 4 CTAs/SM (0.795 vs 0.805: it costs spills): opt-in only
+  static const bool noprefetch = getenv("CTR_EMBED_PREFETCH") == nullptr;
+  const PeerTables& pt = peers ? *peers : none;
+  const float4* tb = reinterpret_cast<const float4*>(table);
+#define EMB_LAUNCH(SH_, MINB_, NCH_)                                                                                 \
+  {                                                                                                                  \
+    auto k = embed_fm2_fwd_kernel<LPR, SH_, MINB_, NCH_>;                                                            \
+    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);                                                          \
+    k<<<grid, 256, 0, st>>>(tb, pt, reinterpret_cast<const long long*>(off), reinterpret_cast<const long long*>(ids), \
+                            (int)B, (int)F, reinterpret_cast<float4*>(tile), fm2);                                   \
   }
+  const int nch = noprefetch ? 0 : (F <= 32 ? 1 : F <= 64 ? 2 : 0);
+  if (peers != nullptr) {
+    if (nch == 1) EMB_LAUNCH(true, 1, 1) else if (nch == 2) EMB_LAUNCH(true, 1, 2) else EMB_LAUNCH(true, 1, 0)
+  } else if (occ4) {
+    if (nch == 1) EMB_LAUNCH(false, 4, 1) else if (nch == 2) EMB_LAUNCH(false, 4, 2) else EMB_LAUNCH(false, 4, 0)
+  } else {
+    if (nch == 1) EMB_LAUNCH(false, 1, 1) else if (nch == 2) EMB_LAUNCH(false, 1, 2) else EMB_LAUNCH(false, 1, 0)
+  }
+#undef EMB_LAUNCH
   CTR_CHECK_LAUNCH("ctr_embed_fm2_fwd");
   return CTR_OK;
 }

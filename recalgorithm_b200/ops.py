@@ -172,11 +172,11 @@ def din_attention_fwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, is_softm
     return (out, att) if want_weights else out
 
 
-def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, is_softmax=False):
-    """Returns (d_query, d_keys, [dw1, db1, dw2, db2, dw3, db3])."""
+def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, is_softmax=False, att_w=None):
+    """Returns (d_query, d_keys, [dw1, db1, dw2, db2, dw3, db3]).  att_w: the forward's (B,T) weights (else recomputed)."""
     B, T, H = keys.shape
     _chk(query, F32, "query", (B, H)); _chk(keys, F32, "keys"); _chk(keys_length, I64, "keys_length", (B,))
-    _chk(g_out, F32, "g_out", (B, H))
+    _chk(g_out, F32, "g_out", (B, H)); _chk(att_w, F32, "att_w", (B, T))
     w3_shape, b3_shape = w3.shape, b3.shape
     w1, b1, w2, b2, w3, b3 = _din_params(H, w1, b1, w2, b2, w3, b3)
     dq = torch.empty_like(query)
@@ -184,7 +184,7 @@ def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, i
     sizes = [4 * H * 64, 64, 64 * 32, 32, 32, 1]
     flat = torch.empty((sum(sizes),), dtype=F32, device=query.device)
     _lib.check(_lib.lib().ctr_din_attention_bwd(_ptr(query), _ptr(keys) if T > 0 else None, _ptr(keys_length), _ptr(w1),
-                                                _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), _ptr(g_out), B, T, H,
+                                                _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), _ptr(g_out), _ptr(att_w), B, T, H,
                                                 int(bool(is_softmax)), _ptr(dq), _ptr(dk) if T > 0 else None, _ptr(flat),
                                                 _stream()))
     parts = list(torch.split(flat, sizes))
