@@ -222,7 +222,10 @@ bilinear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   for (int e = threadIdx.x; e < ndw; e += blockDim.x) atomicAdd(dw + e, dwacc[e]);
 }
 
-// 'interaction' backward, data gradient: one CTA per sample.  smem: xs (F*K) | pairs (P)
+// 'interaction' backward, data gradient: one CTA per sample.  smem: xs (F*K) | dxs (F*K) | dvw (P*K)
+//   phase 1, thread (p,k): vw_p[k] = x_i . W_p[:,k];  dx_j[k] += g*vw;  dvw_p[k] = g*x_j[k]   (kept in smem)
+//   phase 2, thread (p,c): dx_i[c] += dvw_p . W_p[c,:]
+// (P*K shared atomics per phase instead of P*K*K in the first version.)
 __global__ void __launch_bounds__(BIL_THREADS)
 bilinear_bwd_interaction_dx_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ g, int B, int F, int K, float* __restrict__ dx) {
@@ -231,24 +234,34 @@ bilinear_bwd_interaction_dx_kernel(const float* __restrict__ x, const float* __r
   const int P = n * (n - 1) / 2;
   float* xs = smem;
   float* dxs = xs + F * K;
+  float* dvw = dxs + F * K;
+  int* pairs = reinterpret_cast<int*>(dvw + P * K);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int j = i + 1; j < n; ++j) pairs[pair_base(i, n) + (j - i - 1)] = (i << 16) | j;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     for (int i = threadIdx.x; i < F * K; i += blockDim.x) { xs[i] = __ldg(x + (size_t)b * F * K + i); dxs[i] = 0.f; }
     __syncthreads();
     const float* gb = g + (size_t)b * P * K;
-    // thread per (p, k): contributes to dx_j[k] (vw_p[k]*g) and to dx_i[c] for all c (g*x_j[k]*W_p[c][k])
-    for (int i = 0; i < n; ++i) {
-      for (int t = threadIdx.x; t < (n - i - 1) * K; t += blockDim.x) {
-        const int j = i + 1 + t / K, k = t % K;
-        const int p = pair_base(i, n) + (j - i - 1);
-        const float* wp = w + (size_t)p * K * K;
-        const float gv = __ldg(gb + (size_t)p * K + k);
-        float vwk = 0.f;
-        for (int c = 0; c < K; ++c) vwk += xs[i * K + c] * __ldg(wp + c * K + k);
-        atomicAdd(dxs + j * K + k, gv * vwk);
-        const float dv = gv * xs[j * K + k];                   // dvw_p[k]
-        for (int c = 0; c < K; ++c) atomicAdd(dxs + i * K + c, dv * __ldg(wp + c * K + k));
-      }
+    for (int t = threadIdx.x; t < P * K; t += blockDim.x) {
+      const int p = t / K, k = t % K;
+      const int ij = pairs[p];
+      const int i = ij >> 16, j = ij & 0xffff;
+      const float* wp = w + (size_t)p * K * K;
+      float vwk = 0.f;
+      for (int c = 0; c < K; ++c) vwk += xs[i * K + c] * __ldg(wp + c * K + k);
+      const float gv = __ldg(gb + t);
+      atomicAdd(dxs + j * K + k, gv * vwk);
+      dvw[t] = gv * xs[j * K + k];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < P * K; t += blockDim.x) {
+      const int p = t / K, c = t % K;
+      const float* wr = w + (size_t)p * K * K + (size_t)c * K;
+      const float* dv = dvw + p * K;
+      float sacc = 0.f;
+      for (int k = 0; k < K; ++k) sacc += dv[k] * __ldg(wr + k);
+      atomicAdd(dxs + (pairs[p] >> 16) * K + c, sacc);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < F * K; i += blockDim.x) dx[(size_t)b * F * K + i] = dxs[i];
@@ -375,7 +388,9 @@ extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_o
     return CTR_OK;
   }
   if (type == 2) {
-    const size_t smem = sizeof(float) * 2 * F * K;
+    const size_t smem = sizeof(float) * (2 * F * K + P * K) + sizeof(int) * P;
+    CTR_UNSUPPORTED(smem > 200 * 1024, "ctr_bilinear_bwd: F=%lld K=%lld needs %zu B of shared memory", (long long)F,
+                    (long long)K, smem);
     auto k = bilinear_bwd_interaction_dx_kernel;
     if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid_for(B, 8), BIL_THREADS, smem, st>>>(x, w, g_out, (int)B, (int)F, (int)K, dx);

@@ -129,5 +129,87 @@ def main():
             emit(f"bilinear_bwd_{typ}", {"B": B, "F": F, "K": K}, m, bst, bytes_=B * (2 * F * K + P * K) * 4)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--configs" not in sys.argv:
     main()
+
+
+def config_level():
+    """BASELINE configs 2-4 as lookup + interaction chains (hot path only: no dense tail), forward+backward, samples/s.
+    Timed as one CUDA-event region per step, L2 flushed between steps; tables 1 M rows per field."""
+    import statistics
+    torch.cuda.set_device(0)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    flush = torch.empty(64 * 1024 * 1024, device="cuda")
+    rn = lambda *s, std=1.0: torch.randn(s, device="cuda", generator=gen) * std
+
+    def run(name, cfg, B, step, iters=15):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = statistics.median(ts)
+        print(json.dumps({"config_level": name, "config": cfg, "ms_per_step": ms, "samples_per_sec": B / (ms * 1e-3),
+                          "what": "lookup fwd + interaction fwd + interaction bwd + lookup bwd (IndexedSlices); no dense tail",
+                          "l2": "flushed between steps"}), flush=True)
+
+    rows = 1_000_000
+    # ---- config 2: DCN, 30 fields x 16, L = 3, B = 4096
+    B, F, D, L = 4096, 30, 16, 3
+    table = rn(rows * F, D, std=D ** -0.5); off = torch.arange(F + 1, device="cuda") * rows
+    ids = torch.randint(0, rows, (B, F), device="cuda", generator=gen)
+    w, bb = rn(L, F * D, std=0.05), rn(L, F * D, std=0.05); g = rn(B, F * D)
+
+    def dcn():
+        tile, _ = ops.embed_fm2_fwd(table, off, ids, want_fm2=False)
+        x0 = tile.view(B, F * D)
+        ops.cross_fwd(x0, w, bb)
+        dx0, _, _, _ = ops.cross_bwd(x0, w, bb, g)
+        ops.embed_fm2_bwd(tile, dx0.view(B, F, D), None)
+    run("dcn_cfg2", {"B": B, "F": F, "D": D, "L": L, "rows_per_field": rows}, B, dcn)
+
+    # ---- config 3: xDeepFM CIN [128,128], 30 fields x 16, B = 8192
+    B, F, D, H = 8192, 30, 16, 128
+    ids3 = torch.randint(0, rows, (B, F), device="cuda", generator=gen)
+    w1, w2 = rn(F * F, H, std=0.05), rn(H * F, H, std=0.05)
+    gp = rn(B, 2 * H)
+
+    def xdeepfm():
+        x0, _ = ops.embed_fm2_fwd(table, off, ids3, want_fm2=False)
+        x1, p1 = ops.cin_fwd(x0, x0, w1, want_pooled=True)
+        x2, p2 = ops.cin_fwd(x0, x1, w2, want_pooled=True)
+        g2 = gp[:, H:].unsqueeze(-1).expand(B, H, D).contiguous()          # d(pooled)/d(out) broadcast over D
+        dx0b, dx1, _ = ops.cin_bwd(x0, x1, w2, g2)
+        g1 = dx1 + gp[:, :H].unsqueeze(-1)
+        dx0a, dxk, _ = ops.cin_bwd(x0, x0, w1, g1.contiguous())
+        ops.embed_fm2_bwd(x0, (dx0a + dxk + dx0b).contiguous(), None)
+    run("xdeepfm_cfg3", {"B": B, "m": F, "D": D, "cin": [H, H], "rows_per_field": rows}, B, xdeepfm)
+
+    # ---- config 4: DIN attention, history T = 50 (one lookup per step), H = 16, B = 4096
+    B, T, Hd = 4096, 50, 16
+    tab4 = rn(rows, Hd, std=0.25); off4 = torch.tensor([0, rows], device="cuda")
+    lens = torch.randint(0, T + 1, (B,), device="cuda", generator=gen)
+    hist = torch.randint(0, rows, (B * T, 1), device="cuda", generator=gen)
+    hist[(torch.arange(T, device="cuda")[None, :] >= lens[:, None]).reshape(-1)] = -1     # padding -> zero vectors
+    tgt = torch.randint(0, rows, (B, 1), device="cuda", generator=gen)
+    ws = [rn(4 * Hd, 64, std=0.2), rn(64, std=0.1), rn(64, 32, std=0.2), rn(32, std=0.1), rn(32, 1, std=0.3), rn(1, std=0.1)]
+    go = rn(B, Hd)
+
+    def din():
+        keys, _ = ops.embed_fm2_fwd(tab4, off4, hist, want_fm2=False)
+        q, _ = ops.embed_fm2_fwd(tab4, off4, tgt, want_fm2=False)
+        k3, q2 = keys.view(B, T, Hd), q.view(B, Hd)
+        out, att = ops.din_attention_fwd(q2, k3, lens, *ws, want_weights=True)
+        dq, dk, _ = ops.din_attention_bwd(q2, k3, lens, *ws, go, att_w=att)
+        ops.embed_fm2_bwd(keys, dk.view(B * T, 1, Hd), None)
+        ops.embed_fm2_bwd(q, dq.view(B, 1, Hd), None)
+    run("din_cfg4", {"B": B, "T": T, "H": Hd, "rows": rows, "lengths": "uniform{0..50}"}, B, din)
+
+
+if __name__ == "__main__" and "--configs" in sys.argv:
+    config_level()
