@@ -101,6 +101,20 @@ int ctr_sharded_publish_counts(const int64_t* counters, int64_t* const* peer_cou
 int ctr_rows_scatter_add(float* dst, int64_t V, int64_t D, const int64_t* rows, const float* vals, const int64_t* count,
                          int64_t max_n, void* stream);
 
+/* ---- Adam on the IndexedSlices gradient of a table (the step right after the hot path) ------------------
+ * Reference: tf.train.AdamOptimizer(lr, .9, .999, 1e-8) (DeepFM/deepfm.py:246-250); its sparse apply sums duplicate
+ * indices, decays m and v of the WHOLE table and updates every row; DIEN uses LazyAdam (DIEN/dien.py:328).
+ * rows (n) must be UNIQUE with grads (n, D) already summed per row (ctr_rows_scatter_add into a compact buffer does that);
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is computed by the caller.  count: device int64 (NULL = max_n).
+ * ctr_adam_rows updates m, v, var of the listed rows (and sets their bit in touched_bitmap (ceil(V/32) uint32, zeroed by
+ * the caller) when given) = LazyAdam; ctr_adam_dense_rest then applies the g = 0 update to every row whose bit is clear
+ * = the reference's dense semantics. */
+int ctr_adam_rows(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, const float* grads,
+                  const int64_t* count, int64_t max_n, float lr_t, float beta1, float beta2, float eps,
+                  uint32_t* touched_bitmap, void* stream);
+int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, int64_t D, float lr_t, float beta1, float beta2, float eps,
+                        const uint32_t* touched_bitmap, void* stream);
+
 /* DeepFM first-order ("wide") term as a D=1 lookup.  Replaces indicator_column multi-hot (B, sum V) @
  * dense(1) (DeepFM/deepfm.py:72-80,180-181): out[b] = bias + sum_f w[field_row_offset[f] + ids[b,f]]; invalid ids add 0.
  * w (V_total) is the dense(1) kernel; its gradient is the IndexedSlices (ids, d_out[b] broadcast over F) -- no kernel

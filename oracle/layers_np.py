@@ -368,3 +368,33 @@ def bilinear_bwd(x, w, type, g):
         else:
             dw[k] += gw
     return dx, dw
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY 8f.3 -- tf.train.AdamOptimizer on an IndexedSlices gradient (DeepFM/deepfm.py:246-250)  [TF-internal, A.8]
+# --------------------------------------------------------------------------------------
+
+
+def adam_sparse_apply(var, m, v, rows, values, t, lr, beta1=0.9, beta2=0.999, eps=1e-8, lazy=False):
+    """One step.  rows (n,) global row ids (duplicates allowed, summed first), values (n, D).
+    Non-lazy = TF's AdamOptimizer._apply_sparse: dense decay of m and v and a dense variable update;
+    lazy = LazyAdamOptimizer (DIEN/dien.py:328): only the referenced rows change.  Returns new (var, m, v)."""
+    var, m, v = var.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    g = np.zeros_like(var)
+    np.add.at(g, rows, values.astype(np.float64))
+    lr_t = lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    # TF casts beta1_t / beta2_t to the variable dtype and forms (1 - beta_t) in float32 (adam.py _apply_sparse_shared):
+    # float32(0.999) is 0.99900001..., so (1 - beta2_t) differs from 1e-3 by 1.3e-5 relative.  The coefficients below
+    # are those float32 values; the accumulation itself stays in float64.
+    om1 = float(np.float32(1.0) - np.float32(beta1)); om2 = float(np.float32(1.0) - np.float32(beta2))
+    beta1 = float(np.float32(beta1)); beta2 = float(np.float32(beta2))
+    if lazy:
+        idx = np.unique(rows)
+        m[idx] = beta1 * m[idx] + om1 * g[idx]
+        v[idx] = beta2 * v[idx] + om2 * g[idx] ** 2
+        var[idx] -= lr_t * m[idx] / (np.sqrt(v[idx]) + eps)
+    else:
+        m = beta1 * m + om1 * g
+        v = beta2 * v + om2 * g * g
+        var = var - lr_t * m / (np.sqrt(v) + eps)
+    return var, m, v

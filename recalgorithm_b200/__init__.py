@@ -7,4 +7,4 @@ layer signatures (recalgorithm_b200.layers).
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "ops", "layers"]
+__all__ = ["_lib", "ops", "autograd", "layers", "feature_column", "sharded", "io", "build"]

@@ -1,0 +1,106 @@
+// SURVEY.md 8f.3 -- the step right after the hot path: applying the IndexedSlices gradient to the embedding table.
+//
+// Reference: tf.train.AdamOptimizer(lr, 0.9, 0.999, 1e-8) on every variable (DeepFM/deepfm.py:246-250); for a table its
+// gradient is IndexedSlices and TF's _apply_sparse [TF-internal, SURVEY A.8] does
+//     g  = unsorted_segment_sum(values, indices)                  (duplicates summed FIRST; g*g is on the sum)
+//     m <- b1*m (DENSE)   ; m[idx] += (1-b1)*g        v <- b2*v (DENSE) ; v[idx] += (1-b2)*g*g
+//     var <- var - lr_t * m / (sqrt(v) + eps)   (DENSE),    lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
+// i.e. plain Adam on the densified gradient: every row of the table moves every step.  DIEN alone uses LazyAdam
+// (DIEN/dien.py:328): only the referenced rows are touched.
+//
+// B200 mapping (pure HBM streaming, no tensor cores): the caller de-duplicates rows and sums their values (one
+// ctr_rows_scatter_add into a compact buffer); then
+//   ctr_adam_rows        updates m, v, var of the U referenced rows and marks them in a bitmap   (both variants)
+//   ctr_adam_dense_rest  streams over ALL other rows with g = 0: m*=b1, v*=b2, var -= lr_t*m/(sqrt(v)+eps)   (TF variant only)
+// so the faithful variant costs 6 table-sized streams per step (77 GB at config 5 -> ~12 ms at HBM peak, 40x the hot
+// path itself) and the lazy variant a few hundred MB.
+#include "ctr_common.cuh"
+
+namespace ctr {
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_rows_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, long long V,
+                 const long long* __restrict__ rows, const float4* __restrict__ grads, const long long* __restrict__ count,
+                 long long max_n, float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched) {
+  long long n = count ? *count : max_n;
+  if (n > max_n) n = max_n;
+  const size_t total = (size_t)n * LPR;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const long long row = __ldg(rows + t / LPR);
+    if (row < 0 || row >= V) continue;
+    const size_t off = (size_t)row * LPR + t % LPR;
+    const float4 g = ldg_stream_f4(grads + t);
+    float4 mm = m[off], vv = v[off], w = var[off];
+    mm.x = b1 * mm.x + (1.f - b1) * g.x; mm.y = b1 * mm.y + (1.f - b1) * g.y;
+    mm.z = b1 * mm.z + (1.f - b1) * g.z; mm.w = b1 * mm.w + (1.f - b1) * g.w;
+    vv.x = b2 * vv.x + (1.f - b2) * g.x * g.x; vv.y = b2 * vv.y + (1.f - b2) * g.y * g.y;
+    vv.z = b2 * vv.z + (1.f - b2) * g.z * g.z; vv.w = b2 * vv.w + (1.f - b2) * g.w * g.w;
+    w.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); w.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
+    w.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); w.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+    m[off] = mm; v[off] = vv; var[off] = w;
+    if (touched != nullptr && t % LPR == 0) atomicOr(touched + (row >> 5), 1u << (row & 31));
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_dense_rest_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, long long V, float lr_t,
+                       float b1, float b2, float eps, const unsigned int* __restrict__ touched) {
+  const size_t total = (size_t)V * LPR;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const long long row = (long long)(t / LPR);
+    if (touched != nullptr && (__ldg(touched + (row >> 5)) >> (row & 31)) & 1u) continue;   // done by adam_rows_kernel
+    float4 mm = ldg_stream_f4(m + t), vv = ldg_stream_f4(v + t), w = ldg_stream_f4(var + t);
+    mm.x *= b1; mm.y *= b1; mm.z *= b1; mm.w *= b1;
+    vv.x *= b2; vv.y *= b2; vv.z *= b2; vv.w *= b2;
+    w.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); w.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
+    w.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); w.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+    stg_stream_f4(m + t, mm); stg_stream_f4(v + t, vv); stg_stream_f4(var + t, w);
+  }
+}
+
+static int check_adam(const char* fn, int64_t V, int64_t D) {
+  CTR_REQUIRE(V >= 0, "%s: bad V", fn);
+  CTR_UNSUPPORTED(D % 4 != 0 || D > 128 || (D & (D - 1)) != 0, "%s: D=%lld unsupported (power of two in 4..128)", fn, (long long)D);
+  return CTR_OK;
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+extern "C" int ctr_adam_rows(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, const float* grads,
+                             const int64_t* count, int64_t max_n, float lr_t, float beta1, float beta2, float eps,
+                             uint32_t* touched_bitmap, void* stream) {
+  int rc = check_adam("ctr_adam_rows", V, D);
+  if (rc) return rc;
+  CTR_REQUIRE(var && m && v && rows && grads && max_n >= 0, "ctr_adam_rows: null argument / bad size");
+  CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(grads), "ctr_adam_rows: buffers must be 16-byte aligned");
+  if (max_n == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)max_n * (D / 4);
+  const int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
+#define GO(L) adam_rows_kernel<L><<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), V, reinterpret_cast<const long long*>(rows), reinterpret_cast<const float4*>(grads), reinterpret_cast<const long long*>(count), max_n, lr_t, beta1, beta2, eps, touched_bitmap)
+  switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
+#undef GO
+  CTR_CHECK_LAUNCH("ctr_adam_rows");
+  return CTR_OK;
+}
+
+extern "C" int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, int64_t D, float lr_t, float beta1, float beta2,
+                                   float eps, const uint32_t* touched_bitmap, void* stream) {
+  int rc = check_adam("ctr_adam_dense_rest", V, D);
+  if (rc) return rc;
+  CTR_REQUIRE(var && m && v, "ctr_adam_dense_rest: null argument");
+  CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v), "ctr_adam_dense_rest: buffers must be 16-byte aligned");
+  if (V == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)V * (D / 4);
+  const int grid = (int)((total + 255) / 256 < (long long)sm_count() * 32 ? (total + 255) / 256 : (long long)sm_count() * 32);
+#define GO(L) adam_dense_rest_kernel<L><<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), V, lr_t, beta1, beta2, eps, touched_bitmap)
+  switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
+#undef GO
+  CTR_CHECK_LAUNCH("ctr_adam_dense_rest");
+  return CTR_OK;
+}

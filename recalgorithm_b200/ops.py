@@ -147,9 +147,6 @@ def cross_bwd(x0, w, b, g_out, xl_in=None):
 
 
 # ------------------------------------------------------------------ Row DIN-ATT
-DIN_PARAM_SHAPES = lambda H: [(4 * H, 64), (64,), (64, 32), (32,), (32, 1), (1,)]   # f1_att / f2_att / f3_att kernel+bias
-
-
 def _din_params(H, w1, b1, w2, b2, w3, b3):
     w3 = w3.reshape(32)
     b3 = b3.reshape(1)
