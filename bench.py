@@ -420,7 +420,7 @@ def run_ours(args, cfg):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 8 + B * 4,
                 "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "what": "pinned-host ids+labels -> H2D (double-buffered on a copy stream) -> lookup_fm2 autograd fwd -> dense(1) head + sigmoid-CE (torch) -> "
-                        "backward (fused bwd kernel -> IndexedSlices) -> loss.item()"},
+                        "backward (fused bwd kernel -> IndexedSlices) -> loss D2H to pinned memory, read on the host one step later"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -115,6 +115,16 @@ int ctr_adam_rows(float* var, float* m, float* v, int64_t V, int64_t D, const in
 int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, int64_t D, float lr_t, float beta1, float beta2, float eps,
                         const uint32_t* touched_bitmap, void* stream);
 
+/* Fused IndexedSlices step (no sort, no host round trip): ids (B,F) per-field local ids (out-of-range = skipped, like the
+ * lookup), row_grads (B,F,D) = the IndexedSlices values of ctr_embed_fm2_bwd -- CONSUMED (duplicates of a row are summed
+ * into one of its entries).  slot_of_row: int32 per table row, all -1 on entry and again on exit (persistent scratch of
+ * the optimizer).  Applies the LazyAdam update to every referenced row with the SUMMED gradient (TF sums duplicates
+ * first); sets the rows' bits in touched_bitmap when given (then ctr_adam_dense_rest completes tf.train.AdamOptimizer's
+ * dense semantics); adds the number of distinct rows to *n_unique when given.  B*F < 2^31. */
+int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field_row_offset, int64_t F, int64_t D,
+                            const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, float lr_t, float beta1,
+                            float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
+
 /* DeepFM first-order ("wide") term as a D=1 lookup.  Replaces indicator_column multi-hot (B, sum V) @
  * dense(1) (DeepFM/deepfm.py:72-80,180-181): out[b] = bias + sum_f w[field_row_offset[f] + ids[b,f]]; invalid ids add 0.
  * w (V_total) is the dense(1) kernel; its gradient is the IndexedSlices (ids, d_out[b] broadcast over F) -- no kernel

@@ -39,6 +39,8 @@ SIGNATURES = {
     "ctr_rows_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, _I, _P]),
     "ctr_adam_rows": (c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                               ctypes.c_float, _P, _P]),
+    "ctr_adam_indexed_slices": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _I, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_float, _P, _P, _P]),
     "ctr_adam_dense_rest": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P]),
     "ctr_first_order_fwd": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, _P, _P]),
     "ctr_bag_lookup_fwd": (c_int, [_P, _I, _I, _P, _P, _I, _P, _I, _P]),

@@ -60,6 +60,81 @@ adam_dense_rest_kernel(float4* __restrict__ var, float4* __restrict__ m, float4*
   }
 }
 
+// ---- fused IndexedSlices step: device-side de-duplication without a sort -------------------------------------------------
+// slot_of_row (int32 per table row, -1 when idle) elects, per referenced row, the FIRST-claiming (b,f) entry as the row's
+// accumulator:  claim (atomicCAS) -> merge (every other entry of that row adds its gradient into the winner's slot of
+// row_grads, 128-bit reductions) -> update (the winner applies Adam with the summed gradient, clears the slot, marks the
+// bitmap).  Three launches on one stream, no host round trip; row_grads is consumed (clobbered).
+__device__ __forceinline__ long long entry_row(const long long* __restrict__ ids, const long long* __restrict__ off, int F, long long e) {
+  const int f = (int)(e % F);
+  const long long id = __ldg(ids + e), base = __ldg(off + f);
+  return (id < 0 || id >= __ldg(off + f + 1) - base) ? -1 : base + id;
+}
+
+__global__ void __launch_bounds__(256)
+adam_claim_kernel(const long long* __restrict__ ids, const long long* __restrict__ off, int F, long long n, int* __restrict__ slot) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = entry_row(ids, off, F, e);
+    if (row >= 0) atomicCAS(slot + row, -1, (int)e);
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_merge_kernel(const long long* __restrict__ ids, const long long* __restrict__ off, int F, long long n,
+                  const int* __restrict__ slot, float4* __restrict__ grads) {
+  const size_t total = (size_t)n * LPR;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const long long e = (long long)(t / LPR);
+    const long long row = entry_row(ids, off, F, e);
+    if (row < 0) continue;
+    const int w = __ldg(slot + row);
+    if (w != (int)e) atomicAdd(grads + (size_t)w * LPR + t % LPR, grads[t]);
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, const long long* __restrict__ ids,
+                   const long long* __restrict__ off, int F, long long n, int* __restrict__ slot, const float4* __restrict__ grads,
+                   float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched, long long* __restrict__ n_unique) {
+  const size_t total = (size_t)n * LPR;
+  int mine = 0;
+  // warp-uniform trip count: the lanes of one entry (LPR <= 32, aligned) sit in one warp and all read the slot before
+  // lane 0 of the entry clears it
+  for (size_t base = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); base < total; base += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = base + (threadIdx.x & 31);
+    long long row = -1;
+    bool win = false;
+    if (t < total) {
+      const long long e = (long long)(t / LPR);
+      row = entry_row(ids, off, F, e);
+      win = row >= 0 && slot[row] == (int)e;
+    }
+    __syncwarp();
+    if (!win) continue;
+    const size_t o = (size_t)row * LPR + t % LPR;
+    const float4 g = ldg_stream_f4(grads + t);
+    float4 mm = m[o], vv = v[o], w = var[o];
+    mm.x = b1 * mm.x + (1.f - b1) * g.x; mm.y = b1 * mm.y + (1.f - b1) * g.y;
+    mm.z = b1 * mm.z + (1.f - b1) * g.z; mm.w = b1 * mm.w + (1.f - b1) * g.w;
+    vv.x = b2 * vv.x + (1.f - b2) * g.x * g.x; vv.y = b2 * vv.y + (1.f - b2) * g.y * g.y;
+    vv.z = b2 * vv.z + (1.f - b2) * g.z * g.z; vv.w = b2 * vv.w + (1.f - b2) * g.w * g.w;
+    w.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); w.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
+    w.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); w.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+    m[o] = mm; v[o] = vv; var[o] = w;
+    if (t % LPR == 0) {
+      slot[row] = -1;
+      if (touched != nullptr) atomicOr(touched + (row >> 5), 1u << (row & 31));
+      ++mine;
+    }
+  }
+  if (n_unique != nullptr) {
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(n_unique), (unsigned long long)mine);
+  }
+}
+
 static int check_adam(const char* fn, int64_t V, int64_t D) {
   CTR_REQUIRE(V >= 0, "%s: bad V", fn);
   CTR_UNSUPPORTED(D % 4 != 0 || D > 128 || (D & (D - 1)) != 0, "%s: D=%lld unsupported (power of two in 4..128)", fn, (long long)D);
@@ -102,5 +177,36 @@ extern "C" int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, in
   switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
 #undef GO
   CTR_CHECK_LAUNCH("ctr_adam_dense_rest");
+  return CTR_OK;
+}
+
+extern "C" int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field_row_offset, int64_t F, int64_t D,
+                                       const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, float lr_t,
+                                       float beta1, float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique,
+                                       void* stream) {
+  int rc = check_adam("ctr_adam_indexed_slices", 0, D);
+  if (rc) return rc;
+  CTR_REQUIRE(var && m && v && field_row_offset && ids && row_grads && slot_of_row, "ctr_adam_indexed_slices: null argument");
+  CTR_REQUIRE(B >= 0 && F >= 1 && F <= (1 << 20) && B * F < (1LL << 31), "ctr_adam_indexed_slices: bad B/F (B*F must be < 2^31)");
+  CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(row_grads),
+              "ctr_adam_indexed_slices: buffers must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  const long long n = B * F, total = n * (D / 4);
+  auto cap = [](long long want, long long lim) { return (int)(want < lim ? want : lim); };
+  const int grid_e = cap((n + 255) / 256, (long long)sm_count() * 16), grid_t = cap((total + 255) / 256, (long long)sm_count() * 16);
+  auto* idp = reinterpret_cast<const long long*>(ids);
+  auto* offp = reinterpret_cast<const long long*>(field_row_offset);
+  auto* g4 = reinterpret_cast<float4*>(row_grads);
+  adam_claim_kernel<<<grid_e, 256, 0, st>>>(idp, offp, (int)F, n, slot_of_row);
+#define GO(L)                                                                                                               \
+  adam_merge_kernel<L><<<grid_t, 256, 0, st>>>(idp, offp, (int)F, n, slot_of_row, g4);                                      \
+  adam_update_kernel<L><<<grid_t, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),               \
+                                                reinterpret_cast<float4*>(v), idp, offp, (int)F, n, slot_of_row, g4, lr_t,  \
+                                                beta1, beta2, eps, touched_bitmap, reinterpret_cast<long long*>(n_unique))
+  switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
+#undef GO
+  CTR_CHECK_LAUNCH("ctr_adam_indexed_slices");
+  count_launch(2);
   return CTR_OK;
 }

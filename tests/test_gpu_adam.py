@@ -29,8 +29,9 @@ def test_table_adam_matches_oracle(lazy, D):
         valid = (ids >= 0) & (ids < rows)
         grows = (ids + off[:-1][None, :])[valid]
         gvals = sl.values.cpu().double().numpy()[valid]
-        n_unique = opt.step()
-        assert n_unique == len(np.unique(grows)) and not tables.grad_slices
+        opt.step()
+        assert opt.last_unique_rows() == len(np.unique(grows)) and not tables.grad_slices
+        assert bool((opt._slot == -1).all()), "slot table must be idle (-1) between steps"
         var, m, v = O.adam_sparse_apply(var, m, v, grows, gvals, t, 0.01, lazy=lazy)
         assert_close(tables.weight, var, 2e-6, f"var step {t}")
         assert_close(opt.m, m, 1e-5, f"m step {t}"); assert_close(opt.v, v, 1e-5, f"v step {t}")
@@ -38,3 +39,29 @@ def test_table_adam_matches_oracle(lazy, D):
         before = tables.weight.clone()
         opt.step()
         assert not torch.equal(before, tables.weight)
+
+
+@pytest.mark.parametrize("lazy", [False, True])
+def test_table_adam_heavy_duplicates_and_two_backward_passes(lazy):
+    """3 rows per field shared by 512 samples (every row has ~170 duplicates) and two backward passes before one step:
+    TF sums every IndexedSlices entry of a row before the moment update."""
+    from recalgorithm_b200 import autograd, optim
+    rng = np.random.default_rng(7 + int(lazy))
+    F, B, rows, D = 3, 512, 3, 8
+    tables = autograd.EmbeddingTables([rows] * F, D, device="cuda")
+    opt = optim.TableAdam(tables, lr=0.05, lazy=lazy)
+    var = tables.weight.cpu().double().numpy(); m = np.zeros_like(var); v = np.zeros_like(var)
+    off = tables.field_row_offset.cpu().numpy()
+    for t in range(1, 4):
+        grows, gvals = [], []
+        for _ in range(2):
+            ids = rng.integers(0, rows, size=(B, F)).astype(np.int64)
+            d_tile = trunc_normal(rng, (B, F, D), 1.0)
+            tile, _ = autograd.lookup_fm2(tables, dev(ids))
+            (tile * dev(d_tile)).sum().backward()
+            grows.append((ids + off[:-1][None, :]).reshape(-1)); gvals.append(d_tile.reshape(-1, D).astype(np.float64))
+        opt.step()
+        assert opt.last_unique_rows() == rows * F
+        var, m, v = O.adam_sparse_apply(var, m, v, np.concatenate(grows), np.concatenate(gvals), t, 0.05, lazy=lazy)
+        assert_close(tables.weight, var, 2e-6, f"var step {t}")
+        assert_close(opt.m, m, 1e-5, f"m step {t}"); assert_close(opt.v, v, 1e-5, f"v step {t}")

@@ -128,6 +128,29 @@ def main():
             m, bst = timeit(lambda: ops.bilinear_bwd(x, w, typ, gp), max(3, args.iters // 4), flush)
             emit(f"bilinear_bwd_{typ}", {"B": B, "F": F, "K": K}, m, bst, bytes_=B * (2 * F * K + P * K) * 4)
 
+    if "adam" in only:   # SURVEY 8f.3 at BASELINE config 5: the table update that follows the hot path
+        from recalgorithm_b200 import autograd, optim
+        rows = int(os.environ.get("CTR_BENCH_ROWS", 2_500_000))
+        B, F, D = 65536, 40, 32
+        tables = autograd.EmbeddingTables([rows] * F, D, device="cuda")
+        ids = [torch.randint(0, rows, (B, F), device="cuda", generator=gen) for _ in range(4)]
+        vals = rn(B, F, D)
+        for lazy in (True, False):
+            opt = optim.TableAdam(tables, lr=1e-3, lazy=lazy)
+            k = [0]
+
+            def step():
+                k[0] += 1
+                tables.grad_slices.append(autograd.IndexedSlices(vals.clone(), ids[k[0] % 4], tables.field_row_offset))
+                opt.step()
+            m_, bst = timeit(step, max(5, args.iters // 2), flush)
+            n = B * F
+            # algorithmic bytes: ids + values read; (m, v, var) read+written for the referenced rows; dense variant: 6 table streams
+            by = n * 8 + n * D * 4 + 6 * n * D * 4 if lazy else 6 * tables.num_rows * D * 4 + n * 8 + n * D * 4
+            emit("table_adam_lazy" if lazy else "table_adam_dense", {"B": B, "F": F, "D": D, "rows_per_field": rows}, m_, bst,
+                 bytes_=by, note="includes a 336 MB clone of the gradient values per step (the step consumes them)")
+            del opt
+
 
 if __name__ == "__main__" and "--configs" not in sys.argv:
     main()
