@@ -209,6 +209,29 @@ int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64_t F, int64
 int ctr_bilinear_bwd(const float* x, const float* w, const float* g_out, int64_t B, int64_t F, int64_t K, int type,
                      float* dx, float* dw, void* stream);
 
+/* ---- siblings of FM2 ------------------------------------------------------------------------------------------
+ * NFM bi-interaction pooling (NFM/nfm.py:155-168): the fused gather of ctr_embed_fm2_fwd with a (B, D) output
+ * bi[b,:] = 0.5 * ((sum_f e_f)^2 - sum_f e_f^2) instead of its sum over D; tile may be NULL.  Backward:
+ * row_grads[b,f,:] = d_tile[b,f,:] (nullable) + d_bi[b,:] * (S[b,:] - e[b,f,:]). */
+int ctr_embed_bi_fwd(const float* table, const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F, int64_t D,
+                     float* tile, float* bi, void* stream);
+int ctr_embed_bi_bwd(const float* tile, const float* d_tile, const float* d_bi, int64_t B, int64_t F, int64_t D,
+                     float* row_grads, void* stream);
+
+/* FwFM second-order logit (FwFM/fwfm.py:140-158): out[b] = sum_{i<j} r[pair(i,j)] * <tile[b,i,:], tile[b,j,:]>, r (F(F-1)/2,)
+ * indexed like utils.py:67-82 (row-major strict upper triangle).  Backward: d_tile (B,F,K) and d_r (overwritten). */
+int ctr_fwfm_fwd(const float* tile, const float* r, int64_t B, int64_t F, int64_t K, float* out, void* stream);
+int ctr_fwfm_bwd(const float* tile, const float* r, const float* g, int64_t B, int64_t F, int64_t K, float* d_tile, float* d_r,
+                 void* stream);
+
+/* AFM attention pooling (AFM/afm.py:152-186): pairs (i<j) in the reference's order, a_p = h^T relu(W^T (e_i*e_j) + b),
+ * softmax over the pair axis, pooled (B,K) = sum_p s_p (e_i*e_j).  w (K,T) row-major, b (T,), h (T,); score (B,P) optional
+ * output.  K in {4,8,16,32} with K*ceil(T/32) <= 64.  Backward overwrites d_tile (B,F,K), d_w, d_b, d_h. */
+int ctr_afm_fwd(const float* tile, const float* w, const float* b, const float* h, int64_t B, int64_t F, int64_t K, int64_t T,
+                float* pooled, float* score, void* stream);
+int ctr_afm_bwd(const float* tile, const float* w, const float* b, const float* h, const float* g_pooled, int64_t B, int64_t F,
+                int64_t K, int64_t T, float* d_tile, float* d_w, float* d_b, float* d_h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

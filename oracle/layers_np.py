@@ -132,6 +132,95 @@ def fm2_pairwise(e: np.ndarray) -> np.ndarray:
         out[:, 0] += np.sum(e[:, i, :] * e[:, j, :], axis=1)
     return out
 
+# ---- siblings of FM2 (NFM bi-interaction, FwFM, AFM) ---------------------------------------------------------
+
+def bi_interaction_fwd(e: np.ndarray) -> np.ndarray:
+    """NFM bi-interaction pooling (B, K): FM2 without the sum over K.  NFM/nfm.py:155-168:
+    ``0.5 * (square(add_n(e_f)) - add_n(square(e_f)))`` (the BN/dropout after it are outside the path)."""
+    F = e.shape[1]
+    s = e[:, 0, :].copy()
+    q = np.square(e[:, 0, :])
+    for f in range(1, F):
+        s = s + e[:, f, :]
+        q = q + np.square(e[:, f, :])
+    return e.dtype.type(0.5) * (np.square(s) - q)
+
+
+def bi_interaction_bwd(e: np.ndarray, g: np.ndarray) -> np.ndarray:
+    """g: (B, K) -> de[b,f,:] = g[b,:] * (S[b,:] - e[b,f,:])."""
+    return g[:, None, :] * (e.sum(axis=1, keepdims=True) - e)
+
+
+def pair_index(i: int, j: int, n: int) -> int:
+    """Flat index of (i, j), i < j, in the row-major strict upper triangle of an n x n matrix
+    (utils.py:67-82: sum_{k<i}(n-1-k) + j-i-1)."""
+    return i * (n - 1) - i * (i - 1) // 2 + (j - i - 1)
+
+
+def fwfm_fwd(e: np.ndarray, r: np.ndarray) -> np.ndarray:
+    """FwFM second-order logit (B, 1): sum_{i<j} r[pair_index(i,j,F)] * <e_i, e_j>, pairs accumulated in the reference's
+    loop order (FwFM/fwfm.py:152-158: ``+= scalar_mul(r[index], batch_dot(e_i, e_j, axes=1))``)."""
+    B, F, _ = e.shape
+    out = np.zeros((B, 1), dtype=e.dtype)
+    for i in range(F - 1):
+        for j in range(i + 1, F):
+            out = out + r[pair_index(i, j, F)] * np.sum(e[:, i, :] * e[:, j, :], axis=1, keepdims=True)
+    return out
+
+
+def fwfm_bwd(e: np.ndarray, r: np.ndarray, g: np.ndarray):
+    """g: (B,) or (B,1).  Returns (de (B,F,K), dr (P,))."""
+    B, F, _ = e.shape
+    g = g.reshape(B, 1)
+    de = np.zeros_like(e)
+    dr = np.zeros_like(r)
+    for i in range(F - 1):
+        for j in range(i + 1, F):
+            p = pair_index(i, j, F)
+            de[:, i, :] += g * r[p] * e[:, j, :]
+            de[:, j, :] += g * r[p] * e[:, i, :]
+            dr[p] = np.sum(g[:, 0] * np.sum(e[:, i, :] * e[:, j, :], axis=1))
+    return de, dr
+
+
+def afm_pairs(F: int):
+    return [(i, j) for i in range(F) for j in range(i + 1, F)]        # AFM/afm.py:162-164
+
+
+def afm_fwd(e: np.ndarray, w: np.ndarray, b: np.ndarray, h: np.ndarray, return_all: bool = False):
+    """AFM attention pooling (B, K).  AFM/afm.py:152-186: pair_hadamard (B,P,K) = e_i * e_j for i<j;
+    attention = relu(pair @ w + b) @ h -> (B,P,1); softmax over the PAIR axis; sum_p score * pair."""
+    pairs = afm_pairs(e.shape[1])
+    had = np.stack([e[:, i, :] * e[:, j, :] for i, j in pairs], axis=1)                  # (B,P,K)
+    pre = np.matmul(had, w) + b                                                            # (B,P,t)
+    act = np.maximum(pre, 0)
+    att = np.matmul(act, h)                                                                # (B,P,1)
+    att = att - att.max(axis=1, keepdims=True)
+    ex = np.exp(att)
+    score = ex / ex.sum(axis=1, keepdims=True)
+    out = np.sum(had * score, axis=1)
+    return (out, had, pre, act, score) if return_all else out
+
+
+def afm_bwd(e, w, b, h, g):
+    """g: (B,K) gradient of the pooled vector.  Returns (de, dw, db, dh)."""
+    e, w, b, h, g = (np.asarray(x, dtype=np.float64) for x in (e, w, b, h, g))
+    out, had, pre, act, score = afm_fwd(e, w, b, h, return_all=True)
+    pairs = afm_pairs(e.shape[1])
+    dscore = np.sum(had * g[:, None, :], axis=2, keepdims=True)                            # (B,P,1)
+    datt = score * (dscore - np.sum(score * dscore, axis=1, keepdims=True))
+    dh = np.einsum("bpt,bpo->to", act, datt)
+    dact = datt * h[:, 0][None, None, :]
+    dpre = dact * (pre > 0)
+    dw = np.einsum("bpk,bpt->kt", had, dpre)
+    db = dpre.sum(axis=(0, 1))
+    dhad = g[:, None, :] * score + np.matmul(dpre, w.T)
+    de = np.zeros_like(e)
+    for p, (i, j) in enumerate(pairs):
+        de[:, i, :] += dhad[:, p, :] * e[:, j, :]
+        de[:, j, :] += dhad[:, p, :] * e[:, i, :]
+    return de, dw, db, dh
+
 
 # --------------------------------------------------------------------------------------
 # Row CROSS -- DCN cross layer

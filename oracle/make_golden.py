@@ -235,9 +235,83 @@ def gen_restated():
          source="restated:TF1.14 feature_column semantics (SURVEY A.4-A.6) -- parity unpinned")
 
 
+# ---- inline blocks of model_fns: the cited source lines are read from /root/reference at generation time and exec()'d ----
+
+class _FakeFC:
+    """Stand-in for `tf.feature_column` inside the inline blocks: `fc.input_layer(features, [col])` returns the (B, K)
+    embedding injected for that column (the lookup itself is TF-internal and pinned elsewhere as 'unpinned')."""
+    @staticmethod
+    def input_layer(features, columns):
+        return tf.concat([tf.Tensor(features[c]) for c in columns], axis=1)
+
+
+def exec_ref_lines(relpath, first, last, must_contain, ns):
+    import textwrap
+    with open(os.path.join(REF, relpath), encoding="utf-8") as fh:
+        lines = fh.read().split("\n")[first - 1:last]
+    assert must_contain[0] in lines[0] and must_contain[1] in lines[-1], (relpath, lines[0], lines[-1])
+    exec(compile(textwrap.dedent("\n".join(lines)), f"{relpath}:{first}-{last}", "exec"), ns)
+    return ns
+
+
+def _inline_case(relpath, first, last, must, e, key, out_name, variables=None, extra=None):
+    F = e.shape[1]
+    cols = [f"c{f:02d}" for f in range(F)]
+    outs = {}
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        tf.reset(dtype=dt, variables=variables or {})
+        ns = {"tf": tf, "fc": _FakeFC, "features": {c: e[:, f, :].astype(dt) for f, c in enumerate(cols)},
+              "params": {key: cols, **(extra or {})}}
+        sys.path.insert(0, REF)                              # FwFM imports index_from_upper_triangular from utils.py
+        if "index_from_upper_triangular" in must[2:]:
+            ns["index_from_upper_triangular"] = _load("utils.py", "ref_utils").index_from_upper_triangular
+        exec_ref_lines(relpath, first, last, must, ns)
+        outs[tag] = np.asarray(ns[out_name].a if hasattr(ns[out_name], "a") else ns[out_name])
+    return outs, tf.created_variables()
+
+
+def gen_inline():
+    from oracle import layers_np as O
+    rng = np.random.default_rng(2468)
+    for F, D, B in ((6, 8, 16), (40, 32, 8)):
+        e = trunc_normal(rng, (B, F, D), 1.0 / np.sqrt(D))
+        outs, _ = _inline_case("DeepFM/deepfm.py", 184, 200, ("fields_embeddings = []", "keepdims=True)"), e,
+                               "second_order_feature_columns", "fm_second_order_logit")
+        save(f"fm2_ref_F{F}_D{D}", e=e, out_f32=outs["f32"], out_f64=outs["f64"], source="reference-executed:DeepFM/deepfm.py:184-200")
+        outs, _ = _inline_case("NFM/nfm.py", 155, 168, ('variable_scope("bi_interaction_part")', "nfm = 0.5 *"), e,
+                               "category_feature_columns", "nfm")
+        save(f"nfm_bi_F{F}_D{D}", e=e, out_f32=outs["f32"], out_f64=outs["f64"], source="reference-executed:NFM/nfm.py:155-168")
+    for F, D, B in ((6, 8, 16), (30, 16, 8)):
+        e = trunc_normal(rng, (B, F, D), 1.0 / np.sqrt(D))
+        P = F * (F - 1) // 2
+        r = glorot(rng, (P,), fan_in=P, fan_out=P)
+        outs, created = _inline_case("FwFM/fwfm.py", 140, 158, ("fields_embeddings = []", ")", "index_from_upper_triangular"), e,
+                                     "second_order_feature_columns", "fwfm_second_order_logit",
+                                     variables={"fields_pair_strength/fields_pair_strength_weight": r})
+        assert created == {"fields_pair_strength/fields_pair_strength_weight": (P,)}, created
+        save(f"fwfm_F{F}_D{D}", e=e, r=r, out_f32=outs["f32"], out_f64=outs["f64"], source="reference-executed:FwFM/fwfm.py:140-158")
+    for F, D, t, B in ((5, 8, 4, 16), (30, 16, 8, 6)):
+        e = trunc_normal(rng, (B, F, D), 1.0)
+        w, b, h, pv = glorot(rng, (D, t)), glorot(rng, (t,), fan_in=t, fan_out=t), glorot(rng, (t, 1)), glorot(rng, (D, 1))
+        variables = {"attention_part/attention_w": w, "attention_part/attention_b": b, "attention_part/attention_h": h,
+                     "prediction_score_part/p": pv}
+        res = {}
+        for name in ("weighted_sum", "afm_logit", "attention_score"):
+            outs, created = _inline_case("AFM/afm.py", 152, 188, ('variable_scope("pair_interaction_part")', "afm_logit = tf.matmul"), e,
+                                         "category_feature_columns", name, variables=variables,
+                                         extra={"embedding_dim": D, "attention_factor": t})
+            res[name] = outs
+        assert created == {"attention_part/attention_w": (D, t), "attention_part/attention_b": (t,),
+                           "attention_part/attention_h": (t, 1), "prediction_score_part/p": (D, 1)}, created
+        save(f"afm_F{F}_D{D}_t{t}", e=e, w=w, b=b, h=h, p=pv, pooled_f32=res["weighted_sum"]["f32"], pooled_f64=res["weighted_sum"]["f64"],
+             logit_f32=res["afm_logit"]["f32"], logit_f64=res["afm_logit"]["f64"], score_f64=res["attention_score"]["f64"],
+             source="reference-executed:AFM/afm.py:152-188")
+
+
 if __name__ == "__main__":
     gen_cross()
     gen_cin()
     gen_din()
     gen_fibinet()
     gen_restated()
+    gen_inline()

@@ -14,7 +14,10 @@ reshape index order, variable shapes -- is what produces the golden vectors.  Wh
 pinned by this is the arithmetic inside each TF primitive (Eigen summation order etc.);
 each primitive below states the public TF 1.14 semantics it implements.
 
-Only what those five files touch is implemented.  Everything evaluates eagerly on
+The same shim also runs the INLINE interaction blocks of DeepFM/NFM/FwFM/AFM model_fns: make_golden.py reads the
+cited line ranges from /root/reference at generation time and exec()s them with a stand-in ``fc.input_layer``.
+
+Only what those files touch is implemented.  Everything evaluates eagerly on
 ``numpy`` arrays in ``_STATE.dtype`` (float32 like the reference, or float64 for the
 high-precision anchor).
 """
@@ -163,7 +166,7 @@ def get_variable(name, shape=None, dtype=None, initializer=None):
     """tf.get_variable: looked up by scoped name among the injected variables; if absent it is
     created with a glorot-uniform draw (the TF1 default initializer) and recorded."""
     full = _full_name(name)
-    shp = tuple(int(s) for s in shape)
+    shp = (int(shape),) if isinstance(shape, (int, _np.integer, Dimension)) else tuple(int(s) for s in shape)   # `shape=n` is legal TF
     _STATE.created[full] = shp
     if full not in _STATE.variables:
         fan_in = shp[0] if len(shp) < 3 else int(_np.prod(shp[:-2])) * shp[-2]
@@ -190,6 +193,11 @@ def matmul(a, b, transpose_a=False, transpose_b=False):
 def multiply(a, b): return Tensor(_np.multiply(_arr(a), _arr(b)))
 def add(a, b): return Tensor(_np.add(_arr(a), _arr(b)))
 def square(a): return Tensor(_np.square(_arr(a)))
+
+
+def scalar_mul(scalar, x):
+    """tf.scalar_mul(scalar, x) = scalar * x (scalar is a 0-d tensor)."""
+    return Tensor(_arr(scalar) * _arr(x))
 
 
 def add_n(xs):
@@ -281,3 +289,20 @@ class _Layers:
 
 
 layers = _Layers()
+
+
+class _KerasBackend:
+    @staticmethod
+    def batch_dot(x, y, axes=None):
+        """tf.keras.backend.batch_dot for the reference's only use (FwFM/fwfm.py:156): two (B, K) tensors, axes=1
+        -> (B, 1) (Keras keeps a trailing unit axis when the result would be rank 1)."""
+        X, Y = _arr(x), _arr(y)
+        assert X.ndim == 2 and Y.ndim == 2 and axes == 1
+        return Tensor(_np.sum(X * Y, axis=1, keepdims=True))
+
+
+class _Keras:
+    backend = _KerasBackend()
+
+
+keras = _Keras()

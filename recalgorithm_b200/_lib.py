@@ -39,6 +39,12 @@ SIGNATURES = {
     "ctr_rows_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, _I, _P]),
     "ctr_adam_rows": (c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                               ctypes.c_float, _P, _P]),
+    "ctr_embed_bi_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "ctr_embed_bi_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "ctr_fwfm_fwd": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "ctr_fwfm_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "ctr_afm_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "ctr_afm_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ctr_adam_indexed_slices": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _I, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, _P, _P, _P]),
     "ctr_adam_dense_rest": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P]),

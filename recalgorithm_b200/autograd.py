@@ -190,3 +190,61 @@ class _Bilinear(torch.autograd.Function):
 
 def bilinear(x, w, type_):
     return _Bilinear.apply(x, w, type_)
+
+
+# ------------------------------------------------------------------------------------ FM2 siblings
+class _LookupBI(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, tables: EmbeddingTables, ids: torch.Tensor):
+        tile, bi = ops.embed_bi_fwd(tables.weight, tables.field_row_offset, ids)
+        ctx.tables, ctx.ids = tables, ids
+        ctx.save_for_backward(tile)
+        return tile, bi
+
+    @staticmethod
+    def backward(ctx, d_tile, d_bi):
+        (tile,) = ctx.saved_tensors
+        d_tile = d_tile.contiguous() if d_tile is not None else None
+        d_bi = d_bi.contiguous() if d_bi is not None else torch.zeros((tile.shape[0], tile.shape[2]), device=tile.device)
+        values = ops.embed_bi_bwd(tile, d_tile, d_bi)
+        ctx.tables.grad_slices.append(IndexedSlices(values, ctx.ids, ctx.tables.field_row_offset))
+        return None, None, None
+
+
+def lookup_bi(tables: EmbeddingTables, ids: torch.Tensor):
+    """(B,F) ids -> (tile (B,F,D), NFM bi-interaction vector (B,D)); differentiable w.r.t. the tables (IndexedSlices)."""
+    return _LookupBI.apply(tables._anchor, tables, ids)
+
+
+class _FwFM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tile, r):
+        tile, r = tile.contiguous(), r.contiguous()
+        ctx.save_for_backward(tile, r)
+        return ops.fwfm_fwd(tile, r)
+
+    @staticmethod
+    def backward(ctx, g):
+        tile, r = ctx.saved_tensors
+        return ops.fwfm_bwd(tile, r, g.contiguous())
+
+
+def fwfm(tile: torch.Tensor, r: torch.Tensor) -> torch.Tensor:
+    return _FwFM.apply(tile, r)
+
+
+class _AFM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tile, w, b, h):
+        tile, w, b, h = tile.contiguous(), w.contiguous(), b.contiguous(), h.contiguous()
+        ctx.save_for_backward(tile, w, b, h)
+        return ops.afm_fwd(tile, w, b, h)
+
+    @staticmethod
+    def backward(ctx, g):
+        tile, w, b, h = ctx.saved_tensors
+        return ops.afm_bwd(tile, w, b, h, g.contiguous())
+
+
+def afm(tile: torch.Tensor, w: torch.Tensor, b: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    return _AFM.apply(tile, w, b, h)

@@ -32,7 +32,9 @@ struct PeerTables {
 
 // NCH > 0: F <= 32*NCH; the lane's row-offset window is cached and the ids of the NEXT sample are requested before the
 // current sample's rows (one DRAM latency taken off the per-sample critical path).  NCH == 0: any F, ids loaded per chunk.
-template <int LPR, bool SH, int MINB, int NCH>
+// BI: `fm2` points at a (B, D) buffer that receives 0.5*(S^2 - Q) per embedding dim (NFM bi-interaction pooling,
+// NFM/nfm.py:155-168) instead of its sum over D.
+template <int LPR, bool SH, int MINB, int NCH, bool BI = false>
 __global__ void __launch_bounds__(256, MINB)
 embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, const long long* __restrict__ row_off,
                      const long long* __restrict__ ids, int B, int F, float4* __restrict__ tile,
@@ -123,6 +125,15 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, c
         Q.x += __shfl_xor_sync(full, Q.x, o); Q.y += __shfl_xor_sync(full, Q.y, o);
         Q.z += __shfl_xor_sync(full, Q.z, o); Q.w += __shfl_xor_sync(full, Q.w, o);
       }
+      if (BI) {
+        if (lane < LPR) {
+          float4 r;
+          r.x = 0.5f * __fsub_rn(__fmul_rn(S.x, S.x), Q.x); r.y = 0.5f * __fsub_rn(__fmul_rn(S.y, S.y), Q.y);
+          r.z = 0.5f * __fsub_rn(__fmul_rn(S.z, S.z), Q.z); r.w = 0.5f * __fsub_rn(__fmul_rn(S.w, S.w), Q.w);
+          reinterpret_cast<float4*>(fm2)[(size_t)b * LPR + c] = r;
+        }
+        continue;
+      }
       // 0.5 * (S^2 - Q) per embedding dim, then reduce over D (4 components x LPR lanes)
       float p = 0.5f * __fsub_rn(__fmul_rn(S.x, S.x), Q.x) + 0.5f * __fsub_rn(__fmul_rn(S.y, S.y), Q.y) +
                 0.5f * __fsub_rn(__fmul_rn(S.z, S.z), Q.z) + 0.5f * __fsub_rn(__fmul_rn(S.w, S.w), Q.w);
@@ -136,7 +147,8 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, c
 // Backward: row_grads[b,f,:] = d_tile[b,f,:] + g[b] * (S[b,:] - e[b,f,:]).
 // HOLD > 0: the sample's tile row (F*D fp32 <= HOLD*128 floats) stays in registers between the S pass and
 // the gradient pass; HOLD == 0: generic two-pass variant (second pass re-reads through L1/L2).
-template <int LPR, int HOLD>
+// BI: d_fm2 is the (B, D) gradient of the bi-interaction vector (g becomes per-dimension).
+template <int LPR, int HOLD, bool BI = false>
 __global__ void __launch_bounds__(256)
 embed_fm2_bwd_kernel(const float4* __restrict__ tile, const float4* __restrict__ d_tile,
                      const float* __restrict__ d_fm2, int B, int F, float4* __restrict__ row_grads) {
@@ -150,7 +162,13 @@ embed_fm2_bwd_kernel(const float4* __restrict__ tile, const float4* __restrict__
     const float4* e_row = tile + (size_t)b * n4;
     float4* o_row = row_grads + (size_t)b * n4;
     const float4* dt_row = d_tile ? d_tile + (size_t)b * n4 : nullptr;
-    const float g = d_fm2 ? __ldg(d_fm2 + b) : 0.f;
+    float4 g4;
+    if (BI) {
+      g4 = __ldg(reinterpret_cast<const float4*>(d_fm2) + (size_t)b * LPR + lane % LPR);
+    } else {
+      const float g = d_fm2 ? __ldg(d_fm2 + b) : 0.f;
+      g4 = make_float4(g, g, g, g);
+    }
     float4 S = f4_zero();
     if (HOLD > 0) {
       constexpr int H = HOLD > 0 ? HOLD : 1;
@@ -180,8 +198,8 @@ embed_fm2_bwd_kernel(const float4* __restrict__ tile, const float4* __restrict__
         const int j = k * 32 + lane;
         if (j < n4) {
           float4 r;
-          r.x = dt[k].x + g * (S.x - e[k].x); r.y = dt[k].y + g * (S.y - e[k].y);
-          r.z = dt[k].z + g * (S.z - e[k].z); r.w = dt[k].w + g * (S.w - e[k].w);
+          r.x = dt[k].x + g4.x * (S.x - e[k].x); r.y = dt[k].y + g4.y * (S.y - e[k].y);
+          r.z = dt[k].z + g4.z * (S.z - e[k].z); r.w = dt[k].w + g4.w * (S.w - e[k].w);
           stg_stream_f4(o_row + j, r);
         }
       }
@@ -198,7 +216,7 @@ embed_fm2_bwd_kernel(const float4* __restrict__ tile, const float4* __restrict__
       for (int j = lane; j < n4; j += 32) {
         const float4 v = __ldg(e_row + j);
         float4 r = dt_row ? ldg_stream_f4(dt_row + j) : f4_zero();
-        r.x += g * (S.x - v.x); r.y += g * (S.y - v.y); r.z += g * (S.z - v.z); r.w += g * (S.w - v.w);
+        r.x += g4.x * (S.x - v.x); r.y += g4.y * (S.y - v.y); r.z += g4.z * (S.z - v.z); r.w += g4.w * (S.w - v.w);
         stg_stream_f4(o_row + j, r);
       }
     }
@@ -346,10 +364,10 @@ static int launch_fwd(const float* table, const PeerTables* peers, const int64_t
   return CTR_OK;
 }
 
-template <int LPR, int HOLD>
+template <int LPR, int HOLD, bool BI = false>
 static int launch_bwd(const float* tile, const float* d_tile, const float* d_fm2, int64_t B, int64_t F,
                       float* row_grads, cudaStream_t st) {
-  auto k = embed_fm2_bwd_kernel<LPR, HOLD>;
+  auto k = embed_fm2_bwd_kernel<LPR, HOLD, BI>;
   const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
   k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(tile), reinterpret_cast<const float4*>(d_tile), d_fm2,
                           (int)B, (int)F, reinterpret_cast<float4*>(row_grads));
@@ -357,14 +375,25 @@ static int launch_bwd(const float* tile, const float* d_tile, const float* d_fm2
   return CTR_OK;
 }
 
-template <int LPR>
+template <int LPR, bool BI = false>
 static int dispatch_bwd(const float* tile, const float* d_tile, const float* d_fm2, int64_t B, int64_t F,
                         float* row_grads, cudaStream_t st) {
   const int64_t per_lane = (F * LPR + 31) / 32;
-  if (per_lane <= 4) return launch_bwd<LPR, 4>(tile, d_tile, d_fm2, B, F, row_grads, st);
-  if (per_lane <= 8) return launch_bwd<LPR, 8>(tile, d_tile, d_fm2, B, F, row_grads, st);
-  if (per_lane <= 12) return launch_bwd<LPR, 12>(tile, d_tile, d_fm2, B, F, row_grads, st);
-  return launch_bwd<LPR, 0>(tile, d_tile, d_fm2, B, F, row_grads, st);
+  if (per_lane <= 4) return launch_bwd<LPR, 4, BI>(tile, d_tile, d_fm2, B, F, row_grads, st);
+  if (per_lane <= 8) return launch_bwd<LPR, 8, BI>(tile, d_tile, d_fm2, B, F, row_grads, st);
+  if (per_lane <= 12) return launch_bwd<LPR, 12, BI>(tile, d_tile, d_fm2, B, F, row_grads, st);
+  return launch_bwd<LPR, 0, BI>(tile, d_tile, d_fm2, B, F, row_grads, st);
+}
+
+template <int LPR>
+static int launch_fwd_bi(const float* table, const int64_t* off, const int64_t* ids, int64_t B, int64_t F, float* tile,
+                         float* bi, cudaStream_t st) {
+  auto k = embed_fm2_fwd_kernel<LPR, false, 4, 0, true>;
+  const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
+  k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), PeerTables{}, reinterpret_cast<const long long*>(off),
+                          reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), bi);
+  CTR_CHECK_LAUNCH("ctr_embed_bi_fwd");
+  return CTR_OK;
 }
 
 static int dispatch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const int64_t* ids, int64_t B,
@@ -525,4 +554,42 @@ extern "C" int ctr_first_order_fwd(const float* w, const int64_t* field_row_offs
                                                               bias, out);
   CTR_CHECK_LAUNCH("ctr_first_order_fwd");
   return CTR_OK;
+}
+
+// ---- NFM bi-interaction pooling: the same gather, (B, D) output instead of the FM2 scalar ------------------
+extern "C" int ctr_embed_bi_fwd(const float* table, const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F,
+                                int64_t D, float* tile, float* bi, void* stream) {
+  int rc = check_bfd("ctr_embed_bi_fwd", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(table && field_row_offset && ids && bi, "ctr_embed_bi_fwd: null table/field_row_offset/ids/bi");
+  CTR_REQUIRE(aligned16(table) && aligned16(tile) && aligned16(bi), "ctr_embed_bi_fwd: table, tile and bi must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  switch (D / 4) {
+    case 1: return launch_fwd_bi<1>(table, field_row_offset, ids, B, F, tile, bi, st);
+    case 2: return launch_fwd_bi<2>(table, field_row_offset, ids, B, F, tile, bi, st);
+    case 4: return launch_fwd_bi<4>(table, field_row_offset, ids, B, F, tile, bi, st);
+    case 8: return launch_fwd_bi<8>(table, field_row_offset, ids, B, F, tile, bi, st);
+    case 16: return launch_fwd_bi<16>(table, field_row_offset, ids, B, F, tile, bi, st);
+    default: return launch_fwd_bi<32>(table, field_row_offset, ids, B, F, tile, bi, st);
+  }
+}
+
+extern "C" int ctr_embed_bi_bwd(const float* tile, const float* d_tile, const float* d_bi, int64_t B, int64_t F, int64_t D,
+                                float* row_grads, void* stream) {
+  int rc = check_bfd("ctr_embed_bi_bwd", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(tile && d_bi && row_grads, "ctr_embed_bi_bwd: null tile/d_bi/row_grads");
+  CTR_REQUIRE(aligned16(tile) && aligned16(d_tile) && aligned16(d_bi) && aligned16(row_grads),
+              "ctr_embed_bi_bwd: tile, d_tile, d_bi and row_grads must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  switch (D / 4) {
+    case 1: return dispatch_bwd<1, true>(tile, d_tile, d_bi, B, F, row_grads, st);
+    case 2: return dispatch_bwd<2, true>(tile, d_tile, d_bi, B, F, row_grads, st);
+    case 4: return dispatch_bwd<4, true>(tile, d_tile, d_bi, B, F, row_grads, st);
+    case 8: return dispatch_bwd<8, true>(tile, d_tile, d_bi, B, F, row_grads, st);
+    case 16: return dispatch_bwd<16, true>(tile, d_tile, d_bi, B, F, row_grads, st);
+    default: return dispatch_bwd<32, true>(tile, d_tile, d_bi, B, F, row_grads, st);
+  }
 }

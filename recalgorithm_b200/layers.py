@@ -193,3 +193,30 @@ def fm_second_order(tables: autograd.EmbeddingTables, ids: torch.Tensor) -> Tupl
     """The lookup + FM second-order block of DeepFM/deepfm.py:184-200 in one kernel: per-field ids (B,F) ->
     (fields_embeddings as a (B,F,K) tile, fm_second_order_logit (B,1))."""
     return autograd.lookup_fm2(tables, ids)
+
+
+# --------------------------------------------------------------------------------------------------- NFM / FwFM / AFM (8f.4)
+def bi_interaction(tables: autograd.EmbeddingTables, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The lookup + bi-interaction pooling block of NFM/nfm.py:155-168 in one kernel: per-field ids (B,F) ->
+    (fields_embeddings (B,F,K), nfm (B,K)) -- the vector the reference then feeds to batch-norm / dropout / the DNN."""
+    return autograd.lookup_bi(tables, ids)
+
+
+def fwfm_second_order(fields_embeddings: torch.Tensor) -> torch.Tensor:
+    """FwFM/fwfm.py:145-158: creates ``fields_pair_strength/fields_pair_strength_weight`` (F(F-1)/2,) and returns
+    ``fwfm_second_order_logit`` (B,1) for the (B,F,K) field embeddings."""
+    F = int(fields_embeddings.shape[1])
+    with variable_scope("fields_pair_strength"):
+        r = get_variable("fields_pair_strength_weight", shape=(F * (F - 1) // 2,))
+    return autograd.fwfm(fields_embeddings, r)
+
+
+def afm_attention(fields_embeddings: torch.Tensor, embedding_dim: int, attention_factor: int) -> torch.Tensor:
+    """AFM/afm.py:152-186: attention-weighted sum of the pairwise hadamard products, (B,K).  Creates
+    ``attention_part/attention_{w,b,h}`` with the reference's shapes; ``p`` and the final matmul (afm.py:187-188) stay
+    with the caller."""
+    with variable_scope("attention_part"):
+        w = get_variable(name="attention_w", shape=(embedding_dim, attention_factor))
+        b = get_variable(name="attention_b", shape=(attention_factor,))
+        h = get_variable(name="attention_h", shape=(attention_factor, 1))
+    return autograd.afm(fields_embeddings, w, b, h)

@@ -292,3 +292,66 @@ def cin_bwd(x0, xk, filt, g_out):
     _lib.check(L.ctr_cin_bwd(_ptr(x0), _ptr(xk), _ptr(filt), _ptr(g_out), B, m, hk, D, H, _ptr(dx0), _ptr(dxk), _ptr(dw),
                              _ptr(ws), nbytes, _stream()))
     return dx0, dxk, dw
+
+
+# ------------------------------------------------------------------------------------ FM2 siblings
+def embed_bi_fwd(table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor, want_tile: bool = True):
+    """Fused lookup + NFM bi-interaction pooling.  Returns (tile (B,F,D) | None, bi (B,D))."""
+    B, F = ids.shape
+    D = table.shape[1]
+    _chk(table, F32, "table"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,)); _chk(ids, I64, "ids")
+    tile = torch.empty((B, F, D), dtype=F32, device=table.device) if want_tile else None
+    bi = torch.empty((B, D), dtype=F32, device=table.device)
+    _lib.check(_lib.lib().ctr_embed_bi_fwd(_ptr(table), _ptr(field_row_offset), _ptr(ids), B, F, D, _ptr(tile), _ptr(bi), _stream()))
+    return tile, bi
+
+
+def embed_bi_bwd(tile: torch.Tensor, d_tile: Optional[torch.Tensor], d_bi: torch.Tensor) -> torch.Tensor:
+    """IndexedSlices values (B,F,D): d_tile + d_bi[b,:] * (S - e)."""
+    B, F, D = tile.shape
+    _chk(tile, F32, "tile"); _chk(d_tile, F32, "d_tile", (B, F, D)); _chk(d_bi, F32, "d_bi", (B, D))
+    row_grads = torch.empty_like(tile)
+    _lib.check(_lib.lib().ctr_embed_bi_bwd(_ptr(tile), _ptr(d_tile), _ptr(d_bi), B, F, D, _ptr(row_grads), _stream()))
+    return row_grads
+
+
+def fwfm_fwd(tile: torch.Tensor, r: torch.Tensor) -> torch.Tensor:
+    """FwFM second-order logit (B,1).  tile (B,F,K); r (F(F-1)/2,) pair strengths in utils.index_from_upper_triangular order."""
+    B, F, K = tile.shape
+    _chk(tile, F32, "tile"); _chk(r, F32, "r", (F * (F - 1) // 2,))
+    out = torch.empty((B, 1), dtype=F32, device=tile.device)
+    _lib.check(_lib.lib().ctr_fwfm_fwd(_ptr(tile), _ptr(r), B, F, K, _ptr(out), _stream()))
+    return out
+
+
+def fwfm_bwd(tile: torch.Tensor, r: torch.Tensor, g: torch.Tensor):
+    B, F, K = tile.shape
+    g = g.reshape(B)
+    _chk(tile, F32, "tile"); _chk(r, F32, "r", (F * (F - 1) // 2,)); _chk(g, F32, "g", (B,))
+    d_tile, d_r = torch.empty_like(tile), torch.empty_like(r)
+    _lib.check(_lib.lib().ctr_fwfm_bwd(_ptr(tile), _ptr(r), _ptr(g), B, F, K, _ptr(d_tile), _ptr(d_r), _stream()))
+    return d_tile, d_r
+
+
+def afm_fwd(tile: torch.Tensor, w: torch.Tensor, b: torch.Tensor, h: torch.Tensor, want_score: bool = False):
+    """AFM attention pooling (B,K) (+ the (B,P) softmax scores).  w (K,T), b (T,), h (T,1) or (T,)."""
+    B, F, K = tile.shape
+    T = w.shape[1]
+    h = h.reshape(T)
+    _chk(tile, F32, "tile"); _chk(w, F32, "w", (K, T)); _chk(b, F32, "b", (T,)); _chk(h, F32, "h", (T,))
+    pooled = torch.empty((B, K), dtype=F32, device=tile.device)
+    score = torch.empty((B, F * (F - 1) // 2), dtype=F32, device=tile.device) if want_score else None
+    _lib.check(_lib.lib().ctr_afm_fwd(_ptr(tile), _ptr(w), _ptr(b), _ptr(h), B, F, K, T, _ptr(pooled), _ptr(score), _stream()))
+    return (pooled, score) if want_score else pooled
+
+
+def afm_bwd(tile, w, b, h, g_pooled):
+    B, F, K = tile.shape
+    T = w.shape[1]
+    h_shape = h.shape
+    h = h.reshape(T)
+    _chk(tile, F32, "tile"); _chk(w, F32, "w", (K, T)); _chk(b, F32, "b", (T,)); _chk(h, F32, "h", (T,)); _chk(g_pooled, F32, "g_pooled", (B, K))
+    d_tile, d_w, d_b, d_h = torch.empty_like(tile), torch.empty_like(w), torch.empty_like(b), torch.empty_like(h)
+    _lib.check(_lib.lib().ctr_afm_bwd(_ptr(tile), _ptr(w), _ptr(b), _ptr(h), _ptr(g_pooled), B, F, K, T, _ptr(d_tile), _ptr(d_w),
+                                      _ptr(d_b), _ptr(d_h), _stream()))
+    return d_tile, d_w, d_b, d_h.reshape(h_shape)

@@ -1,0 +1,128 @@
+"""GPU parity: the FM2 siblings of SURVEY 8f.4 -- NFM bi-interaction (fused with the lookup), FwFM pair-weighted FM2,
+AFM attention pooling -- vs the reference-executed golden vectors (inline model_fn blocks) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from _util import TOL, assert_close, dev, golden, trunc_normal
+from oracle import layers_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _table_from_tile(e):
+    """A table whose row (f, b) is e[b, f, :] and the ids that gather the tile back (lets golden tiles drive the fused lookup)."""
+    B, F, D = e.shape
+    table = np.ascontiguousarray(e.transpose(1, 0, 2).reshape(F * B, D))
+    off = np.arange(F + 1, dtype=np.int64) * B
+    ids = np.tile(np.arange(B, dtype=np.int64)[:, None], (1, F))
+    return table, off, ids
+
+
+@pytest.mark.parametrize("name", ["fm2_ref_F6_D8", "fm2_ref_F40_D32"])
+def test_fm2_reference_executed_golden(name):
+    from recalgorithm_b200 import ops
+    g = golden(name)
+    table, off, ids = _table_from_tile(g["e"])
+    tile, fm2 = ops.embed_fm2_fwd(dev(table), dev(off), dev(ids))
+    assert torch.equal(tile.cpu(), torch.from_numpy(g["e"]))                 # gathered rows bit-exact
+    assert_close(fm2, g["out_f64"], TOL, "fm2 vs deepfm.py:184-200 executed")
+
+
+@pytest.mark.parametrize("name", ["nfm_bi_F6_D8", "nfm_bi_F40_D32"])
+def test_bi_interaction_golden(name):
+    from recalgorithm_b200 import ops
+    g = golden(name)
+    table, off, ids = _table_from_tile(g["e"])
+    tile, bi = ops.embed_bi_fwd(dev(table), dev(off), dev(ids))
+    assert torch.equal(tile.cpu(), torch.from_numpy(g["e"]))
+    assert_close(bi, g["out_f64"], TOL, "bi-interaction vs nfm.py:155-168 executed")
+    _, bi2 = ops.embed_bi_fwd(dev(table), dev(off), dev(ids), want_tile=False)
+    assert torch.equal(bi, bi2)
+
+
+@pytest.mark.parametrize("B,F,D", [(5, 1, 4), (33, 7, 8), (64, 40, 32), (9, 70, 16), (3, 6, 128), (130, 33, 64)])
+def test_bi_interaction_fwd_bwd(B, F, D):
+    from recalgorithm_b200 import autograd
+    rng = np.random.default_rng(B * 7 + F + D)
+    rows = 11
+    tables = autograd.EmbeddingTables([rows] * F, D, device="cuda")
+    ids = rng.integers(-1, rows, size=(B, F)).astype(np.int64)                 # OOV ids -> zero rows
+    w = tables.weight.cpu().numpy()
+    off = tables.field_row_offset.cpu().numpy()
+    e = O.embedding_lookup(w, ids, off)
+    tile, bi = autograd.lookup_bi(tables, dev(ids))
+    assert torch.equal(tile.detach().cpu(), torch.from_numpy(e))
+    assert_close(bi, O.bi_interaction_fwd(e.astype(np.float64)), TOL, "bi")
+    d_tile = trunc_normal(rng, (B, F, D), 1.0); d_bi = trunc_normal(rng, (B, D), 1.0)
+    ((tile * dev(d_tile)).sum() + (bi * dev(d_bi)).sum()).backward()
+    want = d_tile.astype(np.float64) + O.bi_interaction_bwd(e.astype(np.float64), d_bi.astype(np.float64))
+    assert_close(tables.grad_slices[0].values, want, TOL, "row grads")
+
+
+@pytest.mark.parametrize("name", ["fwfm_F6_D8", "fwfm_F30_D16"])
+def test_fwfm_golden(name):
+    from recalgorithm_b200 import ops
+    g = golden(name)
+    assert_close(ops.fwfm_fwd(dev(g["e"]), dev(g["r"])), g["out_f64"], TOL, "fwfm vs fwfm.py:140-158 executed")
+
+
+@pytest.mark.parametrize("B,F,K", [(16, 2, 4), (37, 7, 8), (64, 40, 32), (5, 33, 3), (200, 30, 16), (3, 65, 10)])
+def test_fwfm_fwd_bwd(B, F, K):
+    from recalgorithm_b200 import ops
+    rng = np.random.default_rng(B + 3 * F + K)
+    e = trunc_normal(rng, (B, F, K), 1.0)
+    r = trunc_normal(rng, (F * (F - 1) // 2,), 0.5)
+    g = trunc_normal(rng, (B,), 1.0)
+    d = lambda a: a.astype(np.float64)
+    assert_close(ops.fwfm_fwd(dev(e), dev(r)), O.fwfm_fwd(d(e), d(r)), TOL, "fwd")
+    de, dr = ops.fwfm_bwd(dev(e), dev(r), dev(g))
+    ede, edr = O.fwfm_bwd(d(e), d(r), d(g))
+    assert_close(de, ede, TOL, "d_tile"); assert_close(dr, edr, TOL, "d_r")
+
+
+@pytest.mark.parametrize("name", ["afm_F5_D8_t4", "afm_F30_D16_t8"])
+def test_afm_golden(name):
+    from recalgorithm_b200 import ops
+    g = golden(name)
+    pooled, score = ops.afm_fwd(dev(g["e"]), dev(g["w"]), dev(g["b"]), dev(g["h"]), want_score=True)
+    assert_close(pooled, g["pooled_f64"], TOL, "pooled vs afm.py:152-186 executed")
+    assert_close(score, g["score_f64"][:, :, 0], TOL, "attention_score")
+    assert_close(pooled @ dev(g["p"]), g["logit_f64"], TOL, "afm_logit")
+
+
+# reference defaults: embedding_dim 8, attention_factor 128, 7 fields (AFM/afm.py:37-38)
+@pytest.mark.parametrize("B,F,K,T", [(1, 2, 4, 1), (70, 7, 8, 128), (33, 30, 16, 8), (5, 12, 32, 40), (9, 9, 8, 200), (17, 6, 16, 100),
+                                     (4, 40, 4, 256)])
+def test_afm_fwd_bwd(B, F, K, T):
+    from recalgorithm_b200 import ops
+    rng = np.random.default_rng(B + F + K + T)
+    e = trunc_normal(rng, (B, F, K), 1.0)
+    w = trunc_normal(rng, (K, T), 0.4); b = trunc_normal(rng, (T,), 0.3); h = trunc_normal(rng, (T, 1), 0.4)
+    g = trunc_normal(rng, (B, K), 1.0)
+    d = lambda a: a.astype(np.float64)
+    assert_close(ops.afm_fwd(dev(e), dev(w), dev(b), dev(h)), O.afm_fwd(d(e), d(w), d(b), d(h)), TOL, "pooled")
+    de, dw, db, dh = ops.afm_bwd(dev(e), dev(w), dev(b), dev(h), dev(g))
+    ede, edw, edb, edh = O.afm_bwd(e, w, b, h, g)
+    assert_close(de, ede, TOL, "d_tile"); assert_close(dw, edw, TOL, "d_w"); assert_close(db, edb, TOL, "d_b")
+    assert_close(dh, edh, TOL, "d_h")
+
+
+def test_pairwise_errors_and_layers_api():
+    from recalgorithm_b200 import _lib, layers as L, ops
+    e = torch.zeros((2, 5, 8), device="cuda")
+    with pytest.raises(ValueError):
+        ops.fwfm_fwd(e, torch.zeros((9,), device="cuda"))                       # r must have F(F-1)/2 = 10 entries
+    with pytest.raises(_lib.CtrError):
+        ops.afm_fwd(torch.zeros((2, 5, 12), device="cuda"), torch.zeros((12, 4), device="cuda"), torch.zeros(4, device="cuda"),
+                    torch.zeros(4, device="cuda"))                               # K = 12 unsupported
+    store = L.set_default_store(L.VariableStore(device="cuda", seed=3))
+    x = torch.randn((4, 5, 8), device="cuda", requires_grad=True)
+    logit = L.fwfm_second_order(x)
+    pooled = L.afm_attention(x, embedding_dim=8, attention_factor=16)
+    assert logit.shape == (4, 1) and pooled.shape == (4, 8)
+    assert {k: tuple(v.shape) for k, v in store.vars.items()} == {
+        "fields_pair_strength/fields_pair_strength_weight": (10,), "attention_part/attention_w": (8, 16),
+        "attention_part/attention_b": (16,), "attention_part/attention_h": (16, 1)}
+    (logit.sum() + pooled.sum()).backward()
+    assert x.grad is not None and all(v.grad is not None for v in store.vars.values())

@@ -23,7 +23,7 @@ def rel(a, b):
 
 def test_all_fixtures_present():
     names = {os.path.basename(p) for p in glob.glob(os.path.join(G, "*.npz"))}
-    assert len(names) == 14, names
+    assert len(names) == 22, names
 
 
 # ---------------------------------------------------------------- forward vs reference-executed golden
@@ -209,3 +209,67 @@ def test_senet_bilinear_bwd():
         dx, dw = O.bilinear_bwd(x, w, typ, gp)
         assert rel(dx, xt.grad.numpy()) < 1e-12, typ
         assert rel(dw, wt.grad.numpy()) < 1e-12, typ
+
+
+# ---------------------------------------------------------------- inline model_fn blocks executed from the reference
+@pytest.mark.parametrize("name", ["fm2_ref_F6_D8", "fm2_ref_F40_D32"])
+def test_fm2_matches_reference_executed(name):
+    g = load(name)
+    assert str(g["source"]).startswith("reference-executed:DeepFM/deepfm.py")
+    assert rel(O.fm2_fwd(g["e"]), g["out_f32"]) <= 2e-6
+    assert rel(O.fm2_fwd(g["e"].astype(np.float64)), g["out_f64"]) <= 1e-13
+
+
+@pytest.mark.parametrize("name", ["nfm_bi_F6_D8", "nfm_bi_F40_D32"])
+def test_bi_interaction_matches_reference_executed(name):
+    g = load(name)
+    assert rel(O.bi_interaction_fwd(g["e"]), g["out_f32"]) <= 2e-6
+    assert rel(O.bi_interaction_fwd(g["e"].astype(np.float64)), g["out_f64"]) <= 1e-13
+    # FM2 is its sum over K
+    assert rel(O.bi_interaction_fwd(g["e"].astype(np.float64)).sum(1, keepdims=True), O.fm2_fwd(g["e"].astype(np.float64))) <= 1e-13
+
+
+@pytest.mark.parametrize("name", ["fwfm_F6_D8", "fwfm_F30_D16"])
+def test_fwfm_matches_reference_executed(name):
+    g = load(name)
+    assert rel(O.fwfm_fwd(g["e"], g["r"]), g["out_f32"]) <= 2e-6
+    assert rel(O.fwfm_fwd(g["e"].astype(np.float64), g["r"].astype(np.float64)), g["out_f64"]) <= 1e-13
+
+
+@pytest.mark.parametrize("name", ["afm_F5_D8_t4", "afm_F30_D16_t8"])
+def test_afm_matches_reference_executed(name):
+    g = load(name)
+    e, w, b, h = (g[k].astype(np.float64) for k in ("e", "w", "b", "h"))
+    out, _, _, _, score = O.afm_fwd(e, w, b, h, return_all=True)
+    assert rel(out, g["pooled_f64"]) <= 1e-13 and rel(score, g["score_f64"]) <= 1e-13
+    assert rel(out @ g["p"].astype(np.float64), g["logit_f64"]) <= 1e-13
+    assert rel(O.afm_fwd(g["e"], g["w"], g["b"], g["h"]), g["pooled_f32"]) <= 5e-6
+
+
+def test_sibling_backward_vs_autograd():
+    rng = np.random.default_rng(11)
+    B, F, K, t = 4, 6, 8, 5
+    e = torch.tensor(rng.standard_normal((B, F, K)), requires_grad=True)
+    pairs = O.afm_pairs(F)
+    # NFM bi-interaction
+    gk = rng.standard_normal((B, K))
+    s = e.sum(1)
+    (0.5 * (s * s - (e * e).sum(1)) * torch.tensor(gk)).sum().backward()
+    assert rel(O.bi_interaction_bwd(e.detach().numpy(), gk), e.grad.numpy()) <= 1e-12
+    # FwFM
+    e.grad = None
+    r = torch.tensor(rng.standard_normal(len(pairs)), requires_grad=True)
+    g = rng.standard_normal(B)
+    out = sum(r[O.pair_index(i, j, F)] * (e[:, i] * e[:, j]).sum(1) for i, j in pairs)
+    (out * torch.tensor(g)).sum().backward()
+    de, dr = O.fwfm_bwd(e.detach().numpy(), r.detach().numpy(), g)
+    assert rel(de, e.grad.numpy()) <= 1e-12 and rel(dr, r.grad.numpy()) <= 1e-12
+    # AFM
+    e.grad = None
+    w, b, h = (torch.tensor(rng.standard_normal(sh), requires_grad=True) for sh in ((K, t), (t,), (t, 1)))
+    had = torch.stack([e[:, i] * e[:, j] for i, j in pairs], 1)
+    score = torch.softmax(torch.relu(had @ w + b) @ h, dim=1)
+    ((had * score).sum(1) * torch.tensor(gk)).sum().backward()
+    de, dw, db, dh = O.afm_bwd(e.detach().numpy(), w.detach().numpy(), b.detach().numpy(), h.detach().numpy(), gk)
+    for a, x in ((de, e), (dw, w), (db, b), (dh, h)):
+        assert rel(a, x.grad.numpy()) <= 1e-11

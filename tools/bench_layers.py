@@ -128,6 +128,21 @@ def main():
             m, bst = timeit(lambda: ops.bilinear_bwd(x, w, typ, gp), max(3, args.iters // 4), flush)
             emit(f"bilinear_bwd_{typ}", {"B": B, "F": F, "K": K}, m, bst, bytes_=B * (2 * F * K + P * K) * 4)
 
+    if "pairwise" in only:   # SURVEY 8f.4 siblings (FwFM at the config-5 tile shape; AFM at the reference's flag defaults and at F=30)
+        B, F, K = 65536, 40, 32
+        x, r, g1 = rn(B, F, K, std=0.2), rn(F * (F - 1) // 2, std=0.3), rn(B)
+        m_, bst = timeit(lambda: ops.fwfm_fwd(x, r), args.iters, flush)
+        emit("fwfm_fwd", {"B": B, "F": F, "K": K}, m_, bst, bytes_=B * F * K * 4, flops=2.0 * B * K * F * (F - 1) / 2)
+        m_, bst = timeit(lambda: ops.fwfm_bwd(x, r, g1), args.iters, flush)
+        emit("fwfm_bwd", {"B": B, "F": F, "K": K}, m_, bst, bytes_=2 * B * F * K * 4, flops=2.0 * B * K * (F * F + F * (F - 1) / 2))
+        for (B, F, K, T) in ((65536, 7, 8, 128), (8192, 30, 16, 8)):
+            x, w, b, h, gk = rn(B, F, K, std=0.5), rn(K, T, std=0.3), rn(T, std=0.1), rn(T, std=0.3), rn(B, K)
+            P = F * (F - 1) // 2
+            m_, bst = timeit(lambda: ops.afm_fwd(x, w, b, h), args.iters, flush)
+            emit("afm_fwd", {"B": B, "F": F, "K": K, "T": T}, m_, bst, bytes_=B * (F * K + K) * 4, flops=2.0 * B * P * (K * T + T + K))
+            m_, bst = timeit(lambda: ops.afm_bwd(x, w, b, h, gk), args.iters, flush)
+            emit("afm_bwd", {"B": B, "F": F, "K": K, "T": T}, m_, bst, bytes_=B * (2 * F * K + K) * 4, flops=2.0 * B * P * (4 * K * T + 2 * T + 4 * K))
+
     if "adam" in only:   # SURVEY 8f.3 at BASELINE config 5: the table update that follows the hot path
         from recalgorithm_b200 import autograd, optim
         rows = int(os.environ.get("CTR_BENCH_ROWS", 2_500_000))
