@@ -240,7 +240,17 @@ def run_ours(args, cfg):
         # Every rank holds the full table (it fits one GPU: 12.8 GB of 180 GB) => replicas, no exchange step.
         tables = autograd.EmbeddingTables([rows] * F, D, device=dev, init=None)
         tables.weight.normal_(0, D ** -0.5, generator=gen)
-    id_sets = [torch.randint(0, rows, (B, F), device=dev, generator=gen) for _ in range(NB)]
+    if args.ids == "zipf":
+        # SURVEY 8d config 5, second case: Zipf(1.05) over each field's vocabulary (hot rows are served by L2), drawn by
+        # inverse CDF; a fixed random permutation-free mapping (rank k -> row k) keeps the hot rows of a field adjacent.
+        cdf = torch.cumsum(torch.arange(1, rows + 1, device=dev, dtype=torch.float64) ** -1.05, 0)
+        cdf /= cdf[-1].clone()
+        id_sets = [torch.searchsorted(cdf, torch.rand((B, F), device=dev, generator=gen, dtype=torch.float64)).clamp_(max=rows - 1)
+                   for _ in range(NB)]
+        del cdf
+    else:
+        id_sets = [torch.randint(0, rows, (B, F), device=dev, generator=gen) for _ in range(NB)]
+    ids_desc = "Zipf(1.05) int64 (hot rows L2-resident: not the HBM worst case)" if args.ids == "zipf" else "uniform int64"
     d_tile = torch.randn((B, F, D), device=dev, generator=gen) * 0.01      # upstream grad of the deep part
     d_fm2 = torch.randn((B,), device=dev, generator=gen) * 0.01            # upstream grad of the logit
     tile = torch.empty((B, F, D), device=dev)
@@ -397,7 +407,7 @@ def run_ours(args, cfg):
     ach_step = (fwd_b + bwd_b) * B * args.steps / (ms_total * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")          # dram bytes/launch from the committed ncu capture
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.ids == "uniform":          # the ncu capture was taken on the default (uniform-id) run
         try:
             traffic = json.load(open(tp)).get(args.workload, {}).get("embed_fm2_fwd_dram_bytes_per_launch")
         except Exception:
@@ -407,7 +417,7 @@ def run_ours(args, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "model": cfg["model"], "global_batch": B * world, "B_per_gpu": B, "F": F,
-                   "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "ids": "uniform int64",
+                   "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "ids": ids_desc,
                    "parallelism": "replicated tables (12.8 GB fits one GPU), data-parallel ranks" if world > 1 else "1 GPU",
                    "l2": f"inputs larger than L2: {NB} rotating id batches over a {rows * F * D * 4 / 1e9:.1f} GB table; "
                          f"tile/d_tile/row_grads are {B * F * D * 4 / 1e6:.0f} MB each"},
@@ -438,6 +448,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="deepfm_cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
+                    help="id distribution of the synthetic batches (default: uniform = every row an HBM miss)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = WORKLOADS[args.workload]

@@ -232,6 +232,22 @@ int ctr_afm_fwd(const float* tile, const float* w, const float* b, const float* 
 int ctr_afm_bwd(const float* tile, const float* w, const float* b, const float* h, const float* g_pooled, int64_t B, int64_t F,
                 int64_t K, int64_t T, float* d_tile, float* d_w, float* d_b, float* d_h, void* stream);
 
+/* BST transformer block (BST/transformer_layer.py:6-79): queries/keys/values (B,T,d), keys_length (B,) int64 (mask t >= length,
+ * applied along the QUERY axis as the reference does, float32 collapse included), heads >= 1 (each projecting to d),
+ * position embedding rows [0,T) of a (max_length,d) table added to queries and keys.  params packed as
+ *   position_embedding (max_length,d) | w_q (H,d,d) | w_k | w_v | w_o (H*d,d) | LayerNorm beta,gamma (d,d) |
+ *   dense kernel (d,d), bias (d) | LayerNorm_1 beta,gamma        = ctr_bst_param_count(d, heads, max_length) floats.
+ * out (B,T,d).  Backward recomputes the forward; d_queries/d_keys/d_values (B,T,d) and d_params (same packing) are
+ * overwritten.  One CTA per sample: T <= 128, d <= 64, heads <= 16 and a shared-memory footprint <= 220 KB, else -2. */
+int64_t ctr_bst_param_count(int64_t d, int64_t heads, int64_t max_length);
+int ctr_bst_transformer_fwd(const float* queries, const float* keys, const float* values, const int64_t* keys_length,
+                            const float* params, int64_t B, int64_t T, int64_t d, int64_t heads, int64_t max_length,
+                            int use_position_embedding, float* out, void* stream);
+int ctr_bst_transformer_bwd(const float* queries, const float* keys, const float* values, const int64_t* keys_length,
+                            const float* params, const float* g_out, int64_t B, int64_t T, int64_t d, int64_t heads,
+                            int64_t max_length, int use_position_embedding, float* d_queries, float* d_keys, float* d_values,
+                            float* d_params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

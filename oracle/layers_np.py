@@ -487,3 +487,60 @@ def adam_sparse_apply(var, m, v, rows, values, t, lr, beta1=0.9, beta2=0.999, ep
         v = beta2 * v + om2 * g * g
         var = var - lr_t * m / (np.sqrt(v) + eps)
     return var, m, v
+
+
+# ---- BST transformer block (BST/transformer_layer.py:6-79) -------------------------------------------------
+
+BST_PARAM_ORDER = ("position_embedding", "w_q", "w_k", "w_v", "w_o", "ln1_beta", "ln1_gamma", "dense_kernel", "dense_bias",
+                   "ln2_beta", "ln2_gamma")
+
+
+def bst_param_shapes(d, heads, max_length):
+    return {"position_embedding": (max_length, d), "w_q": (heads, d, d), "w_k": (heads, d, d), "w_v": (heads, d, d),
+            "w_o": (heads * d, d), "ln1_beta": (d,), "ln1_gamma": (d,), "dense_kernel": (d, d), "dense_bias": (d,),
+            "ln2_beta": (d,), "ln2_gamma": (d,)}
+
+
+def _layer_norm_td(x, beta, gamma):
+    """tf.contrib.layers.layer_norm defaults on (B,T,d): moments over T AND d, params over d, eps 1e-12 [TF-internal]."""
+    mean = x.mean(axis=(1, 2), keepdims=True)
+    var = np.mean(np.square(x - mean), axis=(1, 2), keepdims=True)
+    inv = (1.0 / np.sqrt(var + 1e-12)) * gamma
+    return x * inv + (beta - mean * inv)
+
+
+def bst_transformer_fwd(queries, keys, values, keys_length, p, heads, use_position_embedding=True):
+    """One BST transformer block, float64 except where the reference's float32 arithmetic changes the RESULT:
+
+    transformer_layer.py:28-37  queries/keys += position_embedding[0:T]  (values untouched; the residual at :71 uses the
+                                 position-embedded queries because `queries +=` rebinds the name)
+    :40-48   per head h: Q = xq @ w_q[h], K = xk @ w_k[h], V = v @ w_v[h], each (T, d)  (d_model == d_k per head)
+    :52-57   keys_mask = (1 - sequence_mask(keys_length, T)) * (-2**32 + 1), expanded to (B,1,T,1): it is added along the
+             QUERY axis, i.e. the same constant to every entry of a masked row.  Mathematically a no-op for the row softmax;
+             in float32 (what the reference runs in) x + (-4294967296) rounds to the same value for every |x| < 256, so a
+             masked query row attends UNIFORMLY (1/T).  That float32 effect is reproduced here (the add is done in float32).
+    :60-63   softmax(Q K^T / sqrt(d_k) + mask) @ V ;  :66-68 heads concatenated (T, heads*d) @ w_o
+    :71-72   layer_norm(all_heads + queries) ; :75-76 leakyrelu(dense(net)) with leak 0.01 ; :78-79 layer_norm(ffn + net).
+    """
+    q = np.asarray(queries, dtype=np.float64); k = np.asarray(keys, dtype=np.float64); v = np.asarray(values, dtype=np.float64)
+    P = {n: np.asarray(a, dtype=np.float64) for n, a in p.items()}
+    B, T, d = q.shape
+    if use_position_embedding:
+        q = q + P["position_embedding"][None, :T, :]
+        k = k + P["position_embedding"][None, :T, :]
+    masked = (np.arange(T)[None, :] >= np.asarray(keys_length)[:, None])                       # (B,T) query rows
+    maskval = np.float32(-2 ** 32 + 1)
+    heads_out = []
+    for h in range(heads):
+        Q = q @ P["w_q"][h]; K = k @ P["w_k"][h]; V = v @ P["w_v"][h]
+        S = (Q @ K.transpose(0, 2, 1)) / np.sqrt(d)
+        S32 = (S.astype(np.float32) + maskval).astype(np.float64)                             # float32 add, see docstring
+        S = np.where(masked[:, :, None], S32, S)
+        S = S - S.max(axis=-1, keepdims=True)
+        A = np.exp(S); A = A / A.sum(axis=-1, keepdims=True)
+        heads_out.append(A @ V)
+    all_heads = np.concatenate(heads_out, axis=-1) @ P["w_o"]
+    net = _layer_norm_td(all_heads + q, P["ln1_beta"], P["ln1_gamma"])
+    f = net @ P["dense_kernel"] + P["dense_bias"]
+    f = 0.5 * (1 + 0.01) * f + 0.5 * (1 - 0.01) * np.abs(f)                                   # BST/leakyrelu.py:4-16
+    return _layer_norm_td(f + net, P["ln2_beta"], P["ln2_gamma"])

@@ -308,6 +308,38 @@ def gen_inline():
              source="reference-executed:AFM/afm.py:152-188")
 
 
+def gen_bst():
+    """BST/transformer_layer.py imported verbatim (it does `from leakyrelu import leakyrelu`: BST/ goes on sys.path)."""
+    from oracle import layers_np as O
+    sys.path.insert(0, os.path.join(REF, "BST"))
+    ref_bst = _load("BST/transformer_layer.py", "ref_bst_transformer")
+    rng = np.random.default_rng(1357)
+    for name, (B, T, d, H, maxlen, lengths) in {"bst_T3_smoke": (2, 3, 4, 3, 5, [0, 1]),               # the file's own __main__ shapes
+                                                 "bst_T51_d8_h3": (6, 51, 8, 3, 51, [51, 1, 17, 0, 50, 33]),
+                                                 "bst_T20_d16_h2": (4, 20, 16, 2, 24, [20, 7, 0, 13])}.items():
+        x = trunc_normal(rng, (B, T, d), 1.0)
+        shapes = O.bst_param_shapes(d, H, maxlen)
+        p = {"position_embedding": trunc_normal(rng, shapes["position_embedding"], 0.3),
+             "w_q": glorot(rng, shapes["w_q"]), "w_k": glorot(rng, shapes["w_k"]), "w_v": glorot(rng, shapes["w_v"]),
+             "w_o": glorot(rng, shapes["w_o"]), "ln1_beta": trunc_normal(rng, (d,), 0.1), "ln1_gamma": 1 + trunc_normal(rng, (d,), 0.1),
+             "dense_kernel": glorot(rng, (d, d)), "dense_bias": trunc_normal(rng, (d,), 0.1),
+             "ln2_beta": trunc_normal(rng, (d,), 0.1), "ln2_gamma": 1 + trunc_normal(rng, (d,), 0.1)}
+        variables = {"position_embedding": p["position_embedding"], "w_q_0": p["w_q"], "w_k_0": p["w_k"], "w_v_0": p["w_v"],
+                     "w_o_0": p["w_o"], "LayerNorm/beta": p["ln1_beta"], "LayerNorm/gamma": p["ln1_gamma"],
+                     "dense/kernel": p["dense_kernel"], "dense/bias": p["dense_bias"],
+                     "LayerNorm_1/beta": p["ln2_beta"], "LayerNorm_1/gamma": p["ln2_gamma"]}
+        klen = np.asarray(lengths, dtype=np.int64)
+
+        def fn(dt):
+            t = tf.Tensor(x.astype(dt))
+            return ref_bst.bst_transformer(queries=t, keys=t, values=t, keys_length=tf.Tensor(klen), heads=H, index=0,
+                                           max_length=maxlen, use_position_embedding=True).a
+        outs, created = run_both(fn, variables)
+        assert created == {k: tuple(np.shape(v)) for k, v in variables.items()}, created
+        save(name, x=x, keys_length=klen, heads=np.int64(H), max_length=np.int64(maxlen), out_f32=outs["f32"], out_f64=outs["f64"],
+             **{f"p_{k}": v for k, v in p.items()}, source="reference-executed:BST/transformer_layer.py:6-79")
+
+
 if __name__ == "__main__":
     gen_cross()
     gen_cin()
@@ -315,3 +347,4 @@ if __name__ == "__main__":
     gen_fibinet()
     gen_restated()
     gen_inline()
+    gen_bst()

@@ -39,6 +39,7 @@ class _State:
     scope: list = []
     variables: dict = {}     # full name -> ndarray (injected by the caller, or created + recorded)
     created: dict = {}       # name -> shape, for every get_variable call (so tests can check shapes)
+    uniq: dict = {}          # scope-name counters for layers that uniquify their scope (LayerNorm, LayerNorm_1, ...)
     rng = _np.random.default_rng(0)
 
 
@@ -50,6 +51,7 @@ def reset(dtype=_np.float32, variables=None, seed=0):
     _STATE.scope = []
     _STATE.variables = dict(variables or {})
     _STATE.created = {}
+    _STATE.uniq = {}
     _STATE.rng = _np.random.default_rng(seed)
 
 
@@ -237,10 +239,20 @@ def einsum(eq, *ops):
     return Tensor(_np.einsum(eq.replace(" ", ""), *[_arr(o) for o in ops]))
 
 
-def sequence_mask(lengths, maxlen):
-    """tf.sequence_mask(len, T)[b, t] = t < len[b]  (bool)."""
+def sequence_mask(lengths, maxlen, dtype=None):
+    """tf.sequence_mask(len, T)[b, t] = t < len[b]  (bool, or cast to `dtype` -- an EXPLICIT tf.float32 stays float32 even in
+    the float64 anchor run, as it would in TF)."""
     L = _arr(lengths)
-    return Tensor(_np.arange(int(_arr(maxlen)))[None, :] < L[:, None])
+    m = _np.arange(int(_arr(maxlen)))[None, :] < L[:, None]
+    return Tensor(m if dtype is None else m.astype(dtype))
+
+
+def range(n):                                  # noqa: A001  (tf.range)
+    return Tensor(_np.arange(int(_arr(n))))
+
+
+def abs(a):                                    # noqa: A001  (tf.abs)
+    return Tensor(_np.abs(_arr(a)))
 
 
 def random_normal(shape, seed=None):
@@ -258,6 +270,11 @@ class _NN:
         x = x - x.max(axis=axis, keepdims=True)
         e = _np.exp(x)
         return Tensor(e / e.sum(axis=axis, keepdims=True))
+
+    @staticmethod
+    def embedding_lookup(params, ids):
+        """tf.nn.embedding_lookup(table, ids) = table[ids] (single dense table)."""
+        return Tensor(_arr(params)[_arr(ids)])
 
     @staticmethod
     def conv1d(value, filters, stride, padding):
@@ -289,6 +306,38 @@ class _Layers:
 
 
 layers = _Layers()
+
+
+class _ContribLayers:
+    @staticmethod
+    def layer_norm(inputs, center=True, scale=True, begin_norm_axis=1, begin_params_axis=-1, scope=None):
+        """tf.contrib.layers.layer_norm (TF 1.14 defaults): moments over axes [begin_norm_axis:] -- for a (B,T,d) input that
+        is T AND d together --, beta (zeros) / gamma (ones) of shape inputs.shape[begin_params_axis:] in variable scope
+        'LayerNorm' (uniquified 'LayerNorm_1', ... on later calls in the same scope), then
+        tf.nn.batch_normalization(x, mean, var, beta, gamma, variance_epsilon=1e-12):
+        inv = rsqrt(var + eps) * gamma;  y = x * inv + (beta - mean * inv)."""
+        x = _arr(inputs)
+        base = _full_name(scope or "LayerNorm")
+        n = _STATE.uniq.get(base, 0)
+        _STATE.uniq[base] = n + 1
+        with variable_scope((scope or "LayerNorm") + (f"_{n}" if n else "")):
+            pshape = x.shape[begin_params_axis:]
+            for nm, init in (("beta", _np.zeros), ("gamma", _np.ones)):
+                if _full_name(nm) not in _STATE.variables:
+                    _STATE.variables[_full_name(nm)] = init(pshape)
+            beta, gamma = get_variable("beta", shape=pshape).a, get_variable("gamma", shape=pshape).a
+        axes = tuple(_np.arange(begin_norm_axis, x.ndim))
+        mean = x.mean(axis=axes, keepdims=True)
+        var = _np.mean(_np.square(x - mean), axis=axes, keepdims=True)
+        inv = (1.0 / _np.sqrt(var + x.dtype.type(1e-12))) * gamma
+        return Tensor(x * inv + (beta - mean * inv))
+
+
+class _Contrib:
+    layers = _ContribLayers()
+
+
+contrib = _Contrib()
 
 
 class _KerasBackend:

@@ -45,6 +45,9 @@ SIGNATURES = {
     "ctr_fwfm_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ctr_afm_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ctr_afm_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ctr_bst_param_count": (_I, [_I, _I, _I]),
+    "ctr_bst_transformer_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_int, _P, _P]),
+    "ctr_bst_transformer_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_int, _P, _P, _P, _P, _P]),
     "ctr_adam_indexed_slices": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _I, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, _P, _P, _P]),
     "ctr_adam_dense_rest": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P]),

@@ -248,3 +248,28 @@ class _AFM(torch.autograd.Function):
 
 def afm(tile: torch.Tensor, w: torch.Tensor, b: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
     return _AFM.apply(tile, w, b, h)
+
+
+class _BstTransformer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, queries, keys, values, keys_length, heads, max_length, use_pos, *params):
+        d = queries.shape[-1]
+        packed = ops.bst_pack_params(dict(zip(ops.BST_PARAM_ORDER, params)), d, heads, max_length)
+        queries, keys, values = queries.contiguous(), keys.contiguous(), values.contiguous()
+        ctx.save_for_backward(queries, keys, values, keys_length, packed)
+        ctx.cfg = (heads, max_length, use_pos, d)
+        return ops.bst_transformer_fwd(queries, keys, values, keys_length, packed, heads, max_length, use_pos)
+
+    @staticmethod
+    def backward(ctx, g):
+        queries, keys, values, keys_length, packed = ctx.saved_tensors
+        heads, max_length, use_pos, d = ctx.cfg
+        dq, dk, dv, dp = ops.bst_transformer_bwd(queries, keys, values, keys_length, packed, g.contiguous(), heads, max_length, use_pos)
+        grads = ops.bst_unpack_params(dp, d, heads, max_length)
+        return (dq, dk, dv, None, None, None, None) + tuple(grads[n] for n in ops.BST_PARAM_ORDER)
+
+
+def bst_transformer(queries, keys, values, keys_length, params: dict, heads: int, max_length: int, use_position_embedding=True):
+    """params: dict with the names of ops.BST_PARAM_ORDER."""
+    return _BstTransformer.apply(queries, keys, values, keys_length, heads, max_length, use_position_embedding,
+                                 *[params[n] for n in ops.BST_PARAM_ORDER])

@@ -220,3 +220,25 @@ def afm_attention(fields_embeddings: torch.Tensor, embedding_dim: int, attention
         b = get_variable(name="attention_b", shape=(attention_factor,))
         h = get_variable(name="attention_h", shape=(attention_factor, 1))
     return autograd.afm(fields_embeddings, w, b, h)
+
+
+# --------------------------------------------------------------------------------------------------- BST (8f.4)
+def bst_transformer(queries: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, keys_length: torch.Tensor, heads: int,
+                    index: int, max_length: int, use_position_embedding: bool = True) -> torch.Tensor:
+    """Transformer block -- same signature as BST/transformer_layer.py:6.  Variables carry the names TF gives them inside
+    the caller's scope (``transformer_part`` in BST/bst.py:184): ``position_embedding`` (shared by every block),
+    ``w_{q,k,v,o}_{index}``, ``LayerNorm[/_n]/{beta,gamma}`` and ``dense[/_n]/{kernel,bias}`` with TF's uniquifying suffixes
+    for block ``index`` (two layer norms and one dense per block)."""
+    d = int(queries.shape[-1])
+    suffix = lambda base, n: base if n == 0 else f"{base}_{n}"
+    ones, zeros = (lambda s: torch.ones(s)), (lambda s: torch.zeros(s))
+    p = {"position_embedding": get_variable(name="position_embedding", shape=(max_length, d)),
+         "w_q": get_variable(name=f"w_q_{index}", shape=(heads, d, d)), "w_k": get_variable(name=f"w_k_{index}", shape=(heads, d, d)),
+         "w_v": get_variable(name=f"w_v_{index}", shape=(heads, d, d)), "w_o": get_variable(name=f"w_o_{index}", shape=(heads * d, d))}
+    with variable_scope(suffix("LayerNorm", 2 * index)):
+        p["ln1_beta"] = get_variable("beta", (d,), initializer=zeros); p["ln1_gamma"] = get_variable("gamma", (d,), initializer=ones)
+    with variable_scope(suffix("dense", index)):
+        p["dense_kernel"] = get_variable("kernel", (d, d)); p["dense_bias"] = get_variable("bias", (d,), initializer=zeros)
+    with variable_scope(suffix("LayerNorm", 2 * index + 1)):
+        p["ln2_beta"] = get_variable("beta", (d,), initializer=zeros); p["ln2_gamma"] = get_variable("gamma", (d,), initializer=ones)
+    return autograd.bst_transformer(queries, keys, values, keys_length.to(torch.int64), p, heads, max_length, use_position_embedding)

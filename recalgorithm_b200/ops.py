@@ -355,3 +355,66 @@ def afm_bwd(tile, w, b, h, g_pooled):
     _lib.check(_lib.lib().ctr_afm_bwd(_ptr(tile), _ptr(w), _ptr(b), _ptr(h), _ptr(g_pooled), B, F, K, T, _ptr(d_tile), _ptr(d_w),
                                       _ptr(d_b), _ptr(d_h), _stream()))
     return d_tile, d_w, d_b, d_h.reshape(h_shape)
+
+
+# ------------------------------------------------------------------------------------ BST transformer block
+BST_PARAM_ORDER = ("position_embedding", "w_q", "w_k", "w_v", "w_o", "ln1_beta", "ln1_gamma", "dense_kernel", "dense_bias",
+                   "ln2_beta", "ln2_gamma")
+
+
+def bst_param_shapes(d: int, heads: int, max_length: int):
+    return {"position_embedding": (max_length, d), "w_q": (heads, d, d), "w_k": (heads, d, d), "w_v": (heads, d, d),
+            "w_o": (heads * d, d), "ln1_beta": (d,), "ln1_gamma": (d,), "dense_kernel": (d, d), "dense_bias": (d,),
+            "ln2_beta": (d,), "ln2_gamma": (d,)}
+
+
+def bst_pack_params(params: dict, d: int, heads: int, max_length: int) -> torch.Tensor:
+    """dict of named tensors -> the packed float buffer of ctr_bst_transformer_* (include/ctr_b200.h)."""
+    shapes = bst_param_shapes(d, heads, max_length)
+    parts = []
+    for name in BST_PARAM_ORDER:
+        t = params[name]
+        if tuple(t.shape) != shapes[name]:
+            raise ValueError(f"{name}: expected shape {shapes[name]}, got {tuple(t.shape)}")
+        parts.append(t.reshape(-1))
+    packed = torch.cat(parts).contiguous()
+    assert packed.numel() == _lib.lib().ctr_bst_param_count(d, heads, max_length)
+    return packed
+
+
+def bst_unpack_params(packed: torch.Tensor, d: int, heads: int, max_length: int) -> dict:
+    out, o = {}, 0
+    for name, shp in bst_param_shapes(d, heads, max_length).items():
+        n = 1
+        for x in shp:
+            n *= x
+        out[name] = packed[o:o + n].reshape(shp)
+        o += n
+    return out
+
+
+def _bst_args(queries, keys, values, keys_length, packed, heads, max_length):
+    B, T, d = queries.shape
+    _chk(queries, F32, "queries"); _chk(keys, F32, "keys", (B, T, d)); _chk(values, F32, "values", (B, T, d))
+    _chk(keys_length, I64, "keys_length", (B,))
+    _chk(packed, F32, "params", (int(_lib.lib().ctr_bst_param_count(d, heads, max_length)),))
+    return B, T, d
+
+
+def bst_transformer_fwd(queries, keys, values, keys_length, packed, heads: int, max_length: int, use_position_embedding: bool = True):
+    B, T, d = _bst_args(queries, keys, values, keys_length, packed, heads, max_length)
+    out = torch.empty_like(queries)
+    _lib.check(_lib.lib().ctr_bst_transformer_fwd(_ptr(queries), _ptr(keys), _ptr(values), _ptr(keys_length), _ptr(packed), B, T, d,
+                                                  heads, max_length, int(use_position_embedding), _ptr(out), _stream()))
+    return out
+
+
+def bst_transformer_bwd(queries, keys, values, keys_length, packed, g_out, heads: int, max_length: int,
+                        use_position_embedding: bool = True):
+    B, T, d = _bst_args(queries, keys, values, keys_length, packed, heads, max_length)
+    _chk(g_out, F32, "g_out", (B, T, d))
+    dq, dk, dv, dp = torch.empty_like(queries), torch.empty_like(queries), torch.empty_like(queries), torch.empty_like(packed)
+    _lib.check(_lib.lib().ctr_bst_transformer_bwd(_ptr(queries), _ptr(keys), _ptr(values), _ptr(keys_length), _ptr(packed),
+                                                  _ptr(g_out), B, T, d, heads, max_length, int(use_position_embedding), _ptr(dq),
+                                                  _ptr(dk), _ptr(dv), _ptr(dp), _stream()))
+    return dq, dk, dv, dp

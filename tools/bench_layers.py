@@ -143,6 +143,17 @@ def main():
             m_, bst = timeit(lambda: ops.afm_bwd(x, w, b, h, gk), args.iters, flush)
             emit("afm_bwd", {"B": B, "F": F, "K": K, "T": T}, m_, bst, bytes_=B * (2 * F * K + K) * 4, flops=2.0 * B * P * (4 * K * T + 2 * T + 4 * K))
 
+    if "bst" in only:   # BST defaults: 50-step history + target = 51 positions, d = 8, 3 heads (BST/bst.py:45-47), batch 4096
+        for (B, T, d, H) in ((4096, 51, 8, 3), (4096, 51, 16, 3)):
+            x, g = rn(B, T, d), rn(B, T, d)
+            klen = torch.randint(1, T + 1, (B,), device="cuda", generator=gen)
+            packed = rn(int(ops._lib.lib().ctr_bst_param_count(d, H, T)), std=0.3)
+            flops = 2.0 * B * (3 * H * T * d * d + 2 * H * T * T * d + H * T * d * d + T * d * d)
+            m_, bst = timeit(lambda: ops.bst_transformer_fwd(x, x, x, klen, packed, H, T), args.iters, flush)
+            emit("bst_transformer_fwd", {"B": B, "T": T, "d": d, "heads": H}, m_, bst, bytes_=2 * B * T * d * 4, flops=flops)
+            m_, bst = timeit(lambda: ops.bst_transformer_bwd(x, x, x, klen, packed, g, H, T), args.iters, flush)
+            emit("bst_transformer_bwd", {"B": B, "T": T, "d": d, "heads": H}, m_, bst, bytes_=5 * B * T * d * 4, flops=3 * flops)
+
     if "adam" in only:   # SURVEY 8f.3 at BASELINE config 5: the table update that follows the hot path
         from recalgorithm_b200 import autograd, optim
         rows = int(os.environ.get("CTR_BENCH_ROWS", 2_500_000))
