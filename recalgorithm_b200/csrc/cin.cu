@@ -86,6 +86,24 @@ __device__ __forceinline__ int bfly_step(float (&acc)[N], int lane, int o) {
 // top producer stall.  A now goes registers -> TMEM (tcgen05.st; the row-owning thread IS the TMEM lane) and the MMA
 // runs in TS mode (A from TMEM, B from shared memory), so shared memory only carries the filter tiles.
 //   TMEM columns: [0, TILES*NP) accumulators | [256, 512) A staging: stage sa, tile t at 256 + (sa*TILES + t)*32*NA (+32 = lo)
+// Work items of the persistent forward kernel.  A CTA normally processes PAIRS of 128-row M-tiles (both share every filter
+// stage); with n128 tiles and G CTAs that quantises to ceil(n128 / 2G) rounds (config 3: 3.46 -> 4 rounds, 13 % idle).
+// The last round therefore hands out what is left as evenly as possible: full pairs to the first CTAs, SINGLE tiles to
+// the rest (the second M-tile's warps then only keep the barriers in phase), so the tail costs half a round when it can.
+struct FwdItem { int tile0, nt; };                   // first 128-row tile, number of M-tiles (0: nothing for this CTA)
+__device__ __forceinline__ int fwd_num_items(int n128) {
+  const int G = (int)gridDim.x, R = (n128 / 2) / G;
+  return R + (n128 - 2 * R * G > 0 ? 1 : 0);
+}
+__device__ __forceinline__ FwdItem fwd_item(int it, int n128) {
+  const int G = (int)gridDim.x, c = (int)blockIdx.x, R = (n128 / 2) / G;
+  if (it < R) return FwdItem{2 * (c + it * G), 2};
+  const int base = 2 * R * G, rem = n128 - base;      // 0 < rem < 2G
+  if (rem <= G) return FwdItem{base + c, c < rem ? 1 : 0};
+  const int x = rem - G;                              // CTAs that still get a pair
+  return c < x ? FwdItem{base + 2 * c, 2} : FwdItem{base + 2 * x + (c - x), 1};
+}
+
 template <int PASSES, int SB, int NPT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ x0,
@@ -109,7 +127,8 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = 1 << logD;
   const long long rows_total = (long long)B * D;
-  const int num_tiles = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
+  const int n128 = (int)((rows_total + BM - 1) / BM);
+  const int n_items = fwd_num_items(n128);
   const int nch = (hk + chunk - 1) / chunk;
 
   if (threadIdx.x == 0) {
@@ -140,13 +159,13 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
     int sa = 0, pha = 0;
     uint32_t g = 0;                                   // chunk counter (same sequence as the MMA warp)
     float acc[NPT];
-    auto drain = [&](uint32_t gi) {                   // add finished chunk gi into acc, then hand TMEM back
+    auto drain = [&](uint32_t gi, bool on) {          // add finished chunk gi into acc, then hand TMEM back
       mbar_wait(acc_full, gi & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_sel + (uint32_t)(t * NP);
 #pragma unroll
       for (int c0 = 0; c0 < NPT; c0 += 32) {            // two 16-column loads in flight per wait
-        if (c0 < NP) {
+        if (c0 < NP && on) {
           uint32_t v0[16], v1[16];
           tmem_ld16_nowait(taddr + c0, v0);
           if (c0 + 16 < NP) tmem_ld16_nowait(taddr + c0 + 16, v1);
@@ -163,9 +182,12 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
     };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long r = (long long)tile * (TILES * BM) + t * BM + (warp & 3) * 32 + lane;
-      const bool valid = r < rows_total;
+    for (int it = 0; it < n_items; ++it) {
+      const FwdItem item = fwd_item(it, n128);
+      if (item.nt == 0) continue;
+      const bool on = t < item.nt;                     // single-tile item: the second M-tile's warps only keep the barriers in phase
+      const long long r = (long long)(item.tile0 + t) * BM + (warp & 3) * 32 + lane;
+      const bool valid = on && r < rows_total;
       const int b = valid ? (int)(r >> logD) : 0;
       const int d = (int)(r & (D - 1));
       float x0v[KB];
@@ -184,6 +206,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
           mbar_wait(empty_a(sa), pha ^ 1);
           tc_fence_after();
           const uint32_t a_hi = a_stage0 + lane_sel + (uint32_t)((sa * TILES + t) * KB * NA);
+          if (on) {
 #pragma unroll
           for (int part = 0; part < KB / 8; ++part) {
             float p[8];
@@ -202,14 +225,15 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
             }
           }
           tmem_wait_st();
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_a(sa));
           if (++sa == SA) { sa = 0; pha ^= 1; }
-          if (c > 0 && i - i_beg + 1 == drain_at) drain(g - 1);
+          if (c > 0 && i - i_beg + 1 == drain_at) drain(g - 1, on);
         }
       }
-      drain(g - 1);
+      drain(g - 1, on);
       // ---------------- epilogue: registers -> out (B,H,D) and pooled (B,H) ----------------
 #pragma unroll
       for (int n = 0; n < NPT; ++n)
@@ -232,7 +256,8 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
     // ============================ TMA producer for the filter tiles ============================
     if (lane == 0) {
       int s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < n_items; ++it) {
+        if (fwd_item(it, n128).nt == 0) continue;
         for (int i = 0; i < hk; ++i) {
           mbar_wait(empty_b(s), ph ^ 1);
           const uint32_t b_dst = sbase + s * L.stage_bytes;
@@ -249,7 +274,9 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
       const uint32_t idesc = umma_idesc_tf32(NP);
       int sb = 0, phb = 0, sa = 0, pha = 0;
       uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < n_items; ++it) {
+        const int nt = fwd_item(it, n128).nt;
+        if (nt == 0) continue;
         for (int c = 0; c < nch; ++c, ++g) {
           mbar_wait(acc_empty, (g & 1u) ^ 1u);                 // previous chunk has been drained out of TMEM
           tc_fence_after();
@@ -264,6 +291,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
             const uint64_t b_lo = umma_desc_sw128(st_base + L.b_tile_bytes);
 #pragma unroll
             for (int tt = 0; tt < TILES; ++tt) {
+              if (tt >= nt) break;
               const uint32_t a_hi = a_stage0 + (uint32_t)((sa * TILES + tt) * KB * NA);
               const uint32_t a_lo = a_hi + KB;
               const uint32_t dcol = tmem_base + (uint32_t)(tt * NP);
@@ -483,8 +511,8 @@ extern "C" int ctr_cin_fwd(const float* x0, const float* xk, const float* filter
   int logD = 0;
   while ((1 << logD) < D) ++logD;
   const long long rows_total = (long long)B * D;
-  const int num_tiles = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
-  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  const int num_pairs = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
+  const int grid = num_pairs < sm_count() ? num_pairs : sm_count();
 #define CIN_LAUNCH(PASSES_, SB_, NPT_, CHUNK_)                                                                        \
   {                                                                                                                   \
     const FwdSmem L = fwd_smem(NP, PASSES_, SB_);                                                                     \

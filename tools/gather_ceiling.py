@@ -58,6 +58,22 @@ def main():
         ms = t(fn)
         print(json.dumps({"variant": name, "ms": ms, "algorithmic_GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
                           "hbm_peak_GBps": peak}), flush=True)
+    if "--sweep" in sys.argv:
+        # same number of bytes gathered, different row widths: is the random-read rate per ACCESS (row activations) or per byte?
+        del tables, tile, out2, flat
+        torch.cuda.empty_cache()
+        for Dw in (16, 32, 64, 128):
+            Fw = 40 * 32 // Dw
+            rows_w = rows * 32 // Dw // (Fw // 40) if Fw >= 40 else rows * 32 // Dw * (40 // Fw)
+            tb = autograd.EmbeddingTables([rows_w] * Fw, Dw, device="cuda", init=None)
+            tb.weight.normal_(0, 1, generator=gen)
+            idw = [torch.randint(0, rows_w, (B, Fw), device="cuda", generator=gen) for _ in range(8)]
+            ms = t(lambda: ops.embed_fm2_fwd(tb.weight, tb.field_row_offset, idw[k[0] % 8], want_tile=False, fm2=fm2))
+            nb = B * Fw * (Dw * 4 + 8)
+            print(json.dumps({"variant": f"gather_only_row{Dw * 4}B", "F": Fw, "rows_per_field": rows_w, "table_GB": tb.weight.numel() * 4 / 1e9,
+                              "ms": ms, "algorithmic_GBps": nb / ms / 1e6, "row_reads_per_us": B * Fw / ms / 1e3}), flush=True)
+            del tb, idw
+            torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
