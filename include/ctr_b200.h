@@ -238,7 +238,7 @@ int ctr_afm_bwd(const float* tile, const float* w, const float* b, const float* 
  *   position_embedding (max_length,d) | w_q (H,d,d) | w_k | w_v | w_o (H*d,d) | LayerNorm beta,gamma (d,d) |
  *   dense kernel (d,d), bias (d) | LayerNorm_1 beta,gamma        = ctr_bst_param_count(d, heads, max_length) floats.
  * out (B,T,d).  Backward recomputes the forward; d_queries/d_keys/d_values (B,T,d) and d_params (same packing) are
- * overwritten.  One CTA per sample: T <= 128, d <= 64, heads <= 16 and a shared-memory footprint <= 220 KB, else -2. */
+ * overwritten.  One CTA per sample: d in {4,8,16,32,64}, T <= 128, heads <= 16 and a shared-memory footprint <= 220 KB, else -2. */
 int64_t ctr_bst_param_count(int64_t d, int64_t heads, int64_t max_length);
 int ctr_bst_transformer_fwd(const float* queries, const float* keys, const float* values, const int64_t* keys_length,
                             const float* params, int64_t B, int64_t T, int64_t d, int64_t heads, int64_t max_length,

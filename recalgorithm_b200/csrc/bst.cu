@@ -1,6 +1,6 @@
 // SURVEY.md 8f.4 -- BST transformer block (BST/transformer_layer.py:6-79), the sequence sibling of the DIN attention unit.
 //
-// One CTA (128 threads) per sample, every intermediate of the block in shared memory; the backward kernel recomputes the
+// One CTA (256 threads) per sample, every intermediate of the block in shared memory; the backward kernel recomputes the
 // forward (nothing but the layer's inputs is read from HBM) and keeps the weight gradients of the whole CTA in shared
 // memory (each element owned by one thread: no atomics until the final flush).  Shapes are tiny (T <= 64, d <= 32,
 // heads <= 8: BST runs T = 51, d = 8, 3 heads), so this is a CUDA-core kernel; the tensor pipe has nothing to chew on.
@@ -19,7 +19,7 @@
 
 namespace ctr {
 
-constexpr int BST_NT = 128;
+constexpr int BST_NT = 256;
 
 struct BstLayout {
   int pos, wq, wk, wv, wo, b1, g1, wd, bd, b2, g2, total;
@@ -42,35 +42,59 @@ __host__ __device__ inline BstLayout bst_layout(int d, int H, int maxlen) {
   return L;
 }
 
-// ---- tiny shared-memory GEMMs, all threads of the CTA --------------------------------------------------------------------
-// C[t][j] (=|+=) sum_k A[t][k] * B[k][j]
-__device__ __forceinline__ void mm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int T, int K, int N,
-                                      bool acc) {
-  for (int e = threadIdx.x; e < T * N; e += BST_NT) {
-    const int t = e / N, j = e - t * N;
-    float s = 0.f;
-    for (int k = 0; k < K; ++k) s = fmaf(A[t * lda + k], B[k * ldb + j], s);
-    C[t * ldc + j] = acc ? C[t * ldc + j] + s : s;
+// ---- tiny shared-memory GEMMs, all threads of the CTA.  Every matrix has D (= d_k = d_model) columns or D-long rows, so the
+// helpers are specialised on D: one thread produces 4 adjacent outputs from one scalar + one 128-bit shared load per step
+// (mm_nn / mm_tn), or one warp owns an output row with its D-long left operand in registers (mm_nt).  Leading dimensions
+// are multiples of 4 floats; Q/K/V rows are padded to D + 4 so that eight consecutive rows start in eight different banks.
+__device__ __forceinline__ void fma4(float4& s, float a, const float4& b) {
+  s.x = fmaf(a, b.x, s.x); s.y = fmaf(a, b.y, s.y); s.z = fmaf(a, b.z, s.z); s.w = fmaf(a, b.w, s.w);
+}
+// C[t][0:D] (=|+=) sum_k A[t][k] * B[k][0:D]        (t < T, k < K)
+template <int D>
+__device__ __forceinline__ void mm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int T, int K, bool acc) {
+  constexpr int D4 = D / 4;
+  for (int e = threadIdx.x; e < T * D4; e += BST_NT) {
+    const int t = e / D4, j = (e % D4) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* a = A + t * lda;
+    const float* b = B + j;
+    for (int k = 0; k < K; ++k) fma4(s, a[k], *reinterpret_cast<const float4*>(b + k * ldb));
+    float4* c = reinterpret_cast<float4*>(C + t * ldc + j);
+    if (acc) { const float4 o = *c; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    *c = s;
   }
 }
-// C[t][u] (=|+=) scale * sum_k A[t][k] * B[u][k]
-__device__ __forceinline__ void mm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int T, int K, int N,
-                                      float scale, bool acc) {
-  for (int e = threadIdx.x; e < T * N; e += BST_NT) {
-    const int t = e / N, u = e - t * N;
-    float s = 0.f;
-    for (int k = 0; k < K; ++k) s = fmaf(A[t * lda + k], B[u * ldb + k], s);
-    C[t * ldc + u] = acc ? C[t * ldc + u] + scale * s : scale * s;
+// C[k][0:D] (=|+=) sum_t A[t][k] * B[t][0:D]        (k < K, t < T)
+template <int D>
+__device__ __forceinline__ void mm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int T, int K, bool acc) {
+  constexpr int D4 = D / 4;
+  for (int e = threadIdx.x; e < K * D4; e += BST_NT) {
+    const int k = e / D4, j = (e % D4) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) fma4(s, A[t * lda + k], *reinterpret_cast<const float4*>(B + t * ldb + j));
+    float4* c = reinterpret_cast<float4*>(C + k * ldc + j);
+    if (acc) { const float4 o = *c; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    *c = s;
   }
 }
-// C[k][j] (=|+=) sum_t A[t][k] * B[t][j]
-__device__ __forceinline__ void mm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int T, int K, int N,
+// C[t][u] (=|+=) scale * sum_{k<D} A[t][k] * B[u][k]   (t < T, u < N): warp per row t, lanes over u
+template <int D>
+__device__ __forceinline__ void mm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int T, int N, float scale,
                                       bool acc) {
-  for (int e = threadIdx.x; e < K * N; e += BST_NT) {
-    const int k = e / N, j = e - k * N;
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) s = fmaf(A[t * lda + k], B[t * ldb + j], s);
-    C[k * ldc + j] = acc ? C[k * ldc + j] + s : s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < T; t += BST_NT / 32) {
+    float4 a[D / 4];
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q) a[q] = *reinterpret_cast<const float4*>(A + t * lda + 4 * q);
+    for (int u = lane; u < N; u += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < D / 4; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(B + u * ldb + 4 * q);
+        s = fmaf(a[q].x, b.x, s); s = fmaf(a[q].y, b.y, s); s = fmaf(a[q].z, b.z, s); s = fmaf(a[q].w, b.w, s);
+      }
+      C[t * ldc + u] = acc ? C[t * ldc + u] + scale * s : scale * s;
+    }
   }
 }
 
@@ -115,15 +139,17 @@ struct BstSmem {
   float *G, *dS, *dC, *dQ, *dK, *dV, *dxq, *dxk, *dxv;
 };
 
+__host__ __device__ inline int bst_tt(int T) { return (T * (T + 1) + 3) & ~3; }
+
 __host__ __device__ inline size_t bst_smem_floats(int T, int d, int H, int total, bool bwd) {
-  const int Td = T * d, Tp = T * (d + 1), TT = T * (T + 1);
+  const int Td = T * d, Tp = T * (d + 4), TT = bst_tt(T);
   size_t n = (size_t)total + 3 * Td + 3 * Tp + TT + (size_t)T * H * d + 2 * Td + 32;
   if (bwd) n += (size_t)total + Td + TT + (size_t)T * H * d + 3 * Td + 3 * Td;
   return n;
 }
 
 __device__ inline BstSmem bst_carve(float* sm, int T, int d, int H, int total, bool bwd) {
-  const int Td = T * d, Tp = T * (d + 1), TT = T * (T + 1);
+  const int Td = T * d, Tp = T * (d + 4), TT = bst_tt(T);
   BstSmem s;
   float* p = sm;
   s.w = p; p += total;
@@ -147,27 +173,26 @@ __device__ inline BstSmem bst_carve(float* sm, int T, int d, int H, int total, b
 }
 
 // Q, K, V of head h and A = softmax(Q K^T / sqrt(d) + query-axis mask)
-__device__ __forceinline__ void bst_head_forward(const BstSmem& s, const BstLayout& L, int h, int T, int d, int len) {
-  const int dp = d + 1, tp = T + 1;
-  mm_nn(s.xq, d, s.w + L.wq + h * d * d, d, s.Q, dp, T, d, d, false);
-  mm_nn(s.xk, d, s.w + L.wk + h * d * d, d, s.K, dp, T, d, d, false);
-  mm_nn(s.xv, d, s.w + L.wv + h * d * d, d, s.V, dp, T, d, d, false);
+template <int D>
+__device__ __forceinline__ void bst_head_forward(const BstSmem& s, const BstLayout& L, int h, int T, int len) {
+  constexpr int dp = D + 4;
+  const int tp = T + 1;
+  mm_nn<D>(s.xq, D, s.w + L.wq + h * D * D, D, s.Q, dp, T, D, false);
+  mm_nn<D>(s.xk, D, s.w + L.wk + h * D * D, D, s.K, dp, T, D, false);
+  mm_nn<D>(s.xv, D, s.w + L.wv + h * D * D, D, s.V, dp, T, D, false);
   __syncthreads();
-  const float scale = 1.f / sqrtf((float)d);
-  for (int e = threadIdx.x; e < T * T; e += BST_NT) {
-    const int t = e / T, u = e - t * T;
-    float acc = 0.f;
-    for (int k = 0; k < d; ++k) acc = fmaf(s.Q[t * dp + k], s.K[u * dp + k], acc);
-    acc *= scale;                                                        // tf.matmul(Q, K_T) / math.sqrt(d_k)
-    if (t >= len) acc = __fadd_rn(acc, -4294967296.f);                   // float32(-2**32 + 1); collapses the row (see header)
-    s.A[t * tp + u] = acc;
-  }
+  mm_nt<D>(s.Q, dp, s.K, dp, s.A, tp, T, T, 1.f / sqrtf((float)D), false);      // tf.matmul(Q, K_T) / math.sqrt(d_k)
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int t = warp; t < T; t += BST_NT / 32) {
     float* row = s.A + t * tp;
+    const bool masked = t >= len;
     float mx = -INFINITY;
-    for (int u = lane; u < T; u += 32) mx = fmaxf(mx, row[u]);
+    for (int u = lane; u < T; u += 32) {
+      float v = row[u];
+      if (masked) { v = __fadd_rn(v, -4294967296.f); row[u] = v; }             // float32(-2**32 + 1): collapses the row (see header)
+      mx = fmaxf(mx, v);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float den = 0.f;
@@ -179,16 +204,17 @@ __device__ __forceinline__ void bst_head_forward(const BstSmem& s, const BstLayo
   __syncthreads();
 }
 
-template <bool BWD>
+template <int D, bool BWD>
 __global__ void __launch_bounds__(BST_NT)
 bst_kernel(const float* __restrict__ queries, const float* __restrict__ keys, const float* __restrict__ values,
            const long long* __restrict__ keys_length, const float* __restrict__ params, const float* __restrict__ g_out, int B,
-           int T, int d, int H, int maxlen, int use_pos, float* __restrict__ out, float* __restrict__ d_queries,
+           int T, int H, int maxlen, int use_pos, float* __restrict__ out, float* __restrict__ d_queries,
            float* __restrict__ d_keys, float* __restrict__ d_values, float* __restrict__ d_params) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  constexpr int d = D, dp = D + 4;
   const BstLayout L = bst_layout(d, H, maxlen);
   const BstSmem s = bst_carve(sm, T, d, H, L.total, BWD);
-  const int Td = T * d, Hd = H * d, dp = d + 1, tp = T + 1;
+  const int Td = T * d, Hd = H * d, tp = T + 1;
   for (int e = threadIdx.x; e < L.total; e += BST_NT) { s.w[e] = __ldg(params + e); if (BWD) s.gw[e] = 0.f; }
   __syncthreads();
   const float f1 = 0.5f * (1.f + 0.01f), f2 = 0.5f * (1.f - 0.01f);      // BST/leakyrelu.py:14-16
@@ -205,43 +231,38 @@ bst_kernel(const float* __restrict__ queries, const float* __restrict__ keys, co
     __syncthreads();
     // ---- attention, head by head -> cat (T, H*d)
     for (int h = 0; h < H; ++h) {
-      bst_head_forward(s, L, h, T, d, len);
-      mm_nn(s.A, tp, s.V, dp, s.cat + h * d, Hd, T, T, d, false);
+      bst_head_forward<D>(s, L, h, T, len);
+      mm_nn<D>(s.A, tp, s.V, dp, s.cat + h * d, Hd, T, T, false);
       __syncthreads();
     }
     // ---- all_heads = cat @ w_o ; net = layer_norm(all_heads + queries)
-    mm_nn(s.cat, Hd, s.w + L.wo, d, s.xh1, d, T, Hd, d, false);
+    mm_nn<D>(s.cat, Hd, s.w + L.wo, d, s.xh1, d, T, Hd, false);
     __syncthreads();
     for (int e = threadIdx.x; e < Td; e += BST_NT) s.xh1[e] += s.xq[e];
     __syncthreads();
-    const float r1 = ln_forward(s.xh1, Td, s.red);                         // xh1 = xhat1 ; y1 = xhat1 * gamma1 + beta1
+    const float r1 = ln_forward(s.xh1, Td, s.red);                         // xh1 = xhat1
+    float* y1 = BWD ? s.dV : s.xk;                                         // scratch: xk is dead in the forward-only kernel
+    for (int e = threadIdx.x; e < Td; e += BST_NT) y1[e] = fmaf(s.xh1[e], s.w[L.g1 + e % d], s.w[L.b1 + e % d]);
+    __syncthreads();
     // ---- ffn = leakyrelu(dense(net)) ; out = layer_norm(ffn + net)
-    for (int e = threadIdx.x; e < Td; e += BST_NT) {
-      const int t = e / d, j = e - t * d;
-      float acc = s.w[L.bd + j];
-      for (int k = 0; k < d; ++k) acc = fmaf(fmaf(s.xh1[t * d + k], s.w[L.g1 + k], s.w[L.b1 + k]), s.w[L.wd + k * d + j], acc);
-      s.f[e] = acc;
-    }
+    mm_nn<D>(y1, d, s.w + L.wd, d, s.f, d, T, d, false);
     __syncthreads();
     float* n2 = BWD ? s.G : s.xq;                                          // xq is dead in the forward-only kernel
     for (int e = threadIdx.x; e < Td; e += BST_NT) {
-      const int j = e % d;
-      const float y1 = fmaf(s.xh1[e], s.w[L.g1 + j], s.w[L.b1 + j]);
-      n2[e] = f1 * s.f[e] + f2 * fabsf(s.f[e]) + y1;
+      const float fv = s.f[e] + s.w[L.bd + e % d];
+      s.f[e] = fv;
+      n2[e] = f1 * fv + f2 * fabsf(fv) + y1[e];
     }
     __syncthreads();
     const float r2 = ln_forward(n2, Td, s.red);                            // n2 = xhat2
     if (!BWD) {
-      for (int e = threadIdx.x; e < Td; e += BST_NT) {
-        const int j = e % d;
-        out[(size_t)b * Td + e] = fmaf(n2[e], s.w[L.g2 + j], s.w[L.b2 + j]);
-      }
+      for (int e = threadIdx.x; e < Td; e += BST_NT) out[(size_t)b * Td + e] = fmaf(n2[e], s.w[L.g2 + e % d], s.w[L.b2 + e % d]);
       __syncthreads();
       continue;
     }
 
     // =============================================================== backward ===============================================
-    // ---- layer norm 2: G holds xhat2; load g, accumulate d_gamma2 / d_beta2, turn G into d(n2)
+    // ---- layer norm 2: G holds xhat2; load g, accumulate d_gamma2 / d_beta2, turn dn into d(n2)
     float* dn = s.dQ;                                                      // scratch (T,d): free until the head loop
     for (int e = threadIdx.x; e < Td; e += BST_NT) dn[e] = __ldg(g_out + (size_t)b * Td + e);
     __syncthreads();
@@ -253,26 +274,21 @@ bst_kernel(const float* __restrict__ queries, const float* __restrict__ keys, co
     __syncthreads();
     for (int e = threadIdx.x; e < Td; e += BST_NT) dn[e] *= s.w[L.g2 + e % d];
     __syncthreads();
-    ln_backward(dn, s.G, r2, Td, s.red);                                   // dn = d(n2) = d(ffn_out) = d(y1) (residual part)
+    ln_backward(dn, s.G, r2, Td, s.red);                                   // dn = d(n2): gradient of ffn_out and (residual) of y1
     // ---- leaky relu + dense: df -> G ; d_dense_kernel, d_dense_bias ; dy1 = dn + df @ Wd^T -> dK scratch
     for (int e = threadIdx.x; e < Td; e += BST_NT) {
       const float fv = s.f[e];
       s.G[e] = dn[e] * (f1 + f2 * (fv > 0.f ? 1.f : (fv < 0.f ? -1.f : 0.f)));
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < d * d; e += BST_NT) {                    // d_kernel[k][j] += sum_t y1[t][k] df[t][j]
-      const int k = e / d, j = e - k * d;
-      float a = 0.f;
-      for (int t = 0; t < T; ++t) a = fmaf(fmaf(s.xh1[t * d + k], s.w[L.g1 + k], s.w[L.b1 + k]), s.G[t * d + j], a);
-      s.gw[L.wd + e] += a;
-    }
+    mm_tn<D>(y1, d, s.G, d, s.gw + L.wd, d, T, d, true);                   // d_kernel += y1^T df
     for (int j = threadIdx.x; j < d; j += BST_NT) {
       float a = 0.f;
       for (int t = 0; t < T; ++t) a += s.G[t * d + j];
       s.gw[L.bd + j] += a;
     }
     float* dy1 = s.dK;
-    mm_nt(s.G, d, s.w + L.wd, d, dy1, d, T, d, d, 1.f, false);            // df @ Wd^T
+    mm_nt<D>(s.G, d, s.w + L.wd, d, dy1, d, T, d, 1.f, false);            // df @ Wd^T
     __syncthreads();
     for (int e = threadIdx.x; e < Td; e += BST_NT) dy1[e] += dn[e];
     __syncthreads();
@@ -289,16 +305,16 @@ bst_kernel(const float* __restrict__ queries, const float* __restrict__ keys, co
     for (int e = threadIdx.x; e < Td; e += BST_NT) { s.G[e] = dy1[e]; s.dxq[e] = dy1[e]; s.dxk[e] = 0.f; s.dxv[e] = 0.f; }
     __syncthreads();
     // ---- w_o: d_w_o += cat^T @ G ; dC = G @ w_o^T
-    mm_tn(s.cat, Hd, s.G, d, s.gw + L.wo, d, T, Hd, d, true);
-    mm_nt(s.G, d, s.w + L.wo, d, s.dC, Hd, T, d, Hd, 1.f, false);
+    mm_tn<D>(s.cat, Hd, s.G, d, s.gw + L.wo, d, T, Hd, true);
+    mm_nt<D>(s.G, d, s.w + L.wo, d, s.dC, Hd, T, Hd, 1.f, false);
     __syncthreads();
     // ---- heads
     const float scale = 1.f / sqrtf((float)d);
     for (int h = 0; h < H; ++h) {
-      bst_head_forward(s, L, h, T, d, len);
+      bst_head_forward<D>(s, L, h, T, len);
       const float* dO = s.dC + h * d;                                      // (T, d) with leading dimension H*d
-      mm_nt(dO, Hd, s.V, dp, s.dS, tp, T, d, T, 1.f, false);              // dA[t][u] = sum_j dO[t][j] V[u][j]
-      mm_tn(s.A, tp, dO, Hd, s.dV, d, T, T, d, false);                     // dV[u][j] = sum_t A[t][u] dO[t][j]
+      mm_nt<D>(dO, Hd, s.V, dp, s.dS, tp, T, T, 1.f, false);              // dA[t][u] = sum_j dO[t][j] V[u][j]
+      mm_tn<D>(s.A, tp, dO, Hd, s.dV, d, T, T, false);                     // dV[u][j] = sum_t A[t][u] dO[t][j]
       __syncthreads();
       {                                                                    // dS = A * (dA - rowsum(A * dA)) / sqrt(d)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -310,15 +326,15 @@ bst_kernel(const float* __restrict__ queries, const float* __restrict__ keys, co
         }
       }
       __syncthreads();
-      mm_nn(s.dS, tp, s.K, dp, s.dQ, d, T, T, d, false);                   // dQ = dS @ K
-      mm_tn(s.dS, tp, s.Q, dp, s.dK, d, T, T, d, false);                   // dK = dS^T @ Q
+      mm_nn<D>(s.dS, tp, s.K, dp, s.dQ, d, T, T, false);                   // dQ = dS @ K
+      mm_tn<D>(s.dS, tp, s.Q, dp, s.dK, d, T, T, false);                   // dK = dS^T @ Q
       __syncthreads();
-      mm_tn(s.xq, d, s.dQ, d, s.gw + L.wq + h * d * d, d, T, d, d, true);
-      mm_tn(s.xk, d, s.dK, d, s.gw + L.wk + h * d * d, d, T, d, d, true);
-      mm_tn(s.xv, d, s.dV, d, s.gw + L.wv + h * d * d, d, T, d, d, true);
-      mm_nt(s.dQ, d, s.w + L.wq + h * d * d, d, s.dxq, d, T, d, d, 1.f, true);
-      mm_nt(s.dK, d, s.w + L.wk + h * d * d, d, s.dxk, d, T, d, d, 1.f, true);
-      mm_nt(s.dV, d, s.w + L.wv + h * d * d, d, s.dxv, d, T, d, d, 1.f, true);
+      mm_tn<D>(s.xq, d, s.dQ, d, s.gw + L.wq + h * d * d, d, T, d, true);
+      mm_tn<D>(s.xk, d, s.dK, d, s.gw + L.wk + h * d * d, d, T, d, true);
+      mm_tn<D>(s.xv, d, s.dV, d, s.gw + L.wv + h * d * d, d, T, d, true);
+      mm_nt<D>(s.dQ, d, s.w + L.wq + h * d * d, d, s.dxq, d, T, d, 1.f, true);
+      mm_nt<D>(s.dK, d, s.w + L.wk + h * d * d, d, s.dxk, d, T, d, 1.f, true);
+      mm_nt<D>(s.dV, d, s.w + L.wv + h * d * d, d, s.dxv, d, T, d, 1.f, true);
       __syncthreads();
     }
     for (int e = threadIdx.x; e < Td; e += BST_NT) {
@@ -356,23 +372,41 @@ extern "C" int64_t ctr_bst_param_count(int64_t d, int64_t heads, int64_t max_len
   return (int64_t)max_length * d + 4 * heads * d * d + d * d + 5 * d;
 }
 
-template <bool BWD>
-static int bst_launch(const char* fn, const float* q, const float* k, const float* v, const int64_t* len, const float* params,
-                      const float* g, int64_t B, int64_t T, int64_t d, int64_t H, int64_t maxlen, int use_pos, float* out,
-                      float* dq, float* dk, float* dv, float* dparams, cudaStream_t st) {
-  const BstLayout L = bst_layout((int)d, (int)H, (int)maxlen);
-  const size_t smem = bst_smem_floats((int)T, (int)d, (int)H, L.total, BWD) * sizeof(float);
-  CTR_UNSUPPORTED(smem > 220 * 1024, "%s: T=%lld d=%lld heads=%lld max_length=%lld needs %zu bytes of shared memory per sample (limit 220 KB)",
-                  fn, (long long)T, (long long)d, (long long)H, (long long)maxlen, smem);
-  auto kern = bst_kernel<BWD>;
+template <int D, bool BWD>
+static int bst_launch_d(const char* fn, const float* q, const float* k, const float* v, const int64_t* len, const float* params,
+                        const float* g, int64_t B, int64_t T, int64_t H, int64_t maxlen, int use_pos, float* out, float* dq,
+                        float* dk, float* dv, float* dparams, cudaStream_t st) {
+  const BstLayout L = bst_layout(D, (int)H, (int)maxlen);
+  const size_t smem = bst_smem_floats((int)T, D, (int)H, L.total, BWD) * sizeof(float);
+  CTR_UNSUPPORTED(smem > 220 * 1024, "%s: T=%lld d=%d heads=%lld max_length=%lld needs %zu bytes of shared memory per sample (limit 220 KB)",
+                  fn, (long long)T, D, (long long)H, (long long)maxlen, smem);
+  auto kern = bst_kernel<D, BWD>;
   if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BST_NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * sm_count();
   if (grid > B) grid = B;
-  kern<<<(int)grid, BST_NT, smem, st>>>(q, k, v, reinterpret_cast<const long long*>(len), params, g, (int)B, (int)T, (int)d, (int)H,
+  kern<<<(int)grid, BST_NT, smem, st>>>(q, k, v, reinterpret_cast<const long long*>(len), params, g, (int)B, (int)T, (int)H,
                                         (int)maxlen, use_pos, out, dq, dk, dv, dparams);
   CTR_CHECK_LAUNCH(fn);
+  return CTR_OK;
+}
+
+template <bool BWD>
+static int bst_launch(const char* fn, const float* q, const float* k, const float* v, const int64_t* len, const float* params,
+                      const float* g, int64_t B, int64_t T, int64_t d, int64_t H, int64_t maxlen, int use_pos, float* out,
+                      float* dq, float* dk, float* dv, float* dparams, cudaStream_t st) {
+#define BST_GO(D_) return bst_launch_d<D_, BWD>(fn, q, k, v, len, params, g, B, T, H, maxlen, use_pos, out, dq, dk, dv, dparams, st)
+  switch (d) {
+    case 4: BST_GO(4);
+    case 8: BST_GO(8);
+    case 16: BST_GO(16);
+    case 32: BST_GO(32);
+    case 64: BST_GO(64);
+    default: break;
+  }
+#undef BST_GO
+  CTR_UNSUPPORTED(true, "%s: d=%lld unsupported (d_k in {4, 8, 16, 32, 64})", fn, (long long)d);
   return CTR_OK;
 }
 
