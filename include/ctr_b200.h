@@ -125,6 +125,13 @@ int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field
                             const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, float lr_t, float beta1,
                             float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
 
+/* The same step for the OWNER side of a row-sharded table: entries are the receive queues filled by ctr_sharded_grad_push --
+ * rows (nseg, cap) local row ids, vals (nseg, cap, D) (consumed), counts (nseg,) filled slots per segment; duplicates of a
+ * row across and inside segments are summed before the update.  nseg*cap < 2^31. */
+int ctr_adam_rows_dedup(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, float* vals,
+                        const int64_t* counts, int64_t nseg, int64_t cap, int32_t* slot_of_row, float lr_t, float beta1,
+                        float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
+
 /* DeepFM first-order ("wide") term as a D=1 lookup.  Replaces indicator_column multi-hot (B, sum V) @
  * dense(1) (DeepFM/deepfm.py:72-80,180-181): out[b] = bias + sum_f w[field_row_offset[f] + ids[b,f]]; invalid ids add 0.
  * w (V_total) is the dense(1) kernel; its gradient is the IndexedSlices (ids, d_out[b] broadcast over F) -- no kernel

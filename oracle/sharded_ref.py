@@ -49,3 +49,19 @@ def exchange_reference(local_rows: int, field_row_offset: torch.Tensor, ids: tor
         mine = (r_ >= 0) & (r_ % G == rank)
         dense.index_add_(0, r_[mine] // G, v_[mine].double())
     return dense
+
+
+def adam_reference(var, m, v, g_dense, touched, t, lr, lazy, beta1=0.9, beta2=0.999, eps=1e-8):
+    """float64 Adam / LazyAdam step on a shard from its densified gradient (same float32 coefficients as
+    oracle.layers_np.adam_sparse_apply); `touched` marks the rows that received at least one entry."""
+    import numpy as np
+    om1 = float(np.float32(1.0) - np.float32(beta1)); om2 = float(np.float32(1.0) - np.float32(beta2))
+    b1 = float(np.float32(beta1)); b2 = float(np.float32(beta2))
+    lr_t = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
+    m2 = b1 * m + om1 * g_dense
+    v2 = b2 * v + om2 * g_dense * g_dense
+    w2 = var - lr_t * m2 / (v2.sqrt() + eps)
+    if lazy:
+        sel = touched[:, None]
+        return torch.where(sel, w2, var), torch.where(sel, m2, m), torch.where(sel, v2, v)
+    return w2, m2, v2

@@ -65,28 +65,41 @@ adam_dense_rest_kernel(float4* __restrict__ var, float4* __restrict__ m, float4*
 // accumulator:  claim (atomicCAS) -> merge (every other entry of that row adds its gradient into the winner's slot of
 // row_grads, 128-bit reductions) -> update (the winner applies Adam with the summed gradient, clears the slot, marks the
 // bitmap).  Three launches on one stream, no host round trip; row_grads is consumed (clobbered).
-__device__ __forceinline__ long long entry_row(const long long* __restrict__ ids, const long long* __restrict__ off, int F, long long e) {
-  const int f = (int)(e % F);
-  const long long id = __ldg(ids + e), base = __ldg(off + f);
-  return (id < 0 || id >= __ldg(off + f + 1) - base) ? -1 : base + id;
+// Where the entries of one step come from: the (B,F) id matrix of an IndexedSlices (row = field offset + local id), or the
+// receive queues of a row-sharded table (nseg segments of `cap` (row, value) slots, counts[seg] of them filled).
+struct EntrySrc {
+  const long long* ids;      // (B,F) local ids | (nseg, cap) local rows
+  const long long* off;      // (F+1,) field row offsets | nullptr
+  const long long* counts;   // nullptr | (nseg,)
+  long long cap, V;          // segment capacity | rows of the table (range check of the flat form)
+  int F;
+};
+__device__ __forceinline__ long long entry_row(const EntrySrc& s, long long e) {
+  if (s.off != nullptr) {
+    const int f = (int)(e % s.F);
+    const long long id = __ldg(s.ids + e), base = __ldg(s.off + f);
+    return (id < 0 || id >= __ldg(s.off + f + 1) - base) ? -1 : base + id;
+  }
+  if (e % s.cap >= __ldg(s.counts + e / s.cap)) return -1;
+  const long long row = __ldg(s.ids + e);
+  return (row < 0 || row >= s.V) ? -1 : row;
 }
 
 __global__ void __launch_bounds__(256)
-adam_claim_kernel(const long long* __restrict__ ids, const long long* __restrict__ off, int F, long long n, int* __restrict__ slot) {
+adam_claim_kernel(const EntrySrc src, long long n, int* __restrict__ slot) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const long long row = entry_row(ids, off, F, e);
+    const long long row = entry_row(src, e);
     if (row >= 0) atomicCAS(slot + row, -1, (int)e);
   }
 }
 
 template <int LPR>
 __global__ void __launch_bounds__(256)
-adam_merge_kernel(const long long* __restrict__ ids, const long long* __restrict__ off, int F, long long n,
-                  const int* __restrict__ slot, float4* __restrict__ grads) {
+adam_merge_kernel(const EntrySrc src, long long n, const int* __restrict__ slot, float4* __restrict__ grads) {
   const size_t total = (size_t)n * LPR;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const long long e = (long long)(t / LPR);
-    const long long row = entry_row(ids, off, F, e);
+    const long long row = entry_row(src, e);
     if (row < 0) continue;
     const int w = __ldg(slot + row);
     if (w != (int)e) atomicAdd(grads + (size_t)w * LPR + t % LPR, grads[t]);
@@ -95,8 +108,8 @@ adam_merge_kernel(const long long* __restrict__ ids, const long long* __restrict
 
 template <int LPR>
 __global__ void __launch_bounds__(256)
-adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, const long long* __restrict__ ids,
-                   const long long* __restrict__ off, int F, long long n, int* __restrict__ slot, const float4* __restrict__ grads,
+adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, const EntrySrc src, long long n,
+                   int* __restrict__ slot, const float4* __restrict__ grads,
                    float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched, long long* __restrict__ n_unique) {
   const size_t total = (size_t)n * LPR;
   int mine = 0;
@@ -108,7 +121,7 @@ adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __r
     bool win = false;
     if (t < total) {
       const long long e = (long long)(t / LPR);
-      row = entry_row(ids, off, F, e);
+      row = entry_row(src, e);
       win = row >= 0 && slot[row] == (int)e;
     }
     __syncwarp();
@@ -180,6 +193,26 @@ extern "C" int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, in
   return CTR_OK;
 }
 
+static int adam_dedup_launch(const char* fn, float* var, float* m, float* v, int64_t D, const EntrySrc& src, long long n,
+                             float* vals, int32_t* slot_of_row, float lr_t, float beta1, float beta2, float eps,
+                             uint32_t* touched_bitmap, int64_t* n_unique, cudaStream_t st) {
+  const long long total = n * (D / 4);
+  auto cap = [](long long want, long long lim) { return (int)(want < lim ? want : lim); };
+  const int grid_e = cap((n + 255) / 256, (long long)sm_count() * 16), grid_t = cap((total + 255) / 256, (long long)sm_count() * 16);
+  auto* g4 = reinterpret_cast<float4*>(vals);
+  adam_claim_kernel<<<grid_e, 256, 0, st>>>(src, n, slot_of_row);
+#define GO(L)                                                                                                               \
+  adam_merge_kernel<L><<<grid_t, 256, 0, st>>>(src, n, slot_of_row, g4);                                                    \
+  adam_update_kernel<L><<<grid_t, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),               \
+                                                reinterpret_cast<float4*>(v), src, n, slot_of_row, g4, lr_t, beta1, beta2,  \
+                                                eps, touched_bitmap, reinterpret_cast<long long*>(n_unique))
+  switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
+#undef GO
+  CTR_CHECK_LAUNCH(fn);
+  count_launch(2);
+  return CTR_OK;
+}
+
 extern "C" int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field_row_offset, int64_t F, int64_t D,
                                        const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, float lr_t,
                                        float beta1, float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique,
@@ -191,22 +224,21 @@ extern "C" int ctr_adam_indexed_slices(float* var, float* m, float* v, const int
   CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(row_grads),
               "ctr_adam_indexed_slices: buffers must be 16-byte aligned");
   if (B == 0) return CTR_OK;
-  cudaStream_t st = as_stream(stream);
-  const long long n = B * F, total = n * (D / 4);
-  auto cap = [](long long want, long long lim) { return (int)(want < lim ? want : lim); };
-  const int grid_e = cap((n + 255) / 256, (long long)sm_count() * 16), grid_t = cap((total + 255) / 256, (long long)sm_count() * 16);
-  auto* idp = reinterpret_cast<const long long*>(ids);
-  auto* offp = reinterpret_cast<const long long*>(field_row_offset);
-  auto* g4 = reinterpret_cast<float4*>(row_grads);
-  adam_claim_kernel<<<grid_e, 256, 0, st>>>(idp, offp, (int)F, n, slot_of_row);
-#define GO(L)                                                                                                               \
-  adam_merge_kernel<L><<<grid_t, 256, 0, st>>>(idp, offp, (int)F, n, slot_of_row, g4);                                      \
-  adam_update_kernel<L><<<grid_t, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),               \
-                                                reinterpret_cast<float4*>(v), idp, offp, (int)F, n, slot_of_row, g4, lr_t,  \
-                                                beta1, beta2, eps, touched_bitmap, reinterpret_cast<long long*>(n_unique))
-  switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
-#undef GO
-  CTR_CHECK_LAUNCH("ctr_adam_indexed_slices");
-  count_launch(2);
-  return CTR_OK;
+  EntrySrc src = {reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(field_row_offset), nullptr, 0, 0, (int)F};
+  return adam_dedup_launch("ctr_adam_indexed_slices", var, m, v, D, src, B * F, row_grads, slot_of_row, lr_t, beta1, beta2, eps,
+                           touched_bitmap, n_unique, as_stream(stream));
+}
+
+extern "C" int ctr_adam_rows_dedup(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, float* vals,
+                                   const int64_t* counts, int64_t nseg, int64_t cap, int32_t* slot_of_row, float lr_t, float beta1,
+                                   float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream) {
+  int rc = check_adam("ctr_adam_rows_dedup", V, D);
+  if (rc) return rc;
+  CTR_REQUIRE(var && m && v && rows && vals && counts && slot_of_row, "ctr_adam_rows_dedup: null argument");
+  CTR_REQUIRE(nseg >= 1 && cap >= 0 && nseg * cap < (1LL << 31), "ctr_adam_rows_dedup: bad nseg/cap (nseg*cap must be < 2^31)");
+  CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(vals), "ctr_adam_rows_dedup: buffers must be 16-byte aligned");
+  if (cap == 0 || V == 0) return CTR_OK;
+  EntrySrc src = {reinterpret_cast<const long long*>(rows), nullptr, reinterpret_cast<const long long*>(counts), cap, V, 0};
+  return adam_dedup_launch("ctr_adam_rows_dedup", var, m, v, D, src, nseg * cap, vals, slot_of_row, lr_t, beta1, beta2, eps,
+                           touched_bitmap, n_unique, as_stream(stream));
 }

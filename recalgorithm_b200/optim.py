@@ -57,3 +57,43 @@ class TableAdam:
 
     def last_unique_rows(self) -> int:
         return int(self._n_unique.item())
+
+
+class ShardedTableAdam:
+    """The same optimizer on a row-sharded table (``sharded.ShardedEmbeddingTables``): every rank updates the rows it owns
+    from the (row, gradient) entries the other ranks pushed into its receive queues (``push_grads`` must have completed,
+    barrier included).  ``step()`` ends with a barrier so that the next forward pulls updated rows."""
+
+    def __init__(self, tables, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, lazy: bool = False):
+        self.tables, self.lr, self.b1, self.b2, self.eps, self.lazy = tables, lr, beta1, beta2, eps, lazy
+        w = tables.weight
+        self.m = torch.zeros(tuple(w.shape), dtype=torch.float32, device=w.device)
+        self.v = torch.zeros(tuple(w.shape), dtype=torch.float32, device=w.device)
+        self.t = 0
+        self._bitmap = None if lazy else torch.zeros(((tables.local_rows + 31) // 32,), dtype=torch.int32, device=w.device)
+        self._slot = torch.full((tables.local_rows,), -1, dtype=torch.int32, device=w.device)
+        self._n_unique = torch.zeros((1,), dtype=torch.int64, device=w.device)
+
+    def step(self, barrier: bool = True) -> None:
+        tb = self.tables
+        w = tb.weight
+        V, D = w.shape
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        L = _lib.lib()
+        self._n_unique.zero_()
+        if self._bitmap is not None:
+            self._bitmap.zero_()
+        _lib.check(L.ctr_adam_rows_dedup(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), V, D, tb.recv_rows.data_ptr(),
+                                         tb.recv_vals.data_ptr(), tb.recv_counts.data_ptr(), tb.G, tb.capacity,
+                                         self._slot.data_ptr(), lr_t, self.b1, self.b2, self.eps, ops._ptr(self._bitmap),
+                                         self._n_unique.data_ptr(), ops._stream()))
+        if not self.lazy:
+            _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), V, D, lr_t, self.b1, self.b2,
+                                             self.eps, ops._ptr(self._bitmap), ops._stream()))
+        if barrier:
+            torch.cuda.current_stream().synchronize()
+            tb.dist.barrier(group=tb.group)
+
+    def last_unique_rows(self) -> int:
+        return int(self._n_unique.item())

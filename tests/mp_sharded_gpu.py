@@ -44,6 +44,28 @@ def main():
         assert err <= 1e-5, f"pushed gradients differ: {err}"
         assert int(t.recv_counts.sum()) > 0
         dist.barrier()
+        # ---- owner-side Adam on the received entries (SURVEY 8f.3 on the sharded path): two steps, lazy and TF-dense
+        from recalgorithm_b200 import optim
+        for lazy in (True, False):
+            t.weight.copy_(S.full_to_shard(full, rank, world))
+            opt = optim.ShardedTableAdam(t, lr=0.01, lazy=lazy)
+            w64, m64, v64 = t.weight.double().clone(), torch.zeros_like(t.weight, dtype=torch.float64), torch.zeros_like(t.weight, dtype=torch.float64)
+            for step in (1, 2):
+                ids_s = (torch.rand((B, F), device=dev, generator=gi) * (rt[None, :] + 3)).long() - 1
+                rg = torch.randn((B, F, D), device=dev, generator=gi)
+                t.push_grads(ids_s, rg)
+                gd = R.exchange_reference(t.local_rows, t.field_row_offset, ids_s, rg)
+                touched = torch.zeros((t.local_rows,), dtype=torch.bool, device=dev)
+                for src in range(world):
+                    n = int(t.recv_counts[src])
+                    touched[t.recv_rows[src, :n]] = True
+                opt.step()
+                assert opt.last_unique_rows() == int(touched.sum()) and bool((opt._slot == -1).all())
+                w64, m64, v64 = R.adam_reference(w64, m64, v64, gd, touched, step, 0.01, lazy)
+                for name, a, b_ in (("var", t.weight, w64), ("m", opt.m, m64), ("v", opt.v, v64)):
+                    err = (a.double() - b_).abs().max() / b_.abs().max().clamp_min(1e-30)
+                    assert err <= 1e-5, f"sharded adam lazy={lazy} step {step} {name}: {err}"
+            dist.barrier()
     print(f"SHARDED_OK rank={rank}", flush=True)
     dist.destroy_process_group()
 
