@@ -21,16 +21,18 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------------------- FwFM
-// smem: R (F x F, symmetric, zero diagonal) | per warp: e (F x KP), KP = K + 1 (pair-per-lane dot products hit distinct banks)
-template <bool BWD>
+// smem: R (F x F, symmetric, zero diagonal) | BWD: d_r accumulator (P) | per warp: e (F x KP)
+// VEC (K % 4 == 0): rows padded to KP = K + 4 floats, every shared load is 128-bit (eight consecutive rows start in eight
+// different banks); one pair per lane; the backward's R * E product computes four adjacent k per thread.
+template <bool BWD, bool VEC>
 __global__ void __launch_bounds__(PW_WARPS * 32)
 fwfm_kernel(const float* __restrict__ tile, const float* __restrict__ r, const float* __restrict__ g, int B, int F, int K,
             float* __restrict__ out, float* __restrict__ d_tile, float* __restrict__ d_r) {
-  extern __shared__ float sm[];
-  const int KP = K + 1, P = F * (F - 1) / 2;
+  extern __shared__ __align__(16) float sm[];
+  const int KP = VEC ? K + 4 : K + 1, P = F * (F - 1) / 2, PP = (P + 3) & ~3, FF = (F * F + 3) & ~3;
   float* Rs = sm;                                   // F*F
-  float* drs = Rs + F * F;                          // BWD: P   (CTA-level accumulator of d_r)
-  float* es = drs + (BWD ? P : 0) + (threadIdx.x >> 5) * F * KP;
+  float* drs = Rs + FF;                             // BWD: P   (CTA-level accumulator of d_r)
+  float* es = drs + (BWD ? PP : 0) + (threadIdx.x >> 5) * F * KP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int x = threadIdx.x; x < F * F; x += blockDim.x) {
     const int i = x / F, j = x % F;
@@ -46,15 +48,22 @@ fwfm_kernel(const float* __restrict__ tile, const float* __restrict__ r, const f
     for (int x = lane; x < F * K; x += 32) es[(x / K) * KP + x % K] = __ldg(src + x);
     __syncwarp();
     const float gb = BWD ? __ldg(g + b) : 0.f;
-    // pair-per-lane: p = lane, lane+32, ...; (i, j) advanced incrementally
+    // pair-per-lane: p = lane, lane+32, ... in the reference's pair order; (i, j) advanced incrementally (row i holds F-1-i pairs)
     float acc = 0.f;
     int i = 0, j = 1 + lane;
-    while (i < F - 1 && j >= F) { j = j - F + i + 2; ++i; }          // normalise (row i has F-1-i pairs)
+    while (i < F - 1 && j >= F) { j = j - F + i + 2; ++i; }
     for (int p = lane; p < P; p += 32) {
       const float* ei = es + i * KP;
       const float* ej = es + j * KP;
       float dot = 0.f;
-      for (int k = 0; k < K; ++k) dot = fmaf(ei[k], ej[k], dot);
+      if (VEC) {
+        for (int k = 0; k < K; k += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(ei + k), c = *reinterpret_cast<const float4*>(ej + k);
+          dot = fmaf(a.x, c.x, dot); dot = fmaf(a.y, c.y, dot); dot = fmaf(a.z, c.z, dot); dot = fmaf(a.w, c.w, dot);
+        }
+      } else {
+        for (int k = 0; k < K; ++k) dot = fmaf(ei[k], ej[k], dot);
+      }
       if (BWD) atomicAdd(drs + p, gb * dot); else acc = fmaf(Rs[i * F + j], dot, acc);
       j += 32;
       while (i < F - 1 && j >= F) { j = j - F + i + 2; ++i; }
@@ -65,11 +74,25 @@ fwfm_kernel(const float* __restrict__ tile, const float* __restrict__ r, const f
     } else {
       // d e_i[k] = g * sum_j R[i][j] e_j[k]
       float* dst = d_tile + (size_t)b * F * K;
-      for (int x = lane; x < F * K; x += 32) {
-        const int ii = x / K, k = x % K;
-        float s = 0.f;
-        for (int jj = 0; jj < F; ++jj) s = fmaf(Rs[ii * F + jj], es[jj * KP + k], s);
-        dst[x] = gb * s;
+      if (VEC) {
+        const int K4 = K >> 2;
+        for (int x = lane; x < F * K4; x += 32) {
+          const int ii = x / K4, k = (x - ii * K4) * 4;
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int jj = 0; jj < F; ++jj) {
+            const float rij = Rs[ii * F + jj];
+            const float4 c = *reinterpret_cast<const float4*>(es + jj * KP + k);
+            s4.x = fmaf(rij, c.x, s4.x); s4.y = fmaf(rij, c.y, s4.y); s4.z = fmaf(rij, c.z, s4.z); s4.w = fmaf(rij, c.w, s4.w);
+          }
+          *reinterpret_cast<float4*>(dst + ii * K + k) = make_float4(gb * s4.x, gb * s4.y, gb * s4.z, gb * s4.w);
+        }
+      } else {
+        for (int x = lane; x < F * K; x += 32) {
+          const int ii = x / K, k = x % K;
+          float s1 = 0.f;
+          for (int jj = 0; jj < F; ++jj) s1 = fmaf(Rs[ii * F + jj], es[jj * KP + k], s1);
+          dst[x] = gb * s1;
+        }
       }
     }
     __syncwarp();
@@ -308,28 +331,33 @@ static int check_pw(const char* fn, int64_t B, int64_t F, int64_t K) {
   return CTR_OK;
 }
 
+template <bool BWD, bool VEC>
+static int fwfm_launch(const char* fn, const float* tile, const float* r, const float* g, int64_t B, int64_t F, int64_t K, float* out,
+                       float* d_tile, float* d_r, cudaStream_t st) {
+  const int64_t P = F * (F - 1) / 2, PP = (P + 3) & ~3LL, FF = (F * F + 3) & ~3LL, KP = VEC ? K + 4 : K + 1;
+  const size_t smem = (size_t)(FF + (BWD ? PP : 0) + PW_WARPS * F * KP) * sizeof(float);
+  CTR_UNSUPPORTED(smem > 200 * 1024, "%s: F=%lld K=%lld needs %zu bytes of shared memory", fn, (long long)F, (long long)K, smem);
+  auto k = fwfm_kernel<BWD, VEC>;
+  if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<pw_grid(k, smem, B), PW_WARPS * 32, smem, st>>>(tile, r, g, (int)B, (int)F, (int)K, out, d_tile, d_r);
+  CTR_CHECK_LAUNCH(fn);
+  return CTR_OK;
+}
+
 static int fwfm_run(bool bwd, const float* tile, const float* r, const float* g, int64_t B, int64_t F, int64_t K, float* out,
                     float* d_tile, float* d_r, void* stream) {
   const char* fn = bwd ? "ctr_fwfm_bwd" : "ctr_fwfm_fwd";
   int rc = check_pw(fn, B, F, K);
   if (rc) return rc;
-  const int64_t P = F * (F - 1) / 2;
-  const size_t smem = (size_t)(F * F + (bwd ? P : 0) + PW_WARPS * F * (K + 1)) * sizeof(float);
-  CTR_UNSUPPORTED(smem > 200 * 1024, "%s: F=%lld K=%lld needs %zu bytes of shared memory", fn, (long long)F, (long long)K, smem);
   cudaStream_t st = as_stream(stream);
-  if (bwd) CTR_CUDA(cudaMemsetAsync(d_r, 0, (size_t)P * sizeof(float), st));
+  if (bwd) CTR_CUDA(cudaMemsetAsync(d_r, 0, (size_t)(F * (F - 1) / 2) * sizeof(float), st));
   if (B == 0) return CTR_OK;
-  if (bwd) {
-    auto k = fwfm_kernel<true>;
-    if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<pw_grid(k, smem, B), PW_WARPS * 32, smem, st>>>(tile, r, g, (int)B, (int)F, (int)K, nullptr, d_tile, d_r);
-  } else {
-    auto k = fwfm_kernel<false>;
-    if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<pw_grid(k, smem, B), PW_WARPS * 32, smem, st>>>(tile, r, nullptr, (int)B, (int)F, (int)K, out, nullptr, nullptr);
-  }
-  CTR_CHECK_LAUNCH(fn);
-  return CTR_OK;
+  // 128-bit path: K a multiple of 4 and 16-byte aligned rows in global memory for the float4 stores of d_tile
+  const bool vec = K % 4 == 0 && aligned16(tile) && (!bwd || aligned16(d_tile));
+  if (bwd) return vec ? fwfm_launch<true, true>(fn, tile, r, g, B, F, K, out, d_tile, d_r, st)
+                      : fwfm_launch<true, false>(fn, tile, r, g, B, F, K, out, d_tile, d_r, st);
+  return vec ? fwfm_launch<false, true>(fn, tile, r, g, B, F, K, out, d_tile, d_r, st)
+             : fwfm_launch<false, false>(fn, tile, r, g, B, F, K, out, d_tile, d_r, st);
 }
 
 extern "C" int ctr_fwfm_fwd(const float* tile, const float* r, int64_t B, int64_t F, int64_t K, float* out, void* stream) {

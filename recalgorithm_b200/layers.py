@@ -242,3 +242,12 @@ def bst_transformer(queries: torch.Tensor, keys: torch.Tensor, values: torch.Ten
     with variable_scope(suffix("LayerNorm", 2 * index + 1)):
         p["ln2_beta"] = get_variable("beta", (d,), initializer=zeros); p["ln2_gamma"] = get_variable("gamma", (d,), initializer=ones)
     return autograd.bst_transformer(queries, keys, values, keys_length.to(torch.int64), p, heads, max_length, use_position_embedding)
+
+
+# --------------------------------------------------------------------------------------------------- DIN loss-side term
+def mini_batch_aware_regularization(embedding_tensors, l2_lambda: float) -> torch.Tensor:
+    """DIN/din.py:254-257 (SURVEY parity note 7): ``l2_lambda * tf.nn.l2_loss(concat(tensors, -1)) / batch`` -- an L2 on the
+    looked-up ACTIVATIONS, so its gradient ``l2_lambda * e / B`` reaches the tables through the lookup backward
+    (``d_tile`` of ctr_embed_fm2_bwd / ctr_bag_lookup_bwd) like any other upstream gradient.  Torch plumbing, no kernel."""
+    x = torch.cat(list(embedding_tensors), dim=-1)
+    return l2_lambda * 0.5 * x.pow(2).sum() / x.shape[0]

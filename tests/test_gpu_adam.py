@@ -65,3 +65,38 @@ def test_table_adam_heavy_duplicates_and_two_backward_passes(lazy):
         var, m, v = O.adam_sparse_apply(var, m, v, np.concatenate(grows), np.concatenate(gvals), t, 0.05, lazy=lazy)
         assert_close(tables.weight, var, 2e-6, f"var step {t}")
         assert_close(opt.m, m, 1e-5, f"m step {t}"); assert_close(opt.v, v, 1e-5, f"v step {t}")
+
+
+def test_full_size_adam_properties():
+    """BASELINE config 5 shape (B=65536, F=40, D=32, 100 M rows; 38 GB with m and v), ids with heavy duplication in one
+    field -- size-independent properties of the fused IndexedSlices step."""
+    from recalgorithm_b200 import autograd, optim
+    B, F, D, rows = 65536, 40, 32, 2_500_000
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    tables = autograd.EmbeddingTables([rows] * F, D, device="cuda", init=None)
+    tables.weight.normal_(0, D ** -0.5, generator=gen)
+    ids = torch.randint(0, rows, (B, F), device="cuda", generator=gen)
+    ids[:, 0] = torch.randint(0, 50, (B,), device="cuda", generator=gen)            # ~1300 duplicates per row in field 0
+    ids[torch.rand((B, F), device="cuda", generator=gen) < 0.03] = -1
+    vals = torch.randn((B, F, D), device="cuda", generator=gen)
+    flat = (ids + tables.field_row_offset[:-1][None, :])[ids >= 0]
+    uniq = torch.unique(flat)
+    opt = optim.TableAdam(tables, lr=0.01, lazy=True)
+    w0 = tables.weight[uniq].clone()
+    probe = torch.randint(0, rows * F, (1 << 20,), device="cuda", generator=gen)      # random rows, mostly untouched
+    untouched = probe[~torch.isin(probe, uniq)]
+    u0 = tables.weight[untouched].clone()
+    tables.grad_slices.append(autograd.IndexedSlices(vals.clone(), ids, tables.field_row_offset))
+    opt.step()
+    # (1) distinct rows counted exactly, scratch back to idle
+    assert opt.last_unique_rows() == int(uniq.numel()) and bool((opt._slot == -1).all())
+    # (2) untouched rows are bit-identical under LazyAdam, moments stay zero
+    assert torch.equal(tables.weight[untouched], u0) and float(opt.m[untouched].abs().max()) == 0.0
+    # (3) first step from zero state: m = (1-b1) g, v = (1-b2) g^2 with g the SUM over duplicates  =>  |dw| = lr * |g| / (|g| + eps')
+    g = torch.zeros((uniq.numel(), D), device="cuda", dtype=torch.float64)
+    g.index_add_(0, torch.searchsorted(uniq, flat), vals[ids >= 0].double())
+    assert_close(opt.m[uniq], (1.0 - float(np.float32(0.9))) * g, 1e-5, "m = (1-b1) * summed gradient")
+    dw = (tables.weight[uniq] - w0).double()
+    assert float(dw.abs().max()) <= 0.01 * (1 + 1e-5)
+    big = g.abs() > 1e-2
+    assert_close(dw[big], -0.01 * torch.sign(g[big]), 1e-4, "first Adam step is -lr * sign(g) where |g| >> eps")

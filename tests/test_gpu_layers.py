@@ -113,3 +113,16 @@ def test_deepfm_fm_part_and_training_step():
         tables.weight -= 0.5 * sl.to_dense(tables.num_rows)     # plain SGD on the densified IndexedSlices
         losses.append(loss.item())
     assert losses[-1] < losses[0] * 0.9
+
+
+def test_mini_batch_aware_regularization_reaches_the_tables():
+    """DIN/din.py:254-257: the L2 on looked-up activations adds lambda * e / B to the IndexedSlices of the lookup."""
+    from recalgorithm_b200 import autograd, layers as L
+    tables = autograd.EmbeddingTables([7, 5, 9], 8, device="cuda")
+    ids = torch.tensor([[0, 4, -1], [6, 4, 8], [3, 0, 2], [0, 1, 8]], device="cuda")
+    tile = autograd.lookup(tables, ids)
+    B = ids.shape[0]
+    reg = L.mini_batch_aware_regularization([tile.reshape(B, -1)], l2_lambda=0.2)
+    assert_close(reg, 0.2 * 0.5 * float(tile.double().pow(2).sum()) / B * torch.ones((), dtype=torch.float64), TOL, "value")
+    reg.backward()
+    assert_close(tables.grad_slices[0].values, 0.2 * tile.detach().double() / B, TOL, "lambda * e / B")

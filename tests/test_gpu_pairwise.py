@@ -126,3 +126,24 @@ def test_pairwise_errors_and_layers_api():
         "attention_part/attention_b": (16,), "attention_part/attention_h": (16, 1)}
     (logit.sum() + pooled.sum()).backward()
     assert x.grad is not None and all(v.grad is not None for v in store.vars.values())
+
+
+def test_full_size_bi_interaction_properties():
+    """BASELINE config 5 shape: the bi-interaction vector sums (over D) to the FM2 logit of the fused FM2 kernel, the tile is
+    bit-identical between the two kernels, backward is linear in its two upstream gradients."""
+    from recalgorithm_b200 import ops
+    B, F, D, rows = 65536, 40, 32, 2_500_000
+    gen = torch.Generator(device="cuda").manual_seed(4321)
+    table = torch.empty((rows * F, D), device="cuda").normal_(0, D ** -0.5, generator=gen)
+    off = torch.arange(F + 1, device="cuda") * rows
+    ids = torch.randint(0, rows, (B, F), device="cuda", generator=gen)
+    ids[torch.rand((B, F), device="cuda", generator=gen) < 0.05] = -1
+    tile, fm2 = ops.embed_fm2_fwd(table, off, ids)
+    tile_b, bi = ops.embed_bi_fwd(table, off, ids)
+    assert torch.equal(tile, tile_b)
+    assert_close(bi.double().sum(1, keepdim=True), fm2.double(), TOL, "sum_D bi == fm2")
+    d_tile = torch.randn((B, F, D), device="cuda", generator=gen); d_bi = torch.randn((B, D), device="cuda", generator=gen)
+    r1 = ops.embed_bi_bwd(tile, d_tile, d_bi); r2 = ops.embed_bi_bwd(tile, None, d_bi)
+    assert_close(r1 - r2, d_tile, 1e-5, "bwd linearity")
+    ones = torch.ones((B, D), device="cuda")                              # d_bi = 1 reproduces the FM2 backward with g = 1
+    assert_close(ops.embed_bi_bwd(tile, None, ones), ops.embed_fm2_bwd(tile, None, torch.ones((B,), device="cuda")), 1e-6, "bi bwd == fm2 bwd at g=1")
