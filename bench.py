@@ -26,6 +26,9 @@ import sys
 import threading
 import time
 
+# NCCL writes its banner / NCCL_DEBUG output to stdout by default; stdout of this script carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
