@@ -60,7 +60,20 @@ def _worker(rank, world, port, q):
             v_ = ((i_ >= 0) & (i_ < rows[None, :])).reshape(-1)
             fullg.index_add_(0, (i_ + off[:-1][None, :]).reshape(-1)[v_], g_.reshape(-1, D)[v_].double())
         ok_bwd = torch.allclose(dense, S.full_to_shard(fullg, rank, world), rtol=0, atol=1e-12)
-        q.put((rank, bool(ok_fwd), bool(ok_bwd)))
+        # owner-side Adam on the shard == the shard of Adam on the whole table (oracle.layers_np.adam_sparse_apply), both variants
+        from oracle import layers_np as O
+        ok_adam = True
+        rows_all = np.concatenate([(i_ + off[:-1][None, :]).reshape(-1)[((i_ >= 0) & (i_ < rows[None, :])).reshape(-1)].numpy() for i_ in all_ids])
+        vals_all = np.concatenate([g_.reshape(-1, D)[((i_ >= 0) & (i_ < rows[None, :])).reshape(-1)].numpy() for i_, g_ in zip(all_ids, all_g)])
+        touched_full = torch.zeros(V, dtype=torch.bool); touched_full[torch.as_tensor(rows_all)] = True
+        touched = S.full_to_shard(touched_full[:, None].float(), rank, world)[:, 0] > 0
+        for lazy in (False, True):
+            w, m, v = O.adam_sparse_apply(full.numpy(), np.zeros((V, D)), np.zeros((V, D)), rows_all, vals_all, 1, 0.01, lazy=lazy)
+            zs = torch.zeros_like(shard, dtype=torch.float64)
+            ws, ms, vs = R.adam_reference(shard.double(), zs, zs, dense, touched, 1, 0.01, lazy)
+            for got, want_full in ((ws, w), (ms, m), (vs, v)):
+                ok_adam &= torch.allclose(got, S.full_to_shard(torch.as_tensor(want_full), rank, world), rtol=0, atol=1e-12)
+        q.put((rank, bool(ok_fwd), bool(ok_bwd and ok_adam)))
     finally:
         dist.destroy_process_group()
 
