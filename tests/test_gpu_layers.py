@@ -123,6 +123,6 @@ def test_mini_batch_aware_regularization_reaches_the_tables():
     tile = autograd.lookup(tables, ids)
     B = ids.shape[0]
     reg = L.mini_batch_aware_regularization([tile.reshape(B, -1)], l2_lambda=0.2)
-    assert_close(reg, 0.2 * 0.5 * float(tile.double().pow(2).sum()) / B * torch.ones((), dtype=torch.float64), TOL, "value")
+    assert_close(reg, 0.2 * 0.5 * float(tile.detach().double().pow(2).sum()) / B * torch.ones((), dtype=torch.float64), TOL, "value")
     reg.backward()
     assert_close(tables.grad_slices[0].values, 0.2 * tile.detach().double() / B, TOL, "lambda * e / B")
