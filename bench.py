@@ -28,8 +28,8 @@ import time
 
 # NCCL writes its banner / NCCL_DEBUG output to stdout by default; stdout of this script carries exactly one JSON line
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL ignores NCCL_DEBUG_FILE at level VERSION; WARN prints the same banner
-    os.environ["NCCL_DEBUG"] = "WARN"
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":   # level VERSION (env or /etc/nccl.conf) ignores NCCL_DEBUG_FILE;
+    os.environ["NCCL_DEBUG"] = "WARN"                                # WARN prints the same banner, through the debug file
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
