@@ -6,6 +6,8 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libctr_b200.so")
+CSRC_FEED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc_feed")
+LIB_FEED = os.path.join(CSRC_FEED, "libctr_feed.so")          # host-side feeder (g++, no CUDA)
 
 
 def build(verbose: bool = False, jobs: int | None = None) -> str:
@@ -16,6 +18,12 @@ def build(verbose: bool = False, jobs: int | None = None) -> str:
         print(proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("building libctr_b200.so failed (see output above)")
+    proc = subprocess.run(["make", "-C", CSRC_FEED], capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout)
+        print(proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError("building libctr_feed.so failed (see output above)")
     return LIB
 
 

@@ -1,0 +1,474 @@
+// libctr_feed.so -- TFRecord framing, Example / SequenceExample wire parsing and vocabulary mapping on the host
+// (include/ctr_feed.h).  C++17, no dependencies beyond the standard library.
+#include "../../include/ctr_feed.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <nmmintrin.h>
+#endif
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------------ CRC-32C
+struct CrcTables {
+  uint32_t t[8][256];
+  CrcTables() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
+  }
+};
+const CrcTables& tables() {
+  static const CrcTables T;
+  return T;
+}
+
+uint32_t crc32c_sw(uint32_t c, const uint8_t* p, uint64_t n) {     // slice-by-8
+  const CrcTables& T = tables();
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = T.t[7][w & 0xFF] ^ T.t[6][(w >> 8) & 0xFF] ^ T.t[5][(w >> 16) & 0xFF] ^ T.t[4][(w >> 24) & 0xFF] ^
+        T.t[3][(w >> 32) & 0xFF] ^ T.t[2][(w >> 40) & 0xFF] ^ T.t[1][(w >> 48) & 0xFF] ^ T.t[0][w >> 56];
+    p += 8; n -= 8;
+  }
+  while (n--) c = T.t[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return c;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("sse4.2"))) uint32_t crc32c_hw(uint32_t c, const uint8_t* p, uint64_t n) {
+  uint64_t c64 = c;
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    c64 = _mm_crc32_u64(c64, w);
+    p += 8; n -= 8;
+  }
+  c = (uint32_t)c64;
+  while (n--) c = _mm_crc32_u8(c, *p++);
+  return c;
+}
+#endif
+
+uint32_t crc32c(const uint8_t* p, uint64_t n) {
+#if defined(__x86_64__)
+  static const bool hw = __builtin_cpu_supports("sse4.2");
+  if (hw) return crc32c_hw(0xFFFFFFFFu, p, n) ^ 0xFFFFFFFFu;
+#endif
+  return crc32c_sw(0xFFFFFFFFu, p, n) ^ 0xFFFFFFFFu;
+}
+uint32_t masked(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xA282EAD8u; }
+
+// ------------------------------------------------------------------------------------------------ vocabulary
+struct Vocab {
+  std::string blob;
+  std::unordered_map<std::string_view, int64_t> map;     // views into `blob`
+  int64_t size = 0;
+  void build(std::vector<std::pair<uint64_t, uint64_t>>& spans) {
+    size = (int64_t)spans.size();
+    map.reserve(spans.size() * 2);
+    for (int64_t i = 0; i < size; ++i)
+      map.emplace(std::string_view(blob.data() + spans[i].first, spans[i].second), i);       // first occurrence wins
+  }
+  int64_t find(const uint8_t* p, uint64_t n) const {
+    auto it = map.find(std::string_view(reinterpret_cast<const char*>(p), n));
+    return it == map.end() ? -1 : it->second;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ protobuf wire helpers
+struct Span {
+  const uint8_t* p = nullptr;
+  uint64_t n = 0;
+};
+
+inline bool varint(const uint8_t*& p, const uint8_t* end, uint64_t& v) {
+  v = 0;
+  for (int shift = 0; shift < 64 && p < end; shift += 7) {
+    const uint8_t b = *p++;
+    v |= (uint64_t)(b & 0x7F) << shift;
+    if (!(b & 0x80)) return true;
+  }
+  return false;
+}
+
+// next field of a message: number, wire type and payload (length-delimited: the bytes; varint: value in `val`; fixed: bytes)
+inline bool next_field(const uint8_t*& p, const uint8_t* end, uint32_t& fnum, uint32_t& wt, Span& payload, uint64_t& val) {
+  uint64_t tag;
+  if (!varint(p, end, tag)) return false;
+  fnum = (uint32_t)(tag >> 3);
+  wt = (uint32_t)(tag & 7);
+  switch (wt) {
+    case 0: return varint(p, end, val);
+    case 1: if (end - p < 8) return false; payload = {p, 8}; p += 8; return true;
+    case 2: {
+      uint64_t len;
+      if (!varint(p, end, len) || (uint64_t)(end - p) < len) return false;
+      payload = {p, len}; p += len; return true;
+    }
+    case 5: if (end - p < 4) return false; payload = {p, 4}; p += 4; return true;
+    default: return false;     // groups are not used by these protos
+  }
+}
+
+enum Kind { K_NONE = 0, K_BYTES = 1, K_FLOAT = 2, K_INT64 = 3 };
+
+// Feature{ oneof{ BytesList bytes_list=1; FloatList float_list=2; Int64List int64_list=3 } }: which list, and its bytes
+inline bool feature_list_of(Span feat, Kind& kind, Span& list) {
+  const uint8_t* p = feat.p;
+  const uint8_t* end = feat.p + feat.n;
+  kind = K_NONE;
+  list = {};
+  uint32_t f, wt; Span pl; uint64_t v;
+  while (p < end) {
+    if (!next_field(p, end, f, wt, pl, v)) return false;
+    if (wt == 2 && f >= 1 && f <= 3) { kind = (Kind)f; list = pl; }      // last one wins (oneof)
+  }
+  return true;
+}
+
+struct KeySpec {
+  std::string_view key;
+  bool is_cat;
+  int index;          // into cats[] or dense[]
+};
+
+struct RecordView {                  // the final Feature bytes of every spec key in one record (proto map: last entry wins)
+  std::vector<Span> ctx;             // per spec key
+  std::vector<char> has_ctx;
+  std::vector<Span> flist;           // per spec key: FeatureList bytes (only when read_feature_lists)
+  std::vector<char> has_fl;
+};
+
+struct Parser {
+  const std::vector<KeySpec>& keys;
+  std::unordered_map<std::string_view, int> index;
+  bool read_fl;
+  Parser(const std::vector<KeySpec>& k, bool fl) : keys(k), read_fl(fl) {
+    for (int i = 0; i < (int)k.size(); ++i) index.emplace(k[i].key, i);
+  }
+
+  // map<string, X> entries of `msg` (field 1 = entry{key=1, value=2}); records the value span of every spec key
+  bool scan_map(Span msg, std::vector<Span>& out, std::vector<char>& has) const {
+    const uint8_t* p = msg.p;
+    const uint8_t* end = msg.p + msg.n;
+    uint32_t f, wt; Span pl; uint64_t v;
+    while (p < end) {
+      if (!next_field(p, end, f, wt, pl, v)) return false;
+      if (f != 1 || wt != 2) continue;
+      const uint8_t* q = pl.p;
+      const uint8_t* qe = pl.p + pl.n;
+      Span key{}, val{};
+      uint32_t f2, wt2; Span pl2; uint64_t v2;
+      while (q < qe) {
+        if (!next_field(q, qe, f2, wt2, pl2, v2)) return false;
+        if (wt2 == 2 && f2 == 1) key = pl2;
+        else if (wt2 == 2 && f2 == 2) val = pl2;
+      }
+      auto it = index.find(std::string_view(reinterpret_cast<const char*>(key.p), key.n));
+      if (it != index.end()) { out[it->second] = val; has[it->second] = 1; }
+    }
+    return true;
+  }
+
+  bool view(Span rec, RecordView& rv) const {
+    const size_t K = keys.size();
+    rv.ctx.assign(K, Span{}); rv.has_ctx.assign(K, 0);
+    rv.flist.assign(K, Span{}); rv.has_fl.assign(K, 0);
+    const uint8_t* p = rec.p;
+    const uint8_t* end = rec.p + rec.n;
+    uint32_t f, wt; Span pl; uint64_t v;
+    while (p < end) {
+      if (!next_field(p, end, f, wt, pl, v)) return false;
+      if (wt != 2) continue;
+      if (f == 1) {                          // Example.features == SequenceExample.context
+        if (!scan_map(pl, rv.ctx, rv.has_ctx)) return false;
+      } else if (f == 2 && read_fl) {        // SequenceExample.feature_lists (unknown field 2 when parsed as an Example)
+        if (!scan_map(pl, rv.flist, rv.has_fl)) return false;
+      }
+    }
+    return true;
+  }
+};
+
+// values of a BytesList: calls fn(ptr, len) per value
+template <typename Fn>
+inline bool for_each_bytes(Span list, Fn&& fn) {
+  const uint8_t* p = list.p;
+  const uint8_t* end = list.p + list.n;
+  uint32_t f, wt; Span pl; uint64_t v;
+  while (p < end) {
+    if (!next_field(p, end, f, wt, pl, v)) return false;
+    if (f == 1 && wt == 2) fn(pl.p, pl.n);
+  }
+  return true;
+}
+
+// a categorical key of one record: context Feature first, else (optionally) every step of its FeatureList
+template <typename Fn>
+inline int cat_values(const RecordView& rv, int k, bool read_fl, const char* key, Fn&& fn) {
+  if (rv.has_ctx[k]) {
+    Kind kind; Span list;
+    if (!feature_list_of(rv.ctx[k], kind, list)) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized Example.", key);
+    if (kind == K_NONE) return CTR_FEED_OK;
+    if (kind != K_BYTES) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Data types don't match. Expected type: string", key);
+    if (!for_each_bytes(list, fn)) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized Example.", key);
+    return CTR_FEED_OK;
+  }
+  if (read_fl && rv.has_fl[k]) {             // FeatureList{ repeated Feature feature = 1 }
+    const uint8_t* p = rv.flist[k].p;
+    const uint8_t* end = p + rv.flist[k].n;
+    uint32_t f, wt; Span pl; uint64_t v;
+    while (p < end) {
+      if (!next_field(p, end, f, wt, pl, v)) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized SequenceExample.", key);
+      if (f != 1 || wt != 2) continue;
+      Kind kind; Span list;
+      if (!feature_list_of(pl, kind, list)) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized SequenceExample.", key);
+      if (kind == K_NONE) continue;
+      if (kind != K_BYTES) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Data types don't match. Expected type: string", key);
+      if (!for_each_bytes(list, fn)) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized SequenceExample.", key);
+    }
+  }
+  return CTR_FEED_OK;
+}
+
+// FloatList{ repeated float value = 1 [packed] }: packed (wire type 2) or one fixed32 per value (wire type 5)
+inline int dense_values(const RecordView& rv, int k, const ctr_feed_dense_t& d, int64_t b) {
+  float* dst = d.out + b * d.width;
+  for (int64_t i = 0; i < d.width; ++i) dst[i] = d.default_value;
+  if (!rv.has_ctx[k]) return CTR_FEED_OK;
+  Kind kind; Span list;
+  if (!feature_list_of(rv.ctx[k], kind, list)) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized Example.", d.key);
+  if (kind == K_NONE) return CTR_FEED_OK;
+  if (kind != K_FLOAT) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Data types don't match. Expected type: float", d.key);
+  int64_t n = 0;
+  float tmp;
+  const uint8_t* p = list.p;
+  const uint8_t* end = list.p + list.n;
+  uint32_t f, wt; Span pl; uint64_t v;
+  while (p < end) {
+    if (!next_field(p, end, f, wt, pl, v)) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized Example.", d.key);
+    if (f != 1) continue;
+    if (wt == 2) {
+      if (pl.n % 4) return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized Example.", d.key);
+      for (uint64_t o = 0; o < pl.n; o += 4, ++n)
+        if (n < d.width) { memcpy(&tmp, pl.p + o, 4); dst[n] = tmp; }
+    } else if (wt == 5) {
+      if (n < d.width) { memcpy(&tmp, pl.p, 4); dst[n] = tmp; }
+      ++n;
+    }
+  }
+  if (n == 0) { for (int64_t i = 0; i < d.width; ++i) dst[i] = d.default_value; return CTR_FEED_OK; }
+  if (n != d.width)
+    return fail(CTR_FEED_ERR_PROTO, "Key: %s. Can't parse serialized Example: expected %lld values, got %lld", d.key, (long long)d.width,
+                (long long)n);
+  return CTR_FEED_OK;
+}
+
+template <typename Fn>
+int run_chunks(int64_t B, int nthreads, Fn&& fn) {              // fn(thread, b0, b1) -> rc; first error wins
+  std::vector<int> rcs(nthreads, CTR_FEED_OK);
+  std::vector<std::string> msgs(nthreads);
+  std::vector<std::thread> th;
+  const int64_t per = (B + nthreads - 1) / nthreads;
+  auto body = [&](int t) {
+    const int64_t b0 = t * per, b1 = std::min<int64_t>(B, b0 + per);
+    if (b0 < b1) rcs[t] = fn(t, b0, b1);
+    if (rcs[t] != CTR_FEED_OK) msgs[t] = g_err;                 // g_err is thread-local: carry the text to the caller
+  };
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(body, t);
+  body(0);
+  for (auto& x : th) x.join();
+  for (int t = 0; t < nthreads; ++t)
+    if (rcs[t] != CTR_FEED_OK) return fail(rcs[t], "%s", msgs[t].c_str());
+  return CTR_FEED_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ctr_feed_last_error(void) { return g_err; }
+int ctr_feed_version(void) { return 1; }
+
+uint32_t ctr_feed_crc32c(const uint8_t* data, uint64_t n) { return (data || n == 0) ? crc32c(data, n) : 0; }
+uint32_t ctr_feed_masked_crc32c(const uint8_t* data, uint64_t n) { return masked(ctr_feed_crc32c(data, n)); }
+
+int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, uint64_t* offsets, uint64_t* lengths,
+                                int64_t max_records, uint64_t* consumed) {
+  if ((!buf && n) || max_records < 0 || (max_records > 0 && (!offsets || !lengths)))
+    return fail(CTR_FEED_ERR_ARG, "ctr_feed_tfrecord_index: bad arguments");
+  uint64_t pos = 0;
+  int64_t count = 0;
+  while (pos < n) {
+    if (max_records > 0 && count == max_records) break;
+    if (n - pos < 12) return fail(CTR_FEED_ERR_TRUNCATED, "truncated record header at byte %llu", (unsigned long long)pos);
+    uint64_t len;
+    uint32_t len_crc;
+    memcpy(&len, buf + pos, 8);
+    memcpy(&len_crc, buf + pos + 8, 4);
+    if (verify_crc && masked(crc32c(buf + pos, 8)) != len_crc)
+      return fail(CTR_FEED_ERR_CRC, "corrupted record length at byte %llu (crc mismatch)", (unsigned long long)pos);
+    if (len > n - pos - 12 || n - pos - 12 - len < 4)
+      return fail(CTR_FEED_ERR_TRUNCATED, "truncated record at byte %llu", (unsigned long long)pos);
+    const uint8_t* data = buf + pos + 12;
+    uint32_t data_crc;
+    memcpy(&data_crc, data + len, 4);
+    if (verify_crc && masked(crc32c(data, len)) != data_crc)
+      return fail(CTR_FEED_ERR_CRC, "corrupted record data at byte %llu (crc mismatch)", (unsigned long long)pos);
+    if (max_records > 0) { offsets[count] = pos + 12; lengths[count] = len; }
+    ++count;
+    pos += 12 + len + 4;
+  }
+  if (consumed) *consumed = pos;
+  return count;
+}
+
+void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens) {
+  if (n_tokens < 0 || (n_tokens > 0 && (!offsets || (!blob && offsets[n_tokens] > 0)))) {
+    fail(CTR_FEED_ERR_ARG, "ctr_feed_vocab_create: bad arguments");
+    return nullptr;
+  }
+  Vocab* v = new Vocab();
+  std::vector<std::pair<uint64_t, uint64_t>> spans((size_t)n_tokens);
+  if (n_tokens > 0) {
+    v->blob.assign(reinterpret_cast<const char*>(blob) + offsets[0], offsets[n_tokens] - offsets[0]);
+    for (int64_t i = 0; i < n_tokens; ++i) spans[i] = {offsets[i] - offsets[0], offsets[i + 1] - offsets[i]};
+  }
+  v->build(spans);
+  return v;
+}
+
+void* ctr_feed_vocab_load(const char* path) {
+  if (!path) { fail(CTR_FEED_ERR_ARG, "ctr_feed_vocab_load: null path"); return nullptr; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { fail(CTR_FEED_ERR_IO, "ctr_feed_vocab_load: cannot open %s", path); return nullptr; }
+  Vocab* v = new Vocab();
+  char chunk[1 << 16];
+  size_t got;
+  while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) v->blob.append(chunk, got);
+  fclose(f);
+  std::vector<std::pair<uint64_t, uint64_t>> spans;
+  uint64_t start = 0;
+  const uint64_t n = v->blob.size();
+  for (uint64_t i = 0; i <= n; ++i) {
+    if (i == n || v->blob[i] == '\n') {
+      if (i == n && start == n) break;                      // no trailing empty line after the final newline
+      uint64_t end = i;
+      while (end > start && (v->blob[end - 1] == '\r' || v->blob[end - 1] == '\n')) --end;
+      spans.emplace_back(start, end - start);
+      start = i + 1;
+    }
+  }
+  v->build(spans);
+  return v;
+}
+
+int64_t ctr_feed_vocab_size(const void* vocab) { return vocab ? static_cast<const Vocab*>(vocab)->size : -1; }
+void ctr_feed_vocab_destroy(void* vocab) { delete static_cast<Vocab*>(vocab); }
+
+int ctr_feed_vocab_lookup(const void* vocab, const uint8_t* blob, const uint64_t* offsets, int64_t n_keys, int64_t* ids_out) {
+  if (!vocab || n_keys < 0 || (n_keys > 0 && (!offsets || !ids_out))) return fail(CTR_FEED_ERR_ARG, "ctr_feed_vocab_lookup: bad arguments");
+  const Vocab* v = static_cast<const Vocab*>(vocab);
+  for (int64_t i = 0; i < n_keys; ++i) ids_out[i] = v->find(blob + offsets[i], offsets[i + 1] - offsets[i]);
+  return CTR_FEED_OK;
+}
+
+int ctr_feed_parse_examples(const uint8_t* buf, const uint64_t* offsets, const uint64_t* lengths, int64_t B, ctr_feed_cat_t* cats,
+                            int64_t n_cat, ctr_feed_dense_t* dense, int64_t n_dense, int read_feature_lists, int num_threads) {
+  if (B < 0 || n_cat < 0 || n_dense < 0 || (B > 0 && (!buf || !offsets || !lengths)) || (n_cat > 0 && !cats) || (n_dense > 0 && !dense))
+    return fail(CTR_FEED_ERR_ARG, "ctr_feed_parse_examples: bad arguments");
+  std::vector<KeySpec> keys;
+  for (int64_t k = 0; k < n_cat; ++k) {
+    if (!cats[k].key || !cats[k].vocab || !cats[k].row_offsets || cats[k].capacity < 0 || (cats[k].capacity > 0 && !cats[k].ids))
+      return fail(CTR_FEED_ERR_ARG, "ctr_feed_parse_examples: categorical spec %lld is incomplete", (long long)k);
+    keys.push_back({std::string_view(cats[k].key), true, (int)k});
+  }
+  for (int64_t k = 0; k < n_dense; ++k) {
+    if (!dense[k].key || dense[k].width < 1 || (B > 0 && !dense[k].out))
+      return fail(CTR_FEED_ERR_ARG, "ctr_feed_parse_examples: dense spec %lld is incomplete", (long long)k);
+    keys.push_back({std::string_view(dense[k].key), false, (int)k});
+  }
+  for (size_t a = 0; a < keys.size(); ++a)
+    for (size_t b = a + 1; b < keys.size(); ++b)
+      if (keys[a].key == keys[b].key)
+        return fail(CTR_FEED_ERR_ARG, "ctr_feed_parse_examples: key %s appears twice in the spec", std::string(keys[a].key).c_str());
+  int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min({nt, 32, (int)std::max<int64_t>(1, B / 64)}));
+  const Parser parser(keys, read_feature_lists != 0);
+
+  // pass 1: values per (categorical key, record) -> row_offsets; dense keys are final after this pass
+  int rc = run_chunks(B, nt, [&](int, int64_t b0, int64_t b1) -> int {
+    RecordView rv;
+    for (int64_t b = b0; b < b1; ++b) {
+      if (!parser.view(Span{buf + offsets[b], lengths[b]}, rv)) return fail(CTR_FEED_ERR_PROTO, "Could not parse example input, record %lld", (long long)b);
+      for (size_t i = 0; i < keys.size(); ++i) {
+        if (keys[i].is_cat) {
+          int64_t cnt = 0;
+          int r = cat_values(rv, (int)i, read_feature_lists != 0, cats[keys[i].index].key, [&](const uint8_t*, uint64_t) { ++cnt; });
+          if (r) return r;
+          cats[keys[i].index].row_offsets[b + 1] = cnt;
+        } else {
+          int r = dense_values(rv, (int)i, dense[keys[i].index], b);
+          if (r) return r;
+        }
+      }
+    }
+    return CTR_FEED_OK;
+  });
+  if (rc) return rc;
+  bool short_buf = false;
+  for (int64_t k = 0; k < n_cat; ++k) {
+    int64_t* ro = cats[k].row_offsets;
+    ro[0] = 0;
+    for (int64_t b = 0; b < B; ++b) ro[b + 1] += ro[b];
+    cats[k].needed = ro[B];
+    if (ro[B] > cats[k].capacity) short_buf = true;
+  }
+  if (short_buf) return fail(CTR_FEED_ERR_CAPACITY, "ctr_feed_parse_examples: an ids buffer is too small (see `needed`)");
+  if (n_cat == 0) return CTR_FEED_OK;
+
+  // pass 2: vocabulary ids at their final positions
+  return run_chunks(B, nt, [&](int, int64_t b0, int64_t b1) -> int {
+    RecordView rv;
+    for (int64_t b = b0; b < b1; ++b) {
+      if (!parser.view(Span{buf + offsets[b], lengths[b]}, rv)) return fail(CTR_FEED_ERR_PROTO, "Could not parse example input, record %lld", (long long)b);
+      for (size_t i = 0; i < keys.size(); ++i) {
+        if (!keys[i].is_cat) continue;
+        const ctr_feed_cat_t& c = cats[keys[i].index];
+        const Vocab* v = static_cast<const Vocab*>(c.vocab);
+        int64_t* dst = c.ids + c.row_offsets[b];
+        int r = cat_values(rv, (int)i, read_feature_lists != 0, c.key, [&](const uint8_t* p, uint64_t n) { *dst++ = v->find(p, n); });
+        if (r) return r;
+      }
+    }
+    return CTR_FEED_OK;
+  });
+}
+
+}  // extern "C"

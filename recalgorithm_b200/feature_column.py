@@ -160,10 +160,37 @@ class LookupContext:
         return out
 
 
+def _ids_of(col: CategoricalColumn, values) -> np.ndarray:
+    """Vocabulary ids of a ragged feature's values; values that are already int64 ids (parse_example_native) pass through."""
+    if isinstance(values, np.ndarray) and values.dtype == np.int64:
+        return values
+    return col.vocabulary.lookup(values) if len(values) else np.zeros((0,), np.int64)
+
+
 def _ragged_ids(col: CategoricalColumn, features, device) -> Tuple[torch.Tensor, torch.Tensor]:
     values, offsets = features[col.key]
-    ids = col.vocabulary.lookup(values) if len(values) else np.zeros((0,), np.int64)
-    return torch.from_numpy(ids).to(device), torch.from_numpy(np.asarray(offsets, np.int64)).to(device)
+    ids = _ids_of(col, values)
+    return torch.from_numpy(np.ascontiguousarray(ids)).to(device), torch.from_numpy(np.asarray(offsets, np.int64)).to(device)
+
+
+def parse_example_native(buf, offsets, lengths, feature_columns, read_feature_lists: bool = False, num_threads: int = 0):
+    """``tf.parse_example(batch, make_parse_example_spec(feature_columns))`` + the vocabulary lookups in one native call
+    (libctr_feed.so, include/ctr_feed.h): records are ``buf[offsets[b] : offsets[b] + lengths[b]]`` (see
+    io.native.read_tfrecord_file).  Returns the same ``features`` dict input_layer / sequence_input_layer / indicator_dense
+    take, with categorical entries already mapped: key -> (ids int64, row_offsets int64 (B+1,))."""
+    from .io import native
+    cats, dense = {}, {}
+    for c in feature_columns:
+        if isinstance(c, NumericColumn):
+            dense[c.key] = (int(np.prod(c.shape)), float(c.default_value))
+        else:
+            base = c if isinstance(c, CategoricalColumn) else c.categorical_column
+            cats[base.key] = base.vocabulary.native()
+    out = native.parse_examples(buf, offsets, lengths, cats, dense, read_feature_lists=read_feature_lists, num_threads=num_threads)
+    for c in feature_columns:
+        if isinstance(c, NumericColumn):
+            out[c.key] = out[c.key].reshape((out[c.key].shape[0],) + tuple(c.shape))
+    return out
 
 
 def _table_for(col: EmbeddingColumn) -> torch.nn.Parameter:
@@ -218,7 +245,7 @@ def sequence_input_layer(features, feature_columns, ctx: Optional[LookupContext]
         lens = np.diff(offsets)
         B, T = len(lens), int(lens.max()) if len(lens) else 0
         table = _table_for(c)
-        ids = c.categorical_column.vocabulary.lookup(values) if len(values) else np.zeros((0,), np.int64)
+        ids = _ids_of(c.categorical_column, values)
         padded = np.full((B, max(T, 1)), -1, np.int64)        # -1 -> zero vector == zero padding
         for b in range(B):
             padded[b, :lens[b]] = ids[offsets[b]:offsets[b + 1]]
@@ -251,7 +278,7 @@ def indicator_dense(features, indicator_columns, units: int = 1, name: str = "fm
         offsets = np.asarray(offsets)
         if np.any(np.diff(offsets) > 1):
             raise ValueError("indicator_dense: multi-valued indicator columns are not implemented")
-        got = c.categorical_column.vocabulary.lookup(values) if len(values) else np.zeros((0,), np.int64)
+        got = _ids_of(c.categorical_column, values)
         has = np.diff(offsets) == 1
         col_ids = np.full((B,), -1, np.int64)
         col_ids[has] = got

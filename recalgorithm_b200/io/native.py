@@ -1,0 +1,206 @@
+"""ctypes binding of libctr_feed.so (include/ctr_feed.h): the native twins of tfrecord.py / example.py / vocab.py.
+
+    buf, offsets, lengths = native.read_tfrecord_file(path)                # index a whole file (CRC-32C verified)
+    vocab = native.Vocabulary(path_or_tokens)                              # OOV / '' -> -1
+    out = native.parse_examples(buf, offsets[:B], lengths[:B], {"userid": vocab, ...}, {"read_comment": (1, 0.0)})
+    ids, row_offsets = out["userid"]                                       # ragged int64 ids, (B+1,) offsets
+
+Same semantics as recalgorithm_b200.io.parse_example + VocabularyFile.lookup (tests/test_feed_native.py compares them),
+multi-threaded, no Python in the per-record loop.  The library is built in-tree by recalgorithm_b200/build.py.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc_feed", "libctr_feed.so")
+
+ERR_ARG, ERR_IO, ERR_TRUNCATED, ERR_CRC, ERR_PROTO, ERR_CAPACITY = -1, -2, -4, -5, -6, -7
+
+
+class _Cat(ctypes.Structure):
+    _fields_ = [("key", ctypes.c_char_p), ("vocab", ctypes.c_void_p), ("ids", ctypes.c_void_p), ("capacity", ctypes.c_int64),
+                ("row_offsets", ctypes.c_void_p), ("needed", ctypes.c_int64)]
+
+
+class _Dense(ctypes.Structure):
+    _fields_ = [("key", ctypes.c_char_p), ("width", ctypes.c_int64), ("default_value", ctypes.c_float), ("out", ctypes.c_void_p)]
+
+
+_P, _I = ctypes.c_void_p, ctypes.c_int64
+SIGNATURES = {
+    "ctr_feed_last_error": (ctypes.c_char_p, []),
+    "ctr_feed_version": (ctypes.c_int, []),
+    "ctr_feed_crc32c": (ctypes.c_uint32, [_P, ctypes.c_uint64]),
+    "ctr_feed_masked_crc32c": (ctypes.c_uint32, [_P, ctypes.c_uint64]),
+    "ctr_feed_tfrecord_index": (_I, [_P, ctypes.c_uint64, ctypes.c_int, _P, _P, _I, _P]),
+    "ctr_feed_vocab_create": (_P, [_P, _P, _I]),
+    "ctr_feed_vocab_load": (_P, [ctypes.c_char_p]),
+    "ctr_feed_vocab_size": (_I, [_P]),
+    "ctr_feed_vocab_destroy": (None, [_P]),
+    "ctr_feed_vocab_lookup": (ctypes.c_int, [_P, _P, _P, _I, _P]),
+    "ctr_feed_parse_examples": (ctypes.c_int, [_P, _P, _P, _I, ctypes.POINTER(_Cat), _I, ctypes.POINTER(_Dense), _I, ctypes.c_int,
+                                               ctypes.c_int]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m recalgorithm_b200.build` (there is no fallback inside this module; "
+                               "the pure-Python readers live in recalgorithm_b200.io.tfrecord / example / vocab)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class FeedError(RuntimeError):
+    def __init__(self, code: int):
+        super().__init__(f"libctr_feed error {code}: {lib().ctr_feed_last_error().decode('utf-8', 'replace')}")
+        self.code = code
+
+
+class FeedValueError(FeedError, ValueError):
+    """Malformed wire data or a feature of the wrong kind / size (tf.parse_example raises InvalidArgumentError)."""
+
+
+class FeedIOError(FeedError, IOError):
+    """Truncated or corrupted TFRecord."""
+
+
+def _raise(code: int):
+    if code in (ERR_TRUNCATED, ERR_CRC, ERR_IO):
+        raise FeedIOError(code)
+    if code in (ERR_PROTO, ERR_ARG):
+        raise FeedValueError(code)
+    raise FeedError(code)
+
+
+def _u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        return data
+    return np.frombuffer(data, dtype=np.uint8)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None or a.size == 0 else a.ctypes.data
+
+
+def crc32c(data) -> int:
+    a = _u8(data)
+    return int(lib().ctr_feed_crc32c(_ptr(a), a.size))
+
+
+def masked_crc32c(data) -> int:
+    a = _u8(data)
+    return int(lib().ctr_feed_masked_crc32c(_ptr(a), a.size))
+
+
+def index_tfrecord(buf, verify: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """(offsets, lengths) uint64 arrays of the record payloads inside a TFRecord byte buffer."""
+    a = _u8(buf)
+    n = lib().ctr_feed_tfrecord_index(_ptr(a), a.size, int(verify), None, None, 0, None)
+    if n < 0:
+        _raise(int(n))
+    offsets, lengths = np.empty(n, np.uint64), np.empty(n, np.uint64)
+    if n:
+        got = lib().ctr_feed_tfrecord_index(_ptr(a), a.size, 0, offsets.ctypes.data, lengths.ctypes.data, n, None)
+        assert got == n
+    return offsets, lengths
+
+
+def read_tfrecord_file(path: str, verify: bool = True) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Whole file -> (bytes as uint8 array, offsets, lengths).  tf.data.TFRecordDataset(path) without the iterator."""
+    buf = np.fromfile(path, dtype=np.uint8)
+    offsets, lengths = index_tfrecord(buf, verify)
+    return buf, offsets, lengths
+
+
+def _blob(items: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    offsets = np.zeros(len(items) + 1, np.uint64)
+    if len(items):
+        np.cumsum([len(x) for x in items], out=offsets[1:])
+    return np.frombuffer(b"".join(items), dtype=np.uint8), offsets
+
+
+class Vocabulary:
+    """categorical_column_with_vocabulary_file semantics: id = 0-based line of the first occurrence, OOV -> -1."""
+
+    def __init__(self, source: Union[str, Sequence[bytes]]):
+        L = lib()
+        if isinstance(source, str):
+            self._h = L.ctr_feed_vocab_load(source.encode())
+        else:
+            toks = [t if isinstance(t, bytes) else str(t).encode() for t in source]
+            blob, offs = _blob(toks)
+            self._h = L.ctr_feed_vocab_create(_ptr(blob), offs.ctypes.data, len(toks))
+        if not self._h:
+            raise FeedIOError(ERR_IO)
+        self.size = int(L.ctr_feed_vocab_size(self._h))
+
+    def __len__(self) -> int:
+        return self.size
+
+    def lookup(self, keys: Sequence[bytes]) -> np.ndarray:
+        keys = list(keys)
+        blob, offs = _blob(keys)
+        out = np.empty(len(keys), np.int64)
+        rc = lib().ctr_feed_vocab_lookup(self._h, _ptr(blob), offs.ctypes.data, len(keys), _ptr(out))
+        if rc:
+            _raise(rc)
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ctr_feed_vocab_destroy(self._h)
+            self._h = None
+
+
+def parse_examples(buf, offsets: np.ndarray, lengths: np.ndarray, categorical: Dict[str, Vocabulary],
+                   dense: Optional[Dict[str, Tuple[int, float]]] = None, read_feature_lists: bool = False,
+                   num_threads: int = 0) -> Dict[str, object]:
+    """tf.parse_example + vocabulary lookup over records ``buf[offsets[b] : offsets[b] + lengths[b]]``.
+
+    categorical: key -> Vocabulary  => out[key] = (ids int64 (n,), row_offsets int64 (B+1,))   (missing key: empty row)
+    dense: key -> (width, default)  => out[key] = float32 (B, width)"""
+    a = _u8(buf)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+    B = int(offsets.size)
+    dense = dense or {}
+    ckeys, dkeys = list(categorical), list(dense)
+    cats = (_Cat * max(1, len(ckeys)))()
+    dens = (_Dense * max(1, len(dkeys)))()
+    cap = {k: max(16, 2 * B) for k in ckeys}
+    row_off = {k: np.zeros(B + 1, np.int64) for k in ckeys}
+    dense_out = {k: np.empty((B, int(dense[k][0])), np.float32) for k in dkeys}
+    for i, k in enumerate(dkeys):
+        dens[i] = _Dense(k.encode(), int(dense[k][0]), float(dense[k][1]), dense_out[k].ctypes.data)
+    for _ in range(2):                                       # second round only if a ragged buffer was too small
+        ids = {k: np.empty(cap[k], np.int64) for k in ckeys}
+        for i, k in enumerate(ckeys):
+            cats[i] = _Cat(k.encode(), categorical[k]._h, ids[k].ctypes.data, cap[k], row_off[k].ctypes.data, 0)
+        rc = lib().ctr_feed_parse_examples(_ptr(a), _ptr(offsets), _ptr(lengths), B, cats, len(ckeys), dens, len(dkeys),
+                                           int(read_feature_lists), int(num_threads))
+        if rc == ERR_CAPACITY:
+            for i, k in enumerate(ckeys):
+                cap[k] = max(cap[k], int(cats[i].needed))
+            continue
+        if rc:
+            _raise(rc)
+        break
+    out: Dict[str, object] = dict(dense_out)
+    for i, k in enumerate(ckeys):
+        out[k] = (ids[k][: int(cats[i].needed)], row_off[k])
+    return out

@@ -18,12 +18,21 @@ class VocabularyFile:
         else:
             tokens = [t if isinstance(t, bytes) else str(t).encode() for t in source]
         self.size = len(tokens)                       # vocabulary_size=None -> number of lines
+        self.tokens = tokens                          # kept for the native twin (io.native.Vocabulary), built on demand
+        self._native = None
         self._table = {}
         for i, t in enumerate(tokens):
             self._table.setdefault(t, i)
 
     def __len__(self) -> int:
         return self.size
+
+    def native(self):
+        """The same vocabulary inside libctr_feed.so (used by feature_column.parse_example_native)."""
+        if self._native is None:
+            from . import native as _n
+            self._native = _n.Vocabulary(self.tokens)
+        return self._native
 
     def lookup(self, keys: Iterable[bytes]) -> np.ndarray:
         get = self._table.get

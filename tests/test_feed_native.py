@@ -1,0 +1,157 @@
+"""CPU tests of libctr_feed.so (include/ctr_feed.h) against the pure-Python readers and the wire-format known answers:
+CRC-32C vectors, TFRecord framing and corruption handling, Example / SequenceExample parsing incl. the reference's
+SequenceExample-parsed-as-Example quirk, FixedLen defaults, vocabulary lookup, multi-threaded == single-threaded."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from recalgorithm_b200 import io as cio
+from recalgorithm_b200.io import native, tfrecord
+from test_io import wechat_record
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ctr_feed.h")).read()
+    declared = set(re.findall(r"\b(ctr_feed_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    L = ctypes.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert native.lib().ctr_feed_version() == 1
+
+
+def test_crc32c_known_answers_and_agreement():
+    assert native.crc32c(b"123456789") == 0xE3069283 and native.crc32c(b"") == 0 and native.crc32c(bytes(32)) == 0x8A9136AA
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 8, 9, 63, 1000, 4097):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert native.crc32c(data) == tfrecord.crc32c(data) and native.masked_crc32c(data) == tfrecord.masked_crc32c(data)
+
+
+def test_tfrecord_index_roundtrip_and_corruption(tmp_path):
+    recs = [b"", b"a", os.urandom(1000), b"x" * 70000]
+    p = str(tmp_path / "t.tfrecord")
+    cio.write_records(p, recs)
+    buf, off, ln = native.read_tfrecord_file(p)
+    assert [buf[int(o): int(o + l)].tobytes() for o, l in zip(off, ln)] == recs
+    raw = bytearray(open(p, "rb").read())
+    raw[12 + 0 + 4 + 12 + 0] ^= 0xFF                              # flip a data byte of the 2nd record
+    with pytest.raises(IOError):
+        native.index_tfrecord(bytes(raw))
+    assert len(native.index_tfrecord(bytes(raw), verify=False)[0]) == 4
+    with pytest.raises(IOError):
+        native.index_tfrecord(bytes(raw[:20]), verify=False)
+    bad_len = bytearray(raw); bad_len[0] ^= 1
+    with pytest.raises(IOError):
+        native.index_tfrecord(bytes(bad_len))
+    assert len(native.index_tfrecord(b"")[0]) == 0
+
+
+def test_vocabulary_matches_python(tmp_path):
+    p = tmp_path / "userid.txt"
+    p.write_bytes(b"userid_8\nuserid_3\r\nuserid_11\nuserid_3\n")
+    for v in (native.Vocabulary(str(p)), native.Vocabulary([b"userid_8", b"userid_3", b"userid_11", b"userid_3"])):
+        assert len(v) == 4
+        assert v.lookup([b"userid_3", b"", b"userid_999", b"userid_8", b"userid_11"]).tolist() == [1, -1, -1, 0, 2]
+    (tmp_path / "nonl.txt").write_bytes(b"a\nb")
+    assert native.Vocabulary(str(tmp_path / "nonl.txt")).lookup([b"b", b"a"]).tolist() == [1, 0]
+    pyv = cio.VocabularyFile(str(p))
+    keys = [b"userid_%d" % i for i in range(15)] + [b""]
+    assert native.Vocabulary(str(p)).lookup(keys).tolist() == pyv.lookup(keys).tolist()
+    with pytest.raises(IOError):
+        native.Vocabulary(str(tmp_path / "missing.txt"))
+
+
+@pytest.mark.parametrize("read_fl", [False, True])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_parse_examples_matches_python_reader(tmp_path, read_fl, threads):
+    rng = np.random.default_rng(3)
+    B = 300
+    recs = [wechat_record(rng, i)[0] for i in range(B)]
+    p = str(tmp_path / "train.tfrecord")
+    cio.write_records(p, recs)
+    cat_keys = ["userid", "feedid", "device", "authorid", "bgm_song_id", "bgm_singer_id", "his_read_comment_7d_seq", "manual_tag_list",
+                "not_in_the_file"]
+    prefix = {"his_read_comment_7d_seq": "feedid", "manual_tag_list": "manual_tag"}
+    toks = {k: [f"{prefix.get(k, k)}_{i}".encode() for i in range(40)] for k in cat_keys}
+    spec = {k: cio.VarLenFeature() for k in cat_keys}
+    spec.update({"videoplayseconds": cio.FixedLenFeature(), "read_comment": cio.FixedLenFeature(), "missing_dense": cio.FixedLenFeature(default_value=-2.5)})
+    want = cio.parse_example(list(cio.read_records(p)), spec, read_feature_lists=read_fl)
+    buf, off, ln = native.read_tfrecord_file(p)
+    got = native.parse_examples(buf, off, ln, {k: native.Vocabulary(toks[k]) for k in cat_keys},
+                                {"videoplayseconds": (1, 0.0), "read_comment": (1, 0.0), "missing_dense": (1, -2.5)},
+                                read_feature_lists=read_fl, num_threads=threads)
+    for k in cat_keys:
+        vals, offs = want[k]
+        ids, row_offsets = got[k]
+        assert np.array_equal(row_offsets, offs), k
+        assert ids.tolist() == cio.VocabularyFile(toks[k]).lookup(vals).tolist(), k
+    if not read_fl:
+        assert got["his_read_comment_7d_seq"][1][-1] == 0          # feature_lists dropped (parity note 8)
+    else:
+        assert got["his_read_comment_7d_seq"][1][-1] > 0
+    for k in ("videoplayseconds", "read_comment", "missing_dense"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.all(got["missing_dense"] == -2.5) and (got["bgm_song_id"][0] == -1).any()
+
+
+def test_parse_examples_kinds_errors_and_unpacked_floats():
+    ex = [cio.encode_example({"a": ("bytes", [b"x", b"y", b"x"]), "f": ("float", [1.5, -2.0]), "i": ("int64", [3])}),
+          cio.encode_example({"a": ("bytes", []), "f": ("float", [])}),
+          cio.encode_example({})]
+    blob = b"".join(ex)
+    off = np.cumsum([0] + [len(e) for e in ex[:-1]]).astype(np.uint64)
+    ln = np.array([len(e) for e in ex], np.uint64)
+    v = native.Vocabulary([b"x", b"y"])
+    out = native.parse_examples(blob, off, ln, {"a": v}, {"f": (2, 9.0)})
+    assert out["a"][0].tolist() == [0, 1, 0] and out["a"][1].tolist() == [0, 3, 3, 3]
+    assert out["f"].tolist() == [[1.5, -2.0], [9.0, 9.0], [9.0, 9.0]]
+    with pytest.raises(ValueError):                                  # wrong number of values for a FixedLen key
+        native.parse_examples(blob, off, ln, {}, {"f": (3, 0.0)})
+    with pytest.raises(ValueError):                                  # kind mismatch: int64 feature under a string key
+        native.parse_examples(blob, off, ln, {"i": v}, {})
+    with pytest.raises(ValueError):                                  # truncated proto
+        native.parse_examples(ex[0][:-2], np.array([0], np.uint64), np.array([len(ex[0]) - 2], np.uint64), {"a": v}, {})
+    # a FloatList written UNPACKED (one fixed32 per value, wire type 5) is legal proto input
+    feat = b"\x12" + bytes([10]) + b"\x0d" + np.float32(1.5).tobytes() + b"\x0d" + np.float32(-2.0).tobytes()      # Feature{float_list{1:fixed32,1:fixed32}}
+    entry = b"\x0a\x01f" + b"\x12" + bytes([len(feat)]) + feat
+    features = b"\x0a" + bytes([len(entry)]) + entry
+    rec = b"\x0a" + bytes([len(features)]) + features
+    out2 = native.parse_examples(rec, np.array([0], np.uint64), np.array([len(rec)], np.uint64), {}, {"f": (2, 0.0)})
+    assert out2["f"].tolist() == [[1.5, -2.0]]
+    assert cio.parse_single(rec)[0]["f"] == ("float", [1.5, -2.0])
+
+
+def test_parse_example_native_equals_python_features(tmp_path):
+    """feature_column.parse_example_native == parse_example + per-column vocabulary lookup for the reference's column set
+    (DeepFM/deepfm.py:56-93 + DIN's shared feedid / history columns)."""
+    from recalgorithm_b200 import feature_column as fc
+    rng = np.random.default_rng(8)
+    B = 120
+    p = str(tmp_path / "train.tfrecord")
+    cio.write_records(p, [wechat_record(rng, i)[0] for i in range(B)])
+    cats = ["userid", "feedid", "device", "authorid", "bgm_song_id", "bgm_singer_id"]
+    vocabs = {k: cio.VocabularyFile([f"{k}_{i}".encode() for i in rng.permutation(60)]) for k in cats}
+    cat_cols = {k: fc.categorical_column_with_vocabulary_file(k, vocabs[k]) for k in cats}
+    seq = fc.categorical_column_with_vocabulary_file("his_read_comment_7d_seq", vocabs["feedid"])
+    cols = [fc.indicator_column(c) for c in cat_cols.values()] + [fc.embedding_column(c, 8) for c in cat_cols.values()] + \
+        list(fc.shared_embedding_columns([cat_cols["feedid"], seq], 16, combiner="mean")) + \
+        [fc.numeric_column("read_comment", default_value=0.0), fc.numeric_column("videoplayseconds", default_value=0.0)]
+    spec = fc.make_parse_example_spec(cols)
+    buf, off, ln = native.read_tfrecord_file(p)
+    for read_fl in (False, True):
+        want = cio.parse_example(list(cio.read_records(p)), spec, read_feature_lists=read_fl)
+        got = fc.parse_example_native(buf, off, ln, cols, read_feature_lists=read_fl)
+        assert set(got) == set(want)
+        for k in want:
+            if isinstance(want[k], tuple):
+                base = seq if k == "his_read_comment_7d_seq" else cat_cols[k]
+                assert got[k][0].dtype == np.int64 and np.array_equal(got[k][1], want[k][1])
+                assert got[k][0].tolist() == base.vocabulary.lookup(want[k][0]).tolist(), k
+            else:
+                assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k

@@ -38,6 +38,15 @@ def test_deepfm_config1_pipeline(tmp_path):
     for col in second_order:                                                           # DeepFM/deepfm.py:187-190
         fields_embeddings.append(fc.input_layer(features, [col], ctx=ctx))
     e = torch.stack(fields_embeddings, dim=1)                                          # (B, F, K)
+    # the native feeder (libctr_feed.so) produces the same features -> bit-identical embeddings and first-order term
+    from recalgorithm_b200.io import native
+    buf, roff, rlen = native.read_tfrecord_file(path)
+    feats_n = fc.parse_example_native(buf, roff[:B], rlen[:B], first_order + second_order + [label])
+    assert np.array_equal(feats_n.pop("read_comment"), labels)
+    e_n = torch.stack([fc.input_layer(feats_n, [col]) for col in second_order], dim=1)
+    assert torch.equal(e_n, e.detach())
+    with L.variable_scope("fm_first_order"):
+        assert torch.equal(fc.indicator_dense(feats_n, first_order, units=1, name="fm_first_order_dense").detach(), fm_first_order_logit.detach())
 
     # ---- oracle on the same ids / weights
     st = L.default_store()
