@@ -1,0 +1,136 @@
+"""The reference's input_fns (algorithm/utils.py:4-47) on top of the native feeder -- the tf.data side of the hot path.
+
+    parser = make_example_parser(total_feature_columns + label_feature_columns, label_keys=["read_comment"])   # DCN/dcn.py:116-131
+    for features, labels in train_input_fn(path, parser, batch_size=1024, num_epochs=1, shuffle_buffer_size=10000):
+        ...   # features: key -> (ids int64, row_offsets) | float32 array, exactly what feature_column.input_layer takes
+
+Pipeline order is the reference's: TFRecordDataset -> shuffle(buffer) -> repeat(num_epochs) -> batch(batch_size) ->
+map(example_parser) -> prefetch(1).  Records are never copied: a batch is (file bytes, offsets[idx], lengths[idx]) and
+libctr_feed.so parses it in place (multi-threaded, GIL released) while the previous batch is being consumed.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Callable, Iterator, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import feature_column as fc
+from .io import native
+
+Batch = Tuple[np.ndarray, np.ndarray, np.ndarray]            # (file bytes uint8, offsets uint64 (B,), lengths uint64 (B,))
+
+
+def make_example_parser(feature_columns, label_keys: Sequence[str] = ("read_comment",), read_feature_lists: bool = False,
+                        num_threads: int = 0) -> Callable[[Batch], Tuple[dict, dict]]:
+    """`example_parser` of the reference's model files (e.g. DCN/dcn.py:116-131): make_parse_example_spec over the feature
+    and label columns, tf.parse_example on the serialized batch, labels popped into their own dict."""
+    def example_parser(serialized: Batch):
+        buf, off, ln = serialized
+        features = fc.parse_example_native(buf, off, ln, feature_columns, read_feature_lists=read_feature_lists, num_threads=num_threads)
+        labels = {k: features.pop(k) for k in label_keys}
+        return features, labels
+    return example_parser
+
+
+def _load(filepath: Union[str, Sequence[str]]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    paths = [filepath] if isinstance(filepath, str) else list(filepath)
+    bufs, offs, lens, base = [], [], [], 0
+    for p in paths:                                           # TFRecordDataset([files]) reads them one after the other
+        b, o, l = native.read_tfrecord_file(p)
+        bufs.append(b); offs.append(o + np.uint64(base)); lens.append(l)
+        base += b.size
+    return (bufs[0] if len(bufs) == 1 else np.concatenate(bufs)), np.concatenate(offs), np.concatenate(lens)
+
+
+def shuffle_order(n: int, buffer_size: int, rng: np.random.Generator) -> np.ndarray:
+    """Order in which dataset.shuffle(buffer_size) emits n elements: a buffer of the next `buffer_size` elements, one of them
+    drawn uniformly at each step and replaced by the next input element (tf.data semantics; buffer >= n = full shuffle)."""
+    if buffer_size <= 1 or n <= 1:
+        return np.arange(n, dtype=np.int64)
+    if buffer_size >= n:
+        return rng.permutation(n).astype(np.int64)
+    buf = np.arange(buffer_size, dtype=np.int64)
+    out = np.empty(n, np.int64)
+    nxt, filled = buffer_size, buffer_size
+    draws = rng.random(n)
+    for i in range(n):
+        j = int(draws[i] * filled)
+        out[i] = buf[j]
+        if nxt < n:
+            buf[j] = nxt
+            nxt += 1
+        else:
+            filled -= 1
+            buf[j] = buf[filled]
+    return out
+
+
+def _prefetch(gen: Iterator, depth: int = 1) -> Iterator:
+    """dataset.prefetch(depth): a producer thread keeps `depth` parsed batches ahead of the consumer."""
+    q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+    stop = threading.Event()
+    END = object()
+
+    def producer():
+        try:
+            for item in gen:
+                while not stop.is_set():
+                    try:
+                        q.put(item, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if stop.is_set():
+                    return
+            q.put(END)
+        except BaseException as e:                           # surfaces in the consumer
+            q.put(e)
+
+    th = threading.Thread(target=producer, daemon=True)
+    th.start()
+    try:
+        while True:
+            item = q.get()
+            if item is END:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+
+
+def _batches(order_epochs: Iterator[np.ndarray], data, batch_size: int, parser) -> Iterator:
+    buf, off, ln = data
+    pending: List[np.ndarray] = []
+    have = 0
+    for order in order_epochs:                               # repeat() happens BEFORE batch(): batches run across epoch borders
+        pending.append(order); have += order.size
+        while have >= batch_size:
+            idx = np.concatenate(pending) if len(pending) > 1 else pending[0]
+            take, rest = idx[:batch_size], idx[batch_size:]
+            pending, have = ([rest] if rest.size else []), rest.size
+            yield parser((buf, off[take], ln[take]))
+    if have:                                                 # drop_remainder=False
+        idx = np.concatenate(pending) if len(pending) > 1 else pending[0]
+        yield parser((buf, off[idx], ln[idx]))
+
+
+def train_input_fn(filepath, example_parser, batch_size: int, num_epochs: int, shuffle_buffer_size: int,
+                   seed: Optional[int] = None) -> Iterator[Tuple[dict, dict]]:
+    """utils.py:4-26.  Iterating the result is `dataset.make_one_shot_iterator()`; each epoch is reshuffled
+    (tf.data's reshuffle_each_iteration default)."""
+    data = _load(filepath)
+    n = int(data[1].size)
+    rng = np.random.default_rng(seed)
+    epochs = (shuffle_order(n, shuffle_buffer_size, rng) if shuffle_buffer_size > 0 else np.arange(n, dtype=np.int64)
+              for _ in range(num_epochs))
+    return _prefetch(_batches(epochs, data, batch_size, example_parser), depth=1)
+
+
+def eval_input_fn(filepath, example_parser, batch_size: int) -> Iterator[Tuple[dict, dict]]:
+    """utils.py:29-47: one pass, file order, no shuffle."""
+    data = _load(filepath)
+    return _prefetch(_batches(iter([np.arange(int(data[1].size), dtype=np.int64)]), data, batch_size, example_parser), depth=1)

@@ -1,0 +1,80 @@
+"""CPU tests of recalgorithm_b200.input_fn -- the reference's train/eval input_fns (utils.py:4-47) over the native feeder."""
+import threading
+
+import numpy as np
+import pytest
+
+from recalgorithm_b200 import feature_column as fc
+from recalgorithm_b200 import input_fn as I
+from recalgorithm_b200 import io as cio
+from test_io import wechat_record
+
+
+@pytest.fixture()
+def dataset(tmp_path):
+    rng = np.random.default_rng(21)
+    n = 103
+    recs = []
+    for i in range(n):                                              # userid_<i> makes every record identifiable
+        ctx = {"userid": ("bytes", [f"userid_{i}".encode()]), "read_comment": ("float", [float(i % 2)]),
+               "videoplayseconds": ("float", [float(i) / 8])}
+        recs.append(cio.encode_example(ctx))
+    p = str(tmp_path / "train.tfrecord")
+    cio.write_records(p, recs)
+    user = fc.categorical_column_with_vocabulary_file("userid", cio.VocabularyFile([f"userid_{i}".encode() for i in range(n)]))
+    cols = [fc.embedding_column(user, 4), fc.numeric_column("videoplayseconds"), fc.numeric_column("read_comment")]
+    return p, n, I.make_example_parser(cols, label_keys=["read_comment"])
+
+
+def _ids(batches):
+    return np.concatenate([f["userid"][0] for f, _ in batches])
+
+
+def test_eval_input_fn_is_one_ordered_pass(dataset):
+    p, n, parser = dataset
+    out = list(I.eval_input_fn(p, parser, batch_size=16))
+    assert [len(f["userid"][1]) - 1 for f, _ in out] == [16] * 6 + [7]              # last partial batch kept
+    assert _ids(out).tolist() == list(range(n))
+    f, l = out[0]
+    assert set(f) == {"userid", "videoplayseconds"} and set(l) == {"read_comment"} and l["read_comment"].shape == (16, 1)
+    assert np.allclose(f["videoplayseconds"][:, 0], np.arange(16) / 8)
+
+
+def test_train_input_fn_repeat_then_batch_and_shuffle(dataset):
+    p, n, parser = dataset
+    out = list(I.train_input_fn(p, parser, batch_size=50, num_epochs=3, shuffle_buffer_size=0))
+    ids = _ids(out)
+    assert ids.tolist() == list(range(n)) * 3                                         # no shuffle: file order, epochs concatenated
+    assert [len(f["userid"][1]) - 1 for f, _ in out] == [50] * 6 + [9]                # batches run across epoch borders
+    sh = _ids(list(I.train_input_fn(p, parser, batch_size=32, num_epochs=2, shuffle_buffer_size=10, seed=5)))
+    e1, e2 = sh[:n], sh[n:]
+    assert sorted(e1.tolist()) == list(range(n)) and sorted(e2.tolist()) == list(range(n)) and e1.tolist() != e2.tolist()
+    assert all(e1[i] < i + 10 for i in range(n))                                      # an element can only move up by < buffer_size
+    full = _ids(list(I.train_input_fn(p, parser, batch_size=32, num_epochs=1, shuffle_buffer_size=10_000, seed=5)))
+    assert sorted(full.tolist()) == list(range(n)) and full.tolist() != list(range(n))
+    again = _ids(list(I.train_input_fn(p, parser, batch_size=32, num_epochs=2, shuffle_buffer_size=10, seed=5)))
+    assert again.tolist() == sh.tolist()                                               # seeded
+
+
+def test_shuffle_order_statistics():
+    rng = np.random.default_rng(0)
+    o = I.shuffle_order(10_000, 100, rng)
+    assert sorted(o.tolist()) == list(range(10_000))
+    disp = o - np.arange(10_000)
+    assert disp.max() < 100 and disp.min() < -100                                     # late emission is unbounded, early is < buffer
+
+
+def test_prefetch_thread_stops_when_consumer_leaves_and_forwards_errors(dataset):
+    p, n, parser = dataset
+    before = threading.active_count()
+    it = I.train_input_fn(p, parser, batch_size=8, num_epochs=50, shuffle_buffer_size=0)
+    next(it); next(it)
+    it.close()
+    import time
+    time.sleep(0.5)
+    assert threading.active_count() <= before + 1
+
+    def bad_parser(batch):
+        raise ValueError("boom")
+    with pytest.raises(ValueError, match="boom"):
+        list(I.eval_input_fn(p, bad_parser, batch_size=8))
