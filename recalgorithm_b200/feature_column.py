@@ -173,6 +173,21 @@ def _ragged_ids(col: CategoricalColumn, features, device) -> Tuple[torch.Tensor,
     return torch.from_numpy(np.ascontiguousarray(ids)).to(device), torch.from_numpy(np.asarray(offsets, np.int64)).to(device)
 
 
+def single_valued_ids(features, categorical_columns) -> np.ndarray:
+    """(B, F) int64 id matrix of F single-valued categorical columns, in the order given, -1 where the value is missing /
+    out of vocabulary -- the input of the fused lookup (autograd.lookup_fm2 / lookup / lookup_bi)."""
+    cols = [c if isinstance(c, CategoricalColumn) else c.categorical_column for c in categorical_columns]
+    B = len(features[cols[0].key][1]) - 1
+    ids = np.full((B, len(cols)), -1, np.int64)
+    for f, c in enumerate(cols):
+        values, offsets = features[c.key]
+        lens = np.diff(np.asarray(offsets))
+        if np.any(lens > 1):
+            raise ValueError(f"single_valued_ids: column {c.key} is multi-valued; use input_layer (bag lookup) for it")
+        ids[lens == 1, f] = _ids_of(c, values)
+    return ids
+
+
 def parse_example_native(buf, offsets, lengths, feature_columns, read_feature_lists: bool = False, num_threads: int = 0):
     """``tf.parse_example(batch, make_parse_example_spec(feature_columns))`` + the vocabulary lookups in one native call
     (libctr_feed.so, include/ctr_feed.h): records are ``buf[offsets[b] : offsets[b] + lengths[b]]`` (see
