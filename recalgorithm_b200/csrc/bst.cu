@@ -205,7 +205,7 @@ __device__ __forceinline__ void bst_head_forward(const BstSmem& s, const BstLayo
 }
 
 template <int D, bool BWD>
-__global__ void __launch_bounds__(BST_NT)
+__global__ void __launch_bounds__(BST_NT, D <= 16 ? (BWD ? 3 : 4) : 1)
 bst_kernel(const float* __restrict__ queries, const float* __restrict__ keys, const float* __restrict__ values,
            const long long* __restrict__ keys_length, const float* __restrict__ params, const float* __restrict__ g_out, int B,
            int T, int H, int maxlen, int use_pos, float* __restrict__ out, float* __restrict__ d_queries,
