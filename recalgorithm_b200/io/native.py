@@ -17,7 +17,7 @@ from typing import Dict, Optional, Sequence, Tuple, Union
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc_feed", "libctr_feed.so")
+LIB_PATH = os.environ.get("CTR_FEED_LIB") or os.path.join(os.path.dirname(_HERE), "csrc_feed", "libctr_feed.so")   # override: sanitizer builds
 
 ERR_ARG, ERR_IO, ERR_TRUNCATED, ERR_CRC, ERR_PROTO, ERR_CAPACITY = -1, -2, -4, -5, -6, -7
 

@@ -155,3 +155,84 @@ def test_parse_example_native_equals_python_features(tmp_path):
                 assert got[k][0].tolist() == base.vocabulary.lookup(want[k][0]).tolist(), k
             else:
                 assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ fuzzing
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+from recalgorithm_b200.io.example import _enc_feature, _enc_varint, _ld  # noqa: E402
+
+_KEYS = ["a", "b", "f", "zz"]
+_entry = st.tuples(st.sampled_from(_KEYS), st.integers(0, 4), st.integers(0, 2 ** 16))
+
+
+def _build_record(entries, with_unknown, with_fl, rng):
+    """Example bytes with repeated map keys (last wins), unknown fields at three nesting levels, optional feature_lists."""
+    feats = b""
+    for key, n, seed in entries:
+        r = np.random.default_rng(seed)
+        if key == "f":
+            kind, vals = "float", [float(x) for x in r.standard_normal(2 if n % 2 else 0).astype(np.float32)]
+        else:
+            kind, vals = "bytes", [b"t%d" % int(x) for x in r.integers(0, 12, n)]
+        entry = _ld(1, key.encode()) + _ld(2, _enc_feature(kind, vals))
+        if with_unknown:
+            entry += _enc_varint((3 << 3) | 0) + _enc_varint(int(rng.integers(0, 1 << 40)))
+        feats += _ld(1, entry)
+        if with_unknown:
+            feats += _ld(2, b"junk") + _enc_varint((5 << 3) | 5) + b"\x01\x02\x03\x04"
+    rec = _ld(1, feats)
+    if with_unknown:
+        rec = _enc_varint((7 << 3) | 1) + b"\x00" * 8 + rec + _enc_varint((3 << 3) | 0) + _enc_varint(5)
+    if with_fl:
+        steps = b"".join(_ld(1, _enc_feature("bytes", [b"t%d" % int(x)])) for x in rng.integers(0, 12, int(rng.integers(0, 4))))
+        rec += _ld(2, _ld(1, _ld(1, b"zz") + _ld(2, steps)))
+    return rec
+
+
+@settings(deadline=None, max_examples=120, suppress_health_check=[HealthCheck.too_slow], derandomize=True)
+@given(records=st.lists(st.tuples(st.lists(_entry, max_size=6), st.booleans(), st.booleans()), min_size=1, max_size=12),
+       read_fl=st.booleans(), seed=st.integers(0, 2 ** 16))
+def test_native_parser_fuzz_against_python(records, read_fl, seed):
+    rng = np.random.default_rng(seed)
+    recs = [_build_record(e, u, fl, rng) for e, u, fl in records]
+    blob = b"".join(recs)
+    ln = np.array([len(r) for r in recs], np.uint64)
+    off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.uint64)
+    toks = [b"t%d" % i for i in range(8)]                          # t8..t11 are out of vocabulary
+    spec = {"a": cio.VarLenFeature(), "b": cio.VarLenFeature(), "zz": cio.VarLenFeature(), "f": cio.FixedLenFeature((2,), "float", 7.0)}
+    want = cio.parse_example(recs, spec, read_feature_lists=read_fl)
+    v = native.Vocabulary(toks)
+    got = native.parse_examples(blob, off, ln, {"a": v, "b": v, "zz": v}, {"f": (2, 7.0)}, read_feature_lists=read_fl, num_threads=2)
+    pyv = cio.VocabularyFile(toks)
+    for k in ("a", "b", "zz"):
+        assert np.array_equal(got[k][1], want[k][1]), k
+        assert got[k][0].tolist() == pyv.lookup(want[k][0]).tolist(), k
+    assert np.array_equal(got["f"], want["f"])
+
+
+def test_native_parser_survives_corrupted_input():
+    """Memory safety: random truncations / byte flips of valid batches must come back as a result or a ValueError."""
+    rng = np.random.default_rng(4)
+    recs = [wechat_record(rng, i)[0] for i in range(64)]
+    v = native.Vocabulary([b"userid_%d" % i for i in range(50)])
+    ok = bad = 0
+    for trial in range(600):
+        rec = bytearray(recs[trial % len(recs)])
+        mode = trial % 3
+        if mode == 0:
+            rec = rec[: int(rng.integers(0, len(rec)))]
+        elif mode == 1:
+            for _ in range(int(rng.integers(1, 6))):
+                rec[int(rng.integers(0, len(rec)))] = int(rng.integers(0, 256))
+        else:
+            pos = int(rng.integers(0, len(rec)))
+            rec[pos:pos] = bytes(rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8))
+        data = bytes(rec)
+        try:
+            out = native.parse_examples(data, np.array([0], np.uint64), np.array([len(data)], np.uint64),
+                                        {"userid": v, "his_read_comment_7d_seq": v}, {"read_comment": (1, 0.0)}, read_feature_lists=True)
+            assert out["userid"][1].shape == (2,)
+            ok += 1
+        except ValueError:
+            bad += 1
+    assert ok > 0 and bad > 0
