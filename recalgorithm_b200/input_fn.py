@@ -134,3 +134,65 @@ def eval_input_fn(filepath, example_parser, batch_size: int) -> Iterator[Tuple[d
     """utils.py:29-47: one pass, file order, no shuffle."""
     data = _load(filepath)
     return _prefetch(_batches(iter([np.arange(int(data[1].size), dtype=np.int64)]), data, batch_size, example_parser), depth=1)
+
+
+class DevicePrefetcher:
+    """Last stage of the feeding side: move each parsed batch to the GPU through pinned staging buffers on a side stream,
+    one batch ahead of the consumer (the H2D copy of batch i+1 overlaps the kernels of batch i).
+
+        for ids, dense, labels in DevicePrefetcher(train_input_fn(...), categorical_columns, dense_keys, label_keys):
+            tile, fm2 = autograd.lookup_fm2(tables, ids)          # ids: (B, F) int64 on the device, -1 = missing / OOV
+
+    `categorical_columns` must be single-valued (feature_column.single_valued_ids); multi-valued columns stay on the
+    feature_column.input_layer path.  Yields (ids (B,F) int64, {key: float32 (B,w)}, {key: float32 (B,w)}) device tensors."""
+
+    def __init__(self, batches, categorical_columns, dense_keys=(), label_keys=("read_comment",), device="cuda"):
+        import torch
+        self.torch = torch
+        self.batches = iter(batches)
+        self.cols, self.dense_keys, self.label_keys = list(categorical_columns), list(dense_keys), list(label_keys)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pinned = [{}, {}]                                # two staging sets: one being copied, one being filled
+        self._slot_ev = [None, None]                           # last H2D copy out of each set (host waits before refilling it)
+        self._turn = 0
+
+    def _stage(self, name: str, arr: np.ndarray):
+        torch = self.torch
+        slot = self._pinned[self._turn]
+        t = slot.get(name)
+        if t is None or t.shape != arr.shape or t.dtype != torch.from_numpy(arr).dtype:
+            t = torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype).pin_memory()
+            slot[name] = t
+        t.copy_(torch.from_numpy(arr))
+        return t.to(self.device, non_blocking=True)
+
+    def _issue(self):
+        try:
+            features, labels = next(self.batches)
+        except StopIteration:
+            return None
+        torch = self.torch
+        ids = fc.single_valued_ids(features, self.cols)
+        if self._slot_ev[self._turn] is not None:
+            self._slot_ev[self._turn].synchronize()            # the copy that last read this staging set has finished
+        with torch.cuda.stream(self.stream):
+            out = (self._stage("ids", ids),
+                   {k: self._stage("d:" + k, np.ascontiguousarray(features[k], np.float32)) for k in self.dense_keys},
+                   {k: self._stage("l:" + k, np.ascontiguousarray(labels[k], np.float32)) for k in self.label_keys})
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._slot_ev[self._turn] = ev
+        self._turn ^= 1
+        return out, ev
+
+    def __iter__(self):
+        torch = self.torch
+        nxt = self._issue()
+        while nxt is not None:
+            cur, ev = nxt
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for t in [cur[0], *cur[1].values(), *cur[2].values()]:
+                t.record_stream(torch.cuda.current_stream(self.device))
+            nxt = self._issue()                                # batch i+1 starts copying before batch i is consumed
+            yield cur

@@ -59,3 +59,23 @@ def _first_order(w, off, ids):
     valid = ids >= 0
     rows = (ids + off[:-1][None, :]).clamp_min(0)
     return (w[rows.reshape(-1), 0].reshape(ids.shape) * valid).sum(1, keepdim=True)
+
+
+def test_device_prefetcher_delivers_the_same_batches(tmp_path):
+    from recalgorithm_b200 import feature_column as fc, input_fn as I, io as cio
+    from test_io import wechat_record
+    rng = np.random.default_rng(2)
+    path = str(tmp_path / "d.tfrecord")
+    cio.write_records(path, [wechat_record(rng, i)[0] for i in range(700)])
+    cat_cols = [fc.categorical_column_with_vocabulary_file(k, cio.VocabularyFile([f"{k}_{i}".encode() for i in range(64)])) for k in CATS]
+    cols = cat_cols + [fc.numeric_column("videoplayseconds"), fc.numeric_column("read_comment")]
+    parser = I.make_example_parser(cols, label_keys=["read_comment"])
+    host = list(I.eval_input_fn(path, parser, batch_size=128))
+    dev_batches = list(I.DevicePrefetcher(I.eval_input_fn(path, parser, batch_size=128), cat_cols, dense_keys=["videoplayseconds"],
+                                          label_keys=["read_comment"]))
+    assert len(dev_batches) == len(host) == 6
+    for (ids, dense, labels), (features, lab) in zip(dev_batches, host):
+        assert ids.is_cuda and ids.dtype == torch.int64
+        assert np.array_equal(ids.cpu().numpy(), fc.single_valued_ids(features, cat_cols))
+        assert np.array_equal(dense["videoplayseconds"].cpu().numpy(), features["videoplayseconds"])
+        assert np.array_equal(labels["read_comment"].cpu().numpy(), lab["read_comment"])
