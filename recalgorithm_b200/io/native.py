@@ -87,7 +87,7 @@ def _raise(code: int):
 
 
 def _u8(data) -> np.ndarray:
-    if isinstance(data, np.ndarray):
+    if isinstance(data, np.ndarray):                             # includes np.memmap
         assert data.dtype == np.uint8 and data.flags.c_contiguous
         return data
     return np.frombuffer(data, dtype=np.uint8)
@@ -120,9 +120,10 @@ def index_tfrecord(buf, verify: bool = True) -> Tuple[np.ndarray, np.ndarray]:
     return offsets, lengths
 
 
-def read_tfrecord_file(path: str, verify: bool = True) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Whole file -> (bytes as uint8 array, offsets, lengths).  tf.data.TFRecordDataset(path) without the iterator."""
-    buf = np.fromfile(path, dtype=np.uint8)
+def read_tfrecord_file(path: str, verify: bool = True, mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Whole file -> (bytes as uint8 array, offsets, lengths).  tf.data.TFRecordDataset(path) without the iterator.
+    mmap=True maps the file instead of reading it (files larger than RAM; pages are pulled in by the CRC / parse passes)."""
+    buf = np.memmap(path, dtype=np.uint8, mode="r") if mmap and os.path.getsize(path) > 0 else np.fromfile(path, dtype=np.uint8)
     offsets, lengths = index_tfrecord(buf, verify)
     return buf, offsets, lengths
 

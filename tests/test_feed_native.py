@@ -39,6 +39,8 @@ def test_tfrecord_index_roundtrip_and_corruption(tmp_path):
     cio.write_records(p, recs)
     buf, off, ln = native.read_tfrecord_file(p)
     assert [buf[int(o): int(o + l)].tobytes() for o, l in zip(off, ln)] == recs
+    mbuf, moff, mln = native.read_tfrecord_file(p, mmap=True)                       # memory-mapped variant
+    assert np.array_equal(moff, off) and np.array_equal(mln, ln) and bytes(mbuf[int(off[2]): int(off[2] + ln[2])]) == recs[2]
     raw = bytearray(open(p, "rb").read())
     raw[12 + 0 + 4 + 12 + 0] ^= 0xFF                              # flip a data byte of the 2nd record
     with pytest.raises(IOError):
