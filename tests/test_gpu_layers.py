@@ -126,3 +126,42 @@ def test_mini_batch_aware_regularization_reaches_the_tables():
     assert_close(reg, 0.2 * 0.5 * float(tile.detach().double().pow(2).sum()) / B * torch.ones((), dtype=torch.float64), TOL, "value")
     reg.backward()
     assert_close(tables.grad_slices[0].values, 0.2 * tile.detach().double() / B, TOL, "lambda * e / B")
+
+
+def test_c_abi_calls_are_cuda_graph_capturable():
+    """Launch-bound small-batch steps (DCN at B=4096 is 4 kernels of ~10 us) can be captured into one CUDA graph: the library
+    only enqueues on the given stream.  Replay with new input CONTENTS must match the eager result."""
+    from recalgorithm_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    B, F, D, L, rows = 96, 5, 8, 3, 50
+    table = torch.randn((rows * F, D), device="cuda", generator=gen)
+    off = torch.arange(F + 1, device="cuda") * rows
+    ids = torch.randint(-1, rows, (B, F), device="cuda", generator=gen)
+    w, b = torch.randn((L, F * D), device="cuda", generator=gen) * 0.1, torch.randn((L, F * D), device="cuda", generator=gen) * 0.1
+    g = torch.randn((B, F * D), device="cuda", generator=gen)
+    outs = {}
+
+    def step():
+        tile, _ = ops.embed_fm2_fwd(table, off, ids, want_fm2=False)
+        x0 = tile.view(B, F * D)
+        outs["y"] = ops.cross_fwd(x0, w, b)
+        dx0, _, outs["dw"], outs["db"] = ops.cross_bwd(x0, w, b, g)
+        outs["rg"] = ops.embed_fm2_bwd(tile, dx0.view(B, F, D), None)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    captured = dict(outs)                                          # static output buffers of the graph
+    ids.copy_(torch.randint(-1, rows, (B, F), device="cuda", generator=gen))       # new contents, same buffers
+    g.copy_(torch.randn((B, F * D), device="cuda", generator=gen))
+    graph.replay()
+    torch.cuda.synchronize()
+    got = {k: v.clone() for k, v in captured.items()}
+    step()                                                         # eager, same inputs
+    for k in got:
+        assert torch.equal(got[k], outs[k]) or float((got[k] - outs[k]).abs().max()) <= 1e-6 * float(outs[k].abs().max()), k

@@ -222,6 +222,22 @@ def config_level():
         ops.embed_fm2_bwd(tile, dx0.view(B, F, D), None)
     run("dcn_cfg2", {"B": B, "F": F, "D": D, "L": L, "rows_per_field": rows}, B, dcn)
 
+    def graphed(fn):
+        """The same C-ABI calls captured once into a CUDA graph (they only enqueue work on the given stream and never
+        allocate or synchronise, so they are capturable as they are); a step is then ONE graph launch."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        return graph.replay
+    run("dcn_cfg2_cuda_graph", {"B": B, "F": F, "D": D, "L": L, "rows_per_field": rows, "launch": "one CUDA graph replay per step"}, B,
+        graphed(dcn))
+
     # ---- config 3: xDeepFM CIN [128,128], 30 fields x 16, B = 8192
     B, F, D, H = 8192, 30, 16, 128
     ids3 = torch.randint(0, rows, (B, F), device="cuda", generator=gen)
