@@ -231,6 +231,13 @@ int ctr_fwfm_fwd(const float* tile, const float* r, int64_t B, int64_t F, int64_
 int ctr_fwfm_bwd(const float* tile, const float* r, const float* g, int64_t B, int64_t F, int64_t K, float* d_tile, float* d_r,
                  void* stream);
 
+/* FFM second-order logit (FFM/ffm.py:128-160).  tile (B, F, F-1, K): the lookup of a table whose row for an id of field i is the
+ * concatenation of its F-1 sub-embeddings, slot s facing field j = s+1 (s >= i) or s (s < i) -- i.e. the reference's
+ * embedding_variables[i] of shape (F-1, |V_i|, K) stored id-major.  out[b] = sum_{i<j} <tile[b,i,j-1,:], tile[b,j,i,:]>.
+ * Backward: d_tile[b,i,s,:] = g[b] * tile[b, partner(i,s), :] (overwritten). */
+int ctr_ffm_fwd(const float* tile, int64_t B, int64_t F, int64_t K, float* out, void* stream);
+int ctr_ffm_bwd(const float* tile, const float* g, int64_t B, int64_t F, int64_t K, float* d_tile, void* stream);
+
 /* AFM attention pooling (AFM/afm.py:152-186): pairs (i<j) in the reference's order, a_p = h^T relu(W^T (e_i*e_j) + b),
  * softmax over the pair axis, pooled (B,K) = sum_p s_p (e_i*e_j).  w (K,T) row-major, b (T,), h (T,); score (B,P) optional
  * output.  K in {4,8,16,32} with K*ceil(T/32) <= 64.  Backward overwrites d_tile (B,F,K), d_w, d_b, d_h. */

@@ -544,3 +544,36 @@ def bst_transformer_fwd(queries, keys, values, keys_length, p, heads, use_positi
     f = net @ P["dense_kernel"] + P["dense_bias"]
     f = 0.5 * (1 + 0.01) * f + 0.5 * (1 - 0.01) * np.abs(f)                                   # BST/leakyrelu.py:4-16
     return _layer_norm_td(f + net, P["ln2_beta"], P["ln2_gamma"])
+
+
+# ---- FFM second-order term (FFM/ffm.py:128-160): field-aware FM, a sibling of FM2 ----------------------------------------
+
+def ffm_partner(i: int, s: int):
+    """Field i keeps one sub-embedding per OTHER field: slot s of field i faces field j = s + 1 if s >= i else s, and field j
+    faces i through its slot i - 1 if i > j else i  (ffm.py:154-155: embedding_variables[i][j-1], embedding_variables[j][i], i < j)."""
+    j = s + 1 if s >= i else s
+    return j, (i - 1 if i > j else i)
+
+
+def ffm_fwd(tile: np.ndarray) -> np.ndarray:
+    """tile (B, F, F-1, K): tile[b, i, s, :] = sub-embedding of field i's id for partner slot s (zero vector for a missing id:
+    safe_embedding_lookup_sparse on an empty row).  Returns (B, 1): sum_{i<j} <v_i^(j), v_j^(i)>, pairs in the reference's
+    loop order (ffm.py:146-160)."""
+    B, F = tile.shape[0], tile.shape[1]
+    out = np.zeros((B, 1), dtype=tile.dtype)
+    for i in range(F - 1):
+        for j in range(i + 1, F):
+            out = out + np.sum(tile[:, i, j - 1, :] * tile[:, j, i, :], axis=-1, keepdims=True)
+    return out
+
+
+def ffm_bwd(tile: np.ndarray, g: np.ndarray) -> np.ndarray:
+    """g (B,) or (B,1) -> d_tile: every (field, slot) position belongs to exactly one pair."""
+    B, F = tile.shape[0], tile.shape[1]
+    g = g.reshape(B, 1)
+    d = np.zeros_like(tile)
+    for i in range(F):
+        for s in range(F - 1):
+            j, sb = ffm_partner(i, s)
+            d[:, i, s, :] = g * tile[:, j, sb, :]
+    return d

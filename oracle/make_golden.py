@@ -340,6 +340,29 @@ def gen_bst():
              **{f"p_{k}": v for k, v in p.items()}, source="reference-executed:BST/transformer_layer.py:6-79")
 
 
+def gen_ffm():
+    """FFM/ffm.py:145-160 executed with per-field (F-1, |V_i|, K) variables and the id vectors standing in for the one-hot ->
+    sparse conversion of :141-144 (to_sparse_tensor + safe_embedding_lookup_sparse == row lookup, empty row -> zeros)."""
+    rng = np.random.default_rng(8642)
+    for F, K, B in ((4, 4, 9), (5, 8, 16), (9, 16, 6)):
+        sizes = [int(v) for v in rng.integers(3, 9, size=F)]
+        emb = [trunc_normal(rng, (F - 1, sizes[f], K), 0.5) for f in range(F)]
+        ids = np.stack([rng.integers(-1, sizes[f], size=B) for f in range(F)], axis=1).astype(np.int64)
+        outs = {}
+        for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+            tf.reset(dtype=dt)
+            ns = {"tf": tf, "params": {"one_hot_category_feature_columns": list(range(F))},
+                  "embedding_variables": [tf.Tensor(e.astype(dt)) for e in emb], "field_sparse_ids_list": [ids[:, f] for f in range(F)]}
+            exec_ref_lines("FFM/ffm.py", 145, 160, ("second_order_vec = 0.0", "second_order_vec += tf.reduce_sum"), ns)
+            outs[tag] = np.asarray(ns["second_order_vec"].a)
+        tile = np.zeros((B, F, F - 1, K), np.float32)                         # the (field, slot) layout our lookup produces
+        for f in range(F):
+            ok = ids[:, f] >= 0
+            tile[ok, f] = emb[f][:, ids[ok, f], :].transpose(1, 0, 2)
+        save(f"ffm_F{F}_K{K}", ids=ids, tile=tile, out_f32=outs["f32"], out_f64=outs["f64"],
+             **{f"emb_{f}": emb[f] for f in range(F)}, source="reference-executed:FFM/ffm.py:145-160")
+
+
 if __name__ == "__main__":
     gen_cross()
     gen_cin()
@@ -348,3 +371,4 @@ if __name__ == "__main__":
     gen_restated()
     gen_inline()
     gen_bst()
+    gen_ffm()

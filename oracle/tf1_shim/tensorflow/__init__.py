@@ -277,6 +277,14 @@ class _NN:
         return Tensor(_arr(params)[_arr(ids)])
 
     @staticmethod
+    def safe_embedding_lookup_sparse(embedding_weights, sparse_ids, sparse_weights=None, combiner="mean"):
+        """tf.nn.safe_embedding_lookup_sparse for ONE id per row, the only way FFM/ffm.py:156-157 uses it (its sparse ids come
+        from a one-hot row): here `sparse_ids` is the (B,) id vector itself, -1 = empty row -> zero vector (the 'safe' part)."""
+        w, ids = _arr(embedding_weights), _np.asarray(_arr(sparse_ids))
+        out = w[_np.maximum(ids, 0)]
+        return Tensor(_np.where((ids >= 0)[:, None], out, 0).astype(w.dtype))
+
+    @staticmethod
     def conv1d(value, filters, stride, padding):
         """tf.nn.conv1d(x:(B,W,C), filters:(fw,C,O), stride, padding).  Only the reference's use is
         supported: fw == 1, stride 1, VALID  ==  x @ filters[0] at every position."""

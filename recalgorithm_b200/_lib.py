@@ -43,6 +43,8 @@ SIGNATURES = {
     "ctr_embed_bi_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "ctr_fwfm_fwd": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "ctr_fwfm_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "ctr_ffm_fwd": (c_int, [_P, _I, _I, _I, _P, _P]),
+    "ctr_ffm_bwd": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "ctr_afm_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ctr_afm_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ctr_bst_param_count": (_I, [_I, _I, _I]),

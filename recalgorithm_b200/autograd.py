@@ -273,3 +273,21 @@ def bst_transformer(queries, keys, values, keys_length, params: dict, heads: int
     """params: dict with the names of ops.BST_PARAM_ORDER."""
     return _BstTransformer.apply(queries, keys, values, keys_length, heads, max_length, use_position_embedding,
                                  *[params[n] for n in ops.BST_PARAM_ORDER])
+
+
+class _FFM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tile):
+        tile = tile.contiguous()
+        ctx.save_for_backward(tile)
+        return ops.ffm_fwd(tile)
+
+    @staticmethod
+    def backward(ctx, g):
+        (tile,) = ctx.saved_tensors
+        return ops.ffm_bwd(tile, g.contiguous())
+
+
+def ffm(tile: torch.Tensor) -> torch.Tensor:
+    """(B, F, F-1, K) field/slot tile -> FFM second-order logit (B,1)."""
+    return _FFM.apply(tile)

@@ -283,6 +283,38 @@ afm_kernel(const float* __restrict__ tile, const float* __restrict__ w, const fl
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------- FFM
+// Field-aware FM (FFM/ffm.py:128-160).  tile (B, F, F-1, K): field i keeps one sub-embedding per other field; slot s of field i
+// faces field j = s + 1 (s >= i) or s (s < i), which faces i through slot i - 1 (i > j) or i.  Every (field, slot) position
+// belongs to exactly one pair, so   out[b] = 0.5 * sum_{i,s,k} tile[b,i,s,k] * tile[b,partner(i,s),k]   and the backward is a
+// permutation scaled by g: both are streaming element-wise kernels (one warp per sample, lanes over (i,s,k)).
+__device__ __forceinline__ int ffm_partner_elem(int e, int F, int K) {
+  const int k = e % K, is = e / K, s = is % (F - 1), i = is / (F - 1);
+  const int j = s >= i ? s + 1 : s, sb = i > j ? i - 1 : i;
+  return (j * (F - 1) + sb) * K + k;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+ffm_kernel(const float* __restrict__ tile, const float* __restrict__ g, int B, int F, int K, float* __restrict__ out,
+           float* __restrict__ d_tile) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n = F * (F - 1) * K;
+  for (int b = warp0; b < B; b += nwarps) {
+    const float* row = tile + (size_t)b * n;
+    if (BWD) {
+      const float gb = __ldg(g + b);
+      for (int e = lane; e < n; e += 32) d_tile[(size_t)b * n + e] = gb * __ldg(row + ffm_partner_elem(e, F, K));
+    } else {
+      float acc = 0.f;
+      for (int e = lane; e < n; e += 32) acc = fmaf(__ldg(row + e), __ldg(row + ffm_partner_elem(e, F, K)), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) out[b] = 0.5f * acc;
+    }
+  }
+}
+
 template <typename Kern>
 static int pw_grid(Kern k, size_t smem, int64_t B) {
   int per_sm = 0;
@@ -393,4 +425,28 @@ extern "C" int ctr_afm_bwd(const float* tile, const float* w, const float* b, co
   CTR_CUDA(cudaMemsetAsync(d_h, 0, (size_t)T * sizeof(float), st));
   if (B == 0) return CTR_OK;
   return afm_dispatch<true>(tile, w, b, h, g_pooled, B, F, K, T, nullptr, nullptr, d_tile, d_w, d_b, d_h, st);
+}
+
+static int ffm_run(bool bwd, const float* tile, const float* g, int64_t B, int64_t F, int64_t K, float* out, float* d_tile, void* stream) {
+  const char* fn = bwd ? "ctr_ffm_bwd" : "ctr_ffm_fwd";
+  int rc = check_pw(fn, B, F, K);
+  if (rc) return rc;
+  CTR_REQUIRE(F * (F - 1) * K < (1LL << 30), "%s: F=%lld K=%lld too large", fn, (long long)F, (long long)K);
+  if (B == 0) return CTR_OK;
+  const long long need = (B + 7) / 8;
+  const int grid = (int)(need < (long long)sm_count() * 8 ? need : (long long)sm_count() * 8);
+  if (bwd) ffm_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(tile, g, (int)B, (int)F, (int)K, nullptr, d_tile);
+  else ffm_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(tile, nullptr, (int)B, (int)F, (int)K, out, nullptr);
+  CTR_CHECK_LAUNCH(fn);
+  return CTR_OK;
+}
+
+extern "C" int ctr_ffm_fwd(const float* tile, int64_t B, int64_t F, int64_t K, float* out, void* stream) {
+  CTR_REQUIRE(tile && out, "ctr_ffm_fwd: null argument");
+  return ffm_run(false, tile, nullptr, B, F, K, out, nullptr, stream);
+}
+
+extern "C" int ctr_ffm_bwd(const float* tile, const float* g, int64_t B, int64_t F, int64_t K, float* d_tile, void* stream) {
+  CTR_REQUIRE(tile && g && d_tile, "ctr_ffm_bwd: null argument");
+  return ffm_run(true, tile, g, B, F, K, nullptr, d_tile, stream);
 }

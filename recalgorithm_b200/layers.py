@@ -251,3 +251,20 @@ def mini_batch_aware_regularization(embedding_tensors, l2_lambda: float) -> torc
     (``d_tile`` of ctr_embed_fm2_bwd / ctr_bag_lookup_bwd) like any other upstream gradient.  Torch plumbing, no kernel."""
     x = torch.cat(list(embedding_tensors), dim=-1)
     return l2_lambda * 0.5 * x.pow(2).sum() / x.shape[0]
+
+
+# --------------------------------------------------------------------------------------------------- FFM
+def ffm_second_order(tables: autograd.EmbeddingTables, ids: torch.Tensor, embedding_dim: int) -> torch.Tensor:
+    """FFM/ffm.py:128-160 in two kernels: `tables` holds, per field, rows of (F-1)*K floats -- the reference's
+    ``{name}_embedding`` variable of shape (F-1, |V_i|, K) stored id-major (``EmbeddingTables([...], dim=(F-1)*K)``;
+    `ffm_table_from_reference` converts) -- looked up by the fused gather, then the field-aware pair sum.  Returns (B,1)."""
+    B, F = ids.shape
+    if tables.dim != (F - 1) * embedding_dim:
+        raise ValueError(f"tables.dim must be (F-1)*embedding_dim = {(F - 1) * embedding_dim}, got {tables.dim}")
+    tile = autograd.lookup(tables, ids)                       # (B, F, (F-1)*K)
+    return autograd.ffm(tile.reshape(B, F, F - 1, embedding_dim))
+
+
+def ffm_table_from_reference(embedding_variables) -> torch.Tensor:
+    """[(F-1, |V_i|, K) per field] (the reference's variables, ffm.py:129-136) -> the (sum |V_i|, (F-1)*K) id-major table."""
+    return torch.cat([e.permute(1, 0, 2).reshape(e.shape[1], -1) for e in embedding_variables], dim=0).contiguous()

@@ -418,3 +418,23 @@ def bst_transformer_bwd(queries, keys, values, keys_length, packed, g_out, heads
                                                   _ptr(g_out), B, T, d, heads, max_length, int(use_position_embedding), _ptr(dq),
                                                   _ptr(dk), _ptr(dv), _ptr(dp), _stream()))
     return dq, dk, dv, dp
+
+
+def ffm_fwd(tile: torch.Tensor) -> torch.Tensor:
+    """FFM second-order logit (B,1) from the (B, F, F-1, K) field/slot tile (see include/ctr_b200.h)."""
+    B, F, S, K = tile.shape
+    if S != F - 1:
+        raise ValueError(f"tile: expected shape (B, F, F-1, K), got {tuple(tile.shape)}")
+    _chk(tile, F32, "tile")
+    out = torch.empty((B, 1), dtype=F32, device=tile.device)
+    _lib.check(_lib.lib().ctr_ffm_fwd(_ptr(tile), B, F, K, _ptr(out), _stream()))
+    return out
+
+
+def ffm_bwd(tile: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    B, F, S, K = tile.shape
+    g = g.reshape(B)
+    _chk(tile, F32, "tile"); _chk(g, F32, "g", (B,))
+    d_tile = torch.empty_like(tile)
+    _lib.check(_lib.lib().ctr_ffm_bwd(_ptr(tile), _ptr(g), B, F, K, _ptr(d_tile), _stream()))
+    return d_tile

@@ -147,3 +147,34 @@ def test_full_size_bi_interaction_properties():
     assert_close(r1 - r2, d_tile, 1e-5, "bwd linearity")
     ones = torch.ones((B, D), device="cuda")                              # d_bi = 1 reproduces the FM2 backward with g = 1
     assert_close(ops.embed_bi_bwd(tile, None, ones), ops.embed_fm2_bwd(tile, None, torch.ones((B,), device="cuda")), 1e-6, "bi bwd == fm2 bwd at g=1")
+
+
+@pytest.mark.parametrize("name", ["ffm_F4_K4", "ffm_F5_K8", "ffm_F9_K16"])
+def test_ffm_golden_through_the_lookup(name):
+    """FFM/ffm.py:145-160 executed on per-field (F-1, |V|, K) variables vs: reference variables -> id-major table -> fused
+    lookup -> ctr_ffm_fwd.  D = (F-1)*K is 12, 32 and 128 here (12 is not a power of two: the layer must refuse it cleanly)."""
+    from recalgorithm_b200 import _lib, autograd, layers as L, ops
+    g = golden(name)
+    B, F = g["ids"].shape
+    K = g["tile"].shape[-1]
+    assert_close(ops.ffm_fwd(dev(g["tile"])), g["out_f64"], TOL, "ffm on the fixture tile")
+    embs = [torch.from_numpy(g[f"emb_{f}"]) for f in range(F)]
+    D = (F - 1) * K
+    tables = autograd.EmbeddingTables([e.shape[1] for e in embs], D, device="cuda", init=None)
+    tables.weight.copy_(L.ffm_table_from_reference(embs))
+    if D & (D - 1):
+        with pytest.raises(_lib.CtrError):
+            L.ffm_second_order(tables, dev(g["ids"]), K)
+        return
+    assert_close(L.ffm_second_order(tables, dev(g["ids"]), K), g["out_f64"], TOL, "lookup + ffm vs ffm.py executed")
+
+
+@pytest.mark.parametrize("B,F,K", [(3, 2, 4), (65, 5, 8), (17, 9, 16), (8, 7, 3), (40, 12, 10)])
+def test_ffm_fwd_bwd(B, F, K):
+    from recalgorithm_b200 import ops
+    rng = np.random.default_rng(B + F + K)
+    t = trunc_normal(rng, (B, F, F - 1, K), 1.0); g = trunc_normal(rng, (B,), 1.0)
+    d = lambda a: a.astype(np.float64)
+    ref = O.ffm_fwd(d(t))
+    assert np.abs(ops.ffm_fwd(dev(t)).cpu().double().numpy() - ref).max() <= TOL * max(np.abs(ref).max(), float(K))
+    assert_close(ops.ffm_bwd(dev(t), dev(g)), O.ffm_bwd(d(t), d(g)), TOL, "d_tile")

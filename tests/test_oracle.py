@@ -23,7 +23,7 @@ def rel(a, b):
 
 def test_all_fixtures_present():
     names = {os.path.basename(p) for p in glob.glob(os.path.join(G, "*.npz"))}
-    assert len(names) == 25, names
+    assert len(names) == 28, names
 
 
 # ---------------------------------------------------------------- forward vs reference-executed golden
@@ -289,3 +289,16 @@ def test_bst_transformer_matches_reference_executed(name):
     tp = {n: torch.tensor(a, dtype=torch.float64) for n, a in p.items()}
     x = torch.tensor(g["x"], dtype=torch.float64)
     assert rel(bst_torch.bst_transformer(x, x, x, torch.as_tensor(g["keys_length"]), tp, int(g["heads"])).numpy(), out) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["ffm_F4_K4", "ffm_F5_K8", "ffm_F9_K16"])
+def test_ffm_matches_reference_executed(name):
+    g = load(name)
+    assert rel(O.ffm_fwd(g["tile"]), g["out_f32"]) <= 2e-6
+    assert rel(O.ffm_fwd(g["tile"].astype(np.float64)), g["out_f64"]) <= 1e-13
+    t = torch.tensor(g["tile"].astype(np.float64), requires_grad=True)
+    F = t.shape[1]
+    out = sum((t[:, i, j - 1] * t[:, j, i]).sum(-1) for i in range(F - 1) for j in range(i + 1, F))
+    gg = np.random.default_rng(0).standard_normal(t.shape[0])
+    (out * torch.tensor(gg)).sum().backward()
+    assert rel(O.ffm_bwd(g["tile"].astype(np.float64), gg), t.grad.numpy()) <= 1e-12
