@@ -18,7 +18,7 @@ Semantics that live inside TensorFlow, not in the reference tree, follow SURVEY 
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
