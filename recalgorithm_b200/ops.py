@@ -14,8 +14,21 @@ from . import _lib
 F32, I64 = torch.float32, torch.int64
 
 
+_empty_anchor = {}
+
+
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
+    """Device address of a tensor; None stays NULL (= "output not wanted").  An EMPTY tensor (batch 0) has data_ptr() == 0,
+    which the C ABI would read as a missing argument: it gets the address of a small per-device anchor instead -- never
+    dereferenced, every entry point returns before launching when its batch dimension is 0."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        a = _empty_anchor.get(t.device)
+        if a is None:
+            a = _empty_anchor[t.device] = torch.zeros(64, dtype=torch.uint8, device=t.device)
+        return a.data_ptr()
+    return t.data_ptr()
 
 
 def _stream() -> int:

@@ -165,3 +165,52 @@ def test_c_abi_calls_are_cuda_graph_capturable():
     step()                                                         # eager, same inputs
     for k in got:
         assert torch.equal(got[k], outs[k]) or float((got[k] - outs[k]).abs().max()) <= 1e-6 * float(outs[k].abs().max()), k
+
+
+def test_empty_batch_is_a_no_op_everywhere():
+    """B = 0 (e.g. an empty last shard of an eval set): every op returns correctly shaped empties and ZERO parameter gradients."""
+    from recalgorithm_b200 import ops
+    z = lambda *s: torch.zeros(s, device="cuda")
+    F, D, rows = 5, 8, 7
+    table, off = torch.randn((rows * F, D), device="cuda"), torch.arange(F + 1, device="cuda") * rows
+    ids = torch.zeros((0, F), dtype=torch.int64, device="cuda")
+    tile, fm2 = ops.embed_fm2_fwd(table, off, ids)
+    assert tile.shape == (0, F, D) and fm2.shape == (0, 1)
+    assert ops.embed_fm2_bwd(tile, z(0, F, D), z(0)).shape == (0, F, D)
+    t2, bi = ops.embed_bi_fwd(table, off, ids)
+    assert bi.shape == (0, D) and ops.embed_bi_bwd(t2, None, z(0, D)).shape == (0, F, D)
+    assert ops.first_order_fwd(torch.randn(rows * F, device="cuda"), off, ids).shape == (0, 1)
+    d = F * D
+    w, b = torch.randn((3, d), device="cuda"), torch.randn((3, d), device="cuda")
+    assert ops.cross_fwd(z(0, d), w, b).shape == (0, d)
+    dx0, _, dw, db = ops.cross_bwd(z(0, d), w, b, z(0, d))
+    assert dx0.shape == (0, d) and float(dw.abs().max()) == 0 and float(db.abs().max()) == 0
+    filt = torch.randn((F * F, 16), device="cuda")
+    out, pooled = ops.cin_fwd(z(0, F, D), z(0, F, D), filt, want_pooled=True)
+    assert out.shape == (0, 16, D) and pooled.shape == (0, 16)
+    _, _, dfilt = ops.cin_bwd(z(0, F, D), z(0, F, D), filt, z(0, 16, D))
+    assert float(dfilt.abs().max()) == 0
+    ws = [torch.randn(s, device="cuda") for s in ((4 * D, 64), (64,), (64, 32), (32,), (32, 1), (1,))]
+    lens = torch.zeros((0,), dtype=torch.int64, device="cuda")
+    assert ops.din_attention_fwd(z(0, D), z(0, 6, D), lens, *ws).shape == (0, D)
+    _, _, dws = ops.din_attention_bwd(z(0, D), z(0, 6, D), lens, *ws, z(0, D))
+    assert all(float(x.abs().max()) == 0 for x in dws)
+    w1, w2 = torch.randn((F, 4), device="cuda"), torch.randn((4, F), device="cuda")
+    assert ops.senet_fwd(z(0, F, D), w1, w2).shape == (0, F, D)
+    _, dw1, dw2 = ops.senet_bwd(z(0, F, D), w1, w2, z(0, F, D))
+    assert float(dw1.abs().max()) == 0 and float(dw2.abs().max()) == 0
+    wb = torch.randn((D, D), device="cuda")
+    assert ops.bilinear_fwd(z(0, F, D), wb, "all").shape == (0, (F - 1) * (F - 2) // 2, D)
+    r = torch.randn((F * (F - 1) // 2,), device="cuda")
+    assert ops.fwfm_fwd(z(0, F, D), r).shape == (0, 1)
+    _, dr = ops.fwfm_bwd(z(0, F, D), r, z(0))
+    assert float(dr.abs().max()) == 0
+    aw, ab, ah = torch.randn((D, 16), device="cuda"), torch.randn((16,), device="cuda"), torch.randn((16, 1), device="cuda")
+    assert ops.afm_fwd(z(0, F, D), aw, ab, ah).shape == (0, D)
+    _, daw, dab, dah = ops.afm_bwd(z(0, F, D), aw, ab, ah, z(0, D))
+    assert float(daw.abs().max()) == 0 and float(dab.abs().max()) == 0 and float(dah.abs().max()) == 0
+    assert ops.ffm_fwd(z(0, F, F - 1, D)).shape == (0, 1) and ops.ffm_bwd(z(0, F, F - 1, D), z(0)).shape == (0, F, F - 1, D)
+    packed = torch.randn(int(ops._lib.lib().ctr_bst_param_count(D, 2, 6)), device="cuda")
+    assert ops.bst_transformer_fwd(z(0, 6, D), z(0, 6, D), z(0, 6, D), lens, packed, 2, 6).shape == (0, 6, D)
+    *_, dpk = ops.bst_transformer_bwd(z(0, 6, D), z(0, 6, D), z(0, 6, D), lens, packed, z(0, 6, D), 2, 6)
+    assert float(dpk.abs().max()) == 0
