@@ -1,24 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the hot path (BASELINE.json metric).
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric: CTR forward+backward samples/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--ids uniform|zipf]
 
-Metric: CTR forward+backward samples/sec.  One "step" = one pass of the hot path over one batch:
-fused embedding lookup + DeepFM second-order term forward (-> (B,F,D) tile + FM2 logit), then its
-backward (-> IndexedSlices row gradients).  Default workload = BASELINE config 5 on ONE GPU:
-DeepFM, 40 fields, embed_dim 32, batch 65536, 100 M-row vocabulary (2.5 M rows per field, 12.8 GB fp32).
-
+One "step" = one pass of the hot path over one batch.  Workloads (BASELINE.json `configs`):
+  deepfm_cfg5          configs[4] on ONE GPU (default at N=1): DeepFM, 40 fields, embed_dim 32, batch 65536, 100 M-row
+                       vocabulary (12.8 GB fp32, fits one GPU): fused lookup+FM2 forward, then its backward.
+  deepfm_cfg5_sharded  configs[4] as named: the vocabulary ROW-SHARDED over the N GPUs (default at N>1; 32 GB shard per rank,
+                       B = 65536 per rank): rows pulled / gradient rows pushed over NVLink inside the kernels.
+  dcn_cfg2 | xdeepfm_cfg3 | din_cfg4   configs[1..3]: lookup + cross stack / CIN / DIN attention, forward+backward.
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  value      device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
-  e2e        same metric through the public autograd API with HOST (pinned) ids/labels: H2D copies, loss,
-             D2H of the loss inside the timed region
-  roofline   achieved algorithmic GB/s of the dominant kernel (the fused gather) vs MEASURED_PEAKS.json
-  cpu_baseline   the restated reference (oracle port, torch CPU op-for-op) timed on this box's host cores
+  value        device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
+  e2e          same metric through the public autograd API with HOST (pinned) ids/labels: H2D copies, loss, D2H of the loss
+               inside the timed region
+  roofline     achieved algorithmic GB/s (or TFLOP/s) of the dominant kernel vs MEASURED_PEAKS.json
+  sustained    the same step looped for >= 2 s with the clock sampler running
+  configs      (default line only) samples/s + roofline fraction of configs 2, 3, 4 from short runs in the same process
+  cpu_baseline the restated reference (oracle port, torch CPU op-for-op) timed on this box's host cores
 --impl reference times that CPU restatement as the reference arm (TF 1.14 itself cannot be installed).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -37,29 +41,31 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-WORKLOADS = {
-    # BASELINE.json configs[4] on one GPU: the configuration the 70 % target is quoted on
+DEEPFM = {
     "deepfm_cfg5": dict(model="DeepFM lookup+FM2", B=65536, F=40, D=32, rows_per_field=2_500_000, id_batches=8),
-    # row-sharded variant: the vocabulary outgrows one GPU -- 6.25 M rows/field PER RANK (32 GB shard each;
-    # 2 G rows = 256 GB at 8 GPUs); rows pulled / gradients pushed over NVLink inside the kernels, no NCCL data collective
+    # 6.25 M rows/field PER RANK (32 GB shard each; 2 G rows = 256 GB at 8 GPUs): the vocabulary outgrows one GPU
     "deepfm_cfg5_sharded": dict(model="DeepFM lookup+FM2, row-sharded tables", B=65536, F=40, D=32,
-                                rows_per_field_per_rank=6_250_000, id_batches=8, sharded=True),
-    # small variant for quick checks
+                                rows_per_field_per_rank=6_250_000, rows_per_field=2_500_000, id_batches=8, sharded=True),
     "deepfm_small": dict(model="DeepFM lookup+FM2", B=8192, F=40, D=32, rows_per_field=100_000, id_batches=4),
+    "deepfm_small_sharded": dict(model="DeepFM lookup+FM2, row-sharded tables", B=8192, F=40, D=32,
+                                 rows_per_field_per_rank=100_000, rows_per_field=100_000, id_batches=4, sharded=True),
 }
-
-FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+LAYER_WORKLOADS = ("dcn_cfg2", "xdeepfm_cfg3", "din_cfg4")
+NVLINK_PEAK_GBS = 770.0       # B200_PROFILING.md: measured peer copy, per direction per GPU
 
 
 def measured_peaks():
+    d = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            j = json.load(open(p))
+            d.update(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j["bf16_tflops"]),
+                     bf16_tflops_sustained=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                     source="measured (MEASURED_PEAKS.json)")
         except Exception:
             pass
-    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    return d
 
 
 def bytes_per_sample(F, D):
@@ -67,6 +73,28 @@ def bytes_per_sample(F, D):
     fwd = F * (8 + 2 * D * 4) + 4          # read id, read row, write tile ; write logit
     bwd = F * (3 * D * 4) + 4              # read d_tile, read tile, write row-grads ; read d_logit
     return fwd, bwd
+
+
+def kernel_source_hash():
+    h = hashlib.sha256()
+    for f in ("embed_fm2.cu", "ctr_common.cuh"):
+        h.update(open(os.path.join(ROOT, "recalgorithm_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(workload, ids_kind):
+    """DRAM bytes per launch of the gather from the committed ncu capture -- only while the kernel source still hashes to
+    what was profiled (ncu cannot run inside the bench); otherwise null + the reason."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(tp)).get(workload, {})
+    except Exception:
+        return None, "profiles/traffic.json missing"
+    if ids_kind != "uniform":
+        return None, "ncu capture was taken with uniform ids"
+    if t.get("kernel_source_sha256_16") != kernel_source_hash():
+        return None, f"stale: kernel source changed since {t.get('source', 'the capture')} (hash {t.get('kernel_source_sha256_16')} != {kernel_source_hash()})"
+    return t.get("embed_fm2_fwd_dram_bytes_per_launch"), t.get("source")
 
 
 class ClockSampler:
@@ -105,6 +133,7 @@ class ClockSampler:
         if self.nv is not None:
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
+        return self
 
     def stop(self):
         self._stop.set()
@@ -114,64 +143,69 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    elif torch.cuda.is_available():
-        torch.cuda.set_device(0)
-    return rank, world, local
+class Dist:
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        else:
+            self.dist = None
+            torch.cuda.set_device(0)
+        self.dev = torch.device("cuda", self.local if self.world > 1 else 0)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, x: float):
+        if self.world == 1:
+            return [x]
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+
+def timed_steps(dd: Dist, step, steps, n_marks=0):
+    """EXACTLY `steps` steps bracketed by barrier + synchronize; returns (total ms = max over ranks, mean ms per mark)."""
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks + 1)] for _ in range(steps)] if n_marks else None
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dd.barrier()
+    t0.record()
+    for i in range(steps):
+        step(i, evs[i] if evs else None)
+    t1.record()
+    dd.barrier()
+    ms = dd.max(t0.elapsed_time(t1))
+    marks = [statistics.mean(e[j].elapsed_time(e[j + 1]) for e in evs) for j in range(n_marks)] if evs else []
+    return ms, marks
+
+
+def sustained_run(dd: Dist, step, ms_per_step, units_per_step, seconds=2.0):
+    """The same step looped for >= `seconds` with the clock sampler running (the headline region is only milliseconds)."""
+    n = max(50, int(seconds * 1e3 / max(ms_per_step, 1e-3)) + 1)
+    sampler = ClockSampler(dd.local if dd.world > 1 else 0).start()
+    ms, _ = timed_steps(dd, step, n)
+    clocks = sampler.stop()
+    return {"seconds": ms * 1e-3, "steps": n, "ms_per_step": ms / n, "value": dd.world * units_per_step * n / (ms * 1e-3), "clocks": clocks}
 
 
 # ----------------------------------------------------------------------------------------------------
 # CPU restatement of the reference model_fn slice (oracle port): used by cpu_baseline and --impl reference
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, steps, warmup, sample_B, rows_per_field):
-    """Times forward+backward of the restated reference on the host cores; returns (samples/s, info)."""
-    from oracle import torch_cpu_model as M            # the only oracle use in bench.py (the measured baseline)
-    cores = usable_cores()
-    model = M.DeepFMLookupFM2CPU(cfg["F"], cfg["D"], rows_per_field, seed=1234)
-    g = torch.Generator().manual_seed(1234)
-    batches = [(torch.randint(0, rows_per_field, (sample_B, cfg["F"]), generator=g),
-                (torch.rand((sample_B, 1), generator=g) < 0.0356).float()) for _ in range(4)]
-    # give the CPU arm its best thread count: many-core hosts oversubscribe badly on these small ops
-    best = None
-    for nt in sorted({min(cores, c) for c in (4, 8, 16, 32, 64, cores)}):
-        torch.set_num_threads(nt)
-        model.step(*batches[0])
-        t0 = time.perf_counter()
-        model.step(*batches[1])
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[0]:
-            best = (dt, nt)
-    threads = best[1]
-    torch.set_num_threads(threads)
-    for i in range(warmup):
-        model.step(*batches[i % 4])
-    # bound the run: shrink the per-step sample so that `steps` steps take about a minute at most
-    t0 = time.perf_counter()
-    model.step(*batches[0])
-    t1 = time.perf_counter() - t0
-    if t1 * steps > 60.0 and sample_B > 512:
-        sample_B = max(512, int(sample_B * 60.0 / (t1 * steps)) // 256 * 256)
-        batches = [(ids[:sample_B].contiguous(), lab[:sample_B].contiguous()) for ids, lab in batches]
-        model.step(*batches[0])
-    t0 = time.perf_counter()
-    for i in range(steps):
-        model.step(*batches[i % 4])
-    dt = time.perf_counter() - t0
-    info = {"cores": threads, "host_cores_usable": cores, "kind": "port",
-            "sample": f"B={sample_B} per step x {steps} steps, F={cfg['F']}, D={cfg['D']}, "
-                      f"{rows_per_field} rows/field ({cfg['F'] * rows_per_field * cfg['D'] * 4 / 1e9:.1f} GB of tables), "
-                      "uniform ids; fwd+bwd of per-field gathers + add_n/square FM2 + dense(1) deep head + sigmoid-CE "
-                      "(torch CPU op-for-op restatement of DeepFM/deepfm.py:178-235; TF 1.14 not installable)"}
-    return sample_B * steps / dt, dt / steps * 1e3, info
-
-
 def usable_cores():
     """Cores this process may really use: affinity mask capped by the cgroup CPU quota."""
     try:
@@ -188,32 +222,80 @@ def usable_cores():
 
 
 def host_table_rows(cfg):
-    """Rows per field for the CPU arm: the full table when host RAM allows, else scaled down (stated in `sample`)."""
-    # capped at 250 k rows/field (1.3 GB at F=40, D=32): first-touch initialisation of the full 12.8 GB host table
-    # alone takes ~50 s; the smaller table is still far larger than any CPU cache and can only flatter the CPU arm.
-    want = min(cfg.get("rows_per_field", 250_000), 250_000)
+    """Rows per field for the CPU arm: the GPU arm's full table when host RAM allows, else halved until it fits (the config
+    keys of the CPU line state what actually ran)."""
+    want = cfg["rows_per_field"]
     try:
         import psutil
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 32 << 30
-    per_row = cfg["F"] * cfg["D"] * 4 * 2.2            # table + its dense grad buffer headroom
-    while want * per_row > 0.5 * avail and want > 10_000:
+    per_row = cfg["F"] * cfg["D"] * 4 * 1.3            # table + sparse-gradient headroom
+    while want * per_row > 0.6 * avail and want > 10_000:
         want //= 2
     return want
 
 
-def run_reference_arm(args, cfg):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+_cpu_model_cache = {}
+
+
+def cpu_reference_run(cfg, steps, warmup, budget_s=90.0):
+    """Forward+backward of the restated reference on the host cores at the GPU arm's B and table size (RAM permitting);
+    returns (samples/s, ms/step, info).  The per-step batch is cut only if `steps` full batches would exceed `budget_s`."""
+    from oracle import torch_cpu_model as M            # the only oracle use in bench.py (the measured baseline)
+    cores = usable_cores()
     rows = host_table_rows(cfg)
-    sample_B = 8192
-    sps, ms, info = cpu_reference_run(cfg, args.steps, max(args.warmup, 1), sample_B, rows)
+    key = (cfg["F"], cfg["D"], rows)
+    if key not in _cpu_model_cache:
+        _cpu_model_cache[key] = M.DeepFMLookupFM2CPU(cfg["F"], cfg["D"], rows, seed=1234)
+    model = _cpu_model_cache[key]
+    B = cfg["B"]
+    g = torch.Generator().manual_seed(1234)
+    batches = [(torch.randint(0, rows, (B, cfg["F"]), generator=g), (torch.rand((B, 1), generator=g) < 0.0356).float())
+               for _ in range(4)]
+    probe = [(i[:8192].contiguous(), l[:8192].contiguous()) for i, l in batches[:2]]
+    best = None                               # give the CPU arm its best thread count: many-core hosts oversubscribe on small ops
+    for nt in sorted({min(cores, c) for c in (4, 8, 16, 32, 64, cores)}):
+        torch.set_num_threads(nt)
+        model.step(*probe[0])
+        t0 = time.perf_counter()
+        model.step(*probe[1])
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    threads = best[1]
+    torch.set_num_threads(threads)
+    est = best[0] * B / 8192
+    sample_B = B
+    if est * (steps + warmup) > budget_s:
+        sample_B = max(4096, int(B * budget_s / (est * (steps + warmup))) // 4096 * 4096)
+        batches = [(i[:sample_B].contiguous(), l[:sample_B].contiguous()) for i, l in batches]
+    for i in range(warmup):
+        model.step(*batches[i % 4])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        model.step(*batches[i % 4])
+    dt = time.perf_counter() - t0
+    info = {"cores": threads, "host_cores_usable": cores, "kind": "port", "B": sample_B, "rows_per_field": rows,
+            "same_config_as_gpu_arm": bool(sample_B == B and rows == cfg["rows_per_field"]),
+            "sample": f"B={sample_B} per step x {steps} steps, F={cfg['F']}, D={cfg['D']}, {rows} rows/field "
+                      f"({cfg['F'] * rows * cfg['D'] * 4 / 1e9:.1f} GB of tables), uniform ids; fwd+bwd of per-field gathers + "
+                      "add_n/square FM2 + dense(1) deep head + sigmoid-CE (torch CPU op-for-op restatement of "
+                      "DeepFM/deepfm.py:178-235; TF 1.14 not installable)"}
+    return sample_B * steps / dt, dt / steps * 1e3, info
+
+
+def run_reference_arm(args, cfg):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sps, ms, info = cpu_reference_run(cfg, args.steps, max(args.warmup, 1))
     line = {"metric": "ctr_fwd_bwd_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, **{k: cfg[k] for k in ("B", "F", "D")}, "rows_per_field": rows},
+            "config": {"workload": args.workload, "model": cfg["model"], "global_batch": info["B"], "B_per_gpu": info["B"],
+                       "B": info["B"], "F": cfg["F"], "D": cfg["D"], "rows_per_field": info["rows_per_field"],
+                       "vocab_rows_total": info["rows_per_field"] * cfg["F"], "ids": "uniform int64",
+                       "note": "CPU arm runs the single-process configuration (one batch of B per step) at every N"},
             "cpu_baseline": {"value": sps, "unit": "samples/s", **info},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -221,135 +303,23 @@ def run_reference_arm(args, cfg):
 
 
 # ----------------------------------------------------------------------------------------------------
-# GPU arm
+# e2e harness: pinned host inputs -> H2D (double-buffered on a copy stream) -> public autograd API -> loss D2H
 # ----------------------------------------------------------------------------------------------------
-def run_ours(args, cfg):
-    from recalgorithm_b200 import _lib, autograd, ops
-    rank, world, local = dist_setup(args.gpus)
-    if world > 1:
-        import torch.distributed as dist
-    dev = torch.device("cuda", local if world > 1 else 0)
-    sharded_mode = bool(cfg.get("sharded"))
-    B, F, D, NB = cfg["B"], cfg["F"], cfg["D"], cfg["id_batches"]
-    rows = cfg["rows_per_field_per_rank"] * world if sharded_mode else cfg["rows_per_field"]
-    if os.environ.get("CTR_BENCH_ROWS"):                       # experiment knob (table-size sweeps); not used by default
-        rows = int(os.environ["CTR_BENCH_ROWS"])
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-
-    if sharded_mode:
-        if world < 2:
-            raise SystemExit("deepfm_cfg5_sharded needs --gpus >= 2 (launch under torchrun)")
-        from recalgorithm_b200 import sharded as shard_mod
-        tables = shard_mod.ShardedEmbeddingTables([rows] * F, D, batch_per_rank=B, device=dev, init="normal")
-    else:
-        # Every rank holds the full table (it fits one GPU: 12.8 GB of 180 GB) => replicas, no exchange step.
-        tables = autograd.EmbeddingTables([rows] * F, D, device=dev, init=None)
-        tables.weight.normal_(0, D ** -0.5, generator=gen)
-    if args.ids == "zipf":
-        # SURVEY 8d config 5, second case: Zipf(1.05) over each field's vocabulary (hot rows are served by L2), drawn by
-        # inverse CDF; a fixed random permutation-free mapping (rank k -> row k) keeps the hot rows of a field adjacent.
-        cdf = torch.cumsum(torch.arange(1, rows + 1, device=dev, dtype=torch.float64) ** -1.05, 0)
-        cdf /= cdf[-1].clone()
-        id_sets = [torch.searchsorted(cdf, torch.rand((B, F), device=dev, generator=gen, dtype=torch.float64)).clamp_(max=rows - 1)
-                   for _ in range(NB)]
-        del cdf
-    else:
-        id_sets = [torch.randint(0, rows, (B, F), device=dev, generator=gen) for _ in range(NB)]
-    ids_desc = "Zipf(1.05) int64 (hot rows L2-resident: not the HBM worst case)" if args.ids == "zipf" else "uniform int64"
-    d_tile = torch.randn((B, F, D), device=dev, generator=gen) * 0.01      # upstream grad of the deep part
-    d_fm2 = torch.randn((B,), device=dev, generator=gen) * 0.01            # upstream grad of the logit
-    tile = torch.empty((B, F, D), device=dev)
-    fm2 = torch.empty((B, 1), device=dev)
-    row_grads = torch.empty((B, F, D), device=dev)
-
-    def step(i, ev=None):
-        ids = id_sets[i % NB]
-        if ev:
-            ev[0].record()
-        if sharded_mode:
-            tables.lookup_fm2(ids, tile=tile, fm2=fm2)             # rows pulled from the owners over NVLink
-        else:
-            ops.embed_fm2_fwd(tables.weight, tables.field_row_offset, ids, tile=tile, fm2=fm2)
-        if ev:
-            ev[1].record()
-        ops.embed_fm2_bwd(tile, d_tile, d_fm2, row_grads=row_grads)
-        if sharded_mode:
-            tables.push_grads(ids, row_grads, barrier=False)      # gradient rows pushed to their owners
-        if ev:
-            ev[2].record()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    launches0 = _lib.kernel_launches()
-    sampler = ClockSampler(local if world > 1 else 0)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
-    barrier()
-    t_start.record()
-    for i in range(args.steps):
-        step(i, evs[i])
-    t_end.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = _lib.kernel_launches() - launches0
-    ms_total = t_start.elapsed_time(t_end)
-    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
-    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    value = world * B * args.steps / (ms_total * 1e-3)
-
-    if sharded_mode:
-        barrier()
-        if rank == 0:
-            peak, peak_src = measured_peaks()
-            fwd_b, bwd_b = bytes_per_sample(F, D)
-            remote = (world - 1) / world
-            nv_bytes = B * F * D * 4 * remote                       # rows crossing NVLink per rank per direction
-            print(json.dumps({
-                "metric": "ctr_fwd_bwd_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "model": cfg["model"], "global_batch": B * world, "B_per_gpu": B, "F": F,
-                           "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F,
-                           "table_bytes_total": rows * F * D * 4, "ids": "uniform int64",
-                           "parallelism": f"tables row-sharded over {world} GPUs (row % G), peer-pull forward + fused gradient push",
-                           "l2": "inputs larger than L2 (see deepfm_cfg5)"},
-                "roofline": {"bound": "nvlink", "kernel": "embed_fm2_fwd_kernel<8,sharded>", "fwd_ms": fwd_ms, "bwd_push_ms": bwd_ms,
-                             "nvlink_bytes_per_direction_per_rank": nv_bytes,
-                             "achieved_pull_GBps": nv_bytes / (fwd_ms * 1e-3) / 1e9, "peak_GBps": 770.0,
-                             "frac": nv_bytes / (fwd_ms * 1e-3) / 1e9 / 770.0,
-                             "peak_source": "B200_PROFILING.md: measured peer copy 770 GB/s per direction"},
-                "gpu_launches": int(launches), "clocks": clocks}), flush=True)
-        return
-
-    # ---------------- e2e: public autograd API with host (pinned) inputs ----------------
-    e2e_steps = max(3, min(args.steps, 50))
-    w_deep = (torch.randn((F * D, 1), device=dev, generator=gen) * 0.01).requires_grad_()
-    ids_host = [s.cpu().pin_memory() for s in id_sets[:4]]
-    lab_host = [(torch.rand((B, 1)) < 0.0356).float().pin_memory() for _ in range(4)]
-    # double-buffered input staging: the H2D copy of step i+1 runs on a copy stream while step i computes (the
-    # reference's input_fn does the same with dataset.prefetch(1), utils.py:24); every step's copy is inside the timed region
+def e2e_loop(dd: Dist, B, F, host_ids, host_labels, model_step, steps):
+    """model_step(ids_dev, labels_dev) -> loss tensor (runs forward+backward through the public API).  Every step's H2D copy
+    of ids+labels and the D2H of its loss are inside the timed region; the loss is READ on the host one step late (so the
+    launch latency of step i hides behind step i-1; the last loss is read before the closing event)."""
+    dev = dd.dev
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
-    slots = [(torch.empty((B, F), dtype=torch.int64, device=dev), torch.empty((B, 1), device=dev)) for _ in range(2)]
+    id_dtype = host_ids[0].dtype
+    slots = [(torch.empty((B, F), dtype=id_dtype, device=dev), torch.empty((B, 1), device=dev)) for _ in range(2)]
     ev_ready = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
-    # every step's loss is copied to pinned host memory and READ on the host inside the timed region, one step late
-    # (the host reads step i-1's loss after it has queued step i, so the launch latency of step i hides behind step i-1;
-    # the last step's loss is read before the closing event)
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     ev_loss = [torch.cuda.Event() for _ in range(2)]
     losses = []
+    nb = len(host_ids)
 
     def read_loss(i):
         ev_loss[i % 2].synchronize()
@@ -359,24 +329,18 @@ def run_ours(args, cfg):
         sl = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_free[sl])
-            slots[sl][0].copy_(ids_host[i % 4], non_blocking=True)
-            slots[sl][1].copy_(lab_host[i % 4], non_blocking=True)
+            slots[sl][0].copy_(host_ids[i % nb], non_blocking=True)
+            slots[sl][1].copy_(host_labels[i % nb], non_blocking=True)
             ev_ready[sl].record(copy_stream)
 
-    def e2e_step(i):
+    def one(i):
         sl = i % 2
         main_stream.wait_event(ev_ready[sl])
-        ids_dev, lab_dev = slots[sl]
-        tables.zero_grad()
-        w_deep.grad = None
-        t_, f_ = autograd.lookup_fm2(tables, ids_dev)
-        logit = f_ + t_.reshape(B, F * D) @ w_deep                  # dense(1) consumer of the tile (torch = plumbing)
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, lab_dev)
-        loss.backward()
+        loss = model_step(*slots[sl])
         ev_free[sl].record(main_stream)
         loss_host[sl:sl + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H of the step's result
         ev_loss[sl].record(main_stream)
-        issue_copy(i + 2)                                             # next use of this slot
+        issue_copy(i + 2)                                                           # next use of this slot
         if i > 0:
             read_loss(i - 1)
 
@@ -385,63 +349,335 @@ def run_ours(args, cfg):
     issue_copy(0)
     issue_copy(1)
     for i in range(3):
-        e2e_step(i)
+        one(i)
     read_loss(2)
-    barrier()
+    dd.barrier()
     t0 = time.perf_counter()
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_start.record()
-    for i in range(3, 3 + e2e_steps):
-        e2e_step(i)
-    read_loss(3 + e2e_steps - 1)
-    e_end.record()
-    barrier()
-    e2e_ms = max(e_start.elapsed_time(e_end), (time.perf_counter() - t0) * 1e3)   # never less than the wall clock
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3, 3 + steps):
+        one(i)
+    read_loss(3 + steps - 1)
+    e1.record()
+    dd.barrier()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # never less than the wall clock
+    return dd.max(ms), losses
 
+
+# ----------------------------------------------------------------------------------------------------
+# DeepFM lookup+FM2 (configs[4]): one GPU / replicas, or row-sharded over the ranks
+# ----------------------------------------------------------------------------------------------------
+def make_ids(args, rows, B, F, NB, dev, gen):
+    if args.ids == "zipf":
+        # SURVEY 8d config 5, second case: Zipf(1.05) over each field's vocabulary (hot rows are served by L2), inverse CDF
+        cdf = torch.cumsum(torch.arange(1, rows + 1, device=dev, dtype=torch.float64) ** -1.05, 0)
+        cdf /= cdf[-1].clone()
+        sets = [torch.searchsorted(cdf, torch.rand((B, F), device=dev, generator=gen, dtype=torch.float64)).clamp_(max=rows - 1)
+                for _ in range(NB)]
+        return sets, "Zipf(1.05) int64 (hot rows L2-resident: not the HBM worst case)"
+    return [torch.randint(0, rows, (B, F), device=dev, generator=gen) for _ in range(NB)], "uniform int64"
+
+
+def run_deepfm(args, cfg, dd: Dist):
+    from recalgorithm_b200 import _lib, autograd, ops
+    dev, world, rank = dd.dev, dd.world, dd.rank
+    sharded_mode = bool(cfg.get("sharded"))
+    B, F, D, NB = cfg["B"], cfg["F"], cfg["D"], cfg["id_batches"]
+    peaks = measured_peaks()
+    fwd_b, bwd_b = bytes_per_sample(F, D)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    d_tile = torch.randn((B, F, D), device=dev, generator=gen) * 0.01      # upstream grad of the deep part
+    d_fm2 = torch.randn((B,), device=dev, generator=gen) * 0.01            # upstream grad of the logit
+    tile = torch.empty((B, F, D), device=dev)
+    fm2 = torch.empty((B, 1), device=dev)
+    sampler_idx = dd.local if world > 1 else 0
+
+    def replica_setup():
+        rows = int(os.environ.get("CTR_BENCH_ROWS", cfg["rows_per_field"]))      # experiment knob (table-size sweeps)
+        tables = autograd.EmbeddingTables([rows] * F, D, device=dev, init=None)
+        tables.weight.normal_(0, D ** -0.5, generator=gen)
+        id_sets, ids_desc = make_ids(args, rows, B, F, NB, dev, gen)
+        row_grads = torch.empty((B, F, D), device=dev)
+
+        def step(i, ev=None):
+            if ev:
+                ev[0].record()
+            ops.embed_fm2_fwd(tables.weight, tables.field_row_offset, id_sets[i % NB], tile=tile, fm2=fm2)
+            if ev:
+                ev[1].record()
+            ops.embed_fm2_bwd(tile, d_tile, d_fm2, row_grads=row_grads)
+            if ev:
+                ev[2].record()
+        return tables, rows, id_sets, ids_desc, step
+
+    if not sharded_mode:
+        # ------------------------------------------------------------------ one GPU (or N replicas, no exchange step)
+        tables, rows, id_sets, ids_desc, step = replica_setup()
+        for i in range(args.warmup):
+            step(i)
+        dd.barrier()
+        launches0 = _lib.kernel_launches()
+        sampler = ClockSampler(sampler_idx).start()
+        ms_total, (fwd_ms, bwd_ms) = timed_steps(dd, step, args.steps, n_marks=2)
+        clocks = sampler.stop()
+        launches = _lib.kernel_launches() - launches0
+        value = world * B * args.steps / (ms_total * 1e-3)
+        sustained = sustained_run(dd, step, ms_total / args.steps, B)
+
+        # e2e: public autograd API, int32 ids over PCIe, lookup + FM2 + fused dense(1) head -> sigmoid-CE -> backward
+        e2e_steps = max(3, min(args.steps, 50))
+        w_deep = (torch.randn((F * D, 1), device=dev, generator=gen) * 0.01).requires_grad_()
+        ids_host = [s.int().cpu().pin_memory() for s in id_sets[:4]]
+        lab_host = [(torch.rand((B, 1)) < 0.0356).float().pin_memory() for _ in range(4)]
+
+        def model_fused(ids_dev, lab_dev):
+            tables.zero_grad()
+            w_deep.grad = None
+            f_, lin = autograd.lookup_fm2_linear(tables, ids_dev, w_deep)          # deep head fused into the gather
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(f_ + lin, lab_dev)
+            loss.backward()
+            return loss
+
+        def model_unfused(ids_dev, lab_dev):
+            tables.zero_grad()
+            w_deep.grad = None
+            t_, f_ = autograd.lookup_fm2(tables, ids_dev)
+            logit = f_ + t_.reshape(B, F * D) @ w_deep                              # dense(1) consumer of the tile in torch
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, lab_dev)
+            loss.backward()
+            return loss
+
+        e2e_ms, losses = e2e_loop(dd, B, F, ids_host, lab_host, model_fused, e2e_steps)
+        e2e_ms_unf, losses_unf = e2e_loop(dd, B, F, ids_host, lab_host, model_unfused, e2e_steps)
+        e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+        if rank != 0:
+            return
+        ach_fwd = fwd_b * B / (fwd_ms * 1e-3) / 1e9
+        ach_bwd = bwd_b * B / (bwd_ms * 1e-3) / 1e9
+        ach_step = (fwd_b + bwd_b) * B * args.steps / (ms_total * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(args.workload, args.ids)
+        hbm = peaks["hbm_gbs"]
+        line = {
+            "metric": "ctr_fwd_bwd_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "model": cfg["model"], "global_batch": B * world, "B_per_gpu": B, "F": F,
+                       "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "ids": ids_desc,
+                       "parallelism": "replicated tables (12.8 GB fits one GPU), data-parallel ranks, no exchange" if world > 1 else "1 GPU",
+                       "l2": f"inputs larger than L2: {NB} rotating id batches over a {rows * F * D * 4 / 1e9:.1f} GB table; "
+                             f"tile/d_tile/row_grads are {B * F * D * 4 / 1e6:.0f} MB each"},
+            "roofline": {"bound": "hbm", "kernel": "embed_fm2_fwd_kernel<8> (fused gather + FM2)", "achieved": ach_fwd,
+                         "peak": hbm, "unit": "GB/s", "frac": ach_fwd / hbm, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel_source_sha256_16": kernel_source_hash(), "peak_source": peaks["source"],
+                         "algorithmic_bytes_per_launch": fwd_b * B, "avg_launch_ms": fwd_ms},
+            "roofline_bwd": {"kernel": "embed_fm2_bwd_kernel", "achieved": ach_bwd, "frac": ach_bwd / hbm,
+                             "algorithmic_bytes_per_launch": bwd_b * B, "avg_launch_ms": bwd_ms},
+            "roofline_step": {"achieved": ach_step, "frac": ach_step / hbm, "bytes_per_sample": fwd_b + bwd_b},
+            "sustained": sustained,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4,
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1],
+                    "what": "pinned-host int32 ids + labels -> H2D (double-buffered on a copy stream) -> autograd.lookup_fm2_linear "
+                            "(gather + FM2 + dense(1) deep head in one kernel; ids widened on device) -> sigmoid-CE (torch) -> backward "
+                            "(ctr_embed_fm2_lin_bwd -> IndexedSlices + d_w) -> loss D2H to pinned memory, read on the host one step later",
+                    "unfused_head": {"value": world * B * e2e_steps / (e2e_ms_unf * 1e-3), "ms_per_step": e2e_ms_unf / e2e_steps,
+                                     "loss_last": losses_unf[-1],
+                                     "what": "same, with autograd.lookup_fm2 + a torch matmul head (the tile is re-streamed by cuBLAS)"}},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_extra:
+            line["configs"] = {}
+            del tables, id_sets
+            torch.cuda.empty_cache()
+            for name in LAYER_WORKLOADS:
+                line["configs"][name] = layer_workload_measure(dd, name, steps=min(args.steps, 30), warmup=3, brief=True)[0]
+                torch.cuda.empty_cache()
+        if world == 1 and not args.no_cpu_baseline:
+            sps, ms, info = cpu_reference_run(cfg, steps=4, warmup=1, budget_s=30.0)
+            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "ms_per_step": ms, **info}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------------- row-sharded over the ranks
+    if world < 2:
+        raise SystemExit(f"{args.workload} needs --gpus >= 2 (launch under torchrun)")
+    from recalgorithm_b200 import sharded as shard_mod
+    rows = cfg["rows_per_field_per_rank"] * world
+    if os.environ.get("CTR_BENCH_ROWS"):
+        rows = int(os.environ["CTR_BENCH_ROWS"])
+    tables = shard_mod.ShardedEmbeddingTables([rows] * F, D, batch_per_rank=B, device=dev, init="normal")
+    id_sets, ids_desc = make_ids(args, rows, B, F, NB, dev, gen)
+    plan = torch.empty((B, F), dtype=torch.int32, device=dev)
+
+    def step(i, ev=None):
+        ids = id_sets[i % NB]
+        if ev:
+            ev[0].record()
+        tables.plan(ids, plan=plan)                                    # queue slots + row indices (contiguous runs over NVLink)
+        if ev:
+            ev[1].record()
+        tables.lookup_fm2(ids, tile=tile, fm2=fm2)                     # rows pulled from the owners over NVLink
+        if ev:
+            ev[2].record()
+        tables.bwd_push(tile, d_tile, d_fm2, plan)                     # gradient rows stored straight into the owners' queues
+        if ev:
+            ev[3].record()
+
+    for i in range(args.warmup):
+        step(i)
+    dd.barrier()
+    launches0 = _lib.kernel_launches()
+    sampler = ClockSampler(sampler_idx).start()
+    ms_total, (plan_ms, fwd_ms, push_ms) = timed_steps(dd, step, args.steps, n_marks=3)
+    clocks = sampler.stop()
+    launches = _lib.kernel_launches() - launches0
+    tables.finish_push()                                                # raises if a receive queue overflowed
+    value = world * B * args.steps / (ms_total * 1e-3)
+    per_rank = {"plan_ms": dd.gather(plan_ms), "pull_ms": dd.gather(fwd_ms), "bwd_push_ms": dd.gather(push_ms)}
+    sustained = sustained_run(dd, step, ms_total / args.steps, B)
+    tables.finish_push()
+
+    # e2e through the public sharded API: pinned int32 ids -> H2D -> lookup_fm2_autograd -> head + loss -> backward (push)
+    e2e_steps = max(3, min(args.steps, 50))
+    w_deep = (torch.randn((F * D, 1), device=dev, generator=gen) * 0.01).requires_grad_()
+    ids_host = [s.int().cpu().pin_memory() for s in id_sets[:4]]
+    lab_host = [(torch.rand((B, 1)) < 0.0356).float().pin_memory() for _ in range(4)]
+
+    def model_sharded(ids_dev, lab_dev):
+        w_deep.grad = None
+        t_, f_ = shard_mod.lookup_fm2_autograd(tables, ids_dev)
+        logit = f_ + t_.reshape(B, F * D) @ w_deep
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, lab_dev)
+        loss.backward()
+        return loss
+
+    e2e_ms, losses = e2e_loop(dd, B, F, ids_host, lab_host, model_sharded, e2e_steps)
+    tables.finish_push()
+    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    del tables
+    torch.cuda.empty_cache()
+
+    # the zero-traffic split of the same batch (replicated 12.8 GB table) for comparison -- NOT the headline at N > 1
+    rep = None
+    if not args.no_extra:
+        _t, _rows, _ids, _desc, rstep = replica_setup()
+        for i in range(3):
+            rstep(i)
+        rms, _ = timed_steps(dd, rstep, min(args.steps, 50))
+        rep = {"value": world * B * min(args.steps, 50) / (rms * 1e-3), "ms_per_step": rms / min(args.steps, 50),
+               "what": "replicated 12.8 GB table per rank, no exchange (the table fits one GPU): upper bound, zero NVLink traffic"}
     if rank != 0:
         return
-    peak, peak_src = measured_peaks()
-    fwd_b, bwd_b = bytes_per_sample(F, D)
-    ach_fwd = fwd_b * B / (fwd_ms * 1e-3) / 1e9
-    ach_bwd = bwd_b * B / (bwd_ms * 1e-3) / 1e9
-    ach_step = (fwd_b + bwd_b) * B * args.steps / (ms_total * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")          # dram bytes/launch from the committed ncu capture
-    if os.path.exists(tp) and args.ids == "uniform":          # the ncu capture was taken on the default (uniform-id) run
-        try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get("embed_fm2_fwd_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    remote = (world - 1) / world
+    nv_bytes = B * F * D * 4 * remote                       # payload crossing NVLink per rank per direction, each way
+    hbm = peaks["hbm_gbs"]
+    pull_nv_ms = nv_bytes / NVLINK_PEAK_GBS / 1e6
+    pull_hbm_ms = (fwd_b * B - nv_bytes) / hbm / 1e6          # local rows + ids + the tile write
+    push_hbm_ms = (F * 2 * D * 4 + 8) * B / hbm / 1e6         # tile + d_tile read (row_grads never written)
+    bound_ms = max(pull_nv_ms, pull_hbm_ms) + max(pull_nv_ms, push_hbm_ms)
+    pull_gbs = [nv_bytes / (t * 1e-3) / 1e9 for t in per_rank["pull_ms"]]
+    push_gbs = [nv_bytes / (t * 1e-3) / 1e9 for t in per_rank["bwd_push_ms"]]
+    print("[bench] per-rank NVLink GB/s  pull: " + " ".join(f"{x:.0f}" for x in pull_gbs) + "   push: " +
+          " ".join(f"{x:.0f}" for x in push_gbs), file=sys.stderr, flush=True)
     line = {
         "metric": "ctr_fwd_bwd_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "model": cfg["model"], "global_batch": B * world, "B_per_gpu": B, "F": F,
-                   "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "ids": ids_desc,
-                   "parallelism": "replicated tables (12.8 GB fits one GPU), data-parallel ranks" if world > 1 else "1 GPU",
-                   "l2": f"inputs larger than L2: {NB} rotating id batches over a {rows * F * D * 4 / 1e9:.1f} GB table; "
-                         f"tile/d_tile/row_grads are {B * F * D * 4 / 1e6:.0f} MB each"},
-        "roofline": {"bound": "hbm", "kernel": "embed_fm2_fwd_kernel<8> (fused gather + FM2)", "achieved": ach_fwd,
-                     "peak": peak, "unit": "GB/s", "frac": ach_fwd / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": fwd_b * B, "avg_launch_ms": fwd_ms},
-        "roofline_bwd": {"kernel": "embed_fm2_bwd_kernel", "achieved": ach_bwd, "frac": ach_bwd / peak,
-                         "algorithmic_bytes_per_launch": bwd_b * B, "avg_launch_ms": bwd_ms},
-        "roofline_step": {"achieved": ach_step, "frac": ach_step / peak, "bytes_per_sample": fwd_b + bwd_b},
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 8 + B * 4,
-                "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "what": "pinned-host ids+labels -> H2D (double-buffered on a copy stream) -> lookup_fm2 autograd fwd -> dense(1) head + sigmoid-CE (torch) -> "
-                        "backward (fused bwd kernel -> IndexedSlices) -> loss D2H to pinned memory, read on the host one step later"},
-        "gpu_launches": int(launches), "clocks": clocks,
+                   "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "table_bytes_total": rows * F * D * 4,
+                   "shard_bytes_per_gpu": rows * F * D * 4 // world, "ids": ids_desc,
+                   "parallelism": f"row-sharded: tables split over {world} GPUs (global row % {world}); forward pulls rows over NVLink "
+                                  "inside the gather kernel, backward stores gradient rows into the owners' queues (fused "
+                                  "compute+exchange kernels, no NCCL data collective)",
+                   "l2": "inputs larger than L2 (rotating id batches over a 32 GB shard per GPU)"},
+        "roofline": {"bound": "nvlink", "kernel": "embed_fm2_fwd_kernel<8,sharded> (peer-pull gather + FM2)",
+                     "achieved": nv_bytes / (fwd_ms * 1e-3) / 1e9, "peak": NVLINK_PEAK_GBS, "unit": "GB/s",
+                     "frac": nv_bytes / (fwd_ms * 1e-3) / 1e9 / NVLINK_PEAK_GBS, "traffic": None,
+                     "peak_source": "B200_PROFILING.md: measured peer copy 770 GB/s per direction per GPU",
+                     "nvlink_bytes_per_direction_per_rank": nv_bytes, "avg_launch_ms": fwd_ms,
+                     "push": {"kernel": "embed_fm2_bwd_push_kernel<8,12> (backward fused with the gradient exchange)",
+                              "achieved": nv_bytes / (push_ms * 1e-3) / 1e9, "frac": nv_bytes / (push_ms * 1e-3) / 1e9 / NVLINK_PEAK_GBS,
+                              "avg_launch_ms": push_ms},
+                     "plan_ms": plan_ms, "per_rank_pull_GBps": pull_gbs, "per_rank_push_GBps": push_gbs,
+                     "step_bound_ms": bound_ms, "step_frac_of_bound": bound_ms / (ms_total / args.steps),
+                     "bound_terms_ms": {"pull_nvlink": pull_nv_ms, "pull_hbm": pull_hbm_ms, "push_nvlink": pull_nv_ms, "push_hbm": push_hbm_ms},
+                     "link_ceiling_note": "tools/peerbench.cu (all ranks active, 128 B rows): pull tops out at ~650 GB/s, push at ~690 GB/s"},
+        "sustained": sustained,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4, "d2h_bytes_per_step": 4,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1],
+                "what": "per rank: pinned-host int32 ids + labels -> H2D -> sharded.lookup_fm2_autograd (peer-pull gather + FM2, queue plan) "
+                        "-> dense(1) head + sigmoid-CE (torch) -> backward (ctr_embed_fm2_bwd_push: gradient rows into the owners' "
+                        "queues) -> loss D2H, read one step later"},
+        "replicas": rep, "gpu_launches": int(launches), "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        rows_cpu = host_table_rows(cfg)
-        sps, ms, info = cpu_reference_run(cfg, steps=6, warmup=2, sample_B=8192, rows_per_field=rows_cpu)
-        line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "ms_per_step": ms, **info}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# configs 2, 3, 4: lookup + interaction layer chains
+# ----------------------------------------------------------------------------------------------------
+def layer_workload_measure(dd: Dist, name, steps, warmup, brief=False):
+    from tools import workloads as W
+    peaks = measured_peaks()
+    wl = W.BUILDERS[name]()
+    flush = torch.empty(64 * 1024 * 1024, device=dd.dev)      # 256 MB: these working sets fit the 126 MB L2, flush it every step
+    marks = wl["marks"]
+
+    def step(i, ev=None):
+        flush.zero_()
+        wl["step"](ev)
+
+    for i in range(warmup):
+        step(i)
+    # per-stage events bracket the stages only (the flush sits before event 0): step time = sum of the stages
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(marks) + 1)] for _ in range(steps)]
+    dd.barrier()
+    for i in range(steps):
+        step(i, evs[i])
+    dd.barrier()
+    per = {m: statistics.mean(e[j].elapsed_time(e[j + 1]) for e in evs) for j, m in enumerate(marks)}
+    ms_step = dd.max(statistics.mean(e[0].elapsed_time(e[-1]) for e in evs))
+    out = {"value": dd.world * wl["B"] / (ms_step * 1e-3), "unit": "samples/s", "ms_per_step": ms_step, "stage_ms": per,
+           "roofline": wl["roofline"](per, ms_step, peaks), "config": wl["config"], "dtype": wl["dtype"], "steps": steps,
+           "what": "lookup fwd + interaction fwd + interaction bwd + lookup bwd (IndexedSlices); no dense tail; L2 flushed before every step"}
+    if name == "dcn_cfg2":
+        g = W.graphed(lambda: wl["step"](None))
+        for _ in range(3):
+            g()
+        ts = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g(); b.record()
+            ts.append((a, b))
+        torch.cuda.synchronize()
+        gms = statistics.mean(a.elapsed_time(b) for a, b in ts)
+        out["cuda_graph"] = {"ms_per_step": gms, "value": dd.world * wl["B"] / (gms * 1e-3), "what": "the same C-ABI calls captured once, one graph replay per step"}
+    if brief:
+        out = {k: out[k] for k in ("value", "unit", "ms_per_step", "stage_ms", "roofline", "config") if k in out} | (
+            {"cuda_graph": out["cuda_graph"]} if "cuda_graph" in out else {})
+    return out, wl
+
+
+def run_layer_workload(args, dd: Dist):
+    from recalgorithm_b200 import _lib
+    sampler = ClockSampler(dd.local if dd.world > 1 else 0).start()
+    n0 = _lib.kernel_launches()
+    res, wl = layer_workload_measure(dd, args.workload, args.steps, args.warmup)
+    launches = _lib.kernel_launches() - n0
+    clocks = sampler.stop()
+    sustained = sustained_run(dd, lambda i, ev=None: wl["step"](None), res["ms_per_step"], wl["B"])
+    sustained["l2"] = "NOT flushed in this loop (its purpose is the clock record under seconds of load)"
+    if dd.rank != 0:
+        return
+    line = {"metric": "ctr_fwd_bwd_samples_per_sec", "value": res["value"], "unit": "samples/s", "n_gpus": dd.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": res["dtype"], "data": "synthetic",
+            "config": {**res["config"], "l2": "flushed (256 MB write) before every step; flush excluded from the step time",
+                       "parallelism": "independent replicas" if dd.world > 1 else "1 GPU"},
+            "roofline": res["roofline"], "stage_ms": res["stage_ms"], "sustained": sustained,
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "what": res["what"]}
+    if "cuda_graph" in res:
+        line["cuda_graph"] = res["cuda_graph"]
     print(json.dumps(line), flush=True)
 
 
@@ -451,18 +687,26 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="deepfm_cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(DEEPFM) + list(LAYER_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs 2-4 / replica side measurements")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
                     help="id distribution of the synthetic batches (default: uniform = every row an HBM miss)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    cfg = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        # BASELINE config 5 names the row-sharded split: it is the headline whenever there is more than one GPU
+        args.workload = "deepfm_cfg5_sharded" if (world > 1 and args.impl == "ours") else "deepfm_cfg5"
     if args.impl == "reference":
-        run_reference_arm(args, cfg)
+        run_reference_arm(args, DEEPFM.get(args.workload, DEEPFM["deepfm_cfg5"]))
+        return
+    dd = Dist()
+    if args.workload in DEEPFM:
+        run_deepfm(args, DEEPFM[args.workload], dd)
     else:
-        run_ours(args, cfg)
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and torch.distributed.is_initialized():
+        run_layer_workload(args, dd)
+    if dd.world > 1 and torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 
 

@@ -60,6 +60,10 @@ int64_t ctr_kernel_launches(void);              /* kernels launched by this libr
  */
 int ctr_embed_fm2_fwd(const float* table, const int64_t* field_row_offset, const int64_t* ids,
                       int64_t B, int64_t F, int64_t D, float* tile, float* fm2, void* stream);
+/* The same with int32 ids (half the id bytes over PCIe / HBM); ids64_out (may be NULL) receives the widened (B,F) int64 copy
+ * for IndexedSlices consumers (optimizers, ctr_embed_scatter_add). */
+int ctr_embed_fm2_fwd_ids32(const float* table, const int64_t* field_row_offset, const int32_t* ids, int64_t B, int64_t F,
+                            int64_t D, float* tile, float* fm2, int64_t* ids64_out, void* stream);
 
 /* Backward of the pair above = the `values` of TF's IndexedSlices gradient of the gather
  * (indices are the caller's ids):   row_grads[b,f,:] = d_tile[b,f,:] + d_fm2[b] * (S[b,:] - e[b,f,:]),
@@ -67,6 +71,18 @@ int ctr_embed_fm2_fwd(const float* table, const int64_t* field_row_offset, const
  * Rows whose id was invalid receive a gradient too (it is simply never applied; see ctr_embed_scatter_add). */
 int ctr_embed_fm2_bwd(const float* tile, const float* d_tile, const float* d_fm2,
                       int64_t B, int64_t F, int64_t D, float* row_grads, void* stream);
+
+/* Lookup + FM2 with a fused dense(1) consumer of the flattened tile (the first use of the tile by DeepFM's deep part,
+ * DeepFM/deepfm.py:203-212, reduced to one unit): lin[b] = sum_{f,d} tile[b,f,d]*wlin[f,d].  ids: int64 (ids_are_int32 = 0)
+ * or int32 (= 1; ids64_out, may be NULL, receives the widened copy).  tile may be NULL only if no backward follows. */
+int ctr_embed_fm2_lin_fwd(const float* table, const int64_t* field_row_offset, const void* ids, int ids_are_int32, int64_t B,
+                          int64_t F, int64_t D, const float* wlin, float* tile, float* fm2, float* lin, int64_t* ids64_out,
+                          void* stream);
+/* Its backward: the upstream gradient of the tile is the rank-1 product d_lin[b]*wlin[f,d] and is never materialised:
+ *   row_grads[b,f,:] = d_lin[b]*wlin[f,:] + d_fm2[b]*(S[b,:] - e[b,f,:]);   d_wlin[f,:] = sum_b d_lin[b]*e[b,f,:]
+ * (d_wlin (F*D) is zeroed here; fp32 atomics across CTAs).  F*D <= 1536. */
+int ctr_embed_fm2_lin_bwd(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, int64_t B, int64_t F,
+                          int64_t D, float* row_grads, float* d_wlin, void* stream);
 
 /* Densify: grad_table[field_row_offset[f] + ids[b,f], :] += row_grads[b,f,:] for valid ids (duplicates
  * summed, like the optimizer's IndexedSlices de-duplication; TF-internal).  grad_table is
@@ -83,19 +99,33 @@ int ctr_embed_scatter_add(float* grad_table, const int64_t* field_row_offset, co
  * (CUDA IPC / peer mapping for r != own rank).  No collective is involved. */
 int ctr_embed_fm2_fwd_sharded(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
                               const int64_t* ids, int64_t B, int64_t F, int64_t D, float* tile, float* fm2, void* stream);
-/* Backward exchange fused into one kernel: every valid (b,f) writes (local_row, row_grads[b,f,:]) into its OWNER's receive
- * buffer with peer stores.  recv_vals / recv_rows: HOST arrays of G device pointers; entry d = owner d's buffers
- * (G_src, capacity, D) fp32 / (G_src, capacity) int64 as mapped into this process; this rank writes slice [my_rank].
- * counters: device int64[G], zeroed here, ends as the number of entries sent to each owner; *overflow is OR-ed with 1 if
- * an owner's slice would exceed `capacity` (those entries are dropped).  Follow with ctr_sharded_publish_counts, a
- * stream sync and a cross-rank barrier before any owner reads its buffers. */
-int ctr_sharded_grad_push(const float* row_grads, const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F,
-                          int64_t D, int64_t G, int64_t my_rank, float* const* recv_vals, int64_t* const* recv_rows,
-                          int64_t capacity, int64_t* counters, int* overflow, void* stream);
-/* peer_counts_dev: DEVICE array of G device pointers; entry d = owner d's int64[G] count vector (peer mapped);
- * writes peer_counts[d][my_rank] = counters[d]. */
-int ctr_sharded_publish_counts(const int64_t* counters, int64_t* const* peer_counts_dev, int64_t G, int64_t my_rank,
-                               void* stream);
+/* The same with int32 ids (half the id bytes over PCIe / HBM); ids64_out (may be NULL) receives the widened (B,F) int64 copy
+ * that IndexedSlices consumers downstream expect. */
+int ctr_embed_fm2_fwd_sharded_ids32(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
+                                    const int32_t* ids, int64_t B, int64_t F, int64_t D, float* tile, float* fm2,
+                                    int64_t* ids64_out, void* stream);
+/* Gradient exchange, step 1 (independent of the forward; one pass over the ids): assigns every valid (b,f) a slot in its
+ * OWNER's receive queue and writes plan[b,f] = owner << 28 | slot (-1: invalid id, or dropped because the owner's slice is
+ * full -> *overflow = 1).  The queue's local-row indices are written here, as contiguous runs per owner:
+ * recv_rows / recv_counts: HOST arrays of G device pointers; entry d = owner d's (G_src, capacity) int64 row queue /
+ * (G_src,) int64 count vector as mapped into this process; this rank writes slice [my_rank] and, when the kernel ends,
+ * recv_counts[d][my_rank] = min(entries queued at d, capacity) (recv_counts or its entries may be NULL).
+ * counters: device int64[9] scratch, zeroed here (ends as entries per owner + a ticket); overflow: device int, zeroed here.
+ * B*F < 2^28, capacity < 2^28. */
+int ctr_sharded_plan(const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F, int64_t G, int64_t my_rank,
+                     int64_t* const* recv_rows, int64_t* const* recv_counts, int64_t capacity, int64_t* counters,
+                     int* overflow, int32_t* plan, void* stream);
+/* Gradient exchange, step 2, fused into the lookup backward: same arithmetic as ctr_embed_fm2_bwd, but every planned row of
+ * d_tile + d_fm2*(S - e) is stored straight into its owner's value queue with 128-bit peer stores (recv_vals: HOST array of
+ * G device pointers, entry d = owner d's (G_src, capacity, D) fp32 queue; slice [my_rank] is written).  row_grads may be
+ * NULL: the IndexedSlices values then never touch local HBM.  Follow with a stream sync and a cross-rank barrier before
+ * any owner reads its queues. */
+int ctr_embed_fm2_bwd_push(const float* tile, const float* d_tile, const float* d_fm2, const int32_t* plan, int64_t B,
+                           int64_t F, int64_t D, int64_t G, int64_t my_rank, float* const* recv_vals, int64_t capacity,
+                           float* row_grads, void* stream);
+/* The exchange alone, for row gradients (B,F,D) produced by any other backward. */
+int ctr_sharded_grad_push(const float* row_grads, const int32_t* plan, int64_t B, int64_t F, int64_t D, int64_t G,
+                          int64_t my_rank, float* const* recv_vals, int64_t capacity, void* stream);
 /* Owner side / generic IndexedSlices consumer: dst[rows[i], :] += vals[i, :] for i < min(*count, max_n) (count may be
  * NULL = max_n); rows outside [0, V) are ignored.  fp32 vector red.global.add. */
 int ctr_rows_scatter_add(float* dst, int64_t V, int64_t D, const int64_t* rows, const float* vals, const int64_t* count,

@@ -53,11 +53,18 @@ class EmbeddingTables:
         self.grad_slices.clear()
 
 
+def _ids64_for(ids: torch.Tensor):
+    """IndexedSlices carry int64 ids (TF's sparse ids); int32 inputs are widened by the forward kernel itself."""
+    return torch.empty(ids.shape, dtype=torch.int64, device=ids.device) if ids.dtype == torch.int32 else None
+
+
 class _LookupFM2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, tables: EmbeddingTables, ids: torch.Tensor, want_fm2: bool):
-        tile, fm2 = ops.embed_fm2_fwd(tables.weight, tables.field_row_offset, ids, want_tile=True, want_fm2=want_fm2)
-        ctx.tables, ctx.ids, ctx.want_fm2 = tables, ids, want_fm2
+        ids64 = _ids64_for(ids)
+        tile, fm2 = ops.embed_fm2_fwd(tables.weight, tables.field_row_offset, ids, want_tile=True, want_fm2=want_fm2,
+                                      ids64_out=ids64)
+        ctx.tables, ctx.ids, ctx.want_fm2 = tables, (ids if ids64 is None else ids64), want_fm2
         ctx.save_for_backward(tile)
         if want_fm2:
             return tile, fm2
@@ -83,6 +90,32 @@ def lookup_fm2(tables: EmbeddingTables, ids: torch.Tensor):
 def lookup(tables: EmbeddingTables, ids: torch.Tensor):
     """(B,F) ids -> tile (B,F,D)."""
     return _LookupFM2.apply(tables._anchor, tables, ids, False)
+
+
+class _LookupFM2Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wlin, tables: EmbeddingTables, ids: torch.Tensor):
+        ids64 = _ids64_for(ids)
+        wl = wlin.contiguous()
+        tile, fm2, lin = ops.embed_fm2_lin_fwd(tables.weight, tables.field_row_offset, ids, wl, ids64_out=ids64)
+        ctx.tables, ctx.ids = tables, (ids if ids64 is None else ids64)
+        ctx.save_for_backward(tile, wl)
+        return fm2, lin
+
+    @staticmethod
+    def backward(ctx, d_fm2, d_lin):
+        tile, wl = ctx.saved_tensors
+        values, d_wlin = ops.embed_fm2_lin_bwd(tile, wl, None if d_fm2 is None else d_fm2.contiguous(),
+                                               None if d_lin is None else d_lin.contiguous())
+        ctx.tables.grad_slices.append(IndexedSlices(values, ctx.ids, ctx.tables.field_row_offset))
+        return d_wlin.reshape(wl.shape), None, None
+
+
+def lookup_fm2_linear(tables: EmbeddingTables, ids: torch.Tensor, wlin: torch.Tensor):
+    """(B,F) ids -> (fm2 logit (B,1), lin (B,1) = input_layer output (B, F*D) @ wlin): the lookup, DeepFM's second-order
+    term and a dense(1, use_bias=False) consumer of the concatenated embeddings in one kernel each way -- the tile is
+    written once (for the backward) and never re-streamed by the consumer.  wlin: (F*D, 1) or (F*D,), requires_grad."""
+    return _LookupFM2Linear.apply(wlin, tables, ids)
 
 
 class _CrossStack(torch.autograd.Function):

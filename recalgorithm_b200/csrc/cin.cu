@@ -546,8 +546,7 @@ extern "C" int ctr_cin_bwd(const float* x0, const float* xk, const float* filter
   cudaStream_t st = as_stream(stream);
   CTR_CUDA(cudaMemsetAsync(dfilter, 0, sizeof(float) * hk * m * H, st));
   if (B == 0) return CTR_OK;
-  static const bool force_simple = getenv("CTR_CIN_BWD_CUDA_CORE") != nullptr;     // A/B switch for profiling
-  if (!force_simple && ctr_cin_bwd_tc_supported(m, hk, D, H)) {
+  if (ctr_cin_bwd_tc_supported(m, hk, D, H)) {
     const int64_t need = ctr_cin_bwd_workspace_bytes(B, m, hk, D, H);
     CTR_REQUIRE(workspace != nullptr && workspace_bytes >= need,
                 "ctr_cin_bwd: workspace of %lld bytes required (ctr_cin_bwd_workspace_bytes), got %lld", (long long)need,

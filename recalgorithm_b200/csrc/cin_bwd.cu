@@ -541,8 +541,7 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
     const long long rows = (long long)B * D;
     const int tiles = (int)((rows + BM - 1) / BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    static const bool no_mc = getenv("CTR_CIN_NO_MULTICAST") != nullptr;
-    const bool mc = !no_mc && tiles >= 2;
+    const bool mc = tiles >= 2;
     int grid_mc = grid & ~1;                               // whole 2-CTA clusters
     if (grid_mc < 2) grid_mc = 2;
 #define DX_LAUNCH(NKB_)                                                                                              \

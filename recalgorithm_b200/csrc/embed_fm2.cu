@@ -14,8 +14,6 @@
 //   128-bit loads in flight per lane (enough outstanding bytes per SM to cover HBM latency).
 //   S = sum_f e and Q = sum_f e^2 accumulate in registers; the FM2 logit is a shuffle reduction.
 //   The (B,F,D) tile is written with evict-first stores so it does not displace hot table rows in L2.
-#include <stdlib.h>
-
 #include "ctr_common.cuh"
 
 namespace ctr {
@@ -30,15 +28,32 @@ struct PeerTables {
   int G, logG;
 };
 
-// NCH > 0: F <= 32*NCH; the lane's row-offset window is cached and the ids of the NEXT sample are requested before the
-// current sample's rows (one DRAM latency taken off the per-sample critical path).  NCH == 0: any F, ids loaded per chunk.
 // BI: `fm2` points at a (B, D) buffer that receives 0.5*(S^2 - Q) per embedding dim (NFM bi-interaction pooling,
 // NFM/nfm.py:155-168) instead of its sum over D.
-template <int LPR, bool SH, int MINB, int NCH, bool BI = false>
+// IdT: int64 ids (TF's sparse ids) or int32 ids (half the PCIe / HBM bytes of the id matrix; `ids64_out`, when given,
+// receives the widened copy that IndexedSlices consumers downstream expect).
+__device__ __forceinline__ long long load_id(const long long* p) { return ldg_stream_i64(p); }
+__device__ __forceinline__ long long load_id(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return (long long)r;
+}
+// rows of a peer shard: plain (L1-allocating) loads -- measured 650 GB/s over NVLink against 622 GB/s for
+// .nc.L1::no_allocate (tools/peerbench.cu); peer lines bypass the local L2 either way
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// LIN: a dense(1) consumer of the flattened tile is fused in: lin[b] = sum_{f,d} e[b,f,d] * wlin[f,d] (the kernel of a
+// tf.layers.dense(units=1, use_bias=False) over the (B, F*D) input_layer output), so the consumer never re-streams the tile.
+template <int LPR, bool SH, int MINB, bool BI = false, typename IdT = long long, bool LIN = false>
 __global__ void __launch_bounds__(256, MINB)
 embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, const long long* __restrict__ row_off,
-                     const long long* __restrict__ ids, int B, int F, float4* __restrict__ tile,
-                     float* __restrict__ fm2) {
+                     const IdT* __restrict__ ids, int B, int F, float4* __restrict__ tile,
+                     float* __restrict__ fm2, long long* __restrict__ ids64_out,
+                     const float4* __restrict__ wlin, float* __restrict__ lin) {
   constexpr int RPW = 32 / LPR;             // rows fetched per warp-level load
   constexpr int UB = LPR < 8 ? LPR : 8;     // loads batched before first use
   const unsigned full = 0xffffffffu;
@@ -48,43 +63,17 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, c
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
 
-  constexpr int NC = NCH > 0 ? NCH : 1;
-  long long lo_c[NC], n_c[NC], id_next[NC];
-  if (NCH > 0) {
-#pragma unroll
-    for (int ch = 0; ch < NC; ++ch) {
-      const int f = ch * 32 + lane;
-      lo_c[ch] = 0; n_c[ch] = 0; id_next[ch] = -1;
-      if (f < F) {
-        lo_c[ch] = __ldg(row_off + f);
-        n_c[ch] = __ldg(row_off + f + 1) - lo_c[ch];
-        if (warp0 < B) id_next[ch] = ldg_stream_i64(ids + (size_t)warp0 * F + f);
-      }
-    }
-  }
   for (int b = warp0; b < B; b += nwarps) {
     float4 S = f4_zero(), Q = f4_zero();
-    long long row_c[NC];
-    if (NCH > 0) {
-#pragma unroll
-      for (int ch = 0; ch < NC; ++ch) {
-        const long long id = id_next[ch];
-        row_c[ch] = (id >= 0 && id < n_c[ch]) ? lo_c[ch] + id : -1;      // OOV(-1)/out-of-range -> zero vector
-        const int f = ch * 32 + lane;
-        if (f < F && b + nwarps < B) id_next[ch] = ldg_stream_i64(ids + (size_t)(b + nwarps) * F + f);
-      }
-    }
+    float lin_acc = 0.f;
     for (int f0 = 0; f0 < F; f0 += 32) {
       const int nf = min(32, F - f0);
       long long row = -1;
-      if (NCH > 0) {
-#pragma unroll
-        for (int ch = 0; ch < NC; ++ch)
-          if (f0 == ch * 32) row = row_c[ch];
-      } else if (lane < nf) {
-        const long long id = ldg_stream_i64(ids + (size_t)b * F + f0 + lane);
+      if (lane < nf) {
+        const long long id = load_id(ids + (size_t)b * F + f0 + lane);
         const long long lo = __ldg(row_off + f0 + lane), hi = __ldg(row_off + f0 + lane + 1);
         row = (id >= 0 && id < hi - lo) ? lo + id : -1;      // OOV(-1)/out-of-range -> zero vector
+        if (sizeof(IdT) == 4 && ids64_out != nullptr) ids64_out[(size_t)b * F + f0 + lane] = id;
       }
 #pragma unroll
       for (int it0 = 0; it0 < LPR; it0 += UB) {              // LPR iterations cover 32 fields
@@ -98,9 +87,8 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, c
           in[u] = fs < nf;
           v[u] = f4_zero();
           if (in[u] && r >= 0) {
-            const float4* src = SH ? peers.base[r & (peers.G - 1)] + (size_t)(r >> peers.logG) * LPR + c
-                                   : table + (size_t)r * LPR + c;
-            v[u] = ldg_stream_f4(src);
+            if (SH) v[u] = ld_peer_f4(peers.base[r & (peers.G - 1)] + (size_t)(r >> peers.logG) * LPR + c);
+            else v[u] = ldg_stream_f4(table + (size_t)r * LPR + c);
           }
         }
 #pragma unroll
@@ -113,8 +101,16 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, c
             const int fs = (it0 + u) * RPW + sub;
             stg_stream_f4(tile + ((size_t)b * F + f0 + fs) * LPR + c, v[u]);
           }
+          if (LIN && in[u]) {
+            const float4 w = __ldg(wlin + (size_t)(f0 + (it0 + u) * RPW + sub) * LPR + c);
+            lin_acc += v[u].x * w.x + v[u].y * w.y + v[u].z * w.z + v[u].w * w.w;
+          }
         }
       }
+    }
+    if (LIN) {
+      lin_acc = warp_sum(lin_acc);
+      if (lane == 0) lin[b] = lin_acc;
     }
     if (fm2 != nullptr) {
       // complete S and Q over the RPW row-groups (lanes sharing the same chunk c)
@@ -221,6 +217,73 @@ embed_fm2_bwd_kernel(const float4* __restrict__ tile, const float4* __restrict__
       }
     }
   }
+}
+
+// Backward of the LIN form: d_tile is the rank-1 product d_lin[b] * wlin[f,d], so it is never materialised:
+//   row_grads[b,f,:] = d_lin[b]*wlin[f,:] + d_fm2[b]*(S[b,:] - e[b,f,:]) ;  d_wlin[f,:] = sum_b d_lin[b]*e[b,f,:].
+// Warp per sample; the tile row and the warp's share of d_wlin live in registers (HOLD float4 each), wlin in shared memory;
+// per CTA one shared-memory reduction and one vector red.global.add per element.  Reads (tile), writes (row_grads) only.
+template <int LPR, int HOLD>
+__global__ void __launch_bounds__(256, 2)
+embed_fm2_lin_bwd_kernel(const float4* __restrict__ tile, const float4* __restrict__ wlin, const float* __restrict__ d_fm2,
+                         const float* __restrict__ d_lin, int B, int F, float4* __restrict__ row_grads,
+                         float4* __restrict__ d_wlin) {
+  extern __shared__ float4 s_lin[];                 // [n4] wlin, then [n4] d_wlin accumulator
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n4 = F * LPR;
+  float4* s_w = s_lin;
+  float4* s_dw = s_lin + n4;
+  for (int j = threadIdx.x; j < n4; j += blockDim.x) { s_w[j] = __ldg(wlin + j); s_dw[j] = f4_zero(); }
+  __syncthreads();
+  float4 acc[HOLD];
+#pragma unroll
+  for (int k = 0; k < HOLD; ++k) acc[k] = f4_zero();
+  for (int b = warp0; b < B; b += nwarps) {
+    const float4* e_row = tile + (size_t)b * n4;
+    float4* o_row = row_grads + (size_t)b * n4;
+    const float g = d_fm2 ? __ldg(d_fm2 + b) : 0.f;
+    const float gl = d_lin ? __ldg(d_lin + b) : 0.f;
+    float4 e[HOLD];
+#pragma unroll
+    for (int k = 0; k < HOLD; ++k) {
+      const int j = k * 32 + lane;
+      e[k] = f4_zero();
+      if (j < n4) e[k] = ldg_stream_f4(e_row + j);
+    }
+    float4 S = f4_zero();
+#pragma unroll
+    for (int k = 0; k < HOLD; ++k) { S.x += e[k].x; S.y += e[k].y; S.z += e[k].z; S.w += e[k].w; }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      S.x += __shfl_xor_sync(full, S.x, o); S.y += __shfl_xor_sync(full, S.y, o);
+      S.z += __shfl_xor_sync(full, S.z, o); S.w += __shfl_xor_sync(full, S.w, o);
+    }
+#pragma unroll
+    for (int k = 0; k < HOLD; ++k) {
+      const int j = k * 32 + lane;
+      if (j < n4) {
+        const float4 w = s_w[j];
+        float4 r;
+        r.x = gl * w.x + g * (S.x - e[k].x); r.y = gl * w.y + g * (S.y - e[k].y);
+        r.z = gl * w.z + g * (S.z - e[k].z); r.w = gl * w.w + g * (S.w - e[k].w);
+        stg_stream_f4(o_row + j, r);
+        acc[k].x += gl * e[k].x; acc[k].y += gl * e[k].y; acc[k].z += gl * e[k].z; acc[k].w += gl * e[k].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < HOLD; ++k) {
+    const int j = k * 32 + lane;
+    if (j < n4) {
+      atomicAdd(&s_dw[j].x, acc[k].x); atomicAdd(&s_dw[j].y, acc[k].y);
+      atomicAdd(&s_dw[j].z, acc[k].z); atomicAdd(&s_dw[j].w, acc[k].w);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n4; j += blockDim.x) atomicAdd(d_wlin + j, s_dw[j]);
 }
 
 // grad_table[row(b,f), :] += row_grads[b,f,:]  (valid ids only) -- vector red.global.add.
@@ -334,31 +397,22 @@ static int resident_grid(K kernel, int block, size_t smem, long long blocks_need
   return (int)g;
 }
 
-template <int LPR>
-static int launch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const int64_t* ids, int64_t B,
-                      int64_t F, float* tile, float* fm2, cudaStream_t st) {
+template <int LPR, typename IdT>
+static int launch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const IdT* ids, int64_t B,
+                      int64_t F, float* tile, float* fm2, int64_t* ids64_out, cudaStream_t st) {
   PeerTables none = {};
-  // 4 CTAs/SM (64 registers) measured 0.80 of HBM peak vs 0.71-0.80 uncapped; CTR_EMBED_OCC1 keeps the A/B switch
-  static const bool occ4 = getenv("CTR_EMBED_OCC1") == nullptr;
-  // next-sample id prefetch measured neutral-to-negative at 4 CTAs/SM (0.795 vs 0.805: it costs spills): opt-in only
-  static const bool noprefetch = getenv("CTR_EMBED_PREFETCH") == nullptr;
+  // 4 CTAs/SM (64 registers) measured 0.80 of HBM peak vs 0.71-0.80 uncapped; a next-sample id prefetch variant measured
+  // neutral-to-negative (it costs spills) and was removed.  The sharded (peer-pull) variant keeps the register budget open.
   const PeerTables& pt = peers ? *peers : none;
   const float4* tb = reinterpret_cast<const float4*>(table);
-#define EMB_LAUNCH(SH_, MINB_, NCH_)                                                                                 \
+#define EMB_LAUNCH(SH_, MINB_)                                                                                       \
   {                                                                                                                  \
-    auto k = embed_fm2_fwd_kernel<LPR, SH_, MINB_, NCH_>;                                                            \
+    auto k = embed_fm2_fwd_kernel<LPR, SH_, MINB_, false, IdT>;                                                      \
     const int grid = resident_grid(k, 256, 0, (B + 7) / 8);                                                          \
-    k<<<grid, 256, 0, st>>>(tb, pt, reinterpret_cast<const long long*>(off), reinterpret_cast<const long long*>(ids), \
-                            (int)B, (int)F, reinterpret_cast<float4*>(tile), fm2);                                   \
+    k<<<grid, 256, 0, st>>>(tb, pt, reinterpret_cast<const long long*>(off), ids, (int)B, (int)F,                    \
+                            reinterpret_cast<float4*>(tile), fm2, reinterpret_cast<long long*>(ids64_out), nullptr, nullptr); \
   }
-  const int nch = noprefetch ? 0 : (F <= 32 ? 1 : F <= 64 ? 2 : 0);
-  if (peers != nullptr) {
-    if (nch == 1) EMB_LAUNCH(true, 1, 1) else if (nch == 2) EMB_LAUNCH(true, 1, 2) else EMB_LAUNCH(true, 1, 0)
-  } else if (occ4) {
-    if (nch == 1) EMB_LAUNCH(false, 4, 1) else if (nch == 2) EMB_LAUNCH(false, 4, 2) else EMB_LAUNCH(false, 4, 0)
-  } else {
-    if (nch == 1) EMB_LAUNCH(false, 1, 1) else if (nch == 2) EMB_LAUNCH(false, 1, 2) else EMB_LAUNCH(false, 1, 0)
-  }
+  if (peers != nullptr) EMB_LAUNCH(true, 1) else EMB_LAUNCH(false, 4)
 #undef EMB_LAUNCH
   CTR_CHECK_LAUNCH("ctr_embed_fm2_fwd");
   return CTR_OK;
@@ -388,16 +442,13 @@ static int dispatch_bwd(const float* tile, const float* d_tile, const float* d_f
 template <int LPR>
 static int launch_fwd_bi(const float* table, const int64_t* off, const int64_t* ids, int64_t B, int64_t F, float* tile,
                          float* bi, cudaStream_t st) {
-  auto k = embed_fm2_fwd_kernel<LPR, false, 4, 0, true>;
+  auto k = embed_fm2_fwd_kernel<LPR, false, 4, true>;
   const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
   k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), PeerTables{}, reinterpret_cast<const long long*>(off),
-                          reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), bi);
+                          reinterpret_cast<const long long*>(ids), (int)B, (int)F, reinterpret_cast<float4*>(tile), bi, nullptr, nullptr, nullptr);
   CTR_CHECK_LAUNCH("ctr_embed_bi_fwd");
   return CTR_OK;
 }
-
-static int dispatch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const int64_t* ids, int64_t B,
-                        int64_t F, int64_t D, float* tile, float* fm2, cudaStream_t st);
 
 static int check_bfd(const char* fn, int64_t B, int64_t F, int64_t D) {
   CTR_REQUIRE(B >= 0 && F >= 1 && D >= 1, "%s: bad sizes B=%lld F=%lld D=%lld", fn, (long long)B, (long long)F,
@@ -409,16 +460,29 @@ static int check_bfd(const char* fn, int64_t B, int64_t F, int64_t D) {
   return CTR_OK;
 }
 
-static int dispatch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const int64_t* ids, int64_t B,
-                        int64_t F, int64_t D, float* tile, float* fm2, cudaStream_t st) {
+template <typename IdT>
+static int dispatch_fwd(const float* table, const PeerTables* peers, const int64_t* off, const IdT* ids, int64_t B,
+                        int64_t F, int64_t D, float* tile, float* fm2, int64_t* ids64_out, cudaStream_t st) {
   switch (D / 4) {
-    case 1: return launch_fwd<1>(table, peers, off, ids, B, F, tile, fm2, st);
-    case 2: return launch_fwd<2>(table, peers, off, ids, B, F, tile, fm2, st);
-    case 4: return launch_fwd<4>(table, peers, off, ids, B, F, tile, fm2, st);
-    case 8: return launch_fwd<8>(table, peers, off, ids, B, F, tile, fm2, st);
-    case 16: return launch_fwd<16>(table, peers, off, ids, B, F, tile, fm2, st);
-    default: return launch_fwd<32>(table, peers, off, ids, B, F, tile, fm2, st);
+    case 1: return launch_fwd<1>(table, peers, off, ids, B, F, tile, fm2, ids64_out, st);
+    case 2: return launch_fwd<2>(table, peers, off, ids, B, F, tile, fm2, ids64_out, st);
+    case 4: return launch_fwd<4>(table, peers, off, ids, B, F, tile, fm2, ids64_out, st);
+    case 8: return launch_fwd<8>(table, peers, off, ids, B, F, tile, fm2, ids64_out, st);
+    case 16: return launch_fwd<16>(table, peers, off, ids, B, F, tile, fm2, ids64_out, st);
+    default: return launch_fwd<32>(table, peers, off, ids, B, F, tile, fm2, ids64_out, st);
   }
+}
+
+static int fill_peers(const char* fn, PeerTables& peers, const float* const* shard_ptrs, int64_t G) {
+  CTR_REQUIRE(G >= 1 && G <= 8 && (G & (G - 1)) == 0, "%s: G=%lld must be a power of two <= 8", fn, (long long)G);
+  peers = PeerTables{};
+  peers.G = (int)G;
+  while ((1 << peers.logG) < G) ++peers.logG;
+  for (int r = 0; r < G; ++r) {
+    CTR_REQUIRE(shard_ptrs[r] != nullptr && aligned16(shard_ptrs[r]), "%s: shard %d null/unaligned", fn, r);
+    peers.base[r] = reinterpret_cast<const float4*>(shard_ptrs[r]);
+  }
+  return CTR_OK;
 }
 
 }  // namespace ctr
@@ -434,7 +498,19 @@ extern "C" int ctr_embed_fm2_fwd(const float* table, const int64_t* field_row_of
   CTR_REQUIRE(aligned16(table) && aligned16(tile), "ctr_embed_fm2_fwd: table and tile must be 16-byte aligned");
   if (B == 0) return CTR_OK;
   cudaStream_t st = as_stream(stream);
-  return dispatch_fwd(table, nullptr, field_row_offset, ids, B, F, D, tile, fm2, st);
+  return dispatch_fwd(table, nullptr, field_row_offset, reinterpret_cast<const long long*>(ids), B, F, D, tile, fm2, nullptr, st);
+}
+
+extern "C" int ctr_embed_fm2_fwd_ids32(const float* table, const int64_t* field_row_offset, const int32_t* ids, int64_t B,
+                                       int64_t F, int64_t D, float* tile, float* fm2, int64_t* ids64_out, void* stream) {
+  int rc = check_bfd("ctr_embed_fm2_fwd_ids32", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(table && field_row_offset && ids, "ctr_embed_fm2_fwd_ids32: null table/field_row_offset/ids");
+  CTR_REQUIRE(tile || fm2, "ctr_embed_fm2_fwd_ids32: both outputs are NULL");
+  CTR_REQUIRE(aligned16(table) && aligned16(tile), "ctr_embed_fm2_fwd_ids32: table and tile must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  return dispatch_fwd(table, nullptr, field_row_offset, reinterpret_cast<const int*>(ids), B, F, D, tile, fm2, ids64_out,
+                      as_stream(stream));
 }
 
 extern "C" int ctr_embed_fm2_fwd_sharded(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
@@ -443,19 +519,30 @@ extern "C" int ctr_embed_fm2_fwd_sharded(const float* const* shard_ptrs, int64_t
   int rc = check_bfd("ctr_embed_fm2_fwd_sharded", B, F, D);
   if (rc) return rc;
   CTR_REQUIRE(shard_ptrs && field_row_offset && ids, "ctr_embed_fm2_fwd_sharded: null shard_ptrs/field_row_offset/ids");
-  CTR_REQUIRE(G >= 1 && G <= 8 && (G & (G - 1)) == 0, "ctr_embed_fm2_fwd_sharded: G=%lld must be a power of two <= 8",
-              (long long)G);
   CTR_REQUIRE(tile || fm2, "ctr_embed_fm2_fwd_sharded: both outputs are NULL");
-  PeerTables peers = {};
-  peers.G = (int)G;
-  while ((1 << peers.logG) < G) ++peers.logG;
-  for (int r = 0; r < G; ++r) {
-    CTR_REQUIRE(shard_ptrs[r] != nullptr && aligned16(shard_ptrs[r]), "ctr_embed_fm2_fwd_sharded: shard %d null/unaligned", r);
-    peers.base[r] = reinterpret_cast<const float4*>(shard_ptrs[r]);
-  }
+  PeerTables peers;
+  rc = fill_peers("ctr_embed_fm2_fwd_sharded", peers, shard_ptrs, G);
+  if (rc) return rc;
   CTR_REQUIRE(aligned16(tile), "ctr_embed_fm2_fwd_sharded: tile must be 16-byte aligned");
   if (B == 0) return CTR_OK;
-  return dispatch_fwd(nullptr, &peers, field_row_offset, ids, B, F, D, tile, fm2, as_stream(stream));
+  return dispatch_fwd(nullptr, &peers, field_row_offset, reinterpret_cast<const long long*>(ids), B, F, D, tile, fm2, nullptr,
+                      as_stream(stream));
+}
+
+extern "C" int ctr_embed_fm2_fwd_sharded_ids32(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
+                                               const int32_t* ids, int64_t B, int64_t F, int64_t D, float* tile, float* fm2,
+                                               int64_t* ids64_out, void* stream) {
+  int rc = check_bfd("ctr_embed_fm2_fwd_sharded_ids32", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(shard_ptrs && field_row_offset && ids, "ctr_embed_fm2_fwd_sharded_ids32: null shard_ptrs/field_row_offset/ids");
+  CTR_REQUIRE(tile || fm2, "ctr_embed_fm2_fwd_sharded_ids32: both outputs are NULL");
+  PeerTables peers;
+  rc = fill_peers("ctr_embed_fm2_fwd_sharded_ids32", peers, shard_ptrs, G);
+  if (rc) return rc;
+  CTR_REQUIRE(aligned16(tile), "ctr_embed_fm2_fwd_sharded_ids32: tile must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  return dispatch_fwd(nullptr, &peers, field_row_offset, reinterpret_cast<const int*>(ids), B, F, D, tile, fm2, ids64_out,
+                      as_stream(stream));
 }
 
 extern "C" int ctr_embed_fm2_bwd(const float* tile, const float* d_tile, const float* d_fm2, int64_t B, int64_t F,
@@ -591,5 +678,89 @@ extern "C" int ctr_embed_bi_bwd(const float* tile, const float* d_tile, const fl
     case 8: return dispatch_bwd<8, true>(tile, d_tile, d_bi, B, F, row_grads, st);
     case 16: return dispatch_bwd<16, true>(tile, d_tile, d_bi, B, F, row_grads, st);
     default: return dispatch_bwd<32, true>(tile, d_tile, d_bi, B, F, row_grads, st);
+  }
+}
+
+// ---- lookup + FM2 + fused dense(1) head over the flattened tile (e2e form: the consumer does not re-stream the tile) ------
+template <int LPR, typename IdT>
+static int launch_fwd_lin(const float* table, const int64_t* off, const IdT* ids, int64_t B, int64_t F, float* tile, float* fm2,
+                          int64_t* ids64_out, const float* wlin, float* lin, cudaStream_t st) {
+  auto k = embed_fm2_fwd_kernel<LPR, false, 4, false, IdT, true>;
+  const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
+  k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), PeerTables{}, reinterpret_cast<const long long*>(off), ids, (int)B,
+                          (int)F, reinterpret_cast<float4*>(tile), fm2, reinterpret_cast<long long*>(ids64_out),
+                          reinterpret_cast<const float4*>(wlin), lin);
+  CTR_CHECK_LAUNCH("ctr_embed_fm2_lin_fwd");
+  return CTR_OK;
+}
+
+template <typename IdT>
+static int dispatch_fwd_lin(const float* table, const int64_t* off, const IdT* ids, int64_t B, int64_t F, int64_t D, float* tile,
+                            float* fm2, int64_t* ids64_out, const float* wlin, float* lin, cudaStream_t st) {
+  switch (D / 4) {
+    case 1: return launch_fwd_lin<1>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 2: return launch_fwd_lin<2>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 4: return launch_fwd_lin<4>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 8: return launch_fwd_lin<8>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 16: return launch_fwd_lin<16>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    default: return launch_fwd_lin<32>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+  }
+}
+
+extern "C" int ctr_embed_fm2_lin_fwd(const float* table, const int64_t* field_row_offset, const void* ids, int ids_are_int32,
+                                     int64_t B, int64_t F, int64_t D, const float* wlin, float* tile, float* fm2, float* lin,
+                                     int64_t* ids64_out, void* stream) {
+  int rc = check_bfd("ctr_embed_fm2_lin_fwd", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(table && field_row_offset && ids && wlin && lin, "ctr_embed_fm2_lin_fwd: null table/field_row_offset/ids/wlin/lin");
+  CTR_REQUIRE(aligned16(table) && aligned16(tile) && aligned16(wlin), "ctr_embed_fm2_lin_fwd: table, tile and wlin must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  if (ids_are_int32)
+    return dispatch_fwd_lin(table, field_row_offset, reinterpret_cast<const int*>(ids), B, F, D, tile, fm2, ids64_out, wlin, lin, st);
+  return dispatch_fwd_lin(table, field_row_offset, reinterpret_cast<const long long*>(ids), B, F, D, tile, fm2, nullptr, wlin, lin, st);
+}
+
+template <int LPR, int HOLD>
+static int launch_lin_bwd(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, int64_t B, int64_t F,
+                          float* row_grads, float* d_wlin, cudaStream_t st) {
+  auto k = embed_fm2_lin_bwd_kernel<LPR, HOLD>;
+  const size_t smem = sizeof(float4) * 2 * (size_t)F * LPR;
+  if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = resident_grid(k, 256, smem, (B + 7) / 8);
+  k<<<grid, 256, smem, st>>>(reinterpret_cast<const float4*>(tile), reinterpret_cast<const float4*>(wlin), d_fm2, d_lin, (int)B,
+                             (int)F, reinterpret_cast<float4*>(row_grads), reinterpret_cast<float4*>(d_wlin));
+  CTR_CHECK_LAUNCH("ctr_embed_fm2_lin_bwd");
+  return CTR_OK;
+}
+
+template <int LPR>
+static int dispatch_lin_bwd(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, int64_t B, int64_t F,
+                            float* row_grads, float* d_wlin, cudaStream_t st) {
+  const int64_t per_lane = (F * LPR + 31) / 32;
+  if (per_lane <= 4) return launch_lin_bwd<LPR, 4>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+  if (per_lane <= 8) return launch_lin_bwd<LPR, 8>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+  if (per_lane <= 12) return launch_lin_bwd<LPR, 12>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+  set_error("ctr_embed_fm2_lin_bwd: F*D = %lld exceeds the register-resident limit of 1536", (long long)(F * LPR * 4));
+  return CTR_ERR_UNSUPPORTED;
+}
+
+extern "C" int ctr_embed_fm2_lin_bwd(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, int64_t B,
+                                     int64_t F, int64_t D, float* row_grads, float* d_wlin, void* stream) {
+  int rc = check_bfd("ctr_embed_fm2_lin_bwd", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(tile && wlin && row_grads && d_wlin, "ctr_embed_fm2_lin_bwd: null tile/wlin/row_grads/d_wlin");
+  CTR_REQUIRE(aligned16(tile) && aligned16(wlin) && aligned16(row_grads) && aligned16(d_wlin),
+              "ctr_embed_fm2_lin_bwd: buffers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  CTR_CUDA(cudaMemsetAsync(d_wlin, 0, sizeof(float) * F * D, st));
+  if (B == 0) return CTR_OK;
+  switch (D / 4) {
+    case 1: return dispatch_lin_bwd<1>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+    case 2: return dispatch_lin_bwd<2>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+    case 4: return dispatch_lin_bwd<4>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+    case 8: return dispatch_lin_bwd<8>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+    case 16: return dispatch_lin_bwd<16>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+    default: return dispatch_lin_bwd<32>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
   }
 }

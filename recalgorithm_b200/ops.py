@@ -35,11 +35,18 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+I32 = torch.int32
+
+
 def _chk(t: Optional[torch.Tensor], dtype, name: str, shape=None):
     if t is None:
         return
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's current stream: a tensor of another GPU would be touched from the wrong
+        # device / stream (single-process multi-GPU callers wrap their calls in `with torch.cuda.device(t.device)`)
+        raise RuntimeError(f"{name}: lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -51,13 +58,26 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str, shape=None):
 # ------------------------------------------------------------------ Row L + FM2
 def embed_fm2_fwd(table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor,
                   want_tile: bool = True, want_fm2: bool = True,
-                  tile: Optional[torch.Tensor] = None, fm2: Optional[torch.Tensor] = None
+                  tile: Optional[torch.Tensor] = None, fm2: Optional[torch.Tensor] = None,
+                  ids64_out: Optional[torch.Tensor] = None
                   ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """Fused lookup (+ FM second-order logit).  table (V,D); field_row_offset (F+1,) i64; ids (B,F) i64.
+    """Fused lookup (+ FM second-order logit).  table (V,D); field_row_offset (F+1,) i64; ids (B,F) i64 -- or i32 (half the
+    bytes over PCIe; ``ids64_out`` (B,F) i64 then receives the widened copy for IndexedSlices consumers).
     Returns (tile (B,F,D) | None, fm2 (B,1) | None)."""
     B, F = ids.shape
     D = table.shape[1]
-    _chk(table, F32, "table"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,)); _chk(ids, I64, "ids")
+    _chk(table, F32, "table"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,))
+    if ids.dtype == I32:
+        _chk(ids, I32, "ids"); _chk(ids64_out, I64, "ids64_out", (B, F))
+        if want_tile and tile is None:
+            tile = torch.empty((B, F, D), dtype=F32, device=table.device)
+        if want_fm2 and fm2 is None:
+            fm2 = torch.empty((B, 1), dtype=F32, device=table.device)
+        _chk(tile, F32, "tile", (B, F, D)); _chk(fm2, F32, "fm2", (B, 1))
+        _lib.check(_lib.lib().ctr_embed_fm2_fwd_ids32(_ptr(table), _ptr(field_row_offset), _ptr(ids), B, F, D, _ptr(tile),
+                                                      _ptr(fm2), _ptr(ids64_out), _stream()))
+        return tile, fm2
+    _chk(ids, I64, "ids")
     if want_tile and tile is None:
         tile = torch.empty((B, F, D), dtype=F32, device=table.device)
     if want_fm2 and fm2 is None:
@@ -81,6 +101,46 @@ def embed_fm2_bwd(tile: torch.Tensor, d_tile: Optional[torch.Tensor], d_fm2: Opt
     _chk(row_grads, F32, "row_grads", (B, F, D))
     _lib.check(_lib.lib().ctr_embed_fm2_bwd(_ptr(tile), _ptr(d_tile), _ptr(d_fm2), B, F, D, _ptr(row_grads), _stream()))
     return row_grads
+
+
+def embed_fm2_lin_fwd(table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor, wlin: torch.Tensor,
+                      want_tile: bool = True, ids64_out: Optional[torch.Tensor] = None):
+    """Lookup + FM2 + fused dense(1) head over the flattened tile: returns (tile | None, fm2 (B,1), lin (B,1)) with
+    lin = tile.reshape(B, F*D) @ wlin.  ids int64 or int32 (``ids64_out`` then receives the widened copy)."""
+    B, F = ids.shape
+    D = table.shape[1]
+    _chk(table, F32, "table"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,))
+    i32 = ids.dtype == I32
+    _chk(ids, I32 if i32 else I64, "ids"); _chk(ids64_out, I64, "ids64_out", (B, F))
+    wlin = wlin.reshape(F * D)
+    _chk(wlin, F32, "wlin", (F * D,))
+    tile = torch.empty((B, F, D), dtype=F32, device=table.device) if want_tile else None
+    fm2 = torch.empty((B, 1), dtype=F32, device=table.device)
+    lin = torch.empty((B, 1), dtype=F32, device=table.device)
+    _lib.check(_lib.lib().ctr_embed_fm2_lin_fwd(_ptr(table), _ptr(field_row_offset), _ptr(ids), int(i32), B, F, D, _ptr(wlin),
+                                                _ptr(tile), _ptr(fm2), _ptr(lin), _ptr(ids64_out), _stream()))
+    return tile, fm2, lin
+
+
+def embed_fm2_lin_bwd(tile: torch.Tensor, wlin: torch.Tensor, d_fm2: Optional[torch.Tensor], d_lin: Optional[torch.Tensor],
+                      row_grads: Optional[torch.Tensor] = None):
+    """Backward of embed_fm2_lin_fwd: (row_grads (B,F,D) = IndexedSlices values, d_wlin (F*D,))."""
+    B, F, D = tile.shape
+    _chk(tile, F32, "tile")
+    wlin = wlin.reshape(F * D)
+    _chk(wlin, F32, "wlin", (F * D,))
+    if d_fm2 is not None:
+        d_fm2 = d_fm2.reshape(B)
+    if d_lin is not None:
+        d_lin = d_lin.reshape(B)
+    _chk(d_fm2, F32, "d_fm2", (B,)); _chk(d_lin, F32, "d_lin", (B,))
+    if row_grads is None:
+        row_grads = torch.empty_like(tile)
+    _chk(row_grads, F32, "row_grads", (B, F, D))
+    d_wlin = torch.empty((F * D,), dtype=F32, device=tile.device)
+    _lib.check(_lib.lib().ctr_embed_fm2_lin_bwd(_ptr(tile), _ptr(wlin), _ptr(d_fm2), _ptr(d_lin), B, F, D, _ptr(row_grads),
+                                                _ptr(d_wlin), _stream()))
+    return row_grads, d_wlin
 
 
 def embed_scatter_add(grad_table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor,

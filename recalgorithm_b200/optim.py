@@ -61,8 +61,9 @@ class TableAdam:
 
 class ShardedTableAdam:
     """The same optimizer on a row-sharded table (``sharded.ShardedEmbeddingTables``): every rank updates the rows it owns
-    from the (row, gradient) entries the other ranks pushed into its receive queues (``push_grads`` must have completed,
-    barrier included).  ``step()`` ends with a barrier so that the next forward pulls updated rows."""
+    from the (row, gradient) entries the other ranks pushed into its receive queues.  ``step()`` first completes the
+    exchange (``tables.finish_push()``: stream sync + barrier, and it RAISES if any rank's queue overflowed -- dropped
+    entries would otherwise be silently lost gradients) and ends with a barrier so that the next forward pulls updated rows."""
 
     def __init__(self, tables, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, lazy: bool = False):
         self.tables, self.lr, self.b1, self.b2, self.eps, self.lazy = tables, lr, beta1, beta2, eps, lazy
@@ -74,8 +75,10 @@ class ShardedTableAdam:
         self._slot = torch.full((tables.local_rows,), -1, dtype=torch.int32, device=w.device)
         self._n_unique = torch.zeros((1,), dtype=torch.int64, device=w.device)
 
-    def step(self, barrier: bool = True) -> None:
+    def step(self, barrier: bool = True, finish_push: bool = True) -> None:
         tb = self.tables
+        if finish_push:
+            tb.finish_push()
         w = tb.weight
         V, D = w.shape
         self.t += 1

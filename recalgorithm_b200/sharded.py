@@ -10,7 +10,6 @@ Sharding rule: global row ``gr = field_row_offset[f] + id`` lives on rank ``gr %
 from __future__ import annotations
 
 import ctypes
-import os
 from typing import List, Optional
 
 import torch
@@ -104,7 +103,13 @@ class SymmBuffer:
 
 
 class ShardedEmbeddingTables:
-    """F per-field tables, concatenated and row-sharded over the ranks of ``group`` (one process per GPU)."""
+    """F per-field tables, concatenated and row-sharded over the ranks of ``group`` (one process per GPU).
+
+    One training step on every rank:  ``plan(ids)`` (queue slots, any time before the backward) ->
+    ``lookup_fm2(ids)`` (rows pulled over NVLink) -> ... -> ``bwd_push(tile, d_tile, d_fm2, plan)`` (gradient rows
+    stored straight into their owners' queues) -> ``finish_push()`` (stream sync + barrier + overflow check) -> the owner
+    consumes ``recv_rows / recv_vals / recv_counts`` (``optim.ShardedTableAdam``).  ``lookup_fm2_autograd`` wraps the
+    first three for an autograd graph."""
 
     def __init__(self, rows_per_field, dim: int, batch_per_rank: int, group=None, device=None, init: Optional[str] = "normal",
                  seed: int = 1234, slack: float = 1.25):
@@ -124,14 +129,11 @@ class ShardedEmbeddingTables:
         self.field_row_offset = off.to(self.device)
         self.local_rows = shard_rows(self.num_rows, self.G)
         self._bufs = {}
-        self._symm_w = None
-        if os.environ.get("CTR_PEER_BACKEND", "symm") == "symm":
-            grp = group if group is not None else dist.group.WORLD
-            self._symm_w = SymmBuffer((self.local_rows, self.dim), torch.float32, self.device, grp)
-            self.weight = self._symm_w.tensor
-        else:
-            self._bufs["w"] = PeerBuffer((self.local_rows, self.dim), torch.float32, self.device)
-            self.weight = self._bufs["w"].tensor
+        grp = group if group is not None else dist.group.WORLD
+        # the shard lives in CUDA VMM symmetric memory (2 MB pages): a legacy-IPC mapping of a 32 GB shard collapsed to
+        # 7 GB/s under random peer reads (peer-TLB reach); the small receive queues keep plain IPC buffers
+        self._symm_w = SymmBuffer((self.local_rows, self.dim), torch.float32, self.device, grp)
+        self.weight = self._symm_w.tensor
         if init == "normal":
             g = torch.Generator(device=self.device).manual_seed(seed + self.rank)
             self.weight.normal_(0, self.dim ** -0.5, generator=g)
@@ -141,13 +143,14 @@ class ShardedEmbeddingTables:
         self._bufs["c"] = PeerBuffer((self.G,), torch.int64, self.device)
         self.recv_vals, self.recv_rows, self.recv_counts = (self._bufs[k].tensor for k in ("v", "r", "c"))
         self.recv_counts.zero_()
-        self.counters = torch.zeros((self.G,), dtype=torch.int64, device=self.device)
+        self.counters = torch.zeros((9,), dtype=torch.int64, device=self.device)      # entries per owner + a ticket
         self.overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._overflow_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
         self._rendezvous()
 
     def _rendezvous(self):
-        """Exchange the CUDA-IPC handles of the shard and the receive buffers and map every peer's buffers into this
-        device (the import enables NVLink peer access); the mappings live as long as the object."""
+        """Exchange the CUDA-IPC handles of the receive buffers and map every peer's buffers into this device (the import
+        enables NVLink peer access); the mappings live as long as the object."""
         mine = {k: buf.handle for k, buf in self._bufs.items()}
         gathered = [None] * self.G
         self.dist.all_gather_object(gathered, mine, group=self.group)
@@ -157,47 +160,83 @@ class ShardedEmbeddingTables:
                 self._peer.append({k: buf.tensor for k, buf in self._bufs.items()})
             else:
                 self._peer.append({k: self._bufs[k].open_peer(gathered[r][k]) for k in self._bufs})
-        if self._symm_w is not None:
-            self._w_ptrs = _ptr_array(self._symm_w.peer_ptrs)
-        else:
-            self._w_ptrs = _ptr_array([p["w"].data_ptr() for p in self._peer])
+        self._w_ptrs = _ptr_array(self._symm_w.peer_ptrs)
         self._v_ptrs = _ptr_array([p["v"].data_ptr() for p in self._peer])
         self._r_ptrs = _ptr_array([p["r"].data_ptr() for p in self._peer])
-        self._c_ptrs_dev = torch.tensor([p["c"].data_ptr() for p in self._peer], dtype=torch.int64, device=self.device)
+        self._c_ptrs = _ptr_array([p["c"].data_ptr() for p in self._peer])
         torch.cuda.synchronize()
         self.dist.barrier(group=self.group)
 
     # ---- forward: pull
-    def lookup_fm2(self, ids: torch.Tensor, want_tile=True, want_fm2=True, tile=None, fm2=None):
+    def lookup_fm2(self, ids: torch.Tensor, want_tile=True, want_fm2=True, tile=None, fm2=None, ids64_out=None):
+        """ids (B,F) int64, or int32 (then ``ids64_out`` (B,F) int64, if given, receives the widened copy)."""
         B, F = ids.shape
         D = self.dim
         if want_tile and tile is None:
             tile = torch.empty((B, F, D), dtype=torch.float32, device=self.device)
         if want_fm2 and fm2 is None:
             fm2 = torch.empty((B, 1), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().ctr_embed_fm2_fwd_sharded(self._w_ptrs, self.G, self.field_row_offset.data_ptr(), ids.data_ptr(),
-                                                        B, F, D, ops._ptr(tile), ops._ptr(fm2), ops._stream()))
+        L = _lib.lib()
+        if ids.dtype == torch.int32:
+            ops._chk(ids, torch.int32, "ids"); ops._chk(ids64_out, torch.int64, "ids64_out", (B, F))
+            _lib.check(L.ctr_embed_fm2_fwd_sharded_ids32(self._w_ptrs, self.G, self.field_row_offset.data_ptr(), ops._ptr(ids),
+                                                         B, F, D, ops._ptr(tile), ops._ptr(fm2), ops._ptr(ids64_out), ops._stream()))
+        else:
+            ops._chk(ids, torch.int64, "ids")
+            _lib.check(L.ctr_embed_fm2_fwd_sharded(self._w_ptrs, self.G, self.field_row_offset.data_ptr(), ops._ptr(ids), B, F, D,
+                                                   ops._ptr(tile), ops._ptr(fm2), ops._stream()))
         return tile, fm2
 
-    # ---- backward: push
-    def push_grads(self, ids: torch.Tensor, row_grads: torch.Tensor, barrier: bool = True):
-        """Deliver (local_row, grad) of every valid (b,f) to its owner.  After the call (with barrier=True) this rank's
-        ``recv_rows/recv_vals/recv_counts`` hold what all ranks sent to it."""
+    # ---- backward: plan + push
+    def plan(self, ids: torch.Tensor, plan: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Queue slot of every (b,f) at its owner (int32 (B,F); -1 = invalid id / dropped) + the queues' row indices and
+        counts.  The owners' queues are overwritten: the previous step's entries must have been consumed."""
+        B, F = ids.shape
+        ops._chk(ids, torch.int64, "ids")
+        if plan is None:
+            plan = torch.empty((B, F), dtype=torch.int32, device=self.device)
+        ops._chk(plan, torch.int32, "plan", (B, F))
+        _lib.check(_lib.lib().ctr_sharded_plan(self.field_row_offset.data_ptr(), ops._ptr(ids), B, F, self.G, self.rank,
+                                               self._r_ptrs, self._c_ptrs, self.capacity, self.counters.data_ptr(),
+                                               self.overflow.data_ptr(), ops._ptr(plan), ops._stream()))
+        self._overflow_host.copy_(self.overflow, non_blocking=True)      # checked in finish_push(), after the stream sync
+        return plan
+
+    def bwd_push(self, tile, d_tile, d_fm2, plan, row_grads=None):
+        """Lookup backward fused with the exchange; ``row_grads`` (optional) also keeps the values locally."""
+        B, F, D = tile.shape
+        ops._chk(tile, torch.float32, "tile"); ops._chk(d_tile, torch.float32, "d_tile", (B, F, D))
+        if d_fm2 is not None:
+            d_fm2 = d_fm2.reshape(B)
+        ops._chk(d_fm2, torch.float32, "d_fm2", (B,)); ops._chk(plan, torch.int32, "plan", (B, F))
+        ops._chk(row_grads, torch.float32, "row_grads", (B, F, D))
+        _lib.check(_lib.lib().ctr_embed_fm2_bwd_push(ops._ptr(tile), ops._ptr(d_tile), ops._ptr(d_fm2), ops._ptr(plan), B, F, D,
+                                                     self.G, self.rank, self._v_ptrs, self.capacity, ops._ptr(row_grads),
+                                                     ops._stream()))
+
+    def finish_push(self):
+        """Stream sync + cross-rank barrier: afterwards this rank's ``recv_rows/recv_vals/recv_counts`` hold what all
+        ranks sent to it.  Raises if a queue overflowed (entries were dropped): raise ``slack``."""
+        torch.cuda.current_stream().synchronize()
+        over = torch.tensor([int(self._overflow_host[0])], dtype=torch.int32, device=self.device)
+        self.dist.all_reduce(over, op=self.dist.ReduceOp.MAX, group=self.group)     # doubles as the barrier
+        if int(over.item()):
+            raise RuntimeError(f"gradient receive queue overflow (capacity {self.capacity} entries per source and owner): "
+                               "entries were dropped; construct ShardedEmbeddingTables with a larger `slack`")
+
+    def push_grads(self, ids: torch.Tensor, row_grads: torch.Tensor, barrier: bool = True, plan: Optional[torch.Tensor] = None):
+        """Deliver (local_row, grad) of every valid (b,f) to its owner, for row gradients that already exist."""
         B, F, D = row_grads.shape
-        L = _lib.lib()
-        _lib.check(L.ctr_sharded_grad_push(row_grads.data_ptr(), self.field_row_offset.data_ptr(), ids.data_ptr(), B, F, D,
-                                           self.G, self.rank, self._v_ptrs, self._r_ptrs, self.capacity,
-                                           self.counters.data_ptr(), self.overflow.data_ptr(), ops._stream()))
-        _lib.check(L.ctr_sharded_publish_counts(self.counters.data_ptr(), self._c_ptrs_dev.data_ptr(), self.G, self.rank,
-                                                ops._stream()))
+        ops._chk(row_grads, torch.float32, "row_grads")
+        if plan is None:
+            plan = self.plan(ids)
+        _lib.check(_lib.lib().ctr_sharded_grad_push(ops._ptr(row_grads), ops._ptr(plan), B, F, D, self.G, self.rank, self._v_ptrs,
+                                                    self.capacity, ops._stream()))
         if barrier:
-            torch.cuda.current_stream().synchronize()
-            self.dist.barrier(group=self.group)
+            self.finish_push()
 
     def received_to_dense(self) -> torch.Tensor:
         """Densify what this rank received into a (local_rows, D) gradient shard (tests / dense consumers)."""
-        if int(self.overflow.item()):
-            raise RuntimeError("gradient receive buffer overflow: raise `slack`")
         dense = torch.zeros((self.local_rows, self.dim), dtype=torch.float32, device=self.device)
         L = _lib.lib()
         for src in range(self.G):
@@ -205,3 +244,36 @@ class ShardedEmbeddingTables:
                                               self.recv_vals[src].data_ptr(), self.recv_counts[src:].data_ptr(), self.capacity,
                                               ops._stream()))
         return dense
+
+
+class _ShardedLookupFM2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, tables: ShardedEmbeddingTables, ids: torch.Tensor):
+        B, F = ids.shape
+        ids64 = ids
+        if ids.dtype == torch.int32:
+            ids64 = torch.empty((B, F), dtype=torch.int64, device=ids.device)
+            tile, fm2 = tables.lookup_fm2(ids, ids64_out=ids64)
+        else:
+            tile, fm2 = tables.lookup_fm2(ids)
+        ctx.tables = tables
+        ctx.plan = tables.plan(ids64)
+        ctx.save_for_backward(tile)
+        return tile, fm2
+
+    @staticmethod
+    def backward(ctx, d_tile, d_fm2):
+        (tile,) = ctx.saved_tensors
+        ctx.tables.bwd_push(tile, None if d_tile is None else d_tile.contiguous(), None if d_fm2 is None else d_fm2.contiguous(),
+                            ctx.plan)
+        return None, None, None
+
+
+def lookup_fm2_autograd(tables: ShardedEmbeddingTables, ids: torch.Tensor, anchor: Optional[torch.Tensor] = None):
+    """(B,F) ids (int64 or int32) -> (tile (B,F,D), fm2 (B,1)) inside an autograd graph; the backward pushes the gradient
+    rows to their owners (call ``tables.finish_push()`` before the owners' optimizer step)."""
+    if anchor is None:
+        if not hasattr(tables, "_anchor"):
+            tables._anchor = torch.zeros((), device=tables.device, requires_grad=True)
+        anchor = tables._anchor
+    return _ShardedLookupFM2.apply(anchor, tables, ids)

@@ -29,9 +29,26 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def assert_close(a, b, tol=TOL, what=""):
+def elementwise_excess(a, b, tol=TOL):
+    """Worst element of |a-b| / (tol*|b| + tol*rms(b)); <= 1 means every element is within `tol` relative, with an
+    absolute floor of tol*rms(ref) so that elements which are exact zeros / cancellations of the reference still have a scale."""
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    rms = float(np.sqrt(np.mean(b * b)))
+    return float((np.abs(a - b) / (tol * np.abs(b) + tol * rms + 1e-300)).max())
+
+
+def assert_close(a, b, tol=TOL, what="", elementwise=True):
+    """Two criteria, both must hold: max-norm (max|a-b| <= tol*max|ref|) and element-wise
+    (|a-b| <= tol*|ref| + tol*rms(ref) for EVERY element -- north_star's "within 1e-5 relative")."""
     e = relerr(a, b)
-    assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e}"
+    assert e <= tol, f"{what}: max-norm relative error {e:.3e} > {tol:.1e}"
+    if elementwise:
+        x = elementwise_excess(a, b, tol)
+        assert x <= 1.0, f"{what}: element-wise error is {x:.2f}x the bound tol*|ref| + tol*rms(ref), tol={tol:.1e}"
 
 
 def trunc_normal(rng, shape, std):

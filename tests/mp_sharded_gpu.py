@@ -37,12 +37,34 @@ def main():
         d_tile = torch.randn((B, F, D), device=dev, generator=gi)
         d_fm2 = torch.randn((B,), device=dev, generator=gi)
         row_grads = ops.embed_fm2_bwd(tile, d_tile, d_fm2)
+        refd = R.exchange_reference(t.local_rows, t.field_row_offset, ids, row_grads)
+        # (1) plain push of existing row gradients
         t.push_grads(ids, row_grads)
         got = t.received_to_dense()
-        refd = R.exchange_reference(t.local_rows, t.field_row_offset, ids, row_grads)
         err = (got.double() - refd).abs().max() / refd.abs().max().clamp_min(1e-30)
         assert err <= 1e-5, f"pushed gradients differ: {err}"
         assert int(t.recv_counts.sum()) > 0
+        dist.barrier()
+        # (2) backward fused with the push: row_grads never materialised
+        t.recv_vals.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        plan = t.plan(ids)
+        t.bwd_push(tile, d_tile, d_fm2, plan)
+        t.finish_push()
+        got = t.received_to_dense()
+        err = (got.double() - refd).abs().max() / refd.abs().max().clamp_min(1e-30)
+        assert err <= 1e-5, f"fused backward+push differs: {err}"
+        dist.barrier()
+        # (3) the autograd wrapper with int32 ids
+        t.recv_vals.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        tile_a, fm2_a = S.lookup_fm2_autograd(t, ids.int())
+        assert torch.equal(tile_a, tile) and torch.equal(fm2_a, fm2)
+        ((tile_a * d_tile).sum() + (fm2_a.reshape(-1) * d_fm2).sum()).backward()
+        t.finish_push()
+        got = t.received_to_dense()
+        err = (got.double() - refd).abs().max() / refd.abs().max().clamp_min(1e-30)
+        assert err <= 1e-5, f"autograd sharded lookup differs: {err}"
         dist.barrier()
         # ---- owner-side Adam on the received entries (SURVEY 8f.3 on the sharded path): two steps, lazy and TF-dense
         from recalgorithm_b200 import optim

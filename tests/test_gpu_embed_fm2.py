@@ -155,3 +155,37 @@ def test_full_size_properties():
     # (4) idempotence / determinism
     tile2, fm2b = ops.embed_fm2_fwd(table, off, ids)
     assert torch.equal(tile, tile2) and torch.equal(fm2, fm2b)
+
+
+@pytest.mark.parametrize("B,F,D", [(7, 6, 8), (64, 40, 32), (19, 33, 32), (130, 8, 4), (257, 65, 16), (9, 3, 128)])
+def test_int32_ids_and_fused_linear_head(B, F, D):
+    """int32 ids (half the PCIe bytes) give the identical tile and a widened int64 copy; the fused dense(1) head equals the
+    unfused chain tile.reshape(B, F*D) @ w and its backward equals ctr_embed_fm2_bwd fed with the rank-1 d_tile."""
+    from recalgorithm_b200 import autograd, ops
+    rng = np.random.default_rng(7 * B + F + D)
+    table, off, ids = make_case(rng, B, F, D, rng.integers(1, 50, size=F))
+    tile, fm2 = ops.embed_fm2_fwd(dev(table), dev(off), dev(ids))
+    ids64 = torch.empty((B, F), dtype=torch.int64, device="cuda")
+    t32, f32 = ops.embed_fm2_fwd(dev(table), dev(off), dev(ids).int(), ids64_out=ids64)
+    assert torch.equal(t32, tile) and torch.equal(f32, fm2) and torch.equal(ids64, dev(ids))
+    w = trunc_normal(rng, (F * D, 1), 0.3)
+    for id_t in (dev(ids), dev(ids).int()):
+        tl, fl, lin = ops.embed_fm2_lin_fwd(dev(table), dev(off), id_t, dev(w))
+        assert torch.equal(tl, tile) and torch.equal(fl, fm2)
+        e64 = tile.double().cpu().numpy().reshape(B, F * D)
+        assert_close(lin, e64 @ w.astype(np.float64), TOL, "fused dense(1) head")
+    g = trunc_normal(rng, (B,), 1.0)
+    gl = trunc_normal(rng, (B,), 1.0)
+    rg, dw = ops.embed_fm2_lin_bwd(tile, dev(w), dev(g), dev(gl))
+    d_tile = (gl.astype(np.float64)[:, None] * w.astype(np.float64).reshape(1, F * D)).reshape(B, F, D)
+    e = tile.double().cpu().numpy()
+    assert_close(rg, d_tile + O.fm2_bwd(e, g.astype(np.float64)), TOL, "row_grads (rank-1 d_tile)")
+    assert_close(dw, (gl.astype(np.float64)[:, None] * e.reshape(B, F * D)).sum(0), TOL, "d_wlin")
+    # autograd wrapper: same numbers as the unfused public API with a torch matmul head
+    tables = autograd.EmbeddingTables(np.diff(off).tolist(), D, device="cuda", init=None)
+    tables.weight.copy_(dev(table))
+    w_a = dev(w).clone().requires_grad_()
+    f_a, l_a = autograd.lookup_fm2_linear(tables, dev(ids).int(), w_a)
+    ((f_a.reshape(-1) * dev(g)).sum() + (l_a.reshape(-1) * dev(gl)).sum()).backward()
+    assert torch.equal(tables.grad_slices[0].values, rg) and torch.equal(tables.grad_slices[0].ids, dev(ids))
+    assert_close(w_a.grad.reshape(-1), dw, TOL, "autograd d_wlin")
