@@ -155,6 +155,17 @@ int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field
                             const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, float lr_t, float beta1,
                             float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
 
+/* Lookup backward FUSED with that step (the row update without writing row-grads to HBM): computes the
+ * IndexedSlices values d_tile + d_fm2*(S - e) of ctr_embed_fm2_bwd in registers and applies the LazyAdam update to every row
+ * referenced ONCE in the batch on the spot; rows referenced several times park their values in dup_grads ((B,F,D) scratch,
+ * written sparsely) and their entry in dup_list (int32[B*F + 1] scratch, last element = count) and are finished with the
+ * SUMMED gradient by two list-driven launches.  slot_of_row / touched_bitmap / n_unique as in ctr_adam_indexed_slices.
+ * F*D <= 1536, B*F < 2^30.  Same results as ctr_embed_fm2_bwd followed by ctr_adam_indexed_slices. */
+int ctr_embed_fm2_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const int64_t* field_row_offset,
+                           const int64_t* ids, int64_t B, int64_t F, int64_t D, float* var, float* m, float* v,
+                           int32_t* slot_of_row, float* dup_grads, int32_t* dup_list, float lr_t, float beta1, float beta2,
+                           float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
+
 /* The same step for the OWNER side of a row-sharded table: entries are the receive queues filled by ctr_sharded_grad_push --
  * rows (nseg, cap) local row ids, vals (nseg, cap, D) (consumed), counts (nseg,) filled slots per segment; duplicates of a
  * row across and inside segments are summed before the update.  nseg*cap < 2^31. */

@@ -57,6 +57,8 @@ SIGNATURES = {
     "ctr_bst_transformer_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_int, _P, _P, _P, _P, _P]),
     "ctr_adam_indexed_slices": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _I, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, _P, _P, _P]),
+    "ctr_embed_fm2_bwd_adam": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, ctypes.c_float, ctypes.c_float,
+                                       ctypes.c_float, ctypes.c_float, _P, _P, _P]),
     "ctr_adam_rows_dedup": (c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_float, _P, _P, _P]),
     "ctr_adam_dense_rest": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P]),

@@ -77,6 +77,10 @@ class _LookupFM2(torch.autograd.Function):
             d_tile = d_tile.contiguous()
         if d_fm2 is not None:
             d_fm2 = d_fm2.contiguous()
+        fused = getattr(ctx.tables, "_fused_opt", None)
+        if fused is not None:                       # optim.TableAdam(fused_backward=True): the row update happens right here
+            fused.apply_fused(tile, d_tile, d_fm2 if ctx.want_fm2 else None, ctx.ids)
+            return None, None, None, None
         values = ops.embed_fm2_bwd(tile, d_tile, d_fm2 if ctx.want_fm2 else None)
         ctx.tables.grad_slices.append(IndexedSlices(values, ctx.ids, ctx.tables.field_row_offset))
         return None, None, None, None

@@ -148,6 +148,172 @@ adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __r
   }
 }
 
+// ---- lookup backward FUSED with the sparse Adam step ("a fused row-wise update avoids writing row-grads to HBM") ----
+// claim (as above, plus a DUP flag when a second entry meets an already claimed row) -> ONE pass that computes the
+// IndexedSlices values d_tile + g*(S - e) in registers and, for every row referenced once in the batch (~99 % with uniform
+// ids), applies Adam on the spot: row_grads is neither written nor re-read.  Rows referenced more than once park their
+// values in `dup_grads` and their entry index in `dup_list`; two list-driven launches (merge into the claiming entry, update)
+// finish them with the SUMMED gradient, exactly like the unfused path.
+constexpr int DUP_FLAG = 0x40000000;
+
+__global__ void __launch_bounds__(256)
+adam_claim_dup_kernel(const EntrySrc src, long long n, int* __restrict__ slot) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = entry_row(src, e);
+    if (row >= 0 && atomicCAS(slot + row, -1, (int)e) != -1) atomicOr(slot + row, DUP_FLAG);
+  }
+}
+
+__device__ __forceinline__ void adam_apply(float4& w, float4& mm, float4& vv, const float4& g, float lr_t, float b1, float b2, float eps) {
+  mm.x = b1 * mm.x + (1.f - b1) * g.x; mm.y = b1 * mm.y + (1.f - b1) * g.y;
+  mm.z = b1 * mm.z + (1.f - b1) * g.z; mm.w = b1 * mm.w + (1.f - b1) * g.w;
+  vv.x = b2 * vv.x + (1.f - b2) * g.x * g.x; vv.y = b2 * vv.y + (1.f - b2) * g.y * g.y;
+  vv.z = b2 * vv.z + (1.f - b2) * g.z * g.z; vv.w = b2 * vv.w + (1.f - b2) * g.w * g.w;
+  w.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); w.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
+  w.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); w.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+}
+
+// warp per sample; HOLD float4 per lane cover the sample's F*LPR chunks (F*D <= HOLD*128 floats); GK chunks are in flight
+// together in the update phase (d_tile, m, v, var loads issued before the first use).
+template <int LPR, int HOLD>
+__global__ void __launch_bounds__(256, 1)
+embed_fm2_bwd_adam_kernel(const float4* __restrict__ tile, const float4* __restrict__ d_tile, const float* __restrict__ d_fm2,
+                          const long long* __restrict__ row_off, const long long* __restrict__ ids, int B, int F,
+                          float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, int* __restrict__ slot,
+                          float4* __restrict__ dup_grads, int* __restrict__ dup_list, int* __restrict__ n_dup,
+                          float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched,
+                          long long* __restrict__ n_unique) {
+  constexpr int GK = HOLD < 4 ? HOLD : 4;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n4 = F * LPR;
+  const int c = lane % LPR;
+  int mine = 0;
+  for (int b = warp0; b < B; b += nwarps) {
+    const float4* e_row = tile + (size_t)b * n4;
+    const float4* dt_row = d_tile ? d_tile + (size_t)b * n4 : nullptr;
+    const float g = d_fm2 ? __ldg(d_fm2 + b) : 0.f;
+    float4 e[HOLD];
+    long long row[HOLD];
+#pragma unroll
+    for (int k = 0; k < HOLD; ++k) {
+      const int j = k * 32 + lane;
+      e[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      row[k] = -1;
+      if (j < n4) {
+        e[k] = ldg_stream_f4(e_row + j);
+        const int f = j / LPR;
+        const long long id = __ldg(ids + (size_t)b * F + f), lo = __ldg(row_off + f);
+        if (id >= 0 && id < __ldg(row_off + f + 1) - lo) row[k] = lo + id;
+      }
+    }
+    int s[HOLD];
+#pragma unroll
+    for (int k = 0; k < HOLD; ++k) s[k] = row[k] >= 0 ? __ldg(slot + row[k]) : -1;   // read-only during this launch for non-dup rows' peers
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < HOLD; ++k) { S.x += e[k].x; S.y += e[k].y; S.z += e[k].z; S.w += e[k].w; }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      S.x += __shfl_xor_sync(full, S.x, o); S.y += __shfl_xor_sync(full, S.y, o);
+      S.z += __shfl_xor_sync(full, S.z, o); S.w += __shfl_xor_sync(full, S.w, o);
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < HOLD; k0 += GK) {
+      float4 dt[GK], mm[GK], vv[GK], ww[GK];
+#pragma unroll
+      for (int u = 0; u < GK; ++u) {
+        const int k = k0 + u, j = k * 32 + lane;
+        dt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < HOLD && j < n4 && dt_row != nullptr) dt[u] = ldg_stream_f4(dt_row + j);
+        if (k < HOLD && row[k] >= 0 && !(s[k] & DUP_FLAG)) {
+          const size_t o = (size_t)row[k] * LPR + c;
+          mm[u] = m[o]; vv[u] = v[o]; ww[u] = var[o];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < GK; ++u) {
+        const int k = k0 + u, j = k * 32 + lane;
+        if (k >= HOLD || row[k] < 0) continue;
+        float4 r;
+        r.x = dt[u].x + g * (S.x - e[k].x); r.y = dt[u].y + g * (S.y - e[k].y);
+        r.z = dt[u].z + g * (S.z - e[k].z); r.w = dt[u].w + g * (S.w - e[k].w);
+        const int entry = b * F + j / LPR;
+        if (!(s[k] & DUP_FLAG)) {
+          const size_t o = (size_t)row[k] * LPR + c;
+          adam_apply(ww[u], mm[u], vv[u], r, lr_t, b1, b2, eps);
+          m[o] = mm[u]; v[o] = vv[u]; var[o] = ww[u];
+          if (c == 0) {
+            slot[row[k]] = -1;
+            if (touched != nullptr) atomicOr(touched + (row[k] >> 5), 1u << (row[k] & 31));
+            ++mine;
+          }
+        } else {
+          dup_grads[(size_t)entry * LPR + c] = r;
+          if (c == 0) dup_list[atomicAdd(n_dup, 1)] = entry;
+        }
+      }
+    }
+  }
+  if (n_unique != nullptr) {
+    mine = __reduce_add_sync(full, mine);
+    if (lane == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(n_unique), (unsigned long long)mine);
+  }
+}
+
+// list-driven finish of the duplicated rows: MERGE (every non-claiming entry adds its parked values into the claiming entry's)
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_dup_merge_kernel(const EntrySrc src, const int* __restrict__ slot, float4* __restrict__ dup_grads,
+                      const int* __restrict__ dup_list, const int* __restrict__ n_dup) {
+  const size_t total = (size_t)(*n_dup) * LPR;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int e = __ldg(dup_list + t / LPR);
+    const long long row = entry_row(src, e);
+    const int w = __ldg(slot + row) & ~DUP_FLAG;
+    if (w != e) atomicAdd(dup_grads + (size_t)w * LPR + t % LPR, dup_grads[(size_t)e * LPR + t % LPR]);
+  }
+}
+// ... then UPDATE by the claiming entries
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_dup_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, const EntrySrc src,
+                       int* __restrict__ slot, const float4* __restrict__ dup_grads, const int* __restrict__ dup_list,
+                       const int* __restrict__ n_dup, float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched,
+                       long long* __restrict__ n_unique) {
+  const size_t total = (size_t)(*n_dup) * LPR;
+  int mine = 0;
+  for (size_t base = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); base < total; base += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = base + (threadIdx.x & 31);
+    long long row = -1;
+    int e = -1;
+    bool win = false;
+    if (t < total) {
+      e = __ldg(dup_list + t / LPR);
+      row = entry_row(src, e);
+      win = (slot[row] & ~DUP_FLAG) == e;
+    }
+    __syncwarp();                      // every lane of an entry has read the slot before its lane 0 clears it
+    if (!win) continue;
+    const size_t o = (size_t)row * LPR + t % LPR;
+    const float4 g = dup_grads[(size_t)e * LPR + t % LPR];
+    float4 mm = m[o], vv = v[o], w = var[o];
+    adam_apply(w, mm, vv, g, lr_t, b1, b2, eps);
+    m[o] = mm; v[o] = vv; var[o] = w;
+    if (t % LPR == 0) {
+      slot[row] = -1;
+      if (touched != nullptr) atomicOr(touched + (row >> 5), 1u << (row & 31));
+      ++mine;
+    }
+  }
+  if (n_unique != nullptr) {
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long*>(n_unique), (unsigned long long)mine);
+  }
+}
+
 static int check_adam(const char* fn, int64_t V, int64_t D) {
   CTR_REQUIRE(V >= 0, "%s: bad V", fn);
   CTR_UNSUPPORTED(D % 4 != 0 || D > 128 || (D & (D - 1)) != 0, "%s: D=%lld unsupported (power of two in 4..128)", fn, (long long)D);
@@ -241,4 +407,70 @@ extern "C" int ctr_adam_rows_dedup(float* var, float* m, float* v, int64_t V, in
   EntrySrc src = {reinterpret_cast<const long long*>(rows), nullptr, reinterpret_cast<const long long*>(counts), cap, V, 0};
   return adam_dedup_launch("ctr_adam_rows_dedup", var, m, v, D, src, nseg * cap, vals, slot_of_row, lr_t, beta1, beta2, eps,
                            touched_bitmap, n_unique, as_stream(stream));
+}
+
+template <int LPR, int HOLD>
+static int launch_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const EntrySrc& src, int64_t B, int64_t F,
+                           float* var, float* m, float* v, int32_t* slot, float* dup_grads, int32_t* dup_list, float lr_t, float b1,
+                           float b2, float eps, uint32_t* touched, int64_t* n_unique, cudaStream_t st) {
+  auto k = embed_fm2_bwd_adam_kernel<LPR, HOLD>;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long long grid = (long long)per_sm * sm_count();
+  if (grid > (B + 7) / 8) grid = (B + 7) / 8;
+  int* n_dup = dup_list + B * F;
+  k<<<(int)grid, 256, 0, st>>>(reinterpret_cast<const float4*>(tile), reinterpret_cast<const float4*>(d_tile), d_fm2, src.off, src.ids,
+                               (int)B, (int)F, reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),
+                               reinterpret_cast<float4*>(v), slot, reinterpret_cast<float4*>(dup_grads), dup_list, n_dup, lr_t, b1, b2,
+                               eps, touched, reinterpret_cast<long long*>(n_unique));
+  const int g2 = sm_count() * 2;
+  adam_dup_merge_kernel<LPR><<<g2, 256, 0, st>>>(src, slot, reinterpret_cast<float4*>(dup_grads), dup_list, n_dup);
+  adam_dup_update_kernel<LPR><<<g2, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),
+                                                  reinterpret_cast<float4*>(v), src, slot, reinterpret_cast<const float4*>(dup_grads),
+                                                  dup_list, n_dup, lr_t, b1, b2, eps, touched, reinterpret_cast<long long*>(n_unique));
+  CTR_CHECK_LAUNCH("ctr_embed_fm2_bwd_adam");
+  count_launch(2);
+  return CTR_OK;
+}
+
+template <int LPR>
+static int dispatch_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const EntrySrc& src, int64_t B, int64_t F,
+                             float* var, float* m, float* v, int32_t* slot, float* dup_grads, int32_t* dup_list, float lr_t, float b1,
+                             float b2, float eps, uint32_t* touched, int64_t* n_unique, cudaStream_t st) {
+  const int64_t per_lane = (F * LPR + 31) / 32;
+#define GO(H) return launch_bwd_adam<LPR, H>(tile, d_tile, d_fm2, src, B, F, var, m, v, slot, dup_grads, dup_list, lr_t, b1, b2, eps, touched, n_unique, st)
+  if (per_lane <= 4) GO(4);
+  if (per_lane <= 8) GO(8);
+  if (per_lane <= 12) GO(12);
+#undef GO
+  set_error("ctr_embed_fm2_bwd_adam: F*D = %lld exceeds the register-resident limit of 1536 (use ctr_embed_fm2_bwd + ctr_adam_indexed_slices)",
+            (long long)(F * LPR * 4));
+  return CTR_ERR_UNSUPPORTED;
+}
+
+extern "C" int ctr_embed_fm2_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const int64_t* field_row_offset,
+                                      const int64_t* ids, int64_t B, int64_t F, int64_t D, float* var, float* m, float* v,
+                                      int32_t* slot_of_row, float* dup_grads, int32_t* dup_list, float lr_t, float beta1, float beta2,
+                                      float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream) {
+  int rc = check_adam("ctr_embed_fm2_bwd_adam", 0, D);
+  if (rc) return rc;
+  CTR_REQUIRE(tile && field_row_offset && ids && var && m && v && slot_of_row && dup_grads && dup_list,
+              "ctr_embed_fm2_bwd_adam: null argument");
+  CTR_REQUIRE(B >= 0 && F >= 1 && F <= 65536 && B * F < (1LL << 30), "ctr_embed_fm2_bwd_adam: bad B/F (B*F must be < 2^30)");
+  CTR_REQUIRE(aligned16(tile) && aligned16(d_tile) && aligned16(var) && aligned16(m) && aligned16(v) && aligned16(dup_grads),
+              "ctr_embed_fm2_bwd_adam: buffers must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  EntrySrc src = {reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(field_row_offset), nullptr, 0, 0, (int)F};
+  const long long n = (long long)B * F;
+  CTR_CUDA(cudaMemsetAsync(dup_list + n, 0, sizeof(int32_t), st));
+  const int grid_e = (int)((n + 255) / 256 < (long long)sm_count() * 16 ? (n + 255) / 256 : (long long)sm_count() * 16);
+  adam_claim_dup_kernel<<<grid_e, 256, 0, st>>>(src, n, slot_of_row);
+  count_launch(1);
+  switch (D / 4) {
+#define GO(L) case L: return dispatch_bwd_adam<L>(tile, d_tile, d_fm2, src, B, F, var, m, v, slot_of_row, dup_grads, dup_list, lr_t, beta1, beta2, eps, touched_bitmap, n_unique, st)
+    GO(1); GO(2); GO(4); GO(8); GO(16);
+    default: return dispatch_bwd_adam<32>(tile, d_tile, d_fm2, src, B, F, var, m, v, slot_of_row, dup_grads, dup_list, lr_t, beta1, beta2, eps, touched_bitmap, n_unique, st);
+#undef GO
+  }
 }

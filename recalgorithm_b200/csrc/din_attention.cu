@@ -26,6 +26,7 @@ namespace ctr {
 constexpr int DIN_H1 = 64;      // f1_att units (DIN/din_attention.py:21)
 constexpr int DIN_H2 = 32;      // f2_att units (:22)
 constexpr int DIN_TT = 4;       // positions per warp per round
+constexpr int DIN_BT = 4;       // backward: positions per warp per round (shared-memory latency and warp syncs amortised 4x)
 constexpr float DIN_PAD_F = -4294967295.0f;   // -2**32 + 1 (rounds to -2^32 in fp32, like the reference's fp32 tensor)
 
 struct DinSmem {                // offsets in floats into dynamic shared memory
@@ -281,9 +282,9 @@ __host__ __device__ inline DinBwdSmem din_bwd_layout(int H, int HP, int T, int w
   w = (w + 3) & ~3;
   L.o_wt = w; w += DIN_H1 * (HP + 1);               // Weff^T[c][h], padded rows
   w = (w + 3) & ~3;
-  L.o_h1 = w; w += DIN_H1;
-  L.o_dp1 = w; w += DIN_H1;
-  L.o_dp2 = w; w += DIN_H2;
+  L.o_h1 = w; w += DIN_H1 * DIN_BT;
+  L.o_dp1 = w; w += DIN_H1 * DIN_BT;
+  L.o_dp2 = w; w += DIN_H2 * DIN_BT;
   w = (w + 3) & ~3;
   L.warp_stride = w;
   L.total = o + warps * w;
@@ -424,67 +425,126 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
     }
     for (int i = lane; i < T * H; i += 32) sdk[i] = sc[i / H] * sgo[i % H];
     __syncwarp();
-    // ---------------- positions
-    for (int t = 0; t < len; ++t) {
-      const float* k = skeys + t * H;
-      float h1a, h1b, h2, score;
-      mlp_fwd(k, weff, qpart, h1a, h1b, h2, score);
-      const float dsv = sds[t];
-      const float dp2 = h2 > 0.f ? dsv * w3v : 0.f;
-      sdp2[lane] = dp2;
-      acc_w3 += h2 * dsv;
-      acc_b2 += dp2;
-      acc_b3 += dsv;
+    // ---------------- positions, DIN_BT at a time: every shared-memory round trip (h1 broadcast, W2 column/row chunks, Weff^T)
+    // and every warp sync serves DIN_BT positions; accumulators stay in registers
+    for (int t0 = 0; t0 < len; t0 += DIN_BT) {
+      const int n = min(DIN_BT, len - t0);
+      float h1a[DIN_BT], h1b[DIN_BT], dp2[DIN_BT];
+#pragma unroll
+      for (int tt = 0; tt < DIN_BT; ++tt) {
+        float p0 = qpart[0], p1 = qpart[1];
+        const float* k = skeys + (t0 + (tt < n ? tt : 0)) * H;
+#pragma unroll
+        for (int h = 0; h < HP; ++h) {
+          if (h < H) {
+            const float kv = k[h];
+            p0 += kv * weff[h][0];
+            p1 += kv * weff[h][1];
+          }
+        }
+        h1a[tt] = tt < n ? fmaxf(p0, 0.f) : 0.f;
+        h1b[tt] = tt < n ? fmaxf(p1, 0.f) : 0.f;
+        sh1[tt * DIN_H1 + lane] = h1a[tt];
+        sh1[tt * DIN_H1 + lane + 32] = h1b[tt];
+      }
+      __syncwarp();
       {
-        const float4* h1v = reinterpret_cast<const float4*>(sh1);
+        float acc[DIN_BT];
+#pragma unroll
+        for (int tt = 0; tt < DIN_BT; ++tt) acc[tt] = b2v;
 #pragma unroll
         for (int c4 = 0; c4 < DIN_H1 / 4; ++c4) {
-          const float4 v = h1v[c4];
-          acc_w2[4 * c4 + 0] += v.x * dp2; acc_w2[4 * c4 + 1] += v.y * dp2;
-          acc_w2[4 * c4 + 2] += v.z * dp2; acc_w2[4 * c4 + 3] += v.w * dp2;
+          const float w0 = W2s[(4 * c4 + 0) * DIN_H2 + lane], w1v = W2s[(4 * c4 + 1) * DIN_H2 + lane],
+                      w2v = W2s[(4 * c4 + 2) * DIN_H2 + lane], w3c = W2s[(4 * c4 + 3) * DIN_H2 + lane];
+#pragma unroll
+          for (int tt = 0; tt < DIN_BT; ++tt) {
+            const float4 hv = reinterpret_cast<const float4*>(sh1 + tt * DIN_H1)[c4];
+            acc[tt] += hv.x * w0; acc[tt] += hv.y * w1v; acc[tt] += hv.z * w2v; acc[tt] += hv.w * w3c;
+          }
+        }
+#pragma unroll
+        for (int tt = 0; tt < DIN_BT; ++tt) {
+          const float h2 = fmaxf(acc[tt], 0.f);
+          const float dsv = tt < n ? sds[t0 + tt] : 0.f;
+          dp2[tt] = h2 > 0.f ? dsv * w3v : 0.f;
+          sdp2[tt * DIN_H2 + lane] = dp2[tt];
+          acc_w3 += h2 * dsv;
+          acc_b2 += dp2[tt];
+          acc_b3 += dsv;
+        }
+      }
+      // dW2[:, lane] += sum_tt h1[tt][:] * dpre2[tt][lane]
+#pragma unroll
+      for (int c4 = 0; c4 < DIN_H1 / 4; ++c4) {
+#pragma unroll
+        for (int tt = 0; tt < DIN_BT; ++tt) {
+          const float4 hv = reinterpret_cast<const float4*>(sh1 + tt * DIN_H1)[c4];
+          acc_w2[4 * c4 + 0] += hv.x * dp2[tt]; acc_w2[4 * c4 + 1] += hv.y * dp2[tt];
+          acc_w2[4 * c4 + 2] += hv.z * dp2[tt]; acc_w2[4 * c4 + 3] += hv.w * dp2[tt];
         }
       }
       __syncwarp();
-      // dh1[c] = sum_c2 dpre2[c2] * W2[c][c2] for c = lane, lane+32 (rotated 16-byte chunks: conflict-free)
-      float a0 = 0.f, a1 = 0.f;
+      // dh1[tt][c] = sum_c2 dpre2[tt][c2] * W2[c][c2] for c = lane, lane+32 (rotated 16-byte chunks: conflict-free)
+      float d0[DIN_BT], d1[DIN_BT];
       {
-        const float4* dp2v = reinterpret_cast<const float4*>(sdp2);
+        float a0[DIN_BT], a1[DIN_BT];
+#pragma unroll
+        for (int tt = 0; tt < DIN_BT; ++tt) { a0[tt] = 0.f; a1[tt] = 0.f; }
         const float4* r0 = reinterpret_cast<const float4*>(W2s + lane * DIN_H2);
         const float4* r1 = reinterpret_cast<const float4*>(W2s + (lane + 32) * DIN_H2);
 #pragma unroll
         for (int c4 = 0; c4 < DIN_H2 / 4; ++c4) {
           const int ch = (c4 + lane) & (DIN_H2 / 4 - 1);
-          const float4 dd = dp2v[ch], x0 = r0[ch], x1 = r1[ch];
-          a0 += dd.x * x0.x + dd.y * x0.y + dd.z * x0.z + dd.w * x0.w;
-          a1 += dd.x * x1.x + dd.y * x1.y + dd.z * x1.z + dd.w * x1.w;
+          const float4 x0 = r0[ch], x1 = r1[ch];
+#pragma unroll
+          for (int tt = 0; tt < DIN_BT; ++tt) {
+            const float4 dd = reinterpret_cast<const float4*>(sdp2 + tt * DIN_H2)[ch];
+            a0[tt] += dd.x * x0.x + dd.y * x0.y + dd.z * x0.z + dd.w * x0.w;
+            a1[tt] += dd.x * x1.x + dd.y * x1.y + dd.z * x1.z + dd.w * x1.w;
+          }
+        }
+#pragma unroll
+        for (int tt = 0; tt < DIN_BT; ++tt) {
+          d0[tt] = h1a[tt] > 0.f ? a0[tt] : 0.f;
+          d1[tt] = h1b[tt] > 0.f ? a1[tt] : 0.f;
+          dsum[0] += d0[tt]; dsum[1] += d1[tt];
+          sdp1[tt * DIN_H1 + lane] = d0[tt]; sdp1[tt * DIN_H1 + lane + 32] = d1[tt];
         }
       }
-      const float d0 = h1a > 0.f ? a0 : 0.f, d1 = h1b > 0.f ? a1 : 0.f;
-      dsum[0] += d0; dsum[1] += d1;
-      sdp1[lane] = d0; sdp1[lane + 32] = d1;
 #pragma unroll
-      for (int h = 0; h < HP; ++h) {
-        if (h < H) {
-          const float kv = k[h];
-          kd[h][0] += kv * d0;
-          kd[h][1] += kv * d1;
+      for (int tt = 0; tt < DIN_BT; ++tt) {
+        const float* k = skeys + (t0 + (tt < n ? tt : 0)) * H;       // d0 = d1 = 0 beyond n
+#pragma unroll
+        for (int h = 0; h < HP; ++h) {
+          if (h < H) {
+            const float kv = k[h];
+            kd[h][0] += kv * d0[tt];
+            kd[h][1] += kv * d1[tt];
+          }
         }
       }
       __syncwarp();
-      // dk[t][h] += sum_c Weff[h][c] * dpre1[c] : lane = (group, h); every group covers 64/ngroups columns
+      // dk[t][h] += sum_c Weff[h][c] * dpre1[t][c] : lane = (group, h); every group covers 64/ngroups columns
       {
         constexpr int NG = 32 / HP;                 // groups of HP lanes
         constexpr int CPG = DIN_H1 / NG;            // columns per group
         const int hh = lane % HP, grp = lane / HP;
-        float sdk_part = 0.f;
+        float part[DIN_BT];
+#pragma unroll
+        for (int tt = 0; tt < DIN_BT; ++tt) part[tt] = 0.f;
 #pragma unroll 8
         for (int cc = 0; cc < CPG; ++cc) {
           const int c = grp * CPG + cc;
-          sdk_part += sdp1[c] * swt[c * (HP + 1) + hh];
+          const float wv = swt[c * (HP + 1) + hh];
+#pragma unroll
+          for (int tt = 0; tt < DIN_BT; ++tt) part[tt] += sdp1[tt * DIN_H1 + c] * wv;
         }
 #pragma unroll
-        for (int o = HP; o < 32; o <<= 1) sdk_part += __shfl_xor_sync(0xffffffffu, sdk_part, o);
-        if (grp == 0 && hh < H) sdk[t * H + hh] += sdk_part;
+        for (int tt = 0; tt < DIN_BT; ++tt) {
+#pragma unroll
+          for (int o = HP; o < 32; o <<= 1) part[tt] += __shfl_xor_sync(0xffffffffu, part[tt], o);
+          if (grp == 0 && hh < H && tt < n) sdk[(t0 + tt) * H + hh] += part[tt];
+        }
       }
       __syncwarp();
     }

@@ -16,9 +16,18 @@ from . import _lib, autograd, ops
 
 
 class TableAdam:
+    """``fused_backward=True`` registers the optimizer on the tables: the backward of ``autograd.lookup_fm2`` then applies the
+    row updates itself (``ctr_embed_fm2_bwd_adam``: no IndexedSlices values are written to or re-read from HBM) and ``step()``
+    only completes the step (TF's dense decay of the untouched rows when ``lazy=False``).  One lookup backward per step."""
+
     def __init__(self, tables: "autograd.EmbeddingTables", lr: float, beta1: float = 0.9, beta2: float = 0.999,
-                 eps: float = 1e-8, lazy: bool = False):
+                 eps: float = 1e-8, lazy: bool = False, fused_backward: bool = False):
         self.tables, self.lr, self.b1, self.b2, self.eps, self.lazy = tables, lr, beta1, beta2, eps, lazy
+        self.fused_backward = fused_backward
+        self._fused_applied = False
+        self._dup = None
+        if fused_backward:
+            tables._fused_opt = self
         w = tables.weight
         self.m, self.v = torch.zeros_like(w), torch.zeros_like(w)
         self.t = 0
@@ -26,15 +35,51 @@ class TableAdam:
         self._slot = torch.full((tables.num_rows,), -1, dtype=torch.int32, device=w.device)   # -1 between steps
         self._n_unique = torch.zeros((1,), dtype=torch.int64, device=w.device)
 
+    def apply_fused(self, tile, d_tile, d_fm2, ids) -> None:
+        """Called by the lookup's backward (fused_backward=True): backward + row update in one pass."""
+        if self._fused_applied:
+            raise RuntimeError("TableAdam(fused_backward=True) supports one lookup backward per step(); use the unfused optimizer")
+        tb = self.tables
+        w = tb.weight
+        B, F, D = tile.shape
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        self._n_unique.zero_()
+        if self._bitmap is not None:
+            self._bitmap.zero_()
+        if self._dup is None or self._dup[0].shape != (B, F, D):
+            self._dup = (torch.empty((B, F, D), dtype=torch.float32, device=w.device),
+                         torch.empty((B * F + 1,), dtype=torch.int32, device=w.device))
+        ops._chk(tile, torch.float32, "tile"); ops._chk(d_tile, torch.float32, "d_tile", (B, F, D)); ops._chk(ids, torch.int64, "ids", (B, F))
+        if d_fm2 is not None:
+            d_fm2 = d_fm2.reshape(B)
+        ops._chk(d_fm2, torch.float32, "d_fm2", (B,))
+        _lib.check(_lib.lib().ctr_embed_fm2_bwd_adam(ops._ptr(tile), ops._ptr(d_tile), ops._ptr(d_fm2), tb.field_row_offset.data_ptr(),
+                                                     ops._ptr(ids), B, F, D, w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                     self._slot.data_ptr(), self._dup[0].data_ptr(), self._dup[1].data_ptr(), lr_t,
+                                                     self.b1, self.b2, self.eps, ops._ptr(self._bitmap), self._n_unique.data_ptr(),
+                                                     ops._stream()))
+        self._fused_applied = True
+
     def step(self) -> None:
         """Consume tables.grad_slices (every backward since the last zero_grad) and apply one Adam step.  Nothing is read
         back to the host; `last_unique_rows()` fetches the number of distinct rows the step touched."""
         tb = self.tables
         w = tb.weight
         V, D = w.shape
+        L = _lib.lib()
+        if self.fused_backward:
+            if not self._fused_applied:
+                raise RuntimeError("TableAdam(fused_backward=True).step() without a lookup backward since the last step")
+            lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+            if not self.lazy:
+                _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), V, D, lr_t, self.b1, self.b2,
+                                                 self.eps, ops._ptr(self._bitmap), ops._stream()))
+            self._fused_applied = False
+            tb.zero_grad()
+            return
         self.t += 1
         lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
-        L = _lib.lib()
         self._n_unique.zero_()
         if self._bitmap is not None:
             self._bitmap.zero_()

@@ -100,3 +100,68 @@ def test_full_size_adam_properties():
     assert float(dw.abs().max()) <= 0.01 * (1 + 1e-5)
     big = g.abs() > 1e-2
     assert_close(dw[big], -0.01 * torch.sign(g[big]), 1e-4, "first Adam step is -lr * sign(g) where |g| >> eps")
+
+
+@pytest.mark.parametrize("lazy", [False, True])
+@pytest.mark.parametrize("B,F,D,rows", [(64, 5, 16, 37), (512, 3, 8, 3), (300, 40, 32, 1000), (129, 33, 4, 11), (40, 12, 128, 50)])
+def test_backward_fused_with_adam_equals_unfused(lazy, B, F, D, rows):
+    """ctr_embed_fm2_bwd_adam (backward + row update in one pass, duplicates finished through the parked list) against
+    ctr_embed_fm2_bwd + ctr_adam_indexed_slices and the float64 oracle, three steps, duplicates / OOV / out-of-range ids."""
+    from recalgorithm_b200 import autograd, optim
+    rng = np.random.default_rng(B + F + D + int(lazy))
+    tf = autograd.EmbeddingTables([rows] * F, D, device="cuda")
+    tu = autograd.EmbeddingTables([rows] * F, D, device="cuda", init=None)
+    tu.weight.copy_(tf.weight)
+    of = optim.TableAdam(tf, lr=0.01, lazy=lazy, fused_backward=True)
+    ou = optim.TableAdam(tu, lr=0.01, lazy=lazy)
+    var = tf.weight.cpu().double().numpy(); m = np.zeros_like(var); v = np.zeros_like(var)
+    off = tf.field_row_offset.cpu().numpy()
+    for t in range(1, 4):
+        ids = rng.integers(-1, rows + 1, size=(B, F)).astype(np.int64)
+        d_tile = trunc_normal(rng, (B, F, D), 1.0); g = trunc_normal(rng, (B,), 1.0)
+        for tb in (tf, tu):
+            tile, fm2 = autograd.lookup_fm2(tb, dev(ids))
+            (tile * dev(d_tile)).sum().add((fm2[:, 0] * dev(g)).sum()).backward()
+        assert not tf.grad_slices, "the fused backward must not materialise IndexedSlices"
+        valid = (ids >= 0) & (ids < rows)
+        grows = (ids + off[:-1][None, :])[valid]
+        gvals = tu.grad_slices[0].values.cpu().double().numpy()[valid]
+        of.step(); ou.step()
+        assert of.last_unique_rows() == ou.last_unique_rows() == len(np.unique(grows))
+        assert bool((of._slot == -1).all()), "slot table must be idle (-1) between steps"
+        var, m, v = O.adam_sparse_apply(var, m, v, grows, gvals, t, 0.01, lazy=lazy)
+        assert_close(tf.weight, var, 2e-6, f"fused var step {t}")
+        assert_close(of.m, m, 1e-5, f"fused m step {t}"); assert_close(of.v, v, 1e-5, f"fused v step {t}")
+        assert_close(tf.weight, tu.weight.double(), 2e-6, f"fused vs unfused var step {t}")
+
+
+def test_backward_fused_with_adam_full_size():
+    """Config-5 shape with ~1300 duplicates per row in one field: same first-step properties as the unfused test."""
+    from recalgorithm_b200 import autograd, optim, ops
+    B, F, D, rows = 65536, 40, 32, 2_500_000
+    gen = torch.Generator(device="cuda").manual_seed(199)
+    tables = autograd.EmbeddingTables([rows] * F, D, device="cuda", init=None)
+    tables.weight.normal_(0, D ** -0.5, generator=gen)
+    ids = torch.randint(0, rows, (B, F), device="cuda", generator=gen)
+    ids[:, 0] = torch.randint(0, 50, (B,), device="cuda", generator=gen)
+    ids[torch.rand((B, F), device="cuda", generator=gen) < 0.03] = -1
+    d_tile = torch.randn((B, F, D), device="cuda", generator=gen)
+    d_fm2 = torch.randn((B,), device="cuda", generator=gen)
+    tile, _ = ops.embed_fm2_fwd(tables.weight, tables.field_row_offset, ids)
+    vals = ops.embed_fm2_bwd(tile, d_tile, d_fm2)
+    flat = (ids + tables.field_row_offset[:-1][None, :])[ids >= 0]
+    uniq = torch.unique(flat)
+    opt = optim.TableAdam(tables, lr=0.01, lazy=True, fused_backward=True)
+    w0 = tables.weight[uniq].clone()
+    probe = torch.randint(0, rows * F, (1 << 20,), device="cuda", generator=gen)
+    untouched = probe[~torch.isin(probe, uniq)]
+    u0 = tables.weight[untouched].clone()
+    opt.apply_fused(tile, d_tile, d_fm2, ids)
+    opt.step()
+    assert opt.last_unique_rows() == int(uniq.numel()) and bool((opt._slot == -1).all())
+    assert torch.equal(tables.weight[untouched], u0) and float(opt.m[untouched].abs().max()) == 0.0
+    g = torch.zeros((uniq.numel(), D), device="cuda", dtype=torch.float64)
+    g.index_add_(0, torch.searchsorted(uniq, flat), vals[ids >= 0].double())
+    assert_close(opt.m[uniq], (1.0 - float(np.float32(0.9))) * g, 1e-5, "m = (1-b1) * summed gradient")
+    dw = (tables.weight[uniq] - w0).double()
+    assert float(dw.abs().max()) <= 0.01 * (1 + 1e-5)

@@ -176,6 +176,34 @@ def main():
             emit("table_adam_lazy" if lazy else "table_adam_dense", {"B": B, "F": F, "D": D, "rows_per_field": rows}, m_, bst,
                  bytes_=by, note="includes a 336 MB clone of the gradient values per step (the step consumes them)")
             del opt
+        # backward + LazyAdam: unfused pair (ctr_embed_fm2_bwd writes row_grads, ctr_adam_indexed_slices re-reads them) vs the
+        # fused kernel (ctr_embed_fm2_bwd_adam)
+        tile, _ = ops.embed_fm2_fwd(tables.weight, tables.field_row_offset, ids[0])
+        d_tile, d_fm2 = rn(B, F, D, std=0.01), rn(B, std=0.01)
+        opt_u = optim.TableAdam(tables, lr=1e-3, lazy=True)
+        rg = torch.empty_like(tile)
+
+        def unfused():
+            k[0] += 1
+            ops.embed_fm2_bwd(tile, d_tile, d_fm2, row_grads=rg)
+            tables.grad_slices.append(autograd.IndexedSlices(rg, ids[k[0] % 4], tables.field_row_offset))
+            opt_u.step()
+        m_, bst = timeit(unfused, max(5, args.iters // 2), flush)
+        n = B * F
+        by_u = n * 8 + 3 * n * D * 4 + n * D * 4 + 6 * n * D * 4
+        emit("bwd_plus_lazy_adam_unfused", {"B": B, "F": F, "D": D, "rows_per_field": rows}, m_, bst, bytes_=by_u,
+             note="embed_fm2_bwd (read tile, d_tile; write row_grads) + claim/merge/update (read row_grads; RMW m, v, var)")
+        del opt_u
+        opt_f = optim.TableAdam(tables, lr=1e-3, lazy=True, fused_backward=True)
+
+        def fused():
+            k[0] += 1
+            opt_f.apply_fused(tile, d_tile, d_fm2, ids[k[0] % 4])
+            opt_f.step()
+        m_, bst = timeit(fused, max(5, args.iters // 2), flush)
+        by_f = n * 8 + 2 * n * D * 4 + 6 * n * D * 4
+        emit("bwd_plus_lazy_adam_fused", {"B": B, "F": F, "D": D, "rows_per_field": rows}, m_, bst, bytes_=by_f,
+             note="ctr_embed_fm2_bwd_adam: read tile, d_tile; RMW m, v, var; row_grads only for rows with duplicates")
 
 
 if __name__ == "__main__" and "--configs" not in sys.argv:
