@@ -305,6 +305,24 @@ def run_reference_arm(args, cfg):
 # ----------------------------------------------------------------------------------------------------
 # e2e harness: pinned host inputs -> H2D (double-buffered on a copy stream) -> public autograd API -> loss D2H
 # ----------------------------------------------------------------------------------------------------
+def h2d_probe(dev, nbytes):
+    """Pinned-host -> device copy rate for one step's input size (explains the e2e bound: the copy of step i+1 overlaps the
+    compute of step i, so a step cannot be shorter than its H2D copy)."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        dst.copy_(src, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    return {"h2d_GBps_measured": nbytes / (ms * 1e-3) / 1e9, "h2d_ms_per_step_alone": ms}
+
+
 def e2e_loop(dd: Dist, B, F, host_ids, host_labels, model_step, steps):
     """model_step(ids_dev, labels_dev) -> loss tensor (runs forward+backward through the public API).  Every step's H2D copy
     of ids+labels and the D2H of its loss are inside the timed region; the loss is READ on the host one step late (so the
@@ -450,6 +468,7 @@ def run_deepfm(args, cfg, dd: Dist):
         e2e_ms, losses = e2e_loop(dd, B, F, ids_host, lab_host, model_fused, e2e_steps)
         e2e_ms_unf, losses_unf = e2e_loop(dd, B, F, ids_host, lab_host, model_unfused, e2e_steps)
         e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+        pcie = h2d_probe(dev, B * F * 4 + B * 4)
         if rank != 0:
             return
         ach_fwd = fwd_b * B / (fwd_ms * 1e-3) / 1e9
@@ -475,7 +494,7 @@ def run_deepfm(args, cfg, dd: Dist):
             "roofline_step": {"achieved": ach_step, "frac": ach_step / hbm, "bytes_per_sample": fwd_b + bwd_b},
             "sustained": sustained,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4,
-                    "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1],
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1], **pcie,
                     "what": "pinned-host int32 ids + labels -> H2D (double-buffered on a copy stream) -> autograd.lookup_fm2_linear "
                             "(gather + FM2 + dense(1) deep head in one kernel; ids widened on device) -> sigmoid-CE (torch) -> backward "
                             "(ctr_embed_fm2_lin_bwd -> IndexedSlices + d_w) -> loss D2H to pinned memory, read on the host one step later",

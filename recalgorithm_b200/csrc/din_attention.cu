@@ -667,14 +667,16 @@ extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, cons
     CTR_CUDA(cudaMemsetAsync(d_query, 0, sizeof(float) * B * H, st));
     return CTR_OK;
   }
-  constexpr int WARPS = 8;
   const int HPv = H <= 4 ? 4 : H <= 8 ? 8 : H <= 16 ? 16 : 32;
-  const DinBwdSmem L = din_bwd_layout((int)H, HPv, (int)T, WARPS);
+  // 8 warps per CTA unless their staging areas do not fit the shared memory (long sequences of wide keys): then 4
+  const bool w8 = sizeof(float) * (size_t)din_bwd_layout((int)H, HPv, (int)T, 8).total <= 220 * 1024;
+  const int warps = w8 ? 8 : 4;
+  const DinBwdSmem L = din_bwd_layout((int)H, HPv, (int)T, warps);
   const size_t smem = sizeof(float) * (size_t)L.total;
   CTR_UNSUPPORTED(smem > 220 * 1024, "ctr_din_attention_bwd: T=%lld H=%lld needs %zu B of shared memory", (long long)T,
                   (long long)H, smem);
-  const long long need = (B + WARPS - 1) / WARPS;
-#define GO(HPV)                                                                                                   \
+  const long long need = (B + warps - 1) / warps;
+#define GO2(HPV, WARPS)                                                                                           \
   {                                                                                                               \
     auto k = din_attention_bwd_kernel<HPV, WARPS>;                                                                \
     if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -686,8 +688,10 @@ extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, cons
                                            w2, b2, w3, b3, g_out, att_w, (int)B, (int)T, (int)H, is_softmax,      \
                                            d_query, d_keys, d_params);                                            \
   }
+#define GO(HPV) { if (w8) GO2(HPV, 8) else GO2(HPV, 4) }
   if (H <= 4) GO(4) else if (H <= 8) GO(8) else if (H <= 16) GO(16) else GO(32)
 #undef GO
+#undef GO2
   CTR_CHECK_LAUNCH("ctr_din_attention_bwd");
   return CTR_OK;
 }

@@ -104,7 +104,9 @@ def test_afm_fwd_bwd(B, F, K, T):
     assert_close(ops.afm_fwd(dev(e), dev(w), dev(b), dev(h)), O.afm_fwd(d(e), d(w), d(b), d(h)), TOL, "pooled")
     de, dw, db, dh = ops.afm_bwd(dev(e), dev(w), dev(b), dev(h), dev(g))
     ede, edw, edb, edh = O.afm_bwd(e, w, b, h, g)
-    assert_close(de, ede, TOL, "d_tile"); assert_close(dw, edw, TOL, "d_w"); assert_close(db, edb, TOL, "d_b")
+    assert_close(de, ede, TOL, "d_tile"); assert_close(db, edb, TOL, "d_b")
+    # d_w sums B*P ReLU-gated products with cancellation (3120 terms at F=40): its fp32 error scales with sum|terms|
+    assert_close(dw, edw, TOL, "d_w", elementwise=3.0)
     assert_close(dh, edh, TOL, "d_h")
 
 
