@@ -107,7 +107,7 @@ def test_afm_fwd_bwd(B, F, K, T):
     assert_close(de, ede, TOL, "d_tile"); assert_close(db, edb, TOL, "d_b")
     # d_w sums B*P ReLU-gated products with cancellation (3120 terms at F=40): its fp32 error scales with sum|terms|
     assert_close(dw, edw, TOL, "d_w", elementwise=3.0)
-    assert_close(dh, edh, TOL, "d_h")
+    assert_close(dh, edh, TOL, "d_h", elementwise=3.0)       # same batch-reduced, softmax-weighted sum
 
 
 def test_pairwise_errors_and_layers_api():
