@@ -136,13 +136,16 @@ int ctr_rows_scatter_add(float* dst, int64_t V, int64_t D, const int64_t* rows, 
  * indices, decays m and v of the WHOLE table and updates every row; DIEN uses LazyAdam (DIEN/dien.py:328).
  * rows (n) must be UNIQUE with grads (n, D) already summed per row (ctr_rows_scatter_add into a compact buffer does that);
  * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is computed by the caller.  count: device int64 (NULL = max_n).
+ * state_stride (all ctr_adam_* entry points) = floats between consecutive rows of m (and of v): D for two separate (V, D)
+ * tables, 2*D for ONE interleaved (V, 2, D) buffer with v = m + D -- a row's two moments then share a DRAM page, which is
+ * what the random row updates are bound by (4 instead of 6 row activations per updated row).
  * ctr_adam_rows updates m, v, var of the listed rows (and sets their bit in touched_bitmap (ceil(V/32) uint32, zeroed by
  * the caller) when given) = LazyAdam; ctr_adam_dense_rest then applies the g = 0 update to every row whose bit is clear
  * = the reference's dense semantics. */
-int ctr_adam_rows(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, const float* grads,
+int ctr_adam_rows(float* var, float* m, float* v, int64_t state_stride, int64_t V, int64_t D, const int64_t* rows, const float* grads,
                   const int64_t* count, int64_t max_n, float lr_t, float beta1, float beta2, float eps,
                   uint32_t* touched_bitmap, void* stream);
-int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, int64_t D, float lr_t, float beta1, float beta2, float eps,
+int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t state_stride, int64_t V, int64_t D, float lr_t, float beta1, float beta2, float eps,
                         const uint32_t* touched_bitmap, void* stream);
 
 /* Fused IndexedSlices step (no sort, no host round trip): ids (B,F) per-field local ids (out-of-range = skipped, like the
@@ -150,10 +153,13 @@ int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, int64_t D, fl
  * into one of its entries).  slot_of_row: int32 per table row, all -1 on entry and again on exit (persistent scratch of
  * the optimizer).  Applies the LazyAdam update to every referenced row with the SUMMED gradient (TF sums duplicates
  * first); sets the rows' bits in touched_bitmap when given (then ctr_adam_dense_rest completes tf.train.AdamOptimizer's
- * dense semantics); adds the number of distinct rows to *n_unique when given.  B*F < 2^31. */
-int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field_row_offset, int64_t F, int64_t D,
-                            const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, float lr_t, float beta1,
-                            float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
+ * dense semantics); adds the number of distinct rows to *n_unique when given.  dup_list: int32[B*F + 1] scratch or NULL --
+ * when given, the claim pass lists the entries that met an already claimed row and the merge walks that list instead of
+ * re-scanning every entry.  B*F < 2^30. */
+int ctr_adam_indexed_slices(float* var, float* m, float* v, int64_t state_stride, const int64_t* field_row_offset, int64_t F, int64_t D,
+                            const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, int32_t* dup_list,
+                            float lr_t, float beta1, float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique,
+                            void* stream);
 
 /* Lookup backward FUSED with that step (the row update without writing row-grads to HBM): computes the
  * IndexedSlices values d_tile + d_fm2*(S - e) of ctr_embed_fm2_bwd in registers and applies the LazyAdam update to every row
@@ -163,15 +169,16 @@ int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field
  * F*D <= 1536, B*F < 2^30.  Same results as ctr_embed_fm2_bwd followed by ctr_adam_indexed_slices. */
 int ctr_embed_fm2_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const int64_t* field_row_offset,
                            const int64_t* ids, int64_t B, int64_t F, int64_t D, float* var, float* m, float* v,
-                           int32_t* slot_of_row, float* dup_grads, int32_t* dup_list, float lr_t, float beta1, float beta2,
+                           int64_t state_stride, int32_t* slot_of_row, float* dup_grads, int32_t* dup_list, float lr_t, float beta1, float beta2,
                            float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
 
 /* The same step for the OWNER side of a row-sharded table: entries are the receive queues filled by ctr_sharded_grad_push --
  * rows (nseg, cap) local row ids, vals (nseg, cap, D) (consumed), counts (nseg,) filled slots per segment; duplicates of a
- * row across and inside segments are summed before the update.  nseg*cap < 2^31. */
-int ctr_adam_rows_dedup(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, float* vals,
-                        const int64_t* counts, int64_t nseg, int64_t cap, int32_t* slot_of_row, float lr_t, float beta1,
-                        float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
+ * row across and inside segments are summed before the update.  dup_list: int32[nseg*cap + 1] scratch or NULL.
+ * nseg*cap < 2^30. */
+int ctr_adam_rows_dedup(float* var, float* m, float* v, int64_t state_stride, int64_t V, int64_t D, const int64_t* rows, float* vals,
+                        const int64_t* counts, int64_t nseg, int64_t cap, int32_t* slot_of_row, int32_t* dup_list, float lr_t,
+                        float beta1, float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream);
 
 /* DeepFM first-order ("wide") term as a D=1 lookup.  Replaces indicator_column multi-hot (B, sum V) @
  * dense(1) (DeepFM/deepfm.py:72-80,180-181): out[b] = bias + sum_f w[field_row_offset[f] + ids[b,f]]; invalid ids add 0.

@@ -42,7 +42,7 @@ SIGNATURES = {
     "ctr_embed_fm2_bwd_push": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "ctr_sharded_grad_push": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "ctr_rows_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, _I, _P]),
-    "ctr_adam_rows": (c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+    "ctr_adam_rows": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                               ctypes.c_float, _P, _P]),
     "ctr_embed_bi_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ctr_embed_bi_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -55,13 +55,13 @@ SIGNATURES = {
     "ctr_bst_param_count": (_I, [_I, _I, _I]),
     "ctr_bst_transformer_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_int, _P, _P]),
     "ctr_bst_transformer_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_int, _P, _P, _P, _P, _P]),
-    "ctr_adam_indexed_slices": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _I, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+    "ctr_adam_indexed_slices": (c_int, [_P, _P, _P, _I, _P, _I, _I, _P, _P, _I, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, _P, _P, _P]),
-    "ctr_embed_fm2_bwd_adam": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, ctypes.c_float, ctypes.c_float,
+    "ctr_embed_fm2_bwd_adam": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, _P, _P, _P]),
-    "ctr_adam_rows_dedup": (c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+    "ctr_adam_rows_dedup": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_float, _P, _P, _P]),
-    "ctr_adam_dense_rest": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P]),
+    "ctr_adam_dense_rest": (c_int, [_P, _P, _P, _I, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P]),
     "ctr_first_order_fwd": (c_int, [_P, _P, _P, _I, _I, ctypes.c_float, _P, _P]),
     "ctr_bag_lookup_fwd": (c_int, [_P, _I, _I, _P, _P, _I, _P, _I, _P]),
     "ctr_bag_lookup_bwd": (c_int, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),

@@ -20,7 +20,7 @@ namespace ctr {
 
 template <int LPR>
 __global__ void __launch_bounds__(256)
-adam_rows_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, long long V,
+adam_rows_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, int SS, long long V,
                  const long long* __restrict__ rows, const float4* __restrict__ grads, const long long* __restrict__ count,
                  long long max_n, float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched) {
   long long n = count ? *count : max_n;
@@ -29,34 +29,35 @@ adam_rows_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __res
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const long long row = __ldg(rows + t / LPR);
     if (row < 0 || row >= V) continue;
-    const size_t off = (size_t)row * LPR + t % LPR;
+    const size_t off = (size_t)row * LPR + t % LPR, so = (size_t)row * SS + t % LPR;
     const float4 g = ldg_stream_f4(grads + t);
-    float4 mm = m[off], vv = v[off], w = var[off];
+    float4 mm = m[so], vv = v[so], w = var[off];
     mm.x = b1 * mm.x + (1.f - b1) * g.x; mm.y = b1 * mm.y + (1.f - b1) * g.y;
     mm.z = b1 * mm.z + (1.f - b1) * g.z; mm.w = b1 * mm.w + (1.f - b1) * g.w;
     vv.x = b2 * vv.x + (1.f - b2) * g.x * g.x; vv.y = b2 * vv.y + (1.f - b2) * g.y * g.y;
     vv.z = b2 * vv.z + (1.f - b2) * g.z * g.z; vv.w = b2 * vv.w + (1.f - b2) * g.w * g.w;
     w.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); w.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
     w.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); w.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
-    m[off] = mm; v[off] = vv; var[off] = w;
+    m[so] = mm; v[so] = vv; var[off] = w;
     if (touched != nullptr && t % LPR == 0) atomicOr(touched + (row >> 5), 1u << (row & 31));
   }
 }
 
 template <int LPR>
 __global__ void __launch_bounds__(256)
-adam_dense_rest_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, long long V, float lr_t,
+adam_dense_rest_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, int SS, long long V, float lr_t,
                        float b1, float b2, float eps, const unsigned int* __restrict__ touched) {
   const size_t total = (size_t)V * LPR;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const long long row = (long long)(t / LPR);
     if (touched != nullptr && (__ldg(touched + (row >> 5)) >> (row & 31)) & 1u) continue;   // done by adam_rows_kernel
-    float4 mm = ldg_stream_f4(m + t), vv = ldg_stream_f4(v + t), w = ldg_stream_f4(var + t);
+    const size_t so = (size_t)row * SS + t % LPR;
+    float4 mm = ldg_stream_f4(m + so), vv = ldg_stream_f4(v + so), w = ldg_stream_f4(var + t);
     mm.x *= b1; mm.y *= b1; mm.z *= b1; mm.w *= b1;
     vv.x *= b2; vv.y *= b2; vv.z *= b2; vv.w *= b2;
     w.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); w.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
     w.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); w.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
-    stg_stream_f4(m + t, mm); stg_stream_f4(v + t, vv); stg_stream_f4(var + t, w);
+    stg_stream_f4(m + so, mm); stg_stream_f4(v + so, vv); stg_stream_f4(var + t, w);
   }
 }
 
@@ -67,6 +68,7 @@ adam_dense_rest_kernel(float4* __restrict__ var, float4* __restrict__ m, float4*
 // bitmap).  Three launches on one stream, no host round trip; row_grads is consumed (clobbered).
 // Where the entries of one step come from: the (B,F) id matrix of an IndexedSlices (row = field offset + local id), or the
 // receive queues of a row-sharded table (nseg segments of `cap` (row, value) slots, counts[seg] of them filled).
+constexpr int DUP_FLAG = 0x40000000;   // set in slot_of_row[row] when a second entry of the batch meets an already claimed row
 struct EntrySrc {
   const long long* ids;      // (B,F) local ids | (nseg, cap) local rows
   const long long* off;      // (F+1,) field row offsets | nullptr
@@ -93,6 +95,31 @@ adam_claim_kernel(const EntrySrc src, long long n, int* __restrict__ slot) {
   }
 }
 
+// claim that also LISTS the losing entries (rows met a second time): the merge then walks that list (a few per cent of the
+// entries with uniform ids) instead of re-scanning every entry and its slot
+__global__ void __launch_bounds__(256)
+adam_claim_list_kernel(const EntrySrc src, long long n, int* __restrict__ slot, int* __restrict__ dup_list, int* __restrict__ n_dup) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = entry_row(src, e);
+    if (row >= 0 && atomicCAS(slot + row, -1, (int)e) != -1) {
+      atomicOr(slot + row, DUP_FLAG);
+      dup_list[atomicAdd(n_dup, 1)] = (int)e;
+    }
+  }
+}
+template <int LPR>
+__global__ void __launch_bounds__(256)
+adam_merge_list_kernel(const EntrySrc src, const int* __restrict__ slot, float4* __restrict__ grads, const int* __restrict__ dup_list,
+                       const int* __restrict__ n_dup) {
+  const size_t total = (size_t)(*n_dup) * LPR;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int e = __ldg(dup_list + t / LPR);
+    const long long row = entry_row(src, e);
+    const int w = __ldg(slot + row) & ~DUP_FLAG;
+    atomicAdd(grads + (size_t)w * LPR + t % LPR, grads[(size_t)e * LPR + t % LPR]);
+  }
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(256)
 adam_merge_kernel(const EntrySrc src, long long n, const int* __restrict__ slot, float4* __restrict__ grads) {
@@ -108,7 +135,7 @@ adam_merge_kernel(const EntrySrc src, long long n, const int* __restrict__ slot,
 
 template <int LPR>
 __global__ void __launch_bounds__(256)
-adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, const EntrySrc src, long long n,
+adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, int SS, const EntrySrc src, long long n,
                    int* __restrict__ slot, const float4* __restrict__ grads,
                    float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched, long long* __restrict__ n_unique) {
   const size_t total = (size_t)n * LPR;
@@ -122,20 +149,20 @@ adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __r
     if (t < total) {
       const long long e = (long long)(t / LPR);
       row = entry_row(src, e);
-      win = row >= 0 && slot[row] == (int)e;
+      win = row >= 0 && (slot[row] & ~DUP_FLAG) == (int)e;
     }
     __syncwarp();
     if (!win) continue;
-    const size_t o = (size_t)row * LPR + t % LPR;
+    const size_t o = (size_t)row * LPR + t % LPR, so = (size_t)row * SS + t % LPR;
     const float4 g = ldg_stream_f4(grads + t);
-    float4 mm = m[o], vv = v[o], w = var[o];
+    float4 mm = m[so], vv = v[so], w = var[o];
     mm.x = b1 * mm.x + (1.f - b1) * g.x; mm.y = b1 * mm.y + (1.f - b1) * g.y;
     mm.z = b1 * mm.z + (1.f - b1) * g.z; mm.w = b1 * mm.w + (1.f - b1) * g.w;
     vv.x = b2 * vv.x + (1.f - b2) * g.x * g.x; vv.y = b2 * vv.y + (1.f - b2) * g.y * g.y;
     vv.z = b2 * vv.z + (1.f - b2) * g.z * g.z; vv.w = b2 * vv.w + (1.f - b2) * g.w * g.w;
     w.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); w.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
     w.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); w.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
-    m[o] = mm; v[o] = vv; var[o] = w;
+    m[so] = mm; v[so] = vv; var[o] = w;
     if (t % LPR == 0) {
       slot[row] = -1;
       if (touched != nullptr) atomicOr(touched + (row >> 5), 1u << (row & 31));
@@ -154,8 +181,6 @@ adam_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __r
 // ids), applies Adam on the spot: row_grads is neither written nor re-read.  Rows referenced more than once park their
 // values in `dup_grads` and their entry index in `dup_list`; two list-driven launches (merge into the claiming entry, update)
 // finish them with the SUMMED gradient, exactly like the unfused path.
-constexpr int DUP_FLAG = 0x40000000;
-
 __global__ void __launch_bounds__(256)
 adam_claim_dup_kernel(const EntrySrc src, long long n, int* __restrict__ slot) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -179,7 +204,7 @@ template <int LPR, int HOLD>
 __global__ void __launch_bounds__(256, 1)
 embed_fm2_bwd_adam_kernel(const float4* __restrict__ tile, const float4* __restrict__ d_tile, const float* __restrict__ d_fm2,
                           const long long* __restrict__ row_off, const long long* __restrict__ ids, int B, int F,
-                          float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, int* __restrict__ slot,
+                          float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, int SS, int* __restrict__ slot,
                           float4* __restrict__ dup_grads, int* __restrict__ dup_list, int* __restrict__ n_dup,
                           float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched,
                           long long* __restrict__ n_unique) {
@@ -229,8 +254,8 @@ embed_fm2_bwd_adam_kernel(const float4* __restrict__ tile, const float4* __restr
         dt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < HOLD && j < n4 && dt_row != nullptr) dt[u] = ldg_stream_f4(dt_row + j);
         if (k < HOLD && row[k] >= 0 && !(s[k] & DUP_FLAG)) {
-          const size_t o = (size_t)row[k] * LPR + c;
-          mm[u] = m[o]; vv[u] = v[o]; ww[u] = var[o];
+          const size_t o = (size_t)row[k] * LPR + c, so = (size_t)row[k] * SS + c;
+          mm[u] = m[so]; vv[u] = v[so]; ww[u] = var[o];
         }
       }
 #pragma unroll
@@ -242,9 +267,9 @@ embed_fm2_bwd_adam_kernel(const float4* __restrict__ tile, const float4* __restr
         r.z = dt[u].z + g * (S.z - e[k].z); r.w = dt[u].w + g * (S.w - e[k].w);
         const int entry = b * F + j / LPR;
         if (!(s[k] & DUP_FLAG)) {
-          const size_t o = (size_t)row[k] * LPR + c;
+          const size_t o = (size_t)row[k] * LPR + c, so = (size_t)row[k] * SS + c;
           adam_apply(ww[u], mm[u], vv[u], r, lr_t, b1, b2, eps);
-          m[o] = mm[u]; v[o] = vv[u]; var[o] = ww[u];
+          m[so] = mm[u]; v[so] = vv[u]; var[o] = ww[u];
           if (c == 0) {
             slot[row[k]] = -1;
             if (touched != nullptr) atomicOr(touched + (row[k] >> 5), 1u << (row[k] & 31));
@@ -279,7 +304,7 @@ adam_dup_merge_kernel(const EntrySrc src, const int* __restrict__ slot, float4* 
 // ... then UPDATE by the claiming entries
 template <int LPR>
 __global__ void __launch_bounds__(256)
-adam_dup_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, const EntrySrc src,
+adam_dup_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __restrict__ v, int SS, const EntrySrc src,
                        int* __restrict__ slot, const float4* __restrict__ dup_grads, const int* __restrict__ dup_list,
                        const int* __restrict__ n_dup, float lr_t, float b1, float b2, float eps, unsigned int* __restrict__ touched,
                        long long* __restrict__ n_unique) {
@@ -297,11 +322,11 @@ adam_dup_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4*
     }
     __syncwarp();                      // every lane of an entry has read the slot before its lane 0 clears it
     if (!win) continue;
-    const size_t o = (size_t)row * LPR + t % LPR;
+    const size_t o = (size_t)row * LPR + t % LPR, so = (size_t)row * SS + t % LPR;
     const float4 g = dup_grads[(size_t)e * LPR + t % LPR];
-    float4 mm = m[o], vv = v[o], w = var[o];
+    float4 mm = m[so], vv = v[so], w = var[o];
     adam_apply(w, mm, vv, g, lr_t, b1, b2, eps);
-    m[o] = mm; v[o] = vv; var[o] = w;
+    m[so] = mm; v[so] = vv; var[o] = w;
     if (t % LPR == 0) {
       slot[row] = -1;
       if (touched != nullptr) atomicOr(touched + (row >> 5), 1u << (row & 31));
@@ -314,6 +339,15 @@ adam_dup_update_kernel(float4* __restrict__ var, float4* __restrict__ m, float4*
   }
 }
 
+// state_stride: floats between consecutive rows of m (and of v).  D = two separate (V, D) tables; 2*D = ONE interleaved
+// (V, 2, D) buffer with v = m + D: a row's two moments then share a DRAM page, which is what the random row updates are
+// bound by (measured access-rate limit ~30 G rows/s) -- 4 instead of 6 row activations per updated row.
+static int check_stride(const char* fn, int64_t D, int64_t state_stride) {
+  CTR_REQUIRE(state_stride >= D && state_stride % 4 == 0 && state_stride <= (1LL << 20), "%s: state_stride=%lld must be a multiple of 4 and >= D",
+              fn, (long long)state_stride);
+  return CTR_OK;
+}
+
 static int check_adam(const char* fn, int64_t V, int64_t D) {
   CTR_REQUIRE(V >= 0, "%s: bad V", fn);
   CTR_UNSUPPORTED(D % 4 != 0 || D > 128 || (D & (D - 1)) != 0, "%s: D=%lld unsupported (power of two in 4..128)", fn, (long long)D);
@@ -324,53 +358,61 @@ static int check_adam(const char* fn, int64_t V, int64_t D) {
 
 using namespace ctr;
 
-extern "C" int ctr_adam_rows(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, const float* grads,
+extern "C" int ctr_adam_rows(float* var, float* m, float* v, int64_t state_stride, int64_t V, int64_t D, const int64_t* rows, const float* grads,
                              const int64_t* count, int64_t max_n, float lr_t, float beta1, float beta2, float eps,
                              uint32_t* touched_bitmap, void* stream) {
   int rc = check_adam("ctr_adam_rows", V, D);
   if (rc) return rc;
+  if ((rc = check_stride("ctr_adam_rows", D, state_stride))) return rc;
   CTR_REQUIRE(var && m && v && rows && grads && max_n >= 0, "ctr_adam_rows: null argument / bad size");
   CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(grads), "ctr_adam_rows: buffers must be 16-byte aligned");
   if (max_n == 0) return CTR_OK;
   cudaStream_t st = as_stream(stream);
   const long long total = (long long)max_n * (D / 4);
   const int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
-#define GO(L) adam_rows_kernel<L><<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), V, reinterpret_cast<const long long*>(rows), reinterpret_cast<const float4*>(grads), reinterpret_cast<const long long*>(count), max_n, lr_t, beta1, beta2, eps, touched_bitmap)
+#define GO(L) adam_rows_kernel<L><<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), (int)(state_stride / 4), V, reinterpret_cast<const long long*>(rows), reinterpret_cast<const float4*>(grads), reinterpret_cast<const long long*>(count), max_n, lr_t, beta1, beta2, eps, touched_bitmap)
   switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
 #undef GO
   CTR_CHECK_LAUNCH("ctr_adam_rows");
   return CTR_OK;
 }
 
-extern "C" int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t V, int64_t D, float lr_t, float beta1, float beta2,
+extern "C" int ctr_adam_dense_rest(float* var, float* m, float* v, int64_t state_stride, int64_t V, int64_t D, float lr_t, float beta1, float beta2,
                                    float eps, const uint32_t* touched_bitmap, void* stream) {
   int rc = check_adam("ctr_adam_dense_rest", V, D);
   if (rc) return rc;
+  if ((rc = check_stride("ctr_adam_dense_rest", D, state_stride))) return rc;
   CTR_REQUIRE(var && m && v, "ctr_adam_dense_rest: null argument");
   CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v), "ctr_adam_dense_rest: buffers must be 16-byte aligned");
   if (V == 0) return CTR_OK;
   cudaStream_t st = as_stream(stream);
   const long long total = (long long)V * (D / 4);
   const int grid = (int)((total + 255) / 256 < (long long)sm_count() * 32 ? (total + 255) / 256 : (long long)sm_count() * 32);
-#define GO(L) adam_dense_rest_kernel<L><<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), V, lr_t, beta1, beta2, eps, touched_bitmap)
+#define GO(L) adam_dense_rest_kernel<L><<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), (int)(state_stride / 4), V, lr_t, beta1, beta2, eps, touched_bitmap)
   switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
 #undef GO
   CTR_CHECK_LAUNCH("ctr_adam_dense_rest");
   return CTR_OK;
 }
 
-static int adam_dedup_launch(const char* fn, float* var, float* m, float* v, int64_t D, const EntrySrc& src, long long n,
-                             float* vals, int32_t* slot_of_row, float lr_t, float beta1, float beta2, float eps,
+static int adam_dedup_launch(const char* fn, float* var, float* m, float* v, int64_t state_stride, int64_t D, const EntrySrc& src, long long n,
+                             float* vals, int32_t* slot_of_row, int32_t* dup_list, float lr_t, float beta1, float beta2, float eps,
                              uint32_t* touched_bitmap, int64_t* n_unique, cudaStream_t st) {
   const long long total = n * (D / 4);
   auto cap = [](long long want, long long lim) { return (int)(want < lim ? want : lim); };
   const int grid_e = cap((n + 255) / 256, (long long)sm_count() * 16), grid_t = cap((total + 255) / 256, (long long)sm_count() * 16);
   auto* g4 = reinterpret_cast<float4*>(vals);
-  adam_claim_kernel<<<grid_e, 256, 0, st>>>(src, n, slot_of_row);
+  if (dup_list != nullptr) {
+    CTR_CUDA(cudaMemsetAsync(dup_list + n, 0, sizeof(int32_t), st));
+    adam_claim_list_kernel<<<grid_e, 256, 0, st>>>(src, n, slot_of_row, dup_list, dup_list + n);
+  } else {
+    adam_claim_kernel<<<grid_e, 256, 0, st>>>(src, n, slot_of_row);
+  }
 #define GO(L)                                                                                                               \
-  adam_merge_kernel<L><<<grid_t, 256, 0, st>>>(src, n, slot_of_row, g4);                                                    \
+  if (dup_list != nullptr) adam_merge_list_kernel<L><<<sm_count() * 2, 256, 0, st>>>(src, slot_of_row, g4, dup_list, dup_list + n); \
+  else adam_merge_kernel<L><<<grid_t, 256, 0, st>>>(src, n, slot_of_row, g4);                                               \
   adam_update_kernel<L><<<grid_t, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),               \
-                                                reinterpret_cast<float4*>(v), src, n, slot_of_row, g4, lr_t, beta1, beta2,  \
+                                                reinterpret_cast<float4*>(v), (int)(state_stride / 4), src, n, slot_of_row, g4, lr_t, beta1, beta2,  \
                                                 eps, touched_bitmap, reinterpret_cast<long long*>(n_unique))
   switch (D / 4) { case 1: GO(1); break; case 2: GO(2); break; case 4: GO(4); break; case 8: GO(8); break; case 16: GO(16); break; default: GO(32); break; }
 #undef GO
@@ -379,39 +421,42 @@ static int adam_dedup_launch(const char* fn, float* var, float* m, float* v, int
   return CTR_OK;
 }
 
-extern "C" int ctr_adam_indexed_slices(float* var, float* m, float* v, const int64_t* field_row_offset, int64_t F, int64_t D,
-                                       const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, float lr_t,
-                                       float beta1, float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique,
-                                       void* stream) {
+extern "C" int ctr_adam_indexed_slices(float* var, float* m, float* v, int64_t state_stride, const int64_t* field_row_offset, int64_t F, int64_t D,
+                                       const int64_t* ids, float* row_grads, int64_t B, int32_t* slot_of_row, int32_t* dup_list,
+                                       float lr_t, float beta1, float beta2, float eps, uint32_t* touched_bitmap,
+                                       int64_t* n_unique, void* stream) {
   int rc = check_adam("ctr_adam_indexed_slices", 0, D);
   if (rc) return rc;
+  if ((rc = check_stride("ctr_adam_indexed_slices", D, state_stride))) return rc;
   CTR_REQUIRE(var && m && v && field_row_offset && ids && row_grads && slot_of_row, "ctr_adam_indexed_slices: null argument");
-  CTR_REQUIRE(B >= 0 && F >= 1 && F <= (1 << 20) && B * F < (1LL << 31), "ctr_adam_indexed_slices: bad B/F (B*F must be < 2^31)");
+  CTR_REQUIRE(B >= 0 && F >= 1 && F <= (1 << 20) && B * F < (1LL << 30), "ctr_adam_indexed_slices: bad B/F (B*F must be < 2^30)");
   CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(row_grads),
               "ctr_adam_indexed_slices: buffers must be 16-byte aligned");
   if (B == 0) return CTR_OK;
   EntrySrc src = {reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(field_row_offset), nullptr, 0, 0, (int)F};
-  return adam_dedup_launch("ctr_adam_indexed_slices", var, m, v, D, src, B * F, row_grads, slot_of_row, lr_t, beta1, beta2, eps,
+  return adam_dedup_launch("ctr_adam_indexed_slices", var, m, v, state_stride, D, src, B * F, row_grads, slot_of_row, dup_list, lr_t, beta1, beta2, eps,
                            touched_bitmap, n_unique, as_stream(stream));
 }
 
-extern "C" int ctr_adam_rows_dedup(float* var, float* m, float* v, int64_t V, int64_t D, const int64_t* rows, float* vals,
-                                   const int64_t* counts, int64_t nseg, int64_t cap, int32_t* slot_of_row, float lr_t, float beta1,
-                                   float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream) {
+extern "C" int ctr_adam_rows_dedup(float* var, float* m, float* v, int64_t state_stride, int64_t V, int64_t D, const int64_t* rows, float* vals,
+                                   const int64_t* counts, int64_t nseg, int64_t cap, int32_t* slot_of_row, int32_t* dup_list,
+                                   float lr_t, float beta1, float beta2, float eps, uint32_t* touched_bitmap, int64_t* n_unique,
+                                   void* stream) {
   int rc = check_adam("ctr_adam_rows_dedup", V, D);
   if (rc) return rc;
+  if ((rc = check_stride("ctr_adam_rows_dedup", D, state_stride))) return rc;
   CTR_REQUIRE(var && m && v && rows && vals && counts && slot_of_row, "ctr_adam_rows_dedup: null argument");
-  CTR_REQUIRE(nseg >= 1 && cap >= 0 && nseg * cap < (1LL << 31), "ctr_adam_rows_dedup: bad nseg/cap (nseg*cap must be < 2^31)");
+  CTR_REQUIRE(nseg >= 1 && cap >= 0 && nseg * cap < (1LL << 30), "ctr_adam_rows_dedup: bad nseg/cap (nseg*cap must be < 2^30)");
   CTR_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(vals), "ctr_adam_rows_dedup: buffers must be 16-byte aligned");
   if (cap == 0 || V == 0) return CTR_OK;
   EntrySrc src = {reinterpret_cast<const long long*>(rows), nullptr, reinterpret_cast<const long long*>(counts), cap, V, 0};
-  return adam_dedup_launch("ctr_adam_rows_dedup", var, m, v, D, src, nseg * cap, vals, slot_of_row, lr_t, beta1, beta2, eps,
+  return adam_dedup_launch("ctr_adam_rows_dedup", var, m, v, state_stride, D, src, nseg * cap, vals, slot_of_row, dup_list, lr_t, beta1, beta2, eps,
                            touched_bitmap, n_unique, as_stream(stream));
 }
 
 template <int LPR, int HOLD>
 static int launch_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const EntrySrc& src, int64_t B, int64_t F,
-                           float* var, float* m, float* v, int32_t* slot, float* dup_grads, int32_t* dup_list, float lr_t, float b1,
+                           float* var, float* m, float* v, int SS, int32_t* slot, float* dup_grads, int32_t* dup_list, float lr_t, float b1,
                            float b2, float eps, uint32_t* touched, int64_t* n_unique, cudaStream_t st) {
   auto k = embed_fm2_bwd_adam_kernel<LPR, HOLD>;
   int per_sm = 1;
@@ -421,12 +466,12 @@ static int launch_bwd_adam(const float* tile, const float* d_tile, const float* 
   int* n_dup = dup_list + B * F;
   k<<<(int)grid, 256, 0, st>>>(reinterpret_cast<const float4*>(tile), reinterpret_cast<const float4*>(d_tile), d_fm2, src.off, src.ids,
                                (int)B, (int)F, reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),
-                               reinterpret_cast<float4*>(v), slot, reinterpret_cast<float4*>(dup_grads), dup_list, n_dup, lr_t, b1, b2,
+                               reinterpret_cast<float4*>(v), SS, slot, reinterpret_cast<float4*>(dup_grads), dup_list, n_dup, lr_t, b1, b2,
                                eps, touched, reinterpret_cast<long long*>(n_unique));
   const int g2 = sm_count() * 2;
   adam_dup_merge_kernel<LPR><<<g2, 256, 0, st>>>(src, slot, reinterpret_cast<float4*>(dup_grads), dup_list, n_dup);
   adam_dup_update_kernel<LPR><<<g2, 256, 0, st>>>(reinterpret_cast<float4*>(var), reinterpret_cast<float4*>(m),
-                                                  reinterpret_cast<float4*>(v), src, slot, reinterpret_cast<const float4*>(dup_grads),
+                                                  reinterpret_cast<float4*>(v), SS, src, slot, reinterpret_cast<const float4*>(dup_grads),
                                                   dup_list, n_dup, lr_t, b1, b2, eps, touched, reinterpret_cast<long long*>(n_unique));
   CTR_CHECK_LAUNCH("ctr_embed_fm2_bwd_adam");
   count_launch(2);
@@ -435,10 +480,10 @@ static int launch_bwd_adam(const float* tile, const float* d_tile, const float* 
 
 template <int LPR>
 static int dispatch_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const EntrySrc& src, int64_t B, int64_t F,
-                             float* var, float* m, float* v, int32_t* slot, float* dup_grads, int32_t* dup_list, float lr_t, float b1,
+                             float* var, float* m, float* v, int SS, int32_t* slot, float* dup_grads, int32_t* dup_list, float lr_t, float b1,
                              float b2, float eps, uint32_t* touched, int64_t* n_unique, cudaStream_t st) {
   const int64_t per_lane = (F * LPR + 31) / 32;
-#define GO(H) return launch_bwd_adam<LPR, H>(tile, d_tile, d_fm2, src, B, F, var, m, v, slot, dup_grads, dup_list, lr_t, b1, b2, eps, touched, n_unique, st)
+#define GO(H) return launch_bwd_adam<LPR, H>(tile, d_tile, d_fm2, src, B, F, var, m, v, SS, slot, dup_grads, dup_list, lr_t, b1, b2, eps, touched, n_unique, st)
   if (per_lane <= 4) GO(4);
   if (per_lane <= 8) GO(8);
   if (per_lane <= 12) GO(12);
@@ -450,10 +495,11 @@ static int dispatch_bwd_adam(const float* tile, const float* d_tile, const float
 
 extern "C" int ctr_embed_fm2_bwd_adam(const float* tile, const float* d_tile, const float* d_fm2, const int64_t* field_row_offset,
                                       const int64_t* ids, int64_t B, int64_t F, int64_t D, float* var, float* m, float* v,
-                                      int32_t* slot_of_row, float* dup_grads, int32_t* dup_list, float lr_t, float beta1, float beta2,
+                                      int64_t state_stride, int32_t* slot_of_row, float* dup_grads, int32_t* dup_list, float lr_t, float beta1, float beta2,
                                       float eps, uint32_t* touched_bitmap, int64_t* n_unique, void* stream) {
   int rc = check_adam("ctr_embed_fm2_bwd_adam", 0, D);
   if (rc) return rc;
+  if ((rc = check_stride("ctr_embed_fm2_bwd_adam", D, state_stride))) return rc;
   CTR_REQUIRE(tile && field_row_offset && ids && var && m && v && slot_of_row && dup_grads && dup_list,
               "ctr_embed_fm2_bwd_adam: null argument");
   CTR_REQUIRE(B >= 0 && F >= 1 && F <= 65536 && B * F < (1LL << 30), "ctr_embed_fm2_bwd_adam: bad B/F (B*F must be < 2^30)");
@@ -468,9 +514,9 @@ extern "C" int ctr_embed_fm2_bwd_adam(const float* tile, const float* d_tile, co
   adam_claim_dup_kernel<<<grid_e, 256, 0, st>>>(src, n, slot_of_row);
   count_launch(1);
   switch (D / 4) {
-#define GO(L) case L: return dispatch_bwd_adam<L>(tile, d_tile, d_fm2, src, B, F, var, m, v, slot_of_row, dup_grads, dup_list, lr_t, beta1, beta2, eps, touched_bitmap, n_unique, st)
+#define GO(L) case L: return dispatch_bwd_adam<L>(tile, d_tile, d_fm2, src, B, F, var, m, v, (int)(state_stride / 4), slot_of_row, dup_grads, dup_list, lr_t, beta1, beta2, eps, touched_bitmap, n_unique, st)
     GO(1); GO(2); GO(4); GO(8); GO(16);
-    default: return dispatch_bwd_adam<32>(tile, d_tile, d_fm2, src, B, F, var, m, v, slot_of_row, dup_grads, dup_list, lr_t, beta1, beta2, eps, touched_bitmap, n_unique, st);
+    default: return dispatch_bwd_adam<32>(tile, d_tile, d_fm2, src, B, F, var, m, v, (int)(state_stride / 4), slot_of_row, dup_grads, dup_list, lr_t, beta1, beta2, eps, touched_bitmap, n_unique, st);
 #undef GO
   }
 }

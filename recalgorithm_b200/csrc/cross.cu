@@ -282,6 +282,130 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
   }
 }
 
+// Backward, register form (the common case: xl_in == x0 chain, L <= 4, d % 4 == 0): NO per-iteration block phases.
+// With xs == x0 the batch reductions factor through per-sample scalars:
+//     dw_l[i] = sum_q x0[q,i] * a_l(q)  +  cb_l[i] * T_l          a_l = (1 + sum_{k<l} s_k) * t_l ,  T_l = sum_q t_l(q)
+//     db_l[i] = sum_q g_out[q,i]        +  sum_{k>l} w_k[i] * T_k
+// so the warp that owns a sample adds x0*a_l and g_out into lane-owned register accumulators (columns of the lane) while the
+// values are still in its registers; nothing is staged in shared memory, there is no thread-per-column phase and no
+// __syncthreads in the loop (the first form spent ~60 % of its issue slots in that phase and two block syncs per 8 samples).
+// The next sample's x0 / g_out are fetched one iteration ahead.  Per CTA: one shared-memory reduction, then the cb / w terms
+// and one fp32 atomic per element.
+template <int N, int LM>
+__global__ void __launch_bounds__(CROSS_WARPS * 32)
+cross_bwd_reg_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ b,
+                     const float* __restrict__ g_out, int B, int d, int L, float* __restrict__ dx0,
+                     float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int NV = N * 4;
+  extern __shared__ __align__(16) float smem[];
+  float* sw = smem;                                  // (L, d)  weights
+  float* sb = sw + (size_t)L * d;                    // (L, d)  biases, then prefix biases cb_l in place at the end
+  float* rdw = sb + (size_t)L * d;                   // (L, d)  CTA accumulator of sum_q x0*a_l
+  float* rG = rdw + (size_t)L * d;                   // (d)     CTA accumulator of sum_q g_out
+  float* rT = rG + d;                                // (LM)    CTA accumulator of T_l
+  for (int i = threadIdx.x; i < L * d; i += blockDim.x) { sw[i] = __ldg(w + i); sb[i] = __ldg(b + i); rdw[i] = 0.f; }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) rG[i] = 0.f;
+  if (threadIdx.x < LM) rT[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float acc_a[LM][NV], acc_g[NV], T[LM];
+#pragma unroll
+  for (int l = 0; l < LM; ++l) {
+    T[l] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc_a[l][k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc_g[k] = 0.f;
+  LaneVec<4, N> na0, ng;
+  if (warp0 < B) { na0.load(x0 + (size_t)warp0 * d, d, lane); ng.load(g_out + (size_t)warp0 * d, d, lane); }
+  for (int s = warp0; s < B; s += nwarps) {
+    LaneVec<4, N> a0 = na0, g = ng, x;
+    if (s + nwarps < B) { na0.load(x0 + (size_t)(s + nwarps) * d, d, lane); ng.load(g_out + (size_t)(s + nwarps) * d, d, lane); }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { x.v[k] = a0.v[k]; acc_g[k] += g.v[k]; }
+    // forward recurrence -> s_l and the prefix sums cs_l
+    float sl[LM], cs[LM], run = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      sl[l] = 0.f; cs[l] = 0.f;
+      if (l < L) {
+        float wv[NV], bv[NV];
+        lane_load_smem<4, N>(wv, sw + (size_t)l * d, d, lane);
+        lane_load_smem<4, N>(bv, sb + (size_t)l * d, d, lane);
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dot += x.v[k] * wv[k];
+        dot = warp_sum(dot);
+        sl[l] = dot; cs[l] = run; run += dot;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) x.v[k] = (a0.v[k] * dot + bv[k]) + x.v[k];
+      }
+    }
+    // backward walk; x is reused as the dx0 accumulator
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x.v[k] = 0.f;
+#pragma unroll
+    for (int l = LM - 1; l >= 0; --l) {
+      if (l < L) {
+        float wv[NV];
+        lane_load_smem<4, N>(wv, sw + (size_t)l * d, d, lane);
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) t += g.v[k] * a0.v[k];
+        t = warp_sum(t);
+        T[l] += t;
+        const float a = (cs[l] + 1.f) * t;            // x_l = x0*(1 + cs_l) + cb_l
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          acc_a[l][k] += a0.v[k] * a;
+          x.v[k] += g.v[k] * sl[l];
+          g.v[k] += t * wv[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x.v[k] += g.v[k];    // xl_in == x0: d(x0) also receives g_0
+    x.store(dx0 + (size_t)s * d, d, lane);
+  }
+  // ---- CTA reduction of the lane-owned accumulators, then the factored terms and one atomic per element
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = ((k >> 2) * 32 + lane) * 4 + (k & 3);
+    if (i < d) {
+      atomicAdd(rG + i, acc_g[k]);
+#pragma unroll
+      for (int l = 0; l < LM; ++l)
+        if (l < L) atomicAdd(rdw + (size_t)l * d + i, acc_a[l][k]);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < LM; ++l)
+      if (l < L) atomicAdd(rT + l, T[l]);           // T is warp-uniform
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    float cb = 0.f, wsum = 0.f;                      // cb_l = sum_{k<l} b_k ; wsum = sum_{k>l} w_k*T_k built from the top
+    float dbv[LM];
+#pragma unroll
+    for (int l = LM - 1; l >= 0; --l) {
+      dbv[l] = 0.f;
+      if (l < L) { dbv[l] = rG[i] + wsum; wsum += sw[(size_t)l * d + i] * rT[l]; }
+    }
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      if (l < L) {
+        atomicAdd(dw + (size_t)l * d + i, rdw[(size_t)l * d + i] + cb * rT[l]);
+        atomicAdd(db + (size_t)l * d + i, dbv[l]);
+        cb += sb[(size_t)l * d + i];
+      }
+    }
+  }
+}
+
 static size_t cross_bwd_smem(int64_t d, int64_t L, bool has_xl, bool prefetch) {
   return sizeof(float) * ((size_t)3 * L * d + (size_t)(prefetch ? 2 : 1) * (has_xl ? 3 : 2) * CROSS_WARPS * d +
                           2 * CROSS_WARPS * CROSS_LMAX);     // sized for the larger layer bound
@@ -308,6 +432,27 @@ template <int VEC, int N, int CPT>
 static int launch_cross_bwd(const float* x0, const float* xl_in, const float* w, const float* b, const float* g,
                             int64_t B, int64_t d, int64_t L, float* dx0, float* dxl, float* dw, float* db,
                             cudaStream_t st) {
+  if constexpr (VEC == 4 && N <= 4) {                  // d <= 512: the lane-owned accumulators fit the register file
+    if (xl_in == nullptr && L <= 4) {                  // the chain every reference model builds (DCN/dcn.py:157-160)
+      const size_t smem_r = sizeof(float) * ((size_t)3 * L * d + d + 8);
+      if (smem_r <= 200 * 1024) {
+        auto kr = L <= 1 ? cross_bwd_reg_kernel<N, 1> : L == 2 ? cross_bwd_reg_kernel<N, 2> : L == 3 ? cross_bwd_reg_kernel<N, 3>
+                                                                                                        : cross_bwd_reg_kernel<N, 4>;
+        if (smem_r > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr, CROSS_WARPS * 32, smem_r);
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)per_sm * sm_count();
+        const long long need = (B + CROSS_WARPS - 1) / CROSS_WARPS;
+        if (grid > need) grid = need;
+        CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * L * d, st));
+        CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * L * d, st));
+        kr<<<(int)grid, CROSS_WARPS * 32, smem_r, st>>>(x0, w, b, g, (int)B, (int)d, (int)L, dx0, dw, db);
+        CTR_CHECK_LAUNCH("ctr_cross_bwd");
+        return CTR_OK;
+      }
+    }
+  }
   // double-buffered cp.async staging needs 16-byte rows (VEC == 4) and has to fit next to the parameter tables
   const bool pf = VEC == 4 && cross_bwd_smem(d, L, xl_in != nullptr, true) <= 160 * 1024;
   // LM = compile-time bound of the unrolled layer loops (predicated-off iterations still issue): 4 covers the reference's sweeps

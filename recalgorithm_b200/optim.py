@@ -29,11 +29,16 @@ class TableAdam:
         if fused_backward:
             tables._fused_opt = self
         w = tables.weight
-        self.m, self.v = torch.zeros_like(w), torch.zeros_like(w)
+        # the two moments of a row live side by side ((V, 2, D): one DRAM page per row instead of two -- the random row
+        # updates are bound by the row-activation rate, not the bus); self.m / self.v are views
+        self.mv = torch.zeros((w.shape[0], 2, w.shape[1]), dtype=torch.float32, device=w.device)
+        self.m, self.v = self.mv[:, 0, :], self.mv[:, 1, :]
+        self._ss = 2 * w.shape[1]
         self.t = 0
         self._bitmap = None if lazy else torch.zeros(((tables.num_rows + 31) // 32,), dtype=torch.int32, device=w.device)
         self._slot = torch.full((tables.num_rows,), -1, dtype=torch.int32, device=w.device)   # -1 between steps
         self._n_unique = torch.zeros((1,), dtype=torch.int64, device=w.device)
+        self._dup_list = None
 
     def apply_fused(self, tile, d_tile, d_fm2, ids) -> None:
         """Called by the lookup's backward (fused_backward=True): backward + row update in one pass."""
@@ -56,7 +61,7 @@ class TableAdam:
         ops._chk(d_fm2, torch.float32, "d_fm2", (B,))
         _lib.check(_lib.lib().ctr_embed_fm2_bwd_adam(ops._ptr(tile), ops._ptr(d_tile), ops._ptr(d_fm2), tb.field_row_offset.data_ptr(),
                                                      ops._ptr(ids), B, F, D, w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                                     self._slot.data_ptr(), self._dup[0].data_ptr(), self._dup[1].data_ptr(), lr_t,
+                                                     self._ss, self._slot.data_ptr(), self._dup[0].data_ptr(), self._dup[1].data_ptr(), lr_t,
                                                      self.b1, self.b2, self.eps, ops._ptr(self._bitmap), self._n_unique.data_ptr(),
                                                      ops._stream()))
         self._fused_applied = True
@@ -73,8 +78,8 @@ class TableAdam:
                 raise RuntimeError("TableAdam(fused_backward=True).step() without a lookup backward since the last step")
             lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
             if not self.lazy:
-                _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), V, D, lr_t, self.b1, self.b2,
-                                                 self.eps, ops._ptr(self._bitmap), ops._stream()))
+                _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self._ss, V, D, lr_t, self.b1,
+                                                 self.b2, self.eps, ops._ptr(self._bitmap), ops._stream()))
             self._fused_applied = False
             tb.zero_grad()
             return
@@ -91,13 +96,15 @@ class TableAdam:
             ids, vals = ids.contiguous(), vals.contiguous()
             off = tb.grad_slices[0].field_row_offset
             B, F = ids.shape
-            _lib.check(L.ctr_adam_indexed_slices(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), off.data_ptr(), F, D,
-                                                 ids.data_ptr(), vals.data_ptr(), B, self._slot.data_ptr(), lr_t, self.b1,
-                                                 self.b2, self.eps, ops._ptr(self._bitmap), self._n_unique.data_ptr(),
-                                                 ops._stream()))
+            if self._dup_list is None or self._dup_list.numel() != B * F + 1:
+                self._dup_list = torch.empty((B * F + 1,), dtype=torch.int32, device=w.device)
+            _lib.check(L.ctr_adam_indexed_slices(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self._ss, off.data_ptr(), F, D,
+                                                 ids.data_ptr(), vals.data_ptr(), B, self._slot.data_ptr(),
+                                                 self._dup_list.data_ptr(), lr_t, self.b1, self.b2, self.eps,
+                                                 ops._ptr(self._bitmap), self._n_unique.data_ptr(), ops._stream()))
         if not self.lazy:
-            _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), V, D, lr_t, self.b1, self.b2,
-                                             self.eps, ops._ptr(self._bitmap), ops._stream()))
+            _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self._ss, V, D, lr_t, self.b1,
+                                             self.b2, self.eps, ops._ptr(self._bitmap), ops._stream()))
         tb.zero_grad()
 
     def last_unique_rows(self) -> int:
@@ -113,8 +120,10 @@ class ShardedTableAdam:
     def __init__(self, tables, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, lazy: bool = False):
         self.tables, self.lr, self.b1, self.b2, self.eps, self.lazy = tables, lr, beta1, beta2, eps, lazy
         w = tables.weight
-        self.m = torch.zeros(tuple(w.shape), dtype=torch.float32, device=w.device)
-        self.v = torch.zeros(tuple(w.shape), dtype=torch.float32, device=w.device)
+        self.mv = torch.zeros((w.shape[0], 2, w.shape[1]), dtype=torch.float32, device=w.device)     # interleaved, see TableAdam
+        self.m, self.v = self.mv[:, 0, :], self.mv[:, 1, :]
+        self._ss = 2 * w.shape[1]
+        self._dup_list = torch.empty((tables.G * tables.capacity + 1,), dtype=torch.int32, device=w.device)
         self.t = 0
         self._bitmap = None if lazy else torch.zeros(((tables.local_rows + 31) // 32,), dtype=torch.int32, device=w.device)
         self._slot = torch.full((tables.local_rows,), -1, dtype=torch.int32, device=w.device)
@@ -132,13 +141,13 @@ class ShardedTableAdam:
         self._n_unique.zero_()
         if self._bitmap is not None:
             self._bitmap.zero_()
-        _lib.check(L.ctr_adam_rows_dedup(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), V, D, tb.recv_rows.data_ptr(),
+        _lib.check(L.ctr_adam_rows_dedup(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self._ss, V, D, tb.recv_rows.data_ptr(),
                                          tb.recv_vals.data_ptr(), tb.recv_counts.data_ptr(), tb.G, tb.capacity,
-                                         self._slot.data_ptr(), lr_t, self.b1, self.b2, self.eps, ops._ptr(self._bitmap),
-                                         self._n_unique.data_ptr(), ops._stream()))
+                                         self._slot.data_ptr(), self._dup_list.data_ptr(), lr_t, self.b1, self.b2, self.eps,
+                                         ops._ptr(self._bitmap), self._n_unique.data_ptr(), ops._stream()))
         if not self.lazy:
-            _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), V, D, lr_t, self.b1, self.b2,
-                                             self.eps, ops._ptr(self._bitmap), ops._stream()))
+            _lib.check(L.ctr_adam_dense_rest(w.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self._ss, V, D, lr_t, self.b1,
+                                             self.b2, self.eps, ops._ptr(self._bitmap), ops._stream()))
         if barrier:
             torch.cuda.current_stream().synchronize()
             tb.dist.barrier(group=tb.group)

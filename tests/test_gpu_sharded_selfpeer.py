@@ -191,8 +191,10 @@ def test_selfpeer_owner_adam(lazy):
     rows_t = torch.tensor(rows, device=dev)
     gen = torch.Generator(device=dev).manual_seed(5)
     V = grp.local_rows
-    m = [torch.zeros((V, D), device=dev) for _ in range(G)]
-    v = [torch.zeros((V, D), device=dev) for _ in range(G)]
+    mv = [torch.zeros((V, 2, D), device=dev) for _ in range(G)]          # interleaved moments (state_stride = 2*D)
+    m = [x[:, 0, :] for x in mv]
+    v = [x[:, 1, :] for x in mv]
+    dup_list = torch.empty((G * grp.capacity + 1,), dtype=torch.int32, device=dev)
     slot = [torch.full((V,), -1, dtype=torch.int32, device=dev) for _ in range(G)]
     ref = [(grp.shards[d].double().clone(), torch.zeros((V, D), dtype=torch.float64, device=dev),
             torch.zeros((V, D), dtype=torch.float64, device=dev)) for d in range(G)]
@@ -213,12 +215,13 @@ def test_selfpeer_owner_adam(lazy):
                 touched[grp.rows[d][src, : int(grp.counts[d][src])]] = True
             bitmap = None if lazy else torch.zeros(((V + 31) // 32,), dtype=torch.int32, device=dev)
             n_unique = torch.zeros((1,), dtype=torch.int64, device=dev)
-            _lib.check(L.ctr_adam_rows_dedup(grp.shards[d].data_ptr(), m[d].data_ptr(), v[d].data_ptr(), V, D, grp.rows[d].data_ptr(),
+            _lib.check(L.ctr_adam_rows_dedup(grp.shards[d].data_ptr(), m[d].data_ptr(), v[d].data_ptr(), 2 * D, V, D, grp.rows[d].data_ptr(),
                                              grp.vals[d].data_ptr(), grp.counts[d].data_ptr(), G, grp.capacity, slot[d].data_ptr(),
+                                             (dup_list.data_ptr() if d % 2 == 0 else None),       # both merge forms
                                              lr_t, 0.9, 0.999, 1e-8, ops._ptr(bitmap), n_unique.data_ptr(), ops._stream()))
             if not lazy:
-                _lib.check(L.ctr_adam_dense_rest(grp.shards[d].data_ptr(), m[d].data_ptr(), v[d].data_ptr(), V, D, lr_t, 0.9, 0.999,
-                                                 1e-8, ops._ptr(bitmap), ops._stream()))
+                _lib.check(L.ctr_adam_dense_rest(grp.shards[d].data_ptr(), m[d].data_ptr(), v[d].data_ptr(), 2 * D, V, D, lr_t, 0.9,
+                                                 0.999, 1e-8, ops._ptr(bitmap), ops._stream()))
             assert int(n_unique.item()) == int(touched.sum()) and bool((slot[d] == -1).all())
             ref[d] = R.adam_reference(*ref[d], gd[d], touched, step, lr, lazy)
             for name, a, b_ in (("var", grp.shards[d], ref[d][0]), ("m", m[d], ref[d][1]), ("v", v[d], ref[d][2])):

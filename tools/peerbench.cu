@@ -81,6 +81,43 @@ __global__ void __launch_bounds__(256) pull_ldg(const Peers p, const long long* 
   }
 }
 
+// ---- pull shaped like the product kernel (embed_fm2_fwd_kernel<8, SH>): one warp per SAMPLE of F rows; the ids of a 32-field chunk
+// are one coalesced 8-byte load per lane, distributed by shuffle; up to 8 row loads per lane in flight, then the tile stores.
+template <int HINT>
+__global__ void __launch_bounds__(256) pull_sample(const Peers p, const long long* __restrict__ rows, int B, int F,
+                                                   float4* __restrict__ out) {
+  constexpr int LPR = 8, RPW = 4, UB = 8;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, c = lane % LPR;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp0; b < B; b += nwarps) {
+    for (int f0 = 0; f0 < F; f0 += 32) {
+      const int nf = min(32, F - f0);
+      long long row = -1;
+      if (lane < nf) row = __ldg(rows + (size_t)b * F + f0 + lane);
+#pragma unroll
+      for (int it0 = 0; it0 < LPR; it0 += UB) {
+        if (it0 * RPW >= nf) break;
+        float4 v[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int fs = (it0 + u) * RPW + sub;
+          const long long r = __shfl_sync(0xffffffffu, row, fs);
+          v[u] = make_float4(0, 0, 0, 0);
+          if (fs < nf && r >= 0) {
+            const float4* src = p.base[r & (p.G - 1)] + (size_t)(r >> p.logG) * LPR + c;
+            v[u] = HINT == 0 ? ld_nc_na(src) : ld_plain(src);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int fs = (it0 + u) * RPW + sub;
+          if (fs < nf) st_cs(out + ((size_t)b * F + f0 + fs) * LPR + c, v[u]);
+        }
+      }
+    }
+  }
+}
+
 // ---- pull with bulk async copies (TMA unit, non-tensor): each lane fetches one 128-byte row into smem, the warp then
 // emits the 32 rows (4 KB, contiguous in `out`) with one bulk store.  NST stages per warp keep NST*32 rows in flight.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -379,6 +416,14 @@ int main(int argc, char** argv) {
   }
   fill(1, 1);
   PULL(8, 8, 0, 4, "pull_ldg128 random incl-local nc.na UB8 4cta");
+  PULL(8, 8, 1, 4, "pull_ldg128 random incl-local plain UB8 4cta");
+  {
+    const int Bs = (int)(n / 40);
+    run(c, "pull_sample40 (product shape) incl-local plain 3cta", reps, 128.0, [&](int g) { pull_sample<1><<<sms * 3, 256, 0, c.st[g]>>>(peers[g], c.rows[g], Bs, 40, c.buf[g]); });
+    run(c, "pull_sample40 (product shape) incl-local plain 4cta", reps, 128.0, [&](int g) { pull_sample<1><<<sms * 4, 256, 0, c.st[g]>>>(peers[g], c.rows[g], Bs, 40, c.buf[g]); });
+    run(c, "pull_sample40 (product shape) incl-local plain 6cta", reps, 128.0, [&](int g) { pull_sample<1><<<sms * 6, 256, 0, c.st[g]>>>(peers[g], c.rows[g], Bs, 40, c.buf[g]); });
+    run(c, "pull_sample32 (one chunk per sample) incl-local plain 4cta", reps, 128.0, [&](int g) { pull_sample<1><<<sms * 4, 256, 0, c.st[g]>>>(peers[g], c.rows[g], (int)(n / 32), 32, c.buf[g]); });
+  }
   fill(0, 2);
   PULL(16, 8, 0, 4, "pull_ldg256 random (256B rows) nc.na UB8 4cta");
   PULL(16, 4, 0, 4, "pull_ldg256 random (256B rows) nc.na UB4 4cta");
