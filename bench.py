@@ -523,7 +523,8 @@ def run_deepfm(args, cfg, dd: Dist):
     rows = cfg["rows_per_field_per_rank"] * world
     if os.environ.get("CTR_BENCH_ROWS"):
         rows = int(os.environ["CTR_BENCH_ROWS"])
-    tables = shard_mod.ShardedEmbeddingTables([rows] * F, D, batch_per_rank=B, device=dev, init="normal")
+    tables = shard_mod.ShardedEmbeddingTables([rows] * F, D, batch_per_rank=B, device=dev, init="normal",
+                                              shard_backend=args.shard_backend, vmm_align=args.vmm_align << 20)
     id_sets, ids_desc = make_ids(args, rows, B, F, NB, dev, gen)
     plan = torch.empty((B, F), dtype=torch.int32, device=dev)
 
@@ -563,9 +564,8 @@ def run_deepfm(args, cfg, dd: Dist):
 
     def model_sharded(ids_dev, lab_dev):
         w_deep.grad = None
-        t_, f_ = shard_mod.lookup_fm2_autograd(tables, ids_dev)
-        logit = f_ + t_.reshape(B, F * D) @ w_deep
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, lab_dev)
+        f_, lin = shard_mod.lookup_fm2_linear_autograd(tables, ids_dev, w_deep)     # dense(1) deep head fused into the gather
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(f_ + lin, lab_dev)
         loss.backward()
         return loss
 
@@ -604,6 +604,7 @@ def run_deepfm(args, cfg, dd: Dist):
         "config": {"workload": args.workload, "model": cfg["model"], "global_batch": B * world, "B_per_gpu": B, "F": F,
                    "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "table_bytes_total": rows * F * D * 4,
                    "shard_bytes_per_gpu": rows * F * D * 4 // world, "ids": ids_desc,
+                   "shard_backend": args.shard_backend + (f" (align {args.vmm_align} MiB)" if args.shard_backend == "vmm" else ""),
                    "parallelism": f"row-sharded: tables split over {world} GPUs (global row % {world}); forward pulls rows over NVLink "
                                   "inside the gather kernel, backward stores gradient rows into the owners' queues (fused "
                                   "compute+exchange kernels, no NCCL data collective)",
@@ -623,9 +624,9 @@ def run_deepfm(args, cfg, dd: Dist):
         "sustained": sustained,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4, "d2h_bytes_per_step": 4,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1],
-                "what": "per rank: pinned-host int32 ids + labels -> H2D -> sharded.lookup_fm2_autograd (peer-pull gather + FM2, queue plan) "
-                        "-> dense(1) head + sigmoid-CE (torch) -> backward (ctr_embed_fm2_bwd_push: gradient rows into the owners' "
-                        "queues) -> loss D2H, read one step later"},
+                "what": "per rank: pinned-host int32 ids + labels -> H2D -> sharded.lookup_fm2_linear_autograd (peer-pull gather + FM2 + "
+                        "dense(1) deep head in one kernel, queue plan) -> sigmoid-CE (torch) -> backward (ctr_embed_fm2_lin_bwd_push: "
+                        "gradient rows into the owners' queues + d_w) -> loss D2H, read one step later"},
         "replicas": rep, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -709,6 +710,9 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(DEEPFM) + list(LAYER_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs 2-4 / replica side measurements")
+    ap.add_argument("--shard-backend", default="symm", choices=["symm", "vmm"],
+                    help="allocation of the table shard in the sharded workloads: torch symmetric memory or ctr_vmm_alloc")
+    ap.add_argument("--vmm-align", type=int, default=0, help="MiB; size/address alignment of ctr_vmm_alloc (0 = driver granularity)")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
                     help="id distribution of the synthetic batches (default: uniform = every row an HBM miss)")
     args = ap.parse_args()

@@ -42,6 +42,15 @@ int ctr_peer_free(void* ptr);
 int ctr_ipc_export(void* ptr, unsigned char* handle64);
 int ctr_ipc_import(const unsigned char* handle64, void** ptr);
 int ctr_ipc_close(void* ptr);
+/* The same role from the CUDA virtual-memory-management API (cuMemCreate / cuMemMap), shared as POSIX file descriptors: the
+ * mapping the big table shards use -- a legacy-IPC mapping of a 32 GB shard collapses under random 128-byte peer reads, and
+ * with VMM the size / address alignment chosen here (align = 0: the driver's recommended granularity) sets the page size the
+ * peers' TLBs see.  ctr_vmm_alloc maps `bytes` (rounded up to `align`) on the current device and returns the fd to hand to
+ * the peers (e.g. through pidfd_getfd); ctr_vmm_import maps a peer's fd into the current device (read/write over NVLink). */
+int ctr_vmm_granularity(int64_t* minimum, int64_t* recommended);
+int ctr_vmm_alloc(int64_t bytes, int64_t align, void** ptr, int* fd, int64_t* mapped_bytes);
+int ctr_vmm_import(int fd, int64_t mapped_bytes, int64_t align, void** ptr);
+int ctr_vmm_free(void* ptr);
 int64_t ctr_kernel_launches(void);              /* kernels launched by this library so far (process-wide) */
 
 /* ---- Row L + FM2: fused embedding lookup + DeepFM second-order term ------------------------------
@@ -104,6 +113,10 @@ int ctr_embed_fm2_fwd_sharded(const float* const* shard_ptrs, int64_t G, const i
 int ctr_embed_fm2_fwd_sharded_ids32(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
                                     const int32_t* ids, int64_t B, int64_t F, int64_t D, float* tile, float* fm2,
                                     int64_t* ids64_out, void* stream);
+/* Sharded form of ctr_embed_fm2_lin_fwd (fused dense(1) head; rows pulled from the owners' shards). */
+int ctr_embed_fm2_lin_fwd_sharded(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset, const void* ids,
+                                  int ids_are_int32, int64_t B, int64_t F, int64_t D, const float* wlin, float* tile, float* fm2,
+                                  float* lin, int64_t* ids64_out, void* stream);
 /* Gradient exchange, step 1 (independent of the forward; one pass over the ids): assigns every valid (b,f) a slot in its
  * OWNER's receive queue and writes plan[b,f] = owner << 28 | slot (-1: invalid id, or dropped because the owner's slice is
  * full -> *overflow = 1).  The queue's local-row indices are written here, as contiguous runs per owner:
@@ -123,6 +136,11 @@ int ctr_sharded_plan(const int64_t* field_row_offset, const int64_t* ids, int64_
 int ctr_embed_fm2_bwd_push(const float* tile, const float* d_tile, const float* d_fm2, const int32_t* plan, int64_t B,
                            int64_t F, int64_t D, int64_t G, int64_t my_rank, float* const* recv_vals, int64_t capacity,
                            float* row_grads, void* stream);
+/* The same for the fused dense(1) head (ctr_embed_fm2_lin_fwd_sharded): d_tile is the rank-1 product d_lin[b]*wlin[f,d] and is
+ * never materialised; d_wlin (F*D, zeroed here) = sum_b d_lin[b]*tile[b].  F*D <= 1536. */
+int ctr_embed_fm2_lin_bwd_push(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, const int32_t* plan,
+                               int64_t B, int64_t F, int64_t D, int64_t G, int64_t my_rank, float* const* recv_vals,
+                               int64_t capacity, float* row_grads, float* d_wlin, void* stream);
 /* The exchange alone, for row gradients (B,F,D) produced by any other backward. */
 int ctr_sharded_grad_push(const float* row_grads, const int32_t* plan, int64_t B, int64_t F, int64_t D, int64_t G,
                           int64_t my_rank, float* const* recv_vals, int64_t capacity, void* stream);

@@ -29,6 +29,10 @@ SIGNATURES = {
     "ctr_ipc_export": (c_int, [_P, ctypes.c_char_p]),
     "ctr_ipc_import": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),
     "ctr_ipc_close": (c_int, [_P]),
+    "ctr_vmm_granularity": (c_int, [POINTER(c_int64), POINTER(c_int64)]),
+    "ctr_vmm_alloc": (c_int, [_I, _I, POINTER(c_void_p), POINTER(c_int), POINTER(c_int64)]),
+    "ctr_vmm_import": (c_int, [c_int, _I, _I, POINTER(c_void_p)]),
+    "ctr_vmm_free": (c_int, [_P]),
     "ctr_kernel_launches": (c_int64, []),
     "ctr_embed_fm2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ctr_embed_fm2_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -38,6 +42,8 @@ SIGNATURES = {
     "ctr_embed_fm2_lin_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ctr_embed_fm2_fwd_ids32": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "ctr_embed_fm2_fwd_sharded_ids32": (c_int, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "ctr_embed_fm2_lin_fwd_sharded": (c_int, [_P, _I, _P, _P, c_int, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ctr_embed_fm2_lin_bwd_push": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "ctr_sharded_plan": (c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "ctr_embed_fm2_bwd_push": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "ctr_sharded_grad_push": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),

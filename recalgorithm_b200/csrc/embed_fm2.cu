@@ -683,27 +683,35 @@ extern "C" int ctr_embed_bi_bwd(const float* tile, const float* d_tile, const fl
 
 // ---- lookup + FM2 + fused dense(1) head over the flattened tile (e2e form: the consumer does not re-stream the tile) ------
 template <int LPR, typename IdT>
-static int launch_fwd_lin(const float* table, const int64_t* off, const IdT* ids, int64_t B, int64_t F, float* tile, float* fm2,
-                          int64_t* ids64_out, const float* wlin, float* lin, cudaStream_t st) {
-  auto k = embed_fm2_fwd_kernel<LPR, false, 4, false, IdT, true>;
-  const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
-  k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), PeerTables{}, reinterpret_cast<const long long*>(off), ids, (int)B,
-                          (int)F, reinterpret_cast<float4*>(tile), fm2, reinterpret_cast<long long*>(ids64_out),
-                          reinterpret_cast<const float4*>(wlin), lin);
+static int launch_fwd_lin(const float* table, const PeerTables* peers, const int64_t* off, const IdT* ids, int64_t B, int64_t F,
+                          float* tile, float* fm2, int64_t* ids64_out, const float* wlin, float* lin, cudaStream_t st) {
+  if (peers != nullptr) {
+    auto k = embed_fm2_fwd_kernel<LPR, true, 1, false, IdT, true>;
+    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
+    k<<<grid, 256, 0, st>>>(nullptr, *peers, reinterpret_cast<const long long*>(off), ids, (int)B, (int)F,
+                            reinterpret_cast<float4*>(tile), fm2, reinterpret_cast<long long*>(ids64_out),
+                            reinterpret_cast<const float4*>(wlin), lin);
+  } else {
+    auto k = embed_fm2_fwd_kernel<LPR, false, 4, false, IdT, true>;
+    const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
+    k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), PeerTables{}, reinterpret_cast<const long long*>(off), ids, (int)B,
+                            (int)F, reinterpret_cast<float4*>(tile), fm2, reinterpret_cast<long long*>(ids64_out),
+                            reinterpret_cast<const float4*>(wlin), lin);
+  }
   CTR_CHECK_LAUNCH("ctr_embed_fm2_lin_fwd");
   return CTR_OK;
 }
 
 template <typename IdT>
-static int dispatch_fwd_lin(const float* table, const int64_t* off, const IdT* ids, int64_t B, int64_t F, int64_t D, float* tile,
-                            float* fm2, int64_t* ids64_out, const float* wlin, float* lin, cudaStream_t st) {
+static int dispatch_fwd_lin(const float* table, const PeerTables* peers, const int64_t* off, const IdT* ids, int64_t B, int64_t F,
+                            int64_t D, float* tile, float* fm2, int64_t* ids64_out, const float* wlin, float* lin, cudaStream_t st) {
   switch (D / 4) {
-    case 1: return launch_fwd_lin<1>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
-    case 2: return launch_fwd_lin<2>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
-    case 4: return launch_fwd_lin<4>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
-    case 8: return launch_fwd_lin<8>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
-    case 16: return launch_fwd_lin<16>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
-    default: return launch_fwd_lin<32>(table, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 1: return launch_fwd_lin<1>(table, peers, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 2: return launch_fwd_lin<2>(table, peers, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 4: return launch_fwd_lin<4>(table, peers, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 8: return launch_fwd_lin<8>(table, peers, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    case 16: return launch_fwd_lin<16>(table, peers, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
+    default: return launch_fwd_lin<32>(table, peers, off, ids, B, F, tile, fm2, ids64_out, wlin, lin, st);
   }
 }
 
@@ -717,8 +725,25 @@ extern "C" int ctr_embed_fm2_lin_fwd(const float* table, const int64_t* field_ro
   if (B == 0) return CTR_OK;
   cudaStream_t st = as_stream(stream);
   if (ids_are_int32)
-    return dispatch_fwd_lin(table, field_row_offset, reinterpret_cast<const int*>(ids), B, F, D, tile, fm2, ids64_out, wlin, lin, st);
-  return dispatch_fwd_lin(table, field_row_offset, reinterpret_cast<const long long*>(ids), B, F, D, tile, fm2, nullptr, wlin, lin, st);
+    return dispatch_fwd_lin(table, nullptr, field_row_offset, reinterpret_cast<const int*>(ids), B, F, D, tile, fm2, ids64_out, wlin, lin, st);
+  return dispatch_fwd_lin(table, nullptr, field_row_offset, reinterpret_cast<const long long*>(ids), B, F, D, tile, fm2, nullptr, wlin, lin, st);
+}
+
+extern "C" int ctr_embed_fm2_lin_fwd_sharded(const float* const* shard_ptrs, int64_t G, const int64_t* field_row_offset,
+                                             const void* ids, int ids_are_int32, int64_t B, int64_t F, int64_t D, const float* wlin,
+                                             float* tile, float* fm2, float* lin, int64_t* ids64_out, void* stream) {
+  int rc = check_bfd("ctr_embed_fm2_lin_fwd_sharded", B, F, D);
+  if (rc) return rc;
+  CTR_REQUIRE(shard_ptrs && field_row_offset && ids && wlin && lin, "ctr_embed_fm2_lin_fwd_sharded: null argument");
+  PeerTables peers;
+  rc = fill_peers("ctr_embed_fm2_lin_fwd_sharded", peers, shard_ptrs, G);
+  if (rc) return rc;
+  CTR_REQUIRE(aligned16(tile) && aligned16(wlin), "ctr_embed_fm2_lin_fwd_sharded: tile and wlin must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  if (ids_are_int32)
+    return dispatch_fwd_lin(nullptr, &peers, field_row_offset, reinterpret_cast<const int*>(ids), B, F, D, tile, fm2, ids64_out, wlin, lin, st);
+  return dispatch_fwd_lin(nullptr, &peers, field_row_offset, reinterpret_cast<const long long*>(ids), B, F, D, tile, fm2, nullptr, wlin, lin, st);
 }
 
 template <int LPR, int HOLD>

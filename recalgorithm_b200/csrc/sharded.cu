@@ -124,22 +124,36 @@ __device__ __forceinline__ float4* queue_slot(const PeerQueues& q, size_t qbase,
 // Lookup backward fused with the gradient exchange (arithmetic of embed_fm2_bwd_kernel): warp per sample, the sample's
 // tile row is held in registers between the S pass and the gradient pass (HOLD float4 per lane; HOLD == 0 = generic
 // two-pass form); every finished 128-bit piece goes to owner.vals[(my_rank*capacity + slot)*LPR + c].
-template <int LPR, int HOLD>
-__global__ void __launch_bounds__(256)
+// LIN (HOLD > 0 only): the upstream gradient of the tile is the rank-1 product d_lin[b]*wlin[f,d] of a fused dense(1) head
+// (ctr_embed_fm2_lin_fwd): d_tile is not read, `d_tile` carries wlin (F*D) instead, and d_wlin = sum_b d_lin[b]*e[b] is
+// accumulated in registers (per CTA one shared-memory reduction + one vector red.global.add per element).
+template <int LPR, int HOLD, bool LIN = false>
+__global__ void __launch_bounds__(256, LIN ? 2 : 1)
 embed_fm2_bwd_push_kernel(const float4* __restrict__ tile, const float4* __restrict__ d_tile, const float* __restrict__ d_fm2,
-                          const int* __restrict__ plan, int B, int F, const PeerQueues q, float4* __restrict__ row_grads) {
+                          const int* __restrict__ plan, int B, int F, const PeerQueues q, float4* __restrict__ row_grads,
+                          const float* __restrict__ d_lin, float4* __restrict__ d_wlin) {
+  extern __shared__ float4 s_lin[];                 // LIN: [n4] wlin, then [n4] d_wlin accumulator
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n4 = F * LPR;
   const size_t qbase = (size_t)q.my_rank * q.capacity;
+  constexpr int HA = (LIN && HOLD > 0) ? HOLD : 1;
+  float4 acc[HA];
+  if (LIN) {
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) { s_lin[j] = __ldg(d_tile + j); s_lin[n4 + j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < HA; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int b = warp0; b < B; b += nwarps) {
     const float4* e_row = tile + (size_t)b * n4;
-    const float4* dt_row = d_tile ? d_tile + (size_t)b * n4 : nullptr;
+    const float4* dt_row = (d_tile && !LIN) ? d_tile + (size_t)b * n4 : nullptr;
     const int* p_row = plan + (size_t)b * F;
     float4* o_row = row_grads ? row_grads + (size_t)b * n4 : nullptr;
     const float g = d_fm2 ? __ldg(d_fm2 + b) : 0.f;
+    const float gl = (LIN && d_lin) ? __ldg(d_lin + b) : 0.f;
     float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
     if (HOLD > 0) {
       constexpr int H = HOLD > 0 ? HOLD : 1;
@@ -157,7 +171,8 @@ embed_fm2_bwd_push_kernel(const float4* __restrict__ tile, const float4* __restr
         dt[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         pw[k] = -1;
         if (j < n4) {
-          if (dt_row != nullptr) dt[k] = ldg_stream_f4(dt_row + j);
+          if (LIN) { const float4 w = s_lin[j]; dt[k] = make_float4(gl * w.x, gl * w.y, gl * w.z, gl * w.w); }
+          else if (dt_row != nullptr) dt[k] = ldg_stream_f4(dt_row + j);
           pw[k] = __ldg(p_row + j / LPR);
         }
       }
@@ -177,6 +192,7 @@ embed_fm2_bwd_push_kernel(const float4* __restrict__ tile, const float4* __restr
           r.z = dt[k].z + g * (S.z - e[k].z); r.w = dt[k].w + g * (S.w - e[k].w);
           if (o_row != nullptr) stg_stream_f4(o_row + j, r);
           if (pw[k] >= 0) stg_f4(queue_slot(q, qbase, pw[k], LPR, j % LPR), r);
+          if (LIN) { acc[k % HA].x += gl * e[k].x; acc[k % HA].y += gl * e[k].y; acc[k % HA].z += gl * e[k].z; acc[k % HA].w += gl * e[k].w; }
         }
       }
     } else {
@@ -198,6 +214,18 @@ embed_fm2_bwd_push_kernel(const float4* __restrict__ tile, const float4* __restr
         if (pw >= 0) stg_f4(queue_slot(q, qbase, pw, LPR, j % LPR), r);
       }
     }
+  }
+  if (LIN) {
+#pragma unroll
+    for (int k = 0; k < HA; ++k) {
+      const int j = k * 32 + lane;
+      if (j < n4) {
+        float* a = reinterpret_cast<float*>(s_lin + n4 + j);
+        atomicAdd(a + 0, acc[k].x); atomicAdd(a + 1, acc[k].y); atomicAdd(a + 2, acc[k].z); atomicAdd(a + 3, acc[k].w);
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) atomicAdd(d_wlin + j, s_lin[n4 + j]);
   }
 }
 
@@ -269,12 +297,39 @@ static int fill_queues(const char* fn, PeerQueues& q, int64_t G, int64_t my_rank
 template <int LPR, int HOLD>
 static int launch_bwd_push(const float* tile, const float* d_tile, const float* d_fm2, const int32_t* plan, int64_t B, int64_t F,
                            const PeerQueues& q, float* row_grads, cudaStream_t st) {
-  auto k = embed_fm2_bwd_push_kernel<LPR, HOLD>;
+  auto k = embed_fm2_bwd_push_kernel<LPR, HOLD, false>;
   const int grid = resident_grid_sh(k, 256, (B + 7) / 8);
   k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(tile), reinterpret_cast<const float4*>(d_tile), d_fm2, plan, (int)B,
-                          (int)F, q, reinterpret_cast<float4*>(row_grads));
+                          (int)F, q, reinterpret_cast<float4*>(row_grads), nullptr, nullptr);
   CTR_CHECK_LAUNCH("ctr_embed_fm2_bwd_push");
   return CTR_OK;
+}
+
+template <int LPR, int HOLD>
+static int launch_lin_bwd_push(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, const int32_t* plan,
+                               int64_t B, int64_t F, const PeerQueues& q, float* row_grads, float* d_wlin, cudaStream_t st) {
+  auto k = embed_fm2_bwd_push_kernel<LPR, HOLD, true>;
+  const size_t smem = sizeof(float4) * 2 * (size_t)F * LPR;
+  if (smem > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long long grid = (long long)per_sm * sm_count();
+  if (grid > (B + 7) / 8) grid = (B + 7) / 8;
+  k<<<(int)grid, 256, smem, st>>>(reinterpret_cast<const float4*>(tile), reinterpret_cast<const float4*>(wlin), d_fm2, plan, (int)B,
+                                  (int)F, q, reinterpret_cast<float4*>(row_grads), d_lin, reinterpret_cast<float4*>(d_wlin));
+  CTR_CHECK_LAUNCH("ctr_embed_fm2_lin_bwd_push");
+  return CTR_OK;
+}
+
+template <int LPR>
+static int dispatch_lin_bwd_push(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, const int32_t* plan,
+                                 int64_t B, int64_t F, const PeerQueues& q, float* row_grads, float* d_wlin, cudaStream_t st) {
+  const int64_t per_lane = (F * LPR + 31) / 32;
+  if (per_lane <= 4) return launch_lin_bwd_push<LPR, 4>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+  if (per_lane <= 8) return launch_lin_bwd_push<LPR, 8>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+  if (per_lane <= 12) return launch_lin_bwd_push<LPR, 12>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+  set_error("ctr_embed_fm2_lin_bwd_push: F*D = %lld exceeds the register-resident limit of 1536", (long long)(F * LPR * 4));
+  return CTR_ERR_UNSUPPORTED;
 }
 
 template <int LPR>
@@ -333,6 +388,31 @@ extern "C" int ctr_embed_fm2_bwd_push(const float* tile, const float* d_tile, co
     case 8: return dispatch_bwd_push<8>(tile, d_tile, d_fm2, plan, B, F, q, row_grads, st);
     case 16: return dispatch_bwd_push<16>(tile, d_tile, d_fm2, plan, B, F, q, row_grads, st);
     default: return dispatch_bwd_push<32>(tile, d_tile, d_fm2, plan, B, F, q, row_grads, st);
+  }
+}
+
+extern "C" int ctr_embed_fm2_lin_bwd_push(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin,
+                                          const int32_t* plan, int64_t B, int64_t F, int64_t D, int64_t G, int64_t my_rank,
+                                          float* const* recv_vals, int64_t capacity, float* row_grads, float* d_wlin,
+                                          void* stream) {
+  PeerQueues q;
+  int rc = fill_queues("ctr_embed_fm2_lin_bwd_push", q, G, my_rank, recv_vals, nullptr, nullptr, capacity);
+  if (rc) return rc;
+  CTR_REQUIRE(tile && wlin && plan && recv_vals && d_wlin, "ctr_embed_fm2_lin_bwd_push: null tile/wlin/plan/recv_vals/d_wlin");
+  CTR_REQUIRE(B >= 0 && F >= 1 && B <= 0x7fffffffLL / 8 && F <= 65536, "ctr_embed_fm2_lin_bwd_push: bad sizes");
+  CTR_UNSUPPORTED(D % 4 != 0 || D > 128 || (D & (D - 1)) != 0, "ctr_embed_fm2_lin_bwd_push: D=%lld unsupported", (long long)D);
+  CTR_REQUIRE(aligned16(tile) && aligned16(wlin) && aligned16(row_grads) && aligned16(d_wlin),
+              "ctr_embed_fm2_lin_bwd_push: tile, wlin, row_grads and d_wlin must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  CTR_CUDA(cudaMemsetAsync(d_wlin, 0, sizeof(float) * F * D, st));
+  if (B == 0) return CTR_OK;
+  switch (D / 4) {
+    case 1: return dispatch_lin_bwd_push<1>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+    case 2: return dispatch_lin_bwd_push<2>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+    case 4: return dispatch_lin_bwd_push<4>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+    case 8: return dispatch_lin_bwd_push<8>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+    case 16: return dispatch_lin_bwd_push<16>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
+    default: return dispatch_lin_bwd_push<32>(tile, wlin, d_fm2, d_lin, plan, B, F, q, row_grads, d_wlin, st);
   }
 }
 

@@ -102,6 +102,54 @@ class SymmBuffer:
         self.peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
 
 
+def _pidfd_getfd(pid: int, fd: int) -> int:
+    """Duplicate file descriptor `fd` of process `pid` into this process (Linux >= 5.6; same user)."""
+    import os
+    libc = ctypes.CDLL(None, use_errno=True)
+    pidfd = os.pidfd_open(pid)
+    try:
+        got = libc.syscall(438, pidfd, fd, 0)             # SYS_pidfd_getfd
+        if got < 0:
+            raise OSError(ctypes.get_errno(), "pidfd_getfd failed")
+        return int(got)
+    finally:
+        os.close(pidfd)
+
+
+class VmmBuffer:
+    """Same role as SymmBuffer with the allocation made by libctr_b200 itself (ctr_vmm_alloc: cuMemCreate + cuMemMap with an
+    explicit size/address alignment) and the peers' mappings imported from file descriptors passed with pidfd_getfd."""
+
+    def __init__(self, shape, dtype, device, group, align: int = 0):
+        import os
+        import torch.distributed as dist
+        self.shape, self.dtype, self.device = tuple(shape), dtype, device
+        nbytes = int(torch.Size(shape).numel()) * torch.empty((), dtype=dtype).element_size()
+        L = _lib.lib()
+        p, fd, mapped = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int64()
+        _lib.check(L.ctr_vmm_alloc(max(nbytes, 1), align, ctypes.byref(p), ctypes.byref(fd), ctypes.byref(mapped)))
+        self.ptr, self._fd, self.mapped_bytes, self.align = int(p.value), int(fd.value), int(mapped.value), align
+        self.tensor = _view(self.ptr, shape, dtype, device)
+        G, rank = dist.get_world_size(group), dist.get_rank(group)
+        info = [None] * G
+        dist.all_gather_object(info, (os.getpid(), self._fd, self.mapped_bytes), group=group)
+        self.peer_ptrs, self._imported = [], []
+        for r in range(G):
+            if r == rank:
+                self.peer_ptrs.append(self.ptr)
+                continue
+            pid, rfd, rbytes = info[r]
+            lfd = _pidfd_getfd(pid, rfd)
+            q = ctypes.c_void_p()
+            _lib.check(L.ctr_vmm_import(lfd, rbytes, align, ctypes.byref(q)))
+            os.close(lfd)
+            self.peer_ptrs.append(int(q.value))
+            self._imported.append(int(q.value))
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                        # every peer has imported before anybody may close its fd
+        os.close(self._fd)
+
+
 class ShardedEmbeddingTables:
     """F per-field tables, concatenated and row-sharded over the ranks of ``group`` (one process per GPU).
 
@@ -112,7 +160,7 @@ class ShardedEmbeddingTables:
     first three for an autograd graph."""
 
     def __init__(self, rows_per_field, dim: int, batch_per_rank: int, group=None, device=None, init: Optional[str] = "normal",
-                 seed: int = 1234, slack: float = 1.25):
+                 seed: int = 1234, slack: float = 1.25, shard_backend: str = "symm", vmm_align: int = 0):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -132,7 +180,12 @@ class ShardedEmbeddingTables:
         grp = group if group is not None else dist.group.WORLD
         # the shard lives in CUDA VMM symmetric memory (2 MB pages): a legacy-IPC mapping of a 32 GB shard collapsed to
         # 7 GB/s under random peer reads (peer-TLB reach); the small receive queues keep plain IPC buffers
-        self._symm_w = SymmBuffer((self.local_rows, self.dim), torch.float32, self.device, grp)
+        if shard_backend == "vmm":
+            self._symm_w = VmmBuffer((self.local_rows, self.dim), torch.float32, self.device, grp, align=vmm_align)
+        elif shard_backend == "symm":
+            self._symm_w = SymmBuffer((self.local_rows, self.dim), torch.float32, self.device, grp)
+        else:
+            raise ValueError("shard_backend must be 'symm' (torch symmetric memory) or 'vmm' (ctr_vmm_alloc)")
         self.weight = self._symm_w.tensor
         if init == "normal":
             g = torch.Generator(device=self.device).manual_seed(seed + self.rank)
@@ -214,6 +267,39 @@ class ShardedEmbeddingTables:
                                                      self.G, self.rank, self._v_ptrs, self.capacity, ops._ptr(row_grads),
                                                      ops._stream()))
 
+    def lookup_fm2_linear(self, ids: torch.Tensor, wlin: torch.Tensor, ids64_out=None):
+        """Forward with the fused dense(1) head: (tile, fm2 (B,1), lin (B,1) = tile.reshape(B, F*D) @ wlin)."""
+        B, F = ids.shape
+        D = self.dim
+        i32 = ids.dtype == torch.int32
+        ops._chk(ids, torch.int32 if i32 else torch.int64, "ids"); ops._chk(ids64_out, torch.int64, "ids64_out", (B, F))
+        wlin = wlin.reshape(F * D)
+        ops._chk(wlin, torch.float32, "wlin", (F * D,))
+        tile = torch.empty((B, F, D), dtype=torch.float32, device=self.device)
+        fm2 = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        lin = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().ctr_embed_fm2_lin_fwd_sharded(self._w_ptrs, self.G, self.field_row_offset.data_ptr(), ops._ptr(ids), int(i32),
+                                                            B, F, D, ops._ptr(wlin), ops._ptr(tile), ops._ptr(fm2), ops._ptr(lin),
+                                                            ops._ptr(ids64_out), ops._stream()))
+        return tile, fm2, lin
+
+    def lin_bwd_push(self, tile, wlin, d_fm2, d_lin, plan, row_grads=None):
+        """Backward of lookup_fm2_linear fused with the exchange; returns d_wlin (F*D,)."""
+        B, F, D = tile.shape
+        wlin = wlin.reshape(F * D)
+        ops._chk(tile, torch.float32, "tile"); ops._chk(wlin, torch.float32, "wlin", (F * D,)); ops._chk(plan, torch.int32, "plan", (B, F))
+        if d_fm2 is not None:
+            d_fm2 = d_fm2.reshape(B)
+        if d_lin is not None:
+            d_lin = d_lin.reshape(B)
+        ops._chk(d_fm2, torch.float32, "d_fm2", (B,)); ops._chk(d_lin, torch.float32, "d_lin", (B,))
+        ops._chk(row_grads, torch.float32, "row_grads", (B, F, D))
+        d_wlin = torch.empty((F * D,), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().ctr_embed_fm2_lin_bwd_push(ops._ptr(tile), ops._ptr(wlin), ops._ptr(d_fm2), ops._ptr(d_lin), ops._ptr(plan),
+                                                         B, F, D, self.G, self.rank, self._v_ptrs, self.capacity, ops._ptr(row_grads),
+                                                         ops._ptr(d_wlin), ops._stream()))
+        return d_wlin
+
     def finish_push(self):
         """Stream sync + cross-rank barrier: afterwards this rank's ``recv_rows/recv_vals/recv_counts`` hold what all
         ranks sent to it.  Raises if a queue overflowed (entries were dropped): raise ``slack``."""
@@ -267,6 +353,32 @@ class _ShardedLookupFM2(torch.autograd.Function):
         ctx.tables.bwd_push(tile, None if d_tile is None else d_tile.contiguous(), None if d_fm2 is None else d_fm2.contiguous(),
                             ctx.plan)
         return None, None, None
+
+
+class _ShardedLookupFM2Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wlin, tables: ShardedEmbeddingTables, ids: torch.Tensor):
+        B, F = ids.shape
+        wl = wlin.contiguous()
+        ids64 = torch.empty((B, F), dtype=torch.int64, device=ids.device) if ids.dtype == torch.int32 else None
+        tile, fm2, lin = tables.lookup_fm2_linear(ids, wl, ids64_out=ids64)
+        ctx.tables = tables
+        ctx.plan = tables.plan(ids if ids64 is None else ids64)
+        ctx.save_for_backward(tile, wl)
+        return fm2, lin
+
+    @staticmethod
+    def backward(ctx, d_fm2, d_lin):
+        tile, wl = ctx.saved_tensors
+        d_wlin = ctx.tables.lin_bwd_push(tile, wl, None if d_fm2 is None else d_fm2.contiguous(),
+                                         None if d_lin is None else d_lin.contiguous(), ctx.plan)
+        return d_wlin.reshape(wl.shape), None, None
+
+
+def lookup_fm2_linear_autograd(tables: ShardedEmbeddingTables, ids: torch.Tensor, wlin: torch.Tensor):
+    """Row-sharded lookup + FM2 + fused dense(1) head: (fm2 (B,1), lin (B,1)); the backward pushes the gradient rows to their
+    owners and returns d_wlin (call ``tables.finish_push()`` before the owners' optimizer step)."""
+    return _ShardedLookupFM2Linear.apply(wlin, tables, ids)
 
 
 def lookup_fm2_autograd(tables: ShardedEmbeddingTables, ids: torch.Tensor, anchor: Optional[torch.Tensor] = None):

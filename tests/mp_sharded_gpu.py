@@ -17,10 +17,12 @@ def main():
     from oracle import sharded_ref as R                      # checker only
     from recalgorithm_b200 import ops, sharded as S
     dev = torch.device("cuda", local)
-    for (B, F, D, rows_each) in ((257, 40, 32, 5000), (64, 6, 8, 300), (1000, 33, 16, 1)):
+    for ci, (B, F, D, rows_each) in enumerate(((257, 40, 32, 5000), (64, 6, 8, 300), (1000, 33, 16, 1))):
         g = torch.Generator(device=dev).manual_seed(11)
         rows = [rows_each + 3 * f for f in range(F)]
-        t = S.ShardedEmbeddingTables(rows, D, batch_per_rank=B, device=dev, init=None, slack=3.0)
+        # both shard allocators: torch symmetric memory and the library's own VMM allocation (fd passing)
+        t = S.ShardedEmbeddingTables(rows, D, batch_per_rank=B, device=dev, init=None, slack=3.0,
+                                     shard_backend="vmm" if ci % 2 else "symm")
         full = torch.randn((t.num_rows, D), device=dev, generator=g)                # identical on all ranks
         t.weight.copy_(S.full_to_shard(full, rank, world))
         dist.barrier()
@@ -65,6 +67,24 @@ def main():
         got = t.received_to_dense()
         err = (got.double() - refd).abs().max() / refd.abs().max().clamp_min(1e-30)
         assert err <= 1e-5, f"autograd sharded lookup differs: {err}"
+        dist.barrier()
+        # (4) fused dense(1) head through autograd: lin = tile @ w, d_w and the pushed rows
+        t.recv_vals.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        wl = torch.randn((F * D, 1), device=dev, generator=gi).requires_grad_()
+        d_lin = torch.randn((B,), device=dev, generator=gi)
+        f_l, lin = S.lookup_fm2_linear_autograd(t, ids, wl)
+        assert torch.equal(f_l, fm2)
+        ((f_l.reshape(-1) * d_fm2).sum() + (lin.reshape(-1) * d_lin).sum()).backward()
+        t.finish_push()
+        rg_lin = ops.embed_fm2_bwd(tile, (d_lin[:, None] * wl.detach().reshape(1, -1)).reshape(B, F, D).contiguous(), d_fm2)
+        ref_l = R.exchange_reference(t.local_rows, t.field_row_offset, ids, rg_lin)
+        got = t.received_to_dense()
+        err = (got.double() - ref_l).abs().max() / ref_l.abs().max().clamp_min(1e-30)
+        assert err <= 1e-5, f"fused-head sharded backward differs: {err}"
+        dw_ref = (d_lin.double()[:, None] * tile.double().reshape(B, F * D)).sum(0)
+        err = (wl.grad.double().reshape(-1) - dw_ref).abs().max() / dw_ref.abs().max().clamp_min(1e-30)
+        assert err <= 1e-5, f"fused-head d_w differs: {err}"
         dist.barrier()
         # ---- owner-side Adam on the received entries (SURVEY 8f.3 on the sharded path): two steps, lazy and TF-dense
         from recalgorithm_b200 import optim

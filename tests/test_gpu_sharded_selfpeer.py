@@ -226,3 +226,43 @@ def test_selfpeer_owner_adam(lazy):
             ref[d] = R.adam_reference(*ref[d], gd[d], touched, step, lr, lazy)
             for name, a, b_ in (("var", grp.shards[d], ref[d][0]), ("m", m[d], ref[d][1]), ("v", v[d], ref[d][2])):
                 assert_close(a, b_, what=f"owner adam lazy={lazy} step {step} owner {d} {name}")
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_selfpeer_fused_linear_head(G):
+    """Sharded lookup + FM2 + fused dense(1) head and its backward+push equal the unsharded fused kernels / the plain chain."""
+    from recalgorithm_b200 import _lib, ops
+    dev = torch.device("cuda", 0)
+    B, F, D = 300, 40, 32
+    rows = [500 + 3 * f for f in range(F)]
+    grp = LocalShardGroup(rows, D, G, B)
+    rows_t = torch.tensor(rows, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(17 + G)
+    wlin = torch.randn((F * D,), device=dev, generator=gen) * 0.3
+    L = _lib.lib()
+    ids_all, rg_all = [], []
+    dw_sum = torch.zeros((F * D,), dtype=torch.float64, device=dev)
+    for rank in range(G):
+        ids = _ids(gen, B, rows_t, dev)
+        id_in = ids.int() if rank % 2 else ids
+        tile = torch.empty((B, F, D), device=dev); fm2 = torch.empty((B, 1), device=dev); lin = torch.empty((B, 1), device=dev)
+        ids64 = torch.empty((B, F), dtype=torch.int64, device=dev)
+        _lib.check(L.ctr_embed_fm2_lin_fwd_sharded(grp.w_ptrs, G, grp.off.data_ptr(), ops._ptr(id_in), int(rank % 2), B, F, D, ops._ptr(wlin),
+                                                   ops._ptr(tile), ops._ptr(fm2), ops._ptr(lin), ops._ptr(ids64), ops._stream()))
+        t_ref, f_ref, _ = grp.lookup(ids)
+        assert torch.equal(tile, t_ref) and torch.equal(fm2, f_ref)
+        if rank % 2:
+            assert torch.equal(ids64, ids)
+        assert_close(lin, tile.double().reshape(B, F * D) @ wlin.double()[:, None], what="fused head")
+        d_fm2 = torch.randn((B,), device=dev, generator=gen); d_lin = torch.randn((B,), device=dev, generator=gen)
+        rg_ref, dw_ref = ops.embed_fm2_lin_bwd(tile, wlin, d_fm2, d_lin)
+        plan = grp.plan(rank, ids)
+        rg = torch.empty_like(tile); dw = torch.empty((F * D,), device=dev)
+        _lib.check(L.ctr_embed_fm2_lin_bwd_push(ops._ptr(tile), ops._ptr(wlin), ops._ptr(d_fm2), ops._ptr(d_lin), ops._ptr(plan), B, F, D, G,
+                                                rank, grp.v_ptrs, grp.capacity, ops._ptr(rg), ops._ptr(dw), ops._stream()))
+        assert torch.equal(rg, rg_ref)
+        assert_close(dw, dw_ref.double(), what="d_wlin")
+        ids_all.append(ids); rg_all.append(rg_ref)
+    want = _reference_dense(grp, ids_all, rg_all)
+    for d in range(G):
+        assert_close(grp.received_dense(d), want[d], what=f"fused-head push, owner {d}")
