@@ -254,18 +254,21 @@ int64_t ctr_cin_bwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D,
  * Replaces din_attention(query, keys, keys_length, is_softmax) (DIN/din_attention.py:17-43).
  * query (B,H); keys (B,T,H); keys_length int64 (B); dense layers f1_att (4H->64, relu), f2_att (64->32,
  * relu), f3_att (32->1): w1 (4H,64) b1 (64) w2 (64,32) b2 (32) w3 (32) b3 (1); out (B,H).
- * att_w (B,T): the final per-position weights (saved for backward), or NULL. */
+ * att_w (B,T): the final per-position weights (saved for backward), or NULL.
+ * sched_scratch: device int32[B + 64] or NULL.  When given, a one-CTA pass orders the samples by descending keys_length and
+ * the warps take them from a shared counter (longest-first list scheduling: a warp's cost is its samples' lengths); NULL =
+ * static round-robin.  Same results either way (weight gradients are fp32-atomic sums in both). */
 int ctr_din_attention_fwd(const float* query, const float* keys, const int64_t* keys_length,
                           const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* w3, const float* b3, int64_t B, int64_t T, int64_t H, int is_softmax,
-                          float* out, float* att_w, void* stream);
+                          float* out, float* att_w, int32_t* sched_scratch, void* stream);
 /* d_params: one flat fp32 buffer laid out [w1 | b1 | w2 | b2 | w3 | b3] (4H*64+64+64*32+32+32+1), overwritten.
  * att_w: the (B,T) weights saved by the forward, or NULL (they are then recomputed). */
 int ctr_din_attention_bwd(const float* query, const float* keys, const int64_t* keys_length,
                           const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* w3, const float* b3, const float* g_out, const float* att_w,
                           int64_t B, int64_t T, int64_t H, int is_softmax,
-                          float* d_query, float* d_keys, float* d_params, void* stream);
+                          float* d_query, float* d_keys, float* d_params, int32_t* sched_scratch, void* stream);
 
 /* ---- Rows SENET / BILINEAR: FiBiNET ---------------------------------------------------------------------
  * senet(input, embedding_dim, reduction_ratio) (FiBiNET/senet.py:26-34): x (B,F,K); w1 (F,r); w2 (r,F). */

@@ -26,7 +26,9 @@ namespace ctr {
 constexpr int DIN_H1 = 64;      // f1_att units (DIN/din_attention.py:21)
 constexpr int DIN_H2 = 32;      // f2_att units (:22)
 constexpr int DIN_TT = 4;       // positions per warp per round
-constexpr int DIN_BT = 4;       // backward: positions per warp per round (shared-memory latency and warp syncs amortised 4x)
+constexpr int DIN_BT = 2;       // backward: positions per warp per round (4 measured no faster: the unrolled body outgrew the
+                                // 32 KB instruction cache -- 23 % of the stall samples were instruction fetches)
+constexpr int DIN_SCHED_HDR = 64;   // ints in front of the order array of the schedule scratch ([0] = work counter)
 constexpr float DIN_PAD_F = -4294967295.0f;   // -2**32 + 1 (rounds to -2^32 in fp32, like the reference's fp32 tensor)
 
 struct DinSmem {                // offsets in floats into dynamic shared memory
@@ -189,13 +191,54 @@ __device__ __forceinline__ void din_weights(float* sc, int T, int len, int H, in
   __syncwarp();
 }
 
+// Work distribution.  A warp's cost is its samples' keys_length (0..T), so a static round-robin leaves the CTA waiting for
+// its slowest warp (ncu: 26 % of the backward's stall samples at the final barrier, and SMs idle behind it).  One tiny
+// kernel counting-sorts the sample ids by DESCENDING length into sched[64 + i]; warps then take samples from a global counter
+// (sched[0]) -- longest-processing-time-first list scheduling.  sched == NULL keeps the static assignment.
+__global__ void __launch_bounds__(1024)
+din_schedule_kernel(const long long* __restrict__ keys_length, int B, int T, int* __restrict__ sched) {
+  extern __shared__ int s_bin[];                       // (T + 2) bins, then their start offsets
+  for (int i = threadIdx.x; i < T + 2; i += blockDim.x) s_bin[i] = 0;
+  if (threadIdx.x == 0) sched[0] = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    long long l = __ldg(keys_length + b);
+    const int len = (int)(l < 0 ? 0 : (l > T ? T : l));
+    atomicAdd(&s_bin[T - len], 1);                     // bin 0 = longest
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i <= T; ++i) { const int c = s_bin[i]; s_bin[i] = acc; acc += c; }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    long long l = __ldg(keys_length + b);
+    const int len = (int)(l < 0 ? 0 : (l > T ? T : l));
+    sched[DIN_SCHED_HDR + atomicAdd(&s_bin[T - len], 1)] = b;
+  }
+}
+
+// next sample of this warp: static stride, or the shared work counter over the longest-first order
+__device__ __forceinline__ int din_next_sample(int* __restrict__ sched, int B, int& static_b, int stride, int lane) {
+  if (sched == nullptr) {
+    const int b = static_b;
+    static_b += stride;
+    return b < B ? b : -1;
+  }
+  int i = 0;
+  if (lane == 0) i = atomicAdd(sched, 1);
+  i = __shfl_sync(0xffffffffu, i, 0);
+  return i < B ? __ldg(sched + DIN_SCHED_HDR + i) : -1;
+}
+
 template <int HP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 din_attention_fwd_kernel(const float* __restrict__ query, const float* __restrict__ keys,
                          const long long* __restrict__ keys_length, const float* __restrict__ w1,
                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                          const float* __restrict__ w3, const float* __restrict__ b3, int B, int T, int H,
-                         int is_softmax, float* __restrict__ out, float* __restrict__ att_w) {
+                         int is_softmax, float* __restrict__ out, float* __restrict__ att_w, int* __restrict__ sched) {
   extern __shared__ __align__(16) float sm[];
   const DinSmem L = din_layout(H, T, WARPS, false);
   din_stage_weights(sm, L, w1, b1, w2, b2, w3, b3, H, false);
@@ -209,7 +252,9 @@ din_attention_fwd_kernel(const float* __restrict__ query, const float* __restric
   float* sc = wsm + T * H;
   float* tile = sm + L.tile + wid * DIN_TT * L.tile_stride;
 
-  for (int b = blockIdx.x * WARPS + wid; b < B; b += gridDim.x * WARPS) {
+  int static_b = blockIdx.x * WARPS + wid;
+  for (int b = din_next_sample(sched, B, static_b, gridDim.x * WARPS, lane); b >= 0;
+       b = din_next_sample(sched, B, static_b, gridDim.x * WARPS, lane)) {
     float weff[HP][2], qpart[2];
     __syncwarp();
     din_prepare<HP>(sm, L, wsm, query, keys, b, T, H, lane, weff, qpart);
@@ -298,7 +343,8 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                          const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ g_out,
                          const float* __restrict__ att_w, int B, int T, int H, int is_softmax,
-                         float* __restrict__ d_query, float* __restrict__ d_keys, float* __restrict__ d_params) {
+                         float* __restrict__ d_query, float* __restrict__ d_keys, float* __restrict__ d_params,
+                         int* __restrict__ sched) {
   extern __shared__ __align__(16) float sm[];
   const DinBwdSmem L = din_bwd_layout(H, HP, T, WARPS);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
@@ -369,7 +415,9 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
     score = warp_sum(h2 * w3v) + b3v;
   };
 
-  for (int b = blockIdx.x * WARPS + wid; b < B; b += gridDim.x * WARPS) {
+  int static_b = blockIdx.x * WARPS + wid;
+  for (int b = din_next_sample(sched, B, static_b, gridDim.x * WARPS, lane); b >= 0;
+       b = din_next_sample(sched, B, static_b, gridDim.x * WARPS, lane)) {
     // ---------------- per-sample preparation
     __syncwarp();
     for (int i = lane; i < T * H; i += 32) skeys[i] = __ldg(keys + (size_t)b * T * H + i);
@@ -610,7 +658,7 @@ static int check_din(const char* fn, int64_t B, int64_t T, int64_t H) {
 template <int WARPS>
 static int din_fwd_launch(const float* query, const float* keys, const int64_t* len, const float* w1, const float* b1,
                           const float* w2, const float* b2, const float* w3, const float* b3, int64_t B, int64_t T,
-                          int64_t H, int is_softmax, float* out, float* att_w, cudaStream_t st) {
+                          int64_t H, int is_softmax, float* out, float* att_w, int* sched, cudaStream_t st) {
   const DinSmem L = din_layout((int)H, (int)T, WARPS, false);
   const size_t smem = sizeof(float) * (size_t)L.total;
   CTR_UNSUPPORTED(smem > 220 * 1024, "ctr_din_attention_fwd: T=%lld H=%lld needs %zu B of shared memory", (long long)T,
@@ -625,7 +673,7 @@ static int din_fwd_launch(const float* query, const float* keys, const int64_t* 
     long long grid = (long long)(per_sm < 1 ? 1 : per_sm) * sm_count();                                           \
     if (grid > need) grid = need;                                                                                 \
     k<<<(int)grid, WARPS * 32, smem, st>>>(query, keys, reinterpret_cast<const long long*>(len), w1, b1, w2, b2,  \
-                                           w3, b3, (int)B, (int)T, (int)H, is_softmax, out, att_w);               \
+                                           w3, b3, (int)B, (int)T, (int)H, is_softmax, out, att_w, sched);        \
   }
   if (H <= 4) GO(4) else if (H <= 8) GO(8) else if (H <= 16) GO(16) else GO(32)
 #undef GO
@@ -636,7 +684,7 @@ static int din_fwd_launch(const float* query, const float* keys, const int64_t* 
 extern "C" int ctr_din_attention_fwd(const float* query, const float* keys, const int64_t* keys_length, const float* w1,
                                      const float* b1, const float* w2, const float* b2, const float* w3,
                                      const float* b3, int64_t B, int64_t T, int64_t H, int is_softmax, float* out,
-                                     float* att_w, void* stream) {
+                                     float* att_w, int32_t* sched_scratch, void* stream) {
   int rc = check_din("ctr_din_attention_fwd", B, T, H);
   if (rc) return rc;
   CTR_REQUIRE(query && keys_length && w1 && b1 && w2 && b2 && w3 && b3 && out && (keys || T == 0),
@@ -647,14 +695,19 @@ extern "C" int ctr_din_attention_fwd(const float* query, const float* keys, cons
     CTR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * B * H, st));
     return CTR_OK;
   }
-  return din_fwd_launch<4>(query, keys, keys_length, w1, b1, w2, b2, w3, b3, B, T, H, is_softmax, out, att_w, st);
+  if (sched_scratch != nullptr) {
+    CTR_UNSUPPORTED(T > 8192, "ctr_din_attention_fwd: T=%lld too long for the schedule pass", (long long)T);
+    din_schedule_kernel<<<1, 1024, sizeof(int) * (T + 2), st>>>(reinterpret_cast<const long long*>(keys_length), (int)B, (int)T, sched_scratch);
+    count_launch();
+  }
+  return din_fwd_launch<4>(query, keys, keys_length, w1, b1, w2, b2, w3, b3, B, T, H, is_softmax, out, att_w, sched_scratch, st);
 }
 
 extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, const int64_t* keys_length, const float* w1,
                                      const float* b1, const float* w2, const float* b2, const float* w3,
                                      const float* b3, const float* g_out, const float* att_w, int64_t B, int64_t T,
                                      int64_t H, int is_softmax, float* d_query, float* d_keys, float* d_params,
-                                     void* stream) {
+                                     int32_t* sched_scratch, void* stream) {
   int rc = check_din("ctr_din_attention_bwd", B, T, H);
   if (rc) return rc;
   CTR_REQUIRE(query && keys_length && w1 && b1 && w2 && b2 && w3 && b3 && g_out && d_query && d_params &&
@@ -667,6 +720,12 @@ extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, cons
     CTR_CUDA(cudaMemsetAsync(d_query, 0, sizeof(float) * B * H, st));
     return CTR_OK;
   }
+  if (sched_scratch != nullptr) {
+    CTR_UNSUPPORTED(T > 8192, "ctr_din_attention_bwd: T=%lld too long for the schedule pass", (long long)T);
+    din_schedule_kernel<<<1, 1024, sizeof(int) * (T + 2), st>>>(reinterpret_cast<const long long*>(keys_length), (int)B, (int)T, sched_scratch);
+    count_launch();
+  }
+  int* sched = sched_scratch;
   const int HPv = H <= 4 ? 4 : H <= 8 ? 8 : H <= 16 ? 16 : 32;
   // 8 warps per CTA unless their staging areas do not fit the shared memory (long sequences of wide keys): then 4
   const bool w8 = sizeof(float) * (size_t)din_bwd_layout((int)H, HPv, (int)T, 8).total <= 220 * 1024;
@@ -686,7 +745,7 @@ extern "C" int ctr_din_attention_bwd(const float* query, const float* keys, cons
     if (grid > need) grid = need;                                                                                 \
     k<<<(int)grid, WARPS * 32, smem, st>>>(query, keys, reinterpret_cast<const long long*>(keys_length), w1, b1,  \
                                            w2, b2, w3, b3, g_out, att_w, (int)B, (int)T, (int)H, is_softmax,      \
-                                           d_query, d_keys, d_params);                                            \
+                                           d_query, d_keys, d_params, sched);                                     \
   }
 #define GO(HPV) { if (w8) GO2(HPV, 8) else GO2(HPV, 4) }
   if (H <= 4) GO(4) else if (H <= 8) GO(8) else if (H <= 16) GO(16) else GO(32)

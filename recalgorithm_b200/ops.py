@@ -229,8 +229,22 @@ def _din_params(H, w1, b1, w2, b2, w3, b3):
     return w1, b1, w2, b2, w3, b3
 
 
-def din_attention_fwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, is_softmax=False, want_weights=False):
-    """DIN attention unit.  query (B,H); keys (B,T,H); keys_length (B,) int64.  Returns out (B,H) [, att_w (B,T)]."""
+_din_sched = {}
+
+
+def _din_sched_scratch(B: int, device, balanced: bool):
+    """int32[B + 64] schedule scratch of the DIN kernels (longest-first dynamic work distribution), cached per device."""
+    if not balanced or B == 0:
+        return None
+    t = _din_sched.get(device)
+    if t is None or t.numel() < B + 64:
+        t = _din_sched[device] = torch.empty((B + 64,), dtype=torch.int32, device=device)
+    return t
+
+
+def din_attention_fwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, is_softmax=False, want_weights=False, balanced=True):
+    """DIN attention unit.  query (B,H); keys (B,T,H); keys_length (B,) int64.  Returns out (B,H) [, att_w (B,T)].
+    balanced: samples are handed to the warps longest-first from a shared counter instead of round-robin."""
     B, T, H = keys.shape
     _chk(query, F32, "query", (B, H)); _chk(keys, F32, "keys"); _chk(keys_length, I64, "keys_length", (B,))
     w1, b1, w2, b2, w3, b3 = _din_params(H, w1, b1, w2, b2, w3, b3)
@@ -238,11 +252,12 @@ def din_attention_fwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, is_softm
     att = torch.empty((B, T), dtype=F32, device=query.device) if want_weights else None
     _lib.check(_lib.lib().ctr_din_attention_fwd(_ptr(query), _ptr(keys) if T > 0 else None, _ptr(keys_length), _ptr(w1),
                                                 _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), B, T, H,
-                                                int(bool(is_softmax)), _ptr(out), _ptr(att), _stream()))
+                                                int(bool(is_softmax)), _ptr(out), _ptr(att),
+                                                _ptr(_din_sched_scratch(B, query.device, balanced)), _stream()))
     return (out, att) if want_weights else out
 
 
-def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, is_softmax=False, att_w=None):
+def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, is_softmax=False, att_w=None, balanced=True):
     """Returns (d_query, d_keys, [dw1, db1, dw2, db2, dw3, db3]).  att_w: the forward's (B,T) weights (else recomputed)."""
     B, T, H = keys.shape
     _chk(query, F32, "query", (B, H)); _chk(keys, F32, "keys"); _chk(keys_length, I64, "keys_length", (B,))
@@ -256,7 +271,7 @@ def din_attention_bwd(query, keys, keys_length, w1, b1, w2, b2, w3, b3, g_out, i
     _lib.check(_lib.lib().ctr_din_attention_bwd(_ptr(query), _ptr(keys) if T > 0 else None, _ptr(keys_length), _ptr(w1),
                                                 _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), _ptr(g_out), _ptr(att_w), B, T, H,
                                                 int(bool(is_softmax)), _ptr(dq), _ptr(dk) if T > 0 else None, _ptr(flat),
-                                                _stream()))
+                                                _ptr(_din_sched_scratch(B, query.device, balanced)), _stream()))
     parts = list(torch.split(flat, sizes))
     shapes = [(4 * H, 64), (64,), (64, 32), (32,), tuple(w3_shape), tuple(b3_shape)]
     return dq, dk, [p.reshape(s) for p, s in zip(parts, shapes)]

@@ -58,6 +58,11 @@ def test_din_fwd_bwd(B, T, H, soft):
         # d/db3 is analytically 0 under softmax (shift invariance): judge it on the scale of its sibling dw3
         scale = max(np.abs(ref).max(), 1e-2, np.abs(gr["w3"]).max() if name == "b3" else 0.0)
         assert np.abs(got.cpu().double().numpy() - ref).max() <= TOL * scale, name
+    # static round-robin schedule (sched_scratch = NULL): same per-sample results bit for bit
+    out_s = ops.din_attention_fwd(dev(q), dev(k), dev(lens), *[dev(w) for w in ws], is_softmax=soft, balanced=False)
+    dq_s, dk_s, dws_s = ops.din_attention_bwd(dev(q), dev(k), dev(lens), *[dev(w) for w in ws], dev(g), is_softmax=soft, balanced=False)
+    assert torch.equal(out_s, out) and torch.equal(dq_s, dq) and torch.equal(dk_s, dk)
+    assert_close(dws_s[2], dws[2], TOL, "dw2 (static vs balanced schedule)")
 
 
 def test_din_config4_properties():
