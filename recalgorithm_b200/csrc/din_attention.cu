@@ -295,8 +295,8 @@ din_attention_fwd_kernel(const float* __restrict__ query, const float* __restric
 // 3*H*64 values into shared-memory accumulators; per CTA one set of global atomics at the end.
 // d_params layout: [w1 (4H*64) | b1 (64) | w2 (64*32) | b2 (32) | w3 (32) | b3 (1)]
 struct DinBwdSmem {
-  int wq, wk, wd, b1, w2, b2, w3, aw1a, aw1b, aw1d, ab1, aw2, ab2, aw3, per_warp, warp_stride, total;
-  int o_sc, o_q, o_go, o_ds, o_dk, o_wt, o_h1, o_dp1, o_dp2;      // offsets inside a warp's region
+  int wq, wk, wd, b1, w2, b2, w3, aw2, ab2, aw3, per_warp, warp_stride, total;
+  int o_sc, o_q, o_go, o_ds, o_acc, o_wt, o_h1, o_dp1, o_dp2;     // offsets inside a warp's region
 };
 
 __host__ __device__ inline DinBwdSmem din_bwd_layout(int H, int HP, int T, int warps) {
@@ -309,10 +309,6 @@ __host__ __device__ inline DinBwdSmem din_bwd_layout(int H, int HP, int T, int w
   L.w2 = o; o += DIN_H1 * DIN_H2;
   L.b2 = o; o += DIN_H2;
   L.w3 = o; o += DIN_H2 + 4;
-  L.aw1a = o; o += H * DIN_H1;
-  L.aw1b = o; o += H * DIN_H1;
-  L.aw1d = o; o += H * DIN_H1;
-  L.ab1 = o; o += DIN_H1;
   L.aw2 = o; o += DIN_H1 * DIN_H2;
   L.ab2 = o; o += DIN_H2;
   L.aw3 = o; o += DIN_H2 + 4;                       // dw3 (32) + db3 (1)
@@ -323,7 +319,10 @@ __host__ __device__ inline DinBwdSmem din_bwd_layout(int H, int HP, int T, int w
   L.o_q = w; w += H;
   L.o_go = w; w += H;
   L.o_ds = w; w += T;
-  L.o_dk = w; w += T * H;
+  w = (w + 3) & ~3;
+  L.o_acc = w; w += 3 * H * DIN_H1 + DIN_H1;        // the WARP's private sums of dW1a | dW1b | dW1d | db1 over its samples (plain
+                                                    // read-modify-writes: shared-memory atomics here cost 98 x 64 clk of the SM's
+                                                    // atomic unit per sample = a third of the kernel)
   w = (w + 3) & ~3;
   L.o_wt = w; w += DIN_H1 * (HP + 1);               // Weff^T[c][h], padded rows
   w = (w + 3) & ~3;
@@ -356,9 +355,8 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
     sm[L.wq + i] = a + c;
     sm[L.wk + i] = b - c;
     sm[L.wd + i] = d;
-    sm[L.aw1a + i] = 0.f; sm[L.aw1b + i] = 0.f; sm[L.aw1d + i] = 0.f;
   }
-  for (int i = tid; i < DIN_H1; i += blockDim.x) { sm[L.b1 + i] = __ldg(b1 + i); sm[L.ab1 + i] = 0.f; }
+  for (int i = tid; i < DIN_H1; i += blockDim.x) sm[L.b1 + i] = __ldg(b1 + i);
   for (int i = tid; i < DIN_H1 * DIN_H2; i += blockDim.x) { sm[L.w2 + i] = __ldg(w2 + i); sm[L.aw2 + i] = 0.f; }
   for (int i = tid; i < DIN_H2; i += blockDim.x) {
     sm[L.b2 + i] = __ldg(b2 + i); sm[L.w3 + i] = __ldg(w3 + i); sm[L.ab2 + i] = 0.f; sm[L.aw3 + i] = 0.f;
@@ -372,7 +370,9 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
   float* sq = wsm + L.o_q;
   float* sgo = wsm + L.o_go;
   float* sds = wsm + L.o_ds;
-  float* sdk = wsm + L.o_dk;
+  float* pacc = wsm + L.o_acc;                 // [0,H*64) dW1a | [H*64, 2H*64) dW1b | [2H*64, 3H*64) dW1d | 64 db1
+  for (int i = lane; i < 3 * H * DIN_H1 + DIN_H1; i += 32) pacc[i] = 0.f;
+  __syncwarp();
   float* swt = wsm + L.o_wt;
   float* sh1 = wsm + L.o_h1;
   float* sdp1 = wsm + L.o_dp1;
@@ -471,7 +471,11 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
       const float dwv = sds[t];
       sds[t] = t < len ? (is_softmax ? sc[t] * (dwv - dot) / scale : dwv) : 0.f;
     }
-    for (int i = lane; i < T * H; i += 32) sdk[i] = sc[i / H] * sgo[i % H];
+    // d_keys = w[t]*go (every position, padded ones included) + Weff.dpre1[t] (t < len, added below by the lanes that own (t,h))
+    for (int i = lane; i < T * H; i += 32) {
+      const int t = i / H;
+      if (t >= len) d_keys[(size_t)b * T * H + i] = sc[t] * sgo[i - t * H];
+    }
     __syncwarp();
     // ---------------- positions, DIN_BT at a time: every shared-memory round trip (h1 broadcast, W2 column/row chunks, Weff^T)
     // and every warp sync serves DIN_BT positions; accumulators stay in registers
@@ -591,7 +595,8 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
         for (int tt = 0; tt < DIN_BT; ++tt) {
 #pragma unroll
           for (int o = HP; o < 32; o <<= 1) part[tt] += __shfl_xor_sync(0xffffffffu, part[tt], o);
-          if (grp == 0 && hh < H && tt < n) sdk[(t0 + tt) * H + hh] += part[tt];
+          if (grp == 0 && hh < H && tt < n)
+            d_keys[((size_t)b * T + t0 + tt) * H + hh] = sc[t0 + tt] * sgo[hh] + part[tt];
         }
       }
       __syncwarp();
@@ -606,17 +611,16 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
         v = warp_sum(v);
         if (lane == 0) d_query[(size_t)b * H + h] = v;
         const float qh = sq[h];
-        atomicAdd(sm + L.aw1b + h * DIN_H1 + c0, kd[h][0]);
-        atomicAdd(sm + L.aw1b + h * DIN_H1 + c1, kd[h][1]);
-        atomicAdd(sm + L.aw1d + h * DIN_H1 + c0, qh * kd[h][0]);
-        atomicAdd(sm + L.aw1d + h * DIN_H1 + c1, qh * kd[h][1]);
-        atomicAdd(sm + L.aw1a + h * DIN_H1 + c0, qh * dsum[0]);
-        atomicAdd(sm + L.aw1a + h * DIN_H1 + c1, qh * dsum[1]);
+        float* pa = pacc + h * DIN_H1;
+        float* pb = pa + H * DIN_H1;
+        float* pd = pb + H * DIN_H1;
+        pa[c0] += qh * dsum[0]; pa[c1] += qh * dsum[1];
+        pb[c0] += kd[h][0];     pb[c1] += kd[h][1];
+        pd[c0] += qh * kd[h][0]; pd[c1] += qh * kd[h][1];
       }
     }
-    atomicAdd(sm + L.ab1 + c0, dsum[0]);
-    atomicAdd(sm + L.ab1 + c1, dsum[1]);
-    for (int i = lane; i < T * H; i += 32) d_keys[(size_t)b * T * H + i] = sdk[i];
+    pacc[3 * H * DIN_H1 + c0] += dsum[0];
+    pacc[3 * H * DIN_H1 + c1] += dsum[1];
   }
   // ---------------- merge: warp registers -> CTA shared accumulators -> global
 #pragma unroll
@@ -631,14 +635,25 @@ din_attention_bwd_kernel(const float* __restrict__ query, const float* __restric
   float* dB2 = dW2 + DIN_H1 * DIN_H2;
   float* dW3 = dB2 + DIN_H2;
   float* dB3 = dW3 + DIN_H2;
+  const float* pw0 = sm + L.per_warp + L.o_acc;           // warp w's private sums start at pw0 + w * warp_stride
   for (int i = tid; i < H * DIN_H1; i += blockDim.x) {
-    const float a = sm[L.aw1a + i], bb = sm[L.aw1b + i], d = sm[L.aw1d + i];
+    float a = 0.f, bb = 0.f, d = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < WARPS; ++wv) {
+      const float* pw = pw0 + (size_t)wv * L.warp_stride;
+      a += pw[i]; bb += pw[H * DIN_H1 + i]; d += pw[2 * H * DIN_H1 + i];
+    }
     atomicAdd(dW1 + i, a);
     atomicAdd(dW1 + H * DIN_H1 + i, bb);
     atomicAdd(dW1 + 2 * H * DIN_H1 + i, a - bb);
     atomicAdd(dW1 + 3 * H * DIN_H1 + i, d);
   }
-  for (int i = tid; i < DIN_H1; i += blockDim.x) atomicAdd(dB1 + i, sm[L.ab1 + i]);
+  for (int i = tid; i < DIN_H1; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < WARPS; ++wv) v += pw0[(size_t)wv * L.warp_stride + 3 * H * DIN_H1 + i];
+    atomicAdd(dB1 + i, v);
+  }
   for (int i = tid; i < DIN_H1 * DIN_H2; i += blockDim.x) atomicAdd(dW2 + i, sm[L.aw2 + i]);
   for (int i = tid; i < DIN_H2; i += blockDim.x) { atomicAdd(dB2 + i, sm[L.ab2 + i]); atomicAdd(dW3 + i, sm[L.aw3 + i]); }
   if (tid == 0) atomicAdd(dB3, sm[L.aw3 + DIN_H2]);

@@ -102,23 +102,51 @@ class SymmBuffer:
         self.peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
 
 
-def _pidfd_getfd(pid: int, fd: int) -> int:
-    """Duplicate file descriptor `fd` of process `pid` into this process (Linux >= 5.6; same user)."""
+def exchange_fds(fd: int, group=None) -> List[Optional[int]]:
+    """Every rank of `group` contributes one file descriptor; returns this process's duplicates of all ranks' descriptors
+    (None at the own rank).  Descriptors travel over AF_UNIX sockets (SCM_RIGHTS): each rank listens on an abstract-namespace
+    socket, serves its fd from a helper thread and collects the peers'.  (pidfd_getfd would be shorter but is refused between
+    sibling processes under the usual ptrace restrictions.)"""
     import os
-    libc = ctypes.CDLL(None, use_errno=True)
-    pidfd = os.pidfd_open(pid)
-    try:
-        got = libc.syscall(438, pidfd, fd, 0)             # SYS_pidfd_getfd
-        if got < 0:
-            raise OSError(ctypes.get_errno(), "pidfd_getfd failed")
-        return int(got)
-    finally:
-        os.close(pidfd)
+    import socket
+    import threading
+    import uuid
+    import torch.distributed as dist
+    G, rank = dist.get_world_size(group), dist.get_rank(group)
+    name = "\0ctr_fd_" + uuid.uuid4().hex                   # abstract namespace: nothing to unlink
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(name)
+    srv.listen(G)
+
+    def serve():
+        for _ in range(G - 1):
+            conn, _ = srv.accept()
+            with conn:
+                socket.send_fds(conn, [b"f"], [fd])
+                conn.recv(1)                                  # the peer has its duplicate before this side moves on
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    names = [None] * G
+    dist.all_gather_object(names, name, group=group)
+    out: List[Optional[int]] = [None] * G
+    for r in range(G):
+        if r == rank:
+            continue
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.connect(names[r])
+        with c:
+            _, fds, _, _ = socket.recv_fds(c, 1, 1)
+            out[r] = int(fds[0])
+            c.send(b"k")
+    th.join()
+    srv.close()
+    return out
 
 
 class VmmBuffer:
     """Same role as SymmBuffer with the allocation made by libctr_b200 itself (ctr_vmm_alloc: cuMemCreate + cuMemMap with an
-    explicit size/address alignment) and the peers' mappings imported from file descriptors passed with pidfd_getfd."""
+    explicit size/address alignment) and the peers' mappings imported from file descriptors passed over AF_UNIX sockets."""
 
     def __init__(self, shape, dtype, device, group, align: int = 0):
         import os
@@ -131,18 +159,17 @@ class VmmBuffer:
         self.ptr, self._fd, self.mapped_bytes, self.align = int(p.value), int(fd.value), int(mapped.value), align
         self.tensor = _view(self.ptr, shape, dtype, device)
         G, rank = dist.get_world_size(group), dist.get_rank(group)
-        info = [None] * G
-        dist.all_gather_object(info, (os.getpid(), self._fd, self.mapped_bytes), group=group)
+        sizes = [None] * G
+        dist.all_gather_object(sizes, self.mapped_bytes, group=group)
+        fds = exchange_fds(self._fd, group)
         self.peer_ptrs, self._imported = [], []
         for r in range(G):
             if r == rank:
                 self.peer_ptrs.append(self.ptr)
                 continue
-            pid, rfd, rbytes = info[r]
-            lfd = _pidfd_getfd(pid, rfd)
             q = ctypes.c_void_p()
-            _lib.check(L.ctr_vmm_import(lfd, rbytes, align, ctypes.byref(q)))
-            os.close(lfd)
+            _lib.check(L.ctr_vmm_import(fds[r], sizes[r], align, ctypes.byref(q)))
+            os.close(fds[r])
             self.peer_ptrs.append(int(q.value))
             self._imported.append(int(q.value))
         torch.cuda.synchronize()

@@ -90,3 +90,39 @@ def test_reference_exchange_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True, True), (1, True, True)]
+
+
+def _fd_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank offers the read end of a pipe that already holds its rank byte; the peers read it through their duplicate
+        r_fd, w_fd = os.pipe()
+        os.write(w_fd, bytes([65 + rank]) * (world - 1))
+        fds = S.exchange_fds(r_fd)
+        got = []
+        for r in range(world):
+            if r == rank:
+                assert fds[r] is None
+                continue
+            got.append((r, os.read(fds[r], 1)))
+            os.close(fds[r])
+        q.put((rank, all(b == bytes([65 + r]) for r, b in got) and len(got) == world - 1))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fd_exchange_gloo_world3():
+    """The descriptor hand-over VmmBuffer relies on (AF_UNIX + SCM_RIGHTS), without CUDA: 3 processes swap pipe ends."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fd_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(3)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True), (2, True)]
