@@ -523,24 +523,29 @@ def run_deepfm(args, cfg, dd: Dist):
     rows = cfg["rows_per_field_per_rank"] * world
     if os.environ.get("CTR_BENCH_ROWS"):
         rows = int(os.environ["CTR_BENCH_ROWS"])
-    tables = shard_mod.ShardedEmbeddingTables([rows] * F, D, batch_per_rank=B, device=dev, init="normal",
-                                              shard_backend=args.shard_backend, vmm_align=args.vmm_align << 20)
-    id_sets, ids_desc = make_ids(args, rows, B, F, NB, dev, gen)
     plan = torch.empty((B, F), dtype=torch.int32, device=dev)
 
-    def step(i, ev=None):
-        ids = id_sets[i % NB]
-        if ev:
-            ev[0].record()
-        tables.plan(ids, plan=plan)                                    # queue slots + row indices (contiguous runs over NVLink)
-        if ev:
-            ev[1].record()
-        tables.lookup_fm2(ids, tile=tile, fm2=fm2)                     # rows pulled from the owners over NVLink
-        if ev:
-            ev[2].record()
-        tables.bwd_push(tile, d_tile, d_fm2, plan)                     # gradient rows stored straight into the owners' queues
-        if ev:
-            ev[3].record()
+    def make_sharded(rows_):
+        tb = shard_mod.ShardedEmbeddingTables([rows_] * F, D, batch_per_rank=B, device=dev, init="normal",
+                                              shard_backend=args.shard_backend, vmm_align=args.vmm_align << 20)
+        sets, desc = make_ids(args, rows_, B, F, NB, dev, gen)
+
+        def step_(i, ev=None):
+            ids = sets[i % NB]
+            if ev:
+                ev[0].record()
+            tb.plan(ids, plan=plan, side_stream=True)                      # queue slots + row indices, on a side stream BESIDE the pull
+            if ev:
+                ev[1].record()
+            tb.lookup_fm2(ids, tile=tile, fm2=fm2)                         # rows pulled from the owners over NVLink
+            if ev:
+                ev[2].record()
+            tb.bwd_push(tile, d_tile, d_fm2, plan)                         # gradient rows stored straight into the owners' queues
+            if ev:
+                ev[3].record()
+        return tb, sets, desc, step_
+
+    tables, id_sets, ids_desc, step = make_sharded(rows)
 
     for i in range(args.warmup):
         step(i)
@@ -574,6 +579,26 @@ def run_deepfm(args, cfg, dd: Dist):
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
     del tables
     torch.cuda.empty_cache()
+
+    # BASELINE's literal vocabulary (100 M rows in total, 12.8 GB) split over the same ranks: the shard is 12.8 GB / N per GPU
+    v100 = None
+    if not args.no_extra and "rows_per_field" in cfg:
+        rows100 = cfg["rows_per_field"]
+        tb100, _s, _d, step100 = make_sharded(rows100)
+        for i in range(3):
+            step100(i)
+        n100 = min(args.steps, 50)
+        ms100, (p100, f100, b100) = timed_steps(dd, step100, n100, n_marks=3)
+        tb100.finish_push()
+        nvb = B * F * D * 4 * (world - 1) / world
+        v100 = {"value": world * B * n100 / (ms100 * 1e-3), "ms_per_step": ms100 / n100, "rows_per_field": rows100,
+                "vocab_rows_total": rows100 * F, "shard_bytes_per_gpu": rows100 * F * D * 4 // world,
+                "plan_ms": p100, "pull_ms": f100, "bwd_push_ms": b100, "pull_GBps": nvb / (f100 * 1e-3) / 1e9,
+                "push_GBps": nvb / (b100 * 1e-3) / 1e9,
+                "what": "the same step on BASELINE's literal 100 M-row vocabulary row-sharded over the ranks (smaller shards: the peer "
+                        "mappings' translation reach covers more of the footprint, DESIGN 6)"}
+        del tb100, step100
+        torch.cuda.empty_cache()
 
     # the zero-traffic split of the same batch (replicated 12.8 GB table) for comparison -- NOT the headline at N > 1
     rep = None
@@ -627,7 +652,7 @@ def run_deepfm(args, cfg, dd: Dist):
                 "what": "per rank: pinned-host int32 ids + labels -> H2D -> sharded.lookup_fm2_linear_autograd (peer-pull gather + FM2 + "
                         "dense(1) deep head in one kernel, queue plan) -> sigmoid-CE (torch) -> backward (ctr_embed_fm2_lin_bwd_push: "
                         "gradient rows into the owners' queues + d_w) -> loss D2H, read one step later"},
-        "replicas": rep, "gpu_launches": int(launches), "clocks": clocks,
+        "vocab_100m": v100, "replicas": rep, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
 

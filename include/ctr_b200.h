@@ -123,9 +123,10 @@ int ctr_embed_fm2_lin_fwd_sharded(const float* const* shard_ptrs, int64_t G, con
  * recv_rows / recv_counts: HOST arrays of G device pointers; entry d = owner d's (G_src, capacity) int64 row queue /
  * (G_src,) int64 count vector as mapped into this process; this rank writes slice [my_rank] and, when the kernel ends,
  * recv_counts[d][my_rank] = min(entries queued at d, capacity) (recv_counts or its entries may be NULL).
+ * ids: int64 (ids_are_int32 = 0) or int32 (= 1).
  * counters: device int64[9] scratch, zeroed here (ends as entries per owner + a ticket); overflow: device int, zeroed here.
  * B*F < 2^28, capacity < 2^28. */
-int ctr_sharded_plan(const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F, int64_t G, int64_t my_rank,
+int ctr_sharded_plan(const int64_t* field_row_offset, const void* ids, int ids_are_int32, int64_t B, int64_t F, int64_t G, int64_t my_rank,
                      int64_t* const* recv_rows, int64_t* const* recv_counts, int64_t capacity, int64_t* counters,
                      int* overflow, int32_t* plan, void* stream);
 /* Gradient exchange, step 2, fused into the lookup backward: same arithmetic as ctr_embed_fm2_bwd, but every planned row of

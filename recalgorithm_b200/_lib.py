@@ -44,7 +44,7 @@ SIGNATURES = {
     "ctr_embed_fm2_fwd_sharded_ids32": (c_int, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "ctr_embed_fm2_lin_fwd_sharded": (c_int, [_P, _I, _P, _P, c_int, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "ctr_embed_fm2_lin_bwd_push": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
-    "ctr_sharded_plan": (c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
+    "ctr_sharded_plan": (c_int, [_P, _P, c_int, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "ctr_embed_fm2_bwd_push": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "ctr_sharded_grad_push": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "ctr_rows_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, _I, _P]),

@@ -38,8 +38,12 @@ constexpr int PLAN_CHUNK = PLAN_THREADS * PLAN_IPT;  // 1280 ids = 32 samples at
 constexpr int PLAN_SLOT_BITS = 28;                   // plan word = owner << 28 | slot ; -1 = invalid id / dropped
 constexpr int PLAN_SLOT_MASK = (1 << PLAN_SLOT_BITS) - 1;
 
+__device__ __forceinline__ long long plan_load_id(const long long* p) { return ldg_stream_i64(p); }
+__device__ __forceinline__ long long plan_load_id(const int* p) { return (long long)__ldg(p); }
+
+template <typename IdT>
 __global__ void __launch_bounds__(PLAN_THREADS)
-sharded_plan_kernel(const long long* __restrict__ row_off, const long long* __restrict__ ids, long long n, int F,
+sharded_plan_kernel(const long long* __restrict__ row_off, const IdT* __restrict__ ids, long long n, int F,
                     const PeerQueues q, unsigned long long* __restrict__ counters, int* __restrict__ overflow,
                     int* __restrict__ plan) {
   __shared__ unsigned int s_cnt[8], s_off[9];
@@ -60,7 +64,7 @@ sharded_plan_kernel(const long long* __restrict__ row_off, const long long* __re
       owner[k] = -1; pos[k] = 0; lrow[k] = 0;
       if (e < n) {
         const int f = (int)(e % F);
-        const long long id = ldg_stream_i64(ids + e);
+        const long long id = plan_load_id(ids + e);
         const long long lo = __ldg(row_off + f), hi = __ldg(row_off + f + 1);
         if (id >= 0 && id < hi - lo) {
           owner[k] = (int)((lo + id) & (G - 1));
@@ -346,7 +350,7 @@ static int dispatch_bwd_push(const float* tile, const float* d_tile, const float
 
 using namespace ctr;
 
-extern "C" int ctr_sharded_plan(const int64_t* field_row_offset, const int64_t* ids, int64_t B, int64_t F, int64_t G,
+extern "C" int ctr_sharded_plan(const int64_t* field_row_offset, const void* ids, int ids_are_int32, int64_t B, int64_t F, int64_t G,
                                 int64_t my_rank, int64_t* const* recv_rows, int64_t* const* recv_counts, int64_t capacity,
                                 int64_t* counters, int* overflow, int32_t* plan, void* stream) {
   PeerQueues q;
@@ -361,9 +365,14 @@ extern "C" int ctr_sharded_plan(const int64_t* field_row_offset, const int64_t* 
   const long long chunks = (n + PLAN_CHUNK - 1) / PLAN_CHUNK;
   // B == 0 still runs one CTA: it publishes the zero counts
   const int grid = (int)(chunks < 1 ? 1 : (chunks < (long long)sm_count() * 4 ? chunks : (long long)sm_count() * 4));
-  sharded_plan_kernel<<<grid, PLAN_THREADS, 0, st>>>(reinterpret_cast<const long long*>(field_row_offset),
-                                                     reinterpret_cast<const long long*>(ids), n, (int)F, q,
-                                                     reinterpret_cast<unsigned long long*>(counters), overflow, plan);
+  if (ids_are_int32)
+    sharded_plan_kernel<int><<<grid, PLAN_THREADS, 0, st>>>(reinterpret_cast<const long long*>(field_row_offset),
+                                                            reinterpret_cast<const int*>(ids), n, (int)F, q,
+                                                            reinterpret_cast<unsigned long long*>(counters), overflow, plan);
+  else
+    sharded_plan_kernel<long long><<<grid, PLAN_THREADS, 0, st>>>(reinterpret_cast<const long long*>(field_row_offset),
+                                                                  reinterpret_cast<const long long*>(ids), n, (int)F, q,
+                                                                  reinterpret_cast<unsigned long long*>(counters), overflow, plan);
   CTR_CHECK_LAUNCH("ctr_sharded_plan");
   return CTR_OK;
 }

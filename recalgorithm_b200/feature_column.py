@@ -306,7 +306,9 @@ class _FirstOrder(torch.autograd.Function):
     def forward(ctx, kernel, bias, off, ids):
         ctx.save_for_backward(off, ids)
         ctx.shape = kernel.shape
-        return ops.first_order_fwd(kernel.data.reshape(-1).contiguous(), off, ids, float(bias.item()))
+        # the bias is added on the device: reading it back (bias.item()) would be a host sync on every forward and would
+        # make the step impossible to capture in a CUDA graph
+        return ops.first_order_fwd(kernel.data.reshape(-1).contiguous(), off, ids, 0.0) + bias.data.reshape(1, 1)
 
     @staticmethod
     def backward(ctx, g):

@@ -118,15 +118,18 @@ def _batches(order_epochs: Iterator[np.ndarray], data, batch_size: int, parser) 
         yield parser((buf, off[idx], ln[idx]))
 
 
-def train_input_fn(filepath, example_parser, batch_size: int, num_epochs: int, shuffle_buffer_size: int,
+def train_input_fn(filepath, example_parser, batch_size: int, num_epochs: Optional[int], shuffle_buffer_size: int,
                    seed: Optional[int] = None) -> Iterator[Tuple[dict, dict]]:
     """utils.py:4-26.  Iterating the result is `dataset.make_one_shot_iterator()`; each epoch is reshuffled
     (tf.data's reshuffle_each_iteration default)."""
     data = _load(filepath)
     n = int(data[1].size)
     rng = np.random.default_rng(seed)
+    import itertools
+    # num_epochs=None repeats forever, like dataset.repeat(None) (Estimator callers bound the run with max_steps)
+    rounds = itertools.count() if num_epochs is None else range(num_epochs)
     epochs = (shuffle_order(n, shuffle_buffer_size, rng) if shuffle_buffer_size > 0 else np.arange(n, dtype=np.int64)
-              for _ in range(num_epochs))
+              for _ in rounds)
     return _prefetch(_batches(epochs, data, batch_size, example_parser), depth=1)
 
 

@@ -254,17 +254,38 @@ def mini_batch_aware_regularization(embedding_tensors, l2_lambda: float) -> torc
 
 
 # --------------------------------------------------------------------------------------------------- FFM
+def ffm_table_dim(num_fields: int, embedding_dim: int) -> int:
+    """Row width of the id-major FFM table: (F-1)*K padded up to the next width the fused 128-bit gather takes (a power of
+    two in 4..128) -- the reference's default config (7 fields, K = 8: 48 floats) becomes 64, the padding is zeros."""
+    d = (num_fields - 1) * embedding_dim
+    p = 4
+    while p < d:
+        p *= 2
+    if p > 128:
+        raise ValueError(f"(F-1)*embedding_dim = {d} exceeds the 128-float row of the fused lookup")
+    return p
+
+
 def ffm_second_order(tables: autograd.EmbeddingTables, ids: torch.Tensor, embedding_dim: int) -> torch.Tensor:
-    """FFM/ffm.py:128-160 in two kernels: `tables` holds, per field, rows of (F-1)*K floats -- the reference's
-    ``{name}_embedding`` variable of shape (F-1, |V_i|, K) stored id-major (``EmbeddingTables([...], dim=(F-1)*K)``;
-    `ffm_table_from_reference` converts) -- looked up by the fused gather, then the field-aware pair sum.  Returns (B,1)."""
+    """FFM/ffm.py:128-160 in two kernels: `tables` holds, per field, rows of (F-1)*K floats (zero padded to
+    ``ffm_table_dim(F, K)``) -- the reference's ``{name}_embedding`` variable of shape (F-1, |V_i|, K) stored id-major
+    (``EmbeddingTables([...], dim=ffm_table_dim(F, K))``; `ffm_table_from_reference` converts) -- looked up by the fused
+    gather, then the field-aware pair sum.  Returns (B,1).  Single-valued fields only (the reference's mean-combined
+    ``manual_tag_list`` bag is outside this entry point: look it up with ``ctr_bag_lookup_*`` per slot)."""
     B, F = ids.shape
-    if tables.dim != (F - 1) * embedding_dim:
-        raise ValueError(f"tables.dim must be (F-1)*embedding_dim = {(F - 1) * embedding_dim}, got {tables.dim}")
-    tile = autograd.lookup(tables, ids)                       # (B, F, (F-1)*K)
+    d = (F - 1) * embedding_dim
+    if tables.dim != ffm_table_dim(F, embedding_dim):
+        raise ValueError(f"tables.dim must be ffm_table_dim(F, K) = {ffm_table_dim(F, embedding_dim)}, got {tables.dim}")
+    tile = autograd.lookup(tables, ids)                       # (B, F, padded (F-1)*K)
+    if tables.dim != d:
+        tile = tile[:, :, :d].contiguous()
     return autograd.ffm(tile.reshape(B, F, F - 1, embedding_dim))
 
 
 def ffm_table_from_reference(embedding_variables) -> torch.Tensor:
-    """[(F-1, |V_i|, K) per field] (the reference's variables, ffm.py:129-136) -> the (sum |V_i|, (F-1)*K) id-major table."""
-    return torch.cat([e.permute(1, 0, 2).reshape(e.shape[1], -1) for e in embedding_variables], dim=0).contiguous()
+    """[(F-1, |V_i|, K) per field] (the reference's variables, ffm.py:129-136) -> the (sum |V_i|, ffm_table_dim) id-major table."""
+    F = embedding_variables[0].shape[0] + 1
+    K = embedding_variables[0].shape[2]
+    t = torch.cat([e.permute(1, 0, 2).reshape(e.shape[1], -1) for e in embedding_variables], dim=0)
+    pad = ffm_table_dim(F, K) - t.shape[1]
+    return (torch.nn.functional.pad(t, (0, pad)) if pad else t).contiguous()

@@ -226,6 +226,7 @@ class ShardedEmbeddingTables:
         self.counters = torch.zeros((9,), dtype=torch.int64, device=self.device)      # entries per owner + a ticket
         self.overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self._overflow_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self._side, self._plan_ev = None, None
         self._rendezvous()
 
     def _rendezvous(self):
@@ -268,19 +269,37 @@ class ShardedEmbeddingTables:
         return tile, fm2
 
     # ---- backward: plan + push
-    def plan(self, ids: torch.Tensor, plan: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def plan(self, ids: torch.Tensor, plan: Optional[torch.Tensor] = None, side_stream: bool = False) -> torch.Tensor:
         """Queue slot of every (b,f) at its owner (int32 (B,F); -1 = invalid id / dropped) + the queues' row indices and
-        counts.  The owners' queues are overwritten: the previous step's entries must have been consumed."""
+        counts.  The owners' queues are overwritten: the previous step's entries must have been consumed.
+        side_stream=True: the plan only depends on the ids, so it runs on a second stream beside the forward that is launched
+        right after it (the forward is NVLink-bound and leaves issue slots free); the push calls wait for it."""
         B, F = ids.shape
-        ops._chk(ids, torch.int64, "ids")
+        i32 = ids.dtype == torch.int32
+        ops._chk(ids, torch.int32 if i32 else torch.int64, "ids")
         if plan is None:
             plan = torch.empty((B, F), dtype=torch.int32, device=self.device)
         ops._chk(plan, torch.int32, "plan", (B, F))
-        _lib.check(_lib.lib().ctr_sharded_plan(self.field_row_offset.data_ptr(), ops._ptr(ids), B, F, self.G, self.rank,
-                                               self._r_ptrs, self._c_ptrs, self.capacity, self.counters.data_ptr(),
-                                               self.overflow.data_ptr(), ops._ptr(plan), ops._stream()))
-        self._overflow_host.copy_(self.overflow, non_blocking=True)      # checked in finish_push(), after the stream sync
+        main = torch.cuda.current_stream(self.device)
+        if side_stream:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            ids.record_stream(self._side); plan.record_stream(self._side)
+        with torch.cuda.stream(self._side if side_stream else main):
+            _lib.check(_lib.lib().ctr_sharded_plan(self.field_row_offset.data_ptr(), ops._ptr(ids), int(i32), B, F, self.G, self.rank,
+                                                   self._r_ptrs, self._c_ptrs, self.capacity, self.counters.data_ptr(),
+                                                   self.overflow.data_ptr(), ops._ptr(plan), ops._stream()))
+            self._overflow_host.copy_(self.overflow, non_blocking=True)      # checked in finish_push(), after the stream sync
+            if side_stream:
+                self._plan_ev = torch.cuda.Event()
+                self._plan_ev.record(self._side)
         return plan
+
+    def _wait_plan(self):
+        if self._plan_ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._plan_ev)
+            self._plan_ev = None
 
     def bwd_push(self, tile, d_tile, d_fm2, plan, row_grads=None):
         """Lookup backward fused with the exchange; ``row_grads`` (optional) also keeps the values locally."""
@@ -290,6 +309,7 @@ class ShardedEmbeddingTables:
             d_fm2 = d_fm2.reshape(B)
         ops._chk(d_fm2, torch.float32, "d_fm2", (B,)); ops._chk(plan, torch.int32, "plan", (B, F))
         ops._chk(row_grads, torch.float32, "row_grads", (B, F, D))
+        self._wait_plan()
         _lib.check(_lib.lib().ctr_embed_fm2_bwd_push(ops._ptr(tile), ops._ptr(d_tile), ops._ptr(d_fm2), ops._ptr(plan), B, F, D,
                                                      self.G, self.rank, self._v_ptrs, self.capacity, ops._ptr(row_grads),
                                                      ops._stream()))
@@ -322,6 +342,7 @@ class ShardedEmbeddingTables:
         ops._chk(d_fm2, torch.float32, "d_fm2", (B,)); ops._chk(d_lin, torch.float32, "d_lin", (B,))
         ops._chk(row_grads, torch.float32, "row_grads", (B, F, D))
         d_wlin = torch.empty((F * D,), dtype=torch.float32, device=self.device)
+        self._wait_plan()
         _lib.check(_lib.lib().ctr_embed_fm2_lin_bwd_push(ops._ptr(tile), ops._ptr(wlin), ops._ptr(d_fm2), ops._ptr(d_lin), ops._ptr(plan),
                                                          B, F, D, self.G, self.rank, self._v_ptrs, self.capacity, ops._ptr(row_grads),
                                                          ops._ptr(d_wlin), ops._stream()))
@@ -330,6 +351,7 @@ class ShardedEmbeddingTables:
     def finish_push(self):
         """Stream sync + cross-rank barrier: afterwards this rank's ``recv_rows/recv_vals/recv_counts`` hold what all
         ranks sent to it.  Raises if a queue overflowed (entries were dropped): raise ``slack``."""
+        self._wait_plan()
         torch.cuda.current_stream().synchronize()
         over = torch.tensor([int(self._overflow_host[0])], dtype=torch.int32, device=self.device)
         self.dist.all_reduce(over, op=self.dist.ReduceOp.MAX, group=self.group)     # doubles as the barrier
@@ -343,6 +365,7 @@ class ShardedEmbeddingTables:
         ops._chk(row_grads, torch.float32, "row_grads")
         if plan is None:
             plan = self.plan(ids)
+        self._wait_plan()
         _lib.check(_lib.lib().ctr_sharded_grad_push(ops._ptr(row_grads), ops._ptr(plan), B, F, D, self.G, self.rank, self._v_ptrs,
                                                     self.capacity, ops._stream()))
         if barrier:
@@ -363,14 +386,9 @@ class _ShardedLookupFM2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, tables: ShardedEmbeddingTables, ids: torch.Tensor):
         B, F = ids.shape
-        ids64 = ids
-        if ids.dtype == torch.int32:
-            ids64 = torch.empty((B, F), dtype=torch.int64, device=ids.device)
-            tile, fm2 = tables.lookup_fm2(ids, ids64_out=ids64)
-        else:
-            tile, fm2 = tables.lookup_fm2(ids)
+        ctx.plan = tables.plan(ids, side_stream=True)          # beside the forward (int32 or int64 ids alike)
+        tile, fm2 = tables.lookup_fm2(ids)
         ctx.tables = tables
-        ctx.plan = tables.plan(ids64)
         ctx.save_for_backward(tile)
         return tile, fm2
 
@@ -387,10 +405,9 @@ class _ShardedLookupFM2Linear(torch.autograd.Function):
     def forward(ctx, wlin, tables: ShardedEmbeddingTables, ids: torch.Tensor):
         B, F = ids.shape
         wl = wlin.contiguous()
-        ids64 = torch.empty((B, F), dtype=torch.int64, device=ids.device) if ids.dtype == torch.int32 else None
-        tile, fm2, lin = tables.lookup_fm2_linear(ids, wl, ids64_out=ids64)
+        ctx.plan = tables.plan(ids, side_stream=True)          # beside the forward (int32 or int64 ids alike)
+        tile, fm2, lin = tables.lookup_fm2_linear(ids, wl)
         ctx.tables = tables
-        ctx.plan = tables.plan(ids if ids64 is None else ids64)
         ctx.save_for_backward(tile, wl)
         return fm2, lin
 

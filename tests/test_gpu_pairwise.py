@@ -154,21 +154,30 @@ def test_full_size_bi_interaction_properties():
 @pytest.mark.parametrize("name", ["ffm_F4_K4", "ffm_F5_K8", "ffm_F9_K16"])
 def test_ffm_golden_through_the_lookup(name):
     """FFM/ffm.py:145-160 executed on per-field (F-1, |V|, K) variables vs: reference variables -> id-major table -> fused
-    lookup -> ctr_ffm_fwd.  D = (F-1)*K is 12, 32 and 128 here (12 is not a power of two: the layer must refuse it cleanly)."""
+    lookup -> ctr_ffm_fwd.  D = (F-1)*K is 12, 32 and 128 here (12 is not a power of two: the table rows are zero padded to 16)."""
     from recalgorithm_b200 import _lib, autograd, layers as L, ops
     g = golden(name)
     B, F = g["ids"].shape
     K = g["tile"].shape[-1]
     assert_close(ops.ffm_fwd(dev(g["tile"])), g["out_f64"], TOL, "ffm on the fixture tile")
     embs = [torch.from_numpy(g[f"emb_{f}"]) for f in range(F)]
-    D = (F - 1) * K
+    D = L.ffm_table_dim(F, K)
+    assert D >= (F - 1) * K and D & (D - 1) == 0
     tables = autograd.EmbeddingTables([e.shape[1] for e in embs], D, device="cuda", init=None)
     tables.weight.copy_(L.ffm_table_from_reference(embs))
-    if D & (D - 1):
-        with pytest.raises(_lib.CtrError):
-            L.ffm_second_order(tables, dev(g["ids"]), K)
-        return
     assert_close(L.ffm_second_order(tables, dev(g["ids"]), K), g["out_f64"], TOL, "lookup + ffm vs ffm.py executed")
+    # the reference's default shape (7 fields, K = 8 -> 48 floats per row, padded to 64): forward + IndexedSlices backward
+    F7, K8, V = 7, 8, 11
+    gen = torch.Generator().manual_seed(3)
+    embs7 = [torch.randn((F7 - 1, V, K8), generator=gen) for _ in range(F7)]
+    t7 = autograd.EmbeddingTables([V] * F7, L.ffm_table_dim(F7, K8), device="cuda", init=None)
+    t7.weight.copy_(L.ffm_table_from_reference(embs7))
+    ids7 = torch.randint(0, V, (33, F7), generator=gen).cuda()
+    out7 = L.ffm_second_order(t7, ids7, K8)
+    tile7 = torch.stack([torch.stack([embs7[f][:, ids7[b, f].item(), :] for f in range(F7)]) for b in range(33)]).numpy()
+    assert_close(out7, O.ffm_fwd(tile7.astype(np.float64)), TOL, "FFM at the reference's default width (48 -> 64)")
+    out7.sum().backward()
+    assert t7.grad_slices[0].values.shape == (33, F7, 64) and float(t7.grad_slices[0].values[:, :, 48:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("B,F,K", [(3, 2, 4), (65, 5, 8), (17, 9, 16), (8, 7, 3), (40, 12, 10)])

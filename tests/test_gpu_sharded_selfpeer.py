@@ -61,7 +61,7 @@ class LocalShardGroup:
         from recalgorithm_b200 import _lib, ops
         B, F = ids.shape
         plan = torch.empty((B, F), dtype=torch.int32, device=ids.device)
-        _lib.check(_lib.lib().ctr_sharded_plan(self.off.data_ptr(), ops._ptr(ids), B, F, self.G, rank, self.r_ptrs, self.c_ptrs,
+        _lib.check(_lib.lib().ctr_sharded_plan(self.off.data_ptr(), ops._ptr(ids), int(ids.dtype == torch.int32), B, F, self.G, rank, self.r_ptrs, self.c_ptrs,
                                                self.capacity, self.counters.data_ptr(), self.overflow.data_ptr(), ops._ptr(plan),
                                                ops._stream()))
         return plan
@@ -127,6 +127,8 @@ def test_selfpeer_lookup_plan_push(G, B, F, D, rows_each):
         d_tile = torch.randn((B, F, D), device=dev, generator=gen)
         d_fm2 = torch.randn((B,), device=dev, generator=gen)
         row_grads = ops.embed_fm2_bwd(tile, d_tile, d_fm2)
+        plan = grp.plan(rank, ids)
+        assert torch.equal((grp.plan(rank, ids.int()) >> 28), (plan >> 28)), "int32 ids plan to the same owners"
         plan = grp.plan(rank, ids)
         # plan words: valid ids have owner = global row % G and a slot below the published count; invalid ids are -1
         gr = ids + grp.off[:-1][None, :]

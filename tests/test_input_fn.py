@@ -78,3 +78,13 @@ def test_prefetch_thread_stops_when_consumer_leaves_and_forwards_errors(dataset)
         raise ValueError("boom")
     with pytest.raises(ValueError, match="boom"):
         list(I.eval_input_fn(p, bad_parser, batch_size=8))
+
+
+def test_num_epochs_none_repeats_forever(dataset):
+    """dataset.repeat(None): the iterator never ends by itself (Estimator callers stop it with max_steps)."""
+    import itertools
+    p, n, parser = dataset
+    it = I.train_input_fn(p, parser, batch_size=n, num_epochs=None, shuffle_buffer_size=0)
+    taken = list(itertools.islice(it, 5))                  # five full passes, no StopIteration
+    it.close()
+    assert len(taken) == 5
