@@ -452,7 +452,7 @@ def run_deepfm(args, cfg, dd: Dist):
             tables.zero_grad()
             w_deep.grad = None
             f_, lin = autograd.lookup_fm2_linear(tables, ids_dev, w_deep)          # deep head fused into the gather
-            loss = torch.nn.functional.binary_cross_entropy_with_logits(f_ + lin, lab_dev)
+            loss = autograd.sigmoid_cross_entropy_mean(f_, lab_dev, logit_b=lin)   # add_n of the logits + sigmoid-CE + its gradient, one launch
             loss.backward()
             return loss
 
@@ -496,7 +496,7 @@ def run_deepfm(args, cfg, dd: Dist):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4,
                     "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1], **pcie,
                     "what": "pinned-host int32 ids + labels -> H2D (double-buffered on a copy stream) -> autograd.lookup_fm2_linear "
-                            "(gather + FM2 + dense(1) deep head in one kernel; ids widened on device) -> sigmoid-CE (torch) -> backward "
+                            "(gather + FM2 + dense(1) deep head in one kernel; ids widened on device) -> autograd.sigmoid_cross_entropy_mean (logit sum + loss + gradient, one launch) -> backward "
                             "(ctr_embed_fm2_lin_bwd -> IndexedSlices + d_w) -> loss D2H to pinned memory, read on the host one step later",
                     "unfused_head": {"value": world * B * e2e_steps / (e2e_ms_unf * 1e-3), "ms_per_step": e2e_ms_unf / e2e_steps,
                                      "loss_last": losses_unf[-1],
@@ -570,7 +570,7 @@ def run_deepfm(args, cfg, dd: Dist):
     def model_sharded(ids_dev, lab_dev):
         w_deep.grad = None
         f_, lin = shard_mod.lookup_fm2_linear_autograd(tables, ids_dev, w_deep)     # dense(1) deep head fused into the gather
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(f_ + lin, lab_dev)
+        loss = autograd.sigmoid_cross_entropy_mean(f_, lab_dev, logit_b=lin)
         loss.backward()
         return loss
 
@@ -650,7 +650,7 @@ def run_deepfm(args, cfg, dd: Dist):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4, "d2h_bytes_per_step": 4,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1],
                 "what": "per rank: pinned-host int32 ids + labels -> H2D -> sharded.lookup_fm2_linear_autograd (peer-pull gather + FM2 + "
-                        "dense(1) deep head in one kernel, queue plan) -> sigmoid-CE (torch) -> backward (ctr_embed_fm2_lin_bwd_push: "
+                        "dense(1) deep head in one kernel, queue plan beside it) -> sigmoid-CE (ctr_sigmoid_ce) -> backward (ctr_embed_fm2_lin_bwd_push: "
                         "gradient rows into the owners' queues + d_w) -> loss D2H, read one step later"},
         "vocab_100m": v100, "replicas": rep, "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -93,6 +93,12 @@ int ctr_embed_fm2_lin_fwd(const float* table, const int64_t* field_row_offset, c
 int ctr_embed_fm2_lin_bwd(const float* tile, const float* wlin, const float* d_fm2, const float* d_lin, int64_t B, int64_t F,
                           int64_t D, float* row_grads, float* d_wlin, void* stream);
 
+/* Mean sigmoid cross-entropy of logits = logit_a (+ logit_b, may be NULL) against labels, (B) each, and its gradient in one
+ * launch: *loss = mean_b[max(x,0) - x*z + log1p(exp(-|x|))] (tf.nn.sigmoid_cross_entropy_with_logits + reduce_mean,
+ * DeepFM/deepfm.py:214,235), d_logit[b] = (sigmoid(x) - z)/B (may be NULL).  fp32 atomics across CTAs for the mean. */
+int ctr_sigmoid_ce(const float* logit_a, const float* logit_b, const float* labels, int64_t B, float* loss, float* d_logit,
+                   void* stream);
+
 /* Densify: grad_table[field_row_offset[f] + ids[b,f], :] += row_grads[b,f,:] for valid ids (duplicates
  * summed, like the optimizer's IndexedSlices de-duplication; TF-internal).  grad_table is
  * NOT zeroed here.  fp32 red.global.add -> summation order is not deterministic. */

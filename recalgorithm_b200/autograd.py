@@ -122,6 +122,27 @@ def lookup_fm2_linear(tables: EmbeddingTables, ids: torch.Tensor, wlin: torch.Te
     return _LookupFM2Linear.apply(wlin, tables, ids)
 
 
+class _SigmoidCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logit_a, logit_b, labels):
+        loss, d = ops.sigmoid_ce(logit_a.contiguous(), None if logit_b is None else logit_b.contiguous(), labels.contiguous())
+        ctx.save_for_backward(d)
+        ctx.shapes = (logit_a.shape, None if logit_b is None else logit_b.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        gd = d * g                                              # g is the scalar upstream gradient (1 for loss.backward())
+        return gd.reshape(ctx.shapes[0]), (None if ctx.shapes[1] is None else gd.reshape(ctx.shapes[1])), None
+
+
+def sigmoid_cross_entropy_mean(logit_a: torch.Tensor, labels: torch.Tensor, logit_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """reduce_mean(sigmoid_cross_entropy_with_logits(labels, logit_a [+ logit_b])) (DeepFM/deepfm.py:214,235) with its gradient
+    computed by the same launch; returns the scalar loss."""
+    return _SigmoidCE.apply(logit_a, logit_b, labels)
+
+
 class _CrossStack(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, xl, w, b):

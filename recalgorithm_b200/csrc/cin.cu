@@ -513,6 +513,11 @@ extern "C" int ctr_cin_fwd(const float* x0, const float* xk, const float* filter
   const long long rows_total = (long long)B * D;
   const int num_pairs = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
   const int grid = num_pairs < sm_count() ? num_pairs : sm_count();
+  // K-blocks per TMEM accumulation chain of the 3xTF32 path: 12 MMAs each.  The fp32 accumulate of the tensor core truncates
+  // (~2.6e-8 relative per MMA, measured 3.8e-5 after 1440): 16 blocks = 192 MMAs keeps the drift near 5e-6 and halves the
+  // number of accumulator drains (each one stalls the MMA pipe: the accumulator cannot be double-buffered next to two
+  // M-tiles and the A staging in 512 TMEM columns).
+  constexpr int CHUNK3 = 16;
 #define CIN_LAUNCH(PASSES_, SB_, NPT_, CHUNK_)                                                                        \
   {                                                                                                                   \
     const FwdSmem L = fwd_smem(NP, PASSES_, SB_);                                                                     \
@@ -522,7 +527,7 @@ extern "C" int ctr_cin_fwd(const float* x0, const float* xk, const float* filter
                                               CHUNK_);                                                                \
   }
   if (precision == 0) {
-    if (NP <= 32) CIN_LAUNCH(3, 4, 32, 8) else if (NP <= 64) CIN_LAUNCH(3, 4, 64, 8) else CIN_LAUNCH(3, 4, 128, 8)
+    if (NP <= 32) CIN_LAUNCH(3, 4, 32, CHUNK3) else if (NP <= 64) CIN_LAUNCH(3, 4, 64, CHUNK3) else CIN_LAUNCH(3, 4, 128, CHUNK3)
   } else {
     if (NP <= 32) CIN_LAUNCH(1, 6, 32, 32) else if (NP <= 64) CIN_LAUNCH(1, 6, 64, 32) else CIN_LAUNCH(1, 6, 128, 32)
   }

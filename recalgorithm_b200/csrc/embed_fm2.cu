@@ -692,7 +692,8 @@ static int launch_fwd_lin(const float* table, const PeerTables* peers, const int
                             reinterpret_cast<float4*>(tile), fm2, reinterpret_cast<long long*>(ids64_out),
                             reinterpret_cast<const float4*>(wlin), lin);
   } else {
-    auto k = embed_fm2_fwd_kernel<LPR, false, 4, false, IdT, true>;
+    // 3 CTAs/SM (85 registers): at the 64 registers of the plain gather this variant spills 88 bytes in its inner loop
+    auto k = embed_fm2_fwd_kernel<LPR, false, 3, false, IdT, true>;
     const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
     k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), PeerTables{}, reinterpret_cast<const long long*>(off), ids, (int)B,
                             (int)F, reinterpret_cast<float4*>(tile), fm2, reinterpret_cast<long long*>(ids64_out),

@@ -143,6 +143,17 @@ def embed_fm2_lin_bwd(tile: torch.Tensor, wlin: torch.Tensor, d_fm2: Optional[to
     return row_grads, d_wlin
 
 
+def sigmoid_ce(logit_a: torch.Tensor, logit_b: Optional[torch.Tensor], labels: torch.Tensor, want_grad: bool = True):
+    """Mean sigmoid cross-entropy of (logit_a + logit_b) vs labels and d(loss)/d(logit) in one launch: (loss (1,), d_logit (B,1))."""
+    B = logit_a.numel()
+    a = logit_a.reshape(B); b = None if logit_b is None else logit_b.reshape(B); y = labels.reshape(B)
+    _chk(a, F32, "logit_a"); _chk(b, F32, "logit_b", (B,)); _chk(y, F32, "labels", (B,))
+    loss = torch.empty((1,), dtype=F32, device=a.device)
+    d = torch.empty((B, 1), dtype=F32, device=a.device) if want_grad else None
+    _lib.check(_lib.lib().ctr_sigmoid_ce(_ptr(a), _ptr(b), _ptr(y), B, _ptr(loss), _ptr(d), _stream()))
+    return loss, d
+
+
 def embed_scatter_add(grad_table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor,
                       row_grads: torch.Tensor) -> torch.Tensor:
     B, F, D = row_grads.shape

@@ -214,3 +214,27 @@ def test_empty_batch_is_a_no_op_everywhere():
     assert ops.bst_transformer_fwd(z(0, 6, D), z(0, 6, D), z(0, 6, D), lens, packed, 2, 6).shape == (0, 6, D)
     *_, dpk = ops.bst_transformer_bwd(z(0, 6, D), z(0, 6, D), z(0, 6, D), lens, packed, z(0, 6, D), 2, 6)
     assert float(dpk.abs().max()) == 0
+
+
+@pytest.mark.parametrize("B", [1, 7, 256, 65536])
+def test_sigmoid_ce_matches_the_reference_formula(B):
+    """ctr_sigmoid_ce vs reduce_mean(sigmoid_cross_entropy_with_logits) (deepfm.py:235; stable form) in float64,
+    value and gradient through autograd, with one and with two summed logits."""
+    import numpy as np
+    from recalgorithm_b200 import autograd
+    gen = torch.Generator(device="cuda").manual_seed(B)
+    a = (torch.randn((B, 1), device="cuda", generator=gen) * 3).requires_grad_()
+    b = (torch.randn((B, 1), device="cuda", generator=gen) * 3).requires_grad_()
+    y = (torch.rand((B, 1), device="cuda", generator=gen) < 0.3).float()
+    for two in (False, True):
+        a.grad = b.grad = None
+        loss = autograd.sigmoid_cross_entropy_mean(a, y, logit_b=b if two else None)
+        (loss * 2.0).backward()
+        x = (a.detach() + (b.detach() if two else 0)).double()
+        x.requires_grad_()
+        ref = (torch.clamp(x, min=0) - x * y.double() + torch.log1p(torch.exp(-x.abs()))).mean()
+        (ref * 2.0).backward()
+        assert_close(loss.reshape(1), ref.detach().reshape(1), 1e-5, "sigmoid-CE mean")
+        assert_close(a.grad, x.grad, 1e-5, "d loss / d logit")
+        if two:
+            assert torch.equal(a.grad, b.grad)
