@@ -74,6 +74,13 @@ int ctr_embed_fm2_fwd(const float* table, const int64_t* field_row_offset, const
 int ctr_embed_fm2_fwd_ids32(const float* table, const int64_t* field_row_offset, const int32_t* ids, int64_t B, int64_t F,
                             int64_t D, float* tile, float* fm2, int64_t* ids64_out, void* stream);
 
+/* Sequence lookup: ids (B, T) all index ONE table -- rows [row_range[0], row_range[1]) of `table` (device int64[2]) -- e.g.
+ * the padded behaviour history of tf.contrib.feature_column.sequence_input_layer over a shared embedding (DIN/din.py:209-214).
+ * out (B, T, D); id < 0 or out of range -> zero row (the zero padding).  One warp per sample, like ctr_embed_fm2_fwd.  Its
+ * gradient is the IndexedSlices (ids, d_out) as is -- no kernel. */
+int ctr_embed_seq_fwd(const float* table, const int64_t* row_range, const int64_t* ids, int64_t B, int64_t T, int64_t D,
+                      float* out, void* stream);
+
 /* Backward of the pair above = the `values` of TF's IndexedSlices gradient of the gather
  * (indices are the caller's ids):   row_grads[b,f,:] = d_tile[b,f,:] + d_fm2[b] * (S[b,:] - e[b,f,:]),
  * S = sum_f e[b,f,:].   tile = the forward output; d_tile (B,F,D) and d_fm2 (B) may each be NULL (= 0).

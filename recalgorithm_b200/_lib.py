@@ -36,6 +36,7 @@ SIGNATURES = {
     "ctr_kernel_launches": (c_int64, []),
     "ctr_embed_fm2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ctr_embed_fm2_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "ctr_embed_seq_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "ctr_sigmoid_ce": (c_int, [_P, _P, _P, _I, _P, _P, _P]),
     "ctr_embed_scatter_add": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ctr_embed_fm2_fwd_sharded": (c_int, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),

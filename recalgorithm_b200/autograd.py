@@ -81,7 +81,10 @@ class _LookupFM2(torch.autograd.Function):
         if fused is not None:                       # optim.TableAdam(fused_backward=True): the row update happens right here
             fused.apply_fused(tile, d_tile, d_fm2 if ctx.want_fm2 else None, ctx.ids)
             return None, None, None, None
-        values = ops.embed_fm2_bwd(tile, d_tile, d_fm2 if ctx.want_fm2 else None)
+        if not ctx.want_fm2 and d_tile is not None:
+            values = d_tile                                      # plain gather: the IndexedSlices values ARE the upstream gradient
+        else:
+            values = ops.embed_fm2_bwd(tile, d_tile, d_fm2 if ctx.want_fm2 else None)
         ctx.tables.grad_slices.append(IndexedSlices(values, ctx.ids, ctx.tables.field_row_offset))
         return None, None, None, None
 

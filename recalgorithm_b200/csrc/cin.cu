@@ -514,10 +514,10 @@ extern "C" int ctr_cin_fwd(const float* x0, const float* xk, const float* filter
   const int num_pairs = (int)((rows_total + TILES * BM - 1) / (TILES * BM));
   const int grid = num_pairs < sm_count() ? num_pairs : sm_count();
   // K-blocks per TMEM accumulation chain of the 3xTF32 path: 12 MMAs each.  The fp32 accumulate of the tensor core truncates
-  // (~2.6e-8 relative per MMA, measured 3.8e-5 after 1440): 16 blocks = 192 MMAs keeps the drift near 5e-6 and halves the
-  // number of accumulator drains (each one stalls the MMA pipe: the accumulator cannot be double-buffered next to two
-  // M-tiles and the A staging in 512 TMEM columns).
-  constexpr int CHUNK3 = 16;
+  // (~2.6e-8 relative per MMA, measured 3.8e-5 after 1440 MMAs).  8 blocks = 96 MMAs.  16 blocks (192 MMAs, half the drains)
+  // was measured in round 2: 2.94 -> 2.88 ms per config-3 step, but the element-wise error reaches 0.9-1.5x the 1e-5 bound
+  // (profiles/r2_cin_chunk16.jsonl) -- not worth 2 %.
+  constexpr int CHUNK3 = 8;
 #define CIN_LAUNCH(PASSES_, SB_, NPT_, CHUNK_)                                                                        \
   {                                                                                                                   \
     const FwdSmem L = fwd_smem(NP, PASSES_, SB_);                                                                     \

@@ -590,7 +590,7 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
     if (nslices < 1) nslices = 1;
     if (nslices > B) nslices = (int)B;
     const int grid = ngroups * nslices;
-    const int chunk = (int)(512 / D);                        // 192 chained MMAs per accumulator before a drain (see cin.cu CHUNK3)
+    const int chunk = (int)(256 / D);                        // 96 chained MMAs per accumulator before a drain (see cin.cu CHUNK3)
 #define DW_LAUNCH(NPT_, D_)                                                                                          \
   {                                                                                                                  \
     auto k = cin_bwd_dw_tc_kernel<SB, NPT_, D_>;                                                                     \

@@ -48,7 +48,10 @@ __device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
 
 // LIN: a dense(1) consumer of the flattened tile is fused in: lin[b] = sum_{f,d} e[b,f,d] * wlin[f,d] (the kernel of a
 // tf.layers.dense(units=1, use_bias=False) over the (B, F*D) input_layer output), so the consumer never re-streams the tile.
-template <int LPR, bool SH, int MINB, bool BI = false, typename IdT = long long, bool LIN = false>
+// SEQ: every column of the id matrix indexes the SAME table (rows [row_off[0], row_off[1])): the (B, T) history of a sequence
+// feature (sequence_input_layer over a shared embedding, DIN/din.py:209-214) gathered with one warp per sample instead of
+// one per id.
+template <int LPR, bool SH, int MINB, bool BI = false, typename IdT = long long, bool LIN = false, bool SEQ = false>
 __global__ void __launch_bounds__(256, MINB)
 embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, const long long* __restrict__ row_off,
                      const IdT* __restrict__ ids, int B, int F, float4* __restrict__ tile,
@@ -71,7 +74,7 @@ embed_fm2_fwd_kernel(const float4* __restrict__ table, const PeerTables peers, c
       long long row = -1;
       if (lane < nf) {
         const long long id = load_id(ids + (size_t)b * F + f0 + lane);
-        const long long lo = __ldg(row_off + f0 + lane), hi = __ldg(row_off + f0 + lane + 1);
+        const long long lo = __ldg(row_off + (SEQ ? 0 : f0 + lane)), hi = __ldg(row_off + (SEQ ? 1 : f0 + lane + 1));
         row = (id >= 0 && id < hi - lo) ? lo + id : -1;      // OOV(-1)/out-of-range -> zero vector
         if (sizeof(IdT) == 4 && ids64_out != nullptr) ids64_out[(size_t)b * F + f0 + lane] = id;
       }
@@ -788,5 +791,36 @@ extern "C" int ctr_embed_fm2_lin_bwd(const float* tile, const float* wlin, const
     case 8: return dispatch_lin_bwd<8>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
     case 16: return dispatch_lin_bwd<16>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
     default: return dispatch_lin_bwd<32>(tile, wlin, d_fm2, d_lin, B, F, row_grads, d_wlin, st);
+  }
+}
+
+// ---- sequence lookup: (B, T) ids into ONE table -> (B, T, D), zero rows for id -1 / out of range (the zero padding of
+// tf.contrib.feature_column.sequence_input_layer, DIN/din.py:209-214) -------------------------------------------------------
+template <int LPR>
+static int launch_seq(const float* table, const int64_t* range2, const int64_t* ids, int64_t B, int64_t T, float* out, cudaStream_t st) {
+  auto k = embed_fm2_fwd_kernel<LPR, false, 4, false, long long, false, true>;
+  const int grid = resident_grid(k, 256, 0, (B + 7) / 8);
+  k<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), PeerTables{}, reinterpret_cast<const long long*>(range2),
+                          reinterpret_cast<const long long*>(ids), (int)B, (int)T, reinterpret_cast<float4*>(out), nullptr, nullptr,
+                          nullptr, nullptr);
+  CTR_CHECK_LAUNCH("ctr_embed_seq_fwd");
+  return CTR_OK;
+}
+
+extern "C" int ctr_embed_seq_fwd(const float* table, const int64_t* row_range, const int64_t* ids, int64_t B, int64_t T, int64_t D,
+                                 float* out, void* stream) {
+  int rc = check_bfd("ctr_embed_seq_fwd", B, T > 0 ? T : 1, D);
+  if (rc) return rc;
+  CTR_REQUIRE(table && row_range && out && (ids || B * T == 0), "ctr_embed_seq_fwd: null argument");
+  CTR_REQUIRE(aligned16(table) && aligned16(out), "ctr_embed_seq_fwd: table and out must be 16-byte aligned");
+  if (B == 0 || T == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  switch (D / 4) {
+    case 1: return launch_seq<1>(table, row_range, ids, B, T, out, st);
+    case 2: return launch_seq<2>(table, row_range, ids, B, T, out, st);
+    case 4: return launch_seq<4>(table, row_range, ids, B, T, out, st);
+    case 8: return launch_seq<8>(table, row_range, ids, B, T, out, st);
+    case 16: return launch_seq<16>(table, row_range, ids, B, T, out, st);
+    default: return launch_seq<32>(table, row_range, ids, B, T, out, st);
   }
 }

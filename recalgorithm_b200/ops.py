@@ -143,6 +143,23 @@ def embed_fm2_lin_bwd(tile: torch.Tensor, wlin: torch.Tensor, d_fm2: Optional[to
     return row_grads, d_wlin
 
 
+def embed_seq_fwd(table: torch.Tensor, ids: torch.Tensor, row_range: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sequence lookup: ids (B,T) int64 all index ONE table (rows [row_range[0], row_range[1]) of `table`, default the whole
+    table) -> (B,T,D); id < 0 / out of range -> zero row.  The gradient is the IndexedSlices (ids, d_out) as is."""
+    B, T = ids.shape
+    V, D = table.shape
+    _chk(table, F32, "table"); _chk(ids, I64, "ids")
+    if row_range is None:
+        row_range = torch.tensor([0, V], dtype=I64, device=table.device)
+    _chk(row_range, I64, "row_range", (2,))
+    if out is None:
+        out = torch.empty((B, T, D), dtype=F32, device=table.device)
+    _chk(out, F32, "out", (B, T, D))
+    _lib.check(_lib.lib().ctr_embed_seq_fwd(_ptr(table), _ptr(row_range), _ptr(ids), B, T, D, _ptr(out), _stream()))
+    return out
+
+
 def sigmoid_ce(logit_a: torch.Tensor, logit_b: Optional[torch.Tensor], labels: torch.Tensor, want_grad: bool = True):
     """Mean sigmoid cross-entropy of (logit_a + logit_b) vs labels and d(loss)/d(logit) in one launch: (loss (1,), d_logit (B,1))."""
     B = logit_a.numel()

@@ -189,3 +189,21 @@ def test_int32_ids_and_fused_linear_head(B, F, D):
     ((f_a.reshape(-1) * dev(g)).sum() + (l_a.reshape(-1) * dev(gl)).sum()).backward()
     assert torch.equal(tables.grad_slices[0].values, rg) and torch.equal(tables.grad_slices[0].ids, dev(ids))
     assert_close(w_a.grad.reshape(-1), dw, TOL, "autograd d_wlin")
+
+
+@pytest.mark.parametrize("B,T,D", [(1, 1, 4), (33, 50, 16), (257, 7, 8), (64, 70, 32), (5, 3, 128)])
+def test_sequence_lookup(B, T, D):
+    """ctr_embed_seq_fwd: a (B,T) id matrix over ONE table == the F = 1 lookup of every id, zero rows for -1 / out of range."""
+    from recalgorithm_b200 import ops
+    rng = np.random.default_rng(B + T + D)
+    V = 91
+    table = trunc_normal(rng, (V + 10, D), 0.5)
+    ids = rng.integers(-1, V + 2, size=(B, T)).astype(np.int64)
+    rr = torch.tensor([5, 5 + V], device="cuda")
+    out = ops.embed_seq_fwd(dev(table), dev(ids), rr)
+    valid = (ids >= 0) & (ids < V)
+    want = table[5 + np.clip(ids, 0, V - 1)] * valid[..., None]
+    assert np.array_equal(out.cpu().numpy(), want), "sequence lookup must copy rows bit-exactly"
+    off = torch.tensor([5, 5 + V], device="cuda")
+    flat, _ = ops.embed_fm2_fwd(dev(table), off, dev(ids.reshape(-1, 1)), want_fm2=False)
+    assert torch.equal(flat.reshape(B, T, D), out)

@@ -55,10 +55,10 @@ def build_dcn_cfg2(rows=1_000_000, B=4096):
         _rec(ev, 2)
         dx0, _, _, _ = ops.cross_bwd(x0, w, bb, g)
         _rec(ev, 3)
-        ops.embed_fm2_bwd(tile, dx0.view(B, F, D), None)
+        # lookup backward of a plain gather (no FM2 term): the IndexedSlices values ARE dx0.view(B,F,D) -- no kernel, no bytes
         _rec(ev, 4)
 
-    bytes_step = B * (F * (8 + 2 * D * 4) + 20 * d + 3 * F * D * 4)     # lookup fwd + cross fwd/bwd (20*d) + lookup bwd
+    bytes_step = B * (F * (8 + 2 * D * 4) + 20 * d)                      # lookup fwd + cross fwd/bwd (20*d); lookup bwd is an alias
 
     def roofline(ms, ms_step, peaks):
         ach = B * 3 * d * 4 / (ms["cross_bwd"] * 1e-3) / 1e9
@@ -98,7 +98,7 @@ def build_xdeepfm_cfg3(rows=1_000_000, B=8192):
         g1 = dx1 + gp[:, :H].unsqueeze(-1)
         dx0a, dxk, _ = ops.cin_bwd(x0, x0, w1, g1.contiguous())
         _rec(ev, 3)
-        ops.embed_fm2_bwd(x0, (dx0a + dxk + dx0b).contiguous(), None)
+        _values = dx0a + dxk + dx0b                                         # sum of the three paths into x0 = the IndexedSlices values
         _rec(ev, 4)
 
     flops_fwd = 2.0 * B * D * (F * F * H + H * F * H)
@@ -130,10 +130,11 @@ def build_din_cfg4(rows=1_000_000, B=4096):
     pad = (torch.arange(T, device="cuda")[None, :] >= lens[:, None]).reshape(-1)
     hists, tgts = [], []
     for _ in range(4):
-        h = torch.randint(0, rows, (B * T, 1), device="cuda", generator=gen)
+        h = torch.randint(0, rows, (B * T,), device="cuda", generator=gen)
         h[pad] = -1                                                        # padding -> zero vectors
-        hists.append(h)
+        hists.append(h.reshape(B, T).contiguous())
         tgts.append(torch.randint(0, rows, (B, 1), device="cuda", generator=gen))
+    rng2 = torch.tensor([0, rows], device="cuda")
     ws = [_rn(gen, 4 * Hd, 64, std=0.2), _rn(gen, 64, std=0.1), _rn(gen, 64, 32, std=0.2), _rn(gen, 32, std=0.1),
           _rn(gen, 32, 1, std=0.3), _rn(gen, 1, std=0.1)]
     go = _rn(gen, B, Hd)
@@ -142,16 +143,15 @@ def build_din_cfg4(rows=1_000_000, B=4096):
     def step(ev=None):
         k[0] += 1
         _rec(ev, 0)
-        keys, _ = ops.embed_fm2_fwd(tab, off, hists[k[0] % 4], want_fm2=False)
+        k3 = ops.embed_seq_fwd(tab, hists[k[0] % 4], rng2)                # (B,T) history: one warp per sample (ctr_embed_seq_fwd)
         q, _ = ops.embed_fm2_fwd(tab, off, tgts[k[0] % 4], want_fm2=False)
-        k3, q2 = keys.view(B, T, Hd), q.view(B, Hd)
+        q2 = q.view(B, Hd)
         _rec(ev, 1)
         out, att = ops.din_attention_fwd(q2, k3, lens, *ws, want_weights=True)
         _rec(ev, 2)
         dq, dk, _ = ops.din_attention_bwd(q2, k3, lens, *ws, go, att_w=att)
         _rec(ev, 3)
-        ops.embed_fm2_bwd(keys, dk.view(B * T, 1, Hd), None)
-        ops.embed_fm2_bwd(q, dq.view(B, 1, Hd), None)
+        # lookup backward of a plain gather: the IndexedSlices values are dk / dq themselves (no kernel, no bytes)
         _rec(ev, 4)
 
     n_pos = int(lens.sum().item())                                         # positions that reach the MLP (t < keys_length)
