@@ -263,6 +263,10 @@ int ctr_cin_bwd(const float* x0, const float* xk, const float* filter, const flo
                 float* dx0, float* dxk, float* dfilter,
                 void* workspace, int64_t workspace_bytes, void* stream);
 int64_t ctr_cin_bwd_workspace_bytes(int64_t B, int64_t m, int64_t hk, int64_t D, int64_t H);
+/* Tuning hook (process-wide, returns the previous setting): 1 (default) = the dX kernel runs as CTA pairs (tcgen05
+ * cta_group::2, M = 256, each SM feeds half of every filter stage); 0 = the single-CTA form with TMA multicast.  Same results;
+ * used by tools/bench_layers.py for A/B timings. */
+int ctr_cin_bwd_set_dx_pair(int on);
 
 /* ---- Row DIN-ATT: DIN attention unit -----------------------------------------------------------------
  * Replaces din_attention(query, keys, keys_length, is_softmax) (DIN/din_attention.py:17-43).

@@ -276,6 +276,235 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
   }
 }
 
+// ================================================================================================= dX kernel, CTA pair
+// cta_group::2 form of the kernel above (round 2).  Measured bound of the single-CTA kernel: TS-mode kind::tf32 at M = 128
+// reads its B operand from shared memory at 64 B/clk and the TMA fill of a stage that serves ONE row tile adds 42 B/clk --
+// 104 of the SM's 128 B/clk, tensor pipe 49 % busy.  Here two CTAs of a cluster form one M = 256 MMA: every CTA keeps its own
+// 128 rows of Gt in its TMEM and its own dZ buffers, but holds only HALF of each filter stage (the rows of ONE i: N = 64 =
+// 2 x 32, rank r loads i0 + r), so operand reads and TMA fill per SM halve.  The leader (rank 0) issues every MMA and
+// commits to both CTAs' barriers (multicast); the peer's TMA completes on the leader's `full` barrier (cta_group::2 copy),
+// the peer's row owners arrive remotely on the leader's a_full / d_empty barriers.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// instruction descriptor of the pair MMA: D = f32, A = B = tf32, both K-major, M = 256, N
+__device__ __forceinline__ uint32_t umma_idesc_tf32_m256(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int SB, int NKB>
+__global__ void __launch_bounds__(DX_THREADS, 1)
+cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmap_half, const float* __restrict__ x0,
+                      const float* __restrict__ xk, const float* __restrict__ g, float* __restrict__ dx0,
+                      float* __restrict__ dxk, int B, int m, int hk, int logD, int H, int KRP) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int HP = NKB * KB;
+  constexpr int half_copy_bytes = NKB * KB * 128;           // one (hi or lo) copy of THIS CTA's 32 filter rows: NKB sub-tiles of [32 x 128 B]
+  constexpr int stage_bytes = 2 * half_copy_bytes;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SB * stage_bytes;
+  auto full_b = [&](int s) { return bar0 + 8 * s; };
+  auto empty_b = [&](int s) { return bar0 + 8 * (SB + s); };
+  auto d_full = [&](int q) { return bar0 + 8 * (2 * SB + q); };
+  auto d_empty = [&](int q) { return bar0 + 8 * (2 * SB + DX_DBUF + q); };
+  const uint32_t a_full = bar0 + 8 * (2 * SB + 2 * DX_DBUF), a_empty = a_full + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SB * stage_bytes + 8 * (2 * SB + 2 * DX_DBUF + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = 1 << logD;
+  const long long rows_total = (long long)B * D;
+  const int num_tiles = (int)((rows_total + BM - 1) / BM);
+  const int tile_iters = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // identical for both CTAs of a pair (lockstep)
+  const int nsteps = (hk + DX_IPS - 1) / DX_IPS;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int q = 0; q < DX_DBUF; ++q) { mbar_init(d_full(q), 1); mbar_init(d_empty(q), 8); }   // 4 row-owner warps x 2 CTAs
+    mbar_init(a_full, 8);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc_2sm(smem_u32(tmem_ptr), 512u);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // both CTAs' barriers exist before anything is sent to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t d_col0 = tmem_base + 256u;
+
+  if (warp < 4) {
+    // ============================ row owners: stage Gt once per tile, then consume dZ of two i per step ============================
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const uint32_t a_full_leader = mapa_rank(a_full, 0);
+    uint32_t di = 0;
+    int lt = 0;
+    for (int ti = 0; ti < tile_iters; ++ti, ++lt) {
+      const int tile = blockIdx.x + ti * gridDim.x;          // may be past the end: an all-invalid tile keeps the pipeline in step
+      const long long r = (long long)tile * BM + warp * 32 + lane;
+      const bool valid = tile < num_tiles && r < rows_total;
+      const int b = valid ? (int)(r >> logD) : 0;
+      const int d = (int)(r & (D - 1));
+      float x0v[KB], dx0acc[KB];
+#pragma unroll
+      for (int j = 0; j < KB; ++j) {
+        x0v[j] = (valid && j < m) ? __ldg(x0 + ((size_t)b * m + j) * D + d) : 0.f;
+        dx0acc[j] = 0.f;
+      }
+      mbar_wait(a_empty, (lt & 1) ^ 1);                // MMAs of the previous tile pair no longer read the A columns
+      tc_fence_after();
+      const float* gp = g + (size_t)b * H * D + d;
+#pragma unroll 1
+      for (int n0 = 0; n0 < HP; n0 += 8) {
+        float v[8], h[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = (valid && n0 + q < H) ? __ldg(gp + (size_t)(n0 + q) * D) : 0.f;
+          h[q] = tf32_rna(v[q]);
+          v[q] -= h[q];
+        }
+        tmem_st8(tmem_base + lane_sel + (uint32_t)n0, h);
+        tmem_st8(tmem_base + lane_sel + (uint32_t)(HP + n0), v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a_full_leader);
+      const float* xkp = xk + (size_t)b * hk * D + d;
+      for (int st = 0; st < nsteps; ++st, ++di) {
+        const int i0 = st * DX_IPS;
+        float xi[DX_IPS];
+#pragma unroll
+        for (int t = 0; t < DX_IPS; ++t) xi[t] = (valid && i0 + t < hk) ? __ldg(xkp + (size_t)(i0 + t) * D) : 0.f;
+        const uint32_t q = di % DX_DBUF;
+        mbar_wait(d_full(q), (di / DX_DBUF) & 1u);
+        tc_fence_after();
+        uint32_t raw[DX_IPS * 2][16];
+#pragma unroll
+        for (int t = 0; t < DX_IPS * 2; ++t) tmem_ld16_nowait(d_col0 + lane_sel + q * DX_N + t * 16, raw[t]);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_rank(d_empty(q), 0));     // the leader may overwrite buffer q in BOTH CTAs
+#pragma unroll
+        for (int t = 0; t < DX_IPS; ++t) {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+            const float dzv = __uint_as_float(raw[t * 2 + (j >> 4)][j & 15]);
+            s4[j & 3] += dzv * x0v[j];
+            dx0acc[j] += dzv * xi[t];
+          }
+          if (valid && i0 + t < hk) dxk[((size_t)b * hk + i0 + t) * D + d] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < KB; ++j)
+          if (j < m) dx0[((size_t)b * m + j) * D + d] = dx0acc[j];
+      }
+    }
+  } else if (warp == 4) {
+    // ============================ TMA: this CTA's half of every filter stage (the rows of i0 + rank), hi and lo ============================
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int ti = 0; ti < tile_iters; ++ti) {
+        for (int st = 0; st < nsteps; ++st) {
+          mbar_wait(empty_b(s), ph ^ 1);
+          const uint32_t dst = sbase + s * stage_bytes;
+          const uint32_t leader_full = mapa_rank(full_b(s), 0);
+          if (leader) mbar_expect_tx(full_b(s), (uint32_t)(2 * stage_bytes));      // both CTAs' halves complete on the leader's barrier
+          tma_load_4d_2sm(dst, &tmap_half, 0, st * DX_IPS * m, (int)cta_rank, 0, leader_full);
+          tma_load_4d_2sm(dst + half_copy_bytes, &tmap_half, 0, KRP + st * DX_IPS * m, (int)cta_rank, 0, leader_full);
+          if (++s == SB) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (leader) {
+    // ============================ MMA issuer of the pair: 3 passes x NKB x 4 MMAs of 256x64x8 ============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32_m256(DX_N);
+      int s = 0, ph = 0, lt = 0;
+      uint32_t di = 0;
+      for (int ti = 0; ti < tile_iters; ++ti, ++lt) {
+        mbar_wait(a_full, lt & 1);
+        tc_fence_after();
+        for (int st = 0; st < nsteps; ++st, ++di) {
+          const uint32_t q = di % DX_DBUF;
+          mbar_wait(d_empty(q), ((di / DX_DBUF) & 1u) ^ 1u);
+          mbar_wait(full_b(s), ph);
+          tc_fence_after();
+          const uint32_t dcol = d_col0 + q * DX_N;
+          const uint64_t b_hi = umma_desc_sw128(sbase + s * stage_bytes);
+          const uint64_t b_lo = umma_desc_sw128(sbase + s * stage_bytes + half_copy_bytes);
+          const uint32_t a_hi = tmem_base, a_lo = tmem_base + (uint32_t)HP;
+          // sub-tile kb of a CTA's half starts KB*128 bytes (>>4 = 256) further
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts_2sm(dcol, a_lo + (uint32_t)(kb * KB + 8 * k), b_hi + (uint64_t)(kb * (KB * 128 / 16) + 2 * k), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts_2sm(dcol, a_hi + (uint32_t)(kb * KB + 8 * k), b_lo + (uint64_t)(kb * (KB * 128 / 16) + 2 * k), idesc, 1u);
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts_2sm(dcol, a_hi + (uint32_t)(kb * KB + 8 * k), b_hi + (uint64_t)(kb * (KB * 128 / 16) + 2 * k), idesc, 1u);
+          umma_commit_2sm(empty_b(s), (uint16_t)3);
+          umma_commit_2sm(d_full(q), (uint16_t)3);
+          if (++s == SB) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(a_empty, (uint16_t)3);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // nobody leaves while the peer may still signal or read it
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512u);
+  }
+}
+
 // ================================================================================================= dW kernel
 constexpr int DW_THREADS = 384;     // 8 (i,j)-row warps + TMA warp + MMA warp (+2 idle, completes the third warpgroup)
 constexpr int DW_BLOCKS = 2;        // (i,j) blocks of 128 rows per CTA  (= 8 consecutive i)
@@ -485,6 +714,15 @@ static int64_t pad_to(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 using namespace ctr;
 using namespace ctr::cinb;
 
+// dX kernel choice: CTA pairs (cta_group::2, default) or the single-CTA multicast form.  Internal; tools/bench_layers.py flips it
+// through ctr_cin_bwd_set_dx_pair for A/B timings (no environment variable is read anywhere in the library).
+static bool g_dx_pair = true;
+extern "C" __attribute__((visibility("default"))) int ctr_cin_bwd_set_dx_pair(int on) {
+  const int old = g_dx_pair ? 1 : 0;
+  g_dx_pair = on != 0;
+  return old;
+}
+
 // Shapes the tensor-core backward serves; everything else goes to the CUDA-core kernels in cin.cu.
 // (internal, not part of the public ABI)
 extern "C" __attribute__((visibility("hidden"))) int ctr_cin_bwd_tc_supported(int64_t m, int64_t hk, int64_t D, int64_t H) {
@@ -534,6 +772,15 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
       set_error("ctr_cin_bwd: cuTensorMapEncodeTiled(filter) failed with CUresult %d", (int)cr);
       return CTR_ERR_CUDA;
     }
+    // the same tensor with a ONE-i box: what one CTA of a cta_group::2 pair loads per stage
+    CUtensorMap tmap_half;
+    const cuuint32_t box_half[4] = {32, 32, 1, (cuuint32_t)(HP / 32)};
+    cr = enc(&tmap_half, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ws_w, gdim, gstr, box_half, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("ctr_cin_bwd: cuTensorMapEncodeTiled(filter, half box) failed with CUresult %d", (int)cr);
+      return CTR_ERR_CUDA;
+    }
     constexpr int SB = 3;
     const int nkb = HP / 32;
     const int stage_bytes = 2 * nkb * DX_N * 128;
@@ -542,6 +789,31 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
     const int tiles = (int)((rows + BM - 1) / BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
     const bool mc = tiles >= 2;
+    if (mc && g_dx_pair) {
+      // CTA pairs (cta_group::2): SB = 6 stages of half the size fit the same shared memory
+      constexpr int SB2 = 6;
+      const int smem2 = SB2 * (stage_bytes / 2) + 8 * (2 * SB2 + 2 * DX_DBUF + 2) + 16 + 1024;
+      int grid2 = grid & ~1;
+      if (grid2 < 2) grid2 = 2;
+#define DX2_LAUNCH(NKB_)                                                                                             \
+  {                                                                                                                  \
+    auto k = cin_bwd_dx_tc2_kernel<SB2, NKB_>;                                                                       \
+    CTR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));                           \
+    cudaLaunchConfig_t cfg = {};                                                                                     \
+    cfg.gridDim = dim3((unsigned)grid2);                                                                             \
+    cfg.blockDim = dim3(DX_THREADS);                                                                                 \
+    cfg.dynamicSmemBytes = (size_t)smem2;                                                                            \
+    cfg.stream = st;                                                                                                 \
+    cudaLaunchAttribute at[1];                                                                                       \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                                  \
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                              \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                                \
+    CTR_CUDA(cudaLaunchKernelEx(&cfg, k, tmap_half, x0, xk, g_out, dx0, dxk, (int)B, (int)m, (int)hk, logD, (int)H, KRP)); \
+  }
+      if (nkb == 1) DX2_LAUNCH(1) else if (nkb == 2) DX2_LAUNCH(2) else if (nkb == 3) DX2_LAUNCH(3) else DX2_LAUNCH(4)
+#undef DX2_LAUNCH
+      CTR_CHECK_LAUNCH("ctr_cin_bwd(dx, tcgen05 cta_group::2)");
+    } else {
     int grid_mc = grid & ~1;                               // whole 2-CTA clusters
     if (grid_mc < 2) grid_mc = 2;
 #define DX_LAUNCH(NKB_)                                                                                              \
@@ -566,6 +838,7 @@ int ctr_cin_bwd_tc(const float* x0, const float* xk, const float* filter, const 
     if (nkb == 1) DX_LAUNCH(1) else if (nkb == 2) DX_LAUNCH(2) else if (nkb == 3) DX_LAUNCH(3) else DX_LAUNCH(4)
 #undef DX_LAUNCH
     CTR_CHECK_LAUNCH("ctr_cin_bwd(dx, tcgen05)");
+    }
   }
   // ---- dW: g (hi | lo stacked along the batch axis) as a 3-D tensor (d | n | b); box = one sample's [NP x D] tile
   {

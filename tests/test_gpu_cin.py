@@ -91,3 +91,36 @@ def test_cin_config3_properties():
     lhs = ops.cin_fwd(x0, x1, w2 + wb)
     rhs = ops.cin_fwd(x0, x1, w2) + ops.cin_fwd(x0, x1, wb)
     assert_close(lhs, rhs.double(), 2e-5, "linearity")
+
+
+@pytest.mark.parametrize("pair", [1, 0])
+def test_cin_config3_backward(pair):
+    """Backward at BASELINE config-3 size (B=8192, m=30, hk=128, D=16, H=128: 1024 row tiles -> several rounds of the
+    persistent dX schedule incl. its tail, 16 (i,j)-groups x 9 batch slices of the dW kernel): dx0 / dxk against a float64
+    einsum on a batch subsample (a sample's input gradients only depend on that sample), dfilter against the float64
+    contraction over the WHOLE batch (chunked).  Both dX forms: CTA pairs (cta_group::2) and single CTA + multicast."""
+    from recalgorithm_b200 import _lib, ops
+    B, m, hk, D, H = 8192, 30, 128, 16, 128
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x0 = torch.randn((B, m, D), device="cuda", generator=gen) * 0.25
+    xk = torch.randn((B, hk, D), device="cuda", generator=gen) * 0.25
+    w = torch.randn((hk * m, H), device="cuda", generator=gen) * 0.05
+    g = torch.randn((B, H, D), device="cuda", generator=gen)
+    old = _lib.lib().ctr_cin_bwd_set_dx_pair(pair)
+    try:
+        dx0, dxk, dw = ops.cin_bwd(x0, xk, w, g)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().ctr_cin_bwd_set_dx_pair(old)
+    sub = torch.arange(0, B, 131, device="cuda")                       # 63 samples spread over the tiles (incl. tile boundaries)
+    sub = torch.cat([sub, torch.tensor([7, 8, 15, 16, B - 1], device="cuda")])
+    w3 = w.double().reshape(hk, m, H)
+    dz = torch.einsum("bnd,ijn->bijd", g[sub].double(), w3)            # dL/d(outer[b,i,j,d])
+    assert_close(dxk[sub], torch.einsum("bijd,bjd->bid", dz, x0[sub].double()), TOL, "dxk (config-3 size)")
+    assert_close(dx0[sub], torch.einsum("bijd,bid->bjd", dz, xk[sub].double()), TOL, "dx0 (config-3 size)")
+    ref = torch.zeros((hk, m, H), dtype=torch.float64, device="cuda")
+    for b0 in range(0, B, 512):
+        sl = slice(b0, b0 + 512)
+        z = torch.einsum("bid,bjd->bdij", xk[sl].double(), x0[sl].double()).reshape(-1, hk * m)       # (b*d, i*m+j)
+        ref += (z.t() @ g[sl].double().permute(0, 2, 1).reshape(-1, H)).reshape(hk, m, H)
+    assert_close(dw, ref.reshape(hk * m, H), TOL, "dfilter (config-3 size, whole batch)")

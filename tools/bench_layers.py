@@ -91,10 +91,14 @@ def main():
             emit(f"cin_fwd_layer1_{tag}", {"B": B, "m": mm, "hk": mm, "D": D, "H": H}, m, bst, flops=2.0 * B * D * mm * mm * H)
             m, bst = timeit(lambda: ops.cin_fwd(x0, x1, w2, want_pooled=True, precision=prec), args.iters, flush)
             emit(f"cin_fwd_layer2_{tag}", {"B": B, "m": mm, "hk": H, "D": D, "H": H}, m, bst, flops=2.0 * B * D * H * mm * H)
-        m, bst = timeit(lambda: ops.cin_bwd(x0, x0, w1, g), max(3, args.iters // 4), flush)
-        emit("cin_bwd_layer1", {"B": B, "m": mm, "hk": mm, "D": D, "H": H}, m, bst, flops=4.0 * B * D * mm * mm * H)
-        m, bst = timeit(lambda: ops.cin_bwd(x0, x1, w2, g), max(3, args.iters // 4), flush)
-        emit("cin_bwd_layer2", {"B": B, "m": mm, "hk": H, "D": D, "H": H}, m, bst, flops=4.0 * B * D * H * mm * H)
+        for pair in (1, 0):
+            ops._lib.lib().ctr_cin_bwd_set_dx_pair(pair)
+            tag = "dx=cta_group::2 pairs" if pair else "dx=single CTA + multicast"
+            m, bst = timeit(lambda: ops.cin_bwd(x0, x0, w1, g), max(3, args.iters // 4), flush)
+            emit("cin_bwd_layer1", {"B": B, "m": mm, "hk": mm, "D": D, "H": H, "variant": tag}, m, bst, flops=4.0 * B * D * mm * mm * H)
+            m, bst = timeit(lambda: ops.cin_bwd(x0, x1, w2, g), max(3, args.iters // 4), flush)
+            emit("cin_bwd_layer2", {"B": B, "m": mm, "hk": H, "D": D, "H": H, "variant": tag}, m, bst, flops=4.0 * B * D * H * mm * H)
+        ops._lib.lib().ctr_cin_bwd_set_dx_pair(1)
 
     if "din" in only:   # BASELINE config 4: DIN attention, seq_len 50, H=16, batch 4096
         B, T, H = 4096, 50, 16
