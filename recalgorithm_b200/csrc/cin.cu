@@ -270,7 +270,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
     }
   } else if (warp == 9) {
     // ============================ MMA issuer (TS mode: A from TMEM, B from shared memory) ============================
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_tf32(NP);
       int sb = 0, phb = 0, sa = 0, pha = 0;
       uint32_t g = 0;
@@ -285,6 +285,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
             mbar_wait(full_a(sa), pha);
             mbar_wait(full_b(sb), phb);
             tc_fence_after();
+            if (elect_one()) {
             const uint32_t first = (i == i_beg) ? 0u : 1u;
             const uint32_t st_base = sbase + sb * L.stage_bytes;
             const uint64_t b_hi = umma_desc_sw128(st_base);
@@ -310,10 +311,12 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __res
             }
             umma_commit(empty_a(sa));                  // A staging columns free once these MMAs have read them
             umma_commit(empty_b(sb));                  // and the filter stage
+            if (i + 1 == i_end) umma_commit(acc_full); // chunk complete -> drain
+            }
+            __syncwarp();
             if (++sa == SA) { sa = 0; pha ^= 1; }
             if (++sb == SB) { sb = 0; phb ^= 1; }
           }
-          umma_commit(acc_full);                       // chunk complete -> drain
         }
       }
     }

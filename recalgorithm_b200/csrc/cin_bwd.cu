@@ -226,7 +226,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
     }
   } else {
     // ============================ MMA issuer (fully unrolled: 3 passes x NKB x 4 MMAs of 128x64x8) ============================
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_tf32(DX_N);
       int s = 0, ph = 0, lt = 0;
       uint32_t di = 0;
@@ -238,6 +238,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
           mbar_wait(d_empty(q), ((di / DX_DBUF) & 1u) ^ 1u);
           mbar_wait(full_b(s), ph);
           tc_fence_after();
+          if (elect_one()) {
           const uint32_t dcol = d_col0 + q * DX_N;
           const uint64_t b_hi = umma_desc_sw128(sbase + s * stage_bytes);
           const uint64_t b_lo = umma_desc_sw128(sbase + s * stage_bytes + b_copy_bytes);
@@ -261,9 +262,11 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __
               umma_tf32_ts(dcol, a_hi + (uint32_t)(kb * KB + 8 * k), b_hi + (uint64_t)(kb * (DX_N * 128 / 16) + 2 * k), idesc, 1u);
           if (MC) umma_commit_mc(empty_b(s), (uint16_t)3); else umma_commit(empty_b(s));
           umma_commit(d_full(q));
+          if (st + 1 == nsteps) umma_commit(a_empty);
+          }
+          __syncwarp();
           if (++s == SB) { s = 0; ph ^= 1; }
         }
-        umma_commit(a_empty);
       }
     }
   }
@@ -455,7 +458,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmap_half, const float
     }
   } else if (leader) {
     // ============================ MMA issuer of the pair: 3 passes x NKB x 4 MMAs of 256x64x8 ============================
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_tf32_m256(DX_N);
       int s = 0, ph = 0, lt = 0;
       uint32_t di = 0;
@@ -467,6 +470,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmap_half, const float
           mbar_wait(d_empty(q), ((di / DX_DBUF) & 1u) ^ 1u);
           mbar_wait(full_b(s), ph);
           tc_fence_after();
+          if (elect_one()) {
           const uint32_t dcol = d_col0 + q * DX_N;
           const uint64_t b_hi = umma_desc_sw128(sbase + s * stage_bytes);
           const uint64_t b_lo = umma_desc_sw128(sbase + s * stage_bytes + half_copy_bytes);
@@ -490,9 +494,11 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmap_half, const float
               umma_tf32_ts_2sm(dcol, a_hi + (uint32_t)(kb * KB + 8 * k), b_hi + (uint64_t)(kb * (KB * 128 / 16) + 2 * k), idesc, 1u);
           umma_commit_2sm(empty_b(s), (uint16_t)3);
           umma_commit_2sm(d_full(q), (uint16_t)3);
+          if (st + 1 == nsteps) umma_commit_2sm(a_empty, (uint16_t)3);
+          }
+          __syncwarp();
           if (++s == SB) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(a_empty, (uint16_t)3);
       }
     }
   }
@@ -661,7 +667,7 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __
     }
   } else if (warp == 9) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_tf32(NP);
       int sb = 0, phb = 0, sa = 0, pha = 0;
       uint32_t gch = 0;
@@ -673,6 +679,7 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __
           mbar_wait(full_a(sa), pha);
           mbar_wait(full_b(sb), phb);
           tc_fence_after();
+          if (elect_one()) {
           const uint32_t first = (b == s_beg) ? 0u : 1u;
           const uint32_t st = sbase + sb * stage_bytes;
           const uint64_t b_hi = umma_desc_kmajor(st, row_bytes);
@@ -691,10 +698,12 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const float* __
           }
           umma_commit(empty_a(sa));
           umma_commit(empty_b(sb));
+          if (b + 1 == s_end) umma_commit(acc_full);
+          }
+          __syncwarp();
           if (++sa == SA) { sa = 0; pha ^= 1; }
           if (++sb == SB) { sb = 0; phb ^= 1; }
         }
-        umma_commit(acc_full);
       }
     }
   }

@@ -34,6 +34,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// One lane of a CONVERGED warp (elect.sync).  The MMA-issuing warps run their loops with all 32 lanes (the barrier waits are
+// harmless in parallel) and guard only the tcgen05.mma / tcgen05.commit bursts with this: behind `if (lane == 0)` nvcc wraps
+// EVERY UTCHMMA in a six-instruction ELECT / BRA.U.ANY retry loop (it cannot prove that a single lane is active), which made
+// the issue of one MMA cost more than the 32 cycles a 128x64x8 MMA runs -- the round-1 kernels were issue-bound (tensor pipe
+// 49-68 %).  Behind elect.sync the UTCHMMAs are emitted back to back (profiles/r2_sass_summary.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.b32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
