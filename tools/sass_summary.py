@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "recalgorithm_b200", "csrc")
-PATTERNS = [("UTCHMMA", r"\bUTCHMMA"), ("UTC*MMA(other)", r"\bUTC(?!HMMA|BAR)[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
+PATTERNS = [("UTCHMMA", r"\bUTCHMMA"), ("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("BRA.U.ANY(elect retry loops)", r"BRA\.U\.ANY"), ("UTC*MMA(other)", r"\bUTC(?!HMMA|BAR)[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
             ("UTMALDG", r"\bUTMALDG"), ("UTMALDG.MULTICAST", r"\bUTMALDG\S*MULTICAST"), ("UTMASTG", r"\bUTMASTG"), ("UBLKCP", r"\bUBLKCP"),
             ("UTCBAR", r"\bUTCBAR"), ("SYNCS", r"\bSYNCS"), ("LDGSTS", r"\bLDGSTS"), ("HMMA(legacy)", r"\bHMMA"),
             ("LDG.E.128", r"\bLDG\.E\S*\.128"), ("STG.E.128", r"\bSTG\.E\S*\.128"), ("RED/ATOM", r"\b(RED|ATOM)G?\.")]
@@ -47,7 +47,7 @@ def main():
             tot.update(c)
         print(f"\n## {os.path.basename(o)}: {len(per_kernel)} kernels; " + ", ".join(f"{n}={tot[n]}" for n, _ in PATTERNS if tot[n]))
         for k, c in per_kernel.items():
-            hot = {n: c[n] for n in ("UTCHMMA", "UTC*MMA(other)", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "HMMA(legacy)") if c[n]}
+            hot = {n: c[n] for n in ("UTCHMMA", "UTCHMMA.2CTA", "BRA.U.ANY(elect retry loops)", "UTC*MMA(other)", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "HMMA(legacy)") if c[n]}
             if hot:
                 dem = subprocess.run(["cu++filt", k], capture_output=True, text=True).stdout.strip() or k
                 print(f"   {dem[:150]}: " + ", ".join(f"{n}={v}" for n, v in hot.items()))
