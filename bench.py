@@ -558,6 +558,7 @@ def run_deepfm(args, cfg, dd: Dist):
     if os.environ.get("CTR_BENCH_ROWS"):
         rows = int(os.environ["CTR_BENCH_ROWS"])
     plan = torch.empty((B, F), dtype=torch.int32, device=dev)
+    align_token = torch.zeros((1,), device=dev)
 
     def make_sharded(rows_):
         tb = shard_mod.ShardedEmbeddingTables([rows_] * F, D, batch_per_rank=B, device=dev, init="normal",
@@ -577,6 +578,11 @@ def run_deepfm(args, cfg, dd: Dist):
             tb.bwd_push(tile, d_tile, d_fm2, plan)                         # gradient rows stored straight into the owners' queues
             if ev:
                 ev[3].record()
+            if args.align_steps and world > 1:
+                # what the dense-gradient all-reduce of a real step does as a side effect: it keeps the ranks' pull / push phases
+                # aligned (stream-ordered 1-element NCCL all-reduce, no host sync).  Unaligned ranks load one NVLink direction with
+                # push payload AND read responses while the other idles.
+                dd.dist.all_reduce(align_token)
         return tb, sets, desc, step_
 
     tables, id_sets, ids_desc, step = make_sharded(rows)
@@ -664,6 +670,7 @@ def run_deepfm(args, cfg, dd: Dist):
                    "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "table_bytes_total": rows * F * D * 4,
                    "shard_bytes_per_gpu": rows * F * D * 4 // world, "ids": ids_desc,
                    "shard_backend": args.shard_backend + (f" (align {args.vmm_align} MiB)" if args.shard_backend == "vmm" else ""),
+                   "rank_alignment": "1-element NCCL all-reduce per step (stream-ordered, no host sync)" if args.align_steps else "none (free-running ranks)",
                    "parallelism": f"row-sharded: tables split over {world} GPUs (global row % {world}); forward pulls rows over NVLink "
                                   "inside the gather kernel, backward stores gradient rows into the owners' queues (fused "
                                   "compute+exchange kernels, no NCCL data collective)",
@@ -772,6 +779,9 @@ def main():
     ap.add_argument("--shard-backend", default="symm", choices=["symm", "vmm"],
                     help="allocation of the table shard in the sharded workloads: torch symmetric memory or ctr_vmm_alloc")
     ap.add_argument("--vmm-align", type=int, default=0, help="MiB; size/address alignment of ctr_vmm_alloc (0 = driver granularity)")
+    ap.add_argument("--align-steps", type=int, default=1,
+                    help="sharded workloads: 1 = every step ends with a stream-ordered 1-element NCCL all-reduce that keeps the ranks' "
+                         "phases aligned (stands in for the dense-gradient all-reduce of a real step); 0 = free-running ranks")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
                     help="id distribution of the synthetic batches (default: uniform = every row an HBM miss)")
     args = ap.parse_args()

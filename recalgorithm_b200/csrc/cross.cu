@@ -289,6 +289,8 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
 // so the warp that owns a sample adds x0*a_l and g_out into lane-owned register accumulators (columns of the lane) while the
 // values are still in its registers; nothing is staged in shared memory, there is no thread-per-column phase and no
 // __syncthreads in the loop (the first form spent ~60 % of its issue slots in that phase and two block syncs per 8 samples).
+// Second step (ncu: six DEPENDENT warp reductions per sample kept 8 warps/SM latency-bound at 36 % of HBM): with x_l affine in
+// x0 the whole layer chain becomes scalar recurrences over L + 1 independent dot products (see the loop body).
 // The next sample's x0 / g_out are fetched one iteration ahead.  Per CTA: one shared-memory reduction, then the cb / w terms
 // and one fp32 atomic per element.
 template <int N, int LM>
@@ -319,55 +321,86 @@ cross_bwd_reg_kernel(const float* __restrict__ x0, const float* __restrict__ w, 
   }
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc_g[k] = 0.f;
-  LaneVec<4, N> na0, ng;
-  if (warp0 < B) { na0.load(x0 + (size_t)warp0 * d, d, lane); ng.load(g_out + (size_t)warp0 * d, d, lane); }
-  for (int s = warp0; s < B; s += nwarps) {
-    LaneVec<4, N> a0 = na0, g = ng, x;
-    if (s + nwarps < B) { na0.load(x0 + (size_t)(s + nwarps) * d, d, lane); ng.load(g_out + (size_t)(s + nwarps) * d, d, lane); }
+  // v_l = cb_l . w_l (sample independent): the bias part of s_l = x_l . w_l with x_l = x0*(1 + cs_l) + cb_l
+  float vl[LM];
+  {
+    float cbv[NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) { x.v[k] = a0.v[k]; acc_g[k] += g.v[k]; }
-    // forward recurrence -> s_l and the prefix sums cs_l
-    float sl[LM], cs[LM], run = 0.f;
+    for (int k = 0; k < NV; ++k) cbv[k] = 0.f;
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
-      sl[l] = 0.f; cs[l] = 0.f;
+      vl[l] = 0.f;
       if (l < L) {
         float wv[NV], bv[NV];
         lane_load_smem<4, N>(wv, sw + (size_t)l * d, d, lane);
         lane_load_smem<4, N>(bv, sb + (size_t)l * d, d, lane);
         float dot = 0.f;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) dot += x.v[k] * wv[k];
-        dot = warp_sum(dot);
-        sl[l] = dot; cs[l] = run; run += dot;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) x.v[k] = (a0.v[k] * dot + bv[k]) + x.v[k];
+        for (int k = 0; k < NV; ++k) { dot += cbv[k] * wv[k]; cbv[k] += bv[k]; }
+        vl[l] = warp_sum(dot);
       }
     }
-    // backward walk; x is reused as the dx0 accumulator
+  }
+  LaneVec<4, N> na0, ng;
+  if (warp0 < B) { na0.load(x0 + (size_t)warp0 * d, d, lane); ng.load(g_out + (size_t)warp0 * d, d, lane); }
+  for (int s = warp0; s < B; s += nwarps) {
+    LaneVec<4, N> a0 = na0, g = ng;
+    if (s + nwarps < B) { na0.load(x0 + (size_t)(s + nwarps) * d, d, lane); ng.load(g_out + (size_t)(s + nwarps) * d, d, lane); }
+    // The only reductions a sample needs are L + 1 INDEPENDENT dot products -- u_l = x0 . w_l and c0 = g_out . x0 -- done as one
+    // batched butterfly; everything sequential in the layer chain collapses to scalar recurrences:
+    //   s_l = (1 + cs_l) u_l + v_l ,  cs_{l+1} = cs_l + s_l          (forward:  x_l = x0 (1 + cs_l) + cb_l)
+    //   t_l = c0 + sum_{k>l} t_k u_k                                 (backward: g_{l+1} = g_out + sum_{k>l} t_k w_k)
+    //   dx0 = g_out (1 + cs_L) + sum_k a_k w_k ,  a_k = (1 + cs_k) t_k     (a_k is also the dw scalar)
+    float red[LM + 1];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) x.v[k] = 0.f;
+    for (int l = 0; l <= LM; ++l) red[l] = 0.f;
 #pragma unroll
-    for (int l = LM - 1; l >= 0; --l) {
+    for (int k = 0; k < NV; ++k) { red[LM] += g.v[k] * a0.v[k]; acc_g[k] += g.v[k]; }
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
       if (l < L) {
         float wv[NV];
         lane_load_smem<4, N>(wv, sw + (size_t)l * d, d, lane);
-        float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) t += g.v[k] * a0.v[k];
-        t = warp_sum(t);
-        T[l] += t;
-        const float a = (cs[l] + 1.f) * t;            // x_l = x0*(1 + cs_l) + cb_l
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          acc_a[l][k] += a0.v[k] * a;
-          x.v[k] += g.v[k] * sl[l];
-          g.v[k] += t * wv[k];
-        }
+        for (int k = 0; k < NV; ++k) red[l] += a0.v[k] * wv[k];
       }
     }
 #pragma unroll
-    for (int k = 0; k < NV; ++k) x.v[k] += g.v[k];    // xl_in == x0: d(x0) also receives g_0
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int l = 0; l <= LM; ++l) red[l] += __shfl_xor_sync(0xffffffffu, red[l], o);
+    }
+    float cs[LM + 1], tl[LM], al[LM];
+    cs[0] = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM; ++l) cs[l + 1] = l < L ? cs[l] + ((1.f + cs[l]) * red[l] + vl[l]) : cs[l];
+    float run = 0.f;                                   // sum_{k>l} t_k u_k
+#pragma unroll
+    for (int l = LM - 1; l >= 0; --l) {
+      tl[l] = 0.f; al[l] = 0.f;
+      if (l < L) {
+        tl[l] = red[LM] + run;
+        run += tl[l] * red[l];
+        al[l] = (1.f + cs[l]) * tl[l];
+        T[l] += tl[l];
+      }
+    }
+    const float gscale = 1.f + cs[LM];                 // cs[LM] == cs_L for every l >= L
+    LaneVec<4, N> x;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x.v[k] = g.v[k] * gscale;
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      if (l < L) {
+        float wv[NV];
+        lane_load_smem<4, N>(wv, sw + (size_t)l * d, d, lane);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          x.v[k] += al[l] * wv[k];
+          acc_a[l][k] += a0.v[k] * al[l];
+        }
+      }
+    }
     x.store(dx0 + (size_t)s * d, d, lane);
   }
   // ---- CTA reduction of the lane-owned accumulators: the warps take turns adding into the shared arrays with plain
