@@ -14,6 +14,8 @@
 //                 g_{l+1} = g_out + sum_{k>l} t_k * w_k
 //             so no per-layer activations are ever written to HBM; per-CTA partials are merged with
 //             fp32 atomics.
+#include <type_traits>
+
 #include "ctr_common.cuh"
 
 namespace ctr {
@@ -293,8 +295,8 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ xl_in, 
 // x0 the whole layer chain becomes scalar recurrences over L + 1 independent dot products (see the loop body).
 // The next sample's x0 / g_out are fetched one iteration ahead.  Per CTA: one shared-memory reduction, then the cb / w terms
 // and one fp32 atomic per element.
-template <int N, int LM>
-__global__ void __launch_bounds__(CROSS_WARPS * 32)
+template <int N, int LM, int RW>
+__global__ void __launch_bounds__(RW * 32)
 cross_bwd_reg_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ b,
                      const float* __restrict__ g_out, int B, int d, int L, float* __restrict__ dx0,
                      float* __restrict__ dw, float* __restrict__ db) {
@@ -406,7 +408,7 @@ cross_bwd_reg_kernel(const float* __restrict__ x0, const float* __restrict__ w, 
   // ---- CTA reduction of the lane-owned accumulators: the warps take turns adding into the shared arrays with plain
   // 128-bit read-modify-writes (every lane owns distinct columns; shared-memory atomics would serialise on the SM's
   // atomic unit: 64 warp-wide ATOMS per warp = ~17 us per CTA, measured as the floor of the B = 4096 case)
-  for (int wv = 0; wv < CROSS_WARPS; ++wv) {
+  for (int wv = 0; wv < RW; ++wv) {
     if ((threadIdx.x >> 5) == wv) {
 #pragma unroll
       for (int kk = 0; kk < N; ++kk) {
@@ -484,18 +486,26 @@ static int launch_cross_bwd(const float* x0, const float* xl_in, const float* w,
     if (xl_in == nullptr && L <= 4) {                  // the chain every reference model builds (DCN/dcn.py:157-160)
       const size_t smem_r = sizeof(float) * ((size_t)3 * L * d + d + 8);
       if (smem_r <= 200 * 1024) {
-        auto kr = L <= 1 ? cross_bwd_reg_kernel<N, 1> : L == 2 ? cross_bwd_reg_kernel<N, 2> : L == 3 ? cross_bwd_reg_kernel<N, 3>
-                                                                                                        : cross_bwd_reg_kernel<N, 4>;
+        // 12 warps per CTA (168 registers each) once every warp has several samples: one sample of prefetch per warp is then
+        // ~46 KB in flight per SM; small batches keep 8 warps (the per-CTA merge takes one turn per warp)
+        const bool wide = B >= (int64_t)sm_count() * 12 * 4 && !(N == 4 && L > 3);   // (N = 4, L = 4 would spill at 168 registers)
+        auto pick = [&](auto rw) {
+          constexpr int RW = decltype(rw)::value;
+          return L <= 1 ? cross_bwd_reg_kernel<N, 1, RW> : L == 2 ? cross_bwd_reg_kernel<N, 2, RW>
+               : L == 3 ? cross_bwd_reg_kernel<N, 3, RW> : cross_bwd_reg_kernel<N, 4, RW>;
+        };
+        auto kr = wide ? pick(std::integral_constant<int, 12>{}) : pick(std::integral_constant<int, 8>{});
+        const int rw = wide ? 12 : 8;
         if (smem_r > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr, CROSS_WARPS * 32, smem_r);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr, rw * 32, smem_r);
         if (per_sm < 1) per_sm = 1;
         long long grid = (long long)per_sm * sm_count();
-        const long long need = (B + CROSS_WARPS - 1) / CROSS_WARPS;
+        const long long need = (B + rw - 1) / rw;
         if (grid > need) grid = need;
         CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * L * d, st));
         CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * L * d, st));
-        kr<<<(int)grid, CROSS_WARPS * 32, smem_r, st>>>(x0, w, b, g, (int)B, (int)d, (int)L, dx0, dw, db);
+        kr<<<(int)grid, rw * 32, smem_r, st>>>(x0, w, b, g, (int)B, (int)d, (int)L, dx0, dw, db);
         CTR_CHECK_LAUNCH("ctr_cross_bwd");
         return CTR_OK;
       }
