@@ -612,6 +612,8 @@ def run_deepfm(args, cfg, dd: Dist):
         f_, lin = shard_mod.lookup_fm2_linear_autograd(tables, ids_dev, w_deep)     # dense(1) deep head fused into the gather
         loss = autograd.sigmoid_cross_entropy_mean(f_, lab_dev, logit_b=lin)
         loss.backward()
+        if world > 1:
+            dd.dist.all_reduce(w_deep.grad)                    # the replicated dense head's gradient: summed over the data-parallel ranks
         return loss
 
     e2e_ms, losses = e2e_loop(dd, B, F, ids_host, lab_host, model_sharded, e2e_steps)
@@ -692,7 +694,7 @@ def run_deepfm(args, cfg, dd: Dist):
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_last": losses[-1],
                 "what": "per rank: pinned-host int32 ids + labels -> H2D -> sharded.lookup_fm2_linear_autograd (peer-pull gather + FM2 + "
                         "dense(1) deep head in one kernel, queue plan beside it) -> sigmoid-CE (ctr_sigmoid_ce) -> backward (ctr_embed_fm2_lin_bwd_push: "
-                        "gradient rows into the owners' queues + d_w) -> loss D2H, read one step later"},
+                        "gradient rows into the owners' queues + d_w) -> NCCL all-reduce of the replicated head's d_w -> loss D2H, read one step later"},
         "vocab_100m": v100, "replicas": rep, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
