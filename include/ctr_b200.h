@@ -302,6 +302,11 @@ int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64_t F, int64
                      float* out, void* stream);
 int ctr_bilinear_bwd(const float* x, const float* w, const float* g_out, int64_t B, int64_t F, int64_t K, int type,
                      float* dx, float* dw, void* stream);
+/* Tuning hook (process-wide, returns the previous mask): bit t = 1 (default 7) runs type t through the sample-batched
+ * "tournament" kernels (K in {8,16,32}, 16-byte aligned arrays; other shapes always use the CTA-per-sample kernels).
+ * Bits 4..9: samples per shared-memory tile (0 = chosen automatically).
+ * Same results; used by the parity tests (both forms) and tools/bench_layers.py for A/B timings. */
+int ctr_bilinear_set_rr(int mask);
 
 /* ---- siblings of FM2 ------------------------------------------------------------------------------------------
  * NFM bi-interaction pooling (NFM/nfm.py:155-168): the fused gather of ctr_embed_fm2_fwd with a (B, D) output

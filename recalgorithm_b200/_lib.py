@@ -86,6 +86,7 @@ SIGNATURES = {
     "ctr_senet_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ctr_bilinear_fwd": (c_int, [_P, _P, _I, _I, _I, c_int, _P, _P]),
     "ctr_bilinear_bwd": (c_int, [_P, _P, _P, _I, _I, _I, c_int, _P, _P, _P]),
+    "ctr_bilinear_set_rr": (c_int, [c_int]),
 }
 
 

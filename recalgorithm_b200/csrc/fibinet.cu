@@ -290,6 +290,251 @@ bilinear_bwd_interaction_dw_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// bilinear, sample-batched "tournament" form (K = 8 / 16 / 32): the round-2 kernels.
+//
+// The first kernels above run one CTA per sample and fetch every pair's K x K weight from L2 for every sample (416 KB per
+// sample for F = 30, K = 16, 'interaction'), and the 'interaction' weight gradient walks the batch with 4-byte strided loads:
+// 1.86 ms for 122 MB of algorithmic traffic.  Here a CTA owns a TILE of samples (x staged in shared memory once) and a group
+// of K lanes owns one pair at a time: lane l keeps column l and row l of the pair's weight in registers and reuses them for
+// every sample of the tile.  The pairs are visited in the order of a round-robin tournament (circle method): the pairs of one
+// round are field-disjoint, so inside a round every (sample, field, lane) element of the shared dx tile has exactly ONE
+// writer -- plain read-modify-writes, no shared-memory atomics; one block barrier per round.
+//   fwd : vw = x_i . W[:,l] ; out[b,p,l] = vw * x_j[l]
+//   dx  : dx_j[l] += g*vw ; dv[l] = g*x_j[l] (exchanged inside the group through shared memory) ; dx_i[l] += dv . W[l,:]
+//   dW  : second kernel, one CTA per (round, batch chunk): lane l accumulates row l of dW = sum_b x_i[l] * dv[:] in registers
+//         over all samples of its chunk (no weights needed), one vector red per 4 elements at the end.
+// The weight index of a pair is 0 ('all'), i ('each') or the pair index ('interaction').
+// ---------------------------------------------------------------------------------------------------
+struct RRShape {
+  int n, np, rounds, slots, slot0;   // participating fields, padded to even, rounds = np-1, active slots per round, first slot
+};
+
+__host__ __device__ inline RRShape rr_shape(int F) {
+  RRShape s;
+  s.n = F - 1;
+  s.np = (s.n & 1) ? s.n + 1 : s.n;
+  s.rounds = s.np - 1;
+  s.slot0 = (s.n & 1) ? 1 : 0;       // odd n: slot 0 would pair the round's field with the dummy -> skipped
+  s.slots = s.np / 2 - s.slot0;
+  return s;
+}
+
+// pair of (round r, slot) as (i << 16) | j with i < j
+__device__ __forceinline__ int rr_pair(const RRShape& s, int r, int slot) {
+  const int m1 = s.np - 1;
+  const int sl = slot + s.slot0;
+  int a, b;
+  if (sl == 0) { a = r; b = s.np - 1; }
+  else { a = (r + sl) % m1; b = (r - sl + m1) % m1; }
+  return a < b ? (a << 16) | b : (b << 16) | a;
+}
+
+template <int K>
+__device__ __forceinline__ void load_vec(float (&v)[K], const float* p) {      // p 16-byte aligned
+#pragma unroll
+  for (int q = 0; q < K / 4; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+
+template <int K>
+__device__ __forceinline__ float dot_vec(const float (&a)[K], const float (&b)[K]) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < K; c += 2) { s0 += a[c] * b[c]; s1 += a[c + 1] * b[c + 1]; }
+  return s0 + s1;
+}
+
+constexpr int RR_SUB = 8;             // samples whose g / out accesses are issued together
+
+// smem: pair table (rounds*slots ints) | xs (BS * F*K)
+template <int K, int TYPE>
+__global__ void __launch_bounds__(256)
+bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int B, int F, int BS,
+                       float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const RRShape sh = rr_shape(F);
+  const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
+  int* tbl = reinterpret_cast<int*>(smem);
+  float* xs = smem + ((sh.rounds * sh.slots + 3) & ~3);
+  for (int t = threadIdx.x; t < sh.rounds * sh.slots; t += blockDim.x) tbl[t] = rr_pair(sh, t / sh.slots, t % sh.slots);
+  const int grp = threadIdx.x / K, l = threadIdx.x % K, G = blockDim.x / K;
+  const int ntiles = (B + BS - 1) / BS;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = tile * BS, bs = min(BS, B - b0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < bs * FK / 4; t += blockDim.x)
+      reinterpret_cast<float4*>(xs)[t] = __ldg(reinterpret_cast<const float4*>(x + (size_t)b0 * FK) + t);
+    __syncthreads();
+    for (int r = 0; r < sh.rounds; ++r) {
+      for (int slot = grp; slot < sh.slots; slot += G) {
+        const int ij = tbl[r * sh.slots + slot];
+        const int i = ij >> 16, j = ij & 0xffff;
+        const int p = pair_base(i, n) + (j - i - 1);
+        const float* wp = w + (size_t)(TYPE == 0 ? 0 : TYPE == 1 ? i : p) * K * K;
+        float wcol[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) wcol[c] = __ldg(wp + c * K + l);
+        float* ob = out + ((size_t)b0 * P + p) * K + l;
+#pragma unroll 4
+        for (int s = 0; s < bs; ++s) {
+          float xi[K];
+          load_vec<K>(xi, xs + s * FK + i * K);
+          ob[(size_t)s * P * K] = dot_vec<K>(xi, wcol) * xs[s * FK + j * K + l];
+        }
+      }
+    }
+  }
+}
+
+// smem: pair table | xs (BS*FK) | dxs (BS*FK) | dv exchange (groups * 2 * K)
+template <int K, int TYPE>
+__global__ void __launch_bounds__(256)
+bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g, int B,
+                          int F, int BS, float* __restrict__ dx) {
+  extern __shared__ __align__(16) float smem[];
+  const RRShape sh = rr_shape(F);
+  const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
+  int* tbl = reinterpret_cast<int*>(smem);
+  float* xs = smem + ((sh.rounds * sh.slots + 3) & ~3);
+  float* dxs = xs + (size_t)BS * FK;
+  float* dvb = dxs + (size_t)BS * FK;
+  for (int t = threadIdx.x; t < sh.rounds * sh.slots; t += blockDim.x) tbl[t] = rr_pair(sh, t / sh.slots, t % sh.slots);
+  const int grp = threadIdx.x / K, l = threadIdx.x % K, G = blockDim.x / K;
+  float* mydv = dvb + grp * 2 * K;
+  const int nslot_it = (sh.slots + G - 1) / G;          // same trip count for every group: the warp stays converged for __syncwarp
+  const int ntiles = (B + BS - 1) / BS;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = tile * BS, bs = min(BS, B - b0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < bs * FK / 4; t += blockDim.x) {
+      reinterpret_cast<float4*>(xs)[t] = __ldg(reinterpret_cast<const float4*>(x + (size_t)b0 * FK) + t);
+      reinterpret_cast<float4*>(dxs)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int r = 0; r < sh.rounds; ++r) {
+      for (int it = 0; it < nslot_it; ++it) {
+        const int slot = grp + it * G;
+        const bool act = slot < sh.slots;
+        const int ij = act ? tbl[r * sh.slots + slot] : 1;     // idle groups shadow pair (0,1): loads only, no stores
+        const int i = ij >> 16, j = ij & 0xffff;
+        const int p = pair_base(i, n) + (j - i - 1);
+        const float* wp = w + (size_t)(TYPE == 0 ? 0 : TYPE == 1 ? i : p) * K * K;
+        float wcol[K], wrow[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) wcol[c] = __ldg(wp + c * K + l);
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(wp + l * K) + q);
+          wrow[4 * q] = t.x; wrow[4 * q + 1] = t.y; wrow[4 * q + 2] = t.z; wrow[4 * q + 3] = t.w;
+        }
+        const float* gb = g + ((size_t)b0 * P + p) * K + l;
+        for (int s0 = 0; s0 < bs; s0 += RR_SUB) {
+          float gv[RR_SUB];
+#pragma unroll
+          for (int u = 0; u < RR_SUB; ++u) gv[u] = (s0 + u < bs) ? __ldg(gb + (size_t)(s0 + u) * P * K) : 0.f;
+#pragma unroll
+          for (int u = 0; u < RR_SUB; ++u) {
+            const int s = s0 + u;
+            if (s < bs) {                                      // bs is uniform over the CTA
+              float xi[K], dv[K];
+              load_vec<K>(xi, xs + s * FK + i * K);
+              const float vw = dot_vec<K>(xi, wcol);
+              const float dvl = gv[u] * xs[s * FK + j * K + l];
+              float* buf = mydv + (u & 1) * K;
+              buf[l] = dvl;
+              if (act) dxs[s * FK + j * K + l] += gv[u] * vw;
+              __syncwarp();
+              load_vec<K>(dv, buf);
+              if (act) dxs[s * FK + i * K + l] += dot_vec<K>(dv, wrow);
+            }
+          }
+        }
+      }
+      __syncthreads();                                         // next round: the same fields belong to other groups
+    }
+    for (int t = threadIdx.x; t < bs * FK / 4; t += blockDim.x)
+      reinterpret_cast<float4*>(dx + (size_t)b0 * FK)[t] = reinterpret_cast<const float4*>(dxs)[t];
+  }
+}
+
+// grid (rounds, chunks).  smem: dv exchange (groups * 2 * K).  x is read through L2 (7.9 MB at config size, every round
+// reads it once), g streams from HBM exactly once.
+template <int K, int TYPE>
+__global__ void __launch_bounds__(256)
+bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ g, int B, int F, float* __restrict__ dw) {
+  extern __shared__ __align__(16) float smem[];
+  const RRShape sh = rr_shape(F);
+  const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
+  const int r = blockIdx.x;
+  const int grp = threadIdx.x / K, l = threadIdx.x % K, G = blockDim.x / K;
+  float* mydv = smem + grp * 2 * K;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b_lo = blockIdx.y * per, b_hi = min(B, b_lo + per);
+  const int nslot_it = (sh.slots + G - 1) / G;
+  for (int it = 0; it < nslot_it; ++it) {
+    const int slot = grp + it * G;
+    const bool act = slot < sh.slots;
+    const int ij = act ? rr_pair(sh, r, slot) : 1;
+    const int i = ij >> 16, j = ij & 0xffff;
+    const int p = pair_base(i, n) + (j - i - 1);
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    const float* xi_p = x + (size_t)i * K + l;
+    const float* xj_p = x + (size_t)j * K + l;
+    const float* g_p = g + (size_t)p * K + l;
+    for (int s0 = b_lo; s0 < b_hi; s0 += RR_SUB) {
+      float xi[RR_SUB], dvl[RR_SUB];
+#pragma unroll
+      for (int u = 0; u < RR_SUB; ++u) {
+        const int b = s0 + u;
+        const bool ok = b < b_hi;
+        xi[u] = ok ? __ldg(xi_p + (size_t)b * FK) : 0.f;
+        const float xj = ok ? __ldg(xj_p + (size_t)b * FK) : 0.f;
+        dvl[u] = ok ? __ldg(g_p + (size_t)b * P * K) * xj : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < RR_SUB; ++u) {
+        float* buf = mydv + (u & 1) * K;
+        buf[l] = dvl[u];
+        __syncwarp();
+        float dv[K];
+        load_vec<K>(dv, buf);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += xi[u] * dv[k];
+      }
+    }
+    if (act) {
+      float* dst = dw + (size_t)(TYPE == 0 ? 0 : TYPE == 1 ? i : p) * K * K + (size_t)l * K;
+#pragma unroll
+      for (int q = 0; q < K / 4; ++q)
+        atomicAdd(reinterpret_cast<float4*>(dst) + q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+    }
+  }
+}
+
+static int g_bilinear_rr = 7;          // bit t: type t runs the tournament kernels (ctr_bilinear_set_rr)
+static int g_bilinear_tile = 0;        // tuning: samples per tile (0 = chosen from the shared-memory budget)
+
+// threads of a tournament CTA: as many K-lane groups as one round has pairs, at most 256 threads, whole warps
+static int rr_threads(int F, int K) {
+  const RRShape sh = rr_shape(F);
+  int G = sh.slots < 256 / K ? sh.slots : 256 / K;
+  if (G < 1) G = 1;
+  return (G * K + 31) / 32 * 32;
+}
+
+// samples per tile so that `arrays` staged copies of the tile fit `budget` bytes (0: not even one sample fits)
+static int rr_tile(int F, int K, int arrays, size_t fixed, size_t budget) {
+  int bs = g_bilinear_tile > 0 ? g_bilinear_tile : 8;
+  while (bs >= 1 && fixed + (size_t)arrays * bs * F * K * sizeof(float) > budget) bs >>= 1;
+  return bs;
+}
+
 static int grid_for(long long need, int per_sm) {
   long long g = (long long)sm_count() * per_sm;
   if (g > need) g = need;
@@ -342,6 +587,30 @@ extern "C" int ctr_senet_bwd(const float* x, const float* w1, const float* w2, c
   return CTR_OK;
 }
 
+
+// the tournament kernels need K in {8,16,32} and 16-byte aligned arrays
+static bool rr_usable(int64_t K, int type, const void* a, const void* b, const void* c, const void* d) {
+  if (!((g_bilinear_rr >> type) & 1)) return false;
+  if (K != 8 && K != 16 && K != 32) return false;
+  return aligned16(a) && aligned16(b) && aligned16(c) && (d == nullptr || aligned16(d));
+}
+
+#define RR_DISPATCH_T(KK, type, NAME, ...)                                \
+  if (type == 0) { auto kern = NAME<KK, 0>; __VA_ARGS__ }                 \
+  else if (type == 1) { auto kern = NAME<KK, 1>; __VA_ARGS__ }            \
+  else { auto kern = NAME<KK, 2>; __VA_ARGS__ }
+#define RR_DISPATCH(K, type, NAME, ...)                                   \
+  if (K == 8) { RR_DISPATCH_T(8, type, NAME, __VA_ARGS__) }               \
+  else if (K == 16) { RR_DISPATCH_T(16, type, NAME, __VA_ARGS__) }        \
+  else { RR_DISPATCH_T(32, type, NAME, __VA_ARGS__) }
+
+extern "C" int ctr_bilinear_set_rr(int mask) {
+  const int prev = g_bilinear_rr | (g_bilinear_tile << 4);
+  g_bilinear_rr = mask & 7;
+  g_bilinear_tile = (mask >> 4) & 63;                        // tuning only: samples per tile, 0 = automatic
+  return prev;
+}
+
 static int check_bilinear(const char* fn, int64_t B, int64_t F, int64_t K, int type) {
   CTR_REQUIRE(B >= 0 && F >= 1 && K >= 1, "%s: bad sizes", fn);
   // reference: ValueError for an unknown type (FiBiNET/bilinear_interaction_layer.py:36-38)
@@ -358,8 +627,26 @@ extern "C" int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64
   CTR_REQUIRE(x && w && out, "ctr_bilinear_fwd: null argument");
   const int64_t n = F - 1, P = n * (n - 1) / 2;
   if (B == 0 || P == 0) return CTR_OK;
-  const size_t smem = sizeof(float) * (F * K + n * K) + sizeof(int) * P;
   cudaStream_t st = as_stream(stream);
+  if (rr_usable(K, type, x, w, out, nullptr)) {
+    const RRShape sh = rr_shape((int)F);
+    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3);
+    int bs = rr_tile((int)F, (int)K, 1, fixed, 64 * 1024);
+    if (bs < 1) bs = rr_tile((int)F, (int)K, 1, fixed, 200 * 1024);
+    if (bs >= 1) {
+      const size_t smem_rr = fixed + sizeof(float) * bs * F * K;
+      const int threads = rr_threads((int)F, (int)K);
+      RR_DISPATCH(K, type, bilinear_rr_fwd_kernel, {
+        if (smem_rr > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_rr);
+        kern<<<grid_for((B + bs - 1) / bs, per_sm < 1 ? 1 : per_sm), threads, smem_rr, st>>>(x, w, (int)B, (int)F, bs, out);
+      });
+      CTR_CHECK_LAUNCH("ctr_bilinear_fwd");
+      return CTR_OK;
+    }
+  }
+  const size_t smem = sizeof(float) * (F * K + n * K) + sizeof(int) * P;
   const int grid = grid_for(B, 8);
 #define LAUNCH(T)                                                                                            \
   {                                                                                                          \
@@ -386,6 +673,34 @@ extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_o
   if (P == 0) {
     CTR_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * B * F * K, st));
     return CTR_OK;
+  }
+  if (rr_usable(K, type, x, w, dx, dw) && aligned16(g_out)) {
+    const RRShape sh = rr_shape((int)F);
+    const int threads = rr_threads((int)F, (int)K);
+    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3) + sizeof(float) * (threads / K) * 2 * K;
+    int bs = rr_tile((int)F, (int)K, 2, fixed, 72 * 1024);
+    if (bs < 1) bs = rr_tile((int)F, (int)K, 2, fixed, 200 * 1024);
+    if (bs >= 1) {
+      const size_t smem_rr = fixed + sizeof(float) * 2 * bs * F * K;
+      RR_DISPATCH(K, type, bilinear_rr_bwd_dx_kernel, {
+        if (smem_rr > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_rr);
+        kern<<<grid_for((B + bs - 1) / bs, per_sm < 1 ? 1 : per_sm), threads, smem_rr, st>>>(x, w, g_out, (int)B, (int)F, bs, dx);
+      });
+      CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dx)");
+      // weight gradient: one CTA per (round, batch chunk); ~4 CTAs per SM, at least 64 samples per chunk
+      int chunks = (4 * sm_count() + sh.rounds - 1) / sh.rounds;
+      const int max_chunks = (int)((B + 63) / 64);
+      if (chunks > max_chunks) chunks = max_chunks;
+      if (chunks < 1) chunks = 1;
+      const size_t smem_dw = sizeof(float) * (threads / K) * 2 * K;
+      RR_DISPATCH(K, type, bilinear_rr_bwd_dw_kernel, {
+        kern<<<dim3((unsigned)sh.rounds, (unsigned)chunks), threads, smem_dw, st>>>(x, g_out, (int)B, (int)F, dw);
+      });
+      CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dw)");
+      return CTR_OK;
+    }
   }
   if (type == 2) {
     const size_t smem = sizeof(float) * (2 * F * K + P * K) + sizeof(int) * P;

@@ -338,6 +338,12 @@ def bilinear_w_shape(F, K, type_):
     return {"all": (K, K), "each": (F - 1, K, K), "interaction": (F * (F - 1) // 2, K, K)}[type_]
 
 
+def bilinear_set_tournament(mask):
+    """Tuning hook: bit t of `mask` routes type t ('all', 'each', 'interaction') through the sample-batched tournament kernels
+    (default 7).  Returns the previous mask."""
+    return int(_lib.lib().ctr_bilinear_set_rr(int(mask)))
+
+
 def bilinear_fwd(x, w, type_):
     t = _bilinear_type(type_)
     B, F, K = x.shape

@@ -16,10 +16,15 @@ def test_fibinet_golden(name):
     x = dev(g["x"])
     assert_close(ops.senet_fwd(x, dev(g["senet_w1"]), dev(g["senet_w2"])), g["senet_f64"], TOL, "senet")
     F = g["x"].shape[1]
-    for typ in ("all", "each", "interaction"):
-        out = ops.bilinear_fwd(x, dev(g[f"w_{typ}"]), typ)
-        assert out.shape[1] == (F - 1) * (F - 2) // 2          # the reference's range(F-1) quirk
-        assert_close(out, g[f"bilinear_{typ}_f64"], TOL, f"bilinear {typ}")
+    for mask in (7, 0):                                        # tournament kernels, then the CTA-per-sample ones
+        prev = ops.bilinear_set_tournament(mask)
+        try:
+            for typ in ("all", "each", "interaction"):
+                out = ops.bilinear_fwd(x, dev(g[f"w_{typ}"]), typ)
+                assert out.shape[1] == (F - 1) * (F - 2) // 2          # the reference's range(F-1) quirk
+                assert_close(out, g[f"bilinear_{typ}_f64"], TOL, f"bilinear {typ}")
+        finally:
+            ops.bilinear_set_tournament(prev)
     with pytest.raises(ValueError):
         ops.bilinear_fwd(x, dev(g["w_all"]), "nope")
 
@@ -40,9 +45,19 @@ def test_senet_fwd_bwd(B, F, K, r):
         ops.senet_fwd(dev(x), dev(trunc_normal(rng, (F, K), 1.0)), dev(trunc_normal(rng, (K, F), 1.0)))
 
 
-@pytest.mark.parametrize("B,F,K", [(4, 8, 8), (37, 30, 16), (3, 3, 4), (5, 4, 16), (300, 9, 8), (2, 2, 4)])
+@pytest.fixture(params=[7, 0], ids=["tournament", "per_sample"])
+def bilinear_impl(request):
+    """Both kernel families: the sample-batched tournament form (default) and the CTA-per-sample form it falls back to."""
+    from recalgorithm_b200 import ops
+    prev = ops.bilinear_set_tournament(request.param)
+    yield request.param
+    ops.bilinear_set_tournament(prev)
+
+
+@pytest.mark.parametrize("B,F,K", [(4, 8, 8), (37, 30, 16), (3, 3, 4), (5, 4, 16), (300, 9, 8), (2, 2, 4), (19, 3, 16), (50, 7, 32),
+                                   (65, 41, 16), (130, 70, 8), (1, 30, 16)])
 @pytest.mark.parametrize("typ", ["all", "each", "interaction"])
-def test_bilinear_fwd_bwd(B, F, K, typ):
+def test_bilinear_fwd_bwd(B, F, K, typ, bilinear_impl):
     from recalgorithm_b200 import ops
     rng = np.random.default_rng(B + F + K)
     x = trunc_normal(rng, (B, F, K), 1.0)

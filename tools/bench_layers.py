@@ -127,10 +127,14 @@ def main():
         gp = rn(B, P, K)
         for typ in ("all", "each", "interaction"):
             w = rn(*ops.bilinear_w_shape(F, K, typ), std=0.2)
-            m, bst = timeit(lambda: ops.bilinear_fwd(x, w, typ), args.iters, flush)
-            emit(f"bilinear_fwd_{typ}", {"B": B, "F": F, "K": K}, m, bst, bytes_=B * (F * K + P * K) * 4)
-            m, bst = timeit(lambda: ops.bilinear_bwd(x, w, typ, gp), max(3, args.iters // 4), flush)
-            emit(f"bilinear_bwd_{typ}", {"B": B, "F": F, "K": K}, m, bst, bytes_=B * (2 * F * K + P * K) * 4)
+            for mask, impl in ((7, "tournament"), (7 | (4 << 4), "tournament, 4-sample tiles"), (7 | (16 << 4), "tournament, 16-sample tiles"),
+                               (0, "per_sample")):
+                prev = ops.bilinear_set_tournament(mask)
+                m, bst = timeit(lambda: ops.bilinear_fwd(x, w, typ), args.iters, flush)
+                emit(f"bilinear_fwd_{typ}", {"B": B, "F": F, "K": K, "impl": impl}, m, bst, bytes_=B * (F * K + P * K) * 4)
+                m, bst = timeit(lambda: ops.bilinear_bwd(x, w, typ, gp), max(3, args.iters // 4), flush)
+                emit(f"bilinear_bwd_{typ}", {"B": B, "F": F, "K": K, "impl": impl}, m, bst, bytes_=B * (2 * F * K + P * K) * 4)
+                ops.bilinear_set_tournament(prev)
 
     if "pairwise" in only:   # SURVEY 8f.4 siblings (FwFM at the config-5 tile shape; AFM at the reference's flag defaults and at F=30)
         B, F, K = 65536, 40, 32
