@@ -302,10 +302,12 @@ int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64_t F, int64
                      float* out, void* stream);
 int ctr_bilinear_bwd(const float* x, const float* w, const float* g_out, int64_t B, int64_t F, int64_t K, int type,
                      float* dx, float* dw, void* stream);
-/* Tuning hook (process-wide, returns the previous mask): bit t = 1 (default 7) runs type t through the sample-batched
- * "tournament" kernels (K in {8,16,32}, 16-byte aligned arrays; other shapes always use the CTA-per-sample kernels).
- * Bits 4..9: samples per shared-memory tile (0 = chosen automatically).
- * Same results; used by the parity tests (both forms) and tools/bench_layers.py for A/B timings. */
+/* Tuning hook (process-wide, returns the previous mask; default 4).  Bit t (t = 0,1,2): type t runs the sample-batched
+ * "tournament" kernels; otherwise 'all' / 'each' run the staged per-sample kernels and 'interaction' the round-1 kernels.
+ * Bit 3: 'all' / 'each' use the round-1 CTA-per-sample kernels instead of the staged ones.  Bits 4..9: samples per tile of
+ * the tournament kernels; bits 10..12: their weight columns per lane (1, 2, 4); 0 = chosen automatically.  The fast kernels
+ * need K in {8,16,32} and 16-byte aligned arrays; other shapes always use the round-1 kernels.  Same results in every
+ * setting; used by the parity tests (all forms) and tools/bench_layers.py for A/B timings. */
 int ctr_bilinear_set_rr(int mask);
 
 /* ---- siblings of FM2 ------------------------------------------------------------------------------------------

@@ -297,14 +297,17 @@ bilinear_bwd_interaction_dw_kernel(const float* __restrict__ x, const float* __r
 // The first kernels above run one CTA per sample and fetch every pair's K x K weight from L2 for every sample (416 KB per
 // sample for F = 30, K = 16, 'interaction'), and the 'interaction' weight gradient walks the batch with 4-byte strided loads:
 // 1.86 ms for 122 MB of algorithmic traffic.  Here a CTA owns a TILE of samples (x staged in shared memory once) and a group
-// of K lanes owns one pair at a time: lane l keeps column l and row l of the pair's weight in registers and reuses them for
-// every sample of the tile.  The pairs are visited in the order of a round-robin tournament (circle method): the pairs of one
-// round are field-disjoint, so inside a round every (sample, field, lane) element of the shared dx tile has exactly ONE
-// writer -- plain read-modify-writes, no shared-memory atomics; one block barrier per round.
-//   fwd : vw = x_i . W[:,l] ; out[b,p,l] = vw * x_j[l]
-//   dx  : dx_j[l] += g*vw ; dv[l] = g*x_j[l] (exchanged inside the group through shared memory) ; dx_i[l] += dv . W[l,:]
-//   dW  : second kernel, one CTA per (round, batch chunk): lane l accumulates row l of dW = sum_b x_i[l] * dv[:] in registers
+// of LP = K/KT lanes owns one pair at a time: a lane keeps KT columns and KT rows of the pair's weight in registers and reuses
+// them for every sample of the tile.  The pairs are visited in the order of a round-robin tournament (circle method): the
+// pairs of one round are field-disjoint, so inside a round every (sample, field, column) element of the shared dx tile has
+// exactly ONE writer -- plain read-modify-writes, no shared-memory atomics; one block barrier per round.
+//   fwd : vw[t] = x_i . W[:,k0+t] ; out[b,p,k0+t] = vw[t] * x_j[k0+t]
+//   dx  : dx_j[k] += g*vw ; dv[k] = g*x_j[k] (exchanged inside the group through shared memory) ; dx_i[c] += dv . W[c,:]
+//   dW  : second kernel, one CTA per (round, batch chunk): a lane accumulates KT rows of dW = sum_b x_i[c] * dv[:] in registers
 //         over all samples of its chunk (no weights needed), one vector red per 4 elements at the end.
+// KT (columns per lane) is the register-blocking knob: every x_i word a lane fetches from shared memory feeds KT FMAs, and the
+// shared-memory -> register path (128 B/clk/SM, a broadcast LDS.128 still returns 512 B) is what bounds these kernels: with
+// KT = 1 it is 4x oversubscribed against the FMA pipe (measured: fwd 60 us = the LDS time).
 // The weight index of a pair is 0 ('all'), i ('each') or the pair index ('interaction').
 // ---------------------------------------------------------------------------------------------------
 struct RRShape {
@@ -340,6 +343,26 @@ __device__ __forceinline__ void load_vec(float (&v)[K], const float* p) {      /
   }
 }
 
+template <int KT, bool LDG = false>
+__device__ __forceinline__ void ld_kt(float (&v)[KT], const float* p) {        // p aligned to KT floats
+  if constexpr (KT == 1) {
+    v[0] = LDG ? __ldg(p) : *p;
+  } else if constexpr (KT == 2) {
+    const float2 t = LDG ? __ldg(reinterpret_cast<const float2*>(p)) : *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    const float4 t = LDG ? __ldg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+}
+
+template <int KT>
+__device__ __forceinline__ void st_kt(float* p, const float (&v)[KT]) {
+  if constexpr (KT == 1) *p = v[0];
+  else if constexpr (KT == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  else *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 template <int K>
 __device__ __forceinline__ float dot_vec(const float (&a)[K], const float (&b)[K]) {
   float s0 = 0.f, s1 = 0.f;
@@ -348,20 +371,21 @@ __device__ __forceinline__ float dot_vec(const float (&a)[K], const float (&b)[K
   return s0 + s1;
 }
 
-constexpr int RR_SUB = 8;             // samples whose g / out accesses are issued together
+__device__ __forceinline__ size_t rr_widx(int type, int i, int p) { return type == 0 ? 0 : type == 1 ? (size_t)i : (size_t)p; }
 
 // smem: pair table (rounds*slots ints) | xs (BS * F*K)
-template <int K, int TYPE>
+template <int K, int KT>
 __global__ void __launch_bounds__(256)
-bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int B, int F, int BS,
+bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int type, int B, int F, int BS,
                        float* __restrict__ out) {
+  constexpr int LP = K / KT;
   extern __shared__ __align__(16) float smem[];
   const RRShape sh = rr_shape(F);
   const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
   int* tbl = reinterpret_cast<int*>(smem);
   float* xs = smem + ((sh.rounds * sh.slots + 3) & ~3);
   for (int t = threadIdx.x; t < sh.rounds * sh.slots; t += blockDim.x) tbl[t] = rr_pair(sh, t / sh.slots, t % sh.slots);
-  const int grp = threadIdx.x / K, l = threadIdx.x % K, G = blockDim.x / K;
+  const int grp = threadIdx.x / LP, k0 = (threadIdx.x % LP) * KT, G = blockDim.x / LP;
   const int ntiles = (B + BS - 1) / BS;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b0 = tile * BS, bs = min(BS, B - b0);
@@ -374,16 +398,24 @@ bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
         const int ij = tbl[r * sh.slots + slot];
         const int i = ij >> 16, j = ij & 0xffff;
         const int p = pair_base(i, n) + (j - i - 1);
-        const float* wp = w + (size_t)(TYPE == 0 ? 0 : TYPE == 1 ? i : p) * K * K;
-        float wcol[K];
+        const float* wp = w + rr_widx(type, i, p) * K * K;
+        float wcol[KT][K];
 #pragma unroll
-        for (int c = 0; c < K; ++c) wcol[c] = __ldg(wp + c * K + l);
-        float* ob = out + ((size_t)b0 * P + p) * K + l;
-#pragma unroll 4
+        for (int c = 0; c < K; ++c) {
+          float t[KT];
+          ld_kt<KT, true>(t, wp + c * K + k0);
+#pragma unroll
+          for (int u = 0; u < KT; ++u) wcol[u][c] = t[u];
+        }
+        float* ob = out + ((size_t)b0 * P + p) * K + k0;
+#pragma unroll 2
         for (int s = 0; s < bs; ++s) {
-          float xi[K];
+          float xi[K], xj[KT], o[KT];
           load_vec<K>(xi, xs + s * FK + i * K);
-          ob[(size_t)s * P * K] = dot_vec<K>(xi, wcol) * xs[s * FK + j * K + l];
+          ld_kt<KT>(xj, xs + s * FK + j * K + k0);
+#pragma unroll
+          for (int u = 0; u < KT; ++u) o[u] = dot_vec<K>(xi, wcol[u]) * xj[u];
+          st_kt<KT>(ob + (size_t)s * P * K, o);
         }
       }
     }
@@ -391,10 +423,12 @@ bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
 }
 
 // smem: pair table | xs (BS*FK) | dxs (BS*FK) | dv exchange (groups * 2 * K)
-template <int K, int TYPE>
+template <int K, int KT>
 __global__ void __launch_bounds__(256)
-bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g, int B,
-                          int F, int BS, float* __restrict__ dx) {
+bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g, int type,
+                          int B, int F, int BS, float* __restrict__ dx) {
+  constexpr int LP = K / KT;
+  constexpr int SUB = KT >= 4 ? 2 : 4;                  // samples whose g loads are issued together
   extern __shared__ __align__(16) float smem[];
   const RRShape sh = rr_shape(F);
   const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
@@ -403,7 +437,7 @@ bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__
   float* dxs = xs + (size_t)BS * FK;
   float* dvb = dxs + (size_t)BS * FK;
   for (int t = threadIdx.x; t < sh.rounds * sh.slots; t += blockDim.x) tbl[t] = rr_pair(sh, t / sh.slots, t % sh.slots);
-  const int grp = threadIdx.x / K, l = threadIdx.x % K, G = blockDim.x / K;
+  const int grp = threadIdx.x / LP, k0 = (threadIdx.x % LP) * KT, G = blockDim.x / LP;
   float* mydv = dvb + grp * 2 * K;
   const int nslot_it = (sh.slots + G - 1) / G;          // same trip count for every group: the warp stays converged for __syncwarp
   const int ntiles = (B + BS - 1) / BS;
@@ -422,34 +456,56 @@ bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__
         const int ij = act ? tbl[r * sh.slots + slot] : 1;     // idle groups shadow pair (0,1): loads only, no stores
         const int i = ij >> 16, j = ij & 0xffff;
         const int p = pair_base(i, n) + (j - i - 1);
-        const float* wp = w + (size_t)(TYPE == 0 ? 0 : TYPE == 1 ? i : p) * K * K;
-        float wcol[K], wrow[K];
+        const float* wp = w + rr_widx(type, i, p) * K * K;
+        float wcol[KT][K], wrow[KT][K];
 #pragma unroll
-        for (int c = 0; c < K; ++c) wcol[c] = __ldg(wp + c * K + l);
+        for (int c = 0; c < K; ++c) {
+          float t[KT];
+          ld_kt<KT, true>(t, wp + c * K + k0);
 #pragma unroll
-        for (int q = 0; q < K / 4; ++q) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(wp + l * K) + q);
-          wrow[4 * q] = t.x; wrow[4 * q + 1] = t.y; wrow[4 * q + 2] = t.z; wrow[4 * q + 3] = t.w;
+          for (int u = 0; u < KT; ++u) wcol[u][c] = t[u];
         }
-        const float* gb = g + ((size_t)b0 * P + p) * K + l;
-        for (int s0 = 0; s0 < bs; s0 += RR_SUB) {
-          float gv[RR_SUB];
 #pragma unroll
-          for (int u = 0; u < RR_SUB; ++u) gv[u] = (s0 + u < bs) ? __ldg(gb + (size_t)(s0 + u) * P * K) : 0.f;
+        for (int u = 0; u < KT; ++u) {
 #pragma unroll
-          for (int u = 0; u < RR_SUB; ++u) {
+          for (int q = 0; q < K / 4; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(wp + (k0 + u) * K) + q);
+            wrow[u][4 * q] = t.x; wrow[u][4 * q + 1] = t.y; wrow[u][4 * q + 2] = t.z; wrow[u][4 * q + 3] = t.w;
+          }
+        }
+        const float* gb = g + ((size_t)b0 * P + p) * K + k0;
+        for (int s0 = 0; s0 < bs; s0 += SUB) {
+          float gv[SUB][KT];
+#pragma unroll
+          for (int u = 0; u < SUB; ++u) {
+            if (s0 + u < bs) ld_kt<KT, true>(gv[u], gb + (size_t)(s0 + u) * P * K);
+            else {
+#pragma unroll
+              for (int t = 0; t < KT; ++t) gv[u][t] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < SUB; ++u) {
             const int s = s0 + u;
             if (s < bs) {                                      // bs is uniform over the CTA
-              float xi[K], dv[K];
+              float xi[K], dv[K], xj[KT], dvl[KT], dj[KT], di[KT];
               load_vec<K>(xi, xs + s * FK + i * K);
-              const float vw = dot_vec<K>(xi, wcol);
-              const float dvl = gv[u] * xs[s * FK + j * K + l];
+              ld_kt<KT>(xj, xs + s * FK + j * K + k0);
+              ld_kt<KT>(dj, dxs + s * FK + j * K + k0);
+#pragma unroll
+              for (int t = 0; t < KT; ++t) {
+                dvl[t] = gv[u][t] * xj[t];
+                dj[t] += gv[u][t] * dot_vec<K>(xi, wcol[t]);
+              }
               float* buf = mydv + (u & 1) * K;
-              buf[l] = dvl;
-              if (act) dxs[s * FK + j * K + l] += gv[u] * vw;
+              st_kt<KT>(buf + k0, dvl);
+              if (act) st_kt<KT>(dxs + s * FK + j * K + k0, dj);
               __syncwarp();
               load_vec<K>(dv, buf);
-              if (act) dxs[s * FK + i * K + l] += dot_vec<K>(dv, wrow);
+              ld_kt<KT>(di, dxs + s * FK + i * K + k0);
+#pragma unroll
+              for (int t = 0; t < KT; ++t) di[t] += dot_vec<K>(dv, wrow[t]);
+              if (act) st_kt<KT>(dxs + s * FK + i * K + k0, di);
             }
           }
         }
@@ -463,14 +519,17 @@ bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__
 
 // grid (rounds, chunks).  smem: dv exchange (groups * 2 * K).  x is read through L2 (7.9 MB at config size, every round
 // reads it once), g streams from HBM exactly once.
-template <int K, int TYPE>
+template <int K, int KT>
 __global__ void __launch_bounds__(256)
-bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ g, int B, int F, float* __restrict__ dw) {
+bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ g, int type, int B, int F,
+                          float* __restrict__ dw) {
+  constexpr int LP = K / KT;
+  constexpr int SUB = 8 / KT;                             // samples whose loads are issued together (even: the exchange buffers alternate)
   extern __shared__ __align__(16) float smem[];
   const RRShape sh = rr_shape(F);
   const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
   const int r = blockIdx.x;
-  const int grp = threadIdx.x / K, l = threadIdx.x % K, G = blockDim.x / K;
+  const int grp = threadIdx.x / LP, k0 = (threadIdx.x % LP) * KT, G = blockDim.x / LP;
   float* mydv = smem + grp * 2 * K;
   const int per = (B + gridDim.y - 1) / gridDim.y;
   const int b_lo = blockIdx.y * per, b_hi = min(B, b_lo + per);
@@ -481,51 +540,228 @@ bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__
     const int ij = act ? rr_pair(sh, r, slot) : 1;
     const int i = ij >> 16, j = ij & 0xffff;
     const int p = pair_base(i, n) + (j - i - 1);
-    float acc[K];
+    float acc[KT][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.f;
-    const float* xi_p = x + (size_t)i * K + l;
-    const float* xj_p = x + (size_t)j * K + l;
-    const float* g_p = g + (size_t)p * K + l;
-    for (int s0 = b_lo; s0 < b_hi; s0 += RR_SUB) {
-      float xi[RR_SUB], dvl[RR_SUB];
+    for (int t = 0; t < KT; ++t) {
 #pragma unroll
-      for (int u = 0; u < RR_SUB; ++u) {
+      for (int k = 0; k < K; ++k) acc[t][k] = 0.f;
+    }
+    const float* xi_p = x + (size_t)i * K + k0;
+    const float* xj_p = x + (size_t)j * K + k0;
+    const float* g_p = g + (size_t)p * K + k0;
+    for (int s0 = b_lo; s0 < b_hi; s0 += SUB) {
+      float xi[SUB][KT], dvl[SUB][KT];
+#pragma unroll
+      for (int u = 0; u < SUB; ++u) {
         const int b = s0 + u;
-        const bool ok = b < b_hi;
-        xi[u] = ok ? __ldg(xi_p + (size_t)b * FK) : 0.f;
-        const float xj = ok ? __ldg(xj_p + (size_t)b * FK) : 0.f;
-        dvl[u] = ok ? __ldg(g_p + (size_t)b * P * K) * xj : 0.f;
+        if (b < b_hi) {
+          float xj[KT], gv[KT];
+          ld_kt<KT, true>(xi[u], xi_p + (size_t)b * FK);
+          ld_kt<KT, true>(xj, xj_p + (size_t)b * FK);
+          ld_kt<KT, true>(gv, g_p + (size_t)b * P * K);
+#pragma unroll
+          for (int t = 0; t < KT; ++t) dvl[u][t] = gv[t] * xj[t];
+        } else {
+#pragma unroll
+          for (int t = 0; t < KT; ++t) { xi[u][t] = 0.f; dvl[u][t] = 0.f; }
+        }
       }
 #pragma unroll
-      for (int u = 0; u < RR_SUB; ++u) {
+      for (int u = 0; u < SUB; ++u) {
         float* buf = mydv + (u & 1) * K;
-        buf[l] = dvl[u];
+        st_kt<KT>(buf + k0, dvl[u]);
         __syncwarp();
         float dv[K];
         load_vec<K>(dv, buf);
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] += xi[u] * dv[k];
+        for (int t = 0; t < KT; ++t) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[t][k] += xi[u][t] * dv[k];
+        }
       }
     }
     if (act) {
-      float* dst = dw + (size_t)(TYPE == 0 ? 0 : TYPE == 1 ? i : p) * K * K + (size_t)l * K;
+      float* dst = dw + rr_widx(type, i, p) * K * K + (size_t)k0 * K;
 #pragma unroll
-      for (int q = 0; q < K / 4; ++q)
-        atomicAdd(reinterpret_cast<float4*>(dst) + q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+      for (int t = 0; t < KT; ++t) {
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q)
+          atomicAdd(reinterpret_cast<float4*>(dst + t * K) + q,
+                    make_float4(acc[t][4 * q], acc[t][4 * q + 1], acc[t][4 * q + 2], acc[t][4 * q + 3]));
+      }
     }
   }
 }
 
-static int g_bilinear_rr = 7;          // bit t: type t runs the tournament kernels (ctr_bilinear_set_rr)
-static int g_bilinear_tile = 0;        // tuning: samples per tile (0 = chosen from the shared-memory budget)
+// ---------------------------------------------------------------------------------------------------
+// bilinear 'all' / 'each', staged per-sample form (K = 8 / 16 / 32): the reference's default type is 'all'
+// (FiBiNET/fibinet.py:45).  With one weight ('all') or one per field ('each') the projection vw_i = x_i W_i is computed once
+// per field (n*K*K FMAs per sample instead of P*K*K) and the rest is element-wise over the (P,K) tile: these types want to be
+// HBM streams.  The first kernels lost that to (1) runtime divisions `t / K, t % K` on every element, (2) 4-byte strided
+// __ldg walks over g (twice per sample) and (3) un-overlapped loads.  Here K is a template parameter, the NEXT sample's x row
+// and g tile are fetched with cp.async into a second buffer while the current one is processed, and both sweeps over g read
+// the shared-memory copy.  One CTA works on one sample at a time; thread (f,k) owns dvw_f[k] and dx_f[k].
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bl_cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bl_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bl_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// threads of a tournament CTA: as many K-lane groups as one round has pairs, at most 256 threads, whole warps
-static int rr_threads(int F, int K) {
+constexpr int BST_THREADS = 512;
+
+// smem: ws (nw*K*K) | xs[2] (F*K) | vw (n*K) | pair table (P ints)
+template <int K, int TYPE>
+__global__ void __launch_bounds__(BST_THREADS)
+bilinear_st_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int B, int F, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = F - 1, P = n * (n - 1) / 2, FK = F * K;
+  const int nw = TYPE == 0 ? 1 : n;
+  float* ws = smem;
+  float* xs = ws + nw * K * K;
+  float* vw = xs + 2 * FK;
+  int* pairs = reinterpret_cast<int*>(vw + n * K);
+  for (int t = threadIdx.x; t < nw * K * K; t += blockDim.x) ws[t] = __ldg(w + t);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int j = i + 1; j < n; ++j) pairs[pair_base(i, n) + (j - i - 1)] = (i << 16) | j;
+  int buf = 0;
+  if (blockIdx.x < B)
+    for (int t = threadIdx.x; t < FK / 4; t += blockDim.x) bl_cp_async16(xs + 4 * t, x + (size_t)blockIdx.x * FK + 4 * t);
+  bl_cp_async_commit();
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    bl_cp_async_wait_all();
+    __syncthreads();                                         // xs[buf] landed; vw of the previous sample is no longer read
+    const int bn = b + gridDim.x;
+    if (bn < B)
+      for (int t = threadIdx.x; t < FK / 4; t += blockDim.x) bl_cp_async16(xs + (buf ^ 1) * FK + 4 * t, x + (size_t)bn * FK + 4 * t);
+    bl_cp_async_commit();
+    const float* xb = xs + buf * FK;
+    for (int t = threadIdx.x; t < n * K; t += blockDim.x) {
+      const int i = t / K, k = t % K;
+      const float* wi = ws + (TYPE == 0 ? 0 : i * K * K);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < K; c += 2) { s0 += xb[i * K + c] * wi[c * K + k]; s1 += xb[i * K + c + 1] * wi[(c + 1) * K + k]; }
+      vw[t] = s0 + s1;
+    }
+    __syncthreads();
+    float4* ob = reinterpret_cast<float4*>(out + (size_t)b * P * K);
+    for (int t = threadIdx.x; t < P * K / 4; t += blockDim.x) {
+      const int p = t / (K / 4), k4 = (t % (K / 4)) * 4;
+      const int ij = pairs[p];
+      const float4 a = *reinterpret_cast<const float4*>(vw + (ij >> 16) * K + k4);
+      const float4 c = *reinterpret_cast<const float4*>(xb + (ij & 0xffff) * K + k4);
+      stg_stream_f4(ob + t, make_float4(a.x * c.x, a.y * c.y, a.z * c.z, a.w * c.w));
+    }
+    buf ^= 1;
+  }
+}
+
+// smem: ws (nw*K*K) | dwacc (nw*K*K) | xs[2] (F*K) | gs[2] (P*K) | vw (n*K) | dvw (n*K)
+template <int K, int TYPE>
+__global__ void __launch_bounds__(BST_THREADS)
+bilinear_st_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g, int B, int F,
+                       float* __restrict__ dx, float* __restrict__ dw) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = F - 1, P = n * (n - 1) / 2, FK = F * K, PK = P * K;
+  const int nw = TYPE == 0 ? 1 : n;
+  float* ws = smem;
+  float* dwacc = ws + nw * K * K;
+  float* xs = dwacc + nw * K * K;
+  float* gs = xs + 2 * FK;
+  float* vw = gs + 2 * (size_t)PK;
+  float* dvw = vw + n * K;
+  for (int t = threadIdx.x; t < nw * K * K; t += blockDim.x) { ws[t] = __ldg(w + t); dwacc[t] = 0.f; }
+  auto fetch = [&](int b, int bf) {
+    for (int t = threadIdx.x; t < FK / 4; t += blockDim.x) bl_cp_async16(xs + bf * FK + 4 * t, x + (size_t)b * FK + 4 * t);
+    for (int t = threadIdx.x; t < PK / 4; t += blockDim.x) bl_cp_async16(gs + (size_t)bf * PK + 4 * t, g + (size_t)b * PK + 4 * t);
+  };
+  int buf = 0;
+  if (blockIdx.x < B) fetch(blockIdx.x, 0);
+  bl_cp_async_commit();
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    bl_cp_async_wait_all();
+    __syncthreads();                                         // this sample's tiles landed; vw / dvw of the previous one are free
+    const int bn = b + gridDim.x;
+    if (bn < B) fetch(bn, buf ^ 1);
+    bl_cp_async_commit();
+    const float* xb = xs + buf * FK;
+    const float* gb = gs + (size_t)buf * PK;
+    // sweep 1, thread (i,k): vw_i[k] = x_i . W_i[:,k] ;  dvw_i[k] = sum_{j>i} g[(i,j),k] * x_j[k]   (pairs of i are contiguous)
+    for (int t = threadIdx.x; t < n * K; t += blockDim.x) {
+      const int i = t / K, k = t % K;
+      const float* wi = ws + (TYPE == 0 ? 0 : i * K * K);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < K; c += 2) { s0 += xb[i * K + c] * wi[c * K + k]; s1 += xb[i * K + c + 1] * wi[(c + 1) * K + k]; }
+      vw[t] = s0 + s1;
+      const float* gp = gb + pair_base(i, n) * K + k;
+      float d0 = 0.f, d1 = 0.f;
+      int j = i + 1;
+      for (; j + 1 < n; j += 2) {
+        d0 += gp[(j - i - 1) * K] * xb[j * K + k];
+        d1 += gp[(j - i) * K] * xb[(j + 1) * K + k];
+      }
+      if (j < n) d0 += gp[(j - i - 1) * K] * xb[j * K + k];
+      dvw[t] = d0 + d1;
+    }
+    __syncthreads();
+    // sweep 2, thread (j,k): dx_j[k] = sum_{i<j} g[(i,j),k]*vw_i[k] + sum_c dvw_j[c] * W_j[k][c]   (field F-1: zero)
+    for (int t = threadIdx.x; t < FK; t += blockDim.x) {
+      const int j = t / K, k = t % K;
+      float s0 = 0.f, s1 = 0.f;
+      if (j < n) {
+        int i = 0;
+        for (; i + 1 < j; i += 2) {
+          s0 += gb[(pair_base(i, n) + j - i - 1) * K + k] * vw[i * K + k];
+          s1 += gb[(pair_base(i + 1, n) + j - i - 2) * K + k] * vw[(i + 1) * K + k];
+        }
+        if (i < j) s0 += gb[(pair_base(i, n) + j - i - 1) * K + k] * vw[i * K + k];
+        const float* wj = ws + (TYPE == 0 ? 0 : j * K * K) + k * K;
+#pragma unroll
+        for (int c = 0; c < K; c += 2) { s0 += dvw[j * K + c] * wj[c]; s1 += dvw[j * K + c + 1] * wj[c + 1]; }
+      }
+      dx[(size_t)b * FK + t] = s0 + s1;
+    }
+    // dW_i[c][k] += x_i[c] * dvw_i[k]   (element e is always visited by the same thread: private accumulators in smem)
+    for (int e = threadIdx.x; e < nw * K * K; e += blockDim.x) {
+      const int k = e % K, c = (e / K) % K;
+      if (TYPE == 0) {
+        float s0 = 0.f, s1 = 0.f;
+        int i = 0;
+        for (; i + 1 < n; i += 2) { s0 += xb[i * K + c] * dvw[i * K + k]; s1 += xb[(i + 1) * K + c] * dvw[(i + 1) * K + k]; }
+        if (i < n) s0 += xb[i * K + c] * dvw[i * K + k];
+        dwacc[e] += s0 + s1;
+      } else {
+        const int i = e / (K * K);
+        dwacc[e] += xb[i * K + c] * dvw[i * K + k];
+      }
+    }
+    buf ^= 1;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nw * K * K; e += blockDim.x) atomicAdd(dw + e, dwacc[e]);
+}
+
+
+static int g_bilinear_rr = 4;          // bit t: type t runs the tournament kernels (ctr_bilinear_set_rr); default: 'interaction' only
+static int g_bilinear_old = 0;         // 1: 'all' / 'each' use the round-1 CTA-per-sample kernels instead of the staged ones
+static int g_bilinear_tile = 0;        // tuning: samples per tile (0 = chosen from the shared-memory budget)
+static int g_bilinear_kt = 0;          // tuning: weight columns per lane (0 = default for K)
+
+static int rr_kt(int K) {
+  int kt = g_bilinear_kt > 0 ? g_bilinear_kt : 2;
+  while (kt > 1 && (K * kt > 64 || K / kt < 2)) kt >>= 1;      // <= 64 weight registers per operand, >= 2 lanes per pair
+  return kt;
+}
+
+// threads of a tournament CTA: as many (K/kt)-lane groups as one round has pairs, at most 256 threads, whole warps
+static int rr_threads(int F, int K, int kt) {
   const RRShape sh = rr_shape(F);
-  int G = sh.slots < 256 / K ? sh.slots : 256 / K;
+  const int lp = K / kt;
+  int G = sh.slots < 256 / lp ? sh.slots : 256 / lp;
   if (G < 1) G = 1;
-  return (G * K + 31) / 32 * 32;
+  return (G * lp + 31) / 32 * 32;
 }
 
 // samples per tile so that `arrays` staged copies of the tile fit `budget` bytes (0: not even one sample fits)
@@ -595,19 +831,32 @@ static bool rr_usable(int64_t K, int type, const void* a, const void* b, const v
   return aligned16(a) && aligned16(b) && aligned16(c) && (d == nullptr || aligned16(d));
 }
 
-#define RR_DISPATCH_T(KK, type, NAME, ...)                                \
-  if (type == 0) { auto kern = NAME<KK, 0>; __VA_ARGS__ }                 \
-  else if (type == 1) { auto kern = NAME<KK, 1>; __VA_ARGS__ }            \
-  else { auto kern = NAME<KK, 2>; __VA_ARGS__ }
-#define RR_DISPATCH(K, type, NAME, ...)                                   \
-  if (K == 8) { RR_DISPATCH_T(8, type, NAME, __VA_ARGS__) }               \
-  else if (K == 16) { RR_DISPATCH_T(16, type, NAME, __VA_ARGS__) }        \
-  else { RR_DISPATCH_T(32, type, NAME, __VA_ARGS__) }
+// the staged per-sample kernels ('all' / 'each'): K in {8,16,32}, 16-byte aligned arrays
+static bool st_usable(int64_t K, int type, const void* a, const void* b, const void* c, const void* d) {
+  if (g_bilinear_old || type > 1) return false;
+  if (K != 8 && K != 16 && K != 32) return false;
+  return aligned16(a) && aligned16(b) && aligned16(c) && (d == nullptr || aligned16(d));
+}
+#define ST_DISPATCH(K, type, NAME, ...)                                                  \
+  if (K == 8) { if (type == 0) { auto kern = NAME<8, 0>; __VA_ARGS__ } else { auto kern = NAME<8, 1>; __VA_ARGS__ } }        \
+  else if (K == 16) { if (type == 0) { auto kern = NAME<16, 0>; __VA_ARGS__ } else { auto kern = NAME<16, 1>; __VA_ARGS__ } } \
+  else { if (type == 0) { auto kern = NAME<32, 0>; __VA_ARGS__ } else { auto kern = NAME<32, 1>; __VA_ARGS__ } }
+
+#define RR_DISPATCH_KT(KK, kt, NAME, ...)                                  \
+  if (kt == 1) { auto kern = NAME<KK, 1>; __VA_ARGS__ }                   \
+  else if (kt == 2) { auto kern = NAME<KK, 2>; __VA_ARGS__ }              \
+  else { auto kern = NAME<KK, (KK <= 16 ? 4 : 2)>; __VA_ARGS__ }
+#define RR_DISPATCH(K, kt, NAME, ...)                                     \
+  if (K == 8) { RR_DISPATCH_KT(8, kt, NAME, __VA_ARGS__) }                \
+  else if (K == 16) { RR_DISPATCH_KT(16, kt, NAME, __VA_ARGS__) }         \
+  else { RR_DISPATCH_KT(32, kt, NAME, __VA_ARGS__) }
 
 extern "C" int ctr_bilinear_set_rr(int mask) {
-  const int prev = g_bilinear_rr | (g_bilinear_tile << 4);
+  const int prev = g_bilinear_rr | (g_bilinear_old << 3) | (g_bilinear_tile << 4) | (g_bilinear_kt << 10);
   g_bilinear_rr = mask & 7;
+  g_bilinear_old = (mask >> 3) & 1;
   g_bilinear_tile = (mask >> 4) & 63;                        // tuning only: samples per tile, 0 = automatic
+  g_bilinear_kt = (mask >> 10) & 7;                          // tuning only: weight columns per lane (1, 2, 4), 0 = automatic
   return prev;
 }
 
@@ -635,12 +884,27 @@ extern "C" int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64
     if (bs < 1) bs = rr_tile((int)F, (int)K, 1, fixed, 200 * 1024);
     if (bs >= 1) {
       const size_t smem_rr = fixed + sizeof(float) * bs * F * K;
-      const int threads = rr_threads((int)F, (int)K);
-      RR_DISPATCH(K, type, bilinear_rr_fwd_kernel, {
+      const int kt = rr_kt((int)K);
+      const int threads = rr_threads((int)F, (int)K, kt);
+      RR_DISPATCH(K, kt, bilinear_rr_fwd_kernel, {
         if (smem_rr > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_rr);
-        kern<<<grid_for((B + bs - 1) / bs, per_sm < 1 ? 1 : per_sm), threads, smem_rr, st>>>(x, w, (int)B, (int)F, bs, out);
+        kern<<<grid_for((B + bs - 1) / bs, per_sm < 1 ? 1 : per_sm), threads, smem_rr, st>>>(x, w, type, (int)B, (int)F, bs, out);
+      });
+      CTR_CHECK_LAUNCH("ctr_bilinear_fwd");
+      return CTR_OK;
+    }
+  }
+  if (st_usable(K, type, x, w, out, nullptr)) {
+    const int64_t nw = type == 0 ? 1 : n;
+    const size_t smem_st = sizeof(float) * (nw * K * K + 2 * F * K + n * K) + sizeof(int) * P;
+    if (smem_st <= 200 * 1024) {
+      ST_DISPATCH(K, type, bilinear_st_fwd_kernel, {
+        if (smem_st > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st));
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BST_THREADS, smem_st);
+        kern<<<grid_for(B, per_sm < 1 ? 1 : per_sm), BST_THREADS, smem_st, st>>>(x, w, (int)B, (int)F, out);
       });
       CTR_CHECK_LAUNCH("ctr_bilinear_fwd");
       return CTR_OK;
@@ -676,17 +940,19 @@ extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_o
   }
   if (rr_usable(K, type, x, w, dx, dw) && aligned16(g_out)) {
     const RRShape sh = rr_shape((int)F);
-    const int threads = rr_threads((int)F, (int)K);
-    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3) + sizeof(float) * (threads / K) * 2 * K;
+    const int kt = rr_kt((int)K);
+    const int lp = (int)K / kt;
+    const int threads = rr_threads((int)F, (int)K, kt);
+    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3) + sizeof(float) * (threads / lp) * 2 * K;
     int bs = rr_tile((int)F, (int)K, 2, fixed, 72 * 1024);
     if (bs < 1) bs = rr_tile((int)F, (int)K, 2, fixed, 200 * 1024);
     if (bs >= 1) {
       const size_t smem_rr = fixed + sizeof(float) * 2 * bs * F * K;
-      RR_DISPATCH(K, type, bilinear_rr_bwd_dx_kernel, {
+      RR_DISPATCH(K, kt, bilinear_rr_bwd_dx_kernel, {
         if (smem_rr > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_rr);
-        kern<<<grid_for((B + bs - 1) / bs, per_sm < 1 ? 1 : per_sm), threads, smem_rr, st>>>(x, w, g_out, (int)B, (int)F, bs, dx);
+        kern<<<grid_for((B + bs - 1) / bs, per_sm < 1 ? 1 : per_sm), threads, smem_rr, st>>>(x, w, g_out, type, (int)B, (int)F, bs, dx);
       });
       CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dx)");
       // weight gradient: one CTA per (round, batch chunk); ~4 CTAs per SM, at least 64 samples per chunk
@@ -694,9 +960,9 @@ extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_o
       const int max_chunks = (int)((B + 63) / 64);
       if (chunks > max_chunks) chunks = max_chunks;
       if (chunks < 1) chunks = 1;
-      const size_t smem_dw = sizeof(float) * (threads / K) * 2 * K;
-      RR_DISPATCH(K, type, bilinear_rr_bwd_dw_kernel, {
-        kern<<<dim3((unsigned)sh.rounds, (unsigned)chunks), threads, smem_dw, st>>>(x, g_out, (int)B, (int)F, dw);
+      const size_t smem_dw = sizeof(float) * (threads / lp) * 2 * K;
+      RR_DISPATCH(K, kt, bilinear_rr_bwd_dw_kernel, {
+        kern<<<dim3((unsigned)sh.rounds, (unsigned)chunks), threads, smem_dw, st>>>(x, g_out, type, (int)B, (int)F, dw);
       });
       CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dw)");
       return CTR_OK;
@@ -717,6 +983,20 @@ extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_o
                                                                                                (int)K, dw);
     CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dw)");
     return CTR_OK;
+  }
+  if (st_usable(K, type, x, w, dx, dw) && aligned16(g_out)) {
+    const int64_t nw = type == 0 ? 1 : n;
+    const size_t smem_st = sizeof(float) * (2 * nw * K * K + 2 * F * K + 2 * P * K + 2 * n * K);
+    if (smem_st <= 200 * 1024) {
+      ST_DISPATCH(K, type, bilinear_st_bwd_kernel, {
+        if (smem_st > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st));
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BST_THREADS, smem_st);
+        kern<<<grid_for(B, per_sm < 1 ? 1 : per_sm), BST_THREADS, smem_st, st>>>(x, w, g_out, (int)B, (int)F, dx, dw);
+      });
+      CTR_CHECK_LAUNCH("ctr_bilinear_bwd");
+      return CTR_OK;
+    }
   }
   const size_t smem = sizeof(float) * (F * K + 2 * n * K + (type == 0 ? 1 : n) * K * K);
   CTR_UNSUPPORTED(smem > 200 * 1024, "ctr_bilinear_bwd: F=%lld K=%lld needs %zu B of shared memory", (long long)F,

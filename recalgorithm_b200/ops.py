@@ -339,8 +339,9 @@ def bilinear_w_shape(F, K, type_):
 
 
 def bilinear_set_tournament(mask):
-    """Tuning hook: bit t of `mask` routes type t ('all', 'each', 'interaction') through the sample-batched tournament kernels
-    (default 7).  Returns the previous mask."""
+    """Tuning hook (see ctr_bilinear_set_rr in include/ctr_b200.h): bits 0..2 route type 'all' / 'each' / 'interaction' through
+    the sample-batched tournament kernels (default 4: 'interaction' only; 'all' / 'each' run the staged per-sample kernels),
+    bit 3 selects the round-1 kernels for 'all' / 'each'.  Returns the previous mask."""
     return int(_lib.lib().ctr_bilinear_set_rr(int(mask)))
 
 

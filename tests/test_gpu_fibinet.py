@@ -16,7 +16,7 @@ def test_fibinet_golden(name):
     x = dev(g["x"])
     assert_close(ops.senet_fwd(x, dev(g["senet_w1"]), dev(g["senet_w2"])), g["senet_f64"], TOL, "senet")
     F = g["x"].shape[1]
-    for mask in (7, 0):                                        # tournament kernels, then the CTA-per-sample ones
+    for mask in (4, 7, 8):                                     # default, tournament kernels for every type, round-1 kernels
         prev = ops.bilinear_set_tournament(mask)
         try:
             for typ in ("all", "each", "interaction"):
@@ -45,9 +45,11 @@ def test_senet_fwd_bwd(B, F, K, r):
         ops.senet_fwd(dev(x), dev(trunc_normal(rng, (F, K), 1.0)), dev(trunc_normal(rng, (K, F), 1.0)))
 
 
-@pytest.fixture(params=[7, 0], ids=["tournament", "per_sample"])
+@pytest.fixture(params=[4, 7, 7 | (1 << 10), 7 | (4 << 10) | (16 << 4), 8, 0],
+                ids=["default", "tournament", "tournament_kt1", "tournament_kt4_tile16", "round1_kernels", "staged_all_each_round1_interaction"])
 def bilinear_impl(request):
-    """Both kernel families: the sample-batched tournament form (default) and the CTA-per-sample form it falls back to."""
+    """Every kernel family: default (staged per-sample kernels for 'all'/'each', tournament kernels for 'interaction'), the
+    tournament kernels for all three types in three register-blocking variants, and the round-1 CTA-per-sample kernels."""
     from recalgorithm_b200 import ops
     prev = ops.bilinear_set_tournament(request.param)
     yield request.param

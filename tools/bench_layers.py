@@ -45,6 +45,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="dcn,cin,din,fibinet")
+    ap.add_argument("--sweep", action="store_true", help="bilinear: also time every (columns per lane, tile) variant of the tournament kernels")
     args = ap.parse_args()
     only = set(args.only.split(","))
     torch.cuda.set_device(0)
@@ -127,8 +128,11 @@ def main():
         gp = rn(B, P, K)
         for typ in ("all", "each", "interaction"):
             w = rn(*ops.bilinear_w_shape(F, K, typ), std=0.2)
-            for mask, impl in ((7, "tournament"), (7 | (4 << 4), "tournament, 4-sample tiles"), (7 | (16 << 4), "tournament, 16-sample tiles"),
-                               (0, "per_sample")):
+            variants = [(4, "default (staged all/each, tournament interaction)"), (7, "tournament")]
+            if args.sweep:
+                variants += [(7 | (kt << 10) | (tile << 4), f"tournament kt={kt} tile={tile}") for kt in (1, 2, 4) for tile in (8, 16)]
+            variants += [(8, "round-1 CTA-per-sample kernels")]
+            for mask, impl in variants:
                 prev = ops.bilinear_set_tournament(mask)
                 m, bst = timeit(lambda: ops.bilinear_fwd(x, w, typ), args.iters, flush)
                 emit(f"bilinear_fwd_{typ}", {"B": B, "F": F, "K": K, "impl": impl}, m, bst, bytes_=B * (F * K + P * K) * 4)
