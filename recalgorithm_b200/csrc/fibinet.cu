@@ -373,7 +373,7 @@ __device__ __forceinline__ float dot_vec(const float (&a)[K], const float (&b)[K
 
 __device__ __forceinline__ size_t rr_widx(int type, int i, int p) { return type == 0 ? 0 : type == 1 ? (size_t)i : (size_t)p; }
 
-// smem: pair table (rounds*slots ints) | xs (BS * F*K)
+// smem: pair table (P ints, natural order) | xs (BS * F*K)
 template <int K, int KT>
 __global__ void __launch_bounds__(256)
 bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int type, int B, int F, int BS,
@@ -382,9 +382,12 @@ bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
   extern __shared__ __align__(16) float smem[];
   const RRShape sh = rr_shape(F);
   const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
+  // the forward has no accumulation conflicts: the groups of a warp take ADJACENT pairs, so a warp writes 32/LP * 4K contiguous
+  // bytes of a sample's output row (the tournament order wrote 64-byte pieces 26 KB apart: 63 us = the DRAM rate of masked writes)
   int* tbl = reinterpret_cast<int*>(smem);
-  float* xs = smem + ((sh.rounds * sh.slots + 3) & ~3);
-  for (int t = threadIdx.x; t < sh.rounds * sh.slots; t += blockDim.x) tbl[t] = rr_pair(sh, t / sh.slots, t % sh.slots);
+  float* xs = smem + ((P + 3) & ~3);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int j = i + 1; j < n; ++j) tbl[pair_base(i, n) + (j - i - 1)] = (i << 16) | j;
   const int grp = threadIdx.x / LP, k0 = (threadIdx.x % LP) * KT, G = blockDim.x / LP;
   const int ntiles = (B + BS - 1) / BS;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -393,30 +396,27 @@ bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
     for (int t = threadIdx.x; t < bs * FK / 4; t += blockDim.x)
       reinterpret_cast<float4*>(xs)[t] = __ldg(reinterpret_cast<const float4*>(x + (size_t)b0 * FK) + t);
     __syncthreads();
-    for (int r = 0; r < sh.rounds; ++r) {
-      for (int slot = grp; slot < sh.slots; slot += G) {
-        const int ij = tbl[r * sh.slots + slot];
-        const int i = ij >> 16, j = ij & 0xffff;
-        const int p = pair_base(i, n) + (j - i - 1);
-        const float* wp = w + rr_widx(type, i, p) * K * K;
-        float wcol[KT][K];
+    for (int p = grp; p < P; p += G) {
+      const int ij = tbl[p];
+      const int i = ij >> 16, j = ij & 0xffff;
+      const float* wp = w + rr_widx(type, i, p) * K * K;
+      float wcol[KT][K];
 #pragma unroll
-        for (int c = 0; c < K; ++c) {
-          float t[KT];
-          ld_kt<KT, true>(t, wp + c * K + k0);
+      for (int c = 0; c < K; ++c) {
+        float t[KT];
+        ld_kt<KT, true>(t, wp + c * K + k0);
 #pragma unroll
-          for (int u = 0; u < KT; ++u) wcol[u][c] = t[u];
-        }
-        float* ob = out + ((size_t)b0 * P + p) * K + k0;
+        for (int u = 0; u < KT; ++u) wcol[u][c] = t[u];
+      }
+      float* ob = out + ((size_t)b0 * P + p) * K + k0;
 #pragma unroll 2
-        for (int s = 0; s < bs; ++s) {
-          float xi[K], xj[KT], o[KT];
-          load_vec<K>(xi, xs + s * FK + i * K);
-          ld_kt<KT>(xj, xs + s * FK + j * K + k0);
+      for (int s = 0; s < bs; ++s) {
+        float xi[K], xj[KT], o[KT];
+        load_vec<K>(xi, xs + s * FK + i * K);
+        ld_kt<KT>(xj, xs + s * FK + j * K + k0);
 #pragma unroll
-          for (int u = 0; u < KT; ++u) o[u] = dot_vec<K>(xi, wcol[u]) * xj[u];
-          st_kt<KT>(ob + (size_t)s * P * K, o);
-        }
+        for (int u = 0; u < KT; ++u) o[u] = dot_vec<K>(xi, wcol[u]) * xj[u];
+        st_kt<KT>(ob + (size_t)s * P * K, o);
       }
     }
   }
@@ -517,8 +517,8 @@ bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
-// grid (rounds, chunks).  smem: dv exchange (groups * 2 * K).  x is read through L2 (7.9 MB at config size, every round
-// reads it once), g streams from HBM exactly once.
+// grid (pair blocks, chunks).  smem: dv exchange (groups * 2 * K).  x is read through L2 (7.9 MB at config size), g streams
+// from HBM exactly once.
 template <int K, int KT>
 __global__ void __launch_bounds__(256)
 bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ g, int type, int B, int F,
@@ -526,20 +526,20 @@ bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__
   constexpr int LP = K / KT;
   constexpr int SUB = 8 / KT;                             // samples whose loads are issued together (even: the exchange buffers alternate)
   extern __shared__ __align__(16) float smem[];
-  const RRShape sh = rr_shape(F);
-  const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
-  const int r = blockIdx.x;
+  const int n = F - 1, P = n * (n - 1) / 2, FK = F * K;
   const int grp = threadIdx.x / LP, k0 = (threadIdx.x % LP) * KT, G = blockDim.x / LP;
   float* mydv = smem + grp * 2 * K;
   const int per = (B + gridDim.y - 1) / gridDim.y;
   const int b_lo = blockIdx.y * per, b_hi = min(B, b_lo + per);
-  const int nslot_it = (sh.slots + G - 1) / G;
-  for (int it = 0; it < nslot_it; ++it) {
-    const int slot = grp + it * G;
-    const bool act = slot < sh.slots;
-    const int ij = act ? rr_pair(sh, r, slot) : 1;
-    const int i = ij >> 16, j = ij & 0xffff;
-    const int p = pair_base(i, n) + (j - i - 1);
+  {
+    // no accumulation conflicts here either: the groups of a CTA take ADJACENT pairs (a warp reads 32/LP * 4K contiguous bytes
+    // of every sample's g row); idle groups of the last block shadow pair 0
+    const int pp = blockIdx.x * G + grp;
+    const bool act = pp < P;
+    const int p = act ? pp : 0;
+    int i = 0;
+    while (i + 1 < n - 1 && pair_base(i + 1, n) <= p) ++i;
+    const int j = i + 1 + (p - pair_base(i, n));
     float acc[KT][K];
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
@@ -879,13 +879,13 @@ extern "C" int ctr_bilinear_fwd(const float* x, const float* w, int64_t B, int64
   cudaStream_t st = as_stream(stream);
   if (rr_usable(K, type, x, w, out, nullptr)) {
     const RRShape sh = rr_shape((int)F);
-    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3);
+    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3);      // rounds * slots == P
     int bs = rr_tile((int)F, (int)K, 1, fixed, 64 * 1024);
     if (bs < 1) bs = rr_tile((int)F, (int)K, 1, fixed, 200 * 1024);
     if (bs >= 1) {
       const size_t smem_rr = fixed + sizeof(float) * bs * F * K;
       const int kt = rr_kt((int)K);
-      const int threads = rr_threads((int)F, (int)K, kt);
+      const int threads = 256;
       RR_DISPATCH(K, kt, bilinear_rr_fwd_kernel, {
         if (smem_rr > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
         int per_sm = 1;
@@ -955,14 +955,17 @@ extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_o
         kern<<<grid_for((B + bs - 1) / bs, per_sm < 1 ? 1 : per_sm), threads, smem_rr, st>>>(x, w, g_out, type, (int)B, (int)F, bs, dx);
       });
       CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dx)");
-      // weight gradient: one CTA per (round, batch chunk); ~4 CTAs per SM, at least 64 samples per chunk
-      int chunks = (4 * sm_count() + sh.rounds - 1) / sh.rounds;
-      const int max_chunks = (int)((B + 63) / 64);
+      // weight gradient: one CTA per (block of adjacent pairs, batch chunk); ~8 CTAs per SM (the loads are latency-bound: ncu
+      // long-scoreboard 12.6 per issue at 4), at least 32 samples per chunk
+      const int dw_threads = 256, dw_groups = dw_threads / lp;
+      const int pair_blocks = (int)((P + dw_groups - 1) / dw_groups);
+      int chunks = (8 * sm_count() + pair_blocks - 1) / pair_blocks;
+      const int max_chunks = (int)((B + 31) / 32);
       if (chunks > max_chunks) chunks = max_chunks;
       if (chunks < 1) chunks = 1;
-      const size_t smem_dw = sizeof(float) * (threads / lp) * 2 * K;
+      const size_t smem_dw = sizeof(float) * dw_groups * 2 * K;
       RR_DISPATCH(K, kt, bilinear_rr_bwd_dw_kernel, {
-        kern<<<dim3((unsigned)sh.rounds, (unsigned)chunks), threads, smem_dw, st>>>(x, g_out, type, (int)B, (int)F, dw);
+        kern<<<dim3((unsigned)pair_blocks, (unsigned)chunks), dw_threads, smem_dw, st>>>(x, g_out, type, (int)B, (int)F, dw);
       });
       CTR_CHECK_LAUNCH("ctr_bilinear_bwd(dw)");
       return CTR_OK;

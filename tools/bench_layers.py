@@ -130,7 +130,7 @@ def main():
             w = rn(*ops.bilinear_w_shape(F, K, typ), std=0.2)
             variants = [(4, "default (staged all/each, tournament interaction)"), (7, "tournament")]
             if args.sweep:
-                variants += [(7 | (kt << 10) | (tile << 4), f"tournament kt={kt} tile={tile}") for kt in (1, 2, 4) for tile in (8, 16)]
+                variants += [(7 | (kt << 10) | (tile << 4), f"tournament kt={kt} tile={tile}") for kt in (1, 2, 4) for tile in (4, 8, 16)]
             variants += [(8, "round-1 CTA-per-sample kernels")]
             for mask, impl in variants:
                 prev = ops.bilinear_set_tournament(mask)
