@@ -303,13 +303,10 @@ cross_bwd_reg_kernel(const float* __restrict__ x0, const float* __restrict__ w, 
   constexpr int NV = N * 4;
   extern __shared__ __align__(16) float smem[];
   float* sw = smem;                                  // (L, d)  weights
-  float* sb = sw + (size_t)L * d;                    // (L, d)  biases, then prefix biases cb_l in place at the end
-  float* rdw = sb + (size_t)L * d;                   // (L, d)  CTA accumulator of sum_q x0*a_l
-  float* rG = rdw + (size_t)L * d;                   // (d)     CTA accumulator of sum_q g_out
-  float* rT = rG + d;                                // (LM)    CTA accumulator of T_l
-  for (int i = threadIdx.x; i < L * d; i += blockDim.x) { sw[i] = __ldg(w + i); sb[i] = __ldg(b + i); rdw[i] = 0.f; }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) rG[i] = 0.f;
-  if (threadIdx.x < LM) rT[threadIdx.x] = 0.f;
+  float* sb = sw + (size_t)L * d;                    // (L, d)  biases
+  float* part = sb + (size_t)L * d;                  // (RW, (L+1)*d)  per-warp partial sums: sum_q x0*a_l (l < L) and sum_q g_out
+  float* partT = part + (size_t)RW * (L + 1) * d;    // (RW, LM)       per-warp T_l
+  for (int i = threadIdx.x; i < L * d; i += blockDim.x) { sw[i] = __ldg(w + i); sb[i] = __ldg(b + i); }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -405,50 +402,60 @@ cross_bwd_reg_kernel(const float* __restrict__ x0, const float* __restrict__ w, 
     }
     x.store(dx0 + (size_t)s * d, d, lane);
   }
-  // ---- CTA reduction of the lane-owned accumulators: the warps take turns adding into the shared arrays with plain
-  // 128-bit read-modify-writes (every lane owns distinct columns; shared-memory atomics would serialise on the SM's
-  // atomic unit: 64 warp-wide ATOMS per warp = ~17 us per CTA, measured as the floor of the B = 4096 case)
-  for (int wv = 0; wv < RW; ++wv) {
-    if ((threadIdx.x >> 5) == wv) {
+  // ---- CTA reduction of the lane-owned accumulators: every warp parks its partial sums in its own slice of shared memory
+  // (128-bit stores, no ordering between warps), one barrier, then thread-per-column sums over the RW slices.  (The first form
+  // let the warps take turns on ONE shared copy: RW serial read-modify-write rounds with a barrier each = ~8 us of the 19 us
+  // the B = 4096 case took; shared-memory atomics were worse still, ~17 us.)
+  {
+    float* mine = part + (size_t)(threadIdx.x >> 5) * (L + 1) * d;
 #pragma unroll
-      for (int kk = 0; kk < N; ++kk) {
-        const int i = (kk * 32 + lane) * 4;
-        if (i < d) {
-          float4* pg = reinterpret_cast<float4*>(rG + i);
-          float4 a = *pg;
-          a.x += acc_g[kk * 4 + 0]; a.y += acc_g[kk * 4 + 1]; a.z += acc_g[kk * 4 + 2]; a.w += acc_g[kk * 4 + 3];
-          *pg = a;
+    for (int kk = 0; kk < N; ++kk) {
+      const int i = (kk * 32 + lane) * 4;
+      if (i < d) {
+        *reinterpret_cast<float4*>(mine + (size_t)L * d + i) =
+            make_float4(acc_g[kk * 4 + 0], acc_g[kk * 4 + 1], acc_g[kk * 4 + 2], acc_g[kk * 4 + 3]);
 #pragma unroll
-          for (int l = 0; l < LM; ++l) {
-            if (l < L) {
-              float4* pw = reinterpret_cast<float4*>(rdw + (size_t)l * d + i);
-              float4 c = *pw;
-              c.x += acc_a[l][kk * 4 + 0]; c.y += acc_a[l][kk * 4 + 1]; c.z += acc_a[l][kk * 4 + 2]; c.w += acc_a[l][kk * 4 + 3];
-              *pw = c;
-            }
-          }
+        for (int l = 0; l < LM; ++l) {
+          if (l < L)
+            *reinterpret_cast<float4*>(mine + (size_t)l * d + i) =
+                make_float4(acc_a[l][kk * 4 + 0], acc_a[l][kk * 4 + 1], acc_a[l][kk * 4 + 2], acc_a[l][kk * 4 + 3]);
         }
       }
-      if (lane == 0) {
-#pragma unroll
-        for (int l = 0; l < LM; ++l)
-          if (l < L) rT[l] += T[l];                  // T is warp-uniform
-      }
     }
-    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int l = 0; l < LM; ++l) partT[(threadIdx.x >> 5) * LM + l] = T[l];     // T is warp-uniform
+    }
+  }
+  __syncthreads();
+  float Tl[LM];
+#pragma unroll
+  for (int l = 0; l < LM; ++l) {
+    Tl[l] = 0.f;
+    for (int wv = 0; wv < RW; ++wv) Tl[l] += partT[wv * LM + l];
   }
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    float G = 0.f, A[LM];
+#pragma unroll
+    for (int l = 0; l < LM; ++l) A[l] = 0.f;
+    for (int wv = 0; wv < RW; ++wv) {
+      const float* src = part + (size_t)wv * (L + 1) * d + i;
+      G += src[(size_t)L * d];
+#pragma unroll
+      for (int l = 0; l < LM; ++l)
+        if (l < L) A[l] += src[(size_t)l * d];
+    }
     float cb = 0.f, wsum = 0.f;                      // cb_l = sum_{k<l} b_k ; wsum = sum_{k>l} w_k*T_k built from the top
     float dbv[LM];
 #pragma unroll
     for (int l = LM - 1; l >= 0; --l) {
       dbv[l] = 0.f;
-      if (l < L) { dbv[l] = rG[i] + wsum; wsum += sw[(size_t)l * d + i] * rT[l]; }
+      if (l < L) { dbv[l] = G + wsum; wsum += sw[(size_t)l * d + i] * Tl[l]; }
     }
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
       if (l < L) {
-        atomicAdd(dw + (size_t)l * d + i, rdw[(size_t)l * d + i] + cb * rT[l]);
+        atomicAdd(dw + (size_t)l * d + i, A[l] + cb * Tl[l]);
         atomicAdd(db + (size_t)l * d + i, dbv[l]);
         cb += sb[(size_t)l * d + i];
       }
@@ -484,18 +491,18 @@ static int launch_cross_bwd(const float* x0, const float* xl_in, const float* w,
                             cudaStream_t st) {
   if constexpr (VEC == 4 && N <= 4) {                  // d <= 512: the lane-owned accumulators fit the register file
     if (xl_in == nullptr && L <= 4) {                  // the chain every reference model builds (DCN/dcn.py:157-160)
-      const size_t smem_r = sizeof(float) * ((size_t)3 * L * d + d + 8);
+      // 12 warps per CTA (168 registers each) once every warp has several samples: one sample of prefetch per warp is then
+      // ~46 KB in flight per SM; small batches keep 8 warps.  (N = 4, L = 4 would spill at 168 registers.)
+      const bool wide = B >= (int64_t)sm_count() * 12 * 4 && !(N == 4 && L > 3);
+      const int rw = wide ? 12 : 8;
+      const size_t smem_r = sizeof(float) * ((size_t)2 * L * d + (size_t)rw * ((L + 1) * d + 4));
       if (smem_r <= 200 * 1024) {
-        // 12 warps per CTA (168 registers each) once every warp has several samples: one sample of prefetch per warp is then
-        // ~46 KB in flight per SM; small batches keep 8 warps (the per-CTA merge takes one turn per warp)
-        const bool wide = B >= (int64_t)sm_count() * 12 * 4 && !(N == 4 && L > 3);   // (N = 4, L = 4 would spill at 168 registers)
-        auto pick = [&](auto rw) {
-          constexpr int RW = decltype(rw)::value;
+        auto pick = [&](auto tag) {
+          constexpr int RW = decltype(tag)::value;
           return L <= 1 ? cross_bwd_reg_kernel<N, 1, RW> : L == 2 ? cross_bwd_reg_kernel<N, 2, RW>
                : L == 3 ? cross_bwd_reg_kernel<N, 3, RW> : cross_bwd_reg_kernel<N, 4, RW>;
         };
         auto kr = wide ? pick(std::integral_constant<int, 12>{}) : pick(std::integral_constant<int, 8>{});
-        const int rw = wide ? 12 : 8;
         if (smem_r > 48 * 1024) CTR_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr, rw * 32, smem_r);
