@@ -711,12 +711,20 @@ bilinear_st_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
       const int j = t / K, k = t % K;
       float s0 = 0.f, s1 = 0.f;
       if (j < n) {
+        // pair (i,j) sits at pair_base(i) + j - i - 1 and pair_base(i+1) - pair_base(i) = n - i - 1: walk the column with a
+        // shrinking stride instead of re-deriving the index (the integer work was most of this loop's instructions)
+        const float* gp = gb + (j - 1) * K + k;
+        const float* vp = vw + k;
+        int stride = (n - 2) * K;
         int i = 0;
         for (; i + 1 < j; i += 2) {
-          s0 += gb[(pair_base(i, n) + j - i - 1) * K + k] * vw[i * K + k];
-          s1 += gb[(pair_base(i + 1, n) + j - i - 2) * K + k] * vw[(i + 1) * K + k];
+          s0 += gp[0] * vp[0];
+          s1 += gp[stride] * vp[K];
+          gp += 2 * stride - K;
+          stride -= 2 * K;
+          vp += 2 * K;
         }
-        if (i < j) s0 += gb[(pair_base(i, n) + j - i - 1) * K + k] * vw[i * K + k];
+        if (i < j) s0 += gp[0] * vp[0];
         const float* wj = ws + (TYPE == 0 ? 0 : j * K * K) + k * K;
 #pragma unroll
         for (int c = 0; c < K; c += 2) { s0 += dvw[j * K + c] * wj[c]; s1 += dvw[j * K + c + 1] * wj[c + 1]; }
