@@ -243,6 +243,15 @@ int ctr_cross_fwd(const float* x0, const float* xl_in, const float* w, const flo
  * dw, db (L,d) are overwritten (batch-reduced with fp32 atomics across CTAs). */
 int ctr_cross_bwd(const float* x0, const float* xl_in, const float* w, const float* b, const float* g_out,
                   int64_t B, int64_t d, int64_t L, float* dx0, float* dxl_in, float* dw, float* db, void* stream);
+/* Lookup FUSED with the cross stack: `net = fc.input_layer(features, cols)` (DCN/dcn.py:153) followed by the loop over
+ * cross_layer (DCN/dcn.py:157-160) for uniform-width embedding columns.  table / field_row_offset / ids as in
+ * ctr_embed_fm2_fwd (ids int64, or int32 when ids_are_int32 != 0; invalid ids give the zero vector); d = F*D.
+ * x0 (B, F*D) receives the gathered input (the backward needs it; the lookup backward of a plain gather is the view
+ * dx0 -> (B,F,D), no kernel), out (B, F*D) = x_L.  Needs D % 4 == 0, F*D <= 512, L <= 4 (CTR_ERR_UNSUPPORTED otherwise: call
+ * ctr_embed_fm2_fwd + ctr_cross_fwd). */
+int ctr_embed_cross_fwd(const float* table, const int64_t* field_row_offset, const void* ids, int ids_are_int32,
+                        int64_t B, int64_t F, int64_t D, const float* w, const float* b, int64_t L, float* x0, float* out,
+                        void* stream);
 
 /* ---- Row CIN: xDeepFM compressed-interaction layer -------------------------------------------------
  * Replaces cin_layer(x0, xk, hk_1, index) (xDeepFM/cin_layer.py:17-30):

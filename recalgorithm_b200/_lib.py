@@ -75,6 +75,7 @@ SIGNATURES = {
     "ctr_bag_lookup_bwd": (c_int, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
     "ctr_cross_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "ctr_cross_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ctr_embed_cross_fwd": (c_int, [_P, _P, _P, c_int, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
     "ctr_cin_fwd_workspace_bytes": (c_int64, [_I, _I, _I, _I, _I]),
     "ctr_cin_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, c_int, _P, _I, _P]),
     "ctr_cin_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),

@@ -170,6 +170,37 @@ def cross_stack(x0: torch.Tensor, w: torch.Tensor, b: torch.Tensor, xl: Optional
     return _CrossStack.apply(x0, xl, w, b)
 
 
+class _LookupCross(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, tables: EmbeddingTables, ids, w, b):
+        wc, bc = w.contiguous(), b.contiguous()
+        x0, out = ops.embed_cross_fwd(tables.weight, tables.field_row_offset, ids, wc, bc)
+        ctx.tables, ctx.ids = tables, (ids if ids.dtype == torch.int64 else ids.long())
+        ctx.save_for_backward(x0, wc, bc)
+        return out, x0
+
+    @staticmethod
+    def backward(ctx, g, g_x0=None):
+        x0, w, b = ctx.saved_tensors
+        dw = db = None
+        if g is not None:
+            dx0, _, dw, db = ops.cross_bwd(x0, w, b, g.contiguous())
+            if g_x0 is not None:                     # x0 also feeds the deep tower (DCN/dcn.py:163): both gradients reach the tables
+                dx0 = dx0 + g_x0
+        else:
+            dx0 = g_x0.contiguous()
+        B, F = ctx.ids.shape
+        # the lookup backward of a plain gather: the IndexedSlices values ARE dx0 viewed (B,F,D)
+        ctx.tables.grad_slices.append(IndexedSlices(dx0.view(B, F, -1), ctx.ids, ctx.tables.field_row_offset))
+        return None, None, None, dw, db
+
+
+def lookup_cross(tables: EmbeddingTables, ids: torch.Tensor, w: torch.Tensor, b: torch.Tensor):
+    """`net = input_layer(...)` + the cross loop (DCN/dcn.py:153-160) in one launch: (B,F) ids -> (x_L (B,F*D), x0 (B,F*D)).
+    x0 (the gathered input) is returned for the deep tower (`dcn.py:163`); gradients w.r.t. both outputs reach the tables."""
+    return _LookupCross.apply(tables._anchor, tables, ids, w, b)
+
+
 class _CIN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, xk, filt, want_pooled):

@@ -463,6 +463,118 @@ cross_bwd_reg_kernel(const float* __restrict__ x0, const float* __restrict__ w, 
   }
 }
 
+// Forward FUSED with the lookup (DCN/dcn.py:153-160: net = input_layer(...); x_{l+1} = cross_layer(x0, x_l, l)): the warp that owns a
+// sample gathers its F table rows straight into the registers that hold x0, writes x0 once (the backward needs it) and runs the
+// stack in the scalar-recurrence form of cross_bwd_reg_kernel -- x_l = x0 (1 + cs_l) + cb_l, so the L dot products u_l = x0 . w_l
+// are independent (one batched butterfly) and  out = x0 (1 + cs_L) + cb_L.  Shared memory holds w, cb_L and the L scalars
+// v_l = cb_l . w_l (computed once per CTA by warp 0); ~90 registers keep 2-3 CTAs per SM, which is what a 4096-sample batch
+// needs (the register-resident-parameter version ran 1 CTA/SM and was slower than two launches).
+// ids < 0 or >= the field's row count give the zero vector, exactly like ctr_embed_fm2_fwd.
+template <int N, int LM, typename IdT>
+__global__ void __launch_bounds__(CROSS_WARPS * 32)
+embed_cross_fwd_kernel(const float* __restrict__ table, const long long* __restrict__ off, const IdT* __restrict__ ids,
+                       const float* __restrict__ w, const float* __restrict__ b, int B, int F, int D, int L,
+                       float* __restrict__ x0_out, float* __restrict__ out) {
+  constexpr int NV = N * 4;
+  extern __shared__ __align__(16) float smem[];
+  const int d = F * D;
+  float* sw = smem;                          // (L, d)
+  float* scb = sw + (size_t)L * d;           // (d)   cb_L = sum_l b_l
+  float* svl = scb + d;                      // (LM)  v_l = cb_l . w_l
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < L * d; i += blockDim.x) sw[i] = __ldg(w + i);
+  if (threadIdx.x < 32) {                    // warp 0: prefix biases and the L scalars (reads w from global: no barrier needed)
+    float cb[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) cb[k] = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      if (l < L) {
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const int i = (k * 32 + lane) * 4;
+          if (i < d) {
+            const float4 tw = __ldg(reinterpret_cast<const float4*>(w + (size_t)l * d + i));
+            const float4 tb = __ldg(reinterpret_cast<const float4*>(b + (size_t)l * d + i));
+            dot += cb[k * 4 + 0] * tw.x + cb[k * 4 + 1] * tw.y + cb[k * 4 + 2] * tw.z + cb[k * 4 + 3] * tw.w;
+            cb[k * 4 + 0] += tb.x; cb[k * 4 + 1] += tb.y; cb[k * 4 + 2] += tb.z; cb[k * 4 + 3] += tb.w;
+          }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) svl[l] = dot;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int i = (k * 32 + lane) * 4;
+      if (i < d) *reinterpret_cast<float4*>(scb + i) = make_float4(cb[k * 4], cb[k * 4 + 1], cb[k * 4 + 2], cb[k * 4 + 3]);
+    }
+  }
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  int fk[N], part[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int i = (k * 32 + lane) * 4;
+    fk[k] = i < d ? i / D : -1;
+    part[k] = i < d ? i - fk[k] * D : 0;
+  }
+  auto gather = [&](int s, float (&a)[NV]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fk[k] >= 0) {
+        const long long id = (long long)__ldg(ids + (size_t)s * F + fk[k]);
+        const long long base = __ldg(off + fk[k]);
+        if (id >= 0 && id < __ldg(off + fk[k] + 1) - base)
+          t = __ldg(reinterpret_cast<const float4*>(table + (size_t)(base + id) * D + part[k]));
+      }
+      a[k * 4 + 0] = t.x; a[k * 4 + 1] = t.y; a[k * 4 + 2] = t.z; a[k * 4 + 3] = t.w;
+    }
+  };
+  float na[NV];
+  if (warp0 < B) gather(warp0, na);          // in flight while the parameters are staged
+  __syncthreads();
+  for (int s = warp0; s < B; s += nwarps) {
+    float a0[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a0[k] = na[k];
+    if (s + nwarps < B) gather(s + nwarps, na);
+    float red[LM];
+#pragma unroll
+    for (int l = 0; l < LM; ++l) {
+      red[l] = 0.f;
+      if (l < L) {
+        float wv[NV];
+        lane_load_smem<4, N>(wv, sw + (size_t)l * d, d, lane);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[l] += a0[k] * wv[k];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int l = 0; l < LM; ++l) red[l] += __shfl_xor_sync(0xffffffffu, red[l], o);
+    }
+    float cs = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM; ++l)
+      if (l < L) cs += (1.f + cs) * red[l] + svl[l];
+    const float scale = 1.f + cs;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int i = (k * 32 + lane) * 4;
+      if (i < d) {
+        const float4 cb = *reinterpret_cast<const float4*>(scb + i);
+        *reinterpret_cast<float4*>(x0_out + (size_t)s * d + i) = make_float4(a0[k * 4], a0[k * 4 + 1], a0[k * 4 + 2], a0[k * 4 + 3]);
+        *reinterpret_cast<float4*>(out + (size_t)s * d + i) =
+            make_float4(a0[k * 4] * scale + cb.x, a0[k * 4 + 1] * scale + cb.y, a0[k * 4 + 2] * scale + cb.z, a0[k * 4 + 3] * scale + cb.w);
+      }
+    }
+  }
+}
+
 static size_t cross_bwd_smem(int64_t d, int64_t L, bool has_xl, bool prefetch) {
   return sizeof(float) * ((size_t)3 * L * d + (size_t)(prefetch ? 2 : 1) * (has_xl ? 3 : 2) * CROSS_WARPS * d +
                           2 * CROSS_WARPS * CROSS_LMAX);     // sized for the larger layer bound
@@ -605,3 +717,46 @@ extern "C" int ctr_cross_bwd(const float* x0, const float* xl_in, const float* w
   CTR_CROSS_DISPATCH(BWD, x0, xl_in, w, b, g_out, B, d, L, dx0, dxl_in, dw, db, st)
 #undef BWD
 }
+
+template <int N, typename IdT>
+static int launch_embed_cross(const float* table, const int64_t* off, const IdT* ids, const float* w, const float* b, int64_t B,
+                              int64_t F, int64_t D, int64_t L, float* x0, float* out, cudaStream_t st) {
+  auto k = L <= 1 ? embed_cross_fwd_kernel<N, 1, IdT> : L == 2 ? embed_cross_fwd_kernel<N, 2, IdT>
+         : L == 3 ? embed_cross_fwd_kernel<N, 3, IdT> : embed_cross_fwd_kernel<N, 4, IdT>;
+  const size_t smem = sizeof(float) * ((size_t)L * F * D + F * D + 8);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, CROSS_WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)per_sm * sm_count();
+  const long long need = (B + CROSS_WARPS - 1) / CROSS_WARPS;
+  if (grid > need) grid = need;
+  k<<<(int)grid, CROSS_WARPS * 32, smem, st>>>(table, reinterpret_cast<const long long*>(off), ids, w, b, (int)B, (int)F, (int)D,
+                                             (int)L, x0, out);
+  CTR_CHECK_LAUNCH("ctr_embed_cross_fwd");
+  return CTR_OK;
+}
+
+extern "C" int ctr_embed_cross_fwd(const float* table, const int64_t* field_row_offset, const void* ids, int ids_are_int32,
+                                   int64_t B, int64_t F, int64_t D, const float* w, const float* b, int64_t L, float* x0,
+                                   float* out, void* stream) {
+  CTR_REQUIRE(B >= 0 && F >= 1 && D >= 1 && L >= 1, "ctr_embed_cross_fwd: bad sizes B=%lld F=%lld D=%lld L=%lld", (long long)B,
+              (long long)F, (long long)D, (long long)L);
+  CTR_REQUIRE(table && field_row_offset && ids && w && b && x0 && out, "ctr_embed_cross_fwd: null argument");
+  const int64_t d = F * D;
+  CTR_UNSUPPORTED((D & 3) != 0 || d > 512 || L > 4, "ctr_embed_cross_fwd: needs D %% 4 == 0, F*D <= 512, L <= 4 (D=%lld, d=%lld, "
+                  "L=%lld); use ctr_embed_fm2_fwd + ctr_cross_fwd", (long long)D, (long long)d, (long long)L);
+  CTR_REQUIRE(aligned16(table) && aligned16(w) && aligned16(b) && aligned16(x0) && aligned16(out),
+              "ctr_embed_cross_fwd: arrays must be 16-byte aligned");
+  CTR_REQUIRE(B < (1ll << 31), "ctr_embed_cross_fwd: batch too large");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = as_stream(stream);
+  const int n = (int)((d + 127) / 128);
+#define EC(NN)                                                                                                              \
+  return ids_are_int32 ? launch_embed_cross<NN, int>(table, field_row_offset, static_cast<const int*>(ids), w, b, B, F, D, L, x0, \
+                                                     out, st)                                                                \
+                       : launch_embed_cross<NN, long long>(table, field_row_offset, static_cast<const long long*>(ids), w, b, B, \
+                                                           F, D, L, x0, out, st);
+  if (n <= 1) { EC(1) } else if (n == 2) { EC(2) } else if (n == 3) { EC(3) } else { EC(4) }
+#undef EC
+}
+

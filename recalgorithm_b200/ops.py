@@ -232,6 +232,38 @@ def cross_fwd(x0: torch.Tensor, w: torch.Tensor, b: torch.Tensor, xl_in: Optiona
     return out
 
 
+def embed_cross_supported(F: int, D: int, L: int) -> bool:
+    """Shapes the fused lookup + cross forward covers (ctr_embed_cross_fwd): D % 4 == 0, F*D <= 512, L <= 4."""
+    return D % 4 == 0 and F * D <= 512 and 1 <= L <= 4
+
+
+def embed_cross_fwd(table: torch.Tensor, field_row_offset: torch.Tensor, ids: torch.Tensor, w: torch.Tensor, b: torch.Tensor,
+                    x0: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Lookup fused with the cross stack (DCN/dcn.py:153-160): ids (B,F) i64 | i32 -> (x0 (B,F*D), x_L (B,F*D)) in one launch.
+    Shapes outside embed_cross_supported() run the lookup kernel followed by the cross kernel (same results)."""
+    B, F = ids.shape
+    D = table.shape[1]
+    d, L = F * D, w.shape[0]
+    _chk(table, F32, "table"); _chk(field_row_offset, I64, "field_row_offset", (F + 1,))
+    _chk(w, F32, "w", (L, d)); _chk(b, F32, "b", (L, d))
+    if ids.dtype not in (I64, I32):
+        raise TypeError(f"ids must be int64 or int32, got {ids.dtype}")
+    _chk(ids, ids.dtype, "ids")
+    if x0 is None:
+        x0 = torch.empty((B, d), dtype=F32, device=table.device)
+    if out is None:
+        out = torch.empty((B, d), dtype=F32, device=table.device)
+    _chk(x0, F32, "x0", (B, d)); _chk(out, F32, "out", (B, d))
+    if not embed_cross_supported(F, D, L):
+        if ids.dtype == I32:
+            ids = ids.long()
+        embed_fm2_fwd(table, field_row_offset, ids, want_fm2=False, tile=x0.view(B, F, D))
+        return x0, cross_fwd(x0, w, b, out=out)
+    _lib.check(_lib.lib().ctr_embed_cross_fwd(_ptr(table), _ptr(field_row_offset), _ptr(ids), int(ids.dtype == I32), B, F, D,
+                                              _ptr(w), _ptr(b), L, _ptr(x0), _ptr(out), _stream()))
+    return x0, out
+
+
 def cross_bwd(x0, w, b, g_out, xl_in=None):
     """Returns (dx0, dxl_in | None, dw, db)."""
     B, d = x0.shape

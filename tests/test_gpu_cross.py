@@ -73,3 +73,73 @@ def test_cross_config2_properties():
     for l in range(L):
         x = x64 * (x @ w[l].double())[:, None] + b[l].double()[None, :] + x
     assert_close(o1, x, TOL, "config-2 forward vs float64 torch")
+
+
+@pytest.mark.parametrize("B,F,D,L,rows,i32", [(1, 1, 4, 1, 3, False), (9, 6, 8, 3, 11, False), (64, 30, 16, 3, 50, True),
+                                              (260, 8, 12, 4, 7, False), (37, 16, 32, 2, 5, True), (5, 3, 4, 4, 2, False)])
+def test_lookup_cross_fused_forward(B, F, D, L, rows, i32):
+    """ctr_embed_cross_fwd = input_layer gather + the cross loop (DCN/dcn.py:153-160) in one launch: x0 is the bit-exact gather
+    (OOV / out-of-range ids -> zero vector), x_L within 1e-5 of the float64 oracle."""
+    from recalgorithm_b200 import ops
+    rng = np.random.default_rng(B * 7 + F + D + L)
+    d = F * D
+    table = trunc_normal(rng, (rows * F, D), D ** -0.5)
+    ids = rng.integers(-1, rows + 1, (B, F))                       # -1 (OOV) and `rows` (out of range) included
+    lim = (6.0 / (d + 1)) ** 0.5
+    ws = rng.uniform(-lim, lim, (L, d)).astype(np.float32)
+    bs = rng.uniform(-lim, lim, (L, d)).astype(np.float32)
+    off = torch.arange(F + 1, device="cuda", dtype=torch.int64) * rows
+    ids_t = torch.from_numpy(ids).cuda()
+    if i32:
+        ids_t = ids_t.int()
+    x0, out = ops.embed_cross_fwd(dev(table), off, ids_t, dev(ws), dev(bs))
+    valid = (ids >= 0) & (ids < rows)
+    ex0 = np.where(valid[..., None], table[(np.arange(F)[None, :] * rows + np.clip(ids, 0, rows - 1))], 0.0).reshape(B, d)
+    assert np.array_equal(x0.cpu().numpy(), ex0.astype(np.float32))          # the gather is a copy: bit-exact
+    e = O.cross_stack_fwd(ex0.astype(np.float64), ws.astype(np.float64), bs.astype(np.float64))[-1]
+    assert_close(out, e, TOL, "fused lookup+cross fwd")
+    # and equal to the two-launch form within rounding of the reformulated recurrence
+    assert_close(out, ops.cross_fwd(x0, dev(ws), dev(bs)).double().cpu().numpy(), TOL, "fused vs two launches")
+
+
+def test_lookup_cross_unsupported_shapes_use_two_launches():
+    from recalgorithm_b200 import ops
+    rng = np.random.default_rng(5)
+    B, F, D, L, rows = 7, 40, 16, 5, 9                               # d = 640 > 512 and L = 5 > 4
+    assert not ops.embed_cross_supported(F, D, L)
+    table = trunc_normal(rng, (rows * F, D), 0.25)
+    ids = torch.from_numpy(rng.integers(0, rows, (B, F))).cuda()
+    ws, bs = trunc_normal(rng, (L, F * D), 0.05), trunc_normal(rng, (L, F * D), 0.05)
+    off = torch.arange(F + 1, device="cuda", dtype=torch.int64) * rows
+    x0, out = ops.embed_cross_fwd(dev(table), off, ids, dev(ws), dev(bs))
+    e = O.cross_stack_fwd(x0.double().cpu().numpy(), ws.astype(np.float64), bs.astype(np.float64))[-1]
+    assert_close(out, e, TOL, "fallback chain")
+
+
+def test_lookup_cross_autograd_matches_unfused_chain():
+    """autograd.lookup_cross (one launch forward; both outputs differentiable) == lookup + cross_stack, including the table
+    gradient when x0 also feeds a deep tower (DCN/dcn.py:163)."""
+    from recalgorithm_b200 import autograd
+    torch.manual_seed(3)
+    B, F, D, L, rows = 50, 30, 16, 3, 40
+    d = F * D
+    ids = torch.randint(-1, rows, (B, F), device="cuda")
+    w0 = torch.randn((L, d), device="cuda") * 0.05
+    b0 = torch.randn((L, d), device="cuda") * 0.05
+    deep = torch.randn((d, 1), device="cuda") * 0.1
+    gy = torch.randn((B, d), device="cuda")
+    res = []
+    for fused in (True, False):
+        tables = autograd.EmbeddingTables([rows] * F, D, device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
+        w, b = w0.clone().requires_grad_(), b0.clone().requires_grad_()
+        if fused:
+            xl, x0 = autograd.lookup_cross(tables, ids, w, b)
+        else:
+            x0 = autograd.lookup(tables, ids).reshape(B, d)
+            xl = autograd.cross_stack(x0, w, b)
+        loss = (xl * gy).sum() + (x0 @ deep).sum()
+        loss.backward()
+        dense = sum(s.to_dense(tables.num_rows) for s in tables.grad_slices)
+        res.append((xl.detach(), w.grad, b.grad, dense))
+    for a, e, name in zip(res[0], res[1], ("x_L", "dw", "db", "table grad")):
+        assert_close(a, e.double().cpu().numpy(), TOL, name)

@@ -45,18 +45,17 @@ def build_dcn_cfg2(rows=1_000_000, B=4096):
     w, bb, g = _rn(gen, L, d, std=0.05), _rn(gen, L, d, std=0.05), _rn(gen, B, d)
     k = [0]
 
+    x0, xl = torch.empty((B, d), device="cuda"), torch.empty((B, d), device="cuda")
+
     def step(ev=None):
         k[0] += 1
         _rec(ev, 0)
-        tile, _ = ops.embed_fm2_fwd(table, off, ids[k[0] % 4], want_fm2=False)
-        x0 = tile.view(B, d)
+        ops.embed_cross_fwd(table, off, ids[k[0] % 4], w, bb, x0=x0, out=xl)     # input_layer gather + the cross loop, ONE launch
         _rec(ev, 1)
-        ops.cross_fwd(x0, w, bb)
-        _rec(ev, 2)
         dx0, _, _, _ = ops.cross_bwd(x0, w, bb, g)
-        _rec(ev, 3)
+        _rec(ev, 2)
         # lookup backward of a plain gather (no FM2 term): the IndexedSlices values ARE dx0.view(B,F,D) -- no kernel, no bytes
-        _rec(ev, 4)
+        _rec(ev, 3)
 
     bytes_step = B * (F * (8 + 2 * D * 4) + 20 * d)                      # lookup fwd + cross fwd/bwd (20*d); lookup bwd is an alias
 
@@ -67,9 +66,9 @@ def build_dcn_cfg2(rows=1_000_000, B=4096):
                 "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": B * 3 * d * 4,
                 "avg_launch_ms": ms["cross_bwd"], "step_algorithmic_GBps": step_gbs, "step_frac": step_gbs / peaks["hbm_gbs"],
                 "step_bytes_per_sample": bytes_step // B,
-                "note": "79 MB per step fits the 126 MB L2 and 4 launches of ~10 us each: launch/latency-bound, see DESIGN 4.3"}
+                "note": "79 MB per step fits the 126 MB L2; two kernel launches (fused lookup+cross forward, cross backward) + 2 memsets: launch/latency-bound, see DESIGN 4.3"}
 
-    return {"step": step, "marks": ["lookup_fwd", "cross_fwd", "cross_bwd", "lookup_bwd"], "B": B, "roofline": roofline,
+    return {"step": step, "marks": ["lookup+cross_fwd", "cross_bwd", "lookup_bwd"], "B": B, "roofline": roofline,
             "config": {"workload": "dcn_cfg2", "model": "DCN lookup + 3 cross layers", "B": B, "F": F, "D": D, "d": d, "L": L,
                        "rows_per_field": rows, "ids": "uniform int64"}, "dtype": "f32"}
 
