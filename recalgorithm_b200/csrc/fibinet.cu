@@ -549,27 +549,30 @@ bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__
     const float* xi_p = x + (size_t)i * K + k0;
     const float* xj_p = x + (size_t)j * K + k0;
     const float* g_p = g + (size_t)p * K + k0;
-    for (int s0 = b_lo; s0 < b_hi; s0 += SUB) {
-      float xi[SUB][KT], dvl[SUB][KT];
+    // software pipeline: the loads of batch n+1 are issued before batch n is multiplied (first form: 81 % of the stall samples sat
+    // on the first use of the loaded g / x_j values -- every batch waited a full DRAM latency, profiles/r2_bilinear_tournament_ncu_full)
+    auto load = [&](int s0, float (&xi)[SUB][KT], float (&xj)[SUB][KT], float (&gv)[SUB][KT]) {
 #pragma unroll
       for (int u = 0; u < SUB; ++u) {
         const int b = s0 + u;
         if (b < b_hi) {
-          float xj[KT], gv[KT];
           ld_kt<KT, true>(xi[u], xi_p + (size_t)b * FK);
-          ld_kt<KT, true>(xj, xj_p + (size_t)b * FK);
-          ld_kt<KT, true>(gv, g_p + (size_t)b * P * K);
-#pragma unroll
-          for (int t = 0; t < KT; ++t) dvl[u][t] = gv[t] * xj[t];
+          ld_kt<KT, true>(xj[u], xj_p + (size_t)b * FK);
+          ld_kt<KT, true>(gv[u], g_p + (size_t)b * P * K);
         } else {
 #pragma unroll
-          for (int t = 0; t < KT; ++t) { xi[u][t] = 0.f; dvl[u][t] = 0.f; }
+          for (int t = 0; t < KT; ++t) { xi[u][t] = 0.f; xj[u][t] = 0.f; gv[u][t] = 0.f; }
         }
       }
+    };
+    auto mult = [&](const float (&xi)[SUB][KT], const float (&xj)[SUB][KT], const float (&gv)[SUB][KT]) {
 #pragma unroll
       for (int u = 0; u < SUB; ++u) {
+        float dvl[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) dvl[t] = gv[u][t] * xj[u][t];
         float* buf = mydv + (u & 1) * K;
-        st_kt<KT>(buf + k0, dvl[u]);
+        st_kt<KT>(buf + k0, dvl);
         __syncwarp();
         float dv[K];
         load_vec<K>(dv, buf);
@@ -579,6 +582,14 @@ bilinear_rr_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__
           for (int k = 0; k < K; ++k) acc[t][k] += xi[u][t] * dv[k];
         }
       }
+    };
+    float xa[SUB][KT], ja[SUB][KT], ga[SUB][KT], xb[SUB][KT], jb[SUB][KT], gb[SUB][KT];
+    load(b_lo, xa, ja, ga);
+    for (int s0 = b_lo; s0 < b_hi; s0 += 2 * SUB) {          // trip count is uniform over the CTA
+      load(s0 + SUB, xb, jb, gb);
+      mult(xa, ja, ga);
+      load(s0 + 2 * SUB, xa, ja, ga);
+      mult(xb, jb, gb);
     }
     if (act) {
       float* dst = dw + rr_widx(type, i, p) * K * K + (size_t)k0 * K;
