@@ -396,18 +396,24 @@ bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
     for (int t = threadIdx.x; t < bs * FK / 4; t += blockDim.x)
       reinterpret_cast<float4*>(xs)[t] = __ldg(reinterpret_cast<const float4*>(x + (size_t)b0 * FK) + t);
     __syncthreads();
-    for (int p = grp; p < P; p += G) {
+    // the weight columns of the group's NEXT pair are requested before the current pair is multiplied (first form: a third of the
+    // stall samples sat on the first FMA after the weight loads)
+    auto loadw = [&](int p, float (&wc)[KT][K]) {
+      if (p < P) {
+        const int ij = tbl[p];
+        const float* wp = w + rr_widx(type, ij >> 16, p) * K * K;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          float t[KT];
+          ld_kt<KT, true>(t, wp + c * K + k0);
+#pragma unroll
+          for (int u = 0; u < KT; ++u) wc[u][c] = t[u];
+        }
+      }
+    };
+    auto run = [&](int p, const float (&wc)[KT][K]) {
       const int ij = tbl[p];
       const int i = ij >> 16, j = ij & 0xffff;
-      const float* wp = w + rr_widx(type, i, p) * K * K;
-      float wcol[KT][K];
-#pragma unroll
-      for (int c = 0; c < K; ++c) {
-        float t[KT];
-        ld_kt<KT, true>(t, wp + c * K + k0);
-#pragma unroll
-        for (int u = 0; u < KT; ++u) wcol[u][c] = t[u];
-      }
       float* ob = out + ((size_t)b0 * P + p) * K + k0;
 #pragma unroll 2
       for (int s = 0; s < bs; ++s) {
@@ -415,20 +421,37 @@ bilinear_rr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
         load_vec<K>(xi, xs + s * FK + i * K);
         ld_kt<KT>(xj, xs + s * FK + j * K + k0);
 #pragma unroll
-        for (int u = 0; u < KT; ++u) o[u] = dot_vec<K>(xi, wcol[u]) * xj[u];
+        for (int u = 0; u < KT; ++u) o[u] = dot_vec<K>(xi, wc[u]) * xj[u];
         st_kt<KT>(ob + (size_t)s * P * K, o);
+      }
+    };
+    float wa[KT][K], wb[KT][K];
+    loadw(grp, wa);
+    for (int p = grp; p < P; p += 2 * G) {
+      loadw(p + G, wb);
+      run(p, wa);
+      if (p + G < P) {
+        loadw(p + 2 * G, wa);
+        run(p + G, wb);
       }
     }
   }
 }
 
-// smem: pair table | xs (BS*FK) | dxs (BS*FK) | dv exchange (groups * 2 * K)
+constexpr int RR_GP = 8;              // samples per tile of the dX kernel (their g values are prefetched into registers)
+
+// smem: pair table | xs (BS*FK) | dxs (BS*FK) | dv exchange (groups * RR_GP * K).   BS <= RR_GP.
+// A "step" is one (round, slot pass): every group holds one pair.  Each step runs two passes over the tile's samples:
+//   pass A (needs the weight's columns + g):  dv = g*x_j -> exchange buffer ;  dx_j += g * (x_i . W[:,k])
+//   pass B (needs the weight's rows):         dx_i += dv . W[c,:]
+// so the global loads can be issued a pass ahead INTO THE SAME REGISTERS: the rows are requested before pass A, the NEXT step's
+// columns and g values before pass B (first form: ncu attributed 17 % of the stall samples to the first use of g and ~18 % to the
+// weight loads at the top of every step).
 template <int K, int KT>
 __global__ void __launch_bounds__(256)
 bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g, int type,
                           int B, int F, int BS, float* __restrict__ dx) {
   constexpr int LP = K / KT;
-  constexpr int SUB = KT >= 4 ? 2 : 4;                  // samples whose g loads are issued together
   extern __shared__ __align__(16) float smem[];
   const RRShape sh = rr_shape(F);
   const int n = sh.n, P = n * (n - 1) / 2, FK = F * K;
@@ -438,8 +461,20 @@ bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__
   float* dvb = dxs + (size_t)BS * FK;
   for (int t = threadIdx.x; t < sh.rounds * sh.slots; t += blockDim.x) tbl[t] = rr_pair(sh, t / sh.slots, t % sh.slots);
   const int grp = threadIdx.x / LP, k0 = (threadIdx.x % LP) * KT, G = blockDim.x / LP;
-  float* mydv = dvb + grp * 2 * K;
+  float* mydv = dvb + (size_t)grp * RR_GP * K;
   const int nslot_it = (sh.slots + G - 1) / G;          // same trip count for every group: the warp stays converged for __syncwarp
+  const int NS = sh.rounds * nslot_it;
+  auto pair_of = [&](int st, int& i, int& j, int& p, size_t& wi) -> bool {
+    const int r = st / nslot_it, slot = grp + (st % nslot_it) * G;
+    const bool act = slot < sh.slots;
+    const int ij = act ? tbl[r * sh.slots + slot] : 1;
+    i = ij >> 16; j = ij & 0xffff;
+    p = pair_base(i, n) + (j - i - 1);
+    wi = rr_widx(type, i, p);
+    // idle groups load the weight / g of pair 0 but read the shared tiles at field F-1, which no pair ever writes (no stores at all)
+    if (!act) i = j = F - 1;
+    return act;
+  };
   const int ntiles = (B + BS - 1) / BS;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b0 = tile * BS, bs = min(BS, B - b0);
@@ -449,22 +484,36 @@ bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__
       reinterpret_cast<float4*>(dxs)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    for (int r = 0; r < sh.rounds; ++r) {
-      for (int it = 0; it < nslot_it; ++it) {
-        const int slot = grp + it * G;
-        const bool act = slot < sh.slots;
-        const int ij = act ? tbl[r * sh.slots + slot] : 1;     // idle groups shadow pair (0,1): loads only, no stores
-        const int i = ij >> 16, j = ij & 0xffff;
-        const int p = pair_base(i, n) + (j - i - 1);
-        const float* wp = w + rr_widx(type, i, p) * K * K;
-        float wcol[KT][K], wrow[KT][K];
+    float wcol[KT][K], wrow[KT][K], gq[RR_GP][KT];
+    auto ld_cols_and_g = [&](int st) {
+      int i, j, p;
+      size_t wi;
+      pair_of(st, i, j, p, wi);
+      const float* wp = w + wi * K * K;
 #pragma unroll
-        for (int c = 0; c < K; ++c) {
-          float t[KT];
-          ld_kt<KT, true>(t, wp + c * K + k0);
+      for (int c = 0; c < K; ++c) {
+        float t[KT];
+        ld_kt<KT, true>(t, wp + c * K + k0);
 #pragma unroll
-          for (int u = 0; u < KT; ++u) wcol[u][c] = t[u];
+        for (int u = 0; u < KT; ++u) wcol[u][c] = t[u];
+      }
+      const float* gb = g + ((size_t)b0 * P + p) * K + k0;
+#pragma unroll
+      for (int s = 0; s < RR_GP; ++s) {
+        if (s < bs) ld_kt<KT, true>(gq[s], gb + (size_t)s * P * K);
+        else {
+#pragma unroll
+          for (int t = 0; t < KT; ++t) gq[s][t] = 0.f;
         }
+      }
+    };
+    ld_cols_and_g(0);
+    for (int st = 0; st < NS; ++st) {
+      int i, j, p;
+      size_t wi;
+      const bool act = pair_of(st, i, j, p, wi);
+      {
+        const float* wp = w + wi * K * K;
 #pragma unroll
         for (int u = 0; u < KT; ++u) {
 #pragma unroll
@@ -473,44 +522,38 @@ bilinear_rr_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__
             wrow[u][4 * q] = t.x; wrow[u][4 * q + 1] = t.y; wrow[u][4 * q + 2] = t.z; wrow[u][4 * q + 3] = t.w;
           }
         }
-        const float* gb = g + ((size_t)b0 * P + p) * K + k0;
-        for (int s0 = 0; s0 < bs; s0 += SUB) {
-          float gv[SUB][KT];
+      }
+      __syncwarp();                                            // the previous step's pass B is done with the exchange buffer
 #pragma unroll
-          for (int u = 0; u < SUB; ++u) {
-            if (s0 + u < bs) ld_kt<KT, true>(gv[u], gb + (size_t)(s0 + u) * P * K);
-            else {
+      for (int s = 0; s < RR_GP; ++s) {                        // ---- pass A  (bs is uniform over the CTA)
+        if (s < bs) {
+          float xi[K], xj[KT], dvl[KT], dj[KT];
+          load_vec<K>(xi, xs + s * FK + i * K);
+          ld_kt<KT>(xj, xs + s * FK + j * K + k0);
+          ld_kt<KT>(dj, dxs + s * FK + j * K + k0);
 #pragma unroll
-              for (int t = 0; t < KT; ++t) gv[u][t] = 0.f;
-            }
+          for (int t = 0; t < KT; ++t) {
+            dvl[t] = gq[s][t] * xj[t];
+            dj[t] += gq[s][t] * dot_vec<K>(xi, wcol[t]);
           }
-#pragma unroll
-          for (int u = 0; u < SUB; ++u) {
-            const int s = s0 + u;
-            if (s < bs) {                                      // bs is uniform over the CTA
-              float xi[K], dv[K], xj[KT], dvl[KT], dj[KT], di[KT];
-              load_vec<K>(xi, xs + s * FK + i * K);
-              ld_kt<KT>(xj, xs + s * FK + j * K + k0);
-              ld_kt<KT>(dj, dxs + s * FK + j * K + k0);
-#pragma unroll
-              for (int t = 0; t < KT; ++t) {
-                dvl[t] = gv[u][t] * xj[t];
-                dj[t] += gv[u][t] * dot_vec<K>(xi, wcol[t]);
-              }
-              float* buf = mydv + (u & 1) * K;
-              st_kt<KT>(buf + k0, dvl);
-              if (act) st_kt<KT>(dxs + s * FK + j * K + k0, dj);
-              __syncwarp();
-              load_vec<K>(dv, buf);
-              ld_kt<KT>(di, dxs + s * FK + i * K + k0);
-#pragma unroll
-              for (int t = 0; t < KT; ++t) di[t] += dot_vec<K>(dv, wrow[t]);
-              if (act) st_kt<KT>(dxs + s * FK + i * K + k0, di);
-            }
-          }
+          st_kt<KT>(mydv + s * K + k0, dvl);
+          if (act) st_kt<KT>(dxs + s * FK + j * K + k0, dj);
         }
       }
-      __syncthreads();                                         // next round: the same fields belong to other groups
+      __syncwarp();
+      if (st + 1 < NS) ld_cols_and_g(st + 1);                  // into the registers pass A just finished with
+#pragma unroll
+      for (int s = 0; s < RR_GP; ++s) {                        // ---- pass B
+        if (s < bs) {
+          float dv[K], di[KT];
+          load_vec<K>(dv, mydv + s * K);
+          ld_kt<KT>(di, dxs + s * FK + i * K + k0);
+#pragma unroll
+          for (int t = 0; t < KT; ++t) di[t] += dot_vec<K>(dv, wrow[t]);
+          if (act) st_kt<KT>(dxs + s * FK + i * K + k0, di);
+        }
+      }
+      if ((st + 1) % nslot_it == 0) __syncthreads();           // next round: the same fields belong to other groups
     }
     for (int t = threadIdx.x; t < bs * FK / 4; t += blockDim.x)
       reinterpret_cast<float4*>(dx + (size_t)b0 * FK)[t] = reinterpret_cast<const float4*>(dxs)[t];
@@ -962,9 +1005,10 @@ extern "C" int ctr_bilinear_bwd(const float* x, const float* w, const float* g_o
     const int kt = rr_kt((int)K);
     const int lp = (int)K / kt;
     const int threads = rr_threads((int)F, (int)K, kt);
-    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3) + sizeof(float) * (threads / lp) * 2 * K;
+    const size_t fixed = sizeof(int) * ((sh.rounds * sh.slots + 3) & ~3) + sizeof(float) * (threads / lp) * RR_GP * K;
     int bs = rr_tile((int)F, (int)K, 2, fixed, 72 * 1024);
     if (bs < 1) bs = rr_tile((int)F, (int)K, 2, fixed, 200 * 1024);
+    if (bs > RR_GP) bs = RR_GP;                                  // the dX kernel keeps the tile's g values in registers
     if (bs >= 1) {
       const size_t smem_rr = fixed + sizeof(float) * 2 * bs * F * K;
       RR_DISPATCH(K, kt, bilinear_rr_bwd_dx_kernel, {
