@@ -34,11 +34,13 @@ def make_example_parser(feature_columns, label_keys: Sequence[str] = ("read_comm
     return example_parser
 
 
-def _load(filepath: Union[str, Sequence[str]]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def _load(filepath: Union[str, Sequence[str]], mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """mmap=True maps the file(s) instead of reading them into RAM (a single file stays mapped; several files are concatenated,
+    which materialises them)."""
     paths = [filepath] if isinstance(filepath, str) else list(filepath)
     bufs, offs, lens, base = [], [], [], 0
     for p in paths:                                           # TFRecordDataset([files]) reads them one after the other
-        b, o, l = native.read_tfrecord_file(p)
+        b, o, l = native.read_tfrecord_file(p, mmap=mmap)
         bufs.append(b); offs.append(o + np.uint64(base)); lens.append(l)
         base += b.size
     return (bufs[0] if len(bufs) == 1 else np.concatenate(bufs)), np.concatenate(offs), np.concatenate(lens)
@@ -119,10 +121,10 @@ def _batches(order_epochs: Iterator[np.ndarray], data, batch_size: int, parser) 
 
 
 def train_input_fn(filepath, example_parser, batch_size: int, num_epochs: Optional[int], shuffle_buffer_size: int,
-                   seed: Optional[int] = None) -> Iterator[Tuple[dict, dict]]:
+                   seed: Optional[int] = None, mmap: bool = False) -> Iterator[Tuple[dict, dict]]:
     """utils.py:4-26.  Iterating the result is `dataset.make_one_shot_iterator()`; each epoch is reshuffled
-    (tf.data's reshuffle_each_iteration default)."""
-    data = _load(filepath)
+    (tf.data's reshuffle_each_iteration default).  mmap=True maps the TFRecord file instead of reading it into RAM."""
+    data = _load(filepath, mmap=mmap)
     n = int(data[1].size)
     rng = np.random.default_rng(seed)
     import itertools
@@ -133,9 +135,9 @@ def train_input_fn(filepath, example_parser, batch_size: int, num_epochs: Option
     return _prefetch(_batches(epochs, data, batch_size, example_parser), depth=1)
 
 
-def eval_input_fn(filepath, example_parser, batch_size: int) -> Iterator[Tuple[dict, dict]]:
+def eval_input_fn(filepath, example_parser, batch_size: int, mmap: bool = False) -> Iterator[Tuple[dict, dict]]:
     """utils.py:29-47: one pass, file order, no shuffle."""
-    data = _load(filepath)
+    data = _load(filepath, mmap=mmap)
     return _prefetch(_batches(iter([np.arange(int(data[1].size), dtype=np.int64)]), data, batch_size, example_parser), depth=1)
 
 

@@ -88,3 +88,13 @@ def test_num_epochs_none_repeats_forever(dataset):
     taken = list(itertools.islice(it, 5))                  # five full passes, no StopIteration
     it.close()
     assert len(taken) == 5
+
+
+def test_mmap_reads_the_same_batches(dataset):
+    """mmap=True maps the TFRecord file instead of reading it into RAM: same records, same order."""
+    p, n, parser = dataset
+    a = list(I.eval_input_fn(p, parser, batch_size=16))
+    b = list(I.eval_input_fn(p, parser, batch_size=16, mmap=True))
+    assert _ids(a).tolist() == _ids(b).tolist() == list(range(n))
+    t = list(I.train_input_fn(p, parser, batch_size=50, num_epochs=1, shuffle_buffer_size=0, mmap=True))
+    assert _ids(t).tolist() == list(range(n))
