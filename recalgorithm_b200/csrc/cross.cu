@@ -622,8 +622,12 @@ static int launch_cross_bwd(const float* x0, const float* xl_in, const float* w,
         long long grid = (long long)per_sm * sm_count();
         const long long need = (B + rw - 1) / rw;
         if (grid > need) grid = need;
-        CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * L * d, st));
-        CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * L * d, st));
+        if (db == dw + L * d) {                          // the host API allocates dw | db back to back: one memset node
+          CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 2 * L * d, st));
+        } else {
+          CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * L * d, st));
+          CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * L * d, st));
+        }
         kr<<<(int)grid, rw * 32, smem_r, st>>>(x0, w, b, g, (int)B, (int)d, (int)L, dx0, dw, db);
         CTR_CHECK_LAUNCH("ctr_cross_bwd");
         return CTR_OK;

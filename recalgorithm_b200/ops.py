@@ -272,8 +272,8 @@ def cross_bwd(x0, w, b, g_out, xl_in=None):
     _chk(g_out, F32, "g_out", (B, d)); _chk(xl_in, F32, "xl_in", (B, d))
     dx0 = torch.empty_like(x0)
     dxl = torch.empty_like(x0) if xl_in is not None else None
-    dw = torch.empty_like(w)
-    db = torch.empty_like(b)
+    dwb = torch.empty((2,) + tuple(w.shape), dtype=F32, device=w.device)     # dw | db back to back: zeroed by one memset
+    dw, db = dwb[0], dwb[1]
     _lib.check(_lib.lib().ctr_cross_bwd(_ptr(x0), _ptr(xl_in), _ptr(w), _ptr(b), _ptr(g_out), B, d, L,
                                         _ptr(dx0), _ptr(dxl), _ptr(dw), _ptr(db), _stream()))
     return dx0, dxl, dw, db
