@@ -721,6 +721,7 @@ def run_deepfm(args, cfg, dd: Dist):
                         "dense(1) deep head in one kernel, queue plan beside it) -> sigmoid-CE (ctr_sigmoid_ce) -> backward (ctr_embed_fm2_lin_bwd_push: "
                         "gradient rows into the owners' queues + d_w) -> NCCL all-reduce of the replicated head's d_w -> loss D2H, read one step later"},
         "vocab_100m": v100, "replicas": rep, "gpu_launches": int(launches), "clocks": clocks,
+        "comm_nranks": int(dd.dist.get_world_size()), "comm_backend": "nccl (handles, barriers, 1-element alignment all-reduce; no data-plane collective)",
     }
     print(json.dumps(line), flush=True)
 
