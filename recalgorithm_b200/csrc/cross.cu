@@ -603,9 +603,10 @@ static int launch_cross_bwd(const float* x0, const float* xl_in, const float* w,
                             cudaStream_t st) {
   if constexpr (VEC == 4 && N <= 4) {                  // d <= 512: the lane-owned accumulators fit the register file
     if (xl_in == nullptr && L <= 4) {                  // the chain every reference model builds (DCN/dcn.py:157-160)
-      // 12 warps per CTA (168 registers each) once every warp has several samples: one sample of prefetch per warp is then
-      // ~46 KB in flight per SM; small batches keep 8 warps.  (N = 4, L = 4 would spill at 168 registers.)
-      const bool wide = B >= (int64_t)sm_count() * 12 * 4 && !(N == 4 && L > 3);
+      // 12 warps per CTA (168 registers each) once all of them have work (two samples each): one sample of prefetch per warp is
+      // then ~46 KB in flight per SM, and a 4096-sample batch is 2.3 instead of 3.5 dependent samples per warp.  (N = 4, L = 4
+      // would spill at 168 registers.)
+      const bool wide = B >= (int64_t)sm_count() * 12 * 2 && !(N == 4 && L > 3);
       const int rw = wide ? 12 : 8;
       const size_t smem_r = sizeof(float) * ((size_t)2 * L * d + (size_t)rw * ((L + 1) * d + 4));
       if (smem_r <= 200 * 1024) {
