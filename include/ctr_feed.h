@@ -40,6 +40,11 @@ uint32_t ctr_feed_masked_crc32c(const uint8_t* data, uint64_t n);
  * *consumed (nullable) = bytes of complete records read. */
 int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, uint64_t* offsets, uint64_t* lengths,
                                 int64_t max_records, uint64_t* consumed);
+/* verify_crc: 0 = none, 1 = length and payload CRCs inside the (sequential) scan, 2 = length CRCs only -- the scan needs those
+ * to trust the lengths; the payload CRCs are then checked by ctr_feed_tfrecord_verify on `num_threads` threads (0 = all cores):
+ * CTR_FEED_OK, or CTR_FEED_ERR_CRC naming the first corrupted record. */
+int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* offsets, const uint64_t* lengths, int64_t count,
+                             int num_threads);
 
 /* Vocabulary: token i = blob[offsets[i], offsets[i+1]); id = index of the FIRST occurrence of a token. */
 void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens);

@@ -339,14 +339,37 @@ int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, 
     const uint8_t* data = buf + pos + 12;
     uint32_t data_crc;
     memcpy(&data_crc, data + len, 4);
-    if (verify_crc && masked(crc32c(data, len)) != data_crc)
-      return fail(CTR_FEED_ERR_CRC, "corrupted record data at byte %llu (crc mismatch)", (unsigned long long)pos);
+    if (verify_crc == 1 && masked(crc32c(data, len)) != data_crc)          // verify_crc == 2: length CRCs only (the scan needs them to
+      return fail(CTR_FEED_ERR_CRC, "corrupted record data at byte %llu (crc mismatch)", (unsigned long long)pos);   // trust `len`);
+                                                                               // the payload CRCs go to ctr_feed_tfrecord_verify
     if (max_records > 0) { offsets[count] = pos + 12; lengths[count] = len; }
     ++count;
     pos += 12 + len + 4;
   }
   if (consumed) *consumed = pos;
   return count;
+}
+
+int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* offsets, const uint64_t* lengths, int64_t count,
+                             int num_threads) {
+  if (count < 0 || (count > 0 && (!buf || !offsets || !lengths)))
+    return fail(CTR_FEED_ERR_ARG, "ctr_feed_tfrecord_verify: bad arguments");
+  if (count == 0) return CTR_FEED_OK;
+  int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min({nt, 64, (int)std::max<int64_t>(1, count / 256)}));
+  // every chunk stops at ITS first bad record; run_chunks reports the chunk with the lowest index first = the first bad record
+  return run_chunks(count, nt, [&](int, int64_t b0, int64_t b1) -> int {
+    for (int64_t b = b0; b < b1; ++b) {
+      const uint64_t off = offsets[b], len = lengths[b];
+      if (off < 12 || off > n || len > n - off || n - off - len < 4)
+        return fail(CTR_FEED_ERR_ARG, "ctr_feed_tfrecord_verify: record %lld lies outside the buffer", (long long)b);
+      uint32_t data_crc;
+      memcpy(&data_crc, buf + off + len, 4);
+      if (masked(crc32c(buf + off, len)) != data_crc)
+        return fail(CTR_FEED_ERR_CRC, "corrupted record data at byte %llu (crc mismatch)", (unsigned long long)(off - 12));
+    }
+    return CTR_FEED_OK;
+  });
 }
 
 void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens) {

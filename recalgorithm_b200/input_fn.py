@@ -35,12 +35,15 @@ def make_example_parser(feature_columns, label_keys: Sequence[str] = ("read_comm
 
 
 def _load(filepath: Union[str, Sequence[str]], mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """mmap=True maps the file(s) instead of reading them into RAM (a single file stays mapped; several files are concatenated,
+    """Read (or map) the file(s) and index their records in one sequential scan that checks the length CRCs; the payload CRCs
+    are checked per batch in `_batches` (inside the prefetch thread), so a corrupted record raises when its batch is produced --
+    like TFRecordDataset's DataLossError -- and the CRC pass overlaps the consumer instead of delaying the first batch.
+    mmap=True maps the file(s) instead of reading them into RAM (a single file stays mapped; several files are concatenated,
     which materialises them)."""
     paths = [filepath] if isinstance(filepath, str) else list(filepath)
     bufs, offs, lens, base = [], [], [], 0
     for p in paths:                                           # TFRecordDataset([files]) reads them one after the other
-        b, o, l = native.read_tfrecord_file(p, mmap=mmap)
+        b, o, l = native.read_tfrecord_file(p, verify="headers", mmap=mmap)
         bufs.append(b); offs.append(o + np.uint64(base)); lens.append(l)
         base += b.size
     return (bufs[0] if len(bufs) == 1 else np.concatenate(bufs)), np.concatenate(offs), np.concatenate(lens)
@@ -106,6 +109,16 @@ def _prefetch(gen: Iterator, depth: int = 1) -> Iterator:
 
 def _batches(order_epochs: Iterator[np.ndarray], data, batch_size: int, parser) -> Iterator:
     buf, off, ln = data
+    verified = np.zeros(off.size, dtype=bool)                # payload CRCs are checked the first time a record is used
+
+    def parse(idx):
+        o, l = off[idx], ln[idx]
+        new = ~verified[idx]
+        if new.any():
+            native.verify_records(buf, o[new], l[new])
+            verified[idx] = True
+        return parser((buf, o, l))
+
     pending: List[np.ndarray] = []
     have = 0
     for order in order_epochs:                               # repeat() happens BEFORE batch(): batches run across epoch borders
@@ -114,10 +127,10 @@ def _batches(order_epochs: Iterator[np.ndarray], data, batch_size: int, parser) 
             idx = np.concatenate(pending) if len(pending) > 1 else pending[0]
             take, rest = idx[:batch_size], idx[batch_size:]
             pending, have = ([rest] if rest.size else []), rest.size
-            yield parser((buf, off[take], ln[take]))
+            yield parse(take)
     if have:                                                 # drop_remainder=False
         idx = np.concatenate(pending) if len(pending) > 1 else pending[0]
-        yield parser((buf, off[idx], ln[idx]))
+        yield parse(idx)
 
 
 def train_input_fn(filepath, example_parser, batch_size: int, num_epochs: Optional[int], shuffle_buffer_size: int,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "ctr_feed_crc32c": (ctypes.c_uint32, [_P, ctypes.c_uint64]),
     "ctr_feed_masked_crc32c": (ctypes.c_uint32, [_P, ctypes.c_uint64]),
     "ctr_feed_tfrecord_index": (_I, [_P, ctypes.c_uint64, ctypes.c_int, _P, _P, _I, _P]),
+    "ctr_feed_tfrecord_verify": (ctypes.c_int, [_P, ctypes.c_uint64, _P, _P, _I, ctypes.c_int]),
     "ctr_feed_vocab_create": (_P, [_P, _P, _I]),
     "ctr_feed_vocab_load": (_P, [ctypes.c_char_p]),
     "ctr_feed_vocab_size": (_I, [_P]),
@@ -107,22 +108,46 @@ def masked_crc32c(data) -> int:
     return int(lib().ctr_feed_masked_crc32c(_ptr(a), a.size))
 
 
-def index_tfrecord(buf, verify: bool = True) -> Tuple[np.ndarray, np.ndarray]:
-    """(offsets, lengths) uint64 arrays of the record payloads inside a TFRecord byte buffer."""
+def index_tfrecord(buf, verify=True, num_threads: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """(offsets, lengths) uint64 arrays of the record payloads inside a TFRecord byte buffer, found in ONE sequential scan
+    (the output arrays are sized by the 16-bytes-per-record lower bound; untouched pages are never committed).
+    verify=True: length CRCs during the scan, payload CRCs afterwards on `num_threads` threads (0 = all cores);
+    verify="headers": length CRCs only -- the caller checks payloads later with verify_records (input_fn does it per batch, in
+    the prefetch thread, so that the CRC pass overlaps the consumer); verify=False: nothing is checked."""
     a = _u8(buf)
-    n = lib().ctr_feed_tfrecord_index(_ptr(a), a.size, int(verify), None, None, 0, None)
+    if verify not in (True, False, "headers"):
+        raise ValueError(f"verify must be True, False or 'headers', got {verify!r}")
+    bound = a.size // 16 + 1                                          # header 12 + footer 4 bytes: no record is shorter
+    offsets, lengths = np.empty(bound, np.uint64), np.empty(bound, np.uint64)
+    consumed = ctypes.c_uint64(0)
+    n = lib().ctr_feed_tfrecord_index(_ptr(a), a.size, 2 if verify else 0, offsets.ctypes.data, lengths.ctypes.data, bound,
+                                      ctypes.byref(consumed))
     if n < 0:
         _raise(int(n))
-    offsets, lengths = np.empty(n, np.uint64), np.empty(n, np.uint64)
-    if n:
-        got = lib().ctr_feed_tfrecord_index(_ptr(a), a.size, 0, offsets.ctypes.data, lengths.ctypes.data, n, None)
-        assert got == n
+    assert consumed.value == a.size, "the 16-byte bound cannot be reached before the buffer ends"
+    offsets, lengths = offsets[:n].copy(), lengths[:n].copy()         # drop the over-sized allocations
+    if verify is True:
+        verify_records(a, offsets, lengths, num_threads)
     return offsets, lengths
 
 
-def read_tfrecord_file(path: str, verify: bool = True, mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def verify_records(buf, offsets: np.ndarray, lengths: np.ndarray, num_threads: int = 0) -> None:
+    """Check the payload CRC of the given records (any subset, any order) on `num_threads` threads (0 = all cores); raises
+    FeedIOError naming the first corrupted one."""
+    a = _u8(buf)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+    if offsets.size == 0:
+        return
+    rc = lib().ctr_feed_tfrecord_verify(_ptr(a), a.size, offsets.ctypes.data, lengths.ctypes.data, int(offsets.size), int(num_threads))
+    if rc < 0:
+        _raise(int(rc))
+
+
+def read_tfrecord_file(path: str, verify=True, mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Whole file -> (bytes as uint8 array, offsets, lengths).  tf.data.TFRecordDataset(path) without the iterator.
-    mmap=True maps the file instead of reading it (files larger than RAM; pages are pulled in by the CRC / parse passes)."""
+    mmap=True maps the file instead of reading it (files larger than RAM; pages are pulled in by the scan / CRC / parse passes);
+    verify as in index_tfrecord."""
     buf = np.memmap(path, dtype=np.uint8, mode="r") if mmap and os.path.getsize(path) > 0 else np.fromfile(path, dtype=np.uint8)
     offsets, lengths = index_tfrecord(buf, verify)
     return buf, offsets, lengths

@@ -238,3 +238,25 @@ def test_native_parser_survives_corrupted_input():
         except ValueError:
             bad += 1
     assert ok > 0 and bad > 0
+
+
+def test_parallel_crc_verification_reports_the_first_bad_record(tmp_path):
+    """The payload CRCs are checked on several threads (ctr_feed_tfrecord_verify) after a sequential scan that only trusts
+    lengths whose own CRC matched: same verdict as the sequential verifier, and the FIRST corrupted record is the one named."""
+    recs = [bytes([i % 251]) * (40 + i % 17) for i in range(5000)]
+    p = str(tmp_path / "many.tfrecord")
+    cio.write_records(p, recs)
+    raw = bytearray(open(p, "rb").read())
+    off, ln = native.index_tfrecord(bytes(raw), num_threads=8)
+    assert len(off) == 5000 and [int(x) for x in ln[:3]] == [40, 41, 42]
+    bad = bytearray(raw)
+    for r in (4100, 700):                                          # two corrupted payloads, in different thread chunks
+        bad[int(off[r]) + 5] ^= 0x40
+    for nt in (1, 3, 8):
+        with pytest.raises(IOError) as e:
+            native.index_tfrecord(bytes(bad), num_threads=nt)
+        assert f"byte {int(off[700]) - 12} " in str(e.value)        # record 700 starts 12 bytes before its payload
+    assert len(native.index_tfrecord(bytes(bad), verify=False)[0]) == 5000
+    hdr = bytearray(raw); hdr[int(off[3000]) - 12] ^= 1              # a corrupted LENGTH is caught by the scan itself
+    with pytest.raises(IOError):
+        native.index_tfrecord(bytes(hdr), num_threads=8)

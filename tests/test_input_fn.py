@@ -98,3 +98,23 @@ def test_mmap_reads_the_same_batches(dataset):
     assert _ids(a).tolist() == _ids(b).tolist() == list(range(n))
     t = list(I.train_input_fn(p, parser, batch_size=50, num_epochs=1, shuffle_buffer_size=0, mmap=True))
     assert _ids(t).tolist() == list(range(n))
+
+
+def test_corrupted_payload_raises_when_its_batch_is_produced(dataset, tmp_path):
+    """Payload CRCs are verified per batch inside the prefetch thread (DataLossError-like timing): the batches before the
+    corrupted record arrive, the one that contains it raises; a corrupted LENGTH already fails at open time."""
+    from recalgorithm_b200.io import native
+    p, n, parser = dataset
+    raw = bytearray(open(p, "rb").read())
+    off, ln = native.index_tfrecord(bytes(raw))
+    bad = bytearray(raw); bad[int(off[70]) + 2] ^= 0x10              # record 70 -> batch 4 at batch_size 16
+    q = str(tmp_path / "bad.tfrecord"); open(q, "wb").write(bad)
+    it = I.eval_input_fn(q, parser, batch_size=16)
+    got = [next(it) for _ in range(4)]                                # records 0..63 are fine
+    assert _ids(got).tolist() == list(range(64))
+    with pytest.raises(IOError):
+        next(it)
+    hdr = bytearray(raw); hdr[int(off[5]) - 12] ^= 1
+    r = str(tmp_path / "badlen.tfrecord"); open(r, "wb").write(hdr)
+    with pytest.raises(IOError):
+        I.eval_input_fn(r, parser, batch_size=16)
