@@ -46,6 +46,13 @@ int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, 
 int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* offsets, const uint64_t* lengths, int64_t count,
                              int num_threads);
 
+/* dataset.shuffle(buffer_size) (algorithm/utils.py:20): the order in which a shuffle buffer emits n elements -- a buffer of the
+ * next `buffer_size` inputs, one of them drawn uniformly at each step (draws[i] in [0,1) picks slot floor(draws[i] * filled))
+ * and replaced by the next input, or by the buffer's last element once the input is exhausted.  The caller supplies the n
+ * draws, so the order is a pure function of them (input_fn.shuffle_order feeds numpy's seeded generator).
+ * buffer_size <= 1: identity; buffer_size >= n: still the buffer walk (a uniform permutation).  out: (n,) int64. */
+int ctr_feed_shuffle_order(int64_t n, int64_t buffer_size, const double* draws, int64_t* out);
+
 /* Vocabulary: token i = blob[offsets[i], offsets[i+1]); id = index of the FIRST occurrence of a token. */
 void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens);
 void* ctr_feed_vocab_load(const char* path);                 /* one token per line ('\n' or '\r\n'), like the reference's files */

@@ -372,6 +372,28 @@ int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* off
   });
 }
 
+int ctr_feed_shuffle_order(int64_t n, int64_t buffer_size, const double* draws, int64_t* out) {
+  if (n < 0 || (n > 0 && !out)) return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_order: bad arguments");
+  if (buffer_size <= 1 || n <= 1) {
+    for (int64_t i = 0; i < n; ++i) out[i] = i;
+    return CTR_FEED_OK;
+  }
+  if (!draws) return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_order: draws is null");
+  const int64_t cap = std::min(buffer_size, n);
+  std::vector<int64_t> slots((size_t)cap);
+  for (int64_t i = 0; i < cap; ++i) slots[i] = i;
+  int64_t next = cap, filled = cap;
+  for (int64_t i = 0; i < n; ++i) {
+    const double u = draws[i];
+    if (!(u >= 0.0 && u < 1.0)) return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_order: draws[%lld] is outside [0,1)", (long long)i);
+    const int64_t j = std::min<int64_t>((int64_t)(u * (double)filled), filled - 1);
+    out[i] = slots[j];
+    if (next < n) slots[j] = next++;
+    else slots[j] = slots[--filled];
+  }
+  return CTR_FEED_OK;
+}
+
 void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens) {
   if (n_tokens < 0 || (n_tokens > 0 && (!offsets || (!blob && offsets[n_tokens] > 0)))) {
     fail(CTR_FEED_ERR_ARG, "ctr_feed_vocab_create: bad arguments");

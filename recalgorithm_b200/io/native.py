@@ -39,6 +39,7 @@ SIGNATURES = {
     "ctr_feed_masked_crc32c": (ctypes.c_uint32, [_P, ctypes.c_uint64]),
     "ctr_feed_tfrecord_index": (_I, [_P, ctypes.c_uint64, ctypes.c_int, _P, _P, _I, _P]),
     "ctr_feed_tfrecord_verify": (ctypes.c_int, [_P, ctypes.c_uint64, _P, _P, _I, ctypes.c_int]),
+    "ctr_feed_shuffle_order": (ctypes.c_int, [_I, _I, _P, _P]),
     "ctr_feed_vocab_create": (_P, [_P, _P, _I]),
     "ctr_feed_vocab_load": (_P, [ctypes.c_char_p]),
     "ctr_feed_vocab_size": (_I, [_P]),
@@ -142,6 +143,18 @@ def verify_records(buf, offsets: np.ndarray, lengths: np.ndarray, num_threads: i
     rc = lib().ctr_feed_tfrecord_verify(_ptr(a), a.size, offsets.ctypes.data, lengths.ctypes.data, int(offsets.size), int(num_threads))
     if rc < 0:
         _raise(int(rc))
+
+
+def shuffle_order(n: int, buffer_size: int, draws: np.ndarray) -> np.ndarray:
+    """Emission order of dataset.shuffle(buffer_size) over n elements for the given n uniform draws (ctr_feed_shuffle_order)."""
+    draws = np.ascontiguousarray(draws, dtype=np.float64)
+    if draws.size < n:
+        raise ValueError(f"shuffle_order needs {n} draws, got {draws.size}")
+    out = np.empty(n, np.int64)
+    rc = lib().ctr_feed_shuffle_order(int(n), int(buffer_size), draws.ctypes.data, out.ctypes.data)
+    if rc < 0:
+        _raise(int(rc))
+    return out
 
 
 def read_tfrecord_file(path: str, verify=True, mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

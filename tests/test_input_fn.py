@@ -118,3 +118,37 @@ def test_corrupted_payload_raises_when_its_batch_is_produced(dataset, tmp_path):
     r = str(tmp_path / "badlen.tfrecord"); open(r, "wb").write(hdr)
     with pytest.raises(IOError):
         I.eval_input_fn(r, parser, batch_size=16)
+
+
+def _shuffle_order_py(n, buffer_size, draws):
+    """The buffer walk of dataset.shuffle written out in Python: the readable twin ctr_feed_shuffle_order is compared with."""
+    buf = list(range(min(buffer_size, n)))
+    out, nxt, filled = [], len(buf), len(buf)
+    for i in range(n):
+        j = int(draws[i] * filled)
+        out.append(buf[j])
+        if nxt < n:
+            buf[j] = nxt; nxt += 1
+        else:
+            filled -= 1; buf[j] = buf[filled]
+    return out
+
+
+def test_native_shuffle_order_is_the_buffer_walk():
+    from recalgorithm_b200.io import native
+    rng = np.random.default_rng(5)
+    for n, bs in [(2, 2), (10, 3), (1000, 7), (1000, 999), (1000, 1000), (1000, 5000), (50_000, 10_000)]:
+        draws = rng.random(n)
+        got = native.shuffle_order(n, bs, draws)
+        assert got.tolist() == _shuffle_order_py(n, bs, draws)
+        assert sorted(got.tolist()) == list(range(n))                # a permutation
+        pos = np.empty(n, np.int64); pos[got] = np.arange(n)
+        assert (np.arange(n) - pos < bs).all()                        # element i cannot be emitted before input i - bs + 1 arrived
+    assert native.shuffle_order(5, 1, np.zeros(5)).tolist() == [0, 1, 2, 3, 4]
+    assert native.shuffle_order(0, 10, np.zeros(0)).size == 0
+    with pytest.raises(ValueError):
+        native.shuffle_order(5, 3, np.array([0.1, 0.2, 1.0, 0.3, 0.4]))   # a draw outside [0,1)
+    with pytest.raises(ValueError):
+        native.shuffle_order(5, 3, np.zeros(2))
+    a = I.shuffle_order(20_000, 100, np.random.default_rng(3)); b = I.shuffle_order(20_000, 100, np.random.default_rng(3))
+    assert a.tolist() == b.tolist() and a.tolist() != list(range(20_000))
