@@ -51,6 +51,17 @@ DEEPFM = {
                                  rows_per_field_per_rank=100_000, rows_per_field=100_000, id_batches=4, sharded=True),
 }
 LAYER_WORKLOADS = ("dcn_cfg2", "xdeepfm_cfg3", "din_cfg4")
+
+
+def deepfm_config(workload, model, B, world, F, D, rows, ids_desc, NB):
+    """`config` of a replicated-table DeepFM line.  ONE builder for the GPU arm and for `--impl reference`: when the CPU arm runs
+    the same B / table / id batches its config dict is equal to the GPU arm's, key for key (it says what ran when it could not)."""
+    return {"workload": workload, "model": model, "global_batch": B * world, "B_per_gpu": B, "F": F, "D": D,
+            "rows_per_field": rows, "vocab_rows_total": rows * F, "ids": ids_desc,
+            "parallelism": ("replicated tables (12.8 GB fits one device), data-parallel ranks, no exchange" if world > 1
+                            else "single device, no exchange"),
+            "l2": f"inputs larger than the last-level cache: {NB} rotating id batches over a {rows * F * D * 4 / 1e9:.1f} GB table; "
+                  f"tile/d_tile/row_grads are {B * F * D * 4 / 1e6:.0f} MB each"}
 NVLINK_PEAK_GBS = 770.0       # B200_PROFILING.md: measured peer copy, per direction per GPU
 
 
@@ -251,8 +262,9 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=90.0):
     model = _cpu_model_cache[key]
     B = cfg["B"]
     g = torch.Generator().manual_seed(1234)
+    NB = cfg["id_batches"]                    # as many rotating id batches as the GPU arm
     batches = [(torch.randint(0, rows, (B, cfg["F"]), generator=g), (torch.rand((B, 1), generator=g) < 0.0356).float())
-               for _ in range(4)]
+               for _ in range(NB)]
     probe = [(i[:8192].contiguous(), l[:8192].contiguous()) for i, l in batches[:2]]
     best = None                               # give the CPU arm its best thread count: many-core hosts oversubscribe on small ops
     for nt in sorted({min(cores, c) for c in (4, 8, 16, 32, 64, cores)}):
@@ -271,10 +283,10 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=90.0):
         sample_B = max(4096, int(B * budget_s / (est * (steps + warmup))) // 4096 * 4096)
         batches = [(i[:sample_B].contiguous(), l[:sample_B].contiguous()) for i, l in batches]
     for i in range(warmup):
-        model.step(*batches[i % 4])
+        model.step(*batches[i % NB])
     t0 = time.perf_counter()
     for i in range(steps):
-        model.step(*batches[i % 4])
+        model.step(*batches[i % NB])
     dt = time.perf_counter() - t0
     info = {"cores": threads, "host_cores_usable": cores, "kind": "port", "B": sample_B, "rows_per_field": rows,
             "same_config_as_gpu_arm": bool(sample_B == B and rows == cfg["rows_per_field"]),
@@ -292,10 +304,12 @@ def run_reference_arm(args, cfg):
     line = {"metric": "ctr_fwd_bwd_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "model": cfg["model"], "global_batch": info["B"], "B_per_gpu": info["B"],
-                       "B": info["B"], "F": cfg["F"], "D": cfg["D"], "rows_per_field": info["rows_per_field"],
-                       "vocab_rows_total": info["rows_per_field"] * cfg["F"], "ids": "uniform int64",
-                       "note": "CPU arm runs the single-process configuration (one batch of B per step) at every N"},
+            # the GPU arm's N = 1 config, key for key (B / rows differ only if the host could not hold or finish them); launched
+            # with N > 1 the CPU arm still runs this single-process configuration, and says so
+            "config": deepfm_config(args.workload, cfg["model"], info["B"], 1, cfg["F"], cfg["D"], info["rows_per_field"],
+                                    "uniform int64", cfg["id_batches"])
+                      | ({"note": "CPU arm runs the single-process configuration (one batch of B per step) at every N"}
+                         if args.gpus > 1 else {}),
             "cpu_baseline": {"value": sps, "unit": "samples/s", **info},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -511,11 +525,7 @@ def run_deepfm(args, cfg, dd: Dist):
             "metric": "ctr_fwd_bwd_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": cfg["model"], "global_batch": B * world, "B_per_gpu": B, "F": F,
-                       "D": D, "rows_per_field": rows, "vocab_rows_total": rows * F, "ids": ids_desc,
-                       "parallelism": "replicated tables (12.8 GB fits one GPU), data-parallel ranks, no exchange" if world > 1 else "1 GPU",
-                       "l2": f"inputs larger than L2: {NB} rotating id batches over a {rows * F * D * 4 / 1e9:.1f} GB table; "
-                             f"tile/d_tile/row_grads are {B * F * D * 4 / 1e6:.0f} MB each"},
+            "config": deepfm_config(args.workload, cfg["model"], B, world, F, D, rows, ids_desc, NB),
             "roofline": {"bound": "hbm", "kernel": "embed_fm2_fwd_kernel<8> (fused gather + FM2)", "achieved": ach_fwd,
                          "peak": hbm, "unit": "GB/s", "frac": ach_fwd / hbm, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel_source_sha256_16": kernel_source_hash(), "peak_source": peaks["source"],

@@ -1,0 +1,55 @@
+"""bench.py's JSON-line contract, as far as it can be checked without a GPU: the reference arm (`--impl reference`, the CPU
+restatement of DeepFM/deepfm.py:178-235) really runs here, and the GPU arm's `config` comes from the same builder."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def _reference_line(extra=(), env=None):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "deepfm_small",
+                          "--steps", "2", "--warmup", "1", *extra], capture_output=True, text=True, timeout=600,
+                         env={**os.environ, **(env or {})})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    return lines
+
+
+def test_reference_arm_line_has_the_contract_keys_and_the_gpu_arms_config():
+    import bench
+    lines = _reference_line()
+    assert len(lines) == 1                                          # ONE JSON line
+    d = json.loads(lines[0])
+    assert BASE_KEYS | {"impl", "cpu_baseline"} <= set(d)
+    assert d["impl"] == "reference" and d["metric"] == "ctr_fwd_bwd_samples_per_sec" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["steps"] == 2 and d["warmup"] >= 3                     # the timing rules ask for W >= 3
+    assert d["value"] > 0 and abs(d["value"] - d["config"]["global_batch"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the config the GPU arm prints for the same workload at N = 1 (bench.run_deepfm builds it with the same function)
+    cfg = bench.DEEPFM["deepfm_small"]
+    assert cb["same_config_as_gpu_arm"] is True
+    assert d["config"] == bench.deepfm_config("deepfm_small", cfg["model"], cfg["B"], 1, cfg["F"], cfg["D"], cfg["rows_per_field"],
+                                              "uniform int64", cfg["id_batches"])
+
+
+def test_reference_arm_under_torchrun_env_prints_on_rank_0_only():
+    assert _reference_line(("--gpus", "2"), env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+    (line,) = _reference_line(("--gpus", "2"), env={"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    d = json.loads(line)
+    assert d["n_gpus"] == 2 and "single-process" in d["config"]["note"]
+
+
+def test_algorithmic_bytes_match_survey_8d():
+    import bench
+    fwd, bwd = bench.bytes_per_sample(40, 32)
+    assert fwd + bwd == 40 * (8 + 20 * 32) + 8 == 25928             # F*(8 + 20*D) + 8 per sample at config 5
+    assert fwd == 40 * (8 + 2 * 32 * 4) + 4 and bwd == 40 * 3 * 32 * 4 + 4
