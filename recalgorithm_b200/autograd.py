@@ -61,6 +61,7 @@ def _ids64_for(ids: torch.Tensor):
 class _LookupFM2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, tables: EmbeddingTables, ids: torch.Tensor, want_fm2: bool):
+        ctx.set_materialize_grads(False)            # an unused output arrives as None in backward, not as a zero-filled (B,F,D)
         ids64 = _ids64_for(ids)
         tile, fm2 = ops.embed_fm2_fwd(tables.weight, tables.field_row_offset, ids, want_tile=True, want_fm2=want_fm2,
                                       ids64_out=ids64)
@@ -73,6 +74,8 @@ class _LookupFM2(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_tile, d_fm2=None):
         (tile,) = ctx.saved_tensors
+        if d_tile is None and d_fm2 is None:        # nothing upstream depends on the lookup: no IndexedSlices
+            return None, None, None, None
         if d_tile is not None:
             d_tile = d_tile.contiguous()
         if d_fm2 is not None:
@@ -102,6 +105,7 @@ def lookup(tables: EmbeddingTables, ids: torch.Tensor):
 class _LookupFM2Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wlin, tables: EmbeddingTables, ids: torch.Tensor):
+        ctx.set_materialize_grads(False)
         ids64 = _ids64_for(ids)
         wl = wlin.contiguous()
         tile, fm2, lin = ops.embed_fm2_lin_fwd(tables.weight, tables.field_row_offset, ids, wl, ids64_out=ids64)
@@ -173,6 +177,7 @@ def cross_stack(x0: torch.Tensor, w: torch.Tensor, b: torch.Tensor, xl: Optional
 class _LookupCross(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, tables: EmbeddingTables, ids, w, b):
+        ctx.set_materialize_grads(False)            # `g_x0` is None when only the cross output is consumed (and vice versa)
         wc, bc = w.contiguous(), b.contiguous()
         x0, out = ops.embed_cross_fwd(tables.weight, tables.field_row_offset, ids, wc, bc)
         ctx.tables, ctx.ids = tables, (ids if ids.dtype == torch.int64 else ids.long())
@@ -288,6 +293,7 @@ def bilinear(x, w, type_):
 class _LookupBI(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, tables: EmbeddingTables, ids: torch.Tensor):
+        ctx.set_materialize_grads(False)
         tile, bi = ops.embed_bi_fwd(tables.weight, tables.field_row_offset, ids)
         ctx.tables, ctx.ids = tables, ids
         ctx.save_for_backward(tile)

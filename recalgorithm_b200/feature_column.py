@@ -173,6 +173,23 @@ def _ragged_ids(col: CategoricalColumn, features, device) -> Tuple[torch.Tensor,
     return torch.from_numpy(np.ascontiguousarray(ids)).to(device), torch.from_numpy(np.asarray(offsets, np.int64)).to(device)
 
 
+def pad_ragged(values: np.ndarray, offsets: np.ndarray, width: int, fill: int = -1) -> np.ndarray:
+    """Ragged rows values[offsets[b]:offsets[b+1]] -> (B, width) int64, left aligned, padded with `fill` (one vectorised
+    scatter: a Python loop over B = 4096 rows costs more than the DIN step it feeds)."""
+    offsets = np.asarray(offsets, np.int64)
+    lens = np.diff(offsets)
+    B = lens.size
+    if B and int(lens.max()) > width:
+        raise ValueError(f"pad_ragged: a row holds {int(lens.max())} values, width is {width}")
+    out = np.full((B, width), fill, np.int64)
+    n = int(offsets[-1] - offsets[0]) if B else 0
+    if n:
+        row = np.repeat(np.arange(B, dtype=np.int64), lens)
+        col = np.arange(n, dtype=np.int64) - np.repeat(offsets[:-1] - offsets[0], lens)
+        out[row, col] = np.asarray(values)[offsets[0]:offsets[-1]]
+    return out
+
+
 def single_valued_ids(features, categorical_columns) -> np.ndarray:
     """(B, F) int64 id matrix of F single-valued categorical columns, in the order given, -1 where the value is missing /
     out of vocabulary -- the input of the fused lookup (autograd.lookup_fm2 / lookup / lookup_bi)."""
@@ -261,9 +278,7 @@ def sequence_input_layer(features, feature_columns, ctx: Optional[LookupContext]
         B, T = len(lens), int(lens.max()) if len(lens) else 0
         table = _table_for(c)
         ids = _ids_of(c.categorical_column, values)
-        padded = np.full((B, max(T, 1)), -1, np.int64)        # -1 -> zero vector == zero padding
-        for b in range(B):
-            padded[b, :lens[b]] = ids[offsets[b]:offsets[b + 1]]
+        padded = pad_ragged(ids, offsets, max(T, 1))            # -1 -> zero vector == zero padding
         flat_ids = torch.from_numpy(padded.reshape(-1)).to(device)
         step_off = torch.arange(flat_ids.numel() + 1, dtype=torch.int64, device=device)
         buf = torch.zeros((flat_ids.numel(), c.dimension), dtype=torch.float32, device=device)

@@ -238,3 +238,75 @@ def test_sigmoid_ce_matches_the_reference_formula(B):
         assert_close(a.grad, x.grad, 1e-5, "d loss / d logit")
         if two:
             assert torch.equal(a.grad, b.grad)
+
+
+def _dense_table_grad(fn, table64, ids_cpu, off_cpu):
+    """d loss / d table from plain float64 torch on the CPU: e = table[off[f] + id] (zero row for id < 0), loss = fn(e)."""
+    t = table64.clone().requires_grad_()
+    valid = (ids_cpu >= 0).unsqueeze(-1)
+    e = t[(ids_cpu.clamp_min(0) + off_cpu[:-1][None, :])] * valid
+    fn(e).backward()
+    return t.grad
+
+
+@pytest.mark.parametrize("which", ["fm2_only", "tile_only", "lin_only", "fm2_of_linear_only", "bi_only", "bi_tile_only",
+                                   "cross_only", "cross_x0_only"])
+def test_unused_lookup_outputs_take_no_gradient_buffer(which):
+    """The multi-output lookups do not materialise a zero gradient for an output the loss never used (the backward receives None
+    and hands a null pointer to the C ABI): the table gradient still equals the float64 restatement of the used branch alone."""
+    from recalgorithm_b200 import autograd
+    torch.manual_seed(7)
+    B, F, D, rows, L = 37, 6, 8, 11, 2
+    tables = autograd.EmbeddingTables([rows] * F, D, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    ids = torch.randint(-1, rows, (B, F), device="cuda")
+    t64, ids_c, off_c = tables.weight.double().cpu(), ids.cpu(), tables.field_row_offset.cpu()
+    gt = torch.randn((B, F, D), dtype=torch.float64)
+    wl = torch.randn((F * D,), dtype=torch.float64) * 0.1
+    cw, cb = torch.randn((L, F * D), dtype=torch.float64) * 0.05, torch.randn((L, F * D), dtype=torch.float64) * 0.05
+    gx = torch.randn((B, F * D), dtype=torch.float64)
+
+    def fm2(e):
+        return 0.5 * ((e.sum(1) ** 2).sum(1) - (e ** 2).sum((1, 2)))
+
+    def bi(e):
+        return 0.5 * (e.sum(1) ** 2 - (e ** 2).sum(1))
+
+    def cross(e):
+        x0 = e.reshape(B, -1); xl = x0
+        for l in range(L):
+            xl = x0 * (xl @ cw[l])[:, None] + cb[l] + xl
+        return xl
+
+    f32 = lambda x: x.float().cuda()                                          # noqa: E731
+    if which == "fm2_only":
+        _, out = autograd.lookup_fm2(tables, ids); loss = out.sum(); ref = lambda e: fm2(e).sum()                     # noqa: E731
+    elif which == "tile_only":
+        out, _ = autograd.lookup_fm2(tables, ids); loss = (out * f32(gt)).sum(); ref = lambda e: (e * gt).sum()       # noqa: E731
+    elif which in ("lin_only", "fm2_of_linear_only"):
+        w = f32(wl).requires_grad_()
+        o_fm2, o_lin = autograd.lookup_fm2_linear(tables, ids, w)
+        if which == "lin_only":
+            loss = o_lin.sum(); ref = lambda e: (e.reshape(B, -1) @ wl).sum()                                          # noqa: E731
+        else:
+            loss = o_fm2.sum(); ref = lambda e: fm2(e).sum()                                                          # noqa: E731
+    elif which == "bi_only":
+        _, out = autograd.lookup_bi(tables, ids); loss = out.sum(); ref = lambda e: bi(e).sum()                       # noqa: E731
+    elif which == "bi_tile_only":
+        out, _ = autograd.lookup_bi(tables, ids); loss = (out * f32(gt)).sum(); ref = lambda e: (e * gt).sum()        # noqa: E731
+    else:
+        w, b = f32(cw).requires_grad_(), f32(cb).requires_grad_()
+        xl, x0 = autograd.lookup_cross(tables, ids, w, b)
+        if which == "cross_only":
+            loss = (xl * f32(gx)).sum(); ref = lambda e: (cross(e) * gx).sum()                                        # noqa: E731
+        else:
+            loss = (x0 * f32(gx)).sum(); ref = lambda e: (e.reshape(B, -1) * gx).sum()                                # noqa: E731
+    loss.backward()
+    (sl,) = tables.grad_slices
+    assert_close(sl.to_dense(tables.num_rows), _dense_table_grad(ref, t64, ids_c, off_c), TOL, which)
+    if which == "lin_only":
+        e = t64[(ids_c.clamp_min(0) + off_c[:-1][None, :])] * (ids_c >= 0).unsqueeze(-1)
+        assert_close(w.grad, e.reshape(B, -1).sum(0), TOL, "d_wlin")
+    if which == "fm2_of_linear_only":
+        assert float(w.grad.abs().max()) == 0.0                               # d_lin = None -> d_wlin is exactly zero
+    if which == "cross_x0_only":
+        assert w.grad is None and b.grad is None                              # the cross weights were not on the used branch

@@ -152,3 +152,20 @@ def test_native_shuffle_order_is_the_buffer_walk():
         native.shuffle_order(5, 3, np.zeros(2))
     a = I.shuffle_order(20_000, 100, np.random.default_rng(3)); b = I.shuffle_order(20_000, 100, np.random.default_rng(3))
     assert a.tolist() == b.tolist() and a.tolist() != list(range(20_000))
+
+
+def test_pad_ragged_is_the_row_by_row_copy():
+    rng = np.random.default_rng(2)
+    for B, tmax in [(0, 3), (1, 0), (5, 4), (300, 50)]:
+        lens = rng.integers(0, tmax + 1, B)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        vals = rng.integers(0, 1000, int(off[-1])).astype(np.int64)
+        width = max(int(lens.max()) if B else 0, 1)
+        want = np.full((B, width), -1, np.int64)
+        for b in range(B):
+            want[b, :lens[b]] = vals[off[b]:off[b + 1]]
+        assert np.array_equal(fc.pad_ragged(vals, off, width), want)
+    with pytest.raises(ValueError):
+        fc.pad_ragged(np.arange(3), np.array([0, 3]), 2)
+    # offsets that do not start at 0 (a slice of a larger ragged array)
+    assert fc.pad_ragged(np.arange(10), np.array([4, 6, 6, 9]), 3).tolist() == [[4, 5, -1], [-1, -1, -1], [6, 7, 8]]
