@@ -239,6 +239,8 @@ def parse_examples(buf, offsets: np.ndarray, lengths: np.ndarray, categorical: D
         if rc:
             _raise(rc)
         break
+    else:                                                    # `needed` is exact, so the second round cannot come up short
+        _raise(ERR_CAPACITY)
     out: Dict[str, object] = dict(dense_out)
     for i, k in enumerate(ckeys):
         out[k] = (ids[k][: int(cats[i].needed)], row_off[k])

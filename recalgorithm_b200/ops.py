@@ -293,12 +293,14 @@ _din_sched = {}
 
 
 def _din_sched_scratch(B: int, device, balanced: bool):
-    """int32[B + 64] schedule scratch of the DIN kernels (longest-first dynamic work distribution), cached per device."""
+    """int32[B + 64] schedule scratch of the DIN kernels (longest-first dynamic work distribution), cached per (device, stream):
+    two streams running the attention at the same time must not share the sample list."""
     if not balanced or B == 0:
         return None
-    t = _din_sched.get(device)
+    key = (device, _stream())
+    t = _din_sched.get(key)
     if t is None or t.numel() < B + 64:
-        t = _din_sched[device] = torch.empty((B + 64,), dtype=torch.int32, device=device)
+        t = _din_sched[key] = torch.empty((B + 64,), dtype=torch.int32, device=device)
     return t
 
 
