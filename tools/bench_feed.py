@@ -71,7 +71,22 @@ def main():
             pyv[k].lookup(parsed[k][0])
         t_py = time.perf_counter() - t0
         assert np.array_equal(out["userid"][0][:n_py], pyv["userid"].lookup(parsed["userid"][0]))
+        # the whole host pipeline as a model sees it (input_fn: open + shuffle + repeat + batch + parse + prefetch), one epoch
+        from recalgorithm_b200 import feature_column as fc, input_fn as I
+        cols = [fc.categorical_column_with_vocabulary_file(k, cio.VocabularyFile(toks[k])) for k in keys]
+        parser = I.make_example_parser(cols + [fc.numeric_column("read_comment")], label_keys=["read_comment"])
+        pipe = {}
+        for label, make in (("eval_input_fn", lambda: I.eval_input_fn(path, parser, 65536)),
+                            ("train_input_fn_shuffle10000", lambda: I.train_input_fn(path, parser, 65536, 1, 10000, seed=0))):
+            best = float("inf")
+            for _ in range(3):
+                t1 = time.perf_counter()
+                n = sum(len(f["userid"][1]) - 1 for f, _ in make())
+                best = min(best, time.perf_counter() - t1)
+            assert n == args.records
+            pipe[label] = args.records / best
         print(json.dumps({"records": args.records, "file_MB": size / 1e6, "cpu_count": os.cpu_count(),
+                          "input_fn_samples_per_s": pipe,  # batch 65536, includes opening the file (length-CRC scan) every epoch
                           "native_read_index_crc_MBps": size / 1e6 / t_index,
                           "native_open_MBps": open_rates,      # input_fn opens with length CRCs only; payload CRCs run per batch in the prefetch thread
                           "native_parse_examples_per_s": {str(nt): args.records / t for nt, t in res.items()},
