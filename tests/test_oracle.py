@@ -302,3 +302,69 @@ def test_ffm_matches_reference_executed(name):
     gg = np.random.default_rng(0).standard_normal(t.shape[0])
     (out * torch.tensor(gg)).sum().backward()
     assert rel(O.ffm_bwd(g["tile"].astype(np.float64), gg), t.grad.numpy()) <= 1e-12
+
+
+# ---------------------------------------------------------------- lookup / optimizer rows against torch's own CPU operators
+# Row L and the Adam step are the rows whose semantics live inside TensorFlow: nothing here can run TF 1.14, so
+# they stay "parity unpinned" against the reference.  What CAN be checked is that the restatement agrees with a second,
+# independent implementation of the same published semantics -- torch's embedding / embedding_bag / (Sparse)Adam on the CPU.
+def test_lookup_restatement_agrees_with_torch_embedding_ops():
+    rng = np.random.default_rng(21)
+    rows, D, B, F = [7, 1, 12], 8, 64, 3
+    off = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+    table = rng.standard_normal((int(off[-1]), D)).astype(np.float32)
+    ids = np.stack([rng.integers(-1, r, B) for r in rows], 1).astype(np.int64)
+    out = O.embedding_lookup(table, ids, off)
+    # torch: one extra all-zero row as padding_idx stands in for "id < 0 -> pruned -> zero vector"
+    padded = torch.from_numpy(np.concatenate([table, np.zeros((1, D), np.float32)]))
+    gidx = torch.from_numpy(np.where(ids >= 0, ids + off[:-1][None, :], int(off[-1])))
+    assert np.array_equal(out, torch.nn.functional.embedding(gidx, padded, padding_idx=int(off[-1])).numpy())
+    # multi-valued bags, combiner='mean': prune ids < 0, mean of the rest, empty bag -> zeros
+    lens = rng.integers(0, 6, B)
+    boff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    bids = rng.integers(-1, int(off[-1]), int(boff[-1])).astype(np.int64)
+    got = O.bag_lookup_mean(table.astype(np.float64), bids, boff)
+    keep = bids >= 0
+    kept_off = np.concatenate([[0], np.cumsum([int(keep[boff[b]:boff[b + 1]].sum()) for b in range(B)])])[:-1]
+    want = torch.nn.functional.embedding_bag(torch.from_numpy(bids[keep]), torch.from_numpy(table.astype(np.float64)),
+                                             torch.from_numpy(kept_off), mode="mean").numpy()
+    assert np.allclose(got, want, rtol=1e-13, atol=1e-15)
+    empty = np.array([not keep[boff[b]:boff[b + 1]].any() for b in range(B)])
+    assert empty.any() and np.all(got[empty] == 0) and np.all(want[empty] == 0)
+    # the gather's gradient: IndexedSlices densified == torch's dense embedding gradient
+    g = rng.standard_normal((B, F, D))
+    w = torch.from_numpy(np.concatenate([table, np.zeros((1, D), np.float32)]).astype(np.float64)).requires_grad_()
+    (torch.nn.functional.embedding(gidx, w, padding_idx=int(off[-1])) * torch.from_numpy(g)).sum().backward()
+    assert np.allclose(O.embedding_lookup_bwd_dense(int(off[-1]), ids, off, g), w.grad[:-1].numpy(), rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("lazy", [False, True])
+def test_adam_restatement_agrees_with_torch_adam(lazy):
+    """tf.train.AdamOptimizer on IndexedSlices (dense decay) == torch.optim.Adam on the densified gradient; LazyAdamOptimizer ==
+    torch.optim.SparseAdam.  TF's epsilon sits outside the bias correction ("epsilon hat"): lr_t*m/(sqrt(v)+eps) equals torch's
+    form with eps_torch = eps/sqrt(1-beta2^t), set per step.  The restatement also keeps TF's float32-rounded (1-beta) factors
+    (1.3e-5 relative on 1-beta2), which torch does not have: hence 5e-5, not 1e-13."""
+    rng = np.random.default_rng(8)
+    V, D, lr, b1, b2, eps = 40, 4, 0.01, 0.9, 0.999, 1e-8
+    var0 = rng.standard_normal((V, D))
+    var, m, v = var0.copy(), np.zeros((V, D)), np.zeros((V, D))
+    p = torch.nn.Parameter(torch.from_numpy(var0.copy()))
+    opt = (torch.optim.SparseAdam if lazy else torch.optim.Adam)([p], lr=lr, betas=(b1, b2), eps=eps)
+    for t in range(1, 8):
+        n = int(rng.integers(1, 30))
+        rows = rng.integers(0, V, n)                                   # duplicates on purpose
+        vals = rng.standard_normal((n, D)) * 0.1
+        var, m, v = O.adam_sparse_apply(var, m, v, rows, vals, t, lr, b1, b2, eps, lazy=lazy)
+        opt.param_groups[0]["eps"] = eps / np.sqrt(1.0 - b2 ** t)
+        if lazy:
+            p.grad = torch.sparse_coo_tensor(torch.from_numpy(rows)[None, :], torch.from_numpy(vals), (V, D))
+        else:
+            dense = np.zeros((V, D)); np.add.at(dense, rows, vals)
+            p.grad = torch.from_numpy(dense)
+        opt.step()
+        assert rel(var, p.detach().numpy()) <= 5e-5, t
+        touched = np.zeros(V, bool); touched[rows] = True
+        if lazy and (~touched).any():                                  # LazyAdam leaves unreferenced rows alone, bit for bit
+            prev = p_prev if t > 1 else var0
+            assert np.array_equal(var[~touched], prev[~touched])
+        p_prev = var.copy()
