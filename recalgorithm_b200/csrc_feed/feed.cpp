@@ -10,7 +10,6 @@
 #include <string>
 #include <string_view>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #if defined(__x86_64__)
@@ -84,21 +83,82 @@ uint32_t crc32c(const uint8_t* p, uint64_t n) {
 }
 uint32_t masked(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xA282EAD8u; }
 
+// ------------------------------------------------------------------------------------------------ string -> int table
+// Multiply-mix hash over 8-byte words (the keys are short tokens such as "userid_8": one or two words).
+inline uint64_t hash_bytes(const uint8_t* p, uint64_t n) {
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xFF51AFD7ED558CCDull);
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+    p += 8; n -= 8;
+  }
+  if (n) {
+    uint64_t w = 0;
+    memcpy(&w, p, n);
+    h = (h ^ w) * 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 29;
+  }
+  h *= 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 32);
+}
+
+// Open addressing, linear probing, load <= 1/2.  A slot holds the key's place in `base` (the table does not own the bytes), its
+// length, 32 bits of its hash and the value: one cache line decides most probes, the key bytes are touched once, to confirm.
+// The first insert of a key wins (categorical_column_with_vocabulary_file: id = line of the FIRST occurrence).
+struct FlatMap {
+  struct Slot {
+    uint64_t off;
+    uint32_t len;
+    uint32_t tag;        // 0 = empty; hashes are forced non-zero
+    int64_t value;
+  };
+  std::vector<Slot> slots;
+  uint64_t mask = 0;
+  const uint8_t* base = nullptr;
+
+  static uint32_t tag_of(uint64_t h) { const uint32_t t = (uint32_t)(h >> 32); return t ? t : 1u; }
+  void init(const uint8_t* b, size_t n_keys) {
+    base = b;
+    size_t cap = 8;
+    while (cap < 2 * n_keys) cap <<= 1;
+    slots.assign(cap, Slot{0, 0, 0, 0});
+    mask = cap - 1;
+  }
+  void insert(uint64_t off, uint32_t len, int64_t value) {
+    const uint64_t h = hash_bytes(base + off, len);
+    const uint32_t tag = tag_of(h);
+    for (uint64_t i = h & mask;; i = (i + 1) & mask) {
+      Slot& s = slots[i];
+      if (!s.tag) { s = Slot{off, len, tag, value}; return; }
+      if (s.tag == tag && s.len == len && memcmp(base + s.off, base + off, len) == 0) return;     // first occurrence wins
+    }
+  }
+  int64_t find(const uint8_t* p, uint64_t n, int64_t missing) const {
+    if (slots.empty() || n > 0xFFFFFFFFull) return missing;
+    const uint64_t h = hash_bytes(p, n);
+    const uint32_t tag = tag_of(h);
+    for (uint64_t i = h & mask;; i = (i + 1) & mask) {
+      const Slot& s = slots[i];
+      if (!s.tag) return missing;
+      if (s.tag == tag && s.len == (uint32_t)n && memcmp(base + s.off, p, n) == 0) return s.value;
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ vocabulary
 struct Vocab {
   std::string blob;
-  std::unordered_map<std::string_view, int64_t> map;     // views into `blob`
+  FlatMap map;                                            // keys live in `blob`
   int64_t size = 0;
   void build(std::vector<std::pair<uint64_t, uint64_t>>& spans) {
     size = (int64_t)spans.size();
-    map.reserve(spans.size() * 2);
+    map.init(reinterpret_cast<const uint8_t*>(blob.data()), spans.size());
     for (int64_t i = 0; i < size; ++i)
-      map.emplace(std::string_view(blob.data() + spans[i].first, spans[i].second), i);       // first occurrence wins
+      if (spans[i].second <= 0xFFFFFFFFull) map.insert(spans[i].first, (uint32_t)spans[i].second, i);
   }
-  int64_t find(const uint8_t* p, uint64_t n) const {
-    auto it = map.find(std::string_view(reinterpret_cast<const char*>(p), n));
-    return it == map.end() ? -1 : it->second;
-  }
+  int64_t find(const uint8_t* p, uint64_t n) const { return map.find(p, n, -1); }
 };
 
 // ------------------------------------------------------------------------------------------------ protobuf wire helpers
@@ -163,21 +223,31 @@ struct RecordView {                  // the final Feature bytes of every spec ke
   std::vector<char> has_ctx;
   std::vector<Span> flist;           // per spec key: FeatureList bytes (only when read_feature_lists)
   std::vector<char> has_fl;
+  // Writers emit the keys of every record in the same order: the j-th map entry of this record is most likely the key the j-th
+  // entry of the previous record was.  Remember that key's bytes (they stay valid: they point into the caller's buffer) and what it
+  // resolved to, so that a match costs one memcmp instead of a hash + probe.  Two maps (context, feature_lists), numbered apart.
+  struct Hint { Span key; int index; };
+  std::vector<Hint> hints[2];
 };
 
 struct Parser {
   const std::vector<KeySpec>& keys;
-  std::unordered_map<std::string_view, int> index;
+  std::string key_bytes;             // the spec keys back to back: FlatMap does not own its keys
+  FlatMap index;
   bool read_fl;
   Parser(const std::vector<KeySpec>& k, bool fl) : keys(k), read_fl(fl) {
-    for (int i = 0; i < (int)k.size(); ++i) index.emplace(k[i].key, i);
+    std::vector<uint64_t> at;
+    for (const KeySpec& ks : k) { at.push_back(key_bytes.size()); key_bytes.append(ks.key.data(), ks.key.size()); }
+    index.init(reinterpret_cast<const uint8_t*>(key_bytes.data()), k.size());
+    for (int i = 0; i < (int)k.size(); ++i) index.insert(at[i], (uint32_t)k[i].key.size(), i);
   }
 
   // map<string, X> entries of `msg` (field 1 = entry{key=1, value=2}); records the value span of every spec key
-  bool scan_map(Span msg, std::vector<Span>& out, std::vector<char>& has) const {
+  bool scan_map(Span msg, std::vector<Span>& out, std::vector<char>& has, std::vector<RecordView::Hint>& hints) const {
     const uint8_t* p = msg.p;
     const uint8_t* end = msg.p + msg.n;
     uint32_t f, wt; Span pl; uint64_t v;
+    size_t j = 0;
     while (p < end) {
       if (!next_field(p, end, f, wt, pl, v)) return false;
       if (f != 1 || wt != 2) continue;
@@ -190,8 +260,17 @@ struct Parser {
         if (wt2 == 2 && f2 == 1) key = pl2;
         else if (wt2 == 2 && f2 == 2) val = pl2;
       }
-      auto it = index.find(std::string_view(reinterpret_cast<const char*>(key.p), key.n));
-      if (it != index.end()) { out[it->second] = val; has[it->second] = 1; }
+      int idx;
+      if (j < hints.size() && hints[j].key.n == key.n && (key.n == 0 || memcmp(hints[j].key.p, key.p, key.n) == 0)) {
+        idx = hints[j].index;
+        hints[j].key = key;                                  // keep pointing at recent bytes (warm cache lines)
+      } else {
+        idx = (int)index.find(key.p, key.n, -1);
+        if (j < hints.size()) hints[j] = {key, idx};
+        else if (j == hints.size() && j < 256) hints.push_back({key, idx});
+      }
+      ++j;
+      if (idx >= 0) { out[idx] = val; has[idx] = 1; }
     }
     return true;
   }
@@ -207,9 +286,9 @@ struct Parser {
       if (!next_field(p, end, f, wt, pl, v)) return false;
       if (wt != 2) continue;
       if (f == 1) {                          // Example.features == SequenceExample.context
-        if (!scan_map(pl, rv.ctx, rv.has_ctx)) return false;
+        if (!scan_map(pl, rv.ctx, rv.has_ctx, rv.hints[0])) return false;
       } else if (f == 2 && read_fl) {        // SequenceExample.feature_lists (unknown field 2 when parsed as an Example)
-        if (!scan_map(pl, rv.flist, rv.has_fl)) return false;
+        if (!scan_map(pl, rv.flist, rv.has_fl, rv.hints[1])) return false;
       }
     }
     return true;
@@ -467,17 +546,24 @@ int ctr_feed_parse_examples(const uint8_t* buf, const uint64_t* offsets, const u
   nt = std::max(1, std::min({nt, 32, (int)std::max<int64_t>(1, B / 64)}));
   const Parser parser(keys, read_feature_lists != 0);
 
-  // pass 1: values per (categorical key, record) -> row_offsets; dense keys are final after this pass
-  int rc = run_chunks(B, nt, [&](int, int64_t b0, int64_t b1) -> int {
+  // One parse per record.  Every thread owns a contiguous run of records: it writes the dense outputs and the per-record value
+  // counts in place and collects the vocabulary ids of its run per categorical key; after the prefix sum over the counts a run's
+  // ids are one contiguous range of the output and are copied there (8 bytes per value -- the wire parse is not repeated).
+  std::vector<std::vector<std::vector<int64_t>>> local((size_t)nt, std::vector<std::vector<int64_t>>((size_t)n_cat));
+  int rc = run_chunks(B, nt, [&](int t, int64_t b0, int64_t b1) -> int {
     RecordView rv;
+    for (int64_t k = 0; k < n_cat; ++k) local[t][k].reserve((size_t)(b1 - b0) + 16);
     for (int64_t b = b0; b < b1; ++b) {
       if (!parser.view(Span{buf + offsets[b], lengths[b]}, rv)) return fail(CTR_FEED_ERR_PROTO, "Could not parse example input, record %lld", (long long)b);
       for (size_t i = 0; i < keys.size(); ++i) {
         if (keys[i].is_cat) {
-          int64_t cnt = 0;
-          int r = cat_values(rv, (int)i, read_feature_lists != 0, cats[keys[i].index].key, [&](const uint8_t*, uint64_t) { ++cnt; });
+          const ctr_feed_cat_t& c = cats[keys[i].index];
+          const Vocab* v = static_cast<const Vocab*>(c.vocab);
+          std::vector<int64_t>& dst = local[t][keys[i].index];
+          const size_t before = dst.size();
+          int r = cat_values(rv, (int)i, read_feature_lists != 0, c.key, [&](const uint8_t* p, uint64_t n) { dst.push_back(v->find(p, n)); });
           if (r) return r;
-          cats[keys[i].index].row_offsets[b + 1] = cnt;
+          c.row_offsets[b + 1] = (int64_t)(dst.size() - before);
         } else {
           int r = dense_values(rv, (int)i, dense[keys[i].index], b);
           if (r) return r;
@@ -497,21 +583,9 @@ int ctr_feed_parse_examples(const uint8_t* buf, const uint64_t* offsets, const u
   }
   if (short_buf) return fail(CTR_FEED_ERR_CAPACITY, "ctr_feed_parse_examples: an ids buffer is too small (see `needed`)");
   if (n_cat == 0) return CTR_FEED_OK;
-
-  // pass 2: vocabulary ids at their final positions
-  return run_chunks(B, nt, [&](int, int64_t b0, int64_t b1) -> int {
-    RecordView rv;
-    for (int64_t b = b0; b < b1; ++b) {
-      if (!parser.view(Span{buf + offsets[b], lengths[b]}, rv)) return fail(CTR_FEED_ERR_PROTO, "Could not parse example input, record %lld", (long long)b);
-      for (size_t i = 0; i < keys.size(); ++i) {
-        if (!keys[i].is_cat) continue;
-        const ctr_feed_cat_t& c = cats[keys[i].index];
-        const Vocab* v = static_cast<const Vocab*>(c.vocab);
-        int64_t* dst = c.ids + c.row_offsets[b];
-        int r = cat_values(rv, (int)i, read_feature_lists != 0, c.key, [&](const uint8_t* p, uint64_t n) { *dst++ = v->find(p, n); });
-        if (r) return r;
-      }
-    }
+  return run_chunks(B, nt, [&](int t, int64_t b0, int64_t) -> int {
+    for (int64_t k = 0; k < n_cat; ++k)
+      if (!local[t][k].empty()) memcpy(cats[k].ids + cats[k].row_offsets[b0], local[t][k].data(), local[t][k].size() * sizeof(int64_t));
     return CTR_FEED_OK;
   });
 }
