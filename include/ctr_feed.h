@@ -40,6 +40,13 @@ uint32_t ctr_feed_masked_crc32c(const uint8_t* data, uint64_t n);
  * *consumed (nullable) = bytes of complete records read. */
 int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, uint64_t* offsets, uint64_t* lengths,
                                 int64_t max_records, uint64_t* consumed);
+/* The same scan resumed at byte `start` of buf (offsets stay relative to buf, error texts name absolute byte positions): lets a
+ * reader index a file chunk by chunk while the chunks behind are already being parsed.  allow_partial_tail = 1: an incomplete
+ * last record is not an error -- the scan stops in front of it (buf[0, n) is a prefix of a file that is still being read).
+ * On an error return *consumed is the byte at which the damaged record starts (everything in front of it is intact: scanning
+ * buf[0, *consumed) again succeeds and yields the records before the damage). */
+int64_t ctr_feed_tfrecord_index_from(const uint8_t* buf, uint64_t n, uint64_t start, int verify_crc, int allow_partial_tail,
+                                     uint64_t* offsets, uint64_t* lengths, int64_t max_records, uint64_t* consumed);
 /* verify_crc: 0 = none, 1 = length and payload CRCs inside the (sequential) scan, 2 = length CRCs only -- the scan needs those
  * to trust the lengths; the payload CRCs are then checked by ctr_feed_tfrecord_verify on `num_threads` threads (0 = all cores):
  * CTR_FEED_OK, or CTR_FEED_ERR_CRC naming the first corrupted record. */
@@ -52,6 +59,15 @@ int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* off
  * draws, so the order is a pure function of them (input_fn.shuffle_order feeds numpy's seeded generator).
  * buffer_size <= 1: identity; buffer_size >= n: still the buffer walk (a uniform permutation).  out: (n,) int64. */
 int ctr_feed_shuffle_order(int64_t n, int64_t buffer_size, const double* draws, int64_t* out);
+/* The same walk, resumable, for an input whose length is not known yet (a file that is still being indexed): emit as many
+ * positions as the input seen so far allows.  n_available = inputs known to exist, input_done = 1 once that is all of them.
+ * Nothing is emitted before the buffer is full (or the input done); after that an emission stops short only when it would
+ * have to know whether input `next` exists and cannot.  One draw per emission, consumed in order: the result is the order
+ * ctr_feed_shuffle_order gives for the same draws, however the calls are cut.  Returns the number emitted (<= max_out). */
+void* ctr_feed_shuffle_create(int64_t buffer_size);
+void ctr_feed_shuffle_destroy(void* shuffle);
+int64_t ctr_feed_shuffle_emit(void* shuffle, int64_t n_available, int input_done, const double* draws, int64_t max_out,
+                              int64_t* out);
 
 /* Vocabulary: token i = blob[offsets[i], offsets[i+1]); id = index of the FIRST occurrence of a token. */
 void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens);

@@ -369,6 +369,34 @@ inline int dense_values(const RecordView& rv, int k, const ctr_feed_dense_t& d, 
   return CTR_FEED_OK;
 }
 
+// dataset.shuffle(buffer_size): the buffer holds input positions; `next` is the first position that has not entered it yet.
+struct ShuffleState {
+  std::vector<int64_t> slots;
+  int64_t cap, filled = 0, next = 0;
+  bool started = false;                                    // emission begins once the buffer is full or the input is done
+  explicit ShuffleState(int64_t capacity) : cap(capacity) {}
+  int64_t emit(int64_t n_available, bool done, const double* draws, int64_t max_out, int64_t* out) {
+    if (!started) {
+      if (slots.size() < (size_t)std::min(cap, n_available)) slots.resize((size_t)std::min(cap, n_available));
+      while (filled < cap && next < n_available) slots[filled++] = next++;
+      if (filled < cap && !done) return 0;
+      started = true;
+    }
+    int64_t k = 0;
+    while (k < max_out && filled > 0) {
+      const bool more = next < n_available;
+      if (!more && !done) break;                           // cannot tell yet whether position `next` exists
+      const double u = draws[k];
+      if (!(u >= 0.0 && u < 1.0)) return fail(CTR_FEED_ERR_ARG, "shuffle: draw %lld of this call is outside [0,1)", (long long)k);
+      const int64_t j = std::min<int64_t>((int64_t)(u * (double)filled), filled - 1);
+      out[k++] = slots[j];
+      if (more) slots[j] = next++;
+      else slots[j] = slots[--filled];
+    }
+    return k;
+  }
+};
+
 template <typename Fn>
 int run_chunks(int64_t B, int nthreads, Fn&& fn) {              // fn(thread, b0, b1) -> rc; first error wins
   std::vector<int> rcs(nthreads, CTR_FEED_OK);
@@ -398,23 +426,29 @@ int ctr_feed_version(void) { return 1; }
 uint32_t ctr_feed_crc32c(const uint8_t* data, uint64_t n) { return (data || n == 0) ? crc32c(data, n) : 0; }
 uint32_t ctr_feed_masked_crc32c(const uint8_t* data, uint64_t n) { return masked(ctr_feed_crc32c(data, n)); }
 
-int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, uint64_t* offsets, uint64_t* lengths,
-                                int64_t max_records, uint64_t* consumed) {
-  if ((!buf && n) || max_records < 0 || (max_records > 0 && (!offsets || !lengths)))
+int64_t ctr_feed_tfrecord_index_from(const uint8_t* buf, uint64_t n, uint64_t start, int verify_crc, int allow_partial_tail,
+                                     uint64_t* offsets, uint64_t* lengths, int64_t max_records, uint64_t* consumed) {
+  if ((!buf && n) || start > n || max_records < 0 || (max_records > 0 && (!offsets || !lengths)))
     return fail(CTR_FEED_ERR_ARG, "ctr_feed_tfrecord_index: bad arguments");
-  uint64_t pos = 0;
+  uint64_t pos = start;
   int64_t count = 0;
   while (pos < n) {
+    if (consumed) *consumed = pos;                         // also on an error return: the damaged record starts here
     if (max_records > 0 && count == max_records) break;
-    if (n - pos < 12) return fail(CTR_FEED_ERR_TRUNCATED, "truncated record header at byte %llu", (unsigned long long)pos);
+    if (n - pos < 12) {
+      if (allow_partial_tail) break;
+      return fail(CTR_FEED_ERR_TRUNCATED, "truncated record header at byte %llu", (unsigned long long)pos);
+    }
     uint64_t len;
     uint32_t len_crc;
     memcpy(&len, buf + pos, 8);
     memcpy(&len_crc, buf + pos + 8, 4);
     if (verify_crc && masked(crc32c(buf + pos, 8)) != len_crc)
       return fail(CTR_FEED_ERR_CRC, "corrupted record length at byte %llu (crc mismatch)", (unsigned long long)pos);
-    if (len > n - pos - 12 || n - pos - 12 - len < 4)
+    if (len > n - pos - 12 || n - pos - 12 - len < 4) {
+      if (allow_partial_tail) break;
       return fail(CTR_FEED_ERR_TRUNCATED, "truncated record at byte %llu", (unsigned long long)pos);
+    }
     const uint8_t* data = buf + pos + 12;
     uint32_t data_crc;
     memcpy(&data_crc, data + len, 4);
@@ -427,6 +461,11 @@ int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, 
   }
   if (consumed) *consumed = pos;
   return count;
+}
+
+int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, uint64_t* offsets, uint64_t* lengths,
+                                int64_t max_records, uint64_t* consumed) {
+  return ctr_feed_tfrecord_index_from(buf, n, 0, verify_crc, 0, offsets, lengths, max_records, consumed);
 }
 
 int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* offsets, const uint64_t* lengths, int64_t count,
@@ -458,19 +497,18 @@ int ctr_feed_shuffle_order(int64_t n, int64_t buffer_size, const double* draws, 
     return CTR_FEED_OK;
   }
   if (!draws) return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_order: draws is null");
-  const int64_t cap = std::min(buffer_size, n);
-  std::vector<int64_t> slots((size_t)cap);
-  for (int64_t i = 0; i < cap; ++i) slots[i] = i;
-  int64_t next = cap, filled = cap;
-  for (int64_t i = 0; i < n; ++i) {
-    const double u = draws[i];
-    if (!(u >= 0.0 && u < 1.0)) return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_order: draws[%lld] is outside [0,1)", (long long)i);
-    const int64_t j = std::min<int64_t>((int64_t)(u * (double)filled), filled - 1);
-    out[i] = slots[j];
-    if (next < n) slots[j] = next++;
-    else slots[j] = slots[--filled];
-  }
-  return CTR_FEED_OK;
+  ShuffleState st(std::min(buffer_size, n));
+  const int64_t got = st.emit(n, true, draws, n, out);
+  return got == n ? CTR_FEED_OK : (int)got;               // a negative `got` is the error code (draw outside [0,1))
+}
+
+void* ctr_feed_shuffle_create(int64_t buffer_size) { return new ShuffleState(std::max<int64_t>(1, buffer_size)); }
+void ctr_feed_shuffle_destroy(void* shuffle) { delete static_cast<ShuffleState*>(shuffle); }
+int64_t ctr_feed_shuffle_emit(void* shuffle, int64_t n_available, int input_done, const double* draws, int64_t max_out,
+                              int64_t* out) {
+  if (!shuffle || n_available < 0 || max_out < 0 || (max_out > 0 && (!out || !draws)))
+    return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_emit: bad arguments");
+  return static_cast<ShuffleState*>(shuffle)->emit(n_available, input_done != 0, draws, max_out, out);
 }
 
 void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens) {

@@ -34,34 +34,110 @@ def make_example_parser(feature_columns, label_keys: Sequence[str] = ("read_comm
     return example_parser
 
 
-def _load(filepath: Union[str, Sequence[str]], mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Read (or map) the file(s) and index their records in one sequential scan that checks the length CRCs; the payload CRCs
-    are checked per batch in `_batches` (inside the prefetch thread), so a corrupted record raises when its batch is produced --
-    like TFRecordDataset's DataLossError -- and the CRC pass overlaps the consumer instead of delaying the first batch.
-    mmap=True maps the file(s) instead of reading them into RAM (a single file stays mapped; several files are concatenated,
-    which materialises them)."""
+class _LoadedIndex:
+    """Same face as native.StreamingIndex for records that are already indexed (several files, concatenated)."""
+
+    def __init__(self, buf, off, ln):
+        self.buf, self.off, self.ln, self.n, self.done, self.capacity = buf, off, ln, int(off.size), True, int(off.size)
+
+    def wait_for(self, count):
+        return self.n, True
+
+    def wait_all(self):
+        return self.n
+
+    failed = False
+
+    def check(self):
+        pass
+
+    def close(self):
+        pass
+
+
+def _open(filepath: Union[str, Sequence[str]], mmap: bool = False):
+    """TFRecordDataset(filepath).  One file (the reference's case, utils.py:18): a native.StreamingIndex -- the file is read (or
+    mapped) and indexed by a background thread while the first batches are already being parsed.  Several files are read one
+    after the other (TFRecordDataset([files]) order) and concatenated, which materialises them.  Length CRCs are checked by the
+    index scan, payload CRCs per batch in `_batches` (inside the prefetch thread): a corrupted record raises when the batch that
+    holds it is produced -- TFRecordDataset's DataLossError timing -- and the CRC pass overlaps the consumer."""
     paths = [filepath] if isinstance(filepath, str) else list(filepath)
+    if len(paths) == 1:
+        return native.StreamingIndex(paths[0], mmap=mmap)
     bufs, offs, lens, base = [], [], [], 0
-    for p in paths:                                           # TFRecordDataset([files]) reads them one after the other
+    for p in paths:
         b, o, l = native.read_tfrecord_file(p, verify="headers", mmap=mmap)
         bufs.append(b); offs.append(o + np.uint64(base)); lens.append(l)
         base += b.size
-    return (bufs[0] if len(bufs) == 1 else np.concatenate(bufs)), np.concatenate(offs), np.concatenate(lens)
+    return _LoadedIndex(np.concatenate(bufs), np.concatenate(offs), np.concatenate(lens))
+
+
+def _load(filepath: Union[str, Sequence[str]], mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(file bytes, offsets, lengths) of all records, complete (blocks until the index is)."""
+    ix = _open(filepath, mmap)
+    n = ix.wait_all()
+    return ix.buf, ix.off[:n], ix.ln[:n]
 
 
 def shuffle_order(n: int, buffer_size: int, rng: np.random.Generator) -> np.ndarray:
     """Order in which dataset.shuffle(buffer_size) emits n elements: a buffer of the next `buffer_size` elements, one of them
-    drawn uniformly at each step and replaced by the next input element (tf.data semantics; buffer >= n = full shuffle)."""
+    drawn uniformly at each step and replaced by the next input element (tf.data semantics; buffer >= n = a uniform permutation).
+    The walk is native (ctr_feed_shuffle_order: a Python loop costs ~0.7 us per record, more than parsing the record); the n
+    draws come from the seeded numpy generator, so the order is reproducible per seed."""
     if buffer_size <= 1 or n <= 1:
         return np.arange(n, dtype=np.int64)
-    if buffer_size >= n:
-        return rng.permutation(n).astype(np.int64)
-    # the buffer walk itself is native (ctr_feed_shuffle_order; a Python loop costs ~0.7 us per record, i.e. more than parsing
-    # the record); the draws come from the seeded numpy generator, so the order is reproducible per seed
     return native.shuffle_order(n, buffer_size, rng.random(n))
 
 
-def _prefetch(gen: Iterator, depth: int = 1) -> Iterator:
+class _Draws:
+    """The generator's uniform draws as ONE stream, one draw per shuffled element, whatever the block sizes they are fetched in
+    (numpy's Generator.random(a) followed by random(b) is random(a + b)): a streamed epoch, whose block sizes depend on timing,
+    consumes exactly the draws shuffle_order would."""
+
+    def __init__(self, rng: np.random.Generator):
+        self.rng, self.buf = rng, np.empty(0, np.float64)
+
+    def peek(self, k: int) -> np.ndarray:
+        if self.buf.size < k:
+            self.buf = np.concatenate([self.buf, self.rng.random(max(k - self.buf.size, 1 << 16))])
+        return self.buf[:k]
+
+    def consume(self, k: int):
+        self.buf = self.buf[k:]
+
+
+def _order_pieces(index, shuffle_buffer_size: int, draws: Optional[_Draws], rounds, piece: int) -> Iterator[np.ndarray]:
+    """shuffle(buffer).repeat(rounds) as a stream of index arrays.  While the file is still being indexed (first epoch) the
+    pieces follow the index: element i of the shuffled order only needs inputs up to i + buffer_size."""
+    shuffled = shuffle_buffer_size > 1
+    for _ in rounds:
+        if index.done and not index.failed:                       # (a failed scan takes the streamed path: it delivers the
+            n = index.wait_all()                                   # records in front of the damage, then raises)
+            if shuffled and n > 1:
+                order = native.shuffle_order(n, shuffle_buffer_size, draws.peek(n)); draws.consume(n)
+            else:
+                order = np.arange(n, dtype=np.int64)
+            yield order
+            continue
+        emitted = 0
+        sh = native.Shuffler(shuffle_buffer_size) if shuffled else None
+        while True:
+            want = emitted + piece + (shuffle_buffer_size if shuffled else 0)
+            avail, done = index.wait_for(want)
+            if shuffled:
+                idx = sh.emit(avail, done, draws.peek(piece), piece)
+                draws.consume(idx.size)
+            else:
+                idx = np.arange(emitted, min(avail, emitted + piece), dtype=np.int64)
+            if idx.size:
+                emitted += idx.size
+                yield idx
+            elif done:
+                index.check()                                      # a corrupted length / truncated file ends the epoch with its error
+                break
+
+
+def _prefetch(gen: Iterator, depth: int = 1, on_close: Optional[Callable[[], None]] = None) -> Iterator:
     """dataset.prefetch(depth): a producer thread keeps `depth` parsed batches ahead of the consumer."""
     q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
     stop = threading.Event()
@@ -94,11 +170,13 @@ def _prefetch(gen: Iterator, depth: int = 1) -> Iterator:
             yield item
     finally:
         stop.set()
+        if on_close is not None:
+            on_close()
 
 
-def _batches(order_epochs: Iterator[np.ndarray], data, batch_size: int, parser) -> Iterator:
-    buf, off, ln = data
-    verified = np.zeros(off.size, dtype=bool)                # payload CRCs are checked the first time a record is used
+def _batches(order_pieces: Iterator[np.ndarray], index, batch_size: int, parser) -> Iterator:
+    buf, off, ln = index.buf, index.off, index.ln            # off / ln are valid for every position an order piece names
+    verified = np.zeros(index.capacity, dtype=bool)          # payload CRCs are checked the first time a record is used
 
     def parse(idx):
         o, l = off[idx], ln[idx]
@@ -110,7 +188,7 @@ def _batches(order_epochs: Iterator[np.ndarray], data, batch_size: int, parser) 
 
     pending: List[np.ndarray] = []
     have = 0
-    for order in order_epochs:                               # repeat() happens BEFORE batch(): batches run across epoch borders
+    for order in order_pieces:                               # repeat() happens BEFORE batch(): batches run across epoch borders
         pending.append(order); have += order.size
         while have >= batch_size:
             idx = np.concatenate(pending) if len(pending) > 1 else pending[0]
@@ -126,21 +204,19 @@ def train_input_fn(filepath, example_parser, batch_size: int, num_epochs: Option
                    seed: Optional[int] = None, mmap: bool = False) -> Iterator[Tuple[dict, dict]]:
     """utils.py:4-26.  Iterating the result is `dataset.make_one_shot_iterator()`; each epoch is reshuffled
     (tf.data's reshuffle_each_iteration default).  mmap=True maps the TFRecord file instead of reading it into RAM."""
-    data = _load(filepath, mmap=mmap)
-    n = int(data[1].size)
-    rng = np.random.default_rng(seed)
+    index = _open(filepath, mmap=mmap)
     import itertools
     # num_epochs=None repeats forever, like dataset.repeat(None) (Estimator callers bound the run with max_steps)
     rounds = itertools.count() if num_epochs is None else range(num_epochs)
-    epochs = (shuffle_order(n, shuffle_buffer_size, rng) if shuffle_buffer_size > 0 else np.arange(n, dtype=np.int64)
-              for _ in rounds)
-    return _prefetch(_batches(epochs, data, batch_size, example_parser), depth=1)
+    pieces = _order_pieces(index, shuffle_buffer_size, _Draws(np.random.default_rng(seed)), rounds, max(batch_size, 1 << 13))
+    return _prefetch(_batches(pieces, index, batch_size, example_parser), depth=1, on_close=index.close)
 
 
 def eval_input_fn(filepath, example_parser, batch_size: int, mmap: bool = False) -> Iterator[Tuple[dict, dict]]:
     """utils.py:29-47: one pass, file order, no shuffle."""
-    data = _load(filepath, mmap=mmap)
-    return _prefetch(_batches(iter([np.arange(int(data[1].size), dtype=np.int64)]), data, batch_size, example_parser), depth=1)
+    index = _open(filepath, mmap=mmap)
+    pieces = _order_pieces(index, 0, None, range(1), max(batch_size, 1 << 13))
+    return _prefetch(_batches(pieces, index, batch_size, example_parser), depth=1, on_close=index.close)
 
 
 class DevicePrefetcher:

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from typing import Dict, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -38,8 +39,12 @@ SIGNATURES = {
     "ctr_feed_crc32c": (ctypes.c_uint32, [_P, ctypes.c_uint64]),
     "ctr_feed_masked_crc32c": (ctypes.c_uint32, [_P, ctypes.c_uint64]),
     "ctr_feed_tfrecord_index": (_I, [_P, ctypes.c_uint64, ctypes.c_int, _P, _P, _I, _P]),
+    "ctr_feed_tfrecord_index_from": (_I, [_P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _P, _P, _I, _P]),
     "ctr_feed_tfrecord_verify": (ctypes.c_int, [_P, ctypes.c_uint64, _P, _P, _I, ctypes.c_int]),
     "ctr_feed_shuffle_order": (ctypes.c_int, [_I, _I, _P, _P]),
+    "ctr_feed_shuffle_create": (_P, [_I]),
+    "ctr_feed_shuffle_destroy": (None, [_P]),
+    "ctr_feed_shuffle_emit": (_I, [_P, _I, ctypes.c_int, _P, _I, _P]),
     "ctr_feed_vocab_create": (_P, [_P, _P, _I]),
     "ctr_feed_vocab_load": (_P, [ctypes.c_char_p]),
     "ctr_feed_vocab_size": (_I, [_P]),
@@ -155,6 +160,124 @@ def shuffle_order(n: int, buffer_size: int, draws: np.ndarray) -> np.ndarray:
     if rc < 0:
         _raise(int(rc))
     return out
+
+
+class Shuffler:
+    """dataset.shuffle(buffer_size) over an input whose length is not known yet (ctr_feed_shuffle_create / _emit): positions
+    come out as far as the input seen so far allows, one caller-supplied draw per emission, in the order
+    shuffle_order(n, buffer_size, draws) gives for the same draws however the calls are cut."""
+
+    def __init__(self, buffer_size: int):
+        self._h = lib().ctr_feed_shuffle_create(int(buffer_size))
+        if not self._h:
+            raise FeedError(ERR_ARG)
+
+    def emit(self, n_available: int, input_done: bool, draws: np.ndarray, max_out: int) -> np.ndarray:
+        """Up to max_out positions; draws[:len(result)] are consumed."""
+        draws = np.ascontiguousarray(draws, dtype=np.float64)
+        max_out = min(int(max_out), int(draws.size))
+        out = np.empty(max_out, np.int64)
+        k = int(lib().ctr_feed_shuffle_emit(self._h, int(n_available), int(bool(input_done)), draws.ctypes.data, max_out,
+                                            out.ctypes.data))
+        if k < 0:
+            _raise(k)
+        return out[:k]
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ctr_feed_shuffle_destroy(self._h)
+            self._h = None
+
+
+class StreamingIndex:
+    """The records of ONE TFRecord file, indexed by a background thread while the consumer already parses the front of it:
+    `off[:n]` / `ln[:n]` are valid for the `n` that `wait_for` returns.  mmap=False reads the file in `chunk_bytes` pieces into
+    one buffer and indexes each piece as it arrives (read, scan and parse overlap); mmap=True maps it and scans it in runs of
+    `chunk_records`.  Length CRCs are checked by the scan, payload CRCs by the consumer (verify_records) -- a corrupted or
+    truncated record raises when the consumer asks for records at or beyond it, like TFRecordDataset's DataLossError."""
+
+    def __init__(self, path: str, mmap: bool = False, chunk_bytes: int = 32 << 20, chunk_records: int = 1 << 16):
+        size = os.path.getsize(path)
+        self.path, self.size = path, size
+        self.capacity = size // 16 + 1                            # header 12 + footer 4 bytes: no record is shorter
+        self.off, self.ln = np.empty(self.capacity, np.uint64), np.empty(self.capacity, np.uint64)   # pages commit when touched
+        self.buf = (np.memmap(path, dtype=np.uint8, mode="r") if mmap and size > 0 else np.empty(size, np.uint8))
+        self._mmap, self._chunk_bytes, self._chunk_records = bool(mmap and size > 0), int(chunk_bytes), int(chunk_records)
+        self.n, self.done, self._error, self._stop = 0, False, None, False
+        self._cv = threading.Condition()
+        self._thread = threading.Thread(target=self._run, daemon=True, name="ctr-feed-index")
+        self._thread.start()
+
+    def _scan(self, have: int, pos: int, final: bool) -> int:
+        """Index buf[pos:have); returns the new scan position."""
+        L = lib()
+        consumed = ctypes.c_uint64(pos)
+        while pos < have and not self._stop:
+            n = self.n
+            k = L.ctr_feed_tfrecord_index_from(self.buf.ctypes.data, have, pos, 2, 0 if final else 1,
+                                               self.off[n:].ctypes.data, self.ln[n:].ctypes.data,
+                                               min(self._chunk_records, self.capacity - n), ctypes.byref(consumed))
+            if k < 0:                                             # damaged record at byte consumed.value: keep what lies in front
+                try:
+                    _raise(int(k))
+                except FeedError as e:
+                    good = L.ctr_feed_tfrecord_index_from(self.buf.ctypes.data, consumed.value, pos, 2, 0,
+                                                          self.off[n:].ctypes.data, self.ln[n:].ctypes.data, self.capacity - n, None)
+                    with self._cv:
+                        self.n = n + max(0, int(good))
+                    raise e
+            if k == 0 and consumed.value == pos:
+                break                                             # an incomplete tail: wait for more bytes
+            pos = int(consumed.value)
+            with self._cv:
+                self.n = n + int(k)
+                self._cv.notify_all()
+        return pos
+
+    def _run(self):
+        try:
+            if self._mmap or self.size == 0:
+                self._scan(self.size, 0, True)
+            else:
+                have = pos = 0
+                with open(self.path, "rb", buffering=0) as f:
+                    while have < self.size and not self._stop:
+                        got = f.readinto(memoryview(self.buf)[have:have + self._chunk_bytes])
+                        if not got:
+                            raise IOError(f"{self.path}: file ended at byte {have} of {self.size} while being read")
+                        have += got
+                        pos = self._scan(have, pos, have >= self.size)
+        except BaseException as e:                                # surfaces in the consumer (wait_for)
+            self._error = e
+        finally:
+            with self._cv:
+                self.done = True
+                self._cv.notify_all()
+
+    def wait_for(self, count: int) -> Tuple[int, bool]:
+        """Block until `count` records are indexed or the scan has ended; returns (records indexed so far, ended).  Does not
+        raise: the records in front of a corrupted one are still delivered -- call check() once they are used up."""
+        with self._cv:
+            while self.n < count and not self.done:
+                self._cv.wait()
+            return self.n, self.done
+
+    @property
+    def failed(self) -> bool:
+        return self._error is not None
+
+    def check(self):
+        """Raise the error that ended the scan early, if any (corrupted length, truncated file)."""
+        if self._error is not None:
+            raise self._error
+
+    def wait_all(self) -> int:
+        n, _ = self.wait_for(self.capacity + 1)
+        self.check()
+        return n
+
+    def close(self):
+        self._stop = True
 
 
 def read_tfrecord_file(path: str, verify=True, mmap: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

@@ -102,7 +102,8 @@ def test_mmap_reads_the_same_batches(dataset):
 
 def test_corrupted_payload_raises_when_its_batch_is_produced(dataset, tmp_path):
     """Payload CRCs are verified per batch inside the prefetch thread (DataLossError-like timing): the batches before the
-    corrupted record arrive, the one that contains it raises; a corrupted LENGTH already fails at open time."""
+    corrupted record arrive, the one that contains it raises; a corrupted LENGTH stops the background index scan there, and the
+    batches in front of it still arrive."""
     from recalgorithm_b200.io import native
     p, n, parser = dataset
     raw = bytearray(open(p, "rb").read())
@@ -116,8 +117,17 @@ def test_corrupted_payload_raises_when_its_batch_is_produced(dataset, tmp_path):
         next(it)
     hdr = bytearray(raw); hdr[int(off[5]) - 12] ^= 1
     r = str(tmp_path / "badlen.tfrecord"); open(r, "wb").write(hdr)
+    it = I.eval_input_fn(r, parser, batch_size=2)
+    assert _ids([next(it), next(it)]).tolist() == [0, 1, 2, 3]        # record 5 has the bad length: 0..3 fill two batches
+    with pytest.raises(IOError, match="corrupted record length"):
+        next(it)
     with pytest.raises(IOError):
-        I.eval_input_fn(r, parser, batch_size=16)
+        next(I.eval_input_fn(r, parser, batch_size=16))                 # the first batch already needs record 5
+    cut = str(tmp_path / "cut.tfrecord"); open(cut, "wb").write(bytes(raw[:int(off[40]) + 3]))   # file ends inside record 40
+    it = I.train_input_fn(cut, parser, batch_size=8, num_epochs=2, shuffle_buffer_size=0)
+    assert _ids([next(it) for _ in range(5)]).tolist() == list(range(40))
+    with pytest.raises(IOError, match="truncated"):
+        next(it)
 
 
 def _shuffle_order_py(n, buffer_size, draws):
@@ -169,3 +179,64 @@ def test_pad_ragged_is_the_row_by_row_copy():
         fc.pad_ragged(np.arange(3), np.array([0, 3]), 2)
     # offsets that do not start at 0 (a slice of a larger ragged array)
     assert fc.pad_ragged(np.arange(10), np.array([4, 6, 6, 9]), 3).tolist() == [[4, 5, -1], [-1, -1, -1], [6, 7, 8]]
+
+
+def test_resumable_shuffle_equals_the_one_shot_walk_however_the_calls_are_cut():
+    from recalgorithm_b200.io import native
+    rng = np.random.default_rng(9)
+    for n, bs in [(1, 5), (7, 3), (500, 50), (500, 500), (500, 9000), (20_000, 1000)]:
+        draws = rng.random(n)
+        want = native.shuffle_order(n, bs, draws) if n > 1 else np.zeros(1, np.int64)
+        sh, got, used, avail = native.Shuffler(bs), [], 0, 0
+        while True:                                                   # the input grows in random steps; emission in random bites
+            avail = min(n, avail + int(rng.integers(0, 2 * bs + 3)))
+            done = avail == n and rng.random() < 0.7
+            out = sh.emit(avail, done, draws[used:], int(rng.integers(1, 300)))
+            assert out.size == 0 or out.max() < avail                 # never names an input that has not been seen
+            got.extend(out.tolist()); used += out.size
+            if done and out.size == 0:
+                break
+        assert got == want.tolist() and used == n
+
+
+def test_streaming_index_equals_the_one_shot_index(dataset, tmp_path):
+    from recalgorithm_b200.io import native
+    p, n, parser = dataset
+    buf, off, ln = native.read_tfrecord_file(p)
+    for kw in (dict(chunk_bytes=1), dict(chunk_bytes=37), dict(chunk_bytes=1 << 20), dict(mmap=True, chunk_records=1),
+               dict(mmap=True, chunk_records=7)):
+        ix = native.StreamingIndex(p, **kw)
+        assert ix.wait_all() == n and ix.done and not ix.failed
+        assert np.array_equal(ix.off[:n], off) and np.array_equal(ix.ln[:n], ln) and np.array_equal(np.asarray(ix.buf), buf)
+        got, _ = ix.wait_for(10)
+        assert got == n
+    empty = str(tmp_path / "empty.tfrecord"); open(empty, "wb").close()
+    for mm in (False, True):
+        ix = native.StreamingIndex(empty, mmap=mm)
+        assert ix.wait_all() == 0
+    assert list(I.eval_input_fn(empty, parser, batch_size=4)) == []
+
+
+def test_streamed_first_epoch_is_the_order_of_a_finished_index(dataset, monkeypatch):
+    """The first epoch runs while the file is still being indexed; its order must not depend on how far the index happens to be:
+    same seed -> the same batches as when the index was complete before the first element was asked for."""
+    from recalgorithm_b200.io import native
+    p, n, parser = dataset
+
+    def run(slow):
+        orig = native.StreamingIndex.__init__
+
+        def init(self, path, mmap=False, **kw):
+            orig(self, path, mmap=mmap, chunk_bytes=64 if slow else 1 << 25, chunk_records=3 if slow else 1 << 16)
+            if not slow:
+                self.wait_all()
+        monkeypatch.setattr(native.StreamingIndex, "__init__", init)
+        try:
+            return _ids(list(I.train_input_fn(p, parser, batch_size=16, num_epochs=3, shuffle_buffer_size=10, seed=4))).tolist()
+        finally:
+            monkeypatch.setattr(native.StreamingIndex, "__init__", orig)
+    a, b = run(True), run(False)
+    assert a == b and sorted(a[:n]) == list(range(n)) and a[:n] != list(range(n))
+    for mm in (False, True):
+        e = _ids(list(I.eval_input_fn(p, parser, batch_size=16, mmap=mm))).tolist()
+        assert e == list(range(n))
