@@ -53,3 +53,34 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_every_compute_entry_rejects_null_pointers_with_an_error_string():
+    """All-NULL pointers with plausible and with zero sizes: every kernel entry point returns a negative code and explains
+    itself through ctr_last_error() -- no launch, no crash (this runs without a GPU)."""
+    import ctypes
+    from recalgorithm_b200 import _lib
+    h = _lib.lib()
+    helpers = {"ctr_version", "ctr_last_error", "ctr_kernel_launches", "ctr_device_info", "ctr_enable_peer_access",
+               "ctr_bilinear_set_rr", "ctr_cin_bwd_set_dx_pair", "ctr_cin_fwd_workspace_bytes", "ctr_cin_bwd_workspace_bytes",
+               "ctr_bst_param_count", "ctr_peer_free", "ctr_ipc_close", "ctr_vmm_free", "ctr_vmm_alloc", "ctr_vmm_import",
+               "ctr_vmm_granularity"}
+    checked = 0
+    for name, (res, args) in sorted(_lib.SIGNATURES.items()):
+        if name in helpers:
+            continue
+        for size in (4, 0):
+            vals = []
+            for a in args:
+                if a in (ctypes.c_float, ctypes.c_double):
+                    vals.append(0.0)
+                elif a in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_longlong):
+                    vals.append(size)
+                else:
+                    vals.append(None)                                 # every pointer (and stream) argument
+            rc = getattr(h, name)(*vals)
+            assert isinstance(rc, int) and rc < 0, (name, size, rc)
+            assert rc in (_lib.CTR_ERR_INVALID_ARG, _lib.CTR_ERR_UNSUPPORTED), (name, size, rc)
+            assert h.ctr_last_error().startswith(name.encode()), (name, h.ctr_last_error())
+            checked += 1
+    assert checked >= 2 * 45                                          # 48 compute entry points today
