@@ -260,3 +260,41 @@ def test_parallel_crc_verification_reports_the_first_bad_record(tmp_path):
     hdr = bytearray(raw); hdr[int(off[3000]) - 12] ^= 1              # a corrupted LENGTH is caught by the scan itself
     with pytest.raises(IOError):
         native.index_tfrecord(bytes(hdr), num_threads=8)
+
+
+def test_plain_c_caller_of_the_feeder(tmp_path):
+    """examples/feed_demo.c: the feeder's C ABI used from plain C (no Python in the process that calls it) -- index, CRC pass,
+    vocabulary files, batched parse with the capacity-retry protocol -- against the Python twin."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "recalgorithm_b200", "csrc_feed")
+    exe = str(tmp_path / "feed_demo")
+    subprocess.run(["gcc", "-O2", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "feed_demo.c"), "-o", exe,
+                    "-L", lib_dir, "-lctr_feed", f"-Wl,-rpath,{lib_dir}"], check=True, capture_output=True)
+    rng = np.random.default_rng(4)
+    n = 1500
+    recs = [wechat_record(rng, i)[0] for i in range(n)]
+    path = str(tmp_path / "d.tfrecord")
+    cio.write_records(path, recs)
+    keys = ["userid", "feedid", "bgm_song_id", "manual_tag_list"]               # the last one lives in feature_lists: parses empty
+    vdir = tmp_path / "vocab"; vdir.mkdir()
+    vocabs = {}
+    for k in keys:
+        toks = [f"{k}_{i}".encode() for i in range(40)]
+        (vdir / f"{k}.txt").write_bytes(b"\n".join(toks) + b"\n")
+        vocabs[k] = cio.VocabularyFile(toks)
+    out = subprocess.run([exe, path, str(vdir), "128", *keys], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == f"records {n} vocabulary sizes 40 40 40 40"
+    spec = {k: cio.VarLenFeature("bytes") for k in keys} | {"read_comment": cio.FixedLenFeature((1,), "float", 0.0)}
+    want = cio.parse_example(recs, spec)
+    for k, line in zip(keys, lines[1:]):
+        ids = vocabs[k].lookup(want[k][0]) if len(want[k][0]) else np.zeros(0, np.int64)
+        chk = int(sum((i + 1) * (int(v) + 2) for i, v in enumerate(ids)) % (1 << 64))
+        assert line == f"{k} values {len(ids)} oov {int((ids < 0).sum())} checksum {chk}", (line, k)
+    assert lines[-1] == f"read_comment sum {float(want['read_comment'].sum()):.1f}"
+    bad = bytearray(open(path, "rb").read()); bad[40] ^= 1
+    open(path, "wb").write(bad)
+    out = subprocess.run([exe, path, str(vdir), "128", *keys], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 1 and "crc mismatch" in out.stderr
