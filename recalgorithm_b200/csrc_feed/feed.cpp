@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -416,6 +418,55 @@ int run_chunks(int64_t B, int nthreads, Fn&& fn) {              // fn(thread, b0
   return CTR_FEED_OK;
 }
 
+// Two phases over the same partition with ONE set of threads: every thread runs phase1 on its run of records, the last one to
+// arrive runs `middle` (which needs all of phase 1: prefix sums), then every thread runs phase2 on the same run -- unless phase 1
+// or `middle` failed.  Saves the second round of thread creation, which costs as much as the work itself at 32 threads.
+template <typename F1, typename M, typename F2>
+int run_two_phase(int64_t B, int nthreads, F1&& phase1, M&& middle, F2&& phase2) {
+  std::vector<int> rcs(nthreads, CTR_FEED_OK);
+  std::vector<std::string> msgs(nthreads);
+  std::vector<std::thread> th;
+  const int64_t per = (B + nthreads - 1) / nthreads;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, middle_rc = CTR_FEED_OK;
+  bool released = false;
+  std::string middle_msg;
+  auto body = [&](int t) {
+    const int64_t b0 = t * per, b1 = std::min<int64_t>(B, b0 + per);
+    if (b0 < b1) rcs[t] = phase1(t, b0, b1);
+    if (rcs[t] != CTR_FEED_OK) msgs[t] = g_err;                 // g_err is thread-local: carry the text to the caller
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      if (++arrived == nthreads) {
+        bool ok = true;
+        for (int i = 0; i < nthreads; ++i) ok = ok && rcs[i] == CTR_FEED_OK;
+        if (ok) {
+          middle_rc = middle();
+          if (middle_rc != CTR_FEED_OK) middle_msg = g_err;
+        } else {
+          middle_rc = CTR_FEED_ERR_ARG;                          // placeholder: phase 2 is skipped, phase 1's error is reported
+        }
+        released = true;
+        cv.notify_all();
+      } else {
+        cv.wait(lk, [&] { return released; });
+      }
+    }
+    if (middle_rc == CTR_FEED_OK && b0 < b1) {
+      const int r = phase2(t, b0, b1);
+      if (r != CTR_FEED_OK) { rcs[t] = r; msgs[t] = g_err; }
+    }
+  };
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(body, t);
+  body(0);
+  for (auto& x : th) x.join();
+  for (int t = 0; t < nthreads; ++t)
+    if (rcs[t] != CTR_FEED_OK) return fail(rcs[t], "%s", msgs[t].c_str());
+  if (middle_rc != CTR_FEED_OK) return fail(middle_rc, "%s", middle_msg.c_str());
+  return CTR_FEED_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -588,44 +639,47 @@ int ctr_feed_parse_examples(const uint8_t* buf, const uint64_t* offsets, const u
   // counts in place and collects the vocabulary ids of its run per categorical key; after the prefix sum over the counts a run's
   // ids are one contiguous range of the output and are copied there (8 bytes per value -- the wire parse is not repeated).
   std::vector<std::vector<std::vector<int64_t>>> local((size_t)nt, std::vector<std::vector<int64_t>>((size_t)n_cat));
-  int rc = run_chunks(B, nt, [&](int t, int64_t b0, int64_t b1) -> int {
-    RecordView rv;
-    for (int64_t k = 0; k < n_cat; ++k) local[t][k].reserve((size_t)(b1 - b0) + 16);
-    for (int64_t b = b0; b < b1; ++b) {
-      if (!parser.view(Span{buf + offsets[b], lengths[b]}, rv)) return fail(CTR_FEED_ERR_PROTO, "Could not parse example input, record %lld", (long long)b);
-      for (size_t i = 0; i < keys.size(); ++i) {
-        if (keys[i].is_cat) {
-          const ctr_feed_cat_t& c = cats[keys[i].index];
-          const Vocab* v = static_cast<const Vocab*>(c.vocab);
-          std::vector<int64_t>& dst = local[t][keys[i].index];
-          const size_t before = dst.size();
-          int r = cat_values(rv, (int)i, read_feature_lists != 0, c.key, [&](const uint8_t* p, uint64_t n) { dst.push_back(v->find(p, n)); });
-          if (r) return r;
-          c.row_offsets[b + 1] = (int64_t)(dst.size() - before);
-        } else {
-          int r = dense_values(rv, (int)i, dense[keys[i].index], b);
-          if (r) return r;
+  return run_two_phase(
+      B, nt,
+      [&](int t, int64_t b0, int64_t b1) -> int {
+        RecordView rv;
+        for (int64_t k = 0; k < n_cat; ++k) local[t][k].reserve((size_t)(b1 - b0) + 16);
+        for (int64_t b = b0; b < b1; ++b) {
+          if (!parser.view(Span{buf + offsets[b], lengths[b]}, rv)) return fail(CTR_FEED_ERR_PROTO, "Could not parse example input, record %lld", (long long)b);
+          for (size_t i = 0; i < keys.size(); ++i) {
+            if (keys[i].is_cat) {
+              const ctr_feed_cat_t& c = cats[keys[i].index];
+              const Vocab* v = static_cast<const Vocab*>(c.vocab);
+              std::vector<int64_t>& dst = local[t][keys[i].index];
+              const size_t before = dst.size();
+              int r = cat_values(rv, (int)i, read_feature_lists != 0, c.key, [&](const uint8_t* p, uint64_t n) { dst.push_back(v->find(p, n)); });
+              if (r) return r;
+              c.row_offsets[b + 1] = (int64_t)(dst.size() - before);
+            } else {
+              int r = dense_values(rv, (int)i, dense[keys[i].index], b);
+              if (r) return r;
+            }
+          }
         }
-      }
-    }
-    return CTR_FEED_OK;
-  });
-  if (rc) return rc;
-  bool short_buf = false;
-  for (int64_t k = 0; k < n_cat; ++k) {
-    int64_t* ro = cats[k].row_offsets;
-    ro[0] = 0;
-    for (int64_t b = 0; b < B; ++b) ro[b + 1] += ro[b];
-    cats[k].needed = ro[B];
-    if (ro[B] > cats[k].capacity) short_buf = true;
-  }
-  if (short_buf) return fail(CTR_FEED_ERR_CAPACITY, "ctr_feed_parse_examples: an ids buffer is too small (see `needed`)");
-  if (n_cat == 0) return CTR_FEED_OK;
-  return run_chunks(B, nt, [&](int t, int64_t b0, int64_t) -> int {
-    for (int64_t k = 0; k < n_cat; ++k)
-      if (!local[t][k].empty()) memcpy(cats[k].ids + cats[k].row_offsets[b0], local[t][k].data(), local[t][k].size() * sizeof(int64_t));
-    return CTR_FEED_OK;
-  });
+        return CTR_FEED_OK;
+      },
+      [&]() -> int {                                                   // counts -> offsets; are the callers' buffers large enough?
+        bool short_buf = false;
+        for (int64_t k = 0; k < n_cat; ++k) {
+          int64_t* ro = cats[k].row_offsets;
+          ro[0] = 0;
+          for (int64_t b = 0; b < B; ++b) ro[b + 1] += ro[b];
+          cats[k].needed = ro[B];
+          if (ro[B] > cats[k].capacity) short_buf = true;
+        }
+        if (short_buf) return fail(CTR_FEED_ERR_CAPACITY, "ctr_feed_parse_examples: an ids buffer is too small (see `needed`)");
+        return CTR_FEED_OK;
+      },
+      [&](int t, int64_t b0, int64_t) -> int {
+        for (int64_t k = 0; k < n_cat; ++k)
+          if (!local[t][k].empty()) memcpy(cats[k].ids + cats[k].row_offsets[b0], local[t][k].data(), local[t][k].size() * sizeof(int64_t));
+        return CTR_FEED_OK;
+      });
 }
 
 }  // extern "C"
