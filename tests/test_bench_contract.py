@@ -53,3 +53,34 @@ def test_algorithmic_bytes_match_survey_8d():
     fwd, bwd = bench.bytes_per_sample(40, 32)
     assert fwd + bwd == 40 * (8 + 20 * 32) + 8 == 25928             # F*(8 + 20*D) + 8 per sample at config 5
     assert fwd == 40 * (8 + 2 * 32 * 4) + 4 and bwd == 40 * 3 * 32 * 4 + 4
+
+
+def test_cpu_baseline_model_computes_the_same_function_as_the_gpu_arm():
+    """oracle/torch_cpu_model.py (what `--impl reference` and cpu_baseline time) against the NumPy oracle: the FM2 logit, the
+    dense(1) head over the concatenated embeddings, the loss, and the sparse table gradients of one step."""
+    import numpy as np
+    import torch
+    from oracle import layers_np as O, torch_cpu_model as M
+    F, D, rows, B = 5, 8, 50, 64
+    m = M.DeepFMLookupFM2CPU(F, D, rows, seed=3)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, rows, (B, F), generator=g)
+    labels = (torch.rand((B, 1), generator=g) < 0.3).float()
+    logit, fm2 = m.forward(ids)
+    table = np.concatenate([t.detach().numpy() for t in m.tables])
+    off = np.arange(F + 1, dtype=np.int64) * rows
+    e = O.embedding_lookup(table, ids.numpy(), off).astype(np.float64)
+    ref_fm2 = O.fm2_fwd(e)
+    assert np.abs(fm2.detach().numpy() - ref_fm2).max() <= 1e-5 * np.abs(ref_fm2).max()
+    ref_logit = ref_fm2 + e.reshape(B, F * D) @ m.w_deep.detach().numpy().astype(np.float64)
+    assert np.abs(logit.detach().numpy() - ref_logit).max() <= 1e-5 * np.abs(ref_logit).max()
+    loss = m.step(ids, labels)
+    y = labels.numpy().astype(np.float64)
+    want_loss = np.mean(np.maximum(ref_logit, 0) - ref_logit * y + np.log1p(np.exp(-np.abs(ref_logit))))   # TF's stable form
+    assert abs(loss - want_loss) <= 1e-5 * abs(want_loss)
+    d_logit = (1 / (1 + np.exp(-ref_logit)) - y) / B
+    want = O.fm2_bwd(e, d_logit[:, 0]) + d_logit[:, :, None] * m.w_deep.detach().numpy().astype(np.float64).reshape(1, F, D)
+    dense = O.embedding_lookup_bwd_dense(F * rows, ids.numpy(), off, want)
+    got = np.concatenate([t.grad.to_dense().numpy() for t in m.tables])
+    assert m.tables[0].grad.is_sparse                                  # IndexedSlices-like gradients, as in the reference
+    assert np.abs(got - dense).max() <= 1e-5 * np.abs(dense).max()
