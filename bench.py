@@ -297,6 +297,70 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=90.0):
     return sample_B * steps / dt, dt / steps * 1e3, info
 
 
+CPU_LAYER_SAMPLE_B = {"xdeepfm_cfg3": 1024}      # the reference materialises a (B, D, hk*m) outer product: 2 GB at B = 8192
+
+
+def cpu_layer_baseline(name, budget_s=5.0, steps=None, warmup=1):
+    """Forward+backward of the reference-restated lookup + interaction chain of config `name` (oracle/torch_cpu_layers.py: the
+    reference's ops as written, e.g. the materialised CIN outer product) on the host cores; a bounded sample of the workload
+    (about `budget_s` seconds of timed steps, or exactly `steps`).  Returns the cpu_baseline object of that config."""
+    from oracle import torch_cpu_layers as C         # oracle use #2 of bench.py: again only as the measured baseline
+    cls, B_full = C.BUILDERS[name]
+    B = CPU_LAYER_SAMPLE_B.get(name, B_full)
+    cores = usable_cores()
+    model = cls()
+    gen = torch.Generator().manual_seed(1234)
+    batches = [model.make_batch(B, gen) for _ in range(2)]
+    best = None
+    for nt in sorted({min(cores, c) for c in (16, 64)}):             # many-core hosts oversubscribe on these small ops
+        torch.set_num_threads(nt)
+        model.step(*batches[0])
+        t0 = time.perf_counter()
+        model.step(*batches[1])
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    torch.set_num_threads(best[1])
+    for i in range(max(0, warmup - 1)):
+        model.step(*batches[i % 2])
+    n = int(steps) if steps else max(2, min(50, int(budget_s / max(best[0], 1e-4))))
+    t0 = time.perf_counter()
+    for i in range(n):
+        model.step(*batches[i % 2])
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "unit": "samples/s", "ms_per_step": dt / n * 1e3, "cores": best[1], "host_cores_usable": cores,
+            "kind": "port", "B": B, "same_config_as_gpu_arm": bool(B == B_full),
+            "sample": f"B={B} per step x {n} steps (GPU arm: B={B_full}); per-field gathers + the interaction layers as the reference "
+                      f"writes them, forward + backward (torch CPU op-for-op restatement, oracle/torch_cpu_layers.py; TF 1.14 not installable)"}
+
+
+def safe_cpu_layer_baseline(name, budget_s):
+    """The CPU baseline must never cost the GPU line: any failure is reported in place of the number."""
+    try:
+        return cpu_layer_baseline(name, budget_s)
+    except Exception as ex:                                            # noqa: BLE001
+        return {"unavailable": f"{type(ex).__name__}: {str(ex)[:160]}"}
+
+
+LAYER_MODELS = {"dcn_cfg2": "DCN lookup + 3 cross layers", "xdeepfm_cfg3": "xDeepFM lookup + CIN [128,128]",
+                "din_cfg4": "DIN lookup + attention"}
+
+
+def run_reference_arm_layers(args):
+    """`--impl reference --workload dcn_cfg2|xdeepfm_cfg3|din_cfg4`: the CPU restatement of that chain as the reference arm."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cb = cpu_layer_baseline(args.workload, steps=args.steps, warmup=args.warmup)
+    line = {"metric": "ctr_fwd_bwd_samples_per_sec", "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "model": LAYER_MODELS[args.workload], "B": cb["B"], "rows_per_field": 1_000_000,
+                       "ids": "uniform int64"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference_arm(args, cfg):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -580,6 +644,8 @@ def run_deepfm(args, cfg, dd: Dist):
                 line["configs"][name] = layer_workload_measure(dd, name, steps=min(args.steps, 30), warmup=3, brief=True)[0]
                 torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
+            for name in line.get("configs", {}):                           # the reference's CPU path beside each of configs 2-4
+                line["configs"][name]["cpu_baseline"] = safe_cpu_layer_baseline(name, budget_s=4.0)
             sps, ms, info = cpu_reference_run(cfg, steps=4, warmup=1, budget_s=30.0)
             line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "ms_per_step": ms, **info}
         print(json.dumps(line), flush=True)
@@ -817,6 +883,8 @@ def run_layer_workload(args, dd: Dist):
             "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "what": res["what"]}
     if "cuda_graph" in res:
         line["cuda_graph"] = res["cuda_graph"]
+    if dd.world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = safe_cpu_layer_baseline(args.workload, budget_s=15.0)
     print(json.dumps(line), flush=True)
 
 
@@ -846,7 +914,10 @@ def main():
         # BASELINE config 5 names the row-sharded split: it is the headline whenever there is more than one GPU
         args.workload = "deepfm_cfg5_sharded" if (world > 1 and args.impl == "ours") else "deepfm_cfg5"
     if args.impl == "reference":
-        run_reference_arm(args, DEEPFM.get(args.workload, DEEPFM["deepfm_cfg5"]))
+        if args.workload in LAYER_WORKLOADS:
+            run_reference_arm_layers(args)
+        else:
+            run_reference_arm(args, DEEPFM[args.workload])
         return
     dd = Dist()
     if args.workload in DEEPFM:

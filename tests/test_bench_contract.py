@@ -84,3 +84,62 @@ def test_cpu_baseline_model_computes_the_same_function_as_the_gpu_arm():
     got = np.concatenate([t.grad.to_dense().numpy() for t in m.tables])
     assert m.tables[0].grad.is_sparse                                  # IndexedSlices-like gradients, as in the reference
     assert np.abs(got - dense).max() <= 1e-5 * np.abs(dense).max()
+
+
+def test_cpu_layer_baselines_compute_the_references_chains():
+    """oracle/torch_cpu_layers.py (the CPU baselines of configs 2-4) against the NumPy oracle, which itself is pinned by the
+    fixtures executed from the reference's layer files."""
+    import numpy as np
+    import torch
+    from oracle import layers_np as O, torch_cpu_layers as C
+    g = torch.Generator().manual_seed(5)
+    rel = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)          # noqa: E731
+
+    dcn = C.DCNCrossCPU(F=4, D=8, L=3, rows=30, seed=1)
+    ids, gout = dcn.make_batch(17, g)
+    table = np.concatenate([t.detach().numpy() for t in dcn.tables]); off = np.arange(5, dtype=np.int64) * 30
+    x0 = O.embedding_lookup(table, ids.numpy(), off).reshape(17, 32).astype(np.float64)
+    ws = np.stack([w.detach().numpy()[:, 0] for w in dcn.wl]).astype(np.float64); bs = np.stack([b.detach().numpy()[:, 0] for b in dcn.bl]).astype(np.float64)
+    assert rel(dcn.forward(ids).detach().numpy(), O.cross_stack_fwd(x0, ws, bs)[-1]) <= 1e-5
+    dcn.step(ids, gout)
+    dx0, dws, dbs = O.cross_stack_bwd(x0, ws, bs, gout.numpy().astype(np.float64))[:3]
+    assert rel(np.stack([w.grad.numpy()[:, 0] for w in dcn.wl]), dws) <= 1e-5 and dcn.tables[0].grad.is_sparse
+
+    xd = C.XDeepFMCinCPU(F=5, D=4, maps=(6, 3), rows=20, seed=2)
+    ids, gp = xd.make_batch(9, g)
+    table = np.concatenate([t.detach().numpy() for t in xd.tables]); off = np.arange(6, dtype=np.int64) * 20
+    x0 = O.embedding_lookup(table, ids.numpy(), off).astype(np.float64)
+    filts = [f.detach().numpy()[0].astype(np.float64) for f in xd.filters]
+    xs, pooled = O.cin_stack_fwd(x0, filts)
+    got_pooled, got_last = xd.forward(ids)
+    assert rel(got_pooled.detach().numpy(), pooled) <= 1e-5 and rel(got_last.detach().numpy(), xs[-1]) <= 1e-5
+    xd.step(ids, gp)
+    assert all(f.grad is not None and float(f.grad.abs().max()) > 0 for f in xd.filters)
+
+    for soft in (False, True):
+        din = C.DINAttentionCPU(T=7, H=8, rows=25, seed=3, is_softmax=soft)
+        hist, tgt, lens, go = din.make_batch(11, g)
+        lens[0] = 0; hist[0] = -1                                                 # an empty history (din_attention.py:52's case)
+        tab = din.table.detach().numpy().astype(np.float64)
+        keys = tab[np.where(hist.numpy() >= 0, hist.numpy(), 25)]
+        assert np.all(keys[0] == 0)
+        ref = O.din_attention_fwd(tab[tgt.numpy()[:, 0]], keys, lens.numpy(), *[p.detach().numpy().astype(np.float64) for p in din.params()[1:]],
+                                  is_softmax=soft)
+        assert rel(din.forward(hist, tgt, lens).detach().numpy(), ref) <= 1e-5
+        din.step(hist, tgt, lens, go)
+        assert din.table.grad.is_sparse and din.w1.grad is not None
+
+
+def test_reference_arm_for_a_layer_workload_and_the_guard_around_the_cpu_baselines():
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "din_cfg4", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    (line,) = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    d = json.loads(line)
+    assert BASE_KEYS | {"impl", "cpu_baseline"} <= set(d) and d["impl"] == "reference"
+    assert d["config"]["workload"] == "din_cfg4" and d["config"]["B"] == 4096 and d["cpu_baseline"]["same_config_as_gpu_arm"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["steps"] == 2
+    # inside the GPU arm a failing CPU baseline must not cost the line: it is reported in place of the number
+    assert "unavailable" in bench.safe_cpu_layer_baseline("no_such_config", 1.0)
+    assert set(bench.CPU_LAYER_SAMPLE_B) <= set(bench.LAYER_WORKLOADS) == set(bench.LAYER_MODELS)
