@@ -298,3 +298,46 @@ def test_plain_c_caller_of_the_feeder(tmp_path):
     open(path, "wb").write(bad)
     out = subprocess.run([exe, path, str(vdir), "128", *keys], capture_output=True, text=True, timeout=120)
     assert out.returncode == 1 and "crc mismatch" in out.stderr
+
+
+def test_key_order_subsets_duplicates_and_unknown_keys_match_the_python_twin():
+    """The native parser predicts the key of map entry j from entry j of the previous record (one memcmp instead of a hash probe);
+    records whose keys come in a different order, are missing, unknown, empty, or repeated (a proto map keeps the LAST entry, two
+    concatenated Example messages merge) must still parse exactly like the Python twin, in every thread split."""
+    rng = np.random.default_rng(77)
+    cat_keys, dense_keys = ["a", "bb", "userid", "k" * 40, ""], ["f1", "f2"]
+    toks = [b"t%d" % i for i in range(30)]
+    vocab_py = cio.VocabularyFile(toks); vocab_n = native.Vocabulary(toks)
+    recs = []
+    for _ in range(3000):
+        entries = []
+        for k in rng.permutation(cat_keys + dense_keys + ["unknown1", "zz"]).tolist():
+            if rng.random() < 0.3:
+                continue                                                       # key absent from this record
+            if k in dense_keys:
+                entries.append((k, ("float", [float(np.float32(rng.standard_normal()))] if rng.random() < 0.9 else [])))
+            else:
+                n = int(rng.integers(0, 4))
+                entries.append((k, ("bytes", [toks[int(rng.integers(0, 30))] if rng.random() < 0.8 else b"oov" for _ in range(n)])))
+        if entries and rng.random() < 0.3:                                     # the same key twice inside one map: the last one wins
+            k, _ = entries[int(rng.integers(0, len(entries)))]
+            if k not in dense_keys:
+                entries.append((k, ("bytes", [toks[int(rng.integers(0, 30))]])))
+        body = b"".join(cio.example._ld(1, cio.example._ld(1, k.encode()) + cio.example._ld(2, cio.example._enc_feature(kind, v)))
+                        for k, (kind, v) in entries)
+        rec = cio.example._ld(1, body)
+        if rng.random() < 0.2:                                                 # two Example messages back to back: maps merge
+            rec += cio.encode_example({"a": ("bytes", [toks[3]]), "f1": ("float", [2.5])})
+        recs.append(rec)
+    spec = {k: cio.VarLenFeature("bytes") for k in cat_keys} | {k: cio.FixedLenFeature((1,), "float", -1.0) for k in dense_keys}
+    want = cio.parse_example(recs, spec)
+    buf = np.frombuffer(b"".join(recs), np.uint8)
+    lens = np.array([len(r) for r in recs], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    for nt in (1, 2, 5, 16):
+        got = native.parse_examples(buf, offs, lens, {k: vocab_n for k in cat_keys}, {k: (1, -1.0) for k in dense_keys}, num_threads=nt)
+        for k in cat_keys:
+            ids = vocab_py.lookup(want[k][0]) if len(want[k][0]) else np.zeros(0, np.int64)
+            assert np.array_equal(got[k][0], ids) and np.array_equal(got[k][1], want[k][1]), (k, nt)
+        for k in dense_keys:
+            assert np.array_equal(got[k], want[k]), (k, nt)
