@@ -84,3 +84,15 @@ def test_every_compute_entry_rejects_null_pointers_with_an_error_string():
             assert h.ctr_last_error().startswith(name.encode()), (name, h.ctr_last_error())
             checked += 1
     assert checked >= 2 * 45                                          # 48 compute entry points today
+
+
+@pytest.mark.parametrize("header", ["ctr_b200.h", "ctr_feed.h"])
+def test_public_headers_are_plain_c_and_cxx(header):
+    """The drop-in boundary is a C ABI: both headers must compile on their own as strict C99 and as C++17 (extern "C")."""
+    path = os.path.join(ROOT, "include", header)
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", path],
+                ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", path]):
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    src = open(path).read()
+    assert 'extern "C"' in src and "#ifdef __cplusplus" in src and "torch" not in src.lower().replace("pytorch", "")
