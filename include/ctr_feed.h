@@ -27,6 +27,7 @@ extern "C" {
 #define CTR_FEED_ERR_CRC (-5)        /* TFRecord: masked CRC-32C mismatch */
 #define CTR_FEED_ERR_PROTO (-6)      /* malformed protobuf wire data, or a feature of the wrong kind / size for its spec */
 #define CTR_FEED_ERR_CAPACITY (-7)   /* a ragged output buffer is too small: `needed` of the offending key(s) is set */
+#define CTR_FEED_ERR_NOMEM (-8)      /* an allocation failed inside the library (no C++ exception ever crosses this ABI) */
 
 const char* ctr_feed_last_error(void);
 int ctr_feed_version(void);

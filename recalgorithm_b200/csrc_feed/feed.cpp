@@ -8,7 +8,10 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <new>
+#include <system_error>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -399,6 +402,20 @@ struct ShuffleState {
   }
 };
 
+// No C++ exception may cross the C ABI (or leave a std::thread: that is std::terminate): turn them into error codes.
+template <typename Fn>
+int guarded(Fn&& fn) {
+  try {
+    return fn();
+  } catch (const std::bad_alloc&) {
+    return fail(CTR_FEED_ERR_NOMEM, "out of memory");
+  } catch (const std::exception& e) {
+    return fail(CTR_FEED_ERR_NOMEM, "unexpected C++ exception: %s", e.what());
+  } catch (...) {
+    return fail(CTR_FEED_ERR_NOMEM, "unexpected C++ exception");
+  }
+}
+
 template <typename Fn>
 int run_chunks(int64_t B, int nthreads, Fn&& fn) {              // fn(thread, b0, b1) -> rc; first error wins
   std::vector<int> rcs(nthreads, CTR_FEED_OK);
@@ -407,11 +424,16 @@ int run_chunks(int64_t B, int nthreads, Fn&& fn) {              // fn(thread, b0
   const int64_t per = (B + nthreads - 1) / nthreads;
   auto body = [&](int t) {
     const int64_t b0 = t * per, b1 = std::min<int64_t>(B, b0 + per);
-    if (b0 < b1) rcs[t] = fn(t, b0, b1);
+    if (b0 < b1) rcs[t] = guarded([&] { return fn(t, b0, b1); });
     if (rcs[t] != CTR_FEED_OK) msgs[t] = g_err;                 // g_err is thread-local: carry the text to the caller
   };
-  for (int t = 1; t < nthreads; ++t) th.emplace_back(body, t);
+  int created = 1;
+  try {
+    for (int t = 1; t < nthreads; ++t, ++created) th.emplace_back(body, t);
+  } catch (const std::system_error&) {                          // the process ran out of threads: finish the rest here
+  }
   body(0);
+  for (int t = created; t < nthreads; ++t) body(t);
   for (auto& x : th) x.join();
   for (int t = 0; t < nthreads; ++t)
     if (rcs[t] != CTR_FEED_OK) return fail(rcs[t], "%s", msgs[t].c_str());
@@ -421,6 +443,7 @@ int run_chunks(int64_t B, int nthreads, Fn&& fn) {              // fn(thread, b0
 // Two phases over the same partition with ONE set of threads: every thread runs phase1 on its run of records, the last one to
 // arrive runs `middle` (which needs all of phase 1: prefix sums), then every thread runs phase2 on the same run -- unless phase 1
 // or `middle` failed.  Saves the second round of thread creation, which costs as much as the work itself at 32 threads.
+// The threads are created parked; if the process cannot create them all, they are dismissed and the call runs on the caller alone.
 template <typename F1, typename M, typename F2>
 int run_two_phase(int64_t B, int nthreads, F1&& phase1, M&& middle, F2&& phase2) {
   std::vector<int> rcs(nthreads, CTR_FEED_OK);
@@ -430,11 +453,16 @@ int run_two_phase(int64_t B, int nthreads, F1&& phase1, M&& middle, F2&& phase2)
   std::mutex mu;
   std::condition_variable cv;
   int arrived = 0, middle_rc = CTR_FEED_OK;
-  bool released = false;
+  bool released = false, go = false, cancel = false;
   std::string middle_msg;
   auto body = [&](int t) {
+    if (t != 0) {                                               // parked until every thread exists
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return go || cancel; });
+      if (cancel) return;
+    }
     const int64_t b0 = t * per, b1 = std::min<int64_t>(B, b0 + per);
-    if (b0 < b1) rcs[t] = phase1(t, b0, b1);
+    if (b0 < b1) rcs[t] = guarded([&] { return phase1(t, b0, b1); });
     if (rcs[t] != CTR_FEED_OK) msgs[t] = g_err;                 // g_err is thread-local: carry the text to the caller
     {
       std::unique_lock<std::mutex> lk(mu);
@@ -442,7 +470,7 @@ int run_two_phase(int64_t B, int nthreads, F1&& phase1, M&& middle, F2&& phase2)
         bool ok = true;
         for (int i = 0; i < nthreads; ++i) ok = ok && rcs[i] == CTR_FEED_OK;
         if (ok) {
-          middle_rc = middle();
+          middle_rc = guarded([&] { return middle(); });
           if (middle_rc != CTR_FEED_OK) middle_msg = g_err;
         } else {
           middle_rc = CTR_FEED_ERR_ARG;                          // placeholder: phase 2 is skipped, phase 1's error is reported
@@ -454,11 +482,25 @@ int run_two_phase(int64_t B, int nthreads, F1&& phase1, M&& middle, F2&& phase2)
       }
     }
     if (middle_rc == CTR_FEED_OK && b0 < b1) {
-      const int r = phase2(t, b0, b1);
+      const int r = guarded([&] { return phase2(t, b0, b1); });
       if (r != CTR_FEED_OK) { rcs[t] = r; msgs[t] = g_err; }
     }
   };
-  for (int t = 1; t < nthreads; ++t) th.emplace_back(body, t);
+  bool all_created = true;
+  try {
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(body, t);
+  } catch (const std::system_error&) {
+    all_created = false;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    (all_created ? go : cancel) = true;
+  }
+  cv.notify_all();
+  if (!all_created) {
+    for (auto& x : th) x.join();
+    return run_two_phase(B, 1, phase1, middle, phase2);          // nthreads = 1 creates no thread: cannot recurse further
+  }
   body(0);
   for (auto& x : th) x.join();
   for (int t = 0; t < nthreads; ++t)
@@ -519,7 +561,7 @@ int64_t ctr_feed_tfrecord_index(const uint8_t* buf, uint64_t n, int verify_crc, 
   return ctr_feed_tfrecord_index_from(buf, n, 0, verify_crc, 0, offsets, lengths, max_records, consumed);
 }
 
-int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* offsets, const uint64_t* lengths, int64_t count,
+static int ctr_feed_tfrecord_verify_impl(const uint8_t* buf, uint64_t n, const uint64_t* offsets, const uint64_t* lengths, int64_t count,
                              int num_threads) {
   if (count < 0 || (count > 0 && (!buf || !offsets || !lengths)))
     return fail(CTR_FEED_ERR_ARG, "ctr_feed_tfrecord_verify: bad arguments");
@@ -541,7 +583,7 @@ int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* off
   });
 }
 
-int ctr_feed_shuffle_order(int64_t n, int64_t buffer_size, const double* draws, int64_t* out) {
+static int ctr_feed_shuffle_order_impl(int64_t n, int64_t buffer_size, const double* draws, int64_t* out) {
   if (n < 0 || (n > 0 && !out)) return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_order: bad arguments");
   if (buffer_size <= 1 || n <= 1) {
     for (int64_t i = 0; i < n; ++i) out[i] = i;
@@ -553,39 +595,43 @@ int ctr_feed_shuffle_order(int64_t n, int64_t buffer_size, const double* draws, 
   return got == n ? CTR_FEED_OK : (int)got;               // a negative `got` is the error code (draw outside [0,1))
 }
 
-void* ctr_feed_shuffle_create(int64_t buffer_size) { return new ShuffleState(std::max<int64_t>(1, buffer_size)); }
+void* ctr_feed_shuffle_create(int64_t buffer_size) {
+  void* h = nullptr;
+  guarded([&] { h = new ShuffleState(std::max<int64_t>(1, buffer_size)); return CTR_FEED_OK; });
+  return h;
+}
 void ctr_feed_shuffle_destroy(void* shuffle) { delete static_cast<ShuffleState*>(shuffle); }
-int64_t ctr_feed_shuffle_emit(void* shuffle, int64_t n_available, int input_done, const double* draws, int64_t max_out,
+static int64_t ctr_feed_shuffle_emit_impl(void* shuffle, int64_t n_available, int input_done, const double* draws, int64_t max_out,
                               int64_t* out) {
   if (!shuffle || n_available < 0 || max_out < 0 || (max_out > 0 && (!out || !draws)))
     return fail(CTR_FEED_ERR_ARG, "ctr_feed_shuffle_emit: bad arguments");
   return static_cast<ShuffleState*>(shuffle)->emit(n_available, input_done != 0, draws, max_out, out);
 }
 
-void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens) {
+static void* ctr_feed_vocab_create_impl(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens) {
   if (n_tokens < 0 || (n_tokens > 0 && (!offsets || (!blob && offsets[n_tokens] > 0)))) {
     fail(CTR_FEED_ERR_ARG, "ctr_feed_vocab_create: bad arguments");
     return nullptr;
   }
-  Vocab* v = new Vocab();
+  std::unique_ptr<Vocab> v(new Vocab());                   // owned until it is handed to the caller: an exception frees it
   std::vector<std::pair<uint64_t, uint64_t>> spans((size_t)n_tokens);
   if (n_tokens > 0) {
     v->blob.assign(reinterpret_cast<const char*>(blob) + offsets[0], offsets[n_tokens] - offsets[0]);
     for (int64_t i = 0; i < n_tokens; ++i) spans[i] = {offsets[i] - offsets[0], offsets[i + 1] - offsets[i]};
   }
   v->build(spans);
-  return v;
+  return v.release();
 }
 
-void* ctr_feed_vocab_load(const char* path) {
+static void* ctr_feed_vocab_load_impl(const char* path) {
   if (!path) { fail(CTR_FEED_ERR_ARG, "ctr_feed_vocab_load: null path"); return nullptr; }
-  FILE* f = fopen(path, "rb");
+  std::unique_ptr<FILE, int (*)(FILE*)> f(fopen(path, "rb"), fclose);
   if (!f) { fail(CTR_FEED_ERR_IO, "ctr_feed_vocab_load: cannot open %s", path); return nullptr; }
-  Vocab* v = new Vocab();
+  std::unique_ptr<Vocab> v(new Vocab());
   char chunk[1 << 16];
   size_t got;
-  while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) v->blob.append(chunk, got);
-  fclose(f);
+  while ((got = fread(chunk, 1, sizeof(chunk), f.get())) > 0) v->blob.append(chunk, got);
+  f.reset();
   std::vector<std::pair<uint64_t, uint64_t>> spans;
   uint64_t start = 0;
   const uint64_t n = v->blob.size();
@@ -599,7 +645,7 @@ void* ctr_feed_vocab_load(const char* path) {
     }
   }
   v->build(spans);
-  return v;
+  return v.release();
 }
 
 int64_t ctr_feed_vocab_size(const void* vocab) { return vocab ? static_cast<const Vocab*>(vocab)->size : -1; }
@@ -612,7 +658,7 @@ int ctr_feed_vocab_lookup(const void* vocab, const uint8_t* blob, const uint64_t
   return CTR_FEED_OK;
 }
 
-int ctr_feed_parse_examples(const uint8_t* buf, const uint64_t* offsets, const uint64_t* lengths, int64_t B, ctr_feed_cat_t* cats,
+static int ctr_feed_parse_examples_impl(const uint8_t* buf, const uint64_t* offsets, const uint64_t* lengths, int64_t B, ctr_feed_cat_t* cats,
                             int64_t n_cat, ctr_feed_dense_t* dense, int64_t n_dense, int read_feature_lists, int num_threads) {
   if (B < 0 || n_cat < 0 || n_dense < 0 || (B > 0 && (!buf || !offsets || !lengths)) || (n_cat > 0 && !cats) || (n_dense > 0 && !dense))
     return fail(CTR_FEED_ERR_ARG, "ctr_feed_parse_examples: bad arguments");
@@ -680,6 +726,40 @@ int ctr_feed_parse_examples(const uint8_t* buf, const uint64_t* offsets, const u
           if (!local[t][k].empty()) memcpy(cats[k].ids + cats[k].row_offsets[b0], local[t][k].data(), local[t][k].size() * sizeof(int64_t));
         return CTR_FEED_OK;
       });
+}
+
+// ---- the exported entry points of everything above that allocates: exceptions become CTR_FEED_ERR_NOMEM / a null handle
+int ctr_feed_tfrecord_verify(const uint8_t* buf, uint64_t n, const uint64_t* offsets, const uint64_t* lengths, int64_t count,
+                             int num_threads) {
+  return guarded([&] { return ctr_feed_tfrecord_verify_impl(buf, n, offsets, lengths, count, num_threads); });
+}
+
+int ctr_feed_shuffle_order(int64_t n, int64_t buffer_size, const double* draws, int64_t* out) {
+  return guarded([&] { return ctr_feed_shuffle_order_impl(n, buffer_size, draws, out); });
+}
+
+int64_t ctr_feed_shuffle_emit(void* shuffle, int64_t n_available, int input_done, const double* draws, int64_t max_out,
+                              int64_t* out) {
+  int64_t r = 0;
+  const int rc = guarded([&] { r = ctr_feed_shuffle_emit_impl(shuffle, n_available, input_done, draws, max_out, out); return CTR_FEED_OK; });
+  return rc != CTR_FEED_OK ? rc : r;
+}
+
+void* ctr_feed_vocab_create(const uint8_t* blob, const uint64_t* offsets, int64_t n_tokens) {
+  void* h = nullptr;
+  guarded([&] { h = ctr_feed_vocab_create_impl(blob, offsets, n_tokens); return CTR_FEED_OK; });
+  return h;
+}
+
+void* ctr_feed_vocab_load(const char* path) {
+  void* h = nullptr;
+  guarded([&] { h = ctr_feed_vocab_load_impl(path); return CTR_FEED_OK; });
+  return h;
+}
+
+int ctr_feed_parse_examples(const uint8_t* buf, const uint64_t* offsets, const uint64_t* lengths, int64_t B, ctr_feed_cat_t* cats,
+                            int64_t n_cat, ctr_feed_dense_t* dense, int64_t n_dense, int read_feature_lists, int num_threads) {
+  return guarded([&] { return ctr_feed_parse_examples_impl(buf, offsets, lengths, B, cats, n_cat, dense, n_dense, read_feature_lists, num_threads); });
 }
 
 }  // extern "C"

@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTR_FEED_LIB") or os.path.join(os.path.dirname(_HERE), "csrc_feed", "libctr_feed.so")   # override: sanitizer builds
 
-ERR_ARG, ERR_IO, ERR_TRUNCATED, ERR_CRC, ERR_PROTO, ERR_CAPACITY = -1, -2, -4, -5, -6, -7
+ERR_ARG, ERR_IO, ERR_TRUNCATED, ERR_CRC, ERR_PROTO, ERR_CAPACITY, ERR_NOMEM = -1, -2, -4, -5, -6, -7, -8
 
 
 class _Cat(ctypes.Structure):
@@ -90,6 +90,8 @@ def _raise(code: int):
         raise FeedIOError(code)
     if code in (ERR_PROTO, ERR_ARG):
         raise FeedValueError(code)
+    if code == ERR_NOMEM:
+        raise MemoryError(f"libctr_feed: {lib().ctr_feed_last_error().decode('utf-8', 'replace')}")
     raise FeedError(code)
 
 

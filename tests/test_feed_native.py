@@ -341,3 +341,11 @@ def test_key_order_subsets_duplicates_and_unknown_keys_match_the_python_twin():
             assert np.array_equal(got[k][0], ids) and np.array_equal(got[k][1], want[k][1]), (k, nt)
         for k in dense_keys:
             assert np.array_equal(got[k], want[k]), (k, nt)
+
+
+def test_allocation_failures_come_back_as_errors_not_as_crashes():
+    """No C++ exception crosses the C ABI: an allocation the process cannot satisfy is CTR_FEED_ERR_NOMEM (MemoryError here)."""
+    sh = native.Shuffler(1 << 62)
+    with pytest.raises(MemoryError):
+        sh.emit(1 << 60, True, np.zeros(4), 4)                               # a 2^60-slot shuffle buffer
+    assert native.shuffle_order(10, 3, np.linspace(0, 0.9, 10)).size == 10    # the library is still usable afterwards
